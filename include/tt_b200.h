@@ -1,0 +1,232 @@
+/*
+ * tt_b200.h -- C ABI of libtt_b200.so: the B200 (sm_100a) kernels behind the
+ * TorchRec-shaped Python surface of two_tower_recommender_model_b200.
+ *
+ * The reference (/root/reference, 100 % Python) has no FFI of its own: the
+ * boundary it programs against is the torchrec import list at
+ * utils/model_training.py:15-41.  Every entry point below names the upstream
+ * call it stands in for and the reference call site that reaches it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the parameter name starts with h_;
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and
+ *     returns without synchronising; no allocation happens inside -- scratch
+ *     comes from the caller (`ws`, sized by the matching *_workspace_bytes);
+ *   - return value: 0 = ok, negative = tt_status; tt_last_error() returns the
+ *     text of the last failure on the calling thread;
+ *   - integer outputs are bit-exact w.r.t. the oracle; floating-point outputs
+ *     differ from it by summation order only (fp32 paths) or by bf16 operand
+ *     rounding (tcgen05 paths) -- tolerances are stated in tests/.
+ */
+#ifndef TT_B200_H_
+#define TT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TT_ABI_VERSION 1
+#define TT_MAX_FEATURES 32
+
+typedef enum {
+  TT_OK = 0,
+  TT_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, ...)   */
+  TT_ERR_UNSUPPORTED = -2, /* shape outside what the kernels implement          */
+  TT_ERR_WORKSPACE = -3,   /* ws too small                                      */
+  TT_ERR_CUDA = -4         /* a CUDA runtime call failed (see tt_last_error)    */
+} tt_status;
+
+enum { TT_POOL_SUM = 0, TT_POOL_MEAN = 1 };
+/* in-backward optimizers (03_model_training.py:791-795) */
+enum {
+  TT_OPT_DENSE_GRAD = 0,      /* no fused optimizer: grad[row] += g_row into state1 */
+  TT_OPT_ROWWISE_ADAGRAD = 1, /* torchrec RowWiseAdagrad / FBGEMM EXACT_ROWWISE_ADAGRAD */
+  TT_OPT_ROWWISE_ADAM = 2,    /* FBGEMM PARTIAL_ROWWISE_ADAM (BASELINE config 4) */
+  TT_OPT_SGD = 3              /* w -= lr * g_row */
+};
+
+int tt_abi_version(void);
+const char* tt_last_error(void);
+/* Compile-time target of the embedded SASS ("sm_100a"). */
+const char* tt_build_arch(void);
+/* Number of kernels this library has launched in this process (all threads). */
+uint64_t tt_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * KeyedJaggedTensor bookkeeping (bit-exact integer work)
+ * ------------------------------------------------------------------------- */
+
+/* fbgemm::asynchronous_complete_cumsum as used by
+ * KeyedJaggedTensor.from_lengths_sync (utils/model_training.py:57):
+ * offsets[0]=0, offsets[i+1]=offsets[i]+lengths[i].  n may be 0. */
+size_t tt_kjt_offsets_workspace_bytes(int64_t n);
+int tt_kjt_lengths_to_offsets(const int32_t* lengths, int32_t* offsets, int64_t n,
+                              void* ws, size_t ws_bytes, void* stream);
+
+/* Device replacement for transform_to_torchrec_batch
+ * (utils/model_training.py:43-61): ids is [F][B] int64 column-major by feature;
+ * id==0 -> empty bag, else value = id mod num_embeddings[f] (Python modulo:
+ * result has the sign of the divisor), length 1.  Writes lengths [F*B],
+ * offsets [F*B+1] and the compacted values (capacity F*B).  The number of
+ * values is offsets[F*B] (stays on the device). */
+size_t tt_kjt_from_columns_workspace_bytes(int64_t num_features, int64_t batch);
+int tt_kjt_from_columns(const int64_t* ids, const int64_t* num_embeddings /* device [F] */,
+                        int64_t num_features, int64_t batch, int64_t* values,
+                        int32_t* lengths, int32_t* offsets, void* ws, size_t ws_bytes,
+                        void* stream);
+
+/* fbgemm::permute_2D_sparse_data (KeyedJaggedTensor.permute and the KJT
+ * all-to-all inside TrainPipelineSparseDist.progress, utils/model_training.py:305):
+ * lengths is [T][B]; output segment i = input segment permute[i].
+ * in_offsets is the complete cumsum of lengths ([T*B+1]).  out_values must hold
+ * the permuted total (== sum over i of len(segment permute[i])). */
+size_t tt_kjt_permute_workspace_bytes(int64_t num_out_segments, int64_t batch);
+int tt_kjt_permute_2d(const int32_t* permute /* device [T_out] */, int64_t num_out_segments,
+                      int64_t num_in_segments, int64_t batch, const int32_t* lengths,
+                      const int32_t* in_offsets, const int64_t* values,
+                      int32_t* out_lengths, int32_t* out_offsets, int64_t* out_values,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* fbgemm::block_bucketize_sparse_features (TorchRec row-wise input_dist):
+ * block=ceil(R_f/W); bucket=id/block; local=id-bucket*block.  Output is
+ * bucket-major: new_lengths[(w*F+f)*B+b]; order inside a bag is preserved.
+ * unbucketize_permute[p] = output position of input position p (may be NULL). */
+size_t tt_kjt_bucketize_workspace_bytes(int64_t num_features, int64_t batch, int64_t world,
+                                        int64_t num_values);
+int tt_kjt_block_bucketize(const int32_t* lengths, const int32_t* offsets, const int64_t* values,
+                           int64_t num_values, const int64_t* num_rows /* device [F] */,
+                           int64_t num_features, int64_t batch, int64_t world,
+                           int32_t* new_lengths, int32_t* new_offsets, int64_t* new_values,
+                           int64_t* unbucketize_permute, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * EmbeddingBagCollection (utils/model_training.py:101; tables built at
+ * 03_model_training.py:770-784)
+ * ------------------------------------------------------------------------- */
+
+/* One entry per looked-up feature ("slot"), in KeyedTensor column order
+ * (tables in config order, features in feature_names order). */
+typedef struct {
+  int32_t num_slots;
+  int32_t batch_size;     /* B = KJT stride                                     */
+  int32_t num_kjt_keys;   /* F of the incoming KJT                              */
+  int32_t out_stride;     /* row pitch of pooled / grad_out, in floats          */
+  int64_t total_rows;     /* sum of rows over distinct tables (< 2^32 - 1)      */
+  void* weights[TT_MAX_FEATURES];    /* fp32 [R, D] table read by this slot     */
+  void* state0[TT_MAX_FEATURES];     /* adagrad sum [R] / adam v [R] (fp32)      */
+  void* state1[TT_MAX_FEATURES];     /* adam m [R, D] / dense grad [R, D]        */
+  int64_t row_base[TT_MAX_FEATURES]; /* first linear key of this slot's table    */
+  int64_t num_rows[TT_MAX_FEATURES];
+  int32_t dim[TT_MAX_FEATURES];
+  int32_t kjt_index[TT_MAX_FEATURES];   /* position of the feature in the KJT    */
+  int32_t out_col[TT_MAX_FEATURES];     /* first output column                   */
+  int32_t pooling[TT_MAX_FEATURES];     /* TT_POOL_*                             */
+  int32_t slot_of_kjt[TT_MAX_FEATURES]; /* inverse of kjt_index; -1 = unused key */
+} tt_ebc_plan;
+
+/* pooled[b, out_col[s] : +dim[s]] = sum (or mean) over ids of bag (s, b) of
+ * weights[s][id].  Empty bag -> zeros.  values int64, offsets int32 [F*B+1]. */
+int tt_ebc_forward(const tt_ebc_plan* h_plan, const int64_t* values, const int32_t* offsets,
+                   float* pooled, void* stream);
+
+typedef struct {
+  int32_t kind;   /* TT_OPT_* */
+  float lr;
+  float eps;
+  float beta1;
+  float beta2;
+  float bias_correction1; /* 1 - beta1^step (host-computed; adam only) */
+  float bias_correction2; /* 1 - beta2^step                            */
+  float weight_decay;     /* reserved, must be 0 */
+} tt_sparse_optimizer;
+
+/* Fused backward + optimizer (FBGEMM split_embedding_backward_*_exact reached
+ * from loss.backward() inside pipeline.progress, utils/model_training.py:305):
+ * sorts the batch's linearised (table,row) keys, reduces grad_out over every
+ * run of equal keys (a row hit k times gets ONE update with the summed
+ * gradient), and applies the optimizer in place.  No dense [R,D] gradient. */
+size_t tt_ebc_backward_workspace_bytes(int64_t num_values);
+int tt_ebc_backward_fused(const tt_ebc_plan* h_plan, const tt_sparse_optimizer* h_opt,
+                          const int64_t* values, int64_t num_values, const int32_t* offsets,
+                          const float* grad_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Stable LSD radix sort of (key, payload) pairs on keys < 2^key_bits; exposed
+ * for the dedup parity tests.  Result lands in keys_out / vals_out. */
+size_t tt_sort_pairs_workspace_bytes(int64_t n);
+int tt_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
+                      uint32_t* vals_out, int64_t n, int32_t key_bits, void* ws, size_t ws_bytes,
+                      void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Tower MLP (torchrec.modules.mlp.MLP, utils/model_training.py:95-96) --
+ * fp32 CUDA-core path (exact-fp32 parity; any shape)
+ * ------------------------------------------------------------------------- */
+
+/* y[M,N] = act(x[M,K] @ w[N,K]^T + bias[N]); relu!=0 applies max(.,0).
+ * x may be a column window of a wider matrix (ldx = row pitch in floats). */
+int tt_linear_forward_f32(const float* x, int64_t ldx, const float* w, const float* bias, float* y,
+                          int64_t M, int64_t N, int64_t K, int32_t relu, void* stream);
+
+/* Backward of the above.  dz = dy * (y > 0) when relu!=0 (y = saved output).
+ * dx[M,K] (may be NULL; lddx = pitch) = dz @ w;  dw[N,K] = dz^T @ x;
+ * db[N] = column sums of dz.  Deterministic (split partials + ordered reduce). */
+size_t tt_linear_backward_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int tt_linear_backward_f32(const float* x, int64_t ldx, const float* w, const float* y,
+                           const float* dy, float* dx, int64_t lddx, float* dw, float* db,
+                           int64_t M, int64_t N, int64_t K, int32_t relu, void* ws,
+                           size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Losses (utils/model_training.py:136-140 and the in-batch-softmax extension)
+ * ------------------------------------------------------------------------- */
+
+/* logits[b] = sum_d q[b,d]*c[b,d]; loss = mean BCEWithLogits(logits, labels).
+ * Also writes dq, dc = d(loss)/d(q,c) when non-NULL (forward+backward fused).
+ * labels are int32 (Batch.labels, utils/model_training.py:62). */
+int tt_dot_bce(const float* q, const float* c, const int32_t* labels, int64_t B, int64_t d,
+               float* logits, float* loss /* [1] */, float* dq, float* dc, float grad_scale,
+               void* ws, size_t ws_bytes, void* stream);
+size_t tt_dot_bce_workspace_bytes(int64_t B);
+
+/* In-batch sampled softmax: S = q c^T * inv_temperature, loss = mean_b(lse_b - S_bb).
+ * fp32 CUDA-core path; S is never written to memory.  Outputs lse[B], diag[B], loss[1]. */
+size_t tt_inbatch_softmax_workspace_bytes(int64_t B);
+int tt_inbatch_softmax_forward_f32(const float* q, const float* c, int64_t B, int64_t d,
+                                   float inv_temperature, float* lse, float* diag, float* loss,
+                                   void* ws, size_t ws_bytes, void* stream);
+/* dq[b] = scale * (sum_j P_bj c_j - c_b), dc[j] = scale * (sum_b P_bj q_b - q_j),
+ * P_bj = exp(S_bj - lse_b), scale = grad_scale * inv_temperature / B. */
+int tt_inbatch_softmax_backward_f32(const float* q, const float* c, const float* lse, int64_t B,
+                                    int64_t d, float inv_temperature, float grad_scale, float* dq,
+                                    float* dc, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Dense optimizer: torch.optim.Adam defaults (03_model_training.py:826-829),
+ * one launch over a flat parameter/grad/state buffer.
+ * ------------------------------------------------------------------------- */
+int tt_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, float bias_correction1,
+                 float bias_correction2, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Retrieval (04_evaluate_retrieval.py:134-141: similarity_search, k = 100)
+ * ------------------------------------------------------------------------- */
+
+/* Exact dot-product top-k: for each query the k best items by descending score,
+ * ties -> lower item index.  fp32 CUDA-core scoring, per-block top-k fused into
+ * the scoring kernel, then a merge.  item_index_base is added to every index
+ * (corpus shards).  k <= 128. */
+size_t tt_topk_workspace_bytes(int64_t num_queries, int64_t num_items, int64_t k);
+int tt_score_topk_f32(const float* queries, const float* items, int64_t num_queries,
+                      int64_t num_items, int64_t d, int64_t k, int64_t item_index_base,
+                      float* out_scores, int64_t* out_indices, void* ws, size_t ws_bytes,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TT_B200_H_ */

@@ -1,0 +1,161 @@
+"""Oracle: the whole unsharded two-tower train step on the CPU, built from stock
+``torch`` ops -- per-table ``nn.EmbeddingBag(include_last_offset=True)`` +
+``relu(Linear)`` towers + loss + row-wise Adagrad applied to the dense embedding
+gradient + ``torch.optim.Adam`` on the tower parameters.  This is the set of
+ops unsharded TorchRec runs on CPU for
+/root/reference/03_model_training.py:770-829 with ``device="cpu"`` and
+/root/reference/utils/model_training.py:79-143, so it doubles as the CPU
+baseline that ``bench.py`` times.  Test infrastructure only.
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from .ebc import TableSpec, output_layout, rowwise_adagrad_dense, rowwise_adam_sparse
+from .kjt import lengths_to_offsets
+
+
+class OracleTwoTower(nn.Module):
+    def __init__(
+        self, tables: Sequence[TableSpec], layer_sizes: Sequence[int],
+        loss: str = "bce", sparse_optimizer: str = "rowwise_adagrad",
+        sparse_lr: float = 1e-2, sparse_eps: Optional[float] = None,
+        dense_lr: float = 1e-2, temperature: float = 1.0,
+        query_features: Optional[List[str]] = None,
+        candidate_features: Optional[List[str]] = None, seed: int = 0,
+    ) -> None:
+        super().__init__()
+        self.tables = list(tables)
+        self.loss_kind = loss
+        self.sparse_optimizer = sparse_optimizer
+        self.sparse_lr = sparse_lr
+        self.sparse_eps = sparse_eps if sparse_eps is not None else (1e-10 if sparse_optimizer == "rowwise_adagrad" else 1e-8)
+        self.temperature = temperature
+        if query_features is None:
+            # utils/model_training.py:88-93 -- exactly two tables, same dim
+            assert len(self.tables) == 2, "Expected two EmbeddingBags in the two tower model"
+            assert self.tables[0].embedding_dim == self.tables[1].embedding_dim
+            query_features = list(self.tables[0].feature_names)
+            candidate_features = list(self.tables[1].feature_names)
+        self.query_features = query_features
+        self.candidate_features = candidate_features
+        g = torch.Generator().manual_seed(seed)
+        self.embedding_bags = nn.ModuleDict()
+        for t in self.tables:
+            eb = nn.EmbeddingBag(t.num_embeddings, t.embedding_dim, mode=t.pooling, include_last_offset=True)
+            bound = (1.0 / t.num_embeddings) ** 0.5  # TorchRec EmbeddingBagConfig default init
+            with torch.no_grad():
+                eb.weight.copy_((torch.rand(eb.weight.shape, generator=g) * 2 - 1) * bound)
+            self.embedding_bags[t.name] = eb
+        keys, dims = output_layout(self.tables)
+        dim_of = dict(zip(keys, dims))
+        q_in = sum(dim_of[f] for f in self.query_features)
+        c_in = sum(dim_of[f] for f in self.candidate_features)
+        self.query_proj = self._make_mlp(q_in, layer_sizes, g)
+        self.candidate_proj = self._make_mlp(c_in, layer_sizes, g)
+        self.sparse_state: Dict[str, Dict[str, torch.Tensor]] = {}
+        for t in self.tables:
+            st = {"sum": torch.zeros(t.num_embeddings)}
+            if sparse_optimizer == "rowwise_adam":
+                st = {"m": torch.zeros(t.num_embeddings, t.embedding_dim), "v": torch.zeros(t.num_embeddings)}
+            self.sparse_state[t.name] = st
+        self.step_count = 0
+        dense_params = list(self.query_proj.parameters()) + list(self.candidate_proj.parameters())
+        self.dense_opt = torch.optim.Adam(dense_params, lr=dense_lr)
+
+    @staticmethod
+    def _make_mlp(in_size: int, layer_sizes: Sequence[int], g: torch.Generator) -> nn.ModuleList:
+        layers = nn.ModuleList()
+        for out in layer_sizes:
+            lin = nn.Linear(in_size, out)
+            bound = 1.0 / in_size ** 0.5
+            with torch.no_grad():
+                lin.weight.copy_((torch.rand(lin.weight.shape, generator=g) * 2 - 1) * bound)
+                lin.bias.copy_((torch.rand(lin.bias.shape, generator=g) * 2 - 1) * bound)
+            layers.append(lin)
+            in_size = out
+        return layers
+
+    # ---- TorchRec-named state dict (N03:1030,1143: ``two_tower.`` prefix stripped by the caller)
+    def torchrec_state_dict(self) -> Dict[str, torch.Tensor]:
+        sd = {}
+        for t in self.tables:
+            sd[f"ebc.embedding_bags.{t.name}.weight"] = self.embedding_bags[t.name].weight.detach().clone()
+        for tower, mods in (("query_proj", self.query_proj), ("candidate_proj", self.candidate_proj)):
+            for i, lin in enumerate(mods):
+                sd[f"{tower}._mlp.{i}._linear.weight"] = lin.weight.detach().clone()
+                sd[f"{tower}._mlp.{i}._linear.bias"] = lin.bias.detach().clone()
+        return sd
+
+    def load_torchrec_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        with torch.no_grad():
+            for t in self.tables:
+                self.embedding_bags[t.name].weight.copy_(sd[f"ebc.embedding_bags.{t.name}.weight"])
+            for tower, mods in (("query_proj", self.query_proj), ("candidate_proj", self.candidate_proj)):
+                for i, lin in enumerate(mods):
+                    lin.weight.copy_(sd[f"{tower}._mlp.{i}._linear.weight"])
+                    lin.bias.copy_(sd[f"{tower}._mlp.{i}._linear.bias"])
+
+    # ---- forward
+    def pooled(self, keys: Sequence[str], values: torch.Tensor, lengths: torch.Tensor) -> Dict[str, torch.Tensor]:
+        Fk = len(keys)
+        B = lengths.numel() // Fk
+        offsets = lengths_to_offsets(lengths).to(torch.int64)
+        out = {}
+        for t in self.tables:
+            for feat in t.feature_names:
+                f = list(keys).index(feat)
+                s, e = int(offsets[f * B]), int(offsets[(f + 1) * B])
+                out[feat] = self.embedding_bags[t.name](values[s:e], offsets[f * B:(f + 1) * B + 1] - s)
+        return out
+
+    def towers(self, pooled: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+        q = torch.cat([pooled[f] for f in self.query_features], dim=1)
+        c = torch.cat([pooled[f] for f in self.candidate_features], dim=1)
+        for lin in self.query_proj:
+            q = torch.relu(lin(q))
+        for lin in self.candidate_proj:
+            c = torch.relu(lin(c))
+        return q, c
+
+    def forward(self, keys, values, lengths):
+        return self.towers(self.pooled(keys, values, lengths))
+
+    def loss(self, q: torch.Tensor, c: torch.Tensor, labels: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.loss_kind == "bce":
+            logits = (q * c).sum(dim=1).squeeze()
+            return F.binary_cross_entropy_with_logits(logits, labels.float()), logits
+        s = (q @ c.t()) / self.temperature
+        return F.cross_entropy(s, torch.arange(q.shape[0])), s.diagonal()
+
+    # ---- one train step: fwd, bwd, row-wise sparse update "in backward", dense Adam
+    def train_step(self, keys, values, lengths, labels) -> Tuple[torch.Tensor, torch.Tensor]:
+        self.dense_opt.zero_grad(set_to_none=True)
+        for eb in self.embedding_bags.values():
+            eb.weight.grad = None
+        q, c = self.forward(keys, values, lengths)
+        loss, logits = self.loss(q, c, labels)
+        loss.backward()
+        self.step_count += 1
+        Fk = len(keys)
+        B = lengths.numel() // Fk
+        offsets = lengths_to_offsets(lengths).to(torch.int64)
+        with torch.no_grad():
+            for t in self.tables:
+                w = self.embedding_bags[t.name].weight
+                g = w.grad
+                if g is None:
+                    continue
+                if self.sparse_optimizer == "rowwise_adagrad":
+                    rowwise_adagrad_dense(w, self.sparse_state[t.name]["sum"], g, lr=self.sparse_lr, eps=self.sparse_eps)
+                else:
+                    ids = torch.cat([values[int(offsets[list(keys).index(f) * B]):int(offsets[(list(keys).index(f) + 1) * B])]
+                                     for f in t.feature_names])
+                    rows = torch.unique(ids, sorted=True)
+                    st = self.sparse_state[t.name]
+                    rowwise_adam_sparse(w, st["m"], st["v"], rows, g[rows], self.step_count, lr=self.sparse_lr, eps=self.sparse_eps)
+                w.grad = None
+        self.dense_opt.step()
+        return loss.detach(), logits.detach()

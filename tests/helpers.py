@@ -1,0 +1,27 @@
+"""Shared builders for the parity tests: the same seeded inputs go to the oracle
+(CPU) and to the CUDA path."""
+from typing import List, Sequence
+
+import torch
+
+from oracle.ebc import TableSpec
+
+
+def random_kjt(keys: Sequence[str], rows: Sequence[int], batch: int, max_len: int, seed: int,
+               empty_frac: float = 0.2, dup_pool: int = 0):
+    """Returns (values int64, lengths int32).  ``dup_pool`` > 0 draws ids from a small
+    pool so many bags hit the same rows (dedup / summed-gradient case)."""
+    g = torch.Generator().manual_seed(seed)
+    lens, vals = [], []
+    for R in rows:
+        ln = torch.randint(0, max_len + 1, (batch,), generator=g)
+        ln[torch.rand(batch, generator=g) < empty_frac] = 0
+        n = int(ln.sum())
+        hi = min(R, dup_pool) if dup_pool else R
+        vals.append(torch.randint(0, hi, (n,), generator=g))
+        lens.append(ln)
+    return torch.cat(vals).to(torch.int64), torch.cat(lens).to(torch.int32)
+
+
+def make_tables(dims: Sequence[int], rows: Sequence[int], pooling: Sequence[str]) -> List[TableSpec]:
+    return [TableSpec(f"t_f{i}", rows[i], dims[i], [f"f{i}"], pooling[i]) for i in range(len(dims))]

@@ -1,0 +1,92 @@
+"""CUDA integer ops vs the oracle: bit-exact."""
+import pytest
+import torch
+
+import oracle
+from oracle.kjt import block_bucketize_vectorized
+from helpers import random_kjt
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 1023, 1024, 4097, 32768, 32769, 300000, 2_000_003])
+def test_lengths_to_offsets(cuda, n):
+    import two_tower_recommender_model_b200 as tt
+    g = torch.Generator().manual_seed(n)
+    lengths = torch.randint(0, 21, (n,), generator=g, dtype=torch.int32)
+    want = oracle.lengths_to_offsets(lengths)
+    kjt = tt.KeyedJaggedTensor(keys=["a"], values=torch.zeros(int(lengths.sum()), dtype=torch.int64, device=cuda),
+                               lengths=lengths.to(cuda))
+    got = kjt.offsets()
+    assert got.dtype == torch.int32 and torch.equal(got.cpu(), want)
+
+
+def test_from_id_columns_matches_reference_loop(cuda):
+    import two_tower_recommender_model_b200 as tt
+    g = torch.Generator().manual_seed(7)
+    B = 5000
+    cols = {"user_id": torch.randint(-50, 400, (B,), generator=g), "product_id": torch.randint(0, 3, (B,), generator=g) * 977,
+            "label": torch.randint(0, 2, (B,), generator=g)}
+    emb = [193, 9740]
+    v, l, _ = oracle.transform_to_torchrec_batch({k: t.tolist() for k, t in cols.items()}, ["user_id", "product_id"], emb)
+    ids = torch.stack([cols["user_id"], cols["product_id"]]).to(cuda)
+    kjt = tt.KeyedJaggedTensor.from_id_columns(["user_id", "product_id"], ids, torch.tensor(emb))
+    assert torch.equal(kjt.lengths().cpu(), l)
+    n = int(kjt.offsets()[-1])
+    assert n == v.numel() and torch.equal(kjt.values()[:n].cpu(), v)
+
+
+@pytest.mark.parametrize("F,B,L,perm", [(3, 7, 3, [2, 0, 1]), (4, 1000, 5, [3, 3, 0]), (2, 65536, 1, [1, 0]), (5, 33, 0, [4, 1])])
+def test_permute_2d(cuda, F, B, L, perm):
+    import two_tower_recommender_model_b200 as tt
+    keys = [f"f{i}" for i in range(F)]
+    v, l = random_kjt(keys, [1000] * F, B, L, seed=F * 131 + B)
+    ol, ov, _ = oracle.permute_2d_sparse_data(perm, l.view(F, B), v)
+    kjt = tt.KeyedJaggedTensor.from_lengths_sync(keys, v.to(cuda), l.to(cuda))
+    out = kjt.permute(perm)
+    assert out.keys() == [keys[i] for i in perm]
+    assert torch.equal(out.lengths().cpu(), ol.reshape(-1)) and torch.equal(out.values().cpu(), ov)
+    assert torch.equal(out.offsets().cpu(), oracle.lengths_to_offsets(ol.reshape(-1)))
+    # permute o inverse permute = identity (for true permutations)
+    if sorted(perm) == list(range(F)):
+        inv = [perm.index(i) for i in range(F)]
+        back = out.permute(inv)
+        assert torch.equal(back.values().cpu(), v) and torch.equal(back.lengths().cpu(), l)
+
+
+@pytest.mark.parametrize("F,B,L,W,rows", [(1, 9, 4, 2, [10]), (3, 257, 6, 4, [1000, 7, 123457]), (2, 4096, 20, 8, [100_000_000, 50]), (2, 50, 0, 3, [5, 5])])
+def test_block_bucketize(cuda, F, B, L, W, rows):
+    from two_tower_recommender_model_b200.functional import block_bucketize
+    keys = [f"f{i}" for i in range(F)]
+    v, l = random_kjt(keys, rows, B, L, seed=W * 17 + B)
+    want = block_bucketize_vectorized(l, v, rows, W, B)
+    if v.numel() <= 5000:
+        loop = oracle.block_bucketize_sparse_features(l, v, rows, W, B)
+        assert all(torch.equal(a, b) for a, b in zip(want, loop))
+    off = oracle.lengths_to_offsets(l)
+    nl, no, nv, unb = block_bucketize(l.to(cuda), off.to(cuda), v.to(cuda), torch.tensor(rows), F, B, W)
+    assert torch.equal(nl.cpu(), want[0]) and torch.equal(nv.cpu(), want[1]) and torch.equal(unb.cpu(), want[2])
+    assert torch.equal(no.cpu(), oracle.lengths_to_offsets(want[0]))
+    # un-bucketise: local id + bucket*block == original id
+    blocks = torch.tensor([-(-r // W) for r in rows])
+    bag = torch.repeat_interleave(torch.arange(W * F * B), want[0].long())
+    w_of = bag // (F * B)
+    f_of = (bag // B) % F
+    assert torch.equal((nv.cpu() + w_of * blocks[f_of])[unb.cpu()], v)
+
+
+@pytest.mark.parametrize("n,bits", [(1, 8), (31, 5), (2048, 16), (2049, 25), (131072, 25), (1_300_000, 28), (70000, 32)])
+def test_radix_sort_stable(cuda, n, bits):
+    from two_tower_recommender_model_b200.functional import sort_pairs
+    g = torch.Generator().manual_seed(n)
+    hi = (1 << bits) - 1 if bits < 32 else (1 << 31) - 1
+    keys = torch.randint(0, min(hi, max(n // 3, 1)) + 1, (n,), generator=g, dtype=torch.int64)
+    if bits == 32:
+        keys[::3] += (1 << 31)  # exercise the top bit
+    vals = torch.arange(n, dtype=torch.int64)
+    order = torch.sort(keys, stable=True).indices
+    k32 = (keys & 0xFFFFFFFF).to(torch.int64)
+    k_dev = torch.where(k32 >= (1 << 31), k32 - (1 << 32), k32).to(torch.int32).to(cuda)
+    ko, vo = sort_pairs(k_dev, vals.to(torch.int32).to(cuda), bits)
+    assert torch.equal(vo.cpu().long(), order)
+    assert torch.equal((ko.cpu().long() & 0xFFFFFFFF), keys[order])

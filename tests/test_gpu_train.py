@@ -1,0 +1,189 @@
+"""End-to-end: N train steps of the CUDA two-tower vs the CPU oracle on the same
+seeded batches, through the reference-facing API (EmbeddingBagCollection on meta,
+apply_optimizer_in_backward, DistributedModelParallel, KeyedOptimizerWrapper,
+TrainPipelineSparseDist.progress).  fp32: loss rtol 1e-4, weights rtol 1e-4 atol 1e-5."""
+import itertools
+import os
+
+import pytest
+import torch
+from torch.distributed.optim import _apply_optimizer_in_backward as apply_optimizer_in_backward
+
+import oracle
+from oracle.ebc import TableSpec
+
+pytestmark = pytest.mark.gpu
+
+CAT = ["user_id", "product_id"]
+
+
+def make_batches(n, B, emb, seed):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        out.append({"user_id": torch.randint(0, emb[0] * 2, (B,), generator=g).tolist(),
+                    "product_id": torch.randint(0, emb[1] * 2, (B,), generator=g).tolist(),
+                    "label": torch.randint(0, 2, (B,), generator=g).tolist()})
+    return out
+
+
+def build_models(cuda, emb, dim, layers, loss, sparse_opt, lr):
+    import two_tower_recommender_model_b200 as tt
+    specs = [TableSpec(f"t_{c}", emb[i], dim, [c]) for i, c in enumerate(CAT)]
+    ref = oracle.OracleTwoTower(specs, layers, loss="bce" if loss == "bce" else "softmax",
+                                sparse_optimizer=sparse_opt, sparse_lr=lr, dense_lr=lr, seed=3)
+    # --- the reference's main() (03_model_training.py:770-829), with our names
+    eb_configs = [tt.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=dim, num_embeddings=emb[i], feature_names=[c])
+                  for i, c in enumerate(CAT)]
+    ebc = tt.EmbeddingBagCollection(tables=eb_configs, device=torch.device("meta"))
+    two_tower = tt.TwoTower(embedding_bag_collection=ebc, layer_sizes=layers, device=cuda)
+    task = tt.TwoTowerTrainTask(two_tower, loss=loss)
+    cls = tt.RowWiseAdagrad if sparse_opt == "rowwise_adagrad" else tt.RowWiseAdam
+    apply_optimizer_in_backward(cls, task.two_tower.ebc.parameters(), {"lr": lr})
+    model = tt.DistributedModelParallel(module=task, device=cuda)
+    model.module.two_tower.load_state_dict(ref.torchrec_state_dict())
+    opt = tt.KeyedOptimizerWrapper(dict(model.named_parameters()), lambda params: torch.optim.Adam(params, lr=lr))
+    return ref, model, opt
+
+
+@pytest.mark.parametrize("loss,sparse_opt", [("bce", "rowwise_adagrad"), ("in_batch_softmax", "rowwise_adagrad"),
+                                             ("bce", "rowwise_adam"), ("in_batch_softmax", "rowwise_adam")])
+def test_train_steps_match_oracle(cuda, loss, sparse_opt):
+    import two_tower_recommender_model_b200 as tt
+    emb, dim, layers, B, lr = [193, 9740], 64, [128, 64], 1024, 0.01  # workshop/02-mosaic-model-training.py:135-136 sizes
+    ref, model, opt = build_models(cuda, emb, dim, layers, loss, sparse_opt, lr)
+    batches = make_batches(6, B, emb, seed=11)
+
+    def transform(b):
+        v, l, y = oracle.transform_to_torchrec_batch(b, CAT, emb)   # the reference's own host transform
+        return tt.Batch(dense_features=torch.zeros(1), sparse_features=tt.KeyedJaggedTensor.from_lengths_sync(CAT, v, l), labels=y)
+
+    pipeline = tt.TrainPipelineSparseDist(model, opt, cuda)
+    assert pipeline._model is model and pipeline._device == cuda and pipeline._optimizer.param_groups[0]["lr"] == lr
+    pipeline._model.train()
+    it = map(transform, iter(batches))
+    n = 0
+    for b in batches:
+        v, l, y = oracle.transform_to_torchrec_batch(b, CAT, emb)
+        loss_r, logits_r = ref.train_step(CAT, v, l, y)
+        loss_d, logits_d, labels_d = pipeline.progress(it)
+        torch.testing.assert_close(loss_d.cpu(), loss_r, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(logits_d.cpu().reshape(-1), logits_r.reshape(-1), rtol=1e-3, atol=1e-5)
+        assert torch.equal(labels_d.cpu(), y)
+        n += 1
+    with pytest.raises(StopIteration):
+        pipeline.progress(it)
+    assert n == 6
+    want = ref.torchrec_state_dict()
+    got = model.module.two_tower.state_dict()
+    assert set(got.keys()) == set(want.keys())
+    for k in want:
+        torch.testing.assert_close(got[k].cpu(), want[k], rtol=1e-4, atol=1e-5, msg=lambda m: f"{k}: {m}")
+    # eval mode: no update
+    pipeline._model.eval()
+    before = {k: v.clone() for k, v in model.module.two_tower.state_dict().items()}
+    out = pipeline.progress(map(transform, iter(batches[:1])))
+    assert out[0].ndim == 0
+    for k, v in model.module.two_tower.state_dict().items():
+        assert torch.equal(v, before[k])
+
+
+def test_multi_feature_towers_mean_pooling(cuda):
+    """BASELINE config 3 shape in miniature: mean-pooled history bag + 3 candidate features."""
+    import two_tower_recommender_model_b200 as tt
+    from helpers import random_kjt
+    specs = [TableSpec("t_hist", 500, 32, ["hist"], "mean"), TableSpec("t_product", 400, 32, ["product"]),
+             TableSpec("t_aisle", 134, 32, ["aisle"]), TableSpec("t_department", 21, 32, ["department"])]
+    keys = ["hist", "product", "aisle", "department"]
+    ref = oracle.OracleTwoTower(specs, [64, 32], loss="softmax", sparse_lr=0.02, dense_lr=0.02,
+                                query_features=["hist"], candidate_features=["product", "aisle", "department"], seed=5)
+    cfgs = [tt.EmbeddingBagConfig(name=s.name, embedding_dim=32, num_embeddings=s.num_embeddings, feature_names=list(s.feature_names),
+                                  pooling=tt.PoolingType.MEAN if s.pooling == "mean" else tt.PoolingType.SUM) for s in specs]
+    ebc = tt.EmbeddingBagCollection(tables=cfgs, device=cuda)
+    tower = tt.TwoTower(ebc, [64, 32], device=cuda, query_features=["hist"], candidate_features=["product", "aisle", "department"])
+    task = tt.TwoTowerTrainTask(tower, loss="in_batch_softmax")
+    apply_optimizer_in_backward(tt.RowWiseAdagrad, ebc.parameters(), {"lr": 0.02})
+    tower.load_state_dict(ref.torchrec_state_dict())
+    opt = torch.optim.Adam([p for n, p in task.named_parameters() if "embedding_bags" not in n], lr=0.02)
+    B = 256
+    for step in range(4):
+        g = torch.Generator().manual_seed(step)
+        lens = torch.cat([torch.randint(0, 21, (B,), generator=g), torch.ones(3 * B, dtype=torch.int64)]).to(torch.int32)
+        vals = torch.cat([torch.randint(0, 500, (int(lens[:B].sum()),), generator=g), torch.randint(0, 400, (B,), generator=g),
+                          torch.randint(0, 134, (B,), generator=g), torch.randint(0, 21, (B,), generator=g)])
+        y = torch.zeros(B, dtype=torch.int32)
+        loss_r, _ = ref.train_step(keys, vals, lens, y)
+        opt.zero_grad()
+        batch = tt.Batch(torch.zeros(1), tt.KeyedJaggedTensor.from_lengths_sync(keys, vals, lens), y).to(cuda)
+        loss, _ = task(batch)
+        loss.backward()
+        opt.step()
+        torch.testing.assert_close(loss.detach().cpu(), loss_r, rtol=1e-4, atol=1e-6)
+    want = ref.torchrec_state_dict()
+    for k, v in tower.state_dict().items():
+        torch.testing.assert_close(v.cpu(), want[k], rtol=1e-4, atol=1e-5, msg=lambda m: f"{k}: {m}")
+
+
+def test_corpus_embedding_and_retrieval(cuda):
+    """03_model_training.py:1056-1122 + 04_evaluate_retrieval.py:134-141 on the device."""
+    import two_tower_recommender_model_b200 as tt
+    emb, dim, layers = [300, 1200], 32, [64, 32]
+    specs = [TableSpec(f"t_{c}", emb[i], dim, [c]) for i, c in enumerate(CAT)]
+    ref = oracle.OracleTwoTower(specs, layers, seed=9)
+    ebc = tt.EmbeddingBagCollection(tables=[tt.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=dim, num_embeddings=emb[i], feature_names=[c])
+                                            for i, c in enumerate(CAT)], device=cuda)
+    model = tt.TwoTower(ebc, layers, device=cuda)
+    model.load_state_dict(ref.torchrec_state_dict())
+    model.eval()
+    kjt = tt.create_keyed_jagged_tensor(emb[1], CAT, "product_id", device=cuda)
+    assert kjt.length_per_key() == [0, emb[1]] and kjt.keys() == CAT
+    items = tt.process_embeddings(model, kjt, "product_id")
+    users = tt.embed_corpus(model, CAT, "user_id", emb[0], cuda, chunk=128)
+    with torch.no_grad():
+        w_items = ref.embedding_bags["t_product_id"].weight
+        w_users = ref.embedding_bags["t_user_id"].weight
+        it_r, us_r = w_items, w_users
+        for lin in ref.candidate_proj:
+            it_r = torch.relu(lin(it_r))
+        for lin in ref.query_proj:
+            us_r = torch.relu(lin(us_r))
+    torch.testing.assert_close(items.cpu(), it_r, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(users.cpu(), us_r, rtol=1e-5, atol=1e-5)
+    index = tt.BruteForceIndex(items)
+    scores, ids = index.search(users, num_results=100)
+    ws, wi = oracle.exact_topk(users.cpu(), items.cpu(), 100)
+    torch.testing.assert_close(scores.cpu(), ws, rtol=1e-5, atol=1e-5)
+    recall = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(ids.cpu(), wi)) / wi.numel()
+    assert recall >= 0.999
+    resp = index.similarity_search(query_vector=users[0].tolist(), columns=["product_id"], num_results=100)
+    assert [c["name"] for c in resp["manifest"]["columns"]] == ["product_id", "score"] and len(resp["result"]["data_array"]) == 100
+    targets = [wi[i, :10].tolist() for i in range(emb[0])]
+    m_dev = tt.retrieval_metrics(ids, targets, 100)
+    m_ref = oracle.retrieval_metrics(ids.cpu().tolist(), targets, 100)
+    for k in m_ref:
+        assert abs(m_dev[k] - m_ref[k]) < 1e-5
+
+
+def test_reference_utils_file_imports_through_shim(cuda):
+    """install_torchrec_shim() makes every torchrec name utils/model_training.py:20-41 imports resolve."""
+    import importlib
+    import two_tower_recommender_model_b200 as tt
+    tt.install_torchrec_shim()
+    for mod, names in {
+        "torchrec.distributed": ["TrainPipelineSparseDist"],
+        "torchrec.distributed.model_parallel": ["DistributedModelParallel", "get_default_sharders"],
+        "torchrec.inference.state_dict_transform": ["state_dict_gather", "state_dict_to_device"],
+        "torchrec.modules.embedding_configs": ["EmbeddingBagConfig"],
+        "torchrec.modules.embedding_modules": ["EmbeddingBagCollection"],
+        "torchrec.optim.keyed": ["KeyedOptimizerWrapper"],
+        "torchrec.optim.rowwise_adagrad": ["RowWiseAdagrad"],
+        "torchrec.sparse.jagged_tensor": ["KeyedJaggedTensor"],
+        "torchrec.datasets.utils": ["Batch"],
+        "torchrec.modules.mlp": ["MLP"],
+        "torchrec.distributed.comm": ["get_local_size"],
+        "torchrec.distributed.planner": ["EmbeddingShardingPlanner", "Topology"],
+        "torchrec.distributed.planner.storage_reservations": ["HeuristicalStorageReservation"],
+    }.items():
+        m = importlib.import_module(mod)
+        for n in names:
+            assert hasattr(m, n), f"{mod}.{n}"

@@ -1,0 +1,501 @@
+// EmbeddingBagCollection kernels (HBM-bound gather / scatter work; no tensor cores).
+//
+//   forward : table-batched jagged gather + sum/mean pooling.  One CTA owns a
+//             tile of kBagsPerCta consecutive bags of one feature; the tile's
+//             offsets are staged in shared memory; a group of G lanes owns a bag
+//             and reads each row with 128-bit loads, UB bags in flight per group.
+//   backward: linearised (table,row) keys -> stable radix sort -> every run of
+//             equal keys is reduced by the group that sits on the run's head and
+//             the row-wise optimizer is applied in place (no dense gradient, no
+//             atomics, deterministic summation order).
+#include "common.cuh"
+
+namespace tt {
+
+constexpr int kBagsPerCta = 128;
+constexpr int kEbcThreads = 256;
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+  float4 v;
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void load_stream(const float* p) { v = ld_stream_f4(p); }
+  __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+  __device__ __forceinline__ void add(const Vec& o) { v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w; }
+  __device__ __forceinline__ void add_scaled(const Vec& o, float s) {
+    v.x += s * o.v.x; v.y += s * o.v.y; v.z += s * o.v.z; v.w += s * o.v.w;
+  }
+  __device__ __forceinline__ void div(float s) { v.x /= s; v.y /= s; v.z /= s; v.w /= s; }
+  __device__ __forceinline__ float sumsq() const { return v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+  template <typename F>
+  __device__ __forceinline__ void map2(const Vec& a, F f) {  // this = f(this, a) elementwise
+    v.x = f(v.x, a.v.x); v.y = f(v.y, a.v.y); v.z = f(v.z, a.v.z); v.w = f(v.w, a.v.w);
+  }
+};
+template <>
+struct Vec<1> {
+  float v;
+  __device__ __forceinline__ void zero() { v = 0.f; }
+  __device__ __forceinline__ void load_stream(const float* p) { v = __ldg(p); }
+  __device__ __forceinline__ void load(const float* p) { v = *p; }
+  __device__ __forceinline__ void store(float* p) const { *p = v; }
+  __device__ __forceinline__ void add(const Vec& o) { v += o.v; }
+  __device__ __forceinline__ void add_scaled(const Vec& o, float s) { v += s * o.v; }
+  __device__ __forceinline__ void div(float s) { v /= s; }
+  __device__ __forceinline__ float sumsq() const { return v * v; }
+  template <typename F>
+  __device__ __forceinline__ void map2(const Vec& a, F f) { v = f(v, a.v); }
+};
+
+// Shape class of a slot: VEC floats per access, G lanes per bag, NV accesses per lane.
+struct ShapeClass {
+  int vec, g, nv;
+};
+static bool classify(int dim, bool all_vec4, ShapeClass* out) {
+  int vec = all_vec4 ? 4 : 1;
+  int units = dim / vec;
+  if (units * vec != dim || units <= 0) return false;
+  static const int gs[9] = {1, 2, 4, 8, 16, 32, 32, 32, 32};
+  static const int nvs[9] = {1, 1, 1, 1, 1, 1, 2, 4, 8};
+  for (int i = 0; i < 9; ++i)
+    if (units <= gs[i] * nvs[i]) {
+      *out = {vec, gs[i], nvs[i]};
+      return true;
+    }
+  return false;
+}
+__host__ __device__ constexpr int class_id(int vec, int g, int nv) { return vec * 10000 + g * 100 + nv; }
+
+struct SlotClasses {
+  int id[TT_MAX_FEATURES];
+};
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+template <int VEC, int G, int NV>
+__global__ void __launch_bounds__(kEbcThreads)
+ebc_forward_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_constant__ SlotClasses cls,
+                   const int64_t* __restrict__ values, const int32_t* __restrict__ offsets,
+                   float* __restrict__ pooled, int tiles_per_slot) {
+  constexpr int NG = kEbcThreads / G;                   // bag groups per CTA
+  constexpr int UB = NV >= 4 ? 1 : (NV == 2 ? 2 : 4);   // bags in flight per group
+  const int slot = blockIdx.x / tiles_per_slot;
+  if (cls.id[slot] != class_id(VEC, G, NV)) return;
+  const int tile = blockIdx.x - slot * tiles_per_slot;
+  const int B = plan.batch_size;
+  const int bag0 = tile * kBagsPerCta;
+  const int nb = min(kBagsPerCta, B - bag0);
+  if (nb <= 0) return;
+
+  __shared__ int s_off[kBagsPerCta + 1];
+  const int32_t* off = offsets + (int64_t)plan.kjt_index[slot] * B + bag0;
+  for (int i = threadIdx.x; i <= nb; i += kEbcThreads) s_off[i] = off[i];
+  __syncthreads();
+
+  const int D = plan.dim[slot];
+  const int units = D / VEC;
+  const float* __restrict__ W = static_cast<const float*>(plan.weights[slot]);
+  const uint64_t R = (uint64_t)plan.num_rows[slot];
+  const bool mean = plan.pooling[slot] == TT_POOL_MEAN;
+  float* out = pooled + (int64_t)bag0 * plan.out_stride + plan.out_col[slot];
+  const int g = threadIdx.x / G, l = threadIdx.x % G;
+
+  for (int bb = g; bb < nb; bb += NG * UB) {
+    int s[UB], len[UB];
+    Vec<VEC> acc[UB][NV];
+    int maxlen = 0;
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int bi = bb + u * NG;
+      s[u] = bi < nb ? s_off[bi] : 0;
+      len[u] = bi < nb ? s_off[bi + 1] - s[u] : 0;
+      maxlen = max(maxlen, len[u]);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[u][v].zero();
+    }
+    for (int j = 0; j < maxlen; ++j) {
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        if (j < len[u]) {
+          const int64_t id = values[s[u] + j];
+          if ((uint64_t)id < R) {
+            const float* row = W + id * D;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              const int c = l + v * G;
+              if (c < units) {
+                Vec<VEC> x;
+                x.load_stream(row + c * VEC);
+                acc[u][v].add(x);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int bi = bb + u * NG;
+      if (bi < nb) {
+        float* o = out + (int64_t)bi * plan.out_stride;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = l + v * G;
+          if (c < units) {
+            if (mean && len[u] > 1) acc[u][v].div((float)len[u]);
+            acc[u][v].store(o + c * VEC);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// backward: key construction
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEbcThreads)
+ebc_backward_keys_kernel(const __grid_constant__ tt_ebc_plan plan, const int64_t* __restrict__ values,
+                         const int32_t* __restrict__ offsets, uint32_t* __restrict__ keys,
+                         uint32_t* __restrict__ payload, int tiles_per_key) {
+  const int f = blockIdx.x / tiles_per_key;  // KJT key index
+  const int tile = blockIdx.x - f * tiles_per_key;
+  const int B = plan.batch_size;
+  const int bag0 = tile * kBagsPerCta;
+  const int nb = min(kBagsPerCta, B - bag0);
+  if (nb <= 0) return;
+  __shared__ int s_off[kBagsPerCta + 1];
+  const int32_t* off = offsets + (int64_t)f * B + bag0;
+  for (int i = threadIdx.x; i <= nb; i += kEbcThreads) s_off[i] = off[i];
+  __syncthreads();
+  const int p0 = s_off[0], p1 = s_off[nb];
+  const int slot = plan.slot_of_kjt[f];
+  const uint32_t sentinel = (uint32_t)plan.total_rows;
+  for (int p = p0 + threadIdx.x; p < p1; p += kEbcThreads) {
+    if (slot < 0) {
+      keys[p] = sentinel;
+      payload[p] = 0;
+      continue;
+    }
+    int lo = 0, hi = nb;  // invariant: s_off[lo] <= p < s_off[hi]
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (s_off[mid] <= p) lo = mid; else hi = mid;
+    }
+    const int64_t id = values[p];
+    const bool ok = (uint64_t)id < (uint64_t)plan.num_rows[slot];
+    keys[p] = ok ? (uint32_t)(plan.row_base[slot] + id) : sentinel;
+    payload[p] = (uint32_t)(slot * B + bag0 + lo);
+  }
+}
+
+// values may be over-allocated (KeyedJaggedTensor.from_id_columns keeps capacity
+// F*B and the live count on the device): park the unused tail on the sentinel.
+__global__ void ebc_backward_tail_kernel(const int32_t* __restrict__ offsets, int64_t num_bags, int64_t n,
+                                         uint32_t sentinel, uint32_t* __restrict__ keys,
+                                         uint32_t* __restrict__ payload) {
+  const int64_t live = offsets[num_bags];
+  for (int64_t p = live + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    keys[p] = sentinel;
+    payload[p] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// backward: segmented reduce over sorted keys + in-place row-wise optimizer
+// ---------------------------------------------------------------------------
+template <int VEC, int G, int NV>
+__global__ void __launch_bounds__(kEbcThreads)
+ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
+                           const __grid_constant__ tt_sparse_optimizer opt,
+                           const uint32_t* __restrict__ keys, const uint32_t* __restrict__ payload,
+                           int64_t n, const int32_t* __restrict__ offsets,
+                           const float* __restrict__ grad_out) {
+  const int64_t gid = ((int64_t)blockIdx.x * kEbcThreads + threadIdx.x) / G;
+  const int l = threadIdx.x % G;
+  if (gid >= n) return;
+  const uint32_t key = keys[gid];
+  if (key >= (uint32_t)plan.total_rows) return;        // sentinel (unused key / bad id)
+  if (gid > 0 && keys[gid - 1] == key) return;         // not the head of its run
+  int slot = 0;
+  for (int i = 0; i < plan.num_slots; ++i)
+    if ((int64_t)key >= plan.row_base[i] && (int64_t)key < plan.row_base[i] + plan.num_rows[i]) {
+      slot = i;
+      break;
+    }
+  const int64_t row = (int64_t)key - plan.row_base[slot];
+  const int D = plan.dim[slot];
+  const int units = D / VEC;
+  const int B = plan.batch_size;
+
+  Vec<VEC> g[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) g[v].zero();
+  for (int64_t j = gid; j < n; ++j) {
+    if (j > gid && keys[j] != key) break;
+    const uint32_t bag = payload[j];
+    const int sl = bag / B;
+    const int b = bag - sl * B;
+    bool div = false;
+    float flen = 1.0f;
+    if (plan.pooling[sl] == TT_POOL_MEAN) {
+      const int64_t kb = (int64_t)plan.kjt_index[sl] * B + b;
+      const int len = offsets[kb + 1] - offsets[kb];
+      if (len > 1) { div = true; flen = (float)len; }
+    }
+    const float* go = grad_out + (int64_t)b * plan.out_stride + plan.out_col[sl];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = l + v * G;
+      if (c < units) {
+        Vec<VEC> x;
+        x.load(go + c * VEC);
+        if (div) x.div(flen);
+        g[v].add(x);
+      }
+    }
+  }
+
+  // mean over D of g^2 (group reduction)
+  float ss = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+    if (l + v * G < units) ss += g[v].sumsq();
+  unsigned mask = 0xffffffffu;
+  if constexpr (G < 32) mask = ((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G);
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(mask, ss, o);
+  const float msq = ss / (float)D;
+
+  float* W = static_cast<float*>(plan.weights[slot]) + row * D;
+  if (opt.kind == TT_OPT_ROWWISE_ADAGRAD) {
+    float* st = static_cast<float*>(plan.state0[slot]) + row;
+    const float snew = *st + msq;
+    __syncwarp(mask);
+    if (l == 0) *st = snew;
+    const float stdv = sqrtf(snew) + opt.eps;
+    const float nlr = -opt.lr;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = l + v * G;
+      if (c < units) {
+        Vec<VEC> w;
+        w.load(W + c * VEC);
+        w.map2(g[v], [nlr, stdv](float wv, float gv) { return wv + (nlr * gv) / stdv; });
+        w.store(W + c * VEC);
+      }
+    }
+  } else if (opt.kind == TT_OPT_ROWWISE_ADAM) {
+    float* vst = static_cast<float*>(plan.state0[slot]) + row;
+    float* M = static_cast<float*>(plan.state1[slot]) + row * D;
+    const float vnew = opt.beta2 * (*vst) + (1.0f - opt.beta2) * msq;
+    __syncwarp(mask);
+    if (l == 0) *vst = vnew;
+    const float denom = sqrtf(vnew / opt.bias_correction2) + opt.eps;
+    const float b1 = opt.beta1, omb1 = 1.0f - opt.beta1, bc1 = opt.bias_correction1, lr = opt.lr;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = l + v * G;
+      if (c < units) {
+        Vec<VEC> m, w;
+        m.load(M + c * VEC);
+        m.map2(g[v], [b1, omb1](float mv, float gv) { return b1 * mv + omb1 * gv; });
+        m.store(M + c * VEC);
+        w.load(W + c * VEC);
+        w.map2(m, [lr, bc1, denom](float wv, float mv) { return wv - lr * (mv / bc1) / denom; });
+        w.store(W + c * VEC);
+      }
+    }
+  } else if (opt.kind == TT_OPT_SGD) {
+    const float lr = opt.lr;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = l + v * G;
+      if (c < units) {
+        Vec<VEC> w;
+        w.load(W + c * VEC);
+        w.map2(g[v], [lr](float wv, float gv) { return wv - lr * gv; });
+        w.store(W + c * VEC);
+      }
+    }
+  } else {  // TT_OPT_DENSE_GRAD: grad[row] += g
+    float* Gd = static_cast<float*>(plan.state1[slot]) + row * D;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = l + v * G;
+      if (c < units) {
+        Vec<VEC> w;
+        w.load(Gd + c * VEC);
+        w.add(g[v]);
+        w.store(Gd + c * VEC);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int validate_plan(const tt_ebc_plan* p, bool* all_vec4) {
+  if (!p) return fail(TT_ERR_INVALID, "ebc: null plan");
+  if (p->num_slots < 0 || p->num_slots > TT_MAX_FEATURES || p->num_kjt_keys < 0 ||
+      p->num_kjt_keys > TT_MAX_FEATURES)
+    return fail(TT_ERR_INVALID, "ebc: num_slots/num_kjt_keys out of range (max %d)", TT_MAX_FEATURES);
+  if (p->batch_size < 0) return fail(TT_ERR_INVALID, "ebc: negative batch");
+  if (p->total_rows < 0 || p->total_rows >= 0xffffffffLL)
+    return fail(TT_ERR_UNSUPPORTED, "ebc: total_rows must be < 2^32-1");
+  *all_vec4 = true;
+  for (int s = 0; s < p->num_slots; ++s) {
+    if (!p->weights[s]) return fail(TT_ERR_INVALID, "ebc: null weights for slot %d", s);
+    if (p->dim[s] <= 0) return fail(TT_ERR_INVALID, "ebc: bad dim for slot %d", s);
+    if (p->kjt_index[s] < 0 || p->kjt_index[s] >= p->num_kjt_keys)
+      return fail(TT_ERR_INVALID, "ebc: kjt_index out of range for slot %d", s);
+    if (p->dim[s] % 4 != 0 || p->out_col[s] % 4 != 0) *all_vec4 = false;
+  }
+  if (p->out_stride % 4 != 0) *all_vec4 = false;
+  return TT_OK;
+}
+
+template <typename Launch>
+static int for_each_class(const tt_ebc_plan* p, bool all_vec4, SlotClasses* cls, Launch launch) {
+  int seen[TT_MAX_FEATURES];
+  int nseen = 0;
+  for (int s = 0; s < p->num_slots; ++s) {
+    ShapeClass c;
+    if (!classify(p->dim[s], all_vec4, &c))
+      return fail(TT_ERR_UNSUPPORTED, "ebc: embedding_dim %d not supported (max %d)", p->dim[s],
+                  all_vec4 ? 1024 : 256);
+    cls->id[s] = class_id(c.vec, c.g, c.nv);
+  }
+  for (int s = 0; s < p->num_slots; ++s) {
+    bool dup = false;
+    for (int i = 0; i < nseen; ++i) dup |= seen[i] == cls->id[s];
+    if (dup) continue;
+    seen[nseen++] = cls->id[s];
+    int rc = launch(cls->id[s]);
+    if (rc) return rc;
+  }
+  return TT_OK;
+}
+
+#define TT_DISPATCH_CLASS(ID, MACRO)                 \
+  switch (ID) {                                      \
+    case class_id(4, 1, 1): MACRO(4, 1, 1); break;   \
+    case class_id(4, 2, 1): MACRO(4, 2, 1); break;   \
+    case class_id(4, 4, 1): MACRO(4, 4, 1); break;   \
+    case class_id(4, 8, 1): MACRO(4, 8, 1); break;   \
+    case class_id(4, 16, 1): MACRO(4, 16, 1); break; \
+    case class_id(4, 32, 1): MACRO(4, 32, 1); break; \
+    case class_id(4, 32, 2): MACRO(4, 32, 2); break; \
+    case class_id(4, 32, 4): MACRO(4, 32, 4); break; \
+    case class_id(4, 32, 8): MACRO(4, 32, 8); break; \
+    case class_id(1, 1, 1): MACRO(1, 1, 1); break;   \
+    case class_id(1, 2, 1): MACRO(1, 2, 1); break;   \
+    case class_id(1, 4, 1): MACRO(1, 4, 1); break;   \
+    case class_id(1, 8, 1): MACRO(1, 8, 1); break;   \
+    case class_id(1, 16, 1): MACRO(1, 16, 1); break; \
+    case class_id(1, 32, 1): MACRO(1, 32, 1); break; \
+    case class_id(1, 32, 2): MACRO(1, 32, 2); break; \
+    case class_id(1, 32, 4): MACRO(1, 32, 4); break; \
+    case class_id(1, 32, 8): MACRO(1, 32, 8); break; \
+    default: return fail(TT_ERR_UNSUPPORTED, "ebc: no kernel for shape class %d", ID); \
+  }
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" {
+
+int tt_ebc_forward(const tt_ebc_plan* h_plan, const int64_t* values, const int32_t* offsets,
+                   float* pooled, void* stream) {
+  bool all_vec4;
+  int rc = validate_plan(h_plan, &all_vec4);
+  if (rc) return rc;
+  TT_CHECK_ARG(offsets && pooled, "ebc_forward: null pointer");
+  if (h_plan->num_slots == 0 || h_plan->batch_size == 0) return TT_OK;
+  if ((reinterpret_cast<uintptr_t>(pooled) & 15) != 0) all_vec4 = false;
+  cudaStream_t s = as_stream(stream);
+  const int tiles = (h_plan->batch_size + kBagsPerCta - 1) / kBagsPerCta;
+  const unsigned grid = (unsigned)(tiles * h_plan->num_slots);
+  SlotClasses cls;
+  return for_each_class(h_plan, all_vec4, &cls, [&](int id) -> int {
+#define TT_LAUNCH_FWD(V, G, N)                                                                       \
+  ebc_forward_kernel<V, G, N><<<grid, kEbcThreads, 0, s>>>(*h_plan, cls, values, offsets, pooled, tiles)
+    TT_DISPATCH_CLASS(id, TT_LAUNCH_FWD);
+#undef TT_LAUNCH_FWD
+    TT_CHECK_LAUNCH("ebc_forward");
+    return TT_OK;
+  });
+}
+
+size_t tt_ebc_backward_workspace_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  return 4 * align_up((size_t)n * 4, 256) + sort_workspace_bytes(n) + 1024;
+}
+
+int tt_ebc_backward_fused(const tt_ebc_plan* h_plan, const tt_sparse_optimizer* h_opt,
+                          const int64_t* values, int64_t n, const int32_t* offsets,
+                          const float* grad_out, void* ws, size_t ws_bytes, void* stream) {
+  bool all_vec4;
+  int rc = validate_plan(h_plan, &all_vec4);
+  if (rc) return rc;
+  TT_CHECK_ARG(h_opt && offsets && grad_out && n >= 0, "ebc_backward: bad args");
+  TT_CHECK_ARG(h_opt->kind >= TT_OPT_DENSE_GRAD && h_opt->kind <= TT_OPT_SGD, "ebc_backward: bad optimizer kind");
+  TT_CHECK_ARG(h_opt->weight_decay == 0.0f, "ebc_backward: weight_decay not supported");
+  if (n == 0 || h_plan->num_slots == 0 || h_plan->batch_size == 0) return TT_OK;
+  if (n >= ((int64_t)1 << 31)) return fail(TT_ERR_UNSUPPORTED, "ebc_backward: too many ids");
+  if ((int64_t)h_plan->num_slots * h_plan->batch_size >= ((int64_t)1 << 32))
+    return fail(TT_ERR_UNSUPPORTED, "ebc_backward: slots*batch must be < 2^32");
+  for (int sl = 0; sl < h_plan->num_slots; ++sl) {
+    if (h_opt->kind == TT_OPT_ROWWISE_ADAGRAD || h_opt->kind == TT_OPT_ROWWISE_ADAM)
+      TT_CHECK_ARG(h_plan->state0[sl] != nullptr, "ebc_backward: null state0 for slot %d", sl);
+    if (h_opt->kind == TT_OPT_ROWWISE_ADAM || h_opt->kind == TT_OPT_DENSE_GRAD)
+      TT_CHECK_ARG(h_plan->state1[sl] != nullptr, "ebc_backward: null state1 for slot %d", sl);
+  }
+  if ((reinterpret_cast<uintptr_t>(grad_out) & 15) != 0) all_vec4 = false;
+  cudaStream_t s = as_stream(stream);
+  Workspace w(ws, ws_bytes);
+  uint32_t* keys = w.take<uint32_t>(n);
+  uint32_t* payload = w.take<uint32_t>(n);
+  uint32_t* skeys = w.take<uint32_t>(n);
+  uint32_t* spayload = w.take<uint32_t>(n);
+  if (!keys || !payload || !skeys || !spayload) return fail(TT_ERR_WORKSPACE, "ebc_backward: workspace too small");
+
+  const int tiles = (h_plan->batch_size + kBagsPerCta - 1) / kBagsPerCta;
+  ebc_backward_keys_kernel<<<(unsigned)(tiles * h_plan->num_kjt_keys), kEbcThreads, 0, s>>>(
+      *h_plan, values, offsets, keys, payload, tiles);
+  TT_CHECK_LAUNCH("ebc_backward_keys");
+  ebc_backward_tail_kernel<<<64, 256, 0, s>>>(offsets, (int64_t)h_plan->num_kjt_keys * h_plan->batch_size, n,
+                                              (uint32_t)h_plan->total_rows, keys, payload);
+  TT_CHECK_LAUNCH("ebc_backward_tail");
+
+  int key_bits = 1;
+  while (key_bits < 32 && ((uint64_t)h_plan->total_rows >> key_bits) != 0) ++key_bits;  // sentinel == total_rows
+  rc = sort_pairs_u32(keys, payload, skeys, spayload, n, key_bits, w.base + w.used, w.size - w.used, s);
+  if (rc) return rc;
+
+  // one shape class for the whole launch: the widest table decides
+  int max_dim = 0;
+  for (int sl = 0; sl < h_plan->num_slots; ++sl) max_dim = h_plan->dim[sl] > max_dim ? h_plan->dim[sl] : max_dim;
+  ShapeClass c;
+  if (!classify(max_dim, all_vec4, &c))
+    return fail(TT_ERR_UNSUPPORTED, "ebc_backward: embedding_dim %d not supported", max_dim);
+  const int id = class_id(c.vec, c.g, c.nv);
+  const int64_t threads = n * c.g;
+  const unsigned grid = (unsigned)((threads + kEbcThreads - 1) / kEbcThreads);
+#define TT_LAUNCH_BWD(V, G, N)                                                                        \
+  ebc_backward_update_kernel<V, G, N><<<grid, kEbcThreads, 0, s>>>(*h_plan, *h_opt, skeys, spayload, n, \
+                                                                   offsets, grad_out)
+  TT_DISPATCH_CLASS(id, TT_LAUNCH_BWD);
+#undef TT_LAUNCH_BWD
+  TT_CHECK_LAUNCH("ebc_backward_update");
+  return TT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,34 @@
+"""Helpers around ``torch.distributed._shard.sharded_tensor.ShardedTensor`` -- the
+type /root/reference/utils/model_training.py:169-176 tests for and calls
+``.gather(0, full_tensor)`` / ``.size()`` / ``.device`` on."""
+from typing import List, Optional
+
+import torch
+from torch import distributed as dist
+
+try:  # the import path the reference uses (deprecated alias) and the current one
+    from torch.distributed._shard.sharded_tensor import Shard, ShardedTensor, ShardMetadata
+except Exception:  # pragma: no cover
+    Shard = ShardedTensor = ShardMetadata = None
+
+
+def make_row_sharded(local_rows: Optional[torch.Tensor], row_offset: int, global_shape, pg=None):
+    """Wraps this rank's block of rows (or nothing) of a ``[R, D]`` table as a ShardedTensor."""
+    shards: List = []
+    if local_rows is not None and local_rows.numel() > 0:
+        rank = dist.get_rank(pg)
+        dev = local_rows.device
+        md = ShardMetadata(shard_offsets=[row_offset, 0], shard_sizes=list(local_rows.shape),
+                           placement=f"rank:{rank}/{dev}")
+        shards.append(Shard(tensor=local_rows, metadata=md))
+    return ShardedTensor._init_from_local_shards(shards, *global_shape, process_group=pg)
+
+
+def gather_if_sharded(t, dst_rank: int = 0) -> Optional[torch.Tensor]:
+    if ShardedTensor is not None and isinstance(t, ShardedTensor):
+        full = None
+        if dist.get_rank() == dst_rank:
+            full = torch.zeros(t.size(), device=t.local_shards()[0].tensor.device if t.local_shards() else None)
+        t.gather(dst_rank, full)
+        return full
+    return t

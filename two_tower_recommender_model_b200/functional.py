@@ -1,0 +1,236 @@
+"""Autograd bridges from torch tensors to the C ABI (include/tt_b200.h).
+
+Each ``torch.autograd.Function`` here does nothing but shape checks, output
+allocation and one or two library calls on torch's current stream.  All of them
+refuse CPU tensors: there is no CPU path.
+"""
+from ctypes import byref
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    N.require_cuda(t, name)
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _rows(t: torch.Tensor, name: str) -> torch.Tensor:
+    """2-D fp32 CUDA tensor whose rows are contiguous (may be a column window)."""
+    N.require_cuda(t, name)
+    if t.dtype != torch.float32 or t.dim() != 2:
+        raise TypeError(f"{name} must be a 2-D float32 tensor")
+    if t.shape[1] > 0 and t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+# --------------------------------------------------------------------------- EBC
+class EbcLookup(torch.autograd.Function):
+    """Pooled lookup; backward either applies the fused row-wise optimizer in
+    place (weights get no ``.grad``, as with TorchRec's fused TBE) or, when no
+    in-backward optimizer was registered, returns dense ``[R, D]`` gradients."""
+
+    @staticmethod
+    def forward(ctx, ebc, kjt_keys, values, offsets, batch, *weights):
+        N.require_cuda(values, "KeyedJaggedTensor.values")
+        dev = values.device
+        plan, total_dim = ebc._build_plan(kjt_keys, batch, with_state=False)
+        pooled = torch.empty(batch, total_dim, dtype=torch.float32, device=dev)
+        N.call("tt_ebc_forward", byref(plan), N.ptr(values), N.ptr(offsets), N.ptr(pooled), N.stream_ptr(dev))
+        ctx.ebc = ebc
+        ctx.kjt_keys = kjt_keys
+        ctx.batch = batch
+        ctx.n_weights = len(weights)
+        ctx.save_for_backward(values, offsets)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, grad_pooled):
+        values, offsets = ctx.saved_tensors
+        ebc = ctx.ebc
+        dev = values.device
+        grad_pooled = _f32c(grad_pooled, "grad_pooled")
+        spec = ebc._sparse_optimizer_spec(advance_step=True)
+        dense_grads = None
+        if spec is None:
+            dense_grads = ebc._alloc_dense_grads()
+            spec = N.SparseOptimizer(kind=N.OPT_DENSE_GRAD)
+        plan, _ = ebc._build_plan(ctx.kjt_keys, ctx.batch, with_state=True, dense_grads=dense_grads)
+        n = values.numel()
+        ws = N.workspace(N.load().tt_ebc_backward_workspace_bytes(n), dev)
+        N.call("tt_ebc_backward_fused", byref(plan), byref(spec), N.ptr(values), n, N.ptr(offsets),
+               N.ptr(grad_pooled), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+        grads = tuple(dense_grads) if dense_grads is not None else (None,) * ctx.n_weights
+        return (None, None, None, None, None) + grads
+
+
+# --------------------------------------------------------------------------- tower layers
+class LinearAct(torch.autograd.Function):
+    """``y = relu?(x @ w.T + b)`` in fp32 on CUDA cores (exact-fp32 path)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu: bool):
+        x = _rows(x, "x")
+        w = _f32c(w, "weight")
+        if b is not None:
+            b = _f32c(b, "bias")
+        M, K = x.shape
+        Nn = w.shape[0]
+        if w.shape[1] != K:
+            raise ValueError(f"shape mismatch: x {tuple(x.shape)} vs weight {tuple(w.shape)}")
+        y = torch.empty(M, Nn, dtype=torch.float32, device=x.device)
+        N.call("tt_linear_forward_f32", N.ptr(x), x.stride(0) if M > 0 else K, N.ptr(w), N.ptr(b), N.ptr(y),
+               M, Nn, K, 1 if relu else 0, N.stream_ptr(x.device))
+        ctx.relu = relu
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(x, w, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = _f32c(dy, "dy")
+        M, K = x.shape
+        Nn = w.shape[0]
+        dev = x.device
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty(M, K, dtype=torch.float32, device=dev) if need_dx else None
+        dw = torch.empty_like(w)
+        db = torch.empty(Nn, dtype=torch.float32, device=dev) if ctx.has_bias else None
+        ws = N.workspace(N.load().tt_linear_backward_workspace_bytes(M, Nn, K), dev)
+        N.call("tt_linear_backward_f32", N.ptr(x), x.stride(0) if M > 0 else K, N.ptr(w), N.ptr(y), N.ptr(dy),
+               N.ptr(dx), K, N.ptr(dw), N.ptr(db), M, Nn, K, 1 if ctx.relu else 0, N.ptr(ws), ws.numel(),
+               N.stream_ptr(dev))
+        return dx, dw, db, None
+
+
+def linear_act(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
+    return LinearAct.apply(x, w, b, relu)
+
+
+# --------------------------------------------------------------------------- losses
+class DotBceLoss(torch.autograd.Function):
+    """utils/model_training.py:136-140 in one launch: logits, mean BCE-with-logits
+    loss and (saved for backward) d loss / d q, d loss / d c."""
+
+    @staticmethod
+    def forward(ctx, q, c, labels):
+        q = _f32c(q, "query_embedding")
+        c = _f32c(c, "candidate_embedding")
+        N.require_cuda(labels, "labels")
+        if labels.dtype != torch.int32:
+            labels = labels.to(torch.int32)
+        labels = labels.contiguous()
+        B, d = q.shape
+        dev = q.device
+        logits = torch.empty(B, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        dq = torch.empty_like(q) if need_grad else None
+        dc = torch.empty_like(c) if need_grad else None
+        ws = N.workspace(N.load().tt_dot_bce_workspace_bytes(B), dev)
+        N.call("tt_dot_bce", N.ptr(q), N.ptr(c), N.ptr(labels), B, d, N.ptr(logits), N.ptr(loss), N.ptr(dq),
+               N.ptr(dc), 1.0, N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+        if need_grad:
+            ctx.save_for_backward(dq, dc)
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_logits):
+        dq, dc = ctx.saved_tensors
+        return dq * g_loss, dc * g_loss, None
+
+
+def dot_bce_loss(q: torch.Tensor, c: torch.Tensor, labels: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    return DotBceLoss.apply(q, c, labels)
+
+
+class InBatchSoftmaxLoss(torch.autograd.Function):
+    """Sampled softmax with in-batch negatives: ``CE(q c^T / T, arange(B))``; the
+    ``[B, B]`` logits are never materialised (fp32 CUDA-core path)."""
+
+    @staticmethod
+    def forward(ctx, q, c, temperature: float):
+        q = _f32c(q, "query_embedding")
+        c = _f32c(c, "candidate_embedding")
+        B, d = q.shape
+        dev = q.device
+        lse = torch.empty(B, dtype=torch.float32, device=dev)
+        diag = torch.empty(B, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        ws = N.workspace(N.load().tt_inbatch_softmax_workspace_bytes(B), dev)
+        N.call("tt_inbatch_softmax_forward_f32", N.ptr(q), N.ptr(c), B, d, 1.0 / temperature, N.ptr(lse),
+               N.ptr(diag), N.ptr(loss), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+        ctx.inv_t = 1.0 / temperature
+        ctx.save_for_backward(q, c, lse)
+        ctx.mark_non_differentiable(diag)
+        return loss, diag
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_diag):
+        q, c, lse = ctx.saved_tensors
+        B, d = q.shape
+        dq = torch.empty_like(q)
+        dc = torch.empty_like(c)
+        N.call("tt_inbatch_softmax_backward_f32", N.ptr(q), N.ptr(c), N.ptr(lse), B, d, ctx.inv_t, 1.0,
+               N.ptr(dq), N.ptr(dc), N.stream_ptr(q.device))
+        return dq * g_loss, dc * g_loss, None
+
+
+def in_batch_softmax_loss(q: torch.Tensor, c: torch.Tensor, temperature: float = 1.0):
+    return InBatchSoftmaxLoss.apply(q, c, temperature)
+
+
+# --------------------------------------------------------------------------- integer ops (no autograd)
+def block_bucketize(lengths: torch.Tensor, offsets: torch.Tensor, values: torch.Tensor, num_rows: torch.Tensor,
+                    num_features: int, batch: int, world: int):
+    """fbgemm::block_bucketize_sparse_features; returns
+    ``(new_lengths, new_offsets, new_values, unbucketize_permute)``."""
+    N.require_cuda(values, "values")
+    dev = values.device
+    n = values.numel()
+    n_out = world * num_features * batch
+    new_len = torch.empty(n_out, dtype=torch.int32, device=dev)
+    new_off = torch.empty(n_out + 1, dtype=torch.int32, device=dev)
+    new_val = torch.empty(n, dtype=torch.int64, device=dev)
+    unb = torch.empty(n, dtype=torch.int64, device=dev)
+    rows = num_rows.to(device=dev, dtype=torch.int64).contiguous()
+    ws = N.workspace(N.load().tt_kjt_bucketize_workspace_bytes(num_features, batch, world, n), dev)
+    N.call("tt_kjt_block_bucketize", N.ptr(lengths.contiguous()), N.ptr(offsets.contiguous()),
+           N.ptr(values.contiguous()), n, N.ptr(rows), num_features, batch, world, N.ptr(new_len), N.ptr(new_off),
+           N.ptr(new_val), N.ptr(unb), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    return new_len, new_off, new_val, unb
+
+
+def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, key_bits: int = 32):
+    """Stable radix sort of (uint32 key, uint32 payload) pairs held in int32 tensors."""
+    N.require_cuda(keys, "keys")
+    dev = keys.device
+    n = keys.numel()
+    ko = torch.empty_like(keys)
+    vo = torch.empty_like(vals)
+    ws = N.workspace(N.load().tt_sort_pairs_workspace_bytes(n), dev)
+    N.call("tt_sort_pairs_u32", N.ptr(keys), N.ptr(vals), N.ptr(ko), N.ptr(vo), n, key_bits, N.ptr(ws), ws.numel(),
+           N.stream_ptr(dev))
+    return ko, vo
+
+
+def score_topk(queries: torch.Tensor, items: torch.Tensor, k: int, item_index_base: int = 0):
+    """Exact dot-product top-k (descending score, ties -> lower index)."""
+    queries = _f32c(queries, "queries")
+    items = _f32c(items, "items")
+    Q, d = queries.shape
+    Nn = items.shape[0]
+    dev = queries.device
+    scores = torch.empty(Q, k, dtype=torch.float32, device=dev)
+    idx = torch.empty(Q, k, dtype=torch.int64, device=dev)
+    ws = N.workspace(N.load().tt_topk_workspace_bytes(Q, Nn, k), dev)
+    N.call("tt_score_topk_f32", N.ptr(queries), N.ptr(items), Q, Nn, d, k, item_index_base, N.ptr(scores),
+           N.ptr(idx), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    return scores, idx

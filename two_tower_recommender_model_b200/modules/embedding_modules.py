@@ -1,0 +1,272 @@
+"""``EmbeddingBagCollection`` with the surface the reference uses
+(/root/reference/03_model_training.py:781-784,1042-1045;
+/root/reference/utils/model_training.py:88-94,101):
+
+* ``EmbeddingBagCollection(tables=[EmbeddingBagConfig...], device=torch.device("meta") | real)``
+* ``.embedding_bag_configs()``; ``__call__(kjt) -> KeyedTensor``; ``.parameters()``
+* state-dict keys ``embedding_bags.<table name>.weight`` (TorchRec's layout, so a
+  checkpoint written by either side loads into the other, 03_model_training.py:1052)
+* ``apply_optimizer_in_backward(RowWiseAdagrad, ebc.parameters(), {"lr": lr})``
+  (03_model_training.py:791-795) is honoured: the tags torch puts on the
+  parameters select the optimizer fused into the backward kernel.
+
+Weights are fp32 ``[R, D]`` in HBM, one allocation per table, initialised
+``U(-1/sqrt(R), 1/sqrt(R))`` like TorchRec.  Lookup, pooling, backward and the
+row-wise optimizer all run in libtt_b200.so; nothing here computes on the CPU.
+"""
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from .. import _native as N
+from ..functional import EbcLookup
+from ..sparse.jagged_tensor import KeyedJaggedTensor, KeyedTensor
+from .embedding_configs import EmbeddingBagConfig, PoolingType
+
+_TAG_ATTRS = ("_in_backward_optimizers", "_optimizer_classes", "_optimizer_kwargs", "_overlapped_optimizer")
+
+
+class _EmbeddingTable(nn.Module):
+    """Parameter holder named like ``nn.EmbeddingBag`` so state-dict keys match."""
+
+    def __init__(self, cfg: EmbeddingBagConfig, device: Optional[torch.device]) -> None:
+        super().__init__()
+        self.num_embeddings = cfg.num_embeddings
+        self.embedding_dim = cfg.embedding_dim
+        self._init_min = cfg.get_weight_init_min()
+        self._init_max = cfg.get_weight_init_max()
+        self.weight = nn.Parameter(torch.empty(cfg.num_embeddings, cfg.embedding_dim, device=device, dtype=torch.float32))
+        if self.weight.device.type != "meta":
+            self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        with torch.no_grad():
+            self.weight.uniform_(self._init_min, self._init_max)
+
+    def materialize(self, device: torch.device) -> None:
+        """Replaces a ``meta`` weight by a real one on ``device`` (what
+        DistributedModelParallel does when it shards), keeping the
+        optimizer-in-backward tags."""
+        old = self.weight
+        new = nn.Parameter(torch.empty(old.shape, device=device, dtype=torch.float32))
+        for a in _TAG_ATTRS:
+            if hasattr(old, a):
+                setattr(new, a, getattr(old, a))
+        self.weight = new
+        self.reset_parameters()
+
+    def extra_repr(self) -> str:
+        return f"{self.num_embeddings}, {self.embedding_dim}"
+
+
+class EmbeddingBagCollection(nn.Module):
+    def __init__(self, tables: List[EmbeddingBagConfig], is_weighted: bool = False,
+                 device: Optional[torch.device] = None) -> None:
+        super().__init__()
+        if is_weighted:
+            raise NotImplementedError("weighted EmbeddingBagCollection is outside the reference's hot path")
+        if len(tables) == 0:
+            raise ValueError("EmbeddingBagCollection needs at least one table")
+        self._is_weighted = False
+        self._embedding_bag_configs = list(tables)
+        self._device = torch.device(device) if device is not None else torch.device("cpu")
+        self.embedding_bags = nn.ModuleDict()
+        names, feats = set(), set()
+        self._slot_feature: List[str] = []
+        self._slot_table: List[int] = []
+        for ti, cfg in enumerate(self._embedding_bag_configs):
+            if cfg.name in names:
+                raise ValueError(f"Duplicate table name {cfg.name}")
+            names.add(cfg.name)
+            if not cfg.feature_names:
+                cfg.feature_names = [cfg.name]
+            if cfg.pooling not in (PoolingType.SUM, PoolingType.MEAN):
+                raise ValueError(f"Unsupported pooling {cfg.pooling}")
+            self.embedding_bags[cfg.name] = _EmbeddingTable(cfg, self._device)
+            for f in cfg.feature_names:
+                if f in feats:
+                    raise ValueError(f"Feature {f} is looked up by more than one table")
+                feats.add(f)
+                self._slot_feature.append(f)
+                self._slot_table.append(ti)
+        if len(self._slot_feature) > N.TT_MAX_FEATURES:
+            raise ValueError(f"at most {N.TT_MAX_FEATURES} features are supported")
+        self._slot_dim = [self._embedding_bag_configs[t].embedding_dim for t in self._slot_table]
+        self._total_dim = sum(self._slot_dim)
+        self._fused_state: Dict[str, Dict[str, torch.Tensor]] = {}
+        self._fused_step = 0
+
+    # ---- TorchRec surface
+    def embedding_bag_configs(self) -> List[EmbeddingBagConfig]:
+        return self._embedding_bag_configs
+
+    def is_weighted(self) -> bool:
+        return self._is_weighted
+
+    @property
+    def device(self) -> torch.device:
+        return self._device
+
+    def feature_names(self) -> List[str]:
+        return list(self._slot_feature)
+
+    def materialize(self, device: torch.device) -> None:
+        for bag in self.embedding_bags.values():
+            if bag.weight.device.type == "meta":
+                bag.materialize(device)
+        self._device = torch.device(device)
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        w = next(iter(self.embedding_bags.values())).weight
+        self._device = w.device
+        for st in self._fused_state.values():
+            for k in list(st.keys()):
+                st[k] = fn(st[k])
+        return out
+
+    def forward(self, features: KeyedJaggedTensor) -> KeyedTensor:
+        weights = [self.embedding_bags[c.name].weight for c in self._embedding_bag_configs]
+        if weights[0].device.type == "meta":
+            raise RuntimeError("EmbeddingBagCollection is on the meta device; wrap it in "
+                               "DistributedModelParallel or call .materialize(device) first")
+        values = features.values()
+        N.require_cuda(values, "KeyedJaggedTensor.values")
+        if values.dtype != torch.int64:
+            values = values.to(torch.int64)
+        offsets = features.offsets()
+        if offsets.dtype != torch.int32:
+            offsets = offsets.to(torch.int32)
+        pooled = EbcLookup.apply(self, tuple(features.keys()), values.contiguous(), offsets.contiguous(),
+                                 features.stride(), *weights)
+        return KeyedTensor(keys=self._slot_feature, length_per_key=self._slot_dim, values=pooled)
+
+    # ---- plumbing for functional.EbcLookup
+    def _build_plan(self, kjt_keys: Tuple[str, ...], batch: int, with_state: bool,
+                    dense_grads: Optional[List[torch.Tensor]] = None) -> Tuple[N.EbcPlan, int]:
+        plan = N.EbcPlan()
+        nk = len(kjt_keys)
+        if nk > N.TT_MAX_FEATURES:
+            raise ValueError(f"KeyedJaggedTensor has more than {N.TT_MAX_FEATURES} keys")
+        plan.num_slots = len(self._slot_feature)
+        plan.batch_size = batch
+        plan.num_kjt_keys = nk
+        plan.out_stride = self._total_dim
+        key_pos = {k: i for i, k in enumerate(kjt_keys)}
+        row_base, acc = [], 0
+        for cfg in self._embedding_bag_configs:
+            row_base.append(acc)
+            acc += cfg.num_embeddings
+        plan.total_rows = acc
+        for i in range(N.TT_MAX_FEATURES):
+            plan.slot_of_kjt[i] = -1
+        spec_kind = self._in_backward_kind() if with_state else None
+        col = 0
+        for s, (feat, ti) in enumerate(zip(self._slot_feature, self._slot_table)):
+            cfg = self._embedding_bag_configs[ti]
+            if feat not in key_pos:
+                raise KeyError(f"feature {feat} is not among the KeyedJaggedTensor keys {list(kjt_keys)}")
+            w = self.embedding_bags[cfg.name].weight
+            plan.weights[s] = w.data_ptr()
+            plan.row_base[s] = row_base[ti]
+            plan.num_rows[s] = cfg.num_embeddings
+            plan.dim[s] = cfg.embedding_dim
+            plan.kjt_index[s] = key_pos[feat]
+            plan.slot_of_kjt[key_pos[feat]] = s
+            plan.out_col[s] = col
+            plan.pooling[s] = N.POOL_MEAN if cfg.pooling == PoolingType.MEAN else N.POOL_SUM
+            col += cfg.embedding_dim
+            if with_state:
+                if dense_grads is not None:
+                    plan.state1[s] = dense_grads[ti].data_ptr()
+                elif spec_kind is not None:
+                    st = self._state_for(cfg, w, spec_kind)
+                    if spec_kind == N.OPT_ROWWISE_ADAGRAD:
+                        plan.state0[s] = st["sum"].data_ptr()
+                    elif spec_kind == N.OPT_ROWWISE_ADAM:
+                        plan.state0[s] = st["exp_avg_sq"].data_ptr()
+                        plan.state1[s] = st["exp_avg"].data_ptr()
+        return plan, self._total_dim
+
+    def _tagged(self):
+        w = self.embedding_bags[self._embedding_bag_configs[0].name].weight
+        classes = getattr(w, "_optimizer_classes", None)
+        if not classes:
+            return None, None
+        return classes[0], dict(getattr(w, "_optimizer_kwargs")[0])
+
+    def _in_backward_kind(self) -> Optional[int]:
+        from ..optim.rowwise_adagrad import RowWiseAdagrad
+        from ..optim.rowwise_adam import RowWiseAdam
+        cls, _ = self._tagged()
+        if cls is None:
+            return None
+        if issubclass(cls, RowWiseAdagrad):
+            return N.OPT_ROWWISE_ADAGRAD
+        if issubclass(cls, RowWiseAdam):
+            return N.OPT_ROWWISE_ADAM
+        if issubclass(cls, torch.optim.SGD):
+            return N.OPT_SGD
+        raise NotImplementedError(
+            f"optimizer {cls.__name__} cannot be fused into the embedding backward; supported: "
+            "RowWiseAdagrad, RowWiseAdam, torch.optim.SGD (plain)")
+
+    def _sparse_optimizer_spec(self, advance_step: bool) -> Optional[N.SparseOptimizer]:
+        from ..optim.rowwise_adagrad import RowWiseAdagrad
+        from ..optim.rowwise_adam import RowWiseAdam
+        kind = self._in_backward_kind()
+        if kind is None:
+            return None
+        cls, kw = self._tagged()
+        for name in self._embedding_bag_configs[1:]:
+            c2 = getattr(self.embedding_bags[name.name].weight, "_optimizer_classes", None)
+            if not c2 or c2[0] is not cls:
+                raise NotImplementedError("all tables of one EmbeddingBagCollection must share the in-backward optimizer")
+        if kw.get("weight_decay", 0.0) != 0.0 or kw.get("lr_decay", 0.0) != 0.0:
+            raise NotImplementedError("weight_decay / lr_decay are not supported by the fused sparse optimizers")
+        spec = N.SparseOptimizer(kind=kind)
+        if kind == N.OPT_ROWWISE_ADAGRAD:
+            spec.lr = float(kw.get("lr", RowWiseAdagrad.DEFAULT_LR))
+            spec.eps = float(kw.get("eps", RowWiseAdagrad.DEFAULT_EPS))
+        elif kind == N.OPT_ROWWISE_ADAM:
+            if advance_step:
+                self._fused_step += 1
+            b1, b2 = kw.get("betas", (0.9, 0.999))
+            spec.lr = float(kw.get("lr", RowWiseAdam.DEFAULT_LR))
+            spec.eps = float(kw.get("eps", RowWiseAdam.DEFAULT_EPS))
+            spec.beta1, spec.beta2 = float(b1), float(b2)
+            step = max(self._fused_step, 1)
+            spec.bias_correction1 = 1.0 - float(b1) ** step
+            spec.bias_correction2 = 1.0 - float(b2) ** step
+        else:
+            spec.lr = float(kw.get("lr", 1e-3))
+        return spec
+
+    def _state_for(self, cfg: EmbeddingBagConfig, w: torch.Tensor, kind: int) -> Dict[str, torch.Tensor]:
+        st = self._fused_state.get(cfg.name)
+        if st is None:
+            st = {}
+            self._fused_state[cfg.name] = st
+        if kind == N.OPT_ROWWISE_ADAGRAD and "sum" not in st:
+            _, kw = self._tagged()
+            st["sum"] = torch.full((cfg.num_embeddings,), float(kw.get("initial_accumulator_value", 0.0)),
+                                   dtype=torch.float32, device=w.device)
+        if kind == N.OPT_ROWWISE_ADAM and "exp_avg" not in st:
+            st["exp_avg"] = torch.zeros_like(w)
+            st["exp_avg_sq"] = torch.zeros(cfg.num_embeddings, dtype=torch.float32, device=w.device)
+        return st
+
+    def _alloc_dense_grads(self) -> List[torch.Tensor]:
+        return [torch.zeros_like(self.embedding_bags[c.name].weight) for c in self._embedding_bag_configs]
+
+    def fused_optimizer_state(self) -> Dict[str, Dict[str, torch.Tensor]]:
+        """Row-wise optimizer state per table (absent in the reference's
+        checkpoints; exposed so a resume can be exact)."""
+        return self._fused_state
+
+    def load_fused_optimizer_state(self, state: Dict[str, Dict[str, torch.Tensor]], step: int = 0) -> None:
+        for name, st in state.items():
+            w = self.embedding_bags[name].weight
+            self._fused_state[name] = {k: v.to(w.device).clone() for k, v in st.items()}
+        self._fused_step = step

@@ -1,0 +1,60 @@
+"""Adam over ONE flat buffer: the dense (tower) parameters are re-homed as views
+of a single contiguous fp32 buffer, their gradients as views of a second one,
+so ``step()`` is one kernel launch (``tt_adam_flat``) and a data-parallel
+all-reduce is one collective on ``flat_grad``.  Same arithmetic and defaults as
+``torch.optim.Adam`` (/root/reference/03_model_training.py:826-829)."""
+from typing import Any, Iterable, Tuple
+
+import torch
+from torch.optim.optimizer import Optimizer
+
+from .. import _native as N
+
+
+class FlatAdam(Optimizer):
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3,
+                 betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8) -> None:
+        params = [p for p in params]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        ps = [p for g in self.param_groups for p in g["params"]]
+        if not ps:
+            raise ValueError("FlatAdam got no parameters")
+        dev = ps[0].device
+        N.require_cuda(ps[0], "parameter")
+        n = sum(p.numel() for p in ps)
+        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.step_count = 0
+        off = 0
+        with torch.no_grad():
+            for p in ps:
+                if p.dtype != torch.float32 or p.device != dev:
+                    raise TypeError("FlatAdam needs float32 parameters on one CUDA device")
+                k = p.numel()
+                self.flat_param[off:off + k].copy_(p.reshape(-1))
+                p.data = self.flat_param[off:off + k].view(p.shape)
+                p.grad = self.flat_grad[off:off + k].view(p.shape)
+                off += k
+        self._params = ps
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        # gradients live in flat_grad permanently; autograd accumulates into the views
+        self.flat_grad.zero_()
+        off = 0
+        for p in self._params:
+            k = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + off * 4:
+                p.grad = self.flat_grad[off:off + k].view(p.shape)
+            off += k
+
+    @torch.no_grad()
+    def step(self, closure: Any = None) -> None:
+        g = self.param_groups[0]
+        self.step_count += 1
+        b1, b2 = g["betas"]
+        N.call("tt_adam_flat", N.ptr(self.flat_param), N.ptr(self.flat_grad), N.ptr(self.exp_avg),
+               N.ptr(self.exp_avg_sq), self.flat_param.numel(), float(g["lr"]), float(b1), float(b2),
+               float(g["eps"]), 1.0 - b1 ** self.step_count, 1.0 - b2 ** self.step_count,
+               N.stream_ptr(self.flat_param.device))

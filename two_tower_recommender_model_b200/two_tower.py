@@ -1,0 +1,82 @@
+"""``TwoTower`` and ``TwoTowerTrainTask`` with the constructor / forward contract of
+/root/reference/utils/model_training.py:79-143, plus the two extensions
+BASELINE.json names: explicit per-tower feature lists (multi-feature towers as in
+ray_tune_optuna_tuning_alex_test.py:227-306) and the in-batch softmax loss.
+
+Defaults reproduce the reference: exactly two tables of equal dim, query tower
+reads table 0's features, candidate tower table 1's, loss =
+``BCEWithLogitsLoss((q*c).sum(1), labels.float())``, forward returns
+``(loss, (loss.detach(), logits.detach(), labels.detach()))``.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from .datasets.utils import Batch
+from .functional import dot_bce_loss, in_batch_softmax_loss
+from .modules.embedding_modules import EmbeddingBagCollection
+from .modules.mlp import MLP
+from .sparse.jagged_tensor import KeyedJaggedTensor, KeyedTensor
+
+
+class TwoTower(nn.Module):
+    def __init__(self, embedding_bag_collection: EmbeddingBagCollection, layer_sizes: List[int],
+                 device: Optional[torch.device] = None, query_features: Optional[List[str]] = None,
+                 candidate_features: Optional[List[str]] = None) -> None:
+        super().__init__()
+        cfgs = embedding_bag_collection.embedding_bag_configs()
+        if query_features is None and candidate_features is None:
+            assert len(cfgs) == 2, "Expected two EmbeddingBags in the two tower model"
+            assert cfgs[0].embedding_dim == cfgs[1].embedding_dim, "Both EmbeddingBagConfigs must have the same dimension"
+            query_features = list(cfgs[0].feature_names)
+            candidate_features = list(cfgs[1].feature_names)
+        elif query_features is None or candidate_features is None:
+            raise ValueError("give both query_features and candidate_features, or neither")
+        dim_of = {f: c.embedding_dim for c in cfgs for f in c.feature_names}
+        self._feature_names_query: List[str] = list(query_features)
+        self._candidate_feature_names: List[str] = list(candidate_features)
+        self.ebc = embedding_bag_collection
+        self.query_proj = MLP(in_size=sum(dim_of[f] for f in self._feature_names_query),
+                              layer_sizes=layer_sizes, device=device)
+        self.candidate_proj = MLP(in_size=sum(dim_of[f] for f in self._candidate_feature_names),
+                                  layer_sizes=layer_sizes, device=device)
+
+    @staticmethod
+    def _tower_input(pooled: KeyedTensor, features: List[str]) -> torch.Tensor:
+        # Adjacent features are one column window of the pooled matrix: no copy,
+        # the GEMM reads it with the pooled row pitch.
+        col, width = pooled.columns(features)
+        if col >= 0:
+            return pooled.values().narrow(1, col, width)
+        return torch.cat([pooled[f] for f in features], dim=1)
+
+    def forward(self, kjt: KeyedJaggedTensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        pooled_embeddings = self.ebc(kjt)
+        query_embedding = self.query_proj(self._tower_input(pooled_embeddings, self._feature_names_query))
+        candidate_embedding = self.candidate_proj(self._tower_input(pooled_embeddings, self._candidate_feature_names))
+        return query_embedding, candidate_embedding
+
+
+class TwoTowerTrainTask(nn.Module):
+    """``loss="bce"`` is the reference (utils/model_training.py:129-140).
+    ``loss="in_batch_softmax"`` treats every other candidate of the batch as a
+    negative: ``CE(q c^T / temperature, arange(B))``; ``logits`` returned in that
+    mode are the positive-pair logits (the diagonal)."""
+
+    def __init__(self, two_tower: TwoTower, loss: str = "bce", temperature: float = 1.0) -> None:
+        super().__init__()
+        if loss not in ("bce", "in_batch_softmax"):
+            raise ValueError(f"unknown loss {loss}")
+        self.two_tower = two_tower
+        self.loss_kind = loss
+        self.temperature = temperature
+        self.loss_fn: nn.Module = nn.BCEWithLogitsLoss()  # kept for API parity; the fused kernel computes it
+
+    def forward(self, batch: Batch) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        query_embedding, candidate_embedding = self.two_tower(batch.sparse_features)
+        if self.loss_kind == "bce":
+            loss, logits = dot_bce_loss(query_embedding, candidate_embedding, batch.labels)
+        else:
+            loss, logits = in_batch_softmax_loss(query_embedding, candidate_embedding, self.temperature)
+        return loss, (loss.detach(), logits.detach(), batch.labels.detach())
