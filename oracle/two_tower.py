@@ -25,6 +25,7 @@ class OracleTwoTower(nn.Module):
         dense_lr: float = 1e-2, temperature: float = 1.0,
         query_features: Optional[List[str]] = None,
         candidate_features: Optional[List[str]] = None, seed: int = 0,
+        dense_optimizer: str = "adam",
     ) -> None:
         super().__init__()
         self.tables = list(tables)
@@ -63,7 +64,13 @@ class OracleTwoTower(nn.Module):
             self.sparse_state[t.name] = st
         self.step_count = 0
         dense_params = list(self.query_proj.parameters()) + list(self.candidate_proj.parameters())
-        self.dense_opt = torch.optim.Adam(dense_params, lr=dense_lr)
+        # Adam is the reference's choice (03_model_training.py:826-829).  "sgd" exists for
+        # parity tests of the in-batch softmax: there the last-layer bias gradient of any
+        # always-active unit is structurally zero (softmax rows sum to one), so it is pure
+        # rounding noise, and Adam's g/sqrt(v) turns that noise into +-lr steps that no two
+        # implementations (or summation orders) agree on.
+        self.dense_opt = (torch.optim.Adam(dense_params, lr=dense_lr) if dense_optimizer == "adam"
+                          else torch.optim.SGD(dense_params, lr=dense_lr))
 
     @staticmethod
     def _make_mlp(in_size: int, layer_sizes: Sequence[int], g: torch.Generator) -> nn.ModuleList:

@@ -1,0 +1,146 @@
+"""CPU: host-side logic of the package (containers, planner, tagging, shim) and the C-ABI
+library's presence -- no compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import two_tower_recommender_model_b200 as tt
+from two_tower_recommender_model_b200 import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from two_tower_recommender_model_b200.build import build_library
+    build_library()
+    lib = N.load()
+    assert lib.tt_abi_version() == N.TT_ABI_VERSION and lib.tt_build_arch() == b"sm_100a"
+    header = open(os.path.join(ROOT, "include", "tt_b200.h")).read()
+    declared = set(re.findall(r"\b(tt_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    raw = ctypes.CDLL(N.library_path())
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in tt_b200.h but not exported"
+    assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
+
+
+def test_struct_layout_matches_header():
+    assert ctypes.sizeof(N.EbcPlan) == 16 + 8 + 32 * (8 * 5 + 4 * 5)
+    assert ctypes.sizeof(N.SparseOptimizer) == 32
+
+
+def test_no_cpu_fallback():
+    cfgs = [tt.EmbeddingBagConfig(name="t", embedding_dim=8, num_embeddings=10, feature_names=["a"])]
+    ebc = tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("cpu"))
+    kjt = tt.KeyedJaggedTensor.from_lengths_sync(["a"], torch.tensor([1, 2]), torch.tensor([1, 1], dtype=torch.int32))
+    with pytest.raises(N.NativeLibraryError):
+        ebc(kjt)
+    with pytest.raises(N.NativeLibraryError):
+        tt.MLP(8, [4])(torch.zeros(2, 8))
+    with pytest.raises(RuntimeError):
+        tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("meta"))(kjt)
+
+
+def test_kjt_container_cpu():
+    keys = ["user_id", "product_id"]
+    kjt = tt.KeyedJaggedTensor.from_lengths_sync(keys, torch.tensor([1, 3, 10, 4]), torch.tensor([1, 0, 1, 1, 1, 0], dtype=torch.int32))
+    assert kjt.keys() == keys and kjt.stride() == 3 and kjt.length_per_key() == [2, 2] and kjt.offset_per_key() == [0, 2, 4]
+    assert kjt.offsets().tolist() == [0, 1, 1, 2, 3, 4, 4] and kjt.offsets().dtype == torch.int32
+    d = kjt.to_dict()
+    assert d["product_id"].values().tolist() == [10, 4] and d["product_id"].lengths().tolist() == [1, 1, 0]
+    assert d["product_id"].offsets().tolist() == [0, 1, 2, 2]
+    assert kjt["user_id"].values().tolist() == [1, 3]
+    p = kjt.permute([1, 0])
+    assert p.keys() == ["product_id", "user_id"] and p.values().tolist() == [10, 4, 1, 3] and p.lengths().tolist() == [1, 1, 0, 1, 0, 1]
+    a, b = kjt.split([1, 1])
+    assert a.keys() == ["user_id"] and b.values().tolist() == [10, 4]
+    # the ctor form of 03_model_training.py:1081-1085
+    k2 = tt.create_keyed_jagged_tensor(4, keys, "product_id", device="cpu")
+    assert k2.values().tolist() == [0, 1, 2, 3] and k2.lengths().tolist() == [0] * 4 + [1] * 4 and k2.length_per_key() == [0, 4]
+    with pytest.raises(ValueError):
+        tt.create_keyed_jagged_tensor(4, keys, "nope", device="cpu")
+
+
+def test_keyed_tensor():
+    kt = tt.KeyedTensor(["a", "b", "c"], [2, 3, 1], torch.arange(12.0).view(2, 6))
+    assert kt["b"].tolist() == [[2, 3, 4], [8, 9, 10]] and kt.columns(["b", "c"]) == (2, 4) and kt.columns(["a", "c"]) == (-1, -1)
+    assert set(kt.to_dict()) == {"a", "b", "c"}
+
+
+def test_ebc_surface_meta_tags_and_state_dict_keys():
+    from torch.distributed.optim import _apply_optimizer_in_backward as apply_optimizer_in_backward
+    cfgs = [tt.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=8, num_embeddings=n, feature_names=[c])
+            for c, n in (("user_id", 10), ("product_id", 20))]
+    ebc = tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("meta"))
+    assert ebc.embedding_bag_configs()[0].embedding_dim == 8 and ebc.embedding_bag_configs()[1].feature_names == ["product_id"]
+    assert all(p.device.type == "meta" for p in ebc.parameters())
+    apply_optimizer_in_backward(tt.RowWiseAdagrad, ebc.parameters(), {"lr": 0.02})
+    ebc.materialize(torch.device("cpu"))
+    assert list(ebc.state_dict().keys()) == ["embedding_bags.t_user_id.weight", "embedding_bags.t_product_id.weight"]
+    w = ebc.embedding_bags["t_user_id"].weight
+    assert w.device.type == "cpu" and w._optimizer_classes[0] is tt.RowWiseAdagrad and w._optimizer_kwargs[0] == {"lr": 0.02}
+    assert float(w.abs().max()) <= (1 / 10) ** 0.5 + 1e-7  # U(-1/sqrt(R), 1/sqrt(R))
+    spec = ebc._sparse_optimizer_spec(advance_step=False)
+    assert spec.kind == N.OPT_ROWWISE_ADAGRAD and abs(spec.lr - 0.02) < 1e-9 and abs(spec.eps - 1e-10) < 1e-16
+    two = tt.TwoTower(ebc, [16, 8])
+    names = set(dict(two.named_parameters()))
+    assert "ebc.embedding_bags.t_user_id.weight" in names and "query_proj._mlp.1._linear.bias" in names
+    opt = tt.KeyedOptimizerWrapper(dict(tt.TwoTowerTrainTask(two).named_parameters()), lambda p: torch.optim.Adam(p, lr=0.1))
+    assert all("embedding_bags" not in k for k in opt.params) and opt.param_groups[0]["lr"] == 0.1
+
+
+def test_two_tower_asserts_like_reference():
+    mk = lambda n, d: tt.EmbeddingBagConfig(name=n, embedding_dim=d, num_embeddings=5, feature_names=[n])
+    with pytest.raises(AssertionError):
+        tt.TwoTower(tt.EmbeddingBagCollection(tables=[mk("a", 8)]), [4])
+    with pytest.raises(AssertionError):
+        tt.TwoTower(tt.EmbeddingBagCollection(tables=[mk("a", 8), mk("b", 4)]), [4])
+
+
+def test_planner():
+    from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
+    mk = lambda n, r: tt.EmbeddingBagConfig(name=n, embedding_dim=64, num_embeddings=r, feature_names=[n])
+    ebc = tt.EmbeddingBagCollection(tables=[mk("t_a", 1000), mk("t_b", 5000), mk("t_c", 10)], device=torch.device("meta"))
+    holder = torch.nn.ModuleDict({"ebc": ebc})
+    plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(local_world_size=8, world_size=8, compute_device="cuda"), batch_size=64,
+                                       storage_reservation=tt.HeuristicalStorageReservation(percentage=0.05)).plan(holder, tt.get_default_sharders())
+    p = plan.plan["ebc"]
+    assert list(p) == ["t_a", "t_b", "t_c"] and all(v.sharding_type == "table_wise" for v in p.values())
+    assert p["t_b"].ranks == [0] and p["t_a"].ranks == [1] and p["t_c"].ranks == [2]  # largest first, least-loaded rank
+    plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=8), constraints={"t_b": ParameterConstraints(sharding_types=["row_wise"])}).plan(holder)
+    assert plan.plan["ebc"]["t_b"].sharding_type == "row_wise" and plan.plan["ebc"]["t_b"].block_size == 625
+    # a table that cannot fit one GPU's budget goes row-wise by itself
+    big = torch.nn.ModuleDict({"ebc": tt.EmbeddingBagCollection(tables=[mk("t_big", 100_000_000)], device=torch.device("meta"))})
+    plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=4, hbm_cap=8 * 2 ** 30)).plan(big)
+    assert plan.plan["ebc"]["t_big"].sharding_type == "row_wise"
+    assert "t_big" in str(plan)
+
+
+def test_shim_resolves_reference_imports():
+    tt.install_torchrec_shim()
+    from torchrec.distributed import TrainPipelineSparseDist  # noqa: F401
+    from torchrec.distributed.model_parallel import DistributedModelParallel, get_default_sharders  # noqa: F401
+    from torchrec.inference.state_dict_transform import state_dict_gather, state_dict_to_device  # noqa: F401
+    from torchrec.modules.embedding_configs import EmbeddingBagConfig  # noqa: F401
+    from torchrec.modules.embedding_modules import EmbeddingBagCollection  # noqa: F401
+    from torchrec.optim.keyed import KeyedOptimizerWrapper  # noqa: F401
+    from torchrec.optim.rowwise_adagrad import RowWiseAdagrad  # noqa: F401
+    from torchrec.sparse.jagged_tensor import KeyedJaggedTensor  # noqa: F401
+    from torchrec.datasets.utils import Batch  # noqa: F401
+    from torchrec.modules.mlp import MLP  # noqa: F401
+    from torchrec.distributed.comm import get_local_size  # noqa: F401
+    from torchrec.distributed.planner import EmbeddingShardingPlanner, Topology  # noqa: F401
+    from torchrec.distributed.planner.storage_reservations import HeuristicalStorageReservation  # noqa: F401
+    assert EmbeddingBagCollection is tt.EmbeddingBagCollection
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "two_tower_recommender_model_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"

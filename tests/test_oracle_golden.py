@@ -1,0 +1,149 @@
+"""CPU: pins the oracle against tests/golden/golden.json (hand-computed known answers and
+outputs of stock torch ops; see tests/golden/make_golden.py) and against stock torch ops on
+random inputs.  The oracle is then trusted as the checker for the CUDA path."""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from oracle.ebc import TableSpec
+from oracle.kjt import block_bucketize_vectorized
+from helpers import random_kjt
+
+with open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")) as f:
+    G = json.load(f)
+T = torch.tensor
+
+
+def test_transform_kat():
+    c = G["transform_kat"]
+    v, l, y = oracle.transform_to_torchrec_batch(c["batch"], c["cat_cols"], c["emb_counts"])
+    assert v.tolist() == c["values"] and l.tolist() == c["lengths"] and y.tolist() == c["labels"]
+    assert v.dtype == torch.int64 and l.dtype == torch.int32 and y.dtype == torch.int32
+    assert oracle.lengths_to_offsets(l).tolist() == c["offsets"]
+
+
+def test_transform_negative_and_modulo():
+    v, l, _ = oracle.transform_to_torchrec_batch({"a": [-3, 7, 0, 5], "label": [0] * 4}, ["a"], [5])
+    assert v.tolist() == [2, 2, 0] and l.tolist() == [1, 1, 0, 1]  # Python modulo; 5 % 5 == 0 stays a length-1 bag
+
+
+def test_permute_kat():
+    c = G["permute_kat"]
+    ol, ov, _ = oracle.permute_2d_sparse_data(c["permute"], T(c["lengths"], dtype=torch.int32).view(c["T"], c["B"]), T(c["values"]))
+    assert ol.reshape(-1).tolist() == c["out_lengths"] and ov.tolist() == c["out_values"]
+
+
+def test_bucketize_kat():
+    c = G["bucketize_kat"]
+    for fn in (oracle.block_bucketize_sparse_features, block_bucketize_vectorized):
+        nl, nv, unb = fn(T(c["lengths"], dtype=torch.int32), T(c["values"]), c["rows"], c["W"], c["B"])
+        assert nl.tolist() == c["new_lengths"] and nv.tolist() == c["new_values"] and unb.tolist() == c["unbucketize"]
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_bucketize_loop_equals_vectorized(seed):
+    F_, B, W = 3, 17, 4
+    rows = [50, 7, 1000]
+    v, l = random_kjt(["a", "b", "c"], rows, B, 6, seed)
+    a = oracle.block_bucketize_sparse_features(l, v, rows, W, B)
+    b = block_bucketize_vectorized(l, v, rows, W, B)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_rowwise_adagrad_kat():
+    c = G["rowwise_adagrad_kat"]
+    w = T(c["weights"]); s = torch.zeros(2)
+    g = torch.zeros(2, 2); g.index_add_(0, T(c["ids"]), T(c["grads"]))
+    oracle.rowwise_adagrad_dense(w, s, g, lr=c["lr"], eps=c["eps"])
+    torch.testing.assert_close(w, T(c["weights_after"])); torch.testing.assert_close(s, T(c["sum_after"]))
+    w2 = T(c["weights"]); s2 = torch.zeros(2)
+    oracle.rowwise_adagrad_sparse(w2, s2, T([0]), g[:1], lr=c["lr"], eps=c["eps"])
+    torch.testing.assert_close(w2, w); torch.testing.assert_close(s2, s)
+
+
+def test_rowwise_adam_kat():
+    c = G["rowwise_adam_kat"]
+    w = T(c["weights"]); m = torch.zeros(2, 2); v = torch.zeros(2)
+    g = torch.zeros(2, 2); g.index_add_(0, T(c["ids"]), T(c["grads"]))
+    oracle.rowwise_adam_sparse(w, m, v, T([0]), g[:1], c["step"], lr=c["lr"], beta1=c["beta1"], beta2=c["beta2"], eps=c["eps"])
+    torch.testing.assert_close(w, T(c["weights_after"])); torch.testing.assert_close(m, T(c["m_after"]))
+    torch.testing.assert_close(v, T(c["v_after"]))
+
+
+def test_topk_ties_kat():
+    c = G["topk_ties_kat"]
+    s, i = oracle.exact_topk(T(c["queries"]), T(c["items"]), c["k"])
+    assert i.tolist() == c["indices"] and s.tolist() == c["scores"]
+
+
+def _specs(c):
+    return [TableSpec(t["name"], t["rows"], t["dim"], t["features"], t["pooling"]) for t in c["tables"]]
+
+
+def test_ebc_forward_and_backward_vs_torch_fixture():
+    c, cb = G["ebc_forward_torch"], G["ebc_backward_torch"]
+    specs = _specs(c)
+    w = [T(x) for x in c["weights"]]
+    v, l = T(c["values"]), T(c["lengths"], dtype=torch.int32)
+    for fn in (oracle.ebc_forward, oracle.ebc_forward_torch):
+        torch.testing.assert_close(fn(specs, w, c["keys"], v, l), T(c["pooled"]), rtol=1e-6, atol=1e-7)
+    grads = oracle.ebc_dense_grads(specs, c["keys"], v, l, T(cb["grad_out"]))
+    for g, want in zip(grads, cb["grads"]):
+        torch.testing.assert_close(g, T(want), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_ebc_forward_spec_equals_embedding_bag(seed):
+    specs = [TableSpec("t0", 40, 8, ["a"], "sum"), TableSpec("t1", 30, 8, ["b", "c"], "mean")]
+    w = [torch.randn(40, 8), torch.randn(30, 8)]
+    keys = ["c", "a", "b"]
+    v, l = random_kjt(keys, [30, 40, 30], 23, 5, seed)
+    torch.testing.assert_close(oracle.ebc_forward(specs, w, keys, v, l), oracle.ebc_forward_torch(specs, w, keys, v, l),
+                               rtol=1e-6, atol=1e-6)
+
+
+def test_mlp_bce_softmax_adam_vs_torch_fixture():
+    c = G["mlp_torch"]
+    y = oracle.mlp_forward(T(c["x"]), [(T(w), T(b)) for w, b in c["layers"]])
+    torch.testing.assert_close(y, T(c["y"]), rtol=1e-6, atol=1e-7)
+    c = G["bce_torch"]
+    loss, logits = oracle.dot_bce_loss(T(c["q"]), T(c["c"]), T(c["labels"], dtype=torch.int32))
+    assert abs(float(loss) - c["loss"]) < 1e-6
+    torch.testing.assert_close(logits, T(c["logits"]), rtol=1e-6, atol=1e-7)
+    c = G["softmax_torch"]
+    loss, _ = oracle.in_batch_softmax_loss(T(c["q"]), T(c["c"]), c["temperature"])
+    assert abs(float(loss) - c["loss"]) < 1e-5
+    c = G["adam_torch"]
+    p = T(c["p0"]); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step, g in enumerate(c["grads"], 1):
+        oracle.adam_step(p, T(g), m, v, step, lr=c["lr"])
+    torch.testing.assert_close(p, T(c["p3"]), rtol=1e-6, atol=1e-7)
+
+
+def test_oracle_two_tower_state_dict_names_and_step():
+    specs = [TableSpec("t_user_id", 20, 8, ["user_id"]), TableSpec("t_product_id", 30, 8, ["product_id"])]
+    m = oracle.OracleTwoTower(specs, [16, 8], seed=0)
+    sd = m.torchrec_state_dict()
+    assert set(sd) == {"ebc.embedding_bags.t_user_id.weight", "ebc.embedding_bags.t_product_id.weight",
+                       "query_proj._mlp.0._linear.weight", "query_proj._mlp.0._linear.bias",
+                       "query_proj._mlp.1._linear.weight", "query_proj._mlp.1._linear.bias",
+                       "candidate_proj._mlp.0._linear.weight", "candidate_proj._mlp.0._linear.bias",
+                       "candidate_proj._mlp.1._linear.weight", "candidate_proj._mlp.1._linear.bias"}
+    v, l, y = oracle.transform_to_torchrec_batch({"user_id": [1, 2, 0, 4], "product_id": [3, 3, 9, 0], "label": [1, 0, 1, 0]},
+                                                 ["user_id", "product_id"], [20, 30])
+    before = sd["ebc.embedding_bags.t_product_id.weight"]
+    loss, logits = m.train_step(["user_id", "product_id"], v, l, y)
+    after = m.torchrec_state_dict()["ebc.embedding_bags.t_product_id.weight"]
+    touched = (after != before).any(dim=1).nonzero().flatten().tolist()
+    assert set(touched) <= {3, 9} and logits.shape == (4,) and loss.ndim == 0
+
+
+def test_retrieval_metrics_known_answer():
+    m = oracle.retrieval_metrics([[1, 2, 3, 4]], [[2, 9]], 4)
+    import math
+    assert abs(m["precision_at_4"] - 0.25) < 1e-9 and abs(m["recall_at_4"] - 0.5) < 1e-9
+    assert abs(m["ndcg_at_4"] - (1 / math.log2(3)) / (1 + 1 / math.log2(3))) < 1e-9

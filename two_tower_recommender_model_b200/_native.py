@@ -134,9 +134,35 @@ def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+_timing = None  # name -> list of (start_event, end_event) while enabled
+
+
+def enable_timing(on: bool) -> None:
+    """Brackets every library call with CUDA events on torch's current stream
+    (bench.py's instrumented pass).  Off by default: zero overhead."""
+    global _timing
+    _timing = {} if on else None
+
+
+def timing_summary():
+    """name -> {"ms": mean device time per call, "calls": n}; synchronise first."""
+    out = {}
+    for name, evs in (_timing or {}).items():
+        ms = [a.elapsed_time(b) for a, b in evs]
+        out[name] = {"ms": sum(ms) / len(ms), "calls": len(ms)}
+    return out
+
+
 def call(name: str, *args) -> None:
     """Invokes a status-returning entry point and raises on failure."""
     global launch_count
     lib = load()
     launch_count += 1
+    if _timing is None:
+        check(getattr(lib, name)(*args), name)
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
     check(getattr(lib, name)(*args), name)
+    b.record()
+    _timing.setdefault(name, []).append((a, b))
