@@ -181,6 +181,26 @@ int tt_linear_backward_f32(const float* x, int64_t ldx, const float* w, const fl
                            size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Tensor-core (tcgen05 + TMA + TMEM) dense path: bf16 operands, fp32 accumulate.
+ * bf16 buffers are passed as void* (2 bytes per element, row pitch in elements,
+ * 16-byte aligned, pitch a multiple of 8).
+ * ------------------------------------------------------------------------- */
+
+/* fp32 [rows, cols] (pitch ldx) -> bf16 row-major `out` (pitch ld_out) and/or the
+ * transposed copy `out_t` [cols, rows] (pitch ld_out_t).  Either output may be NULL. */
+int tt_cast_f32_to_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, void* out,
+                        int64_t ld_out, void* out_t, int64_t ld_out_t, void* stream);
+
+/* C[M,N] = epilogue(A[M,K] . B[N,K]^T): the Linear of torchrec MLP
+ * (utils/model_training.py:95-96) with A = activations, B = nn.Linear.weight.
+ * Epilogue: + bias[N]; relu; mask (out = mask[m,n] > 0 ? out : 0 -- ReLU backward);
+ * stores to any of out_f32 [M,N], out_bf16 [M,N], out_bf16_t [N,M]. */
+int tt_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N,
+                 int64_t K, const float* bias, int32_t relu, const float* mask, int64_t ld_mask,
+                 float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
+                 void* out_bf16_t, int64_t ld_bf16_t, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Losses (utils/model_training.py:136-140 and the in-batch-softmax extension)
  * ------------------------------------------------------------------------- */
 
@@ -203,6 +223,24 @@ int tt_inbatch_softmax_forward_f32(const float* q, const float* c, int64_t B, in
 int tt_inbatch_softmax_backward_f32(const float* q, const float* c, const float* lse, int64_t B,
                                     int64_t d, float inv_temperature, float grad_scale, float* dq,
                                     float* dc, void* stream);
+
+/* Tensor-core in-batch softmax (BASELINE config 2/4's dominant kernel): S = q c^T stays
+ * in TMEM, softmax runs out of TMEM, nothing of size [B,B] touches HBM.  Operands are
+ * the bf16 copies made by tt_cast_f32_to_bf16 (row-major [B,d] and transposed [d,B]).
+ * forward: lse[B], diag[B] (= S_bb / T as the tensor core sees it), loss[1].
+ * backward: dq = g*(P c - c)/(B T), dc = g*(P^T q - q)/(B T), P = exp(S/T - lse);
+ *   relu_gate != 0 additionally zeroes dq where q_f32 <= 0 and dc where c_f32 <= 0
+ *   (the towers end in a ReLU: utils/model_training.py:95-96 / torchrec MLP). */
+size_t tt_inbatch_softmax_bf16_workspace_bytes(int64_t B);
+int tt_inbatch_softmax_forward_bf16(const void* q_bf16, int64_t ldq, const void* c_bf16, int64_t ldc,
+                                    int64_t B, int64_t d, float inv_temperature, float* lse,
+                                    float* diag, float* loss, void* ws, size_t ws_bytes, void* stream);
+int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void* c_bf16, int64_t ldc,
+                                     const void* qt_bf16, int64_t ldqt, const void* ct_bf16, int64_t ldct,
+                                     const float* q_f32, int64_t ldqf, const float* c_f32, int64_t ldcf,
+                                     const float* lse, int64_t B, int64_t d, float inv_temperature,
+                                     float grad_scale, int32_t relu_gate, float* dq, int64_t lddq,
+                                     float* dc, int64_t lddc, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Dense optimizer: torch.optim.Adam defaults (03_model_training.py:826-829),

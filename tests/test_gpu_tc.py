@@ -1,0 +1,91 @@
+"""tcgen05 / TMA / TMEM kernels vs float64 math on the SAME bf16-rounded operands.
+Tolerance: fp32 accumulation of exact bf16 products -> rtol 1e-4, atol 1e-4 * sqrt(K)-ish;
+bf16 outputs add one bf16 rounding (rtol 8e-3)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops(M, N, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g) / K ** 0.5
+    return a, b
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 128, 128), (256, 256, 64), (1000, 100, 80), (4096, 128, 64),
+                                   (333, 64, 1024), (65536, 64, 128), (128, 512, 256), (64, 16, 16), (129, 40, 72)])
+def test_gemm_bf16_plain(cuda, M, N, K):
+    from two_tower_recommender_model_b200.functional import cast_bf16, gemm_bf16
+    a, b = _ops(M, N, K, M + N + K)
+    ad, bd = cast_bf16(a.to(cuda)), cast_bf16(b.to(cuda))
+    assert torch.equal(ad.cpu(), a.bfloat16()) and torch.equal(bd.cpu(), b.bfloat16())
+    want = ad.double().cpu() @ bd.double().cpu().t()
+    got = gemm_bf16(ad, bd)["f32"]
+    torch.testing.assert_close(got.cpu().double(), want, rtol=1e-4, atol=1e-4)
+
+
+def test_cast_transposed(cuda):
+    from two_tower_recommender_model_b200.functional import cast_bf16
+    x = torch.randn(1000, 72)
+    r, t = cast_bf16(x.to(cuda), both=True)
+    assert torch.equal(r.cpu(), x.bfloat16()) and torch.equal(t.cpu(), x.bfloat16().t())
+    win = cast_bf16(x.to(cuda)[:, 8:40], transposed=True)
+    assert torch.equal(win.cpu(), x[:, 8:40].bfloat16().t())
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 128, 64), (777, 64, 128), (2048, 256, 512)])
+def test_gemm_bf16_epilogues(cuda, M, N, K):
+    from two_tower_recommender_model_b200.functional import cast_bf16, gemm_bf16
+    a, b = _ops(M, N, K, 7 + M)
+    g = torch.Generator().manual_seed(1)
+    bias = torch.randn(N, generator=g)
+    mask = torch.randn(M, N, generator=g)
+    ad, bd = cast_bf16(a.to(cuda)), cast_bf16(b.to(cuda))
+    base = ad.double().cpu() @ bd.double().cpu().t()
+    r = gemm_bf16(ad, bd, bias=bias.to(cuda), relu=True, out_f32=True, out_bf16=True, out_bf16_t=True)
+    want = torch.relu(base + bias.double())
+    torch.testing.assert_close(r["f32"].cpu().double(), want, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(r["bf16"].cpu().double(), want, rtol=8e-3, atol=1e-3)
+    torch.testing.assert_close(r["bf16_t"].cpu().double(), want.t(), rtol=8e-3, atol=1e-3)
+    r = gemm_bf16(ad, bd, mask=mask.to(cuda))
+    torch.testing.assert_close(r["f32"].cpu().double(), base * (mask > 0), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,d,T", [(128, 64, 1.0), (256, 64, 1.0), (1000, 64, 0.5), (4096, 64, 1.0), (777, 128, 1.0),
+                                   (300, 36, 2.0), (513, 256, 1.0), (640, 192, 1.0), (65, 8, 1.0)])
+def test_in_batch_softmax_tensor_core(cuda, B, d, T):
+    """bf16 tensor-core softmax vs float64 math on the bf16-rounded q, c.
+    Tolerance: loss/lse rtol 1e-4 (fp32 accumulate).  Gradients: dq = (P c - c_b)/(B T) is a
+    difference of two O(|c|) terms and P is rounded to bf16 (2^-9 relative) before the second
+    GEMM, so the error scales with the TERMS: atol = 6e-3 * max|c| / (B T), rtol 2e-2."""
+    from two_tower_recommender_model_b200.functional import in_batch_softmax_loss
+    g = torch.Generator().manual_seed(B + d)
+    q = torch.rand(B, d, generator=g) * (2.0 / d ** 0.5)
+    c = torch.rand(B, d, generator=g) * (2.0 / d ** 0.5)
+    q[::7] = 0  # ReLU outputs: exact zeros
+    qr = q.bfloat16().double().requires_grad_(True)
+    cr = c.bfloat16().double().requires_grad_(True)
+    s = (qr @ cr.t()) / T
+    loss_r = torch.nn.functional.cross_entropy(s, torch.arange(B))
+    loss_r.backward()
+    qd, cd = q.to(cuda).requires_grad_(True), c.to(cuda).requires_grad_(True)
+    loss, diag = in_batch_softmax_loss(qd, cd, T, precision="bf16")
+    torch.testing.assert_close(loss.cpu().double(), loss_r.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(diag.cpu().double(), s.detach().diagonal(), rtol=1e-4, atol=1e-5)
+    loss.backward()
+    atol = 6e-3 * float(max(q.abs().max(), c.abs().max())) / (B * T)
+    torch.testing.assert_close(qd.grad.cpu().double(), qr.grad, rtol=2e-2, atol=atol)
+    torch.testing.assert_close(cd.grad.cpu().double(), cr.grad, rtol=2e-2, atol=atol)
+
+
+def test_in_batch_softmax_tc_matches_fp32_path(cuda):
+    from two_tower_recommender_model_b200.functional import in_batch_softmax_loss
+    g = torch.Generator().manual_seed(3)
+    B, d = 2048, 64
+    q = torch.rand(B, d, generator=g) * 0.3
+    c = torch.rand(B, d, generator=g) * 0.3
+    a = in_batch_softmax_loss(q.to(cuda), c.to(cuda), 1.0, precision="fp32")[0]
+    b = in_batch_softmax_loss(q.to(cuda), c.to(cuda), 1.0, precision="bf16")[0]
+    torch.testing.assert_close(a, b, rtol=1e-2, atol=1e-3)  # bf16 operand rounding

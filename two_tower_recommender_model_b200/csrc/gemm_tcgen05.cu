@@ -1,0 +1,288 @@
+// C[M,N] = epilogue(A[M,K] . B[N,K]^T) on the 5th-gen tensor cores: bf16 operands staged in
+// shared memory by TMA (128-byte swizzle), tcgen05.mma issued by one thread, fp32
+// accumulator in TMEM, epilogue straight out of TMEM (bias, ReLU, ReLU-backward mask,
+// fp32 / bf16 / transposed-bf16 stores).  One CTA per 128 x BN output tile:
+//   warp 0   : TMA producer            warp 1 : TMEM allocator + MMA issuer
+//   warps 2-5: epilogue (warp w reads TMEM lanes 32*(w%4) ..)
+#include "tc_common.cuh"
+
+namespace tt {
+namespace tc {
+
+// ------------------------------------------------------------------ tensor map encode (driver entry point, no -lcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(TT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 8) != 0)
+    return fail(TT_ERR_INVALID, "TMA operand must be 16-byte aligned with a row pitch that is a multiple of 8 elements");
+  if (rows <= 0 || cols <= 0 || box_rows <= 0 || box_rows > 256) return fail(TT_ERR_INVALID, "bad TMA shape");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return TT_OK;
+}
+
+// ------------------------------------------------------------------ kernel
+struct GemmEpilogue {
+  const float* bias;        // [N] or null
+  const float* mask;        // [M, N] (pitch ld_mask): out = mask > 0 ? out : 0, or null
+  float* out_f32;           // [M, N] row-major or null
+  __nv_bfloat16* out_bf16;  // [M, N] row-major or null
+  __nv_bfloat16* out_bf16_t;  // [N, M] (transposed) or null
+  int64_t ld_mask, ld_f32, ld_bf16, ld_bf16_t;
+  int relu;
+};
+
+constexpr int kBM = 128, kBK = 64, kStages = 4, kGemmThreadsTc = 192;
+
+template <int BN>
+constexpr int gemm_smem_bytes() {
+  return kStages * (kBM * kBK * 2 + BN * kBK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreadsTc, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmEpilogue ep, int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = kBM * kBK * 2, B_BYTES = BN * kBK * 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kStages * B_BYTES);
+  uint64_t* full = bars;                 // [kStages]
+  uint64_t* empty = bars + kStages;      // [kStages]
+  uint64_t* acc_full = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+  const int num_kb = (K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+        tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * kBK, m0);
+        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * kBK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = idesc_bf16_f32(kBM, BN);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (kb / kStages) & 1;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = smem_desc_k_sw128(smem_u32(sA + s * A_BYTES));
+        const uint64_t db = smem_desc_k_sw128(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)
+          mma_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+        tc_commit(&empty[s]);                       // frees the smem stage when these MMAs retire
+        if (kb == num_kb - 1) tc_commit(acc_full);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue: thread owns row (32*(warp%4) + lane) of the tile
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr_row + c0, v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = n0 + c0 + j;
+        float x = __uint_as_float(v[j]);
+        if (ep.bias != nullptr && col < N) x += ep.bias[col];
+        if (ep.relu) x = fmaxf(x, 0.f);
+        f[j] = x;
+      }
+      if (ep.mask != nullptr && row < M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + c0 + j;
+          if (col < N && !(ep.mask[(int64_t)row * ep.ld_mask + col] > 0.f)) f[j] = 0.f;
+        }
+      }
+      if (row < M) {
+        const bool full_chunk = (n0 + c0 + 32 <= N);
+        if (ep.out_f32 != nullptr) {
+          float* o = ep.out_f32 + (int64_t)row * ep.ld_f32 + n0 + c0;
+          if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < N) o[j] = f[j];
+          }
+        }
+        if (ep.out_bf16 != nullptr) {
+          __nv_bfloat16* o = ep.out_bf16 + (int64_t)row * ep.ld_bf16 + n0 + c0;
+          if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              pk.x = pack_bf16(f[j], f[j + 1]); pk.y = pack_bf16(f[j + 2], f[j + 3]);
+              pk.z = pack_bf16(f[j + 4], f[j + 5]); pk.w = pack_bf16(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < N) o[j] = __float2bfloat16(f[j]);
+          }
+        }
+      }
+      if (ep.out_bf16_t != nullptr) {
+        // transposed store: for a fixed column the warp's 32 rows are contiguous
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + c0 + j;
+          if (col < N && row < M) ep.out_bf16_t[(int64_t)col * ep.ld_bf16_t + row] = __float2bfloat16(f[j]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+  }
+}
+
+// fp32 [rows, cols] (pitch ldx) -> bf16 row-major (pitch ld_out) and/or transposed bf16 [cols, rows]
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, __nv_bfloat16* __restrict__ out,
+                 int64_t ld_out, __nv_bfloat16* __restrict__ out_t, int64_t ld_out_t) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + i * 8, c = c0 + tx;
+    float v = (r < rows && c < cols) ? x[(int64_t)r * ldx + c] : 0.f;
+    tile[ty + i * 8][tx] = v;
+    if (out != nullptr && r < rows && c < cols) out[(int64_t)r * ld_out + c] = __float2bfloat16(v);
+  }
+  if (out_t == nullptr) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + i * 8, r = r0 + tx;
+    if (r < rows && c < cols) out_t[(int64_t)c * ld_out_t + r] = __float2bfloat16(tile[tx][ty + i * 8]);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                       cudaStream_t s) {
+  static bool attr = false;
+  constexpr int smem = gemm_smem_bytes<BN>();
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(TT_ERR_CUDA, "tc_gemm smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM);
+  tc_gemm_kernel<BN><<<grid, kGemmThreadsTc, smem, s>>>(ta, tb, ep, M, N, K);
+  TT_CHECK_LAUNCH("tc_gemm");
+  return TT_OK;
+}
+
+}  // namespace tc
+}  // namespace tt
+
+using namespace tt;
+using namespace tt::tc;
+
+extern "C" {
+
+int tt_cast_f32_to_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, void* out, int64_t ld_out,
+                        void* out_t, int64_t ld_out_t, void* stream) {
+  TT_CHECK_ARG(rows >= 0 && cols >= 0 && (out || out_t), "cast_bf16: bad args");
+  if (rows == 0 || cols == 0) return TT_OK;
+  TT_CHECK_ARG(x != nullptr, "cast_bf16: null input");
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  if (grid.y > 65535) return fail(TT_ERR_UNSUPPORTED, "cast_bf16: too many rows");
+  cast_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, ldx, (int)rows, (int)cols,
+                                                        static_cast<__nv_bfloat16*>(out), ld_out,
+                                                        static_cast<__nv_bfloat16*>(out_t), ld_out_t);
+  TT_CHECK_LAUNCH("cast_bf16");
+  return TT_OK;
+}
+
+int tt_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                 const float* bias, int32_t relu, const float* mask, int64_t ld_mask, float* out_f32, int64_t ld_f32,
+                 void* out_bf16, int64_t ld_bf16, void* out_bf16_t, int64_t ld_bf16_t, void* stream) {
+  TT_CHECK_ARG(M > 0 && N > 0 && K > 0 && a && b, "gemm_bf16: bad args");
+  TT_CHECK_ARG(out_f32 || out_bf16 || out_bf16_t, "gemm_bf16: no output");
+  if (M >= ((int64_t)1 << 31) || (M + kBM - 1) / kBM > 65535) return fail(TT_ERR_UNSUPPORTED, "gemm_bf16: M too large");
+  const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_2d(&ta, a, M, K, lda, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tb, b, N, K, ldb, bn);
+  if (rc) return rc;
+  GemmEpilogue ep;
+  ep.bias = bias; ep.mask = mask; ep.out_f32 = out_f32;
+  ep.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
+  ep.out_bf16_t = static_cast<__nv_bfloat16*>(out_bf16_t);
+  ep.ld_mask = ld_mask; ep.ld_f32 = ld_f32; ep.ld_bf16 = ld_bf16; ep.ld_bf16_t = ld_bf16_t; ep.relu = relu;
+  cudaStream_t s = as_stream(stream);
+  switch (bn) {
+    case 32: return launch_gemm<32>(ta, tb, ep, (int)M, (int)N, (int)K, s);
+    case 64: return launch_gemm<64>(ta, tb, ep, (int)M, (int)N, (int)K, s);
+    case 128: return launch_gemm<128>(ta, tb, ep, (int)M, (int)N, (int)K, s);
+    default: return launch_gemm<256>(ta, tb, ep, (int)M, (int)N, (int)K, s);
+  }
+}
+
+}  // extern "C"

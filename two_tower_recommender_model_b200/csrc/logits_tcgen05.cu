@@ -1,0 +1,488 @@
+// In-batch softmax on the tensor cores: the [B, B] logits S = Q C^T live only in TMEM.
+//
+//   forward : CTA = 128 query rows (Q tile resident in smem).  C streams through a TMA ring
+//             in NT-row tiles; tcgen05.mma writes S tiles into a 2-stage TMEM accumulator;
+//             four epilogue warps (one per TMEM lane quarter, thread = row) run an online
+//             log-sum-exp in the log2 domain.  Output: lse[B] (+ per-CTA loss partials).
+//   backward: "fixed-normaliser attention".  out[r,:] = scale * (sum_t P(r,t) Y_t - Y_r),
+//             P = exp(X_r.Y_t/T - lse).  S tile -> TMEM -> registers -> P (bf16) written back
+//             IN PLACE into TMEM -> second tcgen05.mma with A = P from TMEM (TS form) and
+//             B = Y^T tile from smem accumulates O in TMEM.  Run twice: (X,Y)=(Q,C) with the
+//             normaliser indexed by row gives dQ; (X,Y)=(C,Q) indexed by column gives dC.
+//
+// warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2-5: softmax / epilogue.
+#include "tc_common.cuh"
+
+namespace tt {
+namespace tc {
+
+constexpr int kLgThreads = 192;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// ------------------------------------------------------------------ forward
+template <int KB>
+struct FwdCfg {
+  static constexpr int NT = KB <= 2 ? 256 : 128;
+  static constexpr int STAGES = KB == 1 ? 4 : 2;
+  static constexpr int Q_BYTES = KB * 128 * 128;       // KB sub-tiles of [128 x 64] bf16
+  static constexpr int C_BYTES = KB * NT * 128;        // KB sub-tiles of [NT x 64] bf16
+  static constexpr int SMEM = Q_BYTES + STAGES * C_BYTES + 1024 + 256;
+};
+
+template <int KB>
+__global__ void __launch_bounds__(kLgThreads, 1)
+tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, int B,
+                      float scale2, const float* __restrict__ diag, float* __restrict__ lse,
+                      float* __restrict__ partial_loss) {
+  using Cfg = FwdCfg<KB>;
+  constexpr int NT = Cfg::NT, S = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sC = smem + Cfg::Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + S * Cfg::C_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* c_full = bars + 1;            // [S]
+  uint64_t* c_empty = c_full + S;         // [S]
+  uint64_t* acc_full = c_empty + S;       // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [4]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  const int T = (B + NT - 1) / NT;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmC);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < S; ++s) { mbar_init(&c_full[s], 1); mbar_init(&c_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sQ + kb * 128 * 128, &tmQ, q_full, kb * 64, m0);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % S;
+        mbar_wait(&c_empty[s], ((t / S) & 1) ^ 1);
+        mbar_expect_tx(&c_full[s], Cfg::C_BYTES);
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d(sC + s * Cfg::C_BYTES + kb * NT * 128, &tmC, &c_full[s], kb * 64, t * NT);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = idesc_bf16_f32(128, NT);
+    mbar_wait(q_full, 0);
+    for (int t = 0; t < T; ++t) {
+      const int s = t % S, as = t & 1;
+      mbar_wait(&acc_empty[as], ((t >> 1) & 1) ^ 1);
+      mbar_wait(&c_full[s], (t / S) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t da = smem_desc_k_sw128(smem_u32(sQ + kb * 128 * 128));
+          const uint64_t db = smem_desc_k_sw128(smem_u32(sC + s * Cfg::C_BYTES + kb * NT * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(tmem_base + as * NT, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+        }
+        tc_commit(&c_empty[s]);
+        tc_commit(&acc_full[as]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float m = -INFINITY, l = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int as = t & 1;
+      mbar_wait(&acc_full[as], (t >> 1) & 1);
+      tc_fence_after();
+      const int n0 = t * NT;
+      const bool tail = n0 + NT > B;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + as * NT + c0, v);
+        tmem_ld_wait();
+        float x[32];
+        float cmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          x[j] = __uint_as_float(v[j]) * scale2;
+          if (tail && n0 + c0 + j >= B) x[j] = -INFINITY;
+          cmax = fmaxf(cmax, x[j]);
+        }
+        const float mn = fmaxf(m, cmax);
+        if (mn > -INFINITY) {
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += exp2f(x[j] - mn);
+          l = l * exp2f(m - mn) + acc;
+          m = mn;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[as]);
+    }
+    float contrib = 0.f;
+    if (row < B) {
+      const float L = (m + log2f(l)) * kLn2;
+      lse[row] = L;
+      contrib = L - diag[row];
+    }
+    contrib = warp_sum(contrib);
+    if (lane == 0) red[q] = contrib;
+    epi_bar_sync();
+    if (warp == 2 && lane == 0) partial_loss[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ backward
+template <int KB>
+struct BwdCfg {
+  static constexpr int D = KB * 64;
+  static constexpr int NT = KB <= 2 ? 128 : 64;          // Y rows per tile
+  static constexpr int NKB2 = NT / 64;                   // K blocks of the second GEMM
+  static constexpr int STAGES = KB == 1 ? 4 : 2;
+  static constexpr int X_BYTES = KB * 128 * 128;
+  static constexpr int Y_BYTES = KB * NT * 128;          // KB sub-tiles [NT x 64]  (GEMM1 B operand)
+  static constexpr int YT_BYTES = NKB2 * D * 128;        // NKB2 sub-tiles [D x 64] (GEMM2 B operand)
+  static constexpr int STAGE_BYTES = Y_BYTES + YT_BYTES;
+  static constexpr int SMEM = X_BYTES + STAGES * STAGE_BYTES + 1024 + 256 + 2 * 128 * 4;
+  static constexpr int O_COL = 256;                      // O accumulator columns [256, 256 + D)
+};
+
+template <int KB, bool ROW>
+__global__ void __launch_bounds__(kLgThreads, 1)
+tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                      const __grid_constant__ CUtensorMap tmYt, int B, int d, float scale2,
+                      const float* __restrict__ lse, const float* __restrict__ yf, int64_t ld_yf,
+                      const float* __restrict__ relu_mask, int64_t ld_mask, float out_scale,
+                      float* __restrict__ out, int64_t ld_out) {
+  using Cfg = BwdCfg<KB>;
+  constexpr int NT = Cfg::NT, S = Cfg::STAGES, D = Cfg::D;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sX = smem;
+  uint8_t* sY = smem + Cfg::X_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sY + S * Cfg::STAGE_BYTES);
+  uint64_t* x_full = bars;
+  uint64_t* y_full = bars + 1;           // [S]
+  uint64_t* y_empty = y_full + S;        // [S]
+  uint64_t* s_full = y_empty + S;        // [2]
+  uint64_t* p_full = s_full + 2;         // [2]
+  uint64_t* o_full = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float* lse_tile = reinterpret_cast<float*>(tmem_slot + 2);  // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  const int T = (B + NT - 1) / NT;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmY);
+    prefetch_tmap(&tmYt);
+    mbar_init(x_full, 1);
+    for (int s = 0; s < S; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(x_full, Cfg::X_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sX + kb * 128 * 128, &tmX, x_full, kb * 64, m0);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % S;
+        uint8_t* st = sY + s * Cfg::STAGE_BYTES;
+        mbar_wait(&y_empty[s], ((t / S) & 1) ^ 1);
+        mbar_expect_tx(&y_full[s], Cfg::STAGE_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(st + kb * NT * 128, &tmY, &y_full[s], kb * 64, t * NT);
+        for (int k2 = 0; k2 < Cfg::NKB2; ++k2)
+          tma_load_2d(st + Cfg::Y_BYTES + k2 * D * 128, &tmYt, &y_full[s], t * NT + k2 * 64, 0);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc1 = idesc_bf16_f32(128, NT);
+    constexpr uint32_t idesc2 = idesc_bf16_f32(128, D);
+    auto issue_gemm1 = [&](int t) {
+      const int s = t % S, as = t & 1;
+      mbar_wait(&y_full[s], (t / S) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        uint8_t* st = sY + s * Cfg::STAGE_BYTES;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t da = smem_desc_k_sw128(smem_u32(sX + kb * 128 * 128));
+          const uint64_t db = smem_desc_k_sw128(smem_u32(st + kb * NT * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(tmem_base + as * 128, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+        }
+        tc_commit(&s_full[as]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(x_full, 0);
+    issue_gemm1(0);
+    for (int t = 0; t < T; ++t) {
+      const int s = t % S, as = t & 1;
+      if (t + 1 < T) issue_gemm1(t + 1);   // tensor core works on S(t+1) while the softmax warps turn S(t) into P(t)
+      mbar_wait(&p_full[as], (t >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        uint8_t* yt = sY + s * Cfg::STAGE_BYTES + Cfg::Y_BYTES;
+#pragma unroll
+        for (int k2 = 0; k2 < Cfg::NKB2; ++k2) {
+          const uint64_t db = smem_desc_k_sw128(smem_u32(yt + k2 * D * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ts(tmem_base + Cfg::O_COL, tmem_base + as * 128 + (k2 * 4 + k) * 8, db + 2 * k, idesc2,
+                   (t | k2 | k) != 0);
+        }
+        tc_commit(&y_empty[s]);
+        if (t == T - 1) tc_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int r_in = q * 32 + lane;
+    const int row = m0 + r_in;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float lrow = (ROW && row < B) ? lse[row] * kLog2e : 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int as = t & 1;
+      const int n0 = t * NT;
+      if (!ROW) {
+        if (r_in < NT) lse_tile[as * 128 + r_in] = (n0 + r_in < B) ? lse[n0 + r_in] * kLog2e : 0.f;
+        epi_bar_sync();
+      }
+      mbar_wait(&s_full[as], (t >> 1) & 1);
+      tc_fence_after();
+      const bool tail = n0 + NT > B;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + as * 128 + c0, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float l0 = ROW ? lrow : lse_tile[as * 128 + c0 + j];
+          const float l1 = ROW ? lrow : lse_tile[as * 128 + c0 + j + 1];
+          float p0 = exp2f(fmaf(__uint_as_float(v[j]), scale2, -l0));
+          float p1 = exp2f(fmaf(__uint_as_float(v[j + 1]), scale2, -l1));
+          if (tail) {
+            if (n0 + c0 + j >= B) p0 = 0.f;
+            if (n0 + c0 + j + 1 >= B) p1 = 0.f;
+          }
+          pk[j >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st16(trow + as * 128 + (c0 >> 1), pk);   // P overwrites S in place (columns already consumed)
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[as]);
+    }
+    // ---- O -> out = out_scale * (O - Y_r), optionally gated by relu_mask > 0
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(trow + Cfg::O_COL + c0, v);
+      tmem_ld_wait();
+      if (row < B) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = c0 + j;
+          if (col < d) {
+            float o = out_scale * (__uint_as_float(v[j]) - yf[(int64_t)row * ld_yf + col]);
+            if (relu_mask != nullptr && !(relu_mask[(int64_t)row * ld_mask + col] > 0.f)) o = 0.f;
+            out[(int64_t)row * ld_out + col] = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// diag[b] = inv_t * sum_k bf16(q[b,k]) * bf16(c[b,k])   (what the tensor core computes for S_bb)
+__global__ void __launch_bounds__(256)
+rowdot_bf16_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ c, int64_t ldc,
+                   int B, int d, float inv_t, float* __restrict__ diag) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float s = 0.f;
+  for (int k = lane; k < d; k += 32) s = fmaf(__bfloat162float(q[(int64_t)b * ldq + k]), __bfloat162float(c[(int64_t)b * ldc + k]), s);
+  s = warp_sum(s);
+  if (lane == 0) diag[b] = s * inv_t;
+}
+
+__global__ void __launch_bounds__(1024)
+loss_final_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) s += partial[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = warp_sum(red[threadIdx.x]);
+    if (threadIdx.x == 0) *out = t * scale;
+  }
+}
+
+template <int KB>
+static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tcm, int B, float scale2, const float* diag, float* lse,
+                      float* partial, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_softmax_fwd_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         FwdCfg<KB>::SMEM);
+    if (e != cudaSuccess) return fail(TT_ERR_CUDA, "softmax_fwd smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  tc_softmax_fwd_kernel<KB><<<(B + 127) / 128, kLgThreads, FwdCfg<KB>::SMEM, s>>>(tq, tcm, B, scale2, diag, lse, partial);
+  TT_CHECK_LAUNCH("tc_softmax_fwd");
+  return TT_OK;
+}
+
+template <int KB, bool ROW>
+static int launch_bwd(const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tyt, int B, int d, float scale2,
+                      const float* lse, const float* yf, int64_t ld_yf, const float* mask, int64_t ld_mask,
+                      float out_scale, float* out, int64_t ld_out, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_softmax_bwd_kernel<KB, ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         BwdCfg<KB>::SMEM);
+    if (e != cudaSuccess) return fail(TT_ERR_CUDA, "softmax_bwd smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  tc_softmax_bwd_kernel<KB, ROW><<<(B + 127) / 128, kLgThreads, BwdCfg<KB>::SMEM, s>>>(
+      tx, ty, tyt, B, d, scale2, lse, yf, ld_yf, mask, ld_mask, out_scale, out, ld_out);
+  TT_CHECK_LAUNCH("tc_softmax_bwd");
+  return TT_OK;
+}
+
+}  // namespace tc
+}  // namespace tt
+
+using namespace tt;
+using namespace tt::tc;
+
+extern "C" {
+
+size_t tt_inbatch_softmax_bf16_workspace_bytes(int64_t B) { return align_up((size_t)((B + 127) / 128 + 1) * 4, 256); }
+
+int tt_inbatch_softmax_forward_bf16(const void* q_bf16, int64_t ldq, const void* c_bf16, int64_t ldc, int64_t B,
+                                    int64_t d, float inv_t, float* lse, float* diag, float* loss, void* ws,
+                                    size_t ws_bytes, void* stream) {
+  TT_CHECK_ARG(B > 0 && d > 0 && q_bf16 && c_bf16 && lse && diag && loss, "inbatch_softmax_forward_bf16: bad args");
+  if (d > 256) return fail(TT_ERR_UNSUPPORTED, "inbatch_softmax_forward_bf16: d > 256");
+  if (B >= ((int64_t)1 << 30)) return fail(TT_ERR_UNSUPPORTED, "inbatch_softmax_forward_bf16: B too large");
+  const int blocks = (int)((B + 127) / 128);
+  if (!ws || ws_bytes < (size_t)blocks * 4) return fail(TT_ERR_WORKSPACE, "inbatch_softmax_bf16: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  const int KB = (int)((d + 63) / 64);
+  const int NT = KB <= 2 ? 256 : 128;
+  CUtensorMap tq, tcm;
+  int rc = make_tmap_bf16_2d(&tq, q_bf16, B, d, ldq, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tcm, c_bf16, B, d, ldc, NT);
+  if (rc) return rc;
+  rowdot_bf16_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(q_bf16), ldq,
+                                                            static_cast<const __nv_bfloat16*>(c_bf16), ldc, (int)B,
+                                                            (int)d, inv_t, diag);
+  TT_CHECK_LAUNCH("rowdot_bf16");
+  float* partial = static_cast<float*>(ws);
+  const float scale2 = inv_t * kLog2e;
+  switch (KB) {
+    case 1: rc = launch_fwd<1>(tq, tcm, (int)B, scale2, diag, lse, partial, s); break;
+    case 2: rc = launch_fwd<2>(tq, tcm, (int)B, scale2, diag, lse, partial, s); break;
+    case 3: rc = launch_fwd<3>(tq, tcm, (int)B, scale2, diag, lse, partial, s); break;
+    default: rc = launch_fwd<4>(tq, tcm, (int)B, scale2, diag, lse, partial, s); break;
+  }
+  if (rc) return rc;
+  loss_final_kernel<<<1, 1024, 0, s>>>(partial, blocks, 1.0f / (float)B, loss);
+  TT_CHECK_LAUNCH("loss_final");
+  return TT_OK;
+}
+
+int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void* c_bf16, int64_t ldc,
+                                     const void* qt_bf16, int64_t ldqt, const void* ct_bf16, int64_t ldct,
+                                     const float* q_f32, int64_t ldqf, const float* c_f32, int64_t ldcf,
+                                     const float* lse, int64_t B, int64_t d, float inv_t, float grad_scale,
+                                     int32_t relu_gate, float* dq, int64_t lddq, float* dc, int64_t lddc, void* stream) {
+  TT_CHECK_ARG(B > 0 && d > 0 && q_bf16 && c_bf16 && qt_bf16 && ct_bf16 && q_f32 && c_f32 && lse && dq && dc,
+               "inbatch_softmax_backward_bf16: bad args");
+  if (d > 256) return fail(TT_ERR_UNSUPPORTED, "inbatch_softmax_backward_bf16: d > 256");
+  cudaStream_t s = as_stream(stream);
+  const int KB = (int)((d + 63) / 64);
+  const int D = KB * 64;
+  const int NT = KB <= 2 ? 128 : 64;
+  const float scale2 = inv_t * kLog2e;
+  const float out_scale = grad_scale * inv_t / (float)B;
+  // padded column count of the transposed copies: the TMA tensor covers [d, B]
+  CUtensorMap tq128, tc128, tqn, tcn, tqt, tct;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tq128, q_bf16, B, d, ldq, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tc128, c_bf16, B, d, ldc, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tqn, q_bf16, B, d, ldq, NT))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tcn, c_bf16, B, d, ldc, NT))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tqt, qt_bf16, d, B, ldqt, D))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tct, ct_bf16, d, B, ldct, D))) return rc;
+  const float* gate_q = relu_gate ? q_f32 : nullptr;
+  const float* gate_c = relu_gate ? c_f32 : nullptr;
+#define TT_LB(KBV)                                                                                              \
+  do {                                                                                                          \
+    rc = launch_bwd<KBV, true>(tq128, tcn, tct, (int)B, (int)d, scale2, lse, c_f32, ldcf, gate_q, ldqf, out_scale, dq, lddq, s); \
+    if (rc) return rc;                                                                                          \
+    rc = launch_bwd<KBV, false>(tc128, tqn, tqt, (int)B, (int)d, scale2, lse, q_f32, ldqf, gate_c, ldcf, out_scale, dc, lddc, s); \
+  } while (0)
+  switch (KB) {
+    case 1: TT_LB(1); break;
+    case 2: TT_LB(2); break;
+    case 3: TT_LB(3); break;
+    default: TT_LB(4); break;
+  }
+#undef TT_LB
+  return rc;
+}
+
+}  // extern "C"

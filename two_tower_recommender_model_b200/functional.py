@@ -183,7 +183,46 @@ class InBatchSoftmaxLoss(torch.autograd.Function):
         return dq * g_loss, dc * g_loss, None
 
 
-def in_batch_softmax_loss(q: torch.Tensor, c: torch.Tensor, temperature: float = 1.0):
+class InBatchSoftmaxLossTC(torch.autograd.Function):
+    """Same loss on the tensor cores (tcgen05): bf16 operands, fp32 accumulation in TMEM,
+    softmax out of TMEM; the backward recomputes S tile by tile and feeds P back to the tensor
+    core from TMEM.  Nothing of size [B, B] is ever written to HBM."""
+
+    @staticmethod
+    def forward(ctx, q, c, temperature: float):
+        q = _f32c(q, "query_embedding")
+        c = _f32c(c, "candidate_embedding")
+        B, d = q.shape
+        dev = q.device
+        qb, qbt = cast_bf16(q, both=True)
+        cb, cbt = cast_bf16(c, both=True)
+        lse = torch.empty(B, dtype=torch.float32, device=dev)
+        diag = torch.empty(B, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        ws = N.workspace(N.load().tt_inbatch_softmax_bf16_workspace_bytes(B), dev)
+        N.call("tt_inbatch_softmax_forward_bf16", N.ptr(qb), qb.stride(0), N.ptr(cb), cb.stride(0), B, d,
+               1.0 / temperature, N.ptr(lse), N.ptr(diag), N.ptr(loss), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+        ctx.inv_t = 1.0 / temperature
+        ctx.save_for_backward(q, c, qb, cb, qbt, cbt, lse)
+        ctx.mark_non_differentiable(diag)
+        return loss, diag
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_diag):
+        q, c, qb, cb, qbt, cbt, lse = ctx.saved_tensors
+        B, d = q.shape
+        dq = torch.empty_like(q)
+        dc = torch.empty_like(c)
+        N.call("tt_inbatch_softmax_backward_bf16", N.ptr(qb), qb.stride(0), N.ptr(cb), cb.stride(0),
+               N.ptr(qbt), qbt.stride(0), N.ptr(cbt), cbt.stride(0), N.ptr(q), q.stride(0), N.ptr(c), c.stride(0),
+               N.ptr(lse), B, d, ctx.inv_t, 1.0, 0, N.ptr(dq), d, N.ptr(dc), d, N.stream_ptr(q.device))
+        return dq * g_loss, dc * g_loss, None
+
+
+def in_batch_softmax_loss(q: torch.Tensor, c: torch.Tensor, temperature: float = 1.0, precision: str = "fp32"):
+    """``precision="fp32"``: CUDA-core path, exact fp32.  ``"bf16"``: tcgen05 tensor-core path."""
+    if precision == "bf16":
+        return InBatchSoftmaxLossTC.apply(q, c, temperature)
     return InBatchSoftmaxLoss.apply(q, c, temperature)
 
 
@@ -234,3 +273,53 @@ def score_topk(queries: torch.Tensor, items: torch.Tensor, k: int, item_index_ba
     N.call("tt_score_topk_f32", N.ptr(queries), N.ptr(items), Q, Nn, d, k, item_index_base, N.ptr(scores),
            N.ptr(idx), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
     return scores, idx
+
+
+# --------------------------------------------------------------------------- tensor-core (bf16) primitives
+def cast_bf16(x: torch.Tensor, transposed: bool = False, both: bool = False):
+    """fp32 [rows, cols] (row-contiguous, may be a column window) -> bf16 copy; ``transposed`` returns
+    the [cols, rows] copy instead, ``both`` returns (row-major, transposed).  Row pitches are padded to
+    a multiple of 8 elements (TMA needs 16-byte pitches)."""
+    x = _rows(x, "x")
+    rows, cols = x.shape
+    dev = x.device
+    pad = lambda n: (n + 7) // 8 * 8
+    out = out_t = None
+    if both or not transposed:
+        out = torch.empty(rows, pad(cols), dtype=torch.bfloat16, device=dev)[:, :cols]
+    if both or transposed:
+        out_t = torch.empty(cols, pad(rows), dtype=torch.bfloat16, device=dev)[:, :rows]
+    N.call("tt_cast_f32_to_bf16", N.ptr(x), x.stride(0) if rows > 0 else cols, rows, cols,
+           N.ptr(out), out.stride(0) if out is not None else 0, N.ptr(out_t), out_t.stride(0) if out_t is not None else 0,
+           N.stream_ptr(dev))
+    if both:
+        return out, out_t
+    return out_t if transposed else out
+
+
+def gemm_bf16(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+              mask: Optional[torch.Tensor] = None, out_f32: bool = True, out_bf16: bool = False,
+              out_bf16_t: bool = False):
+    """``epilogue(a @ b.T)`` on tcgen05: a [M,K] bf16, b [N,K] bf16 (row pitch multiple of 8).
+    Returns a dict with the requested outputs ("f32", "bf16", "bf16_t")."""
+    N.require_cuda(a, "a")
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    Nn = b.shape[0]
+    dev = a.device
+    pad = lambda n: (n + 7) // 8 * 8
+    res = {}
+    f32 = torch.empty(M, Nn, dtype=torch.float32, device=dev) if out_f32 else None
+    b16 = torch.empty(M, pad(Nn), dtype=torch.bfloat16, device=dev)[:, :Nn] if out_bf16 else None
+    b16t = torch.empty(Nn, pad(M), dtype=torch.bfloat16, device=dev)[:, :M] if out_bf16_t else None
+    N.call("tt_gemm_bf16", N.ptr(a), a.stride(0), N.ptr(b), b.stride(0), M, Nn, K, N.ptr(bias), 1 if relu else 0,
+           N.ptr(mask), mask.stride(0) if mask is not None else 0, N.ptr(f32), Nn,
+           N.ptr(b16), b16.stride(0) if b16 is not None else 0, N.ptr(b16t), b16t.stride(0) if b16t is not None else 0,
+           N.stream_ptr(dev))
+    if f32 is not None:
+        res["f32"] = f32
+    if b16 is not None:
+        res["bf16"] = b16
+    if b16t is not None:
+        res["bf16_t"] = b16t
+    return res

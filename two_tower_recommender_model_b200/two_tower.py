@@ -64,10 +64,14 @@ class TwoTowerTrainTask(nn.Module):
     negative: ``CE(q c^T / temperature, arange(B))``; ``logits`` returned in that
     mode are the positive-pair logits (the diagonal)."""
 
-    def __init__(self, two_tower: TwoTower, loss: str = "bce", temperature: float = 1.0) -> None:
+    def __init__(self, two_tower: TwoTower, loss: str = "bce", temperature: float = 1.0,
+                 precision: str = "fp32") -> None:
         super().__init__()
         if loss not in ("bce", "in_batch_softmax"):
             raise ValueError(f"unknown loss {loss}")
+        if precision not in ("fp32", "bf16"):
+            raise ValueError(f"unknown precision {precision}")
+        self.precision = precision  # "bf16": logits GEMM + softmax on tcgen05 (bf16 operands, fp32 accumulate)
         self.two_tower = two_tower
         self.loss_kind = loss
         self.temperature = temperature
@@ -78,5 +82,5 @@ class TwoTowerTrainTask(nn.Module):
         if self.loss_kind == "bce":
             loss, logits = dot_bce_loss(query_embedding, candidate_embedding, batch.labels)
         else:
-            loss, logits = in_batch_softmax_loss(query_embedding, candidate_embedding, self.temperature)
+            loss, logits = in_batch_softmax_loss(query_embedding, candidate_embedding, self.temperature, self.precision)
         return loss, (loss.detach(), logits.detach(), batch.labels.detach())
