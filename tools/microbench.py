@@ -1,0 +1,111 @@
+"""Per-kernel micro-benchmarks on one GPU (CUDA events, warm-up, L2-sized inputs noted).
+    python tools/microbench.py softmax|ebc|towers|topk [--B 65536] [--d 64] [--iters 10]
+Used for ncu captures (`ncu -k regex:... python tools/microbench.py softmax --iters 1`)."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import two_tower_recommender_model_b200 as tt  # noqa: E402
+from two_tower_recommender_model_b200 import _native as N  # noqa: E402
+from two_tower_recommender_model_b200 import functional as F  # noqa: E402
+
+
+def timed(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def softmax(args):
+    dev = torch.device("cuda:0")
+    B, d = args.B, args.d
+    q = (torch.rand(B, d, device=dev) * 0.3).requires_grad_(True)
+    c = (torch.rand(B, d, device=dev) * 0.3).requires_grad_(True)
+    N.enable_timing(True)
+
+    def run():
+        loss, _ = F.in_batch_softmax_loss(q, c, 1.0, precision=args.precision)
+        loss.backward()
+    ms = timed(run, args.iters, warmup=args.warmup)
+    torch.cuda.synchronize()
+    summ = N.timing_summary()
+    flops_f = 2.0 * B * B * d
+    for k, v in summ.items():
+        fl = flops_f if "forward" in k else (2 * flops_f * 2 if "backward" in k else 0)
+        print(f"{k:42s} {v['ms']:9.4f} ms  x{v['calls']}" + (f"  {fl / v['ms'] / 1e9:8.1f} TFLOP/s (executed)" if fl else ""))
+    print(f"fwd+bwd wall {ms:.4f} ms -> credited 6*B*B*d = {6.0 * B * B * d / ms / 1e9:.1f} TFLOP/s")
+
+
+def ebc(args):
+    dev = torch.device("cuda:0")
+    from torch.distributed.optim import _apply_optimizer_in_backward as aob
+    B, D, R, L = args.B, args.d, args.rows, args.L
+    cfgs = [tt.EmbeddingBagConfig(name=f"t{i}", embedding_dim=D, num_embeddings=R, feature_names=[f"f{i}"],
+                                  pooling=tt.PoolingType.MEAN if L > 1 else tt.PoolingType.SUM) for i in range(2)]
+    e = tt.EmbeddingBagCollection(tables=cfgs, device=dev)
+    aob(tt.RowWiseAdagrad, e.parameters(), {"lr": 0.01})
+    lens = torch.full((2 * B,), L, dtype=torch.int32, device=dev)
+    kjts = [tt.KeyedJaggedTensor.from_lengths_sync(["f0", "f1"], torch.randint(0, R, (2 * B * L,), device=dev), lens) for _ in range(4)]
+    go = torch.randn(B, 2 * D, device=dev)
+    N.enable_timing(True)
+    i = [0]
+
+    def run():
+        kt = e(kjts[i[0] % 4]); i[0] += 1
+        kt.values().backward(go)
+    timed(run, args.iters, warmup=args.warmup)
+    torch.cuda.synchronize()
+    uniq = sum(int(torch.unique(k[f].values()).numel()) for k in kjts[:1] for f in ("f0", "f1"))
+    fwd_bytes = 2 * (B * L * (8 + 4 * D) + 4 * B + 4 * B * D)
+    bwd_bytes = 2 * (4 * B * D + 8 * B * L) + uniq * (8 * D + 8)
+    for k, v in N.timing_summary().items():
+        by = fwd_bytes if "forward" in k else bwd_bytes
+        print(f"{k:42s} {v['ms'] * 1e3:9.1f} us  x{v['calls']}  {by / v['ms'] / 1e6:8.1f} GB/s algorithmic ({by / 1e6:.1f} MB)")
+
+
+def towers(args):
+    dev = torch.device("cuda:0")
+    B = args.B
+    mlp = tt.MLP(64, [128, 64], device=dev)
+    x = torch.randn(B, 64, device=dev, requires_grad=True)
+    N.enable_timing(True)
+
+    def run():
+        mlp(x).sum().backward()
+    ms = timed(run, args.iters, warmup=args.warmup)
+    for k, v in N.timing_summary().items():
+        print(f"{k:42s} {v['ms'] * 1e3:9.1f} us  x{v['calls']}")
+    print(f"one tower fwd+bwd {ms:.3f} ms")
+
+
+def topk(args):
+    dev = torch.device("cuda:0")
+    q = torch.randn(args.Q, args.d, device=dev)
+    it = torch.randn(args.rows, args.d, device=dev)
+    ms = timed(lambda: F.score_topk(q, it, 100), args.iters, warmup=1)
+    print(f"top-100 of {args.rows} items for {args.Q} queries: {ms:.3f} ms, {2.0 * args.Q * args.rows * args.d / ms / 1e9:.2f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["softmax", "ebc", "towers", "topk"])
+    ap.add_argument("--B", type=int, default=65536)
+    ap.add_argument("--d", type=int, default=64)
+    ap.add_argument("--L", type=int, default=1)
+    ap.add_argument("--Q", type=int, default=4096)
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--precision", default="bf16")
+    a = ap.parse_args()
+    {"softmax": softmax, "ebc": ebc, "towers": towers, "topk": topk}[a.what](a)

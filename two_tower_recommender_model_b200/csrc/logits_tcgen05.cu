@@ -16,11 +16,28 @@
 namespace tt {
 namespace tc {
 
-constexpr int kLgThreads = 192;
+constexpr int kLgThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two per TMEM lane quarter)
+constexpr int kEpiThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// one MUFU op; inputs are finite or -inf, flush-to-zero is what we want for tiny probabilities
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 16]));
+#pragma unroll
+  for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; ++i) a[i] = fmaxf(a[i], a[i + w]);
+  return a[0];
+}
 
 // ------------------------------------------------------------------ forward
 template <int KB>
@@ -61,7 +78,7 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     prefetch_tmap(&tmC);
     mbar_init(q_full, 1);
     for (int s = 0; s < S; ++s) { mbar_init(&c_full[s], 1); mbar_init(&c_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiThreads); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -104,49 +121,82 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       __syncwarp();
     }
   } else {
+    // 8 softmax warps: warp w and w+4 share TMEM lane quarter (w & 3) and split the tile's columns
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
+    const int half = (warp - 2) >> 2;
+    const int r_in = q * 32 + lane;
+    const int row = m0 + r_in;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    float m = -INFINITY, l = 0.f;
+    constexpr int HC = NT / 2;                      // columns per warp per tile
+    float m = -INFINITY, l = 0.f;                   // running max / sum, log2 domain
+    auto consume = [&](const uint32_t (&v)[32], int col0, bool tail) {
+      float mx;
+      if (!tail) {
+        mx = max32(v) * scale2;
+      } else {
+        mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < B) mx = fmaxf(mx, __uint_as_float(v[j]) * scale2);
+      }
+      const float mn = fmaxf(m, mx);
+      if (mn == -INFINITY) return;                  // chunk entirely past the last column
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float e0 = ex2(fmaf(__uint_as_float(v[j]), scale2, -mn));
+        float e1 = ex2(fmaf(__uint_as_float(v[j + 1]), scale2, -mn));
+        float e2 = ex2(fmaf(__uint_as_float(v[j + 2]), scale2, -mn));
+        float e3 = ex2(fmaf(__uint_as_float(v[j + 3]), scale2, -mn));
+        if (tail) {
+          if (col0 + j >= B) e0 = 0.f;
+          if (col0 + j + 1 >= B) e1 = 0.f;
+          if (col0 + j + 2 >= B) e2 = 0.f;
+          if (col0 + j + 3 >= B) e3 = 0.f;
+        }
+        a0 += e0; a1 += e1; a2 += e2; a3 += e3;
+      }
+      l = l * ex2(m - mn) + ((a0 + a1) + (a2 + a3));
+      m = mn;
+    };
     for (int t = 0; t < T; ++t) {
       const int as = t & 1;
       mbar_wait(&acc_full[as], (t >> 1) & 1);
       tc_fence_after();
-      const int n0 = t * NT;
-      const bool tail = n0 + NT > B;
+      const int n0 = t * NT + half * HC;
+      const bool tail = t * NT + NT > B;
+      const uint32_t tcol = trow + as * NT + half * HC;
+      uint32_t va[32], vb[32];
+      tmem_ld32(tcol, va);
 #pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(trow + as * NT + c0, v);
+      for (int c0 = 0; c0 < HC; c0 += 64) {
         tmem_ld_wait();
-        float x[32];
-        float cmax = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          x[j] = __uint_as_float(v[j]) * scale2;
-          if (tail && n0 + c0 + j >= B) x[j] = -INFINITY;
-          cmax = fmaxf(cmax, x[j]);
-        }
-        const float mn = fmaxf(m, cmax);
-        if (mn > -INFINITY) {
-          float acc = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc += exp2f(x[j] - mn);
-          l = l * exp2f(m - mn) + acc;
-          m = mn;
-        }
+        tmem_ld32(tcol + c0 + 32, vb);
+        consume(va, n0 + c0, tail);
+        tmem_ld_wait();
+        if (c0 + 64 < HC) tmem_ld32(tcol + c0 + 64, va);
+        consume(vb, n0 + c0 + 32, tail);
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);
     }
+    // merge the two column halves of every row, then the loss partial of this CTA
+    float* mrg = reinterpret_cast<float*>(sC);     // C ring is idle now: [128][2]
+    if (half == 1) { mrg[r_in * 2] = m; mrg[r_in * 2 + 1] = l; }
+    epi_bar_sync();
     float contrib = 0.f;
-    if (row < B) {
-      const float L = (m + log2f(l)) * kLn2;
-      lse[row] = L;
-      contrib = L - diag[row];
+    if (half == 0) {
+      const float m1 = mrg[r_in * 2], l1 = mrg[r_in * 2 + 1];
+      const float mn = fmaxf(m, m1);
+      const float lt = l * ex2(m - mn) + l1 * ex2(m1 - mn);
+      if (row < B) {
+        const float L = (mn + log2f(lt)) * kLn2;
+        lse[row] = L;
+        contrib = L - diag[row];
+      }
+      contrib = warp_sum(contrib);
+      if (lane == 0) red[q] = contrib;
     }
-    contrib = warp_sum(contrib);
-    if (lane == 0) red[q] = contrib;
     epi_bar_sync();
     if (warp == 2 && lane == 0) partial_loss[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
     tc_fence_before();
@@ -194,7 +244,7 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   uint64_t* p_full = s_full + 2;         // [2]
   uint64_t* o_full = p_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* lse_tile = reinterpret_cast<float*>(tmem_slot + 2);  // [2][128]
+  float* lse_tile = reinterpret_cast<float*>(bars + 32);      // [2][128], 16-byte aligned (float4 reads)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
@@ -206,7 +256,7 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     prefetch_tmap(&tmYt);
     mbar_init(x_full, 1);
     for (int s = 0; s < S; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kEpiThreads); }
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -274,49 +324,66 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r_in = q * 32 + lane;
     const int row = m0 + r_in;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    constexpr int HC = NT / 2;                       // S columns per warp per tile (32 or 64)
     const float lrow = (ROW && row < B) ? lse[row] * kLog2e : 0.f;
+    auto to_p = [&](const uint32_t (&v)[32], int as, int cl /*column inside the tile*/, int n0, bool tail) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float l0 = lrow, l1 = lrow, l2 = lrow, l3 = lrow;
+        if (!ROW) {
+          const float4 lv = *reinterpret_cast<const float4*>(&lse_tile[as * 128 + cl + j]);
+          l0 = lv.x; l1 = lv.y; l2 = lv.z; l3 = lv.w;
+        }
+        float p0 = ex2(fmaf(__uint_as_float(v[j]), scale2, -l0));
+        float p1 = ex2(fmaf(__uint_as_float(v[j + 1]), scale2, -l1));
+        float p2 = ex2(fmaf(__uint_as_float(v[j + 2]), scale2, -l2));
+        float p3 = ex2(fmaf(__uint_as_float(v[j + 3]), scale2, -l3));
+        if (tail) {
+          if (n0 + cl + j >= B) p0 = 0.f;
+          if (n0 + cl + j + 1 >= B) p1 = 0.f;
+          if (n0 + cl + j + 2 >= B) p2 = 0.f;
+          if (n0 + cl + j + 3 >= B) p3 = 0.f;
+        }
+        pk[j >> 1] = pack_bf16(p0, p1);
+        pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+      }
+      tmem_st16(trow + as * 128 + (cl >> 1), pk);
+    };
     for (int t = 0; t < T; ++t) {
       const int as = t & 1;
       const int n0 = t * NT;
       if (!ROW) {
-        if (r_in < NT) lse_tile[as * 128 + r_in] = (n0 + r_in < B) ? lse[n0 + r_in] * kLog2e : 0.f;
+        if (half == 0 && r_in < NT) lse_tile[as * 128 + r_in] = (n0 + r_in < B) ? lse[n0 + r_in] * kLog2e : 0.f;
         epi_bar_sync();
       }
       mbar_wait(&s_full[as], (t >> 1) & 1);
       tc_fence_after();
       const bool tail = n0 + NT > B;
-#pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(trow + as * 128 + c0, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float l0 = ROW ? lrow : lse_tile[as * 128 + c0 + j];
-          const float l1 = ROW ? lrow : lse_tile[as * 128 + c0 + j + 1];
-          float p0 = exp2f(fmaf(__uint_as_float(v[j]), scale2, -l0));
-          float p1 = exp2f(fmaf(__uint_as_float(v[j + 1]), scale2, -l1));
-          if (tail) {
-            if (n0 + c0 + j >= B) p0 = 0.f;
-            if (n0 + c0 + j + 1 >= B) p1 = 0.f;
-          }
-          pk[j >> 1] = pack_bf16(p0, p1);
-        }
-        tmem_st16(trow + as * 128 + (c0 >> 1), pk);   // P overwrites S in place (columns already consumed)
-      }
+      // P (bf16) overwrites S (fp32) in place.  Both halves must have READ their S columns before
+      // either writes P: P columns [cl/2, cl/2+16) of half 1 overlap S columns that half 0 reads.
+      uint32_t va[32], vb[32];
+      tmem_ld32(trow + as * 128 + half * HC, va);
+      if (HC == 64) tmem_ld32(trow + as * 128 + half * HC + 32, vb);
+      tmem_ld_wait();
+      tc_fence_before();
+      epi_bar_sync();
+      tc_fence_after();
+      to_p(va, as, half * HC, n0, tail);
+      if (HC == 64) to_p(vb, as, half * HC + 32, n0, tail);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[as]);
     }
-    // ---- O -> out = out_scale * (O - Y_r), optionally gated by relu_mask > 0
+    // ---- O -> out = out_scale * (O - Y_r), optionally gated by relu_mask > 0 (halves alternate chunks)
     mbar_wait(o_full, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < D; c0 += 32) {
+    for (int c0 = half * 32; c0 < D; c0 += 64) {
       uint32_t v[32];
       tmem_ld32(trow + Cfg::O_COL + c0, v);
       tmem_ld_wait();
