@@ -1,27 +1,32 @@
 // In-batch softmax on the tensor cores: the [B, B] logits S = Q C^T live only in TMEM.
 //
 //   forward : CTA = 128 query rows (Q tile resident in smem).  C streams through a TMA ring
-//             in NT-row tiles; tcgen05.mma writes S tiles into a 2-stage TMEM accumulator;
-//             four epilogue warps (one per TMEM lane quarter, thread = row) run an online
-//             log-sum-exp in the log2 domain.  Output: lse[B] (+ per-CTA loss partials).
+//             in NT-row tiles; tcgen05.mma writes S tiles into a 2-stage TMEM accumulator.
+//             Two softmax warpgroups ping-pong: group g owns TMEM stage g and the tiles
+//             t = g (mod 2); inside a group thread = row, one warp per TMEM lane quarter.
+//             Each runs an online log-sum-exp in the log2 domain; the two partial (max, sum)
+//             pairs of a row are merged at the end.  Output: lse[B] + per-CTA loss partials.
 //   backward: "fixed-normaliser attention".  out[r,:] = scale * (sum_t P(r,t) Y_t - Y_r),
 //             P = exp(X_r.Y_t/T - lse).  S tile -> TMEM -> registers -> P (bf16) written back
 //             IN PLACE into TMEM -> second tcgen05.mma with A = P from TMEM (TS form) and
 //             B = Y^T tile from smem accumulates O in TMEM.  Run twice: (X,Y)=(Q,C) with the
 //             normaliser indexed by row gives dQ; (X,Y)=(C,Q) indexed by column gives dC.
 //
-// warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2-5: softmax / epilogue.
+// warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2-5 / 6-9: softmax groups 0 / 1.
+// Both kernels are bound by the MUFU (ex2) pipe, not the tensor pipe, at d = 64: a 128 x 256
+// logits tile costs 512 tensor cycles but 2048 MUFU cycles (16 ex2 / clk / SM).
 #include "tc_common.cuh"
 
 namespace tt {
 namespace tc {
 
-constexpr int kLgThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two per TMEM lane quarter)
-constexpr int kEpiThreads = 256;
+constexpr int kLgThreads = 320;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// named barrier private to one softmax group (ids 1 and 2), 128 threads
+__device__ __forceinline__ void group_bar_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+__device__ __forceinline__ void all_softmax_bar_sync() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
 // one MUFU op; inputs are finite or -inf, flush-to-zero is what we want for tiny probabilities
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -38,6 +43,26 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
     for (int i = 0; i < w; ++i) a[i] = fmaxf(a[i], a[i + w]);
   return a[0];
 }
+// Producer / MMA-issuer waits: these warps share a scheduler with softmax warps, so back off
+// instead of burning issue slots in a try_wait spin.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(64);
+  }
+  printf("tt_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
 
 // ------------------------------------------------------------------ forward
 template <int KB>
@@ -46,8 +71,41 @@ struct FwdCfg {
   static constexpr int STAGES = KB == 1 ? 4 : 2;
   static constexpr int Q_BYTES = KB * 128 * 128;       // KB sub-tiles of [128 x 64] bf16
   static constexpr int C_BYTES = KB * NT * 128;        // KB sub-tiles of [NT x 64] bf16
-  static constexpr int SMEM = Q_BYTES + STAGES * C_BYTES + 1024 + 256;
+  static constexpr int SMEM = Q_BYTES + STAGES * C_BYTES + 1024 + 256 + 1024;  // + merge scratch [128][2]
 };
+
+// running (max, sum) update over one 32-column chunk; TAIL masks columns >= B
+template <bool TAIL>
+__device__ __forceinline__ void lse_chunk(const uint32_t (&v)[32], int col0, int B, float scale2, float& m, float& l) {
+  float mx;
+  if (!TAIL) {
+    mx = max32(v) * scale2;
+  } else {
+    mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < B) mx = fmaxf(mx, __uint_as_float(v[j]) * scale2);
+    if (mx == -INFINITY) return;  // chunk entirely past the last column
+  }
+  const float mn = fmaxf(m, mx);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float e0 = ex2(fmaf(__uint_as_float(v[j]), scale2, -mn));
+    float e1 = ex2(fmaf(__uint_as_float(v[j + 1]), scale2, -mn));
+    float e2 = ex2(fmaf(__uint_as_float(v[j + 2]), scale2, -mn));
+    float e3 = ex2(fmaf(__uint_as_float(v[j + 3]), scale2, -mn));
+    if (TAIL) {
+      e0 = (col0 + j < B) ? e0 : 0.f;
+      e1 = (col0 + j + 1 < B) ? e1 : 0.f;
+      e2 = (col0 + j + 2 < B) ? e2 : 0.f;
+      e3 = (col0 + j + 3 < B) ? e3 : 0.f;
+    }
+    a0 += e0; a1 += e1; a2 += e2; a3 += e3;
+  }
+  l = l * ex2(m - mn) + ((a0 + a1) + (a2 + a3));
+  m = mn;
+}
 
 template <int KB>
 __global__ void __launch_bounds__(kLgThreads, 1)
@@ -78,7 +136,7 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     prefetch_tmap(&tmC);
     mbar_init(q_full, 1);
     for (int s = 0; s < S; ++s) { mbar_init(&c_full[s], 1); mbar_init(&c_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiThreads); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -93,7 +151,7 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int kb = 0; kb < KB; ++kb) tma_load_2d(sQ + kb * 128 * 128, &tmQ, q_full, kb * 64, m0);
       for (int t = 0; t < T; ++t) {
         const int s = t % S;
-        mbar_wait(&c_empty[s], ((t / S) & 1) ^ 1);
+        mbar_wait_relaxed(&c_empty[s], ((t / S) & 1) ^ 1);
         mbar_expect_tx(&c_full[s], Cfg::C_BYTES);
         for (int kb = 0; kb < KB; ++kb)
           tma_load_2d(sC + s * Cfg::C_BYTES + kb * NT * 128, &tmC, &c_full[s], kb * 64, t * NT);
@@ -101,13 +159,13 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = idesc_bf16_f32(128, NT);
-    mbar_wait(q_full, 0);
-    for (int t = 0; t < T; ++t) {
-      const int s = t % S, as = t & 1;
-      mbar_wait(&acc_empty[as], ((t >> 1) & 1) ^ 1);
-      mbar_wait(&c_full[s], (t / S) & 1);
-      tc_fence_after();
-      if (elect_one()) {
+    if (elect_one()) {
+      mbar_wait_relaxed(q_full, 0);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % S, as = t & 1;
+        mbar_wait_relaxed(&acc_empty[as], ((t >> 1) & 1) ^ 1);
+        mbar_wait_relaxed(&c_full[s], (t / S) & 1);
+        tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           const uint64_t da = smem_desc_k_sw128(smem_u32(sQ + kb * 128 * 128));
@@ -118,77 +176,42 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tc_commit(&c_empty[s]);
         tc_commit(&acc_full[as]);
       }
-      __syncwarp();
     }
   } else {
-    // 8 softmax warps: warp w and w+4 share TMEM lane quarter (w & 3) and split the tile's columns
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int g = (warp - 2) >> 2;                  // softmax group = TMEM stage it owns
     const int r_in = q * 32 + lane;
     const int row = m0 + r_in;
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    constexpr int HC = NT / 2;                      // columns per warp per tile
+    const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * NT;
     float m = -INFINITY, l = 0.f;                   // running max / sum, log2 domain
-    auto consume = [&](const uint32_t (&v)[32], int col0, bool tail) {
-      float mx;
-      if (!tail) {
-        mx = max32(v) * scale2;
-      } else {
-        mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < B) mx = fmaxf(mx, __uint_as_float(v[j]) * scale2);
-      }
-      const float mn = fmaxf(m, mx);
-      if (mn == -INFINITY) return;                  // chunk entirely past the last column
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float e0 = ex2(fmaf(__uint_as_float(v[j]), scale2, -mn));
-        float e1 = ex2(fmaf(__uint_as_float(v[j + 1]), scale2, -mn));
-        float e2 = ex2(fmaf(__uint_as_float(v[j + 2]), scale2, -mn));
-        float e3 = ex2(fmaf(__uint_as_float(v[j + 3]), scale2, -mn));
-        if (tail) {
-          if (col0 + j >= B) e0 = 0.f;
-          if (col0 + j + 1 >= B) e1 = 0.f;
-          if (col0 + j + 2 >= B) e2 = 0.f;
-          if (col0 + j + 3 >= B) e3 = 0.f;
-        }
-        a0 += e0; a1 += e1; a2 += e2; a3 += e3;
-      }
-      l = l * ex2(m - mn) + ((a0 + a1) + (a2 + a3));
-      m = mn;
-    };
-    for (int t = 0; t < T; ++t) {
-      const int as = t & 1;
-      mbar_wait(&acc_full[as], (t >> 1) & 1);
+    for (int t = g; t < T; t += 2) {
+      mbar_wait(&acc_full[g], (t >> 1) & 1);
       tc_fence_after();
-      const int n0 = t * NT + half * HC;
-      const bool tail = t * NT + NT > B;
-      const uint32_t tcol = trow + as * NT + half * HC;
+      const int n0 = t * NT;
+      const bool tail = n0 + NT > B;
       uint32_t va[32], vb[32];
       tmem_ld32(tcol, va);
 #pragma unroll 1
-      for (int c0 = 0; c0 < HC; c0 += 64) {
+      for (int c0 = 0; c0 < NT; c0 += 64) {
         tmem_ld_wait();
         tmem_ld32(tcol + c0 + 32, vb);
-        consume(va, n0 + c0, tail);
+        if (!tail) lse_chunk<false>(va, n0 + c0, B, scale2, m, l); else lse_chunk<true>(va, n0 + c0, B, scale2, m, l);
         tmem_ld_wait();
-        if (c0 + 64 < HC) tmem_ld32(tcol + c0 + 64, va);
-        consume(vb, n0 + c0 + 32, tail);
+        if (c0 + 64 < NT) tmem_ld32(tcol + c0 + 64, va);
+        if (!tail) lse_chunk<false>(vb, n0 + c0 + 32, B, scale2, m, l); else lse_chunk<true>(vb, n0 + c0 + 32, B, scale2, m, l);
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[as]);
+      mbar_arrive(&acc_empty[g]);
     }
-    // merge the two column halves of every row, then the loss partial of this CTA
-    float* mrg = reinterpret_cast<float*>(sC);     // C ring is idle now: [128][2]
-    if (half == 1) { mrg[r_in * 2] = m; mrg[r_in * 2 + 1] = l; }
-    epi_bar_sync();
-    float contrib = 0.f;
-    if (half == 0) {
+    // merge the two groups' partial (max, sum) of every row, then this CTA's loss partial
+    float* mrg = reinterpret_cast<float*>(bars + 32);  // [128][2], own scratch (the C ring may still be in use)
+    if (g == 1) { mrg[r_in * 2] = m; mrg[r_in * 2 + 1] = l; }
+    all_softmax_bar_sync();
+    if (g == 0) {
       const float m1 = mrg[r_in * 2], l1 = mrg[r_in * 2 + 1];
       const float mn = fmaxf(m, m1);
-      const float lt = l * ex2(m - mn) + l1 * ex2(m1 - mn);
+      const float lt = l * ex2(m - mn) + ((m1 == -INFINITY) ? 0.f : l1 * ex2(m1 - mn));
+      float contrib = 0.f;
       if (row < B) {
         const float L = (mn + log2f(lt)) * kLn2;
         lse[row] = L;
@@ -197,7 +220,7 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       contrib = warp_sum(contrib);
       if (lane == 0) red[q] = contrib;
     }
-    epi_bar_sync();
+    all_softmax_bar_sync();
     if (warp == 2 && lane == 0) partial_loss[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
     tc_fence_before();
   }
@@ -222,6 +245,34 @@ struct BwdCfg {
   static constexpr int SMEM = X_BYTES + STAGES * STAGE_BYTES + 1024 + 256 + 2 * 128 * 4;
   static constexpr int O_COL = 256;                      // O accumulator columns [256, 256 + D)
 };
+
+// one 32-column chunk of S -> P (bf16 pairs), written back over S in TMEM
+template <bool ROW, bool TAIL>
+__device__ __forceinline__ void p_chunk(const uint32_t (&v)[32], uint32_t tdst, const float* lse_cols, float lrow,
+                                        float scale2, int col0, int B) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float l0 = lrow, l1 = lrow, l2 = lrow, l3 = lrow;
+    if (!ROW) {
+      const float4 lv = *reinterpret_cast<const float4*>(lse_cols + j);
+      l0 = lv.x; l1 = lv.y; l2 = lv.z; l3 = lv.w;
+    }
+    float p0 = ex2(fmaf(__uint_as_float(v[j]), scale2, -l0));
+    float p1 = ex2(fmaf(__uint_as_float(v[j + 1]), scale2, -l1));
+    float p2 = ex2(fmaf(__uint_as_float(v[j + 2]), scale2, -l2));
+    float p3 = ex2(fmaf(__uint_as_float(v[j + 3]), scale2, -l3));
+    if (TAIL) {
+      p0 = (col0 + j < B) ? p0 : 0.f;
+      p1 = (col0 + j + 1 < B) ? p1 : 0.f;
+      p2 = (col0 + j + 2 < B) ? p2 : 0.f;
+      p3 = (col0 + j + 3 < B) ? p3 : 0.f;
+    }
+    pk[j >> 1] = pack_bf16(p0, p1);
+    pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+  }
+  tmem_st16(tdst, pk);
+}
 
 template <int KB, bool ROW>
 __global__ void __launch_bounds__(kLgThreads, 1)
@@ -256,7 +307,7 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     prefetch_tmap(&tmYt);
     mbar_init(x_full, 1);
     for (int s = 0; s < S; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], kEpiThreads); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); }
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -273,7 +324,7 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       for (int t = 0; t < T; ++t) {
         const int s = t % S;
         uint8_t* st = sY + s * Cfg::STAGE_BYTES;
-        mbar_wait(&y_empty[s], ((t / S) & 1) ^ 1);
+        mbar_wait_relaxed(&y_empty[s], ((t / S) & 1) ^ 1);
         mbar_expect_tx(&y_full[s], Cfg::STAGE_BYTES);
         for (int kb = 0; kb < KB; ++kb) tma_load_2d(st + kb * NT * 128, &tmY, &y_full[s], kb * 64, t * NT);
         for (int k2 = 0; k2 < Cfg::NKB2; ++k2)
@@ -283,11 +334,11 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   } else if (warp == 1) {
     constexpr uint32_t idesc1 = idesc_bf16_f32(128, NT);
     constexpr uint32_t idesc2 = idesc_bf16_f32(128, D);
-    auto issue_gemm1 = [&](int t) {
-      const int s = t % S, as = t & 1;
-      mbar_wait(&y_full[s], (t / S) & 1);
-      tc_fence_after();
-      if (elect_one()) {
+    if (elect_one()) {
+      auto issue_gemm1 = [&](int t) {
+        const int s = t % S, as = t & 1;
+        mbar_wait_relaxed(&y_full[s], (t / S) & 1);
+        tc_fence_after();
         uint8_t* st = sY + s * Cfg::STAGE_BYTES;
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
@@ -297,17 +348,17 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           for (int k = 0; k < 4; ++k) mma_ss(tmem_base + as * 128, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
         }
         tc_commit(&s_full[as]);
-      }
-      __syncwarp();
-    };
-    mbar_wait(x_full, 0);
-    issue_gemm1(0);
-    for (int t = 0; t < T; ++t) {
-      const int s = t % S, as = t & 1;
-      if (t + 1 < T) issue_gemm1(t + 1);   // tensor core works on S(t+1) while the softmax warps turn S(t) into P(t)
-      mbar_wait(&p_full[as], (t >> 1) & 1);
-      tc_fence_after();
-      if (elect_one()) {
+      };
+      mbar_wait_relaxed(x_full, 0);
+      issue_gemm1(0);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % S, as = t & 1;
+        // S(t+1) goes to the other TMEM stage: the tensor core computes it while softmax group
+        // `as` turns S(t) into P(t).  Stage (t+1)&1 is free: MMA2(t-1) was issued before this
+        // point and tcgen05.mma executes in issue order.
+        if (t + 1 < T) issue_gemm1(t + 1);
+        mbar_wait_relaxed(&p_full[as], (t >> 1) & 1);
+        tc_fence_after();
         uint8_t* yt = sY + s * Cfg::STAGE_BYTES + Cfg::Y_BYTES;
 #pragma unroll
         for (int k2 = 0; k2 < Cfg::NKB2; ++k2) {
@@ -320,70 +371,50 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         tc_commit(&y_empty[s]);
         if (t == T - 1) tc_commit(o_full);
       }
-      __syncwarp();
     }
   } else {
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int g = (warp - 2) >> 2;                   // softmax group = TMEM S/P stage it owns
     const int r_in = q * 32 + lane;
     const int row = m0 + r_in;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    constexpr int HC = NT / 2;                       // S columns per warp per tile (32 or 64)
+    const uint32_t tsp = trow + g * 128;
     const float lrow = (ROW && row < B) ? lse[row] * kLog2e : 0.f;
-    auto to_p = [&](const uint32_t (&v)[32], int as, int cl /*column inside the tile*/, int n0, bool tail) {
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float l0 = lrow, l1 = lrow, l2 = lrow, l3 = lrow;
-        if (!ROW) {
-          const float4 lv = *reinterpret_cast<const float4*>(&lse_tile[as * 128 + cl + j]);
-          l0 = lv.x; l1 = lv.y; l2 = lv.z; l3 = lv.w;
-        }
-        float p0 = ex2(fmaf(__uint_as_float(v[j]), scale2, -l0));
-        float p1 = ex2(fmaf(__uint_as_float(v[j + 1]), scale2, -l1));
-        float p2 = ex2(fmaf(__uint_as_float(v[j + 2]), scale2, -l2));
-        float p3 = ex2(fmaf(__uint_as_float(v[j + 3]), scale2, -l3));
-        if (tail) {
-          if (n0 + cl + j >= B) p0 = 0.f;
-          if (n0 + cl + j + 1 >= B) p1 = 0.f;
-          if (n0 + cl + j + 2 >= B) p2 = 0.f;
-          if (n0 + cl + j + 3 >= B) p3 = 0.f;
-        }
-        pk[j >> 1] = pack_bf16(p0, p1);
-        pk[(j >> 1) + 1] = pack_bf16(p2, p3);
-      }
-      tmem_st16(trow + as * 128 + (cl >> 1), pk);
-    };
-    for (int t = 0; t < T; ++t) {
-      const int as = t & 1;
+    float* lse_g = lse_tile + g * 128;
+    for (int t = g; t < T; t += 2) {
       const int n0 = t * NT;
       if (!ROW) {
-        if (half == 0 && r_in < NT) lse_tile[as * 128 + r_in] = (n0 + r_in < B) ? lse[n0 + r_in] * kLog2e : 0.f;
-        epi_bar_sync();
+        if (r_in < NT) lse_g[r_in] = (n0 + r_in < B) ? lse[n0 + r_in] * kLog2e : 0.f;
+        group_bar_sync(g);
       }
-      mbar_wait(&s_full[as], (t >> 1) & 1);
+      mbar_wait(&s_full[g], (t >> 1) & 1);
       tc_fence_after();
       const bool tail = n0 + NT > B;
-      // P (bf16) overwrites S (fp32) in place.  Both halves must have READ their S columns before
-      // either writes P: P columns [cl/2, cl/2+16) of half 1 overlap S columns that half 0 reads.
+      // P (bf16) overwrites S (fp32) in place.  P chunk c lands on S columns [16c, 16c+16), which
+      // belong to S chunk floor(c/2) <= c: already in registers when the store is issued.
       uint32_t va[32], vb[32];
-      tmem_ld32(trow + as * 128 + half * HC, va);
-      if (HC == 64) tmem_ld32(trow + as * 128 + half * HC + 32, vb);
-      tmem_ld_wait();
-      tc_fence_before();
-      epi_bar_sync();
-      tc_fence_after();
-      to_p(va, as, half * HC, n0, tail);
-      if (HC == 64) to_p(vb, as, half * HC + 32, n0, tail);
+      tmem_ld32(tsp, va);
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 64) {
+        tmem_ld_wait();
+        tmem_ld32(tsp + c0 + 32, vb);
+        if (!tail) p_chunk<ROW, false>(va, tsp + (c0 >> 1), lse_g + c0, lrow, scale2, n0 + c0, B);
+        else p_chunk<ROW, true>(va, tsp + (c0 >> 1), lse_g + c0, lrow, scale2, n0 + c0, B);
+        tmem_ld_wait();
+        if (c0 + 64 < NT) tmem_ld32(tsp + c0 + 64, va);
+        if (!tail) p_chunk<ROW, false>(vb, tsp + ((c0 + 32) >> 1), lse_g + c0 + 32, lrow, scale2, n0 + c0 + 32, B);
+        else p_chunk<ROW, true>(vb, tsp + ((c0 + 32) >> 1), lse_g + c0 + 32, lrow, scale2, n0 + c0 + 32, B);
+      }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[as]);
+      mbar_arrive(&p_full[g]);
+      if (!ROW) group_bar_sync(g);   // lse_g is rewritten at the top of the next iteration
     }
-    // ---- O -> out = out_scale * (O - Y_r), optionally gated by relu_mask > 0 (halves alternate chunks)
+    // ---- O -> out = out_scale * (O - Y_r), optionally gated by relu_mask > 0 (groups alternate chunks)
     mbar_wait(o_full, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c0 = half * 32; c0 < D; c0 += 64) {
+    for (int c0 = g * 32; c0 < D; c0 += 64) {
       uint32_t v[32];
       tmem_ld32(trow + Cfg::O_COL + c0, v);
       tmem_ld_wait();
@@ -525,7 +556,6 @@ int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void
   const int NT = KB <= 2 ? 128 : 64;
   const float scale2 = inv_t * kLog2e;
   const float out_scale = grad_scale * inv_t / (float)B;
-  // padded column count of the transposed copies: the TMA tensor covers [d, B]
   CUtensorMap tq128, tc128, tqn, tcn, tqt, tct;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tq128, q_bf16, B, d, ldq, 128))) return rc;
