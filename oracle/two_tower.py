@@ -137,6 +137,36 @@ class OracleTwoTower(nn.Module):
         s = (q @ c.t()) / self.temperature
         return F.cross_entropy(s, torch.arange(q.shape[0])), s.diagonal()
 
+    # ---- one data-parallel step as W ranks would do it: every rank's loss is the mean over ITS
+    # batch; embedding gradients of all ranks are SUMMED into the (model-parallel) tables, tower
+    # gradients are AVERAGED (DDP), then both optimizers step once.
+    def train_step_ranks(self, keys, batches) -> List[torch.Tensor]:
+        self.dense_opt.zero_grad(set_to_none=True)
+        for eb in self.embedding_bags.values():
+            eb.weight.grad = None
+        losses = []
+        for values, lengths, labels in batches:
+            q, c = self.forward(keys, values, lengths)
+            loss, _ = self.loss(q, c, labels)
+            loss.backward()
+            losses.append(loss.detach())
+        W = len(batches)
+        self.step_count += 1
+        with torch.no_grad():
+            for group in self.dense_opt.param_groups:
+                for p in group["params"]:
+                    if p.grad is not None:
+                        p.grad.div_(W)
+            for t in self.tables:
+                w = self.embedding_bags[t.name].weight
+                if w.grad is None:
+                    continue
+                assert self.sparse_optimizer == "rowwise_adagrad"
+                rowwise_adagrad_dense(w, self.sparse_state[t.name]["sum"], w.grad, lr=self.sparse_lr, eps=self.sparse_eps)
+                w.grad = None
+        self.dense_opt.step()
+        return losses
+
     # ---- one train step: fwd, bwd, row-wise sparse update "in backward", dense Adam
     def train_step(self, keys, values, lengths, labels) -> Tuple[torch.Tensor, torch.Tensor]:
         self.dense_opt.zero_grad(set_to_none=True)

@@ -1,0 +1,202 @@
+"""CPU, world_size 2, gloo: the host-side logic of table-wise / row-wise sharding -- routing,
+split sizes, the (source rank, feature) -> key-major permutation, output assembly, the reverse
+exchanges in backward, ShardedTensor state dicts.  The device work is replaced by the oracle
+(tests only): sharded(W=2) must equal the unsharded oracle on the same global batch."""
+import os
+import sys
+import traceback
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch import nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import oracle  # noqa: E402
+from oracle.ebc import TableSpec  # noqa: E402
+from oracle.kjt import block_bucketize_vectorized  # noqa: E402
+
+
+# ------------------------------------------------------------------ oracle-backed stand-ins for the CUDA work
+class _OracleLookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, keys, values, lengths, *weights):
+        ctx.mod, ctx.keys = mod, keys
+        ctx.save_for_backward(values, lengths)
+        return oracle.ebc_forward(mod.specs, [w.detach() for w in weights], keys, values, lengths)
+
+    @staticmethod
+    def backward(ctx, g):
+        values, lengths = ctx.saved_tensors
+        mod = ctx.mod
+        grads = oracle.ebc_dense_grads(mod.specs, ctx.keys, values, lengths, g)
+        for s, gr in zip(mod.specs, grads):  # "fused": row-wise Adagrad applied in backward
+            w = mod.embedding_bags[s.name].weight
+            oracle.rowwise_adagrad_dense(w.data, mod.state[s.name], gr, lr=w._optimizer_kwargs[0]["lr"])
+        return (None, None, None, None) + (None,) * len(mod.specs)
+
+
+class _Holder(nn.Module):
+    def __init__(self, rows, dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(rows, dim))
+
+
+class OracleLocalEbc(nn.Module):
+    def __init__(self, tables, device):
+        super().__init__()
+        import two_tower_recommender_model_b200 as tt
+        self.specs = [TableSpec(c.name, c.num_embeddings, c.embedding_dim, list(c.feature_names),
+                                "mean" if c.pooling == tt.PoolingType.MEAN else "sum") for c in tables]
+        self.embedding_bags = nn.ModuleDict({s.name: _Holder(s.num_embeddings, s.embedding_dim) for s in self.specs})
+        self.state = {s.name: torch.zeros(s.num_embeddings) for s in self.specs}
+        self._features = [f for s in self.specs for f in s.feature_names]
+        self._dims = [s.embedding_dim for s in self.specs for _ in s.feature_names]
+
+    def forward(self, kjt):
+        import two_tower_recommender_model_b200 as tt
+        w = [self.embedding_bags[s.name].weight for s in self.specs]
+        out = _OracleLookup.apply(self, list(kjt.keys()), kjt.values(), kjt.lengths(), *w)
+        return tt.KeyedTensor(self._features, self._dims, out)
+
+
+def oracle_bucketize(lengths, offsets, values, rows, F, B, W):
+    nl, nv, unb = block_bucketize_vectorized(lengths, values, rows.tolist(), W, B)
+    return nl, oracle.lengths_to_offsets(nl), nv, unb
+
+
+# ------------------------------------------------------------------ worker
+SPECS = [TableSpec("t_a", 40, 8, ["a"], "sum"), TableSpec("t_b", 30, 8, ["b1", "b2"], "sum"),
+         TableSpec("t_c", 101, 4, ["c"], "mean"), TableSpec("t_d", 7, 4, ["d"], "sum")]
+KEYS = ["c", "a", "b2", "d", "b1"]          # KJT key order differs from table order on purpose
+B, LR = 6, 0.1
+
+
+def _batch(rank):
+    from helpers import random_kjt
+    rows = {"a": 40, "b1": 30, "b2": 30, "c": 101, "d": 7}
+    return random_kjt(KEYS, [rows[k] for k in KEYS], B, 4, seed=100 + rank)
+
+
+def _worker(rank, world, port, errq):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import two_tower_recommender_model_b200 as tt
+        from torch.distributed.optim import _apply_optimizer_in_backward as apply_optimizer_in_backward
+        from torch.distributed._shard.sharded_tensor import ShardedTensor
+        from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
+
+        g = torch.Generator().manual_seed(7)
+        full = {s.name: torch.randn(s.num_embeddings, s.embedding_dim, generator=g) for s in SPECS}
+        cfgs = [tt.EmbeddingBagConfig(name=s.name, embedding_dim=s.embedding_dim, num_embeddings=s.num_embeddings,
+                                      feature_names=list(s.feature_names),
+                                      pooling=tt.PoolingType.MEAN if s.pooling == "mean" else tt.PoolingType.SUM) for s in SPECS]
+        ebc = tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("meta"))
+        apply_optimizer_in_backward(tt.RowWiseAdagrad, ebc.parameters(), {"lr": LR})
+        holder = nn.ModuleDict({"ebc": ebc})
+        planner = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world, compute_device="cpu"),
+                                              constraints={"t_c": ParameterConstraints(sharding_types=["row_wise"]),
+                                                           "t_d": ParameterConstraints(sharding_types=["row_wise"])})
+        plan = planner.collective_plan(holder, tt.get_default_sharders(), dist.GroupMember.WORLD)
+        p = plan.plan["ebc"]
+        assert p["t_a"].sharding_type == "table_wise" and p["t_b"].sharding_type == "table_wise"
+        assert {p["t_a"].ranks[0], p["t_b"].ranks[0]} == {0, 1}
+        assert p["t_c"].sharding_type == "row_wise" and p["t_c"].block_size == 51 and p["t_d"].block_size == 4
+        model = tt.DistributedModelParallel(module=holder, device=torch.device("cpu"), plan=plan,
+                                            sharding_kwargs=dict(local_ebc_factory=OracleLocalEbc, bucketize_fn=oracle_bucketize))
+        assert model._plan is plan and "t_c" in str(model._plan)
+        sharded = model.module["ebc"]
+        sharded.load_state_dict({f"embedding_bags.{k}.weight": v for k, v in full.items()})
+
+        # ---- forward: every rank's output == unsharded lookup of ITS batch
+        values, lengths = _batch(rank)
+        kjt = tt.KeyedJaggedTensor.from_lengths_sync(KEYS, values, lengths)
+        kt = sharded(kjt)
+        want = oracle.ebc_forward(SPECS, [full[s.name] for s in SPECS], KEYS, values, lengths)
+        assert kt.keys() == ["a", "b1", "b2", "c", "d"]
+        torch.testing.assert_close(kt.values(), want, rtol=1e-6, atol=1e-6)
+
+        # ---- backward: weights after the fused update == unsharded update with the GLOBAL batch's gradient
+        gout = torch.randn(B, want.shape[1], generator=torch.Generator().manual_seed(50 + rank))
+        (kt.values() * gout).sum().backward()
+        ref = {k: v.clone() for k, v in full.items()}
+        dense = [torch.zeros_like(ref[s.name]) for s in SPECS]
+        for r in range(world):
+            v_r, l_r = _batch(r)
+            g_r = torch.randn(B, want.shape[1], generator=torch.Generator().manual_seed(50 + r))
+            for acc, gr in zip(dense, oracle.ebc_dense_grads(SPECS, KEYS, v_r, l_r, g_r)):
+                acc += gr
+        for s, gr in zip(SPECS, dense):
+            oracle.rowwise_adagrad_dense(ref[s.name], torch.zeros(s.num_embeddings), gr, lr=LR)
+
+        # ---- state dict: ShardedTensor per table, gathered as utils/model_training.py:161-182 does
+        sd = model.state_dict()
+        assert set(sd) == {f"ebc.embedding_bags.{s.name}.weight" for s in SPECS}
+        for s in SPECS:
+            t = sd[f"ebc.embedding_bags.{s.name}.weight"]
+            assert isinstance(t, ShardedTensor) and tuple(t.size()) == (s.num_embeddings, s.embedding_dim)
+            full_t = torch.zeros(t.size()) if rank == 0 else None
+            t.gather(0, full_t)
+            if rank == 0:
+                torch.testing.assert_close(full_t, ref[s.name], rtol=1e-5, atol=1e-6, msg=lambda m: f"{s.name}: {m}")
+
+        # ---- the pipeline's prefetch hook produces the same result
+        v2, l2 = _batch(rank + 10)
+        kjt2 = tt.KeyedJaggedTensor.from_lengths_sync(KEYS, v2, l2)
+        batch = tt.Batch(torch.zeros(1), kjt2, torch.zeros(B, dtype=torch.int32))
+        model.start_sparse_data_dist(batch, None)
+        with torch.no_grad():
+            kt2 = sharded(kjt2)
+        cur = {}
+        for s in SPECS:
+            t = model.state_dict()[f"ebc.embedding_bags.{s.name}.weight"]
+            ft = torch.zeros(t.size())
+            outs = [torch.zeros(t.size()) for _ in range(world)] if False else None
+            t.gather(0, ft if rank == 0 else None)
+            lst = [ft]
+            dist.broadcast_object_list(lst, src=0)
+            cur[s.name] = lst[0]
+        want2 = oracle.ebc_forward(SPECS, [cur[s.name] for s in SPECS], KEYS, v2, l2)
+        torch.testing.assert_close(kt2.values(), want2, rtol=1e-5, atol=1e-6)
+
+        # ---- dense gradient sync: one all-reduce, mean over ranks
+        from two_tower_recommender_model_b200.distributed.sharding import DenseGradSync
+        lin = nn.Linear(3, 2)
+        sync = DenseGradSync(nn.ModuleDict({"l": lin}), None)
+        w0 = lin.weight.detach().clone()
+        lst = [w0]
+        dist.broadcast_object_list(lst, src=0)
+        assert torch.equal(lst[0], w0)  # broadcast from rank 0 made them identical
+        lin.weight.grad = torch.full_like(lin.weight, float(rank + 1))
+        lin.bias.grad = torch.full_like(lin.bias, float(10 * (rank + 1)))
+        sync.all_reduce()
+        assert torch.allclose(lin.weight.grad, torch.full_like(lin.weight, 1.5)) and torch.allclose(lin.bias.grad, torch.full_like(lin.bias, 15.0))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put(f"rank {rank}:\n{traceback.format_exc()}")
+        raise
+
+
+def test_sharded_equals_unsharded_world2_gloo():
+    ctx = mp.get_context("spawn")
+    errq = ctx.SimpleQueue()
+    port = 29600 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, errq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    msgs = []
+    while not errq.empty():
+        msgs.append(errq.get())
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+            msgs.append("worker hung")
+    assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)

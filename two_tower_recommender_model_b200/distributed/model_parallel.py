@@ -37,7 +37,8 @@ def _world(pg=None) -> Tuple[int, int]:
 class DistributedModelParallel(nn.Module):
     def __init__(self, module: nn.Module, env: Any = None, device: Optional[torch.device] = None,
                  plan: Optional[ShardingPlan] = None, sharders: Optional[List[Any]] = None,
-                 init_data_parallel: bool = True, init_parameters: bool = True, pg: Any = None) -> None:
+                 init_data_parallel: bool = True, init_parameters: bool = True, pg: Any = None,
+                 sharding_kwargs: Optional[Dict[str, Any]] = None) -> None:
         super().__init__()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._pg = pg
@@ -54,7 +55,7 @@ class DistributedModelParallel(nn.Module):
                     m.materialize(self.device)
         else:
             from .sharding import shard_embedding_modules
-            module = shard_embedding_modules(module, plan, self.device, pg)
+            module = shard_embedding_modules(module, plan, self.device, pg, **(sharding_kwargs or {}))
         # move everything that is not already placed (dense towers, buffers)
         for p in module.parameters():
             if p.device.type == "meta":

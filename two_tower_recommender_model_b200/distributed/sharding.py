@@ -1,0 +1,391 @@
+"""Model-parallel EmbeddingBagCollection: table-wise and row-wise sharding over the GPUs of one
+box (what ``DistributedModelParallel`` builds from the plan, /root/reference/03_model_training.py:798-815).
+
+Per step and per sharding group (TW tables, RW tables) the exchange is TorchRec's:
+
+  input_dist   ids travel to the rank that stores their rows
+               TW: feature f -> owner(table of f);   RW: id -> id // block (``block_bucketize``)
+               = all-to-all of per-destination counts (one tiny tensor, the only host sync),
+                 all-to-all of lengths, all-to-all of values, then ``permute_2D_sparse_data``
+                 from (source rank, feature) order to key-major over the GLOBAL batch
+  lookup       the local (unsharded) EmbeddingBagCollection over the global batch W*B
+  output_dist  TW: pooled rows go back to the sample's rank      -> all-to-all
+               RW: partial sums of every rank are added          -> reduce-scatter (mean divides after)
+  backward     the transposes: all-to-all / all-gather of grad, then the local fused
+               backward + row-wise optimizer (no dense gradient anywhere)
+
+Every peer is one NVSwitch hop away at full bandwidth, so the collectives are flat NCCL
+all-to-all / reduce-scatter on the kernels' own output buffers; there is no hierarchical
+(table-row-wise) stage.  Dense towers stay replicated; their gradients are summed by ONE
+all-reduce over the flat gradient buffer (``DenseGradSync``).
+
+The device work (local lookup, bucketize) is injected (``local_ebc_factory``, ``bucketize_fn``)
+so that the routing / split / permutation bookkeeping can be exercised on CPU with gloo in
+tests; the product defaults are the CUDA kernels and fail loudly without them.
+"""
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import torch
+from torch import distributed as dist
+from torch import nn
+
+from ..modules.embedding_configs import EmbeddingBagConfig, PoolingType
+from ..modules.embedding_modules import _TAG_ATTRS, EmbeddingBagCollection
+from ..sparse.jagged_tensor import KeyedJaggedTensor, KeyedTensor
+from .planner import ParameterSharding, ShardingPlan
+
+
+# --------------------------------------------------------------------------- differentiable collectives
+class _AllToAllRows(torch.autograd.Function):
+    """``all_to_all_single`` over flattened row blocks; backward is the reverse exchange."""
+
+    @staticmethod
+    def forward(ctx, x, in_splits, out_splits, pg):
+        ctx.pg, ctx.in_splits, ctx.out_splits = pg, in_splits, out_splits
+        out = x.new_empty(sum(out_splits))
+        dist.all_to_all_single(out, x.contiguous().view(-1), output_split_sizes=out_splits, input_split_sizes=in_splits, group=pg)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out = g.new_empty(sum(ctx.in_splits))
+        dist.all_to_all_single(out, g.contiguous().view(-1), output_split_sizes=ctx.in_splits, input_split_sizes=ctx.out_splits, group=ctx.pg)
+        return out, None, None, None
+
+
+class _ReduceScatterRows(torch.autograd.Function):
+    """[W*B, D] partial sums -> [B, D] (sum over ranks); backward all-gathers the gradient."""
+
+    @staticmethod
+    def forward(ctx, x, pg):
+        ctx.pg = pg
+        W = dist.get_world_size(pg)
+        out = x.new_empty(x.shape[0] // W, x.shape[1])
+        dist.reduce_scatter_tensor(out, x.contiguous(), group=pg)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        W = dist.get_world_size(ctx.pg)
+        out = g.new_empty(g.shape[0] * W, g.shape[1])
+        dist.all_gather_into_tensor(out, g.contiguous(), group=ctx.pg)
+        return out, None
+
+
+def _native_bucketize(lengths, offsets, values, num_rows, F, B, W):
+    from ..functional import block_bucketize
+    return block_bucketize(lengths, offsets, values, num_rows, F, B, W)
+
+
+def _default_local_ebc(tables: List[EmbeddingBagConfig], device: torch.device) -> nn.Module:
+    return EmbeddingBagCollection(tables=tables, device=device)
+
+
+class _Group:
+    """One sharding group (all TW tables, or all RW tables) of a sharded collection."""
+
+    def __init__(self, kind: str) -> None:
+        self.kind = kind
+        self.features: List[str] = []          # features of the group, in send order
+        self.feat_dim: Dict[str, int] = {}
+        self.feat_rows: Dict[str, int] = {}
+        self.dest_features: List[List[str]] = []  # per destination rank
+        self.local_ebc: Optional[nn.Module] = None
+        self.local_features: List[str] = []    # features this rank looks up, local EBC order
+        self.mean_features: List[str] = []     # RW features with mean pooling (divide after reduce-scatter)
+
+
+class ShardedEmbeddingBagCollection(nn.Module):
+    def __init__(self, ebc: EmbeddingBagCollection, plan: Dict[str, ParameterSharding], device: torch.device, pg: Any = None,
+                 local_ebc_factory: Callable[[List[EmbeddingBagConfig], torch.device], nn.Module] = _default_local_ebc,
+                 bucketize_fn: Callable = _native_bucketize) -> None:
+        super().__init__()
+        self._pg = pg
+        self._rank = dist.get_rank(pg)
+        self._world = dist.get_world_size(pg)
+        self._device = torch.device(device)
+        self._configs = ebc.embedding_bag_configs()
+        self._plan = plan
+        self._bucketize = bucketize_fn
+        self._out_features = ebc.feature_names()
+        self._out_dims = [c.embedding_dim for c in self._configs for _ in c.feature_names]
+        W, r = self._world, self._rank
+        tags = {c.name: {a: getattr(ebc.embedding_bags[c.name].weight, a) for a in _TAG_ATTRS
+                         if hasattr(ebc.embedding_bags[c.name].weight, a)} for c in self._configs}
+
+        self._tw, self._rw = _Group("table_wise"), _Group("row_wise")
+        self._tw.dest_features = [[] for _ in range(W)]
+        tw_local_cfgs: List[EmbeddingBagConfig] = []
+        rw_local_cfgs: List[EmbeddingBagConfig] = []
+        self._rw_block: Dict[str, int] = {}
+        self._shard_info: Dict[str, Tuple[str, int, int]] = {}   # table -> (kind, row offset, local rows)
+        for c in self._configs:
+            ps = plan[c.name]
+            if ps.sharding_type == "table_wise":
+                owner = ps.ranks[0]
+                for f in c.feature_names:
+                    self._tw.dest_features[owner].append(f)
+                    self._tw.feat_dim[f], self._tw.feat_rows[f] = c.embedding_dim, c.num_embeddings
+                if owner == r:
+                    tw_local_cfgs.append(EmbeddingBagConfig(name=c.name, embedding_dim=c.embedding_dim, num_embeddings=c.num_embeddings,
+                                                            feature_names=list(c.feature_names), pooling=c.pooling,
+                                                            weight_init_min=c.get_weight_init_min(), weight_init_max=c.get_weight_init_max()))
+                    self._shard_info[c.name] = ("table_wise", 0, c.num_embeddings)
+                else:
+                    self._shard_info[c.name] = ("table_wise", 0, 0)
+            elif ps.sharding_type == "row_wise":
+                block = ps.block_size or -(-c.num_embeddings // W)
+                self._rw_block[c.name] = block
+                local_rows = max(0, min(block, c.num_embeddings - r * block))
+                for f in c.feature_names:
+                    self._rw.features.append(f)
+                    self._rw.feat_dim[f], self._rw.feat_rows[f] = c.embedding_dim, c.num_embeddings
+                    if c.pooling == PoolingType.MEAN:
+                        self._rw.mean_features.append(f)
+                # local shard: SUM pooling (the mean divisor is applied after the reduce-scatter);
+                # at least one row so that the table exists on every rank
+                rw_local_cfgs.append(EmbeddingBagConfig(name=c.name, embedding_dim=c.embedding_dim, num_embeddings=max(local_rows, 1),
+                                                        feature_names=list(c.feature_names), pooling=PoolingType.SUM,
+                                                        weight_init_min=c.get_weight_init_min(), weight_init_max=c.get_weight_init_max()))
+                self._shard_info[c.name] = ("row_wise", r * block, local_rows)
+            else:
+                raise NotImplementedError(f"sharding type {ps.sharding_type}")
+        self._tw.features = [f for d in self._tw.dest_features for f in d]
+        self._tw.local_features = list(self._tw.dest_features[r])
+        self._rw.dest_features = [list(self._rw.features) for _ in range(W)]
+        self._rw.local_features = list(self._rw.features)
+        # The local collections are deliberately NOT registered as sub-modules: this module's
+        # state_dict / load_state_dict speak TorchRec's key names (one ShardedTensor per table).
+        tw_ebc = local_ebc_factory(tw_local_cfgs, self._device) if tw_local_cfgs else None
+        rw_ebc = local_ebc_factory(rw_local_cfgs, self._device) if rw_local_cfgs else None
+        object.__setattr__(self, "tw_ebc", tw_ebc)
+        object.__setattr__(self, "rw_ebc", rw_ebc)
+        self._tw.local_ebc, self._rw.local_ebc = tw_ebc, rw_ebc
+        for local in (tw_ebc, rw_ebc):
+            if local is None or not hasattr(local, "embedding_bags"):
+                continue
+            for name, bag in local.embedding_bags.items():
+                for a, v in tags.get(name, {}).items():
+                    setattr(bag.weight, a, v)
+        self._prefetched: Dict[int, Any] = {}
+
+    # ---- surface shared with EmbeddingBagCollection
+    def embedding_bag_configs(self) -> List[EmbeddingBagConfig]:
+        return self._configs
+
+    def feature_names(self) -> List[str]:
+        return list(self._out_features)
+
+    def shard_info(self) -> Dict[str, Tuple[str, int, int]]:
+        return dict(self._shard_info)
+
+    def local_parameters(self):
+        for local in (self.tw_ebc, self.rw_ebc):
+            if local is not None:
+                yield from local.parameters()
+
+    # ---- input dist ----------------------------------------------------------------------------
+    def _dist_group(self, grp: _Group, kjt: KeyedJaggedTensor):
+        """Returns the key-major KJT of this rank's features over the global batch (or None)."""
+        W, B, pg = self._world, kjt.stride(), self._pg
+        keys = kjt.keys()
+        if not grp.features:
+            return None
+        sub = kjt.permute([keys.index(f) for f in grp.features])
+        lengths, values = sub.lengths(), sub.values()
+        if grp.kind == "row_wise":
+            F = len(grp.features)
+            rows = torch.tensor([grp.feat_rows[f] for f in grp.features], dtype=torch.int64)
+            new_len, _new_off, new_val, _unb = self._bucketize(lengths, sub.offsets(), values, rows, F, B, W)
+            lengths, values = new_len, new_val
+            seg_per_dest = [F] * W
+        else:
+            seg_per_dest = [len(d) for d in grp.dest_features]
+        # per-destination value counts (device) -> exchange -> host (the one sync of the input dist)
+        seg_ends = [0]
+        for n in seg_per_dest:
+            seg_ends.append(seg_ends[-1] + n * B)
+        lens64 = lengths.to(torch.int64)
+        csum = torch.zeros(lens64.numel() + 1, dtype=torch.int64, device=lengths.device)
+        torch.cumsum(lens64, 0, out=csum[1:])
+        ends = csum[torch.tensor(seg_ends, device=lengths.device)]
+        send_counts = (ends[1:] - ends[:-1]).contiguous()
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=pg)
+        both = torch.stack([send_counts, recv_counts]).cpu()
+        send_v, recv_v = both[0].tolist(), both[1].tolist()
+        n_local = seg_per_dest[self._rank]
+        send_l = [n * B for n in seg_per_dest]
+        recv_l = [n_local * B] * W
+        lengths_recv = lengths.new_empty(sum(recv_l))
+        dist.all_to_all_single(lengths_recv, lengths.contiguous(), output_split_sizes=recv_l, input_split_sizes=send_l, group=pg)
+        values_recv = values.new_empty(sum(recv_v))
+        dist.all_to_all_single(values_recv, values[:sum(send_v)].contiguous(), output_split_sizes=recv_v, input_split_sizes=send_v, group=pg)
+        if n_local == 0:
+            return None
+        # (source rank, feature) segments -> key-major over the global batch
+        seg_keys = [f"{s}:{i}" for s in range(W) for i in range(n_local)]
+        recv = KeyedJaggedTensor(keys=seg_keys, values=values_recv, lengths=lengths_recv, stride=B)
+        recv._length_per_key = None
+        perm = [s * n_local + i for i in range(n_local) for s in range(W)]
+        if W > 1 or n_local > 1:
+            recv = self._permute_no_sync(recv, perm, sum(recv_v))
+        return KeyedJaggedTensor(keys=list(grp.local_features), values=recv.values(), lengths=recv.lengths(),
+                                 offsets=recv._offsets, stride=W * B)
+
+    @staticmethod
+    def _permute_no_sync(kjt: KeyedJaggedTensor, perm: List[int], total: int) -> KeyedJaggedTensor:
+        # KJT.permute needs length_per_key only to size the output; a true permutation keeps the total.
+        kjt._length_per_key = [0] * len(kjt.keys())
+        kjt._length_per_key[0] = total
+        if not kjt.values().is_cuda:
+            kjt._length_per_key = None  # CPU path slices by real per-key lengths
+        return kjt.permute(perm)
+
+    def input_dist(self, kjt: KeyedJaggedTensor):
+        return {"B": kjt.stride(), "lengths": kjt.lengths(), "keys": kjt.keys(),
+                "tw": self._dist_group(self._tw, kjt), "rw": self._dist_group(self._rw, kjt)}
+
+    def prefetch_input_dist(self, batch, ready_event=None) -> None:
+        """Called by TrainPipelineSparseDist one batch ahead: issues the KJT exchange early."""
+        kjt = batch.sparse_features
+        if ready_event is not None and kjt.values().is_cuda:
+            torch.cuda.current_stream(kjt.values().device).wait_event(ready_event)
+        self._prefetched[id(kjt)] = self.input_dist(kjt)
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self, features: KeyedJaggedTensor) -> KeyedTensor:
+        ctx = self._prefetched.pop(id(features), None) or self.input_dist(features)
+        W, B, pg = self._world, ctx["B"], self._pg
+        cols: Dict[str, torch.Tensor] = {}
+        # table-wise: lookup over the global batch, rows go home by all-to-all
+        d_by_rank = [sum(self._tw.feat_dim[f] for f in d) for d in self._tw.dest_features]
+        if self._tw.features:
+            d_loc = d_by_rank[self._rank]
+            if ctx["tw"] is not None:
+                pooled = self.tw_ebc(ctx["tw"]).values()            # [W*B, d_loc]
+                flat = pooled.reshape(-1)
+            else:
+                # no table of this group lives here; still take part in the exchange, and in its
+                # backward (requires_grad keeps the reverse all-to-all in this rank's autograd graph)
+                flat = torch.zeros(0, dtype=torch.float32, device=self._device, requires_grad=torch.is_grad_enabled())
+            recv = _AllToAllRows.apply(flat, [B * d_loc] * W, [B * d for d in d_by_rank], pg)
+            off = 0
+            for r in range(W):
+                if d_by_rank[r] == 0:
+                    continue
+                blk = recv[off:off + B * d_by_rank[r]].view(B, d_by_rank[r])
+                off += B * d_by_rank[r]
+                c0 = 0
+                for f in self._tw.dest_features[r]:
+                    cols[f] = blk[:, c0:c0 + self._tw.feat_dim[f]]
+                    c0 += self._tw.feat_dim[f]
+        # row-wise: partial pools over the global batch, summed by reduce-scatter
+        if self._rw.features:
+            part = self.rw_ebc(ctx["rw"]).values()                  # [W*B, sum D_rw]
+            pooled = _ReduceScatterRows.apply(part, pg)             # [B, sum D_rw]
+            c0 = 0
+            keys = ctx["keys"]
+            for f in self._rw.features:
+                d = self._rw.feat_dim[f]
+                col = pooled[:, c0:c0 + d]
+                if f in self._rw.mean_features:
+                    k = keys.index(f)
+                    ln = ctx["lengths"][k * B:(k + 1) * B].to(col.dtype).clamp(min=1.0)
+                    col = col / ln.unsqueeze(1)
+                cols[f] = col
+                c0 += d
+        values = torch.cat([cols[f] for f in self._out_features], dim=1)
+        return KeyedTensor(keys=self._out_features, length_per_key=self._out_dims, values=values)
+
+    # ---- checkpoint surface: ShardedTensor entries named like the unsharded module --------------
+    def _local_weight(self, name: str) -> Optional[torch.Tensor]:
+        kind, _off, rows = self._shard_info[name]
+        if rows == 0:
+            return None
+        local = self.tw_ebc if kind == "table_wise" else self.rw_ebc
+        return local.embedding_bags[name].weight.detach()[:rows]
+
+    def state_dict(self, *args, destination=None, prefix: str = "", keep_vars: bool = False):
+        from .sharded_tensor import make_row_sharded
+        destination = {} if destination is None else destination
+        for c in self._configs:
+            _kind, off, _rows = self._shard_info[c.name]
+            destination[f"{prefix}embedding_bags.{c.name}.weight"] = make_row_sharded(
+                self._local_weight(c.name), off, (c.num_embeddings, c.embedding_dim), self._pg)
+        return destination
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        """Accepts FULL (unsharded) tensors under the TorchRec key names and keeps this rank's rows."""
+        for c in self._configs:
+            key = f"{prefix}embedding_bags.{c.name}.weight"
+            if key not in state_dict:
+                if strict:
+                    missing_keys.append(key)
+                continue
+            full = state_dict[key]
+            w = self._local_weight(c.name)
+            if w is not None:
+                _kind, off, rows = self._shard_info[c.name]
+                with torch.no_grad():
+                    w.copy_(full[off:off + rows].to(w.device))
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        missing: List[str] = []
+        self._load_from_state_dict(state_dict, "", {}, strict, missing, [], [])
+        if strict and missing:
+            raise RuntimeError(f"missing keys {missing}")
+        return torch.nn.modules.module._IncompatibleKeys(missing, [])
+
+
+def shard_embedding_modules(module: nn.Module, plan: ShardingPlan, device: torch.device, pg: Any = None, **kw) -> nn.Module:
+    """Replaces every EmbeddingBagCollection under ``module`` by its sharded form, in place."""
+    targets = [(path, m) for path, m in module.named_modules() if isinstance(m, EmbeddingBagCollection)]
+    for path, ebc in targets:
+        table_plan = plan.get_plan_for_module(path)
+        if table_plan is None:
+            raise RuntimeError(f"no sharding plan for module '{path}'")
+        sharded = ShardedEmbeddingBagCollection(ebc, table_plan, device, pg, **kw)
+        if path == "":
+            return sharded
+        parent = module
+        parts = path.split(".")
+        for p in parts[:-1]:
+            parent = getattr(parent, p)
+        setattr(parent, parts[-1], sharded)
+    return module
+
+
+class DenseGradSync:
+    """Data-parallel towers: gradients of every non-embedding parameter are averaged across ranks with
+    one all-reduce.  When the dense optimizer is ``FlatAdam`` the gradients already live in one flat
+    buffer; otherwise they are flattened into a staging buffer and copied back."""
+
+    def __init__(self, module: nn.Module, pg: Any = None) -> None:
+        self._pg = pg
+        self._params = [p for n, p in module.named_parameters() if "embedding_bags" not in n]
+        self._flat: Optional[torch.Tensor] = None
+        # identical initial dense weights on every rank
+        for p in self._params:
+            dist.broadcast(p.data, src=0, group=pg)
+
+    def all_reduce(self) -> None:
+        W = dist.get_world_size(self._pg)
+        grads = [p.grad for p in self._params if p.grad is not None]
+        if not grads:
+            return
+        base = grads[0].untyped_storage()
+        same = all(g.untyped_storage().data_ptr() == base.data_ptr() for g in grads)
+        if same:  # FlatAdam: one contiguous buffer already
+            flat = torch.empty(0, dtype=grads[0].dtype, device=grads[0].device).set_(base, 0, (base.nbytes() // 4,))
+            dist.all_reduce(flat, group=self._pg)
+            flat.div_(W)
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, group=self._pg)
+        flat.div_(W)
+        off = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
