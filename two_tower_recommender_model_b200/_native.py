@@ -18,7 +18,8 @@ TT_ABI_VERSION = 1
 POOL_SUM, POOL_MEAN = 0, 1
 OPT_DENSE_GRAD, OPT_ROWWISE_ADAGRAD, OPT_ROWWISE_ADAM, OPT_SGD = 0, 1, 2, 3
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtt_b200.so")
+# TT_B200_LIB selects another build of the SAME library (kernel A/B experiments); there is still no fallback.
+_LIB_PATH = os.environ.get("TT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtt_b200.so")
 
 
 class NativeLibraryError(RuntimeError):

@@ -1,9 +1,10 @@
 // In-batch softmax on the tensor cores: the [B, B] logits S = Q C^T live only in TMEM.
 //
 //   forward : CTA = 128 query rows (Q tile resident in smem).  C streams through a TMA ring
-//             in NT-row tiles; tcgen05.mma writes S tiles into a 2-stage TMEM accumulator.
-//             Two softmax warpgroups ping-pong: group g owns TMEM stage g and the tiles
-//             t = g (mod 2); inside a group thread = row, one warp per TMEM lane quarter.
+//             in 128-row tiles; tcgen05.mma writes S tiles into a FOUR-stage TMEM accumulator
+//             (4 x 128 columns = all of TMEM), so the MMA issuer runs up to four tiles ahead.
+//             Two softmax warpgroups ping-pong: group g takes the tiles t = g (mod 2), i.e. TMEM
+//             stages g and g+2; inside a group thread = row, one warp per TMEM lane quarter.
 //             Each runs an online log-sum-exp in the log2 domain; the two partial (max, sum)
 //             pairs of a row are merged at the end.  Output: lse[B] + per-CTA loss partials.
 //   backward: "fixed-normaliser attention".  out[r,:] = scale * (sum_t P(r,t) Y_t - Y_r),
@@ -33,6 +34,36 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA/ALU pipes (Cody-Waite split + minimax polynomial, x <= ~0): the softmax loops
+// are bound by the 16-per-clock MUFU pipe, so a fixed fraction of the exponentials is computed
+// here instead (the FlashAttention-4 trick).  DEG 3: max rel. error 1.0e-4 (below the bf16
+// rounding P gets anyway); DEG 4: 2.8e-6 (forward log-sum-exp).
+template <int DEG>
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                 // 1.5 * 2^23: low mantissa bits = round(x)
+  const float f = x - (t - 12582912.f);           // in [-0.5, 0.5]
+  float p;
+  if (DEG == 3) p = fmaf(fmaf(fmaf(0.05500893f, f, 0.24221095f), f, 0.6932829f), f, 1.0f);
+  else p = fmaf(fmaf(fmaf(fmaf(0.009582853f, f, 0.055906426f), f, 0.24024099f), f, 0.69312418f), f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // * 2^round(x)
+}
+// which of every 8 consecutive elements go to the polynomial: N8 of 8
+template <int N8>
+__device__ __forceinline__ constexpr bool use_poly(int j) {
+  return N8 >= 3 ? ((j & 7) == 2 || (j & 7) == 5 || (j & 7) == 7) : N8 == 2 ? ((j & 7) == 3 || (j & 7) == 7) : N8 == 1 ? (j & 7) == 7 : false;
+}
+#ifndef TT_POLY_FWD
+#define TT_POLY_FWD 2
+#endif
+#ifndef TT_POLY_BWD
+#define TT_POLY_BWD 1
+#endif
+#ifndef TT_MMA_SLEEP_NS
+#define TT_MMA_SLEEP_NS 64
+#endif
+constexpr int kPolyFwd = TT_POLY_FWD, kPolyBwd = TT_POLY_BWD;
+
 __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
   float a[16];
 #pragma unroll
@@ -58,7 +89,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
-    __nanosleep(64);
+    if (TT_MMA_SLEEP_NS > 0) __nanosleep(TT_MMA_SLEEP_NS);
   }
   printf("tt_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
   __trap();
@@ -67,8 +98,9 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 // ------------------------------------------------------------------ forward
 template <int KB>
 struct FwdCfg {
-  static constexpr int NT = KB <= 2 ? 256 : 128;
-  static constexpr int STAGES = KB == 1 ? 4 : 2;
+  static constexpr int NT = KB <= 2 ? 256 : 128;        // C rows (logit columns) per tile
+  static constexpr int NACC = 512 / NT;                 // TMEM accumulator stages (NACC x NT = 512 columns)
+  static constexpr int STAGES = KB == 1 ? 4 : (KB == 3 ? 3 : 2);
   static constexpr int Q_BYTES = KB * 128 * 128;       // KB sub-tiles of [128 x 64] bf16
   static constexpr int C_BYTES = KB * NT * 128;        // KB sub-tiles of [NT x 64] bf16
   static constexpr int SMEM = Q_BYTES + STAGES * C_BYTES + 1024 + 256 + 1024;  // + merge scratch [128][2]
@@ -91,10 +123,12 @@ __device__ __forceinline__ void lse_chunk(const uint32_t (&v)[32], int col0, int
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    float e0 = ex2(fmaf(__uint_as_float(v[j]), scale2, -mn));
-    float e1 = ex2(fmaf(__uint_as_float(v[j + 1]), scale2, -mn));
-    float e2 = ex2(fmaf(__uint_as_float(v[j + 2]), scale2, -mn));
-    float e3 = ex2(fmaf(__uint_as_float(v[j + 3]), scale2, -mn));
+    const float x0 = fmaf(__uint_as_float(v[j]), scale2, -mn), x1 = fmaf(__uint_as_float(v[j + 1]), scale2, -mn);
+    const float x2 = fmaf(__uint_as_float(v[j + 2]), scale2, -mn), x3 = fmaf(__uint_as_float(v[j + 3]), scale2, -mn);
+    float e0 = use_poly<kPolyFwd>(j) ? ex2_poly<4>(x0) : ex2(x0);
+    float e1 = use_poly<kPolyFwd>(j + 1) ? ex2_poly<4>(x1) : ex2(x1);
+    float e2 = use_poly<kPolyFwd>(j + 2) ? ex2_poly<4>(x2) : ex2(x2);
+    float e3 = use_poly<kPolyFwd>(j + 3) ? ex2_poly<4>(x3) : ex2(x3);
     if (TAIL) {
       e0 = (col0 + j < B) ? e0 : 0.f;
       e1 = (col0 + j + 1 < B) ? e1 : 0.f;
@@ -111,7 +145,10 @@ template <int KB>
 __global__ void __launch_bounds__(kLgThreads, 1)
 tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, int B,
                       float scale2, const float* __restrict__ diag, float* __restrict__ lse,
-                      float* __restrict__ partial_loss) {
+                      float* __restrict__ partial_loss, float* __restrict__ ml_out) {
+  // gridDim.y > 1: the logit columns are split between gridDim.y CTAs per row block (so that the
+  // grid is ~7 waves of 148 instead of 3.46); each writes its (max, sum) pair to ml_out and
+  // lse_merge_kernel finishes the job.
   using Cfg = FwdCfg<KB>;
   constexpr int NT = Cfg::NT, S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -122,21 +159,24 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* q_full = bars;
   uint64_t* c_full = bars + 1;            // [S]
   uint64_t* c_empty = c_full + S;         // [S]
-  uint64_t* acc_full = c_empty + S;       // [2]
-  uint64_t* acc_empty = acc_full + 2;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_full = c_empty + S;       // [NACC]
+  uint64_t* acc_empty = acc_full + Cfg::NACC;   // [NACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::NACC);
   float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
-  const int T = (B + NT - 1) / NT;
+  const int Tall = (B + NT - 1) / NT;
+  const int Tper = (Tall + gridDim.y - 1) / gridDim.y;
+  const int t0 = blockIdx.y * Tper;                       // first tile of this CTA
+  const int T = max(0, min(Tper, Tall - t0));             // tiles of this CTA (local index t)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmC);
     mbar_init(q_full, 1);
     for (int s = 0; s < S; ++s) { mbar_init(&c_full[s], 1); mbar_init(&c_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < Cfg::NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -154,7 +194,7 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_wait_relaxed(&c_empty[s], ((t / S) & 1) ^ 1);
         mbar_expect_tx(&c_full[s], Cfg::C_BYTES);
         for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(sC + s * Cfg::C_BYTES + kb * NT * 128, &tmC, &c_full[s], kb * 64, t * NT);
+          tma_load_2d(sC + s * Cfg::C_BYTES + kb * NT * 128, &tmC, &c_full[s], kb * 64, (t0 + t) * NT);
       }
     }
   } else if (warp == 1) {
@@ -162,8 +202,8 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (elect_one()) {
       mbar_wait_relaxed(q_full, 0);
       for (int t = 0; t < T; ++t) {
-        const int s = t % S, as = t & 1;
-        mbar_wait_relaxed(&acc_empty[as], ((t >> 1) & 1) ^ 1);
+        const int s = t % S, as = t % Cfg::NACC;
+        mbar_wait_relaxed(&acc_empty[as], ((t / Cfg::NACC) & 1) ^ 1);
         mbar_wait_relaxed(&c_full[s], (t / S) & 1);
         tc_fence_after();
 #pragma unroll
@@ -182,12 +222,14 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int g = (warp - 2) >> 2;                  // softmax group = TMEM stage it owns
     const int r_in = q * 32 + lane;
     const int row = m0 + r_in;
-    const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * NT;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float m = -INFINITY, l = 0.f;                   // running max / sum, log2 domain
     for (int t = g; t < T; t += 2) {
-      mbar_wait(&acc_full[g], (t >> 1) & 1);
+      const int as = t % Cfg::NACC;
+      const uint32_t tcol = trow + as * NT;
+      mbar_wait(&acc_full[as], (t / Cfg::NACC) & 1);
       tc_fence_after();
-      const int n0 = t * NT;
+      const int n0 = (t0 + t) * NT;
       const bool tail = n0 + NT > B;
       uint32_t va[32], vb[32];
       tmem_ld32(tcol, va);
@@ -201,7 +243,7 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (!tail) lse_chunk<false>(vb, n0 + c0 + 32, B, scale2, m, l); else lse_chunk<true>(vb, n0 + c0 + 32, B, scale2, m, l);
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[g]);
+      mbar_arrive(&acc_empty[as]);
     }
     // merge the two groups' partial (max, sum) of every row, then this CTA's loss partial
     float* mrg = reinterpret_cast<float*>(bars + 32);  // [128][2], own scratch (the C ring may still be in use)
@@ -213,15 +255,20 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const float lt = l * ex2(m - mn) + ((m1 == -INFINITY) ? 0.f : l1 * ex2(m1 - mn));
       float contrib = 0.f;
       if (row < B) {
-        const float L = (mn + log2f(lt)) * kLn2;
-        lse[row] = L;
-        contrib = L - diag[row];
+        if (gridDim.y == 1) {
+          const float L = (mn + log2f(lt)) * kLn2;
+          lse[row] = L;
+          contrib = L - diag[row];
+        } else {
+          ml_out[((int64_t)blockIdx.y * B + row) * 2] = mn;
+          ml_out[((int64_t)blockIdx.y * B + row) * 2 + 1] = lt;
+        }
       }
       contrib = warp_sum(contrib);
       if (lane == 0) red[q] = contrib;
     }
     all_softmax_bar_sync();
-    if (warp == 2 && lane == 0) partial_loss[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
+    if (warp == 2 && lane == 0 && gridDim.y == 1) partial_loss[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
     tc_fence_before();
   }
   __syncthreads();
@@ -235,15 +282,19 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 template <int KB>
 struct BwdCfg {
   static constexpr int D = KB * 64;
-  static constexpr int NT = KB <= 2 ? 128 : 64;          // Y rows per tile
+  static constexpr int NT = KB <= 2 ? 128 : 64;          // Y rows per tile = S/P columns per TMEM stage
+  static constexpr int NSP = KB <= 2 ? 3 : 4;            // TMEM S/P stages: columns [NT*a, NT*a + NT)
   static constexpr int NKB2 = NT / 64;                   // K blocks of the second GEMM
   static constexpr int STAGES = KB == 1 ? 4 : 2;
+  static constexpr int LA0 = NSP - 1;                    // S tiles issued ahead of the P they wait for:
+  static constexpr int LOOKAHEAD = STAGES - 1 < LA0 ? STAGES - 1 : LA0;   // bounded by TMEM and smem stages
   static constexpr int X_BYTES = KB * 128 * 128;
   static constexpr int Y_BYTES = KB * NT * 128;          // KB sub-tiles [NT x 64]  (GEMM1 B operand)
   static constexpr int YT_BYTES = NKB2 * D * 128;        // NKB2 sub-tiles [D x 64] (GEMM2 B operand)
   static constexpr int STAGE_BYTES = Y_BYTES + YT_BYTES;
   static constexpr int SMEM = X_BYTES + STAGES * STAGE_BYTES + 1024 + 256 + 2 * 128 * 4;
-  static constexpr int O_COL = 256;                      // O accumulator columns [256, 256 + D)
+  static constexpr int O_COL = NSP * NT;                 // O accumulator columns [O_COL, O_COL + D) (<= 512)
+  static_assert(O_COL + D <= 512, "TMEM budget");
 };
 
 // one 32-column chunk of S -> P (bf16 pairs), written back over S in TMEM
@@ -258,10 +309,12 @@ __device__ __forceinline__ void p_chunk(const uint32_t (&v)[32], uint32_t tdst, 
       const float4 lv = *reinterpret_cast<const float4*>(lse_cols + j);
       l0 = lv.x; l1 = lv.y; l2 = lv.z; l3 = lv.w;
     }
-    float p0 = ex2(fmaf(__uint_as_float(v[j]), scale2, -l0));
-    float p1 = ex2(fmaf(__uint_as_float(v[j + 1]), scale2, -l1));
-    float p2 = ex2(fmaf(__uint_as_float(v[j + 2]), scale2, -l2));
-    float p3 = ex2(fmaf(__uint_as_float(v[j + 3]), scale2, -l3));
+    const float x0 = fmaf(__uint_as_float(v[j]), scale2, -l0), x1 = fmaf(__uint_as_float(v[j + 1]), scale2, -l1);
+    const float x2 = fmaf(__uint_as_float(v[j + 2]), scale2, -l2), x3 = fmaf(__uint_as_float(v[j + 3]), scale2, -l3);
+    float p0 = use_poly<kPolyBwd>(j) ? ex2_poly<3>(x0) : ex2(x0);
+    float p1 = use_poly<kPolyBwd>(j + 1) ? ex2_poly<3>(x1) : ex2(x1);
+    float p2 = use_poly<kPolyBwd>(j + 2) ? ex2_poly<3>(x2) : ex2(x2);
+    float p3 = use_poly<kPolyBwd>(j + 3) ? ex2_poly<3>(x3) : ex2(x3);
     if (TAIL) {
       p0 = (col0 + j < B) ? p0 : 0.f;
       p1 = (col0 + j + 1 < B) ? p1 : 0.f;
@@ -291,15 +344,18 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   uint64_t* x_full = bars;
   uint64_t* y_full = bars + 1;           // [S]
   uint64_t* y_empty = y_full + S;        // [S]
-  uint64_t* s_full = y_empty + S;        // [2]
-  uint64_t* p_full = s_full + 2;         // [2]
-  uint64_t* o_full = p_full + 2;
+  uint64_t* s_full = y_empty + S;        // [NSP]
+  uint64_t* p_full = s_full + Cfg::NSP;  // [NSP]
+  uint64_t* o_full = p_full + Cfg::NSP;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
   float* lse_tile = reinterpret_cast<float*>(bars + 32);      // [2][128], 16-byte aligned (float4 reads)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
-  const int T = (B + NT - 1) / NT;
+  const int Tall = (B + NT - 1) / NT;
+  const int Tper = (Tall + gridDim.y - 1) / gridDim.y;
+  const int t0 = blockIdx.y * Tper;                       // column split: see the forward kernel
+  const int T = max(0, min(Tper, Tall - t0));             // the host guarantees T >= 1
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX);
@@ -307,7 +363,7 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     prefetch_tmap(&tmYt);
     mbar_init(x_full, 1);
     for (int s = 0; s < S; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); }
+    for (int s = 0; s < Cfg::NSP; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); }
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -326,9 +382,9 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         uint8_t* st = sY + s * Cfg::STAGE_BYTES;
         mbar_wait_relaxed(&y_empty[s], ((t / S) & 1) ^ 1);
         mbar_expect_tx(&y_full[s], Cfg::STAGE_BYTES);
-        for (int kb = 0; kb < KB; ++kb) tma_load_2d(st + kb * NT * 128, &tmY, &y_full[s], kb * 64, t * NT);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(st + kb * NT * 128, &tmY, &y_full[s], kb * 64, (t0 + t) * NT);
         for (int k2 = 0; k2 < Cfg::NKB2; ++k2)
-          tma_load_2d(st + Cfg::Y_BYTES + k2 * D * 128, &tmYt, &y_full[s], t * NT + k2 * 64, 0);
+          tma_load_2d(st + Cfg::Y_BYTES + k2 * D * 128, &tmYt, &y_full[s], (t0 + t) * NT + k2 * 64, 0);
       }
     }
   } else if (warp == 1) {
@@ -336,7 +392,7 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     constexpr uint32_t idesc2 = idesc_bf16_f32(128, D);
     if (elect_one()) {
       auto issue_gemm1 = [&](int t) {
-        const int s = t % S, as = t & 1;
+        const int s = t % S, as = t % Cfg::NSP;
         mbar_wait_relaxed(&y_full[s], (t / S) & 1);
         tc_fence_after();
         uint8_t* st = sY + s * Cfg::STAGE_BYTES;
@@ -345,19 +401,19 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           const uint64_t da = smem_desc_k_sw128(smem_u32(sX + kb * 128 * 128));
           const uint64_t db = smem_desc_k_sw128(smem_u32(st + kb * NT * 128));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_ss(tmem_base + as * 128, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) mma_ss(tmem_base + as * NT, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
         }
         tc_commit(&s_full[as]);
       };
       mbar_wait_relaxed(x_full, 0);
-      issue_gemm1(0);
+      for (int i = 0; i < Cfg::LOOKAHEAD && i < T; ++i) issue_gemm1(i);
       for (int t = 0; t < T; ++t) {
-        const int s = t % S, as = t & 1;
-        // S(t+1) goes to the other TMEM stage: the tensor core computes it while softmax group
-        // `as` turns S(t) into P(t).  Stage (t+1)&1 is free: MMA2(t-1) was issued before this
-        // point and tcgen05.mma executes in issue order.
-        if (t + 1 < T) issue_gemm1(t + 1);
-        mbar_wait_relaxed(&p_full[as], (t >> 1) & 1);
+        const int s = t % S, as = t % Cfg::NSP;
+        // S tiles run LOOKAHEAD ahead of the P tile awaited below, so a softmax group always finds
+        // its next S ready.  TMEM stage (t+LOOKAHEAD)%NSP is free: the last P that lived there was
+        // consumed by an MMA2 issued earlier, and tcgen05.mma executes in issue order.
+        if (t + Cfg::LOOKAHEAD < T) issue_gemm1(t + Cfg::LOOKAHEAD);
+        mbar_wait_relaxed(&p_full[as], (t / Cfg::NSP) & 1);
         tc_fence_after();
         uint8_t* yt = sY + s * Cfg::STAGE_BYTES + Cfg::Y_BYTES;
 #pragma unroll
@@ -365,7 +421,7 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           const uint64_t db = smem_desc_k_sw128(smem_u32(yt + k2 * D * 128));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            mma_ts(tmem_base + Cfg::O_COL, tmem_base + as * 128 + (k2 * 4 + k) * 8, db + 2 * k, idesc2,
+            mma_ts(tmem_base + Cfg::O_COL, tmem_base + as * NT + (k2 * 4 + k) * 8, db + 2 * k, idesc2,
                    (t | k2 | k) != 0);
         }
         tc_commit(&y_empty[s]);
@@ -378,16 +434,17 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int r_in = q * 32 + lane;
     const int row = m0 + r_in;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t tsp = trow + g * 128;
     const float lrow = (ROW && row < B) ? lse[row] * kLog2e : 0.f;
     float* lse_g = lse_tile + g * 128;
     for (int t = g; t < T; t += 2) {
-      const int n0 = t * NT;
+      const int n0 = (t0 + t) * NT;
+      const int as = t % Cfg::NSP;
+      const uint32_t tsp = trow + as * NT;
       if (!ROW) {
         if (r_in < NT) lse_g[r_in] = (n0 + r_in < B) ? lse[n0 + r_in] * kLog2e : 0.f;
         group_bar_sync(g);
       }
-      mbar_wait(&s_full[g], (t >> 1) & 1);
+      mbar_wait(&s_full[as], (t / Cfg::NSP) & 1);
       tc_fence_after();
       const bool tail = n0 + NT > B;
       // P (bf16) overwrites S (fp32) in place.  P chunk c lands on S columns [16c, 16c+16), which
@@ -407,7 +464,7 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[g]);
+      mbar_arrive(&p_full[as]);
       if (!ROW) group_bar_sync(g);   // lse_g is rewritten at the top of the next iteration
     }
     // ---- O -> out = out_scale * (O - Y_r), optionally gated by relu_mask > 0 (groups alternate chunks)
@@ -423,9 +480,12 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         for (int j = 0; j < 32; ++j) {
           const int col = c0 + j;
           if (col < d) {
-            float o = out_scale * (__uint_as_float(v[j]) - yf[(int64_t)row * ld_yf + col]);
+            float o = __uint_as_float(v[j]);
+            if (blockIdx.y == 0) o -= yf[(int64_t)row * ld_yf + col];
+            o *= out_scale;
             if (relu_mask != nullptr && !(relu_mask[(int64_t)row * ld_mask + col] > 0.f)) o = 0.f;
-            out[(int64_t)row * ld_out + col] = o;
+            if (gridDim.y == 1) out[(int64_t)row * ld_out + col] = o;
+            else atomicAdd(&out[(int64_t)row * ld_out + col], o);   // two addends: order-independent
           }
         }
       }
@@ -466,9 +526,45 @@ loss_final_kernel(const float* __restrict__ partial, int n, float scale, float* 
   }
 }
 
+// column-split forward: combine the per-split (max, sum) pairs of a row; block loss partials
+__global__ void __launch_bounds__(256)
+lse_merge_kernel(const float* __restrict__ ml, int splits, int B, const float* __restrict__ diag,
+                 float* __restrict__ lse, float* __restrict__ partial_loss) {
+  __shared__ float red[8];
+  const int row = blockIdx.x * 256 + threadIdx.x;
+  float contrib = 0.f;
+  if (row < B) {
+    float m = -INFINITY, l = 0.f;
+    for (int sp = 0; sp < splits; ++sp) {
+      const float mi = ml[((int64_t)sp * B + row) * 2], li = ml[((int64_t)sp * B + row) * 2 + 1];
+      const float mn = fmaxf(m, mi);
+      l = ((m == -INFINITY) ? 0.f : l * exp2f(m - mn)) + ((mi == -INFINITY) ? 0.f : li * exp2f(mi - mn));
+      m = mn;
+    }
+    const float L = (m + log2f(l)) * kLn2;
+    lse[row] = L;
+    contrib = L - diag[row];
+  }
+  contrib = warp_sum(contrib);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    partial_loss[blockIdx.x] = t;
+  }
+}
+
+// Two column splits once there are at least two tiles per split and enough row blocks to matter.
+static int column_splits(int64_t B, int NT) {
+  const int64_t tall = (B + NT - 1) / NT;
+  return (tall >= 4 && B >= 2048) ? 2 : 1;
+}
+
 template <int KB>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tcm, int B, float scale2, const float* diag, float* lse,
-                      float* partial, cudaStream_t s) {
+                      float* partial, float* ml, int splits, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(tc_softmax_fwd_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -476,7 +572,8 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tcm, int B, floa
     if (e != cudaSuccess) return fail(TT_ERR_CUDA, "softmax_fwd smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  tc_softmax_fwd_kernel<KB><<<(B + 127) / 128, kLgThreads, FwdCfg<KB>::SMEM, s>>>(tq, tcm, B, scale2, diag, lse, partial);
+  dim3 grid((B + 127) / 128, splits);
+  tc_softmax_fwd_kernel<KB><<<grid, kLgThreads, FwdCfg<KB>::SMEM, s>>>(tq, tcm, B, scale2, diag, lse, partial, ml);
   TT_CHECK_LAUNCH("tc_softmax_fwd");
   return TT_OK;
 }
@@ -484,7 +581,7 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tcm, int B, floa
 template <int KB, bool ROW>
 static int launch_bwd(const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tyt, int B, int d, float scale2,
                       const float* lse, const float* yf, int64_t ld_yf, const float* mask, int64_t ld_mask,
-                      float out_scale, float* out, int64_t ld_out, cudaStream_t s) {
+                      float out_scale, float* out, int64_t ld_out, int splits, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(tc_softmax_bwd_kernel<KB, ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -492,7 +589,12 @@ static int launch_bwd(const CUtensorMap& tx, const CUtensorMap& ty, const CUtens
     if (e != cudaSuccess) return fail(TT_ERR_CUDA, "softmax_bwd smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  tc_softmax_bwd_kernel<KB, ROW><<<(B + 127) / 128, kLgThreads, BwdCfg<KB>::SMEM, s>>>(
+  if (splits > 1) {  // the splits accumulate into `out`
+    cudaError_t e = cudaMemset2DAsync(out, (size_t)ld_out * 4, 0, (size_t)d * 4, (size_t)B, s);
+    if (e != cudaSuccess) return fail(TT_ERR_CUDA, "softmax_bwd memset: %s", cudaGetErrorString(e));
+  }
+  dim3 grid((B + 127) / 128, splits);
+  tc_softmax_bwd_kernel<KB, ROW><<<grid, kLgThreads, BwdCfg<KB>::SMEM, s>>>(
       tx, ty, tyt, B, d, scale2, lse, yf, ld_yf, mask, ld_mask, out_scale, out, ld_out);
   TT_CHECK_LAUNCH("tc_softmax_bwd");
   return TT_OK;
@@ -506,7 +608,9 @@ using namespace tt::tc;
 
 extern "C" {
 
-size_t tt_inbatch_softmax_bf16_workspace_bytes(int64_t B) { return align_up((size_t)((B + 127) / 128 + 1) * 4, 256); }
+size_t tt_inbatch_softmax_bf16_workspace_bytes(int64_t B) {
+  return align_up((size_t)((B + 127) / 128 + 1) * 4, 256) + align_up((size_t)B * 2 * 2 * 4, 256) + 256;
+}
 
 int tt_inbatch_softmax_forward_bf16(const void* q_bf16, int64_t ldq, const void* c_bf16, int64_t ldc, int64_t B,
                                     int64_t d, float inv_t, float* lse, float* diag, float* loss, void* ws,
@@ -514,11 +618,12 @@ int tt_inbatch_softmax_forward_bf16(const void* q_bf16, int64_t ldq, const void*
   TT_CHECK_ARG(B > 0 && d > 0 && q_bf16 && c_bf16 && lse && diag && loss, "inbatch_softmax_forward_bf16: bad args");
   if (d > 256) return fail(TT_ERR_UNSUPPORTED, "inbatch_softmax_forward_bf16: d > 256");
   if (B >= ((int64_t)1 << 30)) return fail(TT_ERR_UNSUPPORTED, "inbatch_softmax_forward_bf16: B too large");
-  const int blocks = (int)((B + 127) / 128);
-  if (!ws || ws_bytes < (size_t)blocks * 4) return fail(TT_ERR_WORKSPACE, "inbatch_softmax_bf16: workspace too small");
+  int blocks = (int)((B + 127) / 128);
+  if (!ws || ws_bytes < tt_inbatch_softmax_bf16_workspace_bytes(B)) return fail(TT_ERR_WORKSPACE, "inbatch_softmax_bf16: workspace too small");
   cudaStream_t s = as_stream(stream);
   const int KB = (int)((d + 63) / 64);
   const int NT = KB <= 2 ? 256 : 128;
+  const int splits = column_splits(B, NT);
   CUtensorMap tq, tcm;
   int rc = make_tmap_bf16_2d(&tq, q_bf16, B, d, ldq, 128);
   if (rc) return rc;
@@ -529,14 +634,20 @@ int tt_inbatch_softmax_forward_bf16(const void* q_bf16, int64_t ldq, const void*
                                                             (int)d, inv_t, diag);
   TT_CHECK_LAUNCH("rowdot_bf16");
   float* partial = static_cast<float*>(ws);
+  float* ml = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up((size_t)(blocks + 1) * 4, 256));
   const float scale2 = inv_t * kLog2e;
   switch (KB) {
-    case 1: rc = launch_fwd<1>(tq, tcm, (int)B, scale2, diag, lse, partial, s); break;
-    case 2: rc = launch_fwd<2>(tq, tcm, (int)B, scale2, diag, lse, partial, s); break;
-    case 3: rc = launch_fwd<3>(tq, tcm, (int)B, scale2, diag, lse, partial, s); break;
-    default: rc = launch_fwd<4>(tq, tcm, (int)B, scale2, diag, lse, partial, s); break;
+    case 1: rc = launch_fwd<1>(tq, tcm, (int)B, scale2, diag, lse, partial, ml, splits, s); break;
+    case 2: rc = launch_fwd<2>(tq, tcm, (int)B, scale2, diag, lse, partial, ml, splits, s); break;
+    case 3: rc = launch_fwd<3>(tq, tcm, (int)B, scale2, diag, lse, partial, ml, splits, s); break;
+    default: rc = launch_fwd<4>(tq, tcm, (int)B, scale2, diag, lse, partial, ml, splits, s); break;
   }
   if (rc) return rc;
+  if (splits > 1) {
+    blocks = (int)((B + 255) / 256);
+    lse_merge_kernel<<<blocks, 256, 0, s>>>(ml, splits, (int)B, diag, lse, partial);
+    TT_CHECK_LAUNCH("lse_merge");
+  }
   loss_final_kernel<<<1, 1024, 0, s>>>(partial, blocks, 1.0f / (float)B, loss);
   TT_CHECK_LAUNCH("loss_final");
   return TT_OK;
@@ -554,6 +665,7 @@ int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void
   const int KB = (int)((d + 63) / 64);
   const int D = KB * 64;
   const int NT = KB <= 2 ? 128 : 64;
+  const int splits = column_splits(B, NT);
   const float scale2 = inv_t * kLog2e;
   const float out_scale = grad_scale * inv_t / (float)B;
   CUtensorMap tq128, tc128, tqn, tcn, tqt, tct;
@@ -568,9 +680,9 @@ int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void
   const float* gate_c = relu_gate ? c_f32 : nullptr;
 #define TT_LB(KBV)                                                                                              \
   do {                                                                                                          \
-    rc = launch_bwd<KBV, true>(tq128, tcn, tct, (int)B, (int)d, scale2, lse, c_f32, ldcf, gate_q, ldqf, out_scale, dq, lddq, s); \
+    rc = launch_bwd<KBV, true>(tq128, tcn, tct, (int)B, (int)d, scale2, lse, c_f32, ldcf, gate_q, ldqf, out_scale, dq, lddq, splits, s); \
     if (rc) return rc;                                                                                          \
-    rc = launch_bwd<KBV, false>(tc128, tqn, tqt, (int)B, (int)d, scale2, lse, q_f32, ldqf, gate_c, ldcf, out_scale, dc, lddc, s); \
+    rc = launch_bwd<KBV, false>(tc128, tqn, tqt, (int)B, (int)d, scale2, lse, q_f32, ldqf, gate_c, ldcf, out_scale, dc, lddc, splits, s); \
   } while (0)
   switch (KB) {
     case 1: TT_LB(1); break;
