@@ -89,7 +89,7 @@ def build_model(cfg, dev):
     eb = [tt.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=cfg["dim"], num_embeddings=cfg["rows"][i], feature_names=[c])
           for i, c in enumerate(CAT)]
     ebc = tt.EmbeddingBagCollection(tables=eb, device=torch.device("meta"))
-    task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, cfg["layers"], device=dev), loss=cfg["loss"], precision=cfg.get("precision", "bf16"))
+    task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, cfg["layers"], device=dev, precision=cfg.get("precision", "bf16")), loss=cfg["loss"], precision=cfg.get("precision", "bf16"))
     apply_optimizer_in_backward(tt.RowWiseAdagrad, task.two_tower.ebc.parameters(), {"lr": cfg["sparse_lr"]})
     model = tt.DistributedModelParallel(module=task, device=dev)
     opt = tt.KeyedOptimizerWrapper(dict(model.named_parameters()), lambda p: tt.FlatAdam(p, lr=cfg["dense_lr"]))
@@ -249,7 +249,7 @@ def run_ours(args):
         "metric": "two-tower train samples/s", "value": round(world * B / (ms_value * 1e-3), 1), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_value, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16 logits GEMM (fp32 accumulate) + f32 embeddings/towers/optimizers", "data": "synthetic",
+        "dtype": "bf16 tower + logits GEMMs (fp32 accumulate, fp32 master weights) + f32 embeddings/optimizers", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1] on %d GPU(s): 2 tables 10M x 64 fp32, per-rank batch 65536, MLP 64-128-64, "
                                "in-batch softmax, fused row-wise Adagrad, Adam" % world,
                    "per_rank_batch": B, "global_batch": B * world, "l2": "tables 5.12 GB >> 126 MB L2, random ids; no flush needed"},

@@ -187,9 +187,11 @@ int tt_linear_backward_f32(const float* x, int64_t ldx, const float* w, const fl
  * ------------------------------------------------------------------------- */
 
 /* fp32 [rows, cols] (pitch ldx) -> bf16 row-major `out` (pitch ld_out) and/or the
- * transposed copy `out_t` [cols, rows] (pitch ld_out_t).  Either output may be NULL. */
-int tt_cast_f32_to_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, void* out,
-                        int64_t ld_out, void* out_t, int64_t ld_out_t, void* stream);
+ * transposed copy `out_t` [cols, rows] (pitch ld_out_t).  Either output may be NULL.
+ * gate != NULL zeroes elements whose gate[r,c] <= 0 (ReLU backward: dz = dy * (y > 0)). */
+int tt_cast_f32_to_bf16(const float* x, int64_t ldx, const float* gate, int64_t ld_gate, int64_t rows,
+                        int64_t cols, void* out, int64_t ld_out, void* out_t, int64_t ld_out_t,
+                        void* stream);
 
 /* C[M,N] = epilogue(A[M,K] . B[N,K]^T): the Linear of torchrec MLP
  * (utils/model_training.py:95-96) with A = activations, B = nn.Linear.weight.
@@ -197,8 +199,20 @@ int tt_cast_f32_to_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols,
  * stores to any of out_f32 [M,N], out_bf16 [M,N], out_bf16_t [N,M]. */
 int tt_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N,
                  int64_t K, const float* bias, int32_t relu, const float* mask, int64_t ld_mask,
-                 float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
-                 void* out_bf16_t, int64_t ld_bf16_t, void* stream);
+                 const void* mask_bf16, int64_t ld_mask_bf16, float* out_f32, int64_t ld_f32,
+                 void* out_bf16, int64_t ld_bf16, void* out_bf16_t, int64_t ld_bf16_t, void* stream);
+
+/* Weight gradient shape: C[M,N] fp32 = A[M,K] . B[N,K]^T with M, N small and K = batch.
+ * The K reduction is split over ~2 waves of CTAs; partials land in ws and are reduced in
+ * slice order (deterministic). */
+size_t tt_gemm_bf16_splitk_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int tt_gemm_bf16_splitk(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N,
+                        int64_t K, float* out_f32, void* ws, size_t ws_bytes, void* stream);
+
+/* out[c] = sum_r x[r,c] for a bf16 matrix (bias gradient). */
+size_t tt_colsum_bf16_workspace_bytes(int64_t rows, int64_t cols);
+int tt_colsum_bf16(const void* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* ws,
+                   size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Losses (utils/model_training.py:136-140 and the in-batch-softmax extension)

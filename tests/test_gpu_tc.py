@@ -89,3 +89,72 @@ def test_in_batch_softmax_tc_matches_fp32_path(cuda):
     a = in_batch_softmax_loss(q.to(cuda), c.to(cuda), 1.0, precision="fp32")[0]
     b = in_batch_softmax_loss(q.to(cuda), c.to(cuda), 1.0, precision="bf16")[0]
     torch.testing.assert_close(a, b, rtol=1e-2, atol=1e-3)  # bf16 operand rounding
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 128, 65536), (128, 64, 65536), (100, 36, 5000), (1024, 512, 4096)])
+def test_gemm_splitk_and_colsum(cuda, M, N, K):
+    from two_tower_recommender_model_b200.functional import cast_bf16, colsum_bf16, gemm_bf16_splitk
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g); b = torch.randn(N, K, generator=g)
+    ad, bd = cast_bf16(a.to(cuda)), cast_bf16(b.to(cuda))
+    want = ad.double().cpu() @ bd.double().cpu().t()
+    got = gemm_bf16_splitk(ad, bd)
+    torch.testing.assert_close(got.cpu().double(), want, rtol=1e-4, atol=2e-3)
+    cs = colsum_bf16(cast_bf16(a.t().contiguous().to(cuda)))       # [K, M] -> sums over K
+    torch.testing.assert_close(cs.cpu().double(), a.bfloat16().double().sum(1), rtol=1e-4, atol=1e-3)
+
+
+def test_cast_gate(cuda):
+    from two_tower_recommender_model_b200.functional import cast_bf16
+    x = torch.randn(300, 40); gt = torch.randn(300, 40)
+    r, t = cast_bf16(x.to(cuda), both=True, gate=gt.to(cuda))
+    want = (x * (gt > 0)).bfloat16()
+    assert torch.equal(r.cpu(), want) and torch.equal(t.cpu(), want.t())
+
+
+@pytest.mark.parametrize("B,sizes", [(4096, [64, 128, 64]), (1000, [128, 1024, 512, 256]), (777, [36, 20, 8]), (65536, [64, 128, 64])])
+def test_mlp_tensor_core(cuda, B, sizes):
+    """bf16 tower (tcgen05) vs a float64 emulation of the SAME pipeline (operands and stored
+    activations / dZ rounded to bf16 at the same points; ReLU gates taken from the bf16
+    activations).  A plain fp32 tower is not a usable reference for gradients: a hidden unit
+    whose pre-activation is within bf16 rounding of 0 legitimately gates differently.
+    Tolerance: relative Frobenius error < 1e-2 (outputs 2e-3)."""
+    import two_tower_recommender_model_b200 as tt
+    torch.manual_seed(B)
+    tc = tt.MLP(sizes[0], sizes[1:], device=cuda, precision="bf16")
+    x = torch.randn(B, sizes[0])
+    dy = torch.randn(B, sizes[-1])
+    bf = lambda t: t.float().bfloat16().double()
+    Ws = [p._linear.weight.detach().cpu() for p in tc._mlp]
+    bs = [p._linear.bias.detach().cpu().double() for p in tc._mlp]
+    acts = [bf(x)]
+    pre_last = None
+    for l, (W, b) in enumerate(zip(Ws, bs)):
+        h = torch.relu(acts[-1] @ bf(W).t() + b)
+        pre_last = h
+        acts.append(bf(h))
+    y_ref = pre_last                                   # last layer output is returned in fp32
+    dz = bf(dy.double() * (y_ref > 0))
+    dWs, dbs = [None] * len(Ws), [None] * len(Ws)
+    for l in range(len(Ws) - 1, -1, -1):
+        dWs[l] = dz.t() @ acts[l]
+        dbs[l] = dz.sum(0)
+        da = dz @ bf(Ws[l])
+        if l > 0:
+            dz = bf(da * (acts[l] > 0))
+        else:
+            dx_ref = da
+    xt = x.to(cuda).requires_grad_(True)
+    yt = tc(xt)
+    rel = lambda a, b: float((a.double().cpu() - b).norm() / (b.norm() + 1e-30))
+    assert rel(yt.detach(), y_ref) < 2e-3
+    yt.backward(dy.to(cuda))
+    assert rel(xt.grad, dx_ref) < 1e-2, rel(xt.grad, dx_ref)
+    for l, p in enumerate(tc._mlp):
+        assert rel(p._linear.weight.grad, dWs[l]) < 1e-2, (l, rel(p._linear.weight.grad, dWs[l]))
+        assert rel(p._linear.bias.grad, dbs[l]) < 1e-2, (l, rel(p._linear.bias.grad, dbs[l]))
+    # and it stays close to the fp32 tower in the forward direction
+    ref = tt.MLP(sizes[0], sizes[1:], device=cuda, precision="fp32")
+    ref.load_state_dict(tc.state_dict())
+    yr = ref(x.to(cuda))
+    torch.testing.assert_close(yt.detach(), yr, rtol=3e-2, atol=3e-2 * float(yr.abs().max()))

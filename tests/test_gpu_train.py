@@ -190,3 +190,29 @@ def test_reference_utils_file_imports_through_shim(cuda):
         m = importlib.import_module(mod)
         for n in names:
             assert hasattr(m, n), f"{mod}.{n}"
+
+
+def test_bf16_tensor_core_training_tracks_fp32_oracle(cuda):
+    """precision="bf16" (tcgen05 towers + in-batch softmax): the loss curve over a few steps stays
+    within rtol 1e-2 of the fp32 CPU oracle (tolerance north_star states for bf16 losses)."""
+    import two_tower_recommender_model_b200 as tt
+    emb, dim, layers, B, lr = [193, 9740], 64, [128, 64], 2048, 0.01
+    specs = [TableSpec(f"t_{c}", emb[i], dim, [c]) for i, c in enumerate(CAT)]
+    ref = oracle.OracleTwoTower(specs, layers, loss="softmax", sparse_lr=lr, dense_lr=lr, seed=3, dense_optimizer="sgd")
+    ebc = tt.EmbeddingBagCollection(tables=[tt.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=dim, num_embeddings=emb[i], feature_names=[c])
+                                            for i, c in enumerate(CAT)], device=torch.device("meta"))
+    task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, layers, device=cuda, precision="bf16"), loss="in_batch_softmax", precision="bf16")
+    apply_optimizer_in_backward(tt.RowWiseAdagrad, task.two_tower.ebc.parameters(), {"lr": lr})
+    model = tt.DistributedModelParallel(module=task, device=cuda)
+    model.module.two_tower.load_state_dict(ref.torchrec_state_dict())
+    opt = tt.KeyedOptimizerWrapper(dict(model.named_parameters()), lambda p: torch.optim.SGD(p, lr=lr))
+    model.train()
+    for b in make_batches(5, B, emb, seed=21):
+        v, l, y = oracle.transform_to_torchrec_batch(b, CAT, emb)
+        loss_r, _ = ref.train_step(CAT, v, l, y)
+        batch = tt.Batch(torch.zeros(1), tt.KeyedJaggedTensor.from_lengths_sync(CAT, v, l), y).to(cuda)
+        opt.zero_grad()
+        loss, _ = model(batch)
+        loss.backward()
+        opt.step()
+        torch.testing.assert_close(loss.detach().cpu(), loss_r, rtol=1e-2, atol=1e-3)

@@ -68,9 +68,13 @@ SIGNATURES = {
     "tt_linear_forward_f32": (c_int32, [_P, c_int64, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P]),
     "tt_linear_backward_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "tt_linear_backward_f32": (c_int32, [_P, c_int64, _P, _P, _P, _P, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, c_size_t, _P]),
-    "tt_cast_f32_to_bf16": (c_int32, [_P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P]),
-    "tt_gemm_bf16": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int32, _P, c_int64,
+    "tt_cast_f32_to_bf16": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P]),
+    "tt_gemm_bf16": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int32, _P, c_int64, _P, c_int64,
                                _P, c_int64, _P, c_int64, _P, c_int64, _P]),
+    "tt_gemm_bf16_splitk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "tt_gemm_bf16_splitk": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
+    "tt_colsum_bf16_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "tt_colsum_bf16": (c_int32, [_P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "tt_dot_bce_workspace_bytes": (c_size_t, [c_int64]),
     "tt_dot_bce": (c_int32, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, c_float, _P, c_size_t, _P]),
     "tt_inbatch_softmax_workspace_bytes": (c_size_t, [c_int64]),

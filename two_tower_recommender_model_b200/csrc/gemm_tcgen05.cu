@@ -47,11 +47,14 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t 
 struct GemmEpilogue {
   const float* bias;        // [N] or null
   const float* mask;        // [M, N] (pitch ld_mask): out = mask > 0 ? out : 0, or null
+  const __nv_bfloat16* mask_bf16;  // same gate read from a bf16 matrix (pitch ld_mask_bf16), or null
   float* out_f32;           // [M, N] row-major or null
   __nv_bfloat16* out_bf16;  // [M, N] row-major or null
   __nv_bfloat16* out_bf16_t;  // [N, M] (transposed) or null
-  int64_t ld_mask, ld_f32, ld_bf16, ld_bf16_t;
+  int64_t ld_mask, ld_mask_bf16, ld_f32, ld_bf16, ld_bf16_t;
   int relu;
+  int kb_per_split;         // split-K: gridDim.z slices of kb_per_split K-blocks; slice z stores raw fp32
+                            // partials at out_f32 + z*M*ld_f32 (bias/relu/mask/bf16 outputs must be off)
 };
 
 constexpr int kBM = 128, kBK = 64, kStages = 4, kGemmThreadsTc = 192;
@@ -78,7 +81,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
-  const int num_kb = (K + kBK - 1) / kBK;
+  const int total_kb = (K + kBK - 1) / kBK;
+  const int kb0 = blockIdx.z * ep.kb_per_split;
+  const int num_kb = min(ep.kb_per_split, total_kb - kb0);   // >= 1 by construction of the grid
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -100,8 +105,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-        tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * kBK, m0);
-        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * kBK, n0);
+        tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], (kb0 + kb) * kBK, m0);
+        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], (kb0 + kb) * kBK, n0);
       }
     }
   } else if (warp == 1) {
@@ -150,10 +155,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (col < N && !(ep.mask[(int64_t)row * ep.ld_mask + col] > 0.f)) f[j] = 0.f;
         }
       }
+      if (ep.mask_bf16 != nullptr && row < M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + c0 + j;
+          if (col < N && !(__bfloat162float(ep.mask_bf16[(int64_t)row * ep.ld_mask_bf16 + col]) > 0.f)) f[j] = 0.f;
+        }
+      }
       if (row < M) {
         const bool full_chunk = (n0 + c0 + 32 <= N);
         if (ep.out_f32 != nullptr) {
-          float* o = ep.out_f32 + (int64_t)row * ep.ld_f32 + n0 + c0;
+          float* o = ep.out_f32 + (int64_t)blockIdx.z * M * ep.ld_f32 + (int64_t)row * ep.ld_f32 + n0 + c0;
           if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -200,8 +212,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // fp32 [rows, cols] (pitch ldx) -> bf16 row-major (pitch ld_out) and/or transposed bf16 [cols, rows]
 __global__ void __launch_bounds__(256)
-cast_bf16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, __nv_bfloat16* __restrict__ out,
-                 int64_t ld_out, __nv_bfloat16* __restrict__ out_t, int64_t ld_out_t) {
+cast_bf16_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gate, int64_t ld_gate, int rows,
+                 int cols, __nv_bfloat16* __restrict__ out, int64_t ld_out, __nv_bfloat16* __restrict__ out_t,
+                 int64_t ld_out_t) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -209,6 +222,7 @@ cast_bf16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, _
   for (int i = 0; i < 4; ++i) {
     const int r = r0 + ty + i * 8, c = c0 + tx;
     float v = (r < rows && c < cols) ? x[(int64_t)r * ldx + c] : 0.f;
+    if (gate != nullptr && r < rows && c < cols && !(gate[(int64_t)r * ld_gate + c] > 0.f)) v = 0.f;
     tile[ty + i * 8][tx] = v;
     if (out != nullptr && r < rows && c < cols) out[(int64_t)r * ld_out + c] = __float2bfloat16(v);
   }
@@ -221,9 +235,39 @@ cast_bf16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, _
   }
 }
 
+// partial[z][c] = sum over the rows of chunk z of x[r, c] (bf16 in, fp32 accumulate)
+__global__ void __launch_bounds__(256)
+colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int rows, int cols, int rows_per_chunk,
+                           float* __restrict__ partial) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float s = 0.f;
+  if (c < cols)
+    for (int r = r0 + ty; r < r1; r += 8) s += __bfloat162float(x[(int64_t)r * ldx + c]);
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    partial[(int64_t)blockIdx.y * cols + c] = t;
+  }
+}
+
+// out[i] = sum_z partial[z*count + i], z ascending (deterministic)
+__global__ void tc_reduce_partials_kernel(const float* __restrict__ partial, int S, int64_t count, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float s = 0.f;
+  for (int z = 0; z < S; ++z) s += partial[(int64_t)z * count + i];
+  out[i] = s;
+}
+
 template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
-                       cudaStream_t s) {
+                       int splits, cudaStream_t s) {
   static bool attr = false;
   constexpr int smem = gemm_smem_bytes<BN>();
   if (!attr) {
@@ -231,7 +275,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     if (e != cudaSuccess) return fail(TT_ERR_CUDA, "tc_gemm smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM);
+  dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM, splits);
   tc_gemm_kernel<BN><<<grid, kGemmThreadsTc, smem, s>>>(ta, tb, ep, M, N, K);
   TT_CHECK_LAUNCH("tc_gemm");
   return TT_OK;
@@ -245,23 +289,34 @@ using namespace tt::tc;
 
 extern "C" {
 
-int tt_cast_f32_to_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, void* out, int64_t ld_out,
-                        void* out_t, int64_t ld_out_t, void* stream) {
+int tt_cast_f32_to_bf16(const float* x, int64_t ldx, const float* gate, int64_t ld_gate, int64_t rows, int64_t cols,
+                        void* out, int64_t ld_out, void* out_t, int64_t ld_out_t, void* stream) {
   TT_CHECK_ARG(rows >= 0 && cols >= 0 && (out || out_t), "cast_bf16: bad args");
   if (rows == 0 || cols == 0) return TT_OK;
   TT_CHECK_ARG(x != nullptr, "cast_bf16: null input");
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
   if (grid.y > 65535) return fail(TT_ERR_UNSUPPORTED, "cast_bf16: too many rows");
-  cast_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, ldx, (int)rows, (int)cols,
+  cast_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, ldx, gate, ld_gate, (int)rows, (int)cols,
                                                         static_cast<__nv_bfloat16*>(out), ld_out,
                                                         static_cast<__nv_bfloat16*>(out_t), ld_out_t);
   TT_CHECK_LAUNCH("cast_bf16");
   return TT_OK;
 }
 
+static int gemm_dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                         int splits, cudaStream_t s) {
+  switch (bn) {
+    case 32: return launch_gemm<32>(ta, tb, ep, M, N, K, splits, s);
+    case 64: return launch_gemm<64>(ta, tb, ep, M, N, K, splits, s);
+    case 128: return launch_gemm<128>(ta, tb, ep, M, N, K, splits, s);
+    default: return launch_gemm<256>(ta, tb, ep, M, N, K, splits, s);
+  }
+}
+
 int tt_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N, int64_t K,
-                 const float* bias, int32_t relu, const float* mask, int64_t ld_mask, float* out_f32, int64_t ld_f32,
-                 void* out_bf16, int64_t ld_bf16, void* out_bf16_t, int64_t ld_bf16_t, void* stream) {
+                 const float* bias, int32_t relu, const float* mask, int64_t ld_mask, const void* mask_bf16,
+                 int64_t ld_mask_bf16, float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
+                 void* out_bf16_t, int64_t ld_bf16_t, void* stream) {
   TT_CHECK_ARG(M > 0 && N > 0 && K > 0 && a && b, "gemm_bf16: bad args");
   TT_CHECK_ARG(out_f32 || out_bf16 || out_bf16_t, "gemm_bf16: no output");
   if (M >= ((int64_t)1 << 31) || (M + kBM - 1) / kBM > 65535) return fail(TT_ERR_UNSUPPORTED, "gemm_bf16: M too large");
@@ -272,17 +327,77 @@ int tt_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t
   rc = make_tmap_bf16_2d(&tb, b, N, K, ldb, bn);
   if (rc) return rc;
   GemmEpilogue ep;
+  ep.mask_bf16 = static_cast<const __nv_bfloat16*>(mask_bf16); ep.ld_mask_bf16 = ld_mask_bf16;
+  ep.kb_per_split = (int)((K + kBK - 1) / kBK);
   ep.bias = bias; ep.mask = mask; ep.out_f32 = out_f32;
   ep.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
   ep.out_bf16_t = static_cast<__nv_bfloat16*>(out_bf16_t);
   ep.ld_mask = ld_mask; ep.ld_f32 = ld_f32; ep.ld_bf16 = ld_bf16; ep.ld_bf16_t = ld_bf16_t; ep.relu = relu;
+  return gemm_dispatch(bn, ta, tb, ep, (int)M, (int)N, (int)K, 1, as_stream(stream));
+}
+
+static int splitk_splits(int64_t M, int64_t N, int64_t K, int bn) {
+  const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
+  const int64_t total_kb = (K + kBK - 1) / kBK;
+  int64_t want = (2 * kNumSMs + tiles - 1) / tiles;      // about two waves of CTAs
+  if (want > total_kb / 4) want = total_kb / 4;          // at least 4 K-blocks per slice
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+size_t tt_gemm_bf16_splitk_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  return align_up((size_t)splitk_splits(M, N, K, bn) * M * N * 4, 256) + 256;
+}
+
+// C[M,N] (fp32) = A[M,K] . B[N,K]^T with the K reduction split over CTAs (weight gradients:
+// M, N small, K = batch).  Partials go to ws, an ordered reduce writes out (deterministic).
+int tt_gemm_bf16_splitk(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                        float* out_f32, void* ws, size_t ws_bytes, void* stream) {
+  TT_CHECK_ARG(M > 0 && N > 0 && K > 0 && a && b && out_f32, "gemm_bf16_splitk: bad args");
+  const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  const int want = splitk_splits(M, N, K, bn);
+  const int total_kb = (int)((K + kBK - 1) / kBK);
+  const int per = (total_kb + want - 1) / want;
+  const int splits = (total_kb + per - 1) / per;          // every slice gets >= 1 K-block
+  if (!ws || ws_bytes < (size_t)splits * M * N * 4) return fail(TT_ERR_WORKSPACE, "gemm_bf16_splitk: workspace too small");
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_2d(&ta, a, M, K, lda, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tb, b, N, K, ldb, bn);
+  if (rc) return rc;
+  GemmEpilogue ep = {};
+  ep.out_f32 = static_cast<float*>(ws);
+  ep.ld_f32 = N;
+  ep.kb_per_split = per;
   cudaStream_t s = as_stream(stream);
-  switch (bn) {
-    case 32: return launch_gemm<32>(ta, tb, ep, (int)M, (int)N, (int)K, s);
-    case 64: return launch_gemm<64>(ta, tb, ep, (int)M, (int)N, (int)K, s);
-    case 128: return launch_gemm<128>(ta, tb, ep, (int)M, (int)N, (int)K, s);
-    default: return launch_gemm<256>(ta, tb, ep, (int)M, (int)N, (int)K, s);
-  }
+  rc = gemm_dispatch(bn, ta, tb, ep, (int)M, (int)N, (int)K, splits, s);
+  if (rc) return rc;
+  const int64_t cnt = M * N;
+  tc_reduce_partials_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(static_cast<float*>(ws), splits, cnt, out_f32);
+  TT_CHECK_LAUNCH("tc_reduce_partials");
+  return TT_OK;
+}
+
+size_t tt_colsum_bf16_workspace_bytes(int64_t rows, int64_t cols) {
+  const int64_t chunks = (rows + 1023) / 1024;
+  return align_up((size_t)chunks * cols * 4, 256) + 256;
+}
+
+// out[c] = sum_r x[r, c]  (bias gradient of a tower layer from the bf16 dZ)
+int tt_colsum_bf16(const void* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* ws, size_t ws_bytes,
+                   void* stream) {
+  TT_CHECK_ARG(rows > 0 && cols > 0 && x && out, "colsum_bf16: bad args");
+  const int chunks = (int)((rows + 1023) / 1024);
+  if (!ws || ws_bytes < (size_t)chunks * cols * 4) return fail(TT_ERR_WORKSPACE, "colsum_bf16: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)chunks);
+  colsum_bf16_partial_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ldx, (int)rows, (int)cols, 1024,
+                                                  static_cast<float*>(ws));
+  TT_CHECK_LAUNCH("colsum_bf16_partial");
+  tc_reduce_partials_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(static_cast<float*>(ws), chunks, cols, out);
+  TT_CHECK_LAUNCH("tc_reduce_partials");
+  return TT_OK;
 }
 
 }  // extern "C"

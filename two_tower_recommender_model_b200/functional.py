@@ -276,20 +276,27 @@ def score_topk(queries: torch.Tensor, items: torch.Tensor, k: int, item_index_ba
 
 
 # --------------------------------------------------------------------------- tensor-core (bf16) primitives
-def cast_bf16(x: torch.Tensor, transposed: bool = False, both: bool = False):
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def cast_bf16(x: torch.Tensor, transposed: bool = False, both: bool = False, gate: Optional[torch.Tensor] = None):
     """fp32 [rows, cols] (row-contiguous, may be a column window) -> bf16 copy; ``transposed`` returns
-    the [cols, rows] copy instead, ``both`` returns (row-major, transposed).  Row pitches are padded to
-    a multiple of 8 elements (TMA needs 16-byte pitches)."""
+    the [cols, rows] copy instead, ``both`` returns (row-major, transposed).  ``gate`` (fp32, same
+    shape) zeroes the elements whose gate is <= 0 (ReLU backward).  Row pitches are padded to a
+    multiple of 8 elements (TMA needs 16-byte pitches)."""
     x = _rows(x, "x")
     rows, cols = x.shape
     dev = x.device
-    pad = lambda n: (n + 7) // 8 * 8
     out = out_t = None
     if both or not transposed:
-        out = torch.empty(rows, pad(cols), dtype=torch.bfloat16, device=dev)[:, :cols]
+        out = torch.empty(rows, _pad8(cols), dtype=torch.bfloat16, device=dev)[:, :cols]
     if both or transposed:
-        out_t = torch.empty(cols, pad(rows), dtype=torch.bfloat16, device=dev)[:, :rows]
-    N.call("tt_cast_f32_to_bf16", N.ptr(x), x.stride(0) if rows > 0 else cols, rows, cols,
+        out_t = torch.empty(cols, _pad8(rows), dtype=torch.bfloat16, device=dev)[:, :rows]
+    if gate is not None:
+        gate = _rows(gate, "gate")
+    N.call("tt_cast_f32_to_bf16", N.ptr(x), x.stride(0) if rows > 0 else cols, N.ptr(gate),
+           gate.stride(0) if gate is not None else 0, rows, cols,
            N.ptr(out), out.stride(0) if out is not None else 0, N.ptr(out_t), out_t.stride(0) if out_t is not None else 0,
            N.stream_ptr(dev))
     if both:
@@ -298,8 +305,8 @@ def cast_bf16(x: torch.Tensor, transposed: bool = False, both: bool = False):
 
 
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
-              mask: Optional[torch.Tensor] = None, out_f32: bool = True, out_bf16: bool = False,
-              out_bf16_t: bool = False):
+              mask: Optional[torch.Tensor] = None, mask_bf16: Optional[torch.Tensor] = None, out_f32: bool = True,
+              out_bf16: bool = False, out_bf16_t: bool = False):
     """``epilogue(a @ b.T)`` on tcgen05: a [M,K] bf16, b [N,K] bf16 (row pitch multiple of 8).
     Returns a dict with the requested outputs ("f32", "bf16", "bf16_t")."""
     N.require_cuda(a, "a")
@@ -307,13 +314,13 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = N
     M, K = a.shape
     Nn = b.shape[0]
     dev = a.device
-    pad = lambda n: (n + 7) // 8 * 8
     res = {}
     f32 = torch.empty(M, Nn, dtype=torch.float32, device=dev) if out_f32 else None
-    b16 = torch.empty(M, pad(Nn), dtype=torch.bfloat16, device=dev)[:, :Nn] if out_bf16 else None
-    b16t = torch.empty(Nn, pad(M), dtype=torch.bfloat16, device=dev)[:, :M] if out_bf16_t else None
+    b16 = torch.empty(M, _pad8(Nn), dtype=torch.bfloat16, device=dev)[:, :Nn] if out_bf16 else None
+    b16t = torch.empty(Nn, _pad8(M), dtype=torch.bfloat16, device=dev)[:, :M] if out_bf16_t else None
     N.call("tt_gemm_bf16", N.ptr(a), a.stride(0), N.ptr(b), b.stride(0), M, Nn, K, N.ptr(bias), 1 if relu else 0,
-           N.ptr(mask), mask.stride(0) if mask is not None else 0, N.ptr(f32), Nn,
+           N.ptr(mask), mask.stride(0) if mask is not None else 0,
+           N.ptr(mask_bf16), mask_bf16.stride(0) if mask_bf16 is not None else 0, N.ptr(f32), Nn,
            N.ptr(b16), b16.stride(0) if b16 is not None else 0, N.ptr(b16t), b16t.stride(0) if b16t is not None else 0,
            N.stream_ptr(dev))
     if f32 is not None:
@@ -323,3 +330,74 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = N
     if b16t is not None:
         res["bf16_t"] = b16t
     return res
+
+
+def gemm_bf16_splitk(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """fp32 ``a @ b.T`` for small [M,N] and a long K (weight gradients): K split over the SMs."""
+    M, K = a.shape
+    Nn = b.shape[0]
+    dev = a.device
+    out = torch.empty(M, Nn, dtype=torch.float32, device=dev)
+    ws = N.workspace(N.load().tt_gemm_bf16_splitk_workspace_bytes(M, Nn, K), dev)
+    N.call("tt_gemm_bf16_splitk", N.ptr(a), a.stride(0), N.ptr(b), b.stride(0), M, Nn, K, N.ptr(out), N.ptr(ws), ws.numel(),
+           N.stream_ptr(dev))
+    return out
+
+
+def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
+    rows, cols = x.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    ws = N.workspace(N.load().tt_colsum_bf16_workspace_bytes(rows, cols), x.device)
+    N.call("tt_colsum_bf16", N.ptr(x), x.stride(0), rows, cols, N.ptr(out), N.ptr(ws), ws.numel(), N.stream_ptr(x.device))
+    return out
+
+
+class MlpTC(torch.autograd.Function):
+    """A whole ReLU tower on the tensor cores: ``x -> relu(x W1^T + b1) -> ... -> relu(. WL^T + bL)``.
+    Operands are bf16 (activations are produced in bf16 by the GEMM epilogues, together with the
+    transposed copies the weight-gradient GEMMs read), accumulation is fp32 in TMEM, master weights,
+    the returned output and all gradients are fp32.  Backward: dZ_l = dA_l * (A_l > 0) is fused into
+    the epilogue of the previous data-gradient GEMM; dW_l = dZ_l^T A_{l-1} is a split-K GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        L = len(params) // 2
+        x = _rows(x, "x")
+        xb, xbt = cast_bf16(x, both=True)
+        acts = [(xb, xbt)]
+        out = None
+        for l in range(L):
+            w, b = params[2 * l], params[2 * l + 1]
+            wb = cast_bf16(_f32c(w, "weight"))
+            last = l == L - 1
+            r = gemm_bf16(acts[-1][0], wb, bias=None if b is None else _f32c(b, "bias"), relu=True,
+                          out_f32=last, out_bf16=True, out_bf16_t=not last)
+            acts.append((r["bf16"], r.get("bf16_t")))
+            if last:
+                out = r["f32"]
+        ctx.L = L
+        ctx.acts = acts
+        ctx.save_for_backward(out, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        out, *params = ctx.saved_tensors
+        L, acts = ctx.L, ctx.acts
+        dz, dzt = cast_bf16(_f32c(dout, "dout"), both=True, gate=out)
+        grads = [None] * (2 * L)
+        dx = None
+        for l in range(L - 1, -1, -1):
+            w, b = params[2 * l], params[2 * l + 1]
+            grads[2 * l] = gemm_bf16_splitk(dzt, acts[l][1])            # [N_l, K_l]
+            if b is not None:
+                grads[2 * l + 1] = colsum_bf16(dz)
+            if l > 0:
+                wt = cast_bf16(w, transposed=True)                       # [K_l, N_l]
+                r = gemm_bf16(dz, wt, mask_bf16=acts[l][0], out_f32=False, out_bf16=True, out_bf16_t=True)
+                dz, dzt = r["bf16"], r["bf16_t"]
+            elif ctx.needs_input_grad[0]:
+                wt = cast_bf16(w, transposed=True)
+                dx = gemm_bf16(dz, wt, out_f32=True)["f32"]
+        ctx.acts = None
+        return (dx, *grads)

@@ -12,7 +12,7 @@ from typing import Callable, List, Optional, Union
 import torch
 from torch import nn
 
-from ..functional import linear_act
+from ..functional import MlpTC, linear_act
 
 
 class Perceptron(nn.Module):
@@ -37,8 +37,14 @@ class Perceptron(nn.Module):
 class MLP(nn.Module):
     def __init__(self, in_size: int, layer_sizes: List[int], bias: bool = True,
                  activation: Union[str, Callable[[], nn.Module], nn.Module, Callable[[torch.Tensor], torch.Tensor]] = torch.relu,
-                 device: Optional[torch.device] = None, dtype: torch.dtype = torch.float32) -> None:
+                 device: Optional[torch.device] = None, dtype: torch.dtype = torch.float32,
+                 precision: str = "fp32") -> None:
         super().__init__()
+        if precision not in ("fp32", "bf16"):
+            raise ValueError(f"unknown precision {precision}")
+        # "bf16": the tower runs on tcgen05 (bf16 operands, fp32 accumulate, fp32 master weights);
+        # "fp32": exact-fp32 CUDA-core path (the reference's numerics).
+        self.precision = precision
         if activation == "relu":
             activation = torch.relu
         elif activation == "sigmoid":
@@ -52,4 +58,12 @@ class MLP(nn.Module):
         ])
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
+        layers = list(self._mlp)
+        relu_all = all(p._activation_fn is torch.relu or p._activation_fn is torch.nn.functional.relu
+                       or isinstance(p._activation_fn, nn.ReLU) for p in layers)
+        if self.precision == "bf16" and relu_all and input.shape[0] > 0:
+            params = []
+            for p in layers:
+                params += [p._linear.weight, p._linear.bias]
+            return MlpTC.apply(input, *params)
         return self._mlp(input)

@@ -23,7 +23,7 @@ from .sparse.jagged_tensor import KeyedJaggedTensor, KeyedTensor
 class TwoTower(nn.Module):
     def __init__(self, embedding_bag_collection: EmbeddingBagCollection, layer_sizes: List[int],
                  device: Optional[torch.device] = None, query_features: Optional[List[str]] = None,
-                 candidate_features: Optional[List[str]] = None) -> None:
+                 candidate_features: Optional[List[str]] = None, precision: str = "fp32") -> None:
         super().__init__()
         cfgs = embedding_bag_collection.embedding_bag_configs()
         if query_features is None and candidate_features is None:
@@ -38,9 +38,9 @@ class TwoTower(nn.Module):
         self._candidate_feature_names: List[str] = list(candidate_features)
         self.ebc = embedding_bag_collection
         self.query_proj = MLP(in_size=sum(dim_of[f] for f in self._feature_names_query),
-                              layer_sizes=layer_sizes, device=device)
+                              layer_sizes=layer_sizes, device=device, precision=precision)
         self.candidate_proj = MLP(in_size=sum(dim_of[f] for f in self._candidate_feature_names),
-                                  layer_sizes=layer_sizes, device=device)
+                                  layer_sizes=layer_sizes, device=device, precision=precision)
 
     @staticmethod
     def _tower_input(pooled: KeyedTensor, features: List[str]) -> torch.Tensor:
