@@ -285,6 +285,11 @@ struct BwdCfg {
   static constexpr int NT = KB <= 2 ? 128 : 64;          // Y rows per tile = S/P columns per TMEM stage
   static constexpr int NSP = KB <= 2 ? 3 : 4;            // TMEM S/P stages: columns [NT*a, NT*a + NT)
   static constexpr int NKB2 = NT / 64;                   // K blocks of the second GEMM
+#ifndef TT_BWD_GROUPS
+#define TT_BWD_GROUPS 3
+#endif
+  static constexpr int NG = KB <= 2 ? TT_BWD_GROUPS : 2;  // softmax warpgroups (tiles t = g mod NG)
+  static constexpr int THREADS = 64 + NG * 128;
   static constexpr int STAGES = KB == 1 ? 4 : 2;
   static constexpr int LA0 = NSP - 1;                    // S tiles issued ahead of the P they wait for:
   static constexpr int LOOKAHEAD = STAGES - 1 < LA0 ? STAGES - 1 : LA0;   // bounded by TMEM and smem stages
@@ -292,7 +297,7 @@ struct BwdCfg {
   static constexpr int Y_BYTES = KB * NT * 128;          // KB sub-tiles [NT x 64]  (GEMM1 B operand)
   static constexpr int YT_BYTES = NKB2 * D * 128;        // NKB2 sub-tiles [D x 64] (GEMM2 B operand)
   static constexpr int STAGE_BYTES = Y_BYTES + YT_BYTES;
-  static constexpr int SMEM = X_BYTES + STAGES * STAGE_BYTES + 1024 + 256 + 2 * 128 * 4;
+  static constexpr int SMEM = X_BYTES + STAGES * STAGE_BYTES + 1024 + 256 + 4 * 128 * 4;
   static constexpr int O_COL = NSP * NT;                 // O accumulator columns [O_COL, O_COL + D) (<= 512)
   static_assert(O_COL + D <= 512, "TMEM budget");
 };
@@ -328,7 +333,7 @@ __device__ __forceinline__ void p_chunk(const uint32_t (&v)[32], uint32_t tdst, 
 }
 
 template <int KB, bool ROW>
-__global__ void __launch_bounds__(kLgThreads, 1)
+__global__ void __launch_bounds__(BwdCfg<KB>::THREADS, 1)
 tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                       const __grid_constant__ CUtensorMap tmYt, int B, int d, float scale2,
                       const float* __restrict__ lse, const float* __restrict__ yf, int64_t ld_yf,
@@ -348,7 +353,7 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   uint64_t* p_full = s_full + Cfg::NSP;  // [NSP]
   uint64_t* o_full = p_full + Cfg::NSP;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* lse_tile = reinterpret_cast<float*>(bars + 32);      // [2][128], 16-byte aligned (float4 reads)
+  float* lse_tile = reinterpret_cast<float*>(bars + 32);      // [NG][128], 16-byte aligned (float4 reads)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
@@ -436,7 +441,7 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float lrow = (ROW && row < B) ? lse[row] * kLog2e : 0.f;
     float* lse_g = lse_tile + g * 128;
-    for (int t = g; t < T; t += 2) {
+    for (int t = g; t < T; t += Cfg::NG) {
       const int n0 = (t0 + t) * NT;
       const int as = t % Cfg::NSP;
       const uint32_t tsp = trow + as * NT;
@@ -471,7 +476,7 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     mbar_wait(o_full, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c0 = g * 32; c0 < D; c0 += 64) {
+    for (int c0 = g * 32; c0 < D; c0 += Cfg::NG * 32) {
       uint32_t v[32];
       tmem_ld32(trow + Cfg::O_COL + c0, v);
       tmem_ld_wait();
@@ -594,7 +599,7 @@ static int launch_bwd(const CUtensorMap& tx, const CUtensorMap& ty, const CUtens
     if (e != cudaSuccess) return fail(TT_ERR_CUDA, "softmax_bwd memset: %s", cudaGetErrorString(e));
   }
   dim3 grid((B + 127) / 128, splits);
-  tc_softmax_bwd_kernel<KB, ROW><<<grid, kLgThreads, BwdCfg<KB>::SMEM, s>>>(
+  tc_softmax_bwd_kernel<KB, ROW><<<grid, BwdCfg<KB>::THREADS, BwdCfg<KB>::SMEM, s>>>(
       tx, ty, tyt, B, d, scale2, lse, yf, ld_yf, mask, ld_mask, out_scale, out, ld_out);
   TT_CHECK_LAUNCH("tc_softmax_bwd");
   return TT_OK;
