@@ -117,25 +117,77 @@ ebc_forward_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_consta
 #pragma unroll
       for (int v = 0; v < NV; ++v) acc[u][v].zero();
     }
-    for (int j = 0; j < maxlen; ++j) {
+    if (maxlen <= 1) {
+      // one id per bag (the reference's shape): UB independent rows in flight per group
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
-        if (j < len[u]) {
-          const int64_t id = values[s[u] + j];
+        if (len[u] > 0) {
+          const int64_t id = values[s[u]];
           if ((uint64_t)id < R) {
             const float* row = W + id * D;
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
               const int c = l + v * G;
-              if (c < units) {
-                Vec<VEC> x;
-                x.load_stream(row + c * VEC);
-                acc[u][v].add(x);
-              }
+              if (c < units) acc[u][v].load_stream(row + c * VEC);
             }
           }
         }
       }
+    } else {
+      // multi-hot bags: one bag at a time per group; the group reads G ids with one coalesced
+      // load, then keeps JU row reads in flight (ids broadcast by shuffle) and accumulates in id
+      // order (the oracle's order).
+      constexpr int JU = NV == 1 ? 4 : (NV == 2 ? 2 : 1);
+      unsigned gmask = 0xffffffffu;
+      if constexpr (G < 32) gmask = ((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G);
+#pragma unroll 1
+      for (int u = 0; u < UB; ++u) {
+        const int bi = bb + u * NG;
+        if (bi >= nb) break;
+        const int s0 = s_off[bi], ln = s_off[bi + 1] - s0;
+        Vec<VEC> a1[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) a1[v].zero();
+        for (int base = 0; base < ln; base += G) {
+          const int cnt = min(G, ln - base);
+          const long long myid = (l < cnt) ? values[s0 + base + l] : -1;
+          for (int j = 0; j < cnt; j += JU) {
+            Vec<VEC> x[JU][NV];
+            bool ok[JU];
+#pragma unroll
+            for (int t = 0; t < JU; ++t) {
+              const long long id = __shfl_sync(gmask, myid, (j + t) < G ? (j + t) : 0, G);
+              ok[t] = (j + t < cnt) && ((uint64_t)id < R);
+              if (ok[t]) {
+                const float* row = W + id * D;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                  const int c = l + v * G;
+                  if (c < units) x[t][v].load_stream(row + c * VEC);
+                }
+              }
+            }
+#pragma unroll
+            for (int t = 0; t < JU; ++t) {
+              if (ok[t]) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+                  if (l + v * G < units) a1[v].add(x[t][v]);
+              }
+            }
+          }
+        }
+        float* o = out + (int64_t)bi * plan.out_stride;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = l + v * G;
+          if (c < units) {
+            if (mean && ln > 1) a1[v].div((float)ln);
+            a1[v].store(o + c * VEC);
+          }
+        }
+      }
+      continue;
     }
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
@@ -209,8 +261,11 @@ __global__ void ebc_backward_tail_kernel(const int32_t* __restrict__ offsets, in
 // ---------------------------------------------------------------------------
 // backward: segmented reduce over sorted keys + in-place row-wise optimizer
 // ---------------------------------------------------------------------------
+#ifndef TT_EBC_UPD_MINB
+#define TT_EBC_UPD_MINB 8
+#endif
 template <int VEC, int G, int NV>
-__global__ void __launch_bounds__(kEbcThreads)
+__global__ void __launch_bounds__(kEbcThreads, NV == 1 ? TT_EBC_UPD_MINB : 1)
 ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
                            const __grid_constant__ tt_sparse_optimizer opt,
                            const uint32_t* __restrict__ keys, const uint32_t* __restrict__ payload,
@@ -232,6 +287,23 @@ ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
   const int D = plan.dim[slot];
   const int units = D / VEC;
   const int B = plan.batch_size;
+
+  // The weight row (and Adam's first-moment row) is a random DRAM read whose address is known as
+  // soon as the key is: start pulling it into L2 now, so its latency overlaps the walk over the
+  // run's gradient rows below (prefetch costs no registers, unlike an early load).
+#ifdef TT_EBC_UPD_PREFETCH
+  {
+    const char* wrow = reinterpret_cast<const char*>(static_cast<const float*>(plan.weights[slot]) + row * D);
+    const int bytes = D * 4;
+    for (int o = l * 128; o < bytes; o += G * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(wrow + o));
+    if (opt.kind == TT_OPT_ROWWISE_ADAM || opt.kind == TT_OPT_DENSE_GRAD) {
+      const char* mrow = reinterpret_cast<const char*>(static_cast<const float*>(plan.state1[slot]) + row * D);
+      for (int o = l * 128; o < bytes; o += G * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(mrow + o));
+    }
+    if (l == 0 && (opt.kind == TT_OPT_ROWWISE_ADAGRAD || opt.kind == TT_OPT_ROWWISE_ADAM))
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const float*>(plan.state0[slot]) + row));
+  }
+#endif
 
   Vec<VEC> g[NV];
 #pragma unroll
