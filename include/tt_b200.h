@@ -278,6 +278,14 @@ int tt_score_topk_f32(const float* queries, const float* items, int64_t num_quer
                       float* out_scores, int64_t* out_indices, void* ws, size_t ws_bytes,
                       void* stream);
 
+/* Tensor-core variant (tcgen05 scoring, top-k fused into the TMEM epilogue): operands are the
+ * bf16 copies made by tt_cast_f32_to_bf16; d <= 64, k <= 128.  Same ordering rule. */
+size_t tt_topk_bf16_workspace_bytes(int64_t num_queries, int64_t num_items, int64_t k);
+int tt_score_topk_bf16(const void* queries_bf16, int64_t ldq, const void* items_bf16, int64_t ldi,
+                       int64_t num_queries, int64_t num_items, int64_t d, int64_t k,
+                       int64_t item_index_base, float* out_scores, int64_t* out_indices, void* ws,
+                       size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,3 +158,36 @@ def test_mlp_tensor_core(cuda, B, sizes):
     ref.load_state_dict(tc.state_dict())
     yr = ref(x.to(cuda))
     torch.testing.assert_close(yt.detach(), yr, rtol=3e-2, atol=3e-2 * float(yr.abs().max()))
+
+
+@pytest.mark.parametrize("Q,N,d,k", [(10, 1000, 32, 100), (130, 5000, 64, 100), (64, 50, 16, 100), (1, 1, 8, 5),
+                                     (300, 70000, 64, 100), (5, 300, 24, 128), (1000, 200000, 64, 10)])
+def test_topk_tensor_core_exact_grid(cuda, Q, N, d, k):
+    """tcgen05 scoring + fused top-k on exact-arithmetic vectors (entries k/8 in [-1,1] are exact in
+    bf16 and every dot product is exact in fp32): indices and scores must match the oracle bit for bit."""
+    import oracle
+    from two_tower_recommender_model_b200.functional import score_topk
+    g = torch.Generator().manual_seed(Q * 7 + N)
+    q = torch.randint(-8, 9, (Q, d), generator=g).float() / 8
+    it = torch.randint(-8, 9, (N, d), generator=g).float() / 8
+    ws, wi = oracle.exact_topk(q, it, k)
+    s, i = score_topk(q.to(cuda), it.to(cuda), k, precision="bf16")
+    kk = min(k, N)
+    assert torch.equal(i.cpu()[:, :kk], wi)
+    assert torch.equal(s.cpu()[:, :kk], ws)
+    if kk < k:
+        assert (i.cpu()[:, kk:] == -1).all()
+
+
+def test_topk_tensor_core_random_normal(cuda):
+    """Random-normal vectors: compare with the float64 oracle on the SAME bf16-rounded inputs:
+    scores rtol 1e-5, recall@100 >= 0.999 (near-ties may swap under a different summation order)."""
+    import oracle
+    from two_tower_recommender_model_b200.functional import score_topk
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(256, 64, generator=g); it = torch.randn(50000, 64, generator=g)
+    ws, wi = oracle.exact_topk(q.bfloat16().float(), it.bfloat16().float(), 100)
+    s, i = score_topk(q.to(cuda), it.to(cuda), 100, precision="bf16")
+    torch.testing.assert_close(s.cpu(), ws, rtol=1e-5, atol=1e-5)
+    recall = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(i.cpu(), wi)) / wi.numel()
+    assert recall >= 0.999

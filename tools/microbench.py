@@ -92,7 +92,8 @@ def topk(args):
     dev = torch.device("cuda:0")
     q = torch.randn(args.Q, args.d, device=dev)
     it = torch.randn(args.rows, args.d, device=dev)
-    ms = timed(lambda: F.score_topk(q, it, 100), args.iters, warmup=1)
+    itb = F.cast_bf16(it) if args.precision == "bf16" else None
+    ms = timed(lambda: F.score_topk(q, it, 100, precision=args.precision, items_bf16=itb), args.iters, warmup=1)
     print(f"top-100 of {args.rows} items for {args.Q} queries: {ms:.3f} ms, {2.0 * args.Q * args.rows * args.d / ms / 1e9:.2f} TFLOP/s")
 
 

@@ -26,7 +26,7 @@ extern unsigned long long g_kernel_launches;  // every <<<>>> issued by this lib
 #define TT_CHECK_LAUNCH(name)                                                        \
   do {                                                                               \
     ++::tt::g_kernel_launches;                                                       \
-    cudaError_t e__ = cudaGetLastError();                                            \
+    cudaError_t e__ = cudaGetLastError(); /* also clears it: errors never leak into later calls */ \
     if (e__ != cudaSuccess)                                                          \
       return ::tt::fail(TT_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e__));       \
   } while (0)

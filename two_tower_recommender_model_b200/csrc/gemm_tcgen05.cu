@@ -216,7 +216,7 @@ cast_bf16_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
                  int cols, __nv_bfloat16* __restrict__ out, int64_t ld_out, __nv_bfloat16* __restrict__ out_t,
                  int64_t ld_out_t) {
   __shared__ float tile[32][33];
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;     // rows on x: corpora have millions of rows
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -294,8 +294,8 @@ int tt_cast_f32_to_bf16(const float* x, int64_t ldx, const float* gate, int64_t 
   TT_CHECK_ARG(rows >= 0 && cols >= 0 && (out || out_t), "cast_bf16: bad args");
   if (rows == 0 || cols == 0) return TT_OK;
   TT_CHECK_ARG(x != nullptr, "cast_bf16: null input");
-  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
-  if (grid.y > 65535) return fail(TT_ERR_UNSUPPORTED, "cast_bf16: too many rows");
+  dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+  if (grid.y > 65535) return fail(TT_ERR_UNSUPPORTED, "cast_bf16: too many columns");
   cast_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, ldx, gate, ld_gate, (int)rows, (int)cols,
                                                         static_cast<__nv_bfloat16*>(out), ld_out,
                                                         static_cast<__nv_bfloat16*>(out_t), ld_out_t);

@@ -260,15 +260,26 @@ def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, key_bits: int = 32):
     return ko, vo
 
 
-def score_topk(queries: torch.Tensor, items: torch.Tensor, k: int, item_index_base: int = 0):
-    """Exact dot-product top-k (descending score, ties -> lower index)."""
+def score_topk(queries: torch.Tensor, items: torch.Tensor, k: int, item_index_base: int = 0, precision: str = "fp32",
+               items_bf16: Optional[torch.Tensor] = None):
+    """Exact dot-product top-k (descending score, ties -> lower index).  ``precision="bf16"`` scores
+    on the tensor cores (tcgen05; d <= 64): operands are rounded to bf16, accumulation is fp32, and
+    the top-k is fused into the TMEM epilogue.  ``items_bf16`` lets a caller reuse a resident bf16
+    corpus instead of casting it per call."""
     queries = _f32c(queries, "queries")
-    items = _f32c(items, "items")
     Q, d = queries.shape
-    Nn = items.shape[0]
     dev = queries.device
+    Nn = items.shape[0] if items is not None else items_bf16.shape[0]
     scores = torch.empty(Q, k, dtype=torch.float32, device=dev)
     idx = torch.empty(Q, k, dtype=torch.int64, device=dev)
+    if precision == "bf16":
+        qb = cast_bf16(queries)
+        ib = items_bf16 if items_bf16 is not None else cast_bf16(_f32c(items, "items"))
+        ws = N.workspace(N.load().tt_topk_bf16_workspace_bytes(Q, Nn, k), dev)
+        N.call("tt_score_topk_bf16", N.ptr(qb), qb.stride(0), N.ptr(ib), ib.stride(0), Q, Nn, d, k, item_index_base,
+               N.ptr(scores), N.ptr(idx), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+        return scores, idx
+    items = _f32c(items, "items")
     ws = N.workspace(N.load().tt_topk_workspace_bytes(Q, Nn, k), dev)
     N.call("tt_score_topk_f32", N.ptr(queries), N.ptr(items), Q, Nn, d, k, item_index_base, N.ptr(scores),
            N.ptr(idx), N.ptr(ws), ws.numel(), N.stream_ptr(dev))

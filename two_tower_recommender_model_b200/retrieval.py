@@ -62,10 +62,17 @@ class BruteForceIndex:
     """Exact inner-product index over an item-embedding corpus resident in HBM."""
 
     def __init__(self, item_embeddings: torch.Tensor, item_ids: Optional[torch.Tensor] = None,
-                 primary_key: str = "product_id") -> None:
+                 primary_key: str = "product_id", precision: str = "fp32") -> None:
+        """``precision="bf16"``: the corpus is kept as a bf16 copy in HBM and scored on the tensor cores
+        (embedding dim <= 64); ``"fp32"``: exact fp32 CUDA-core scoring."""
         self._items = item_embeddings.contiguous().float()
         self._ids = item_ids
         self._pk = primary_key
+        self._precision = precision
+        self._items_bf16 = None
+        if precision == "bf16":
+            from .functional import cast_bf16
+            self._items_bf16 = cast_bf16(self._items)
 
     def search(self, query_embeddings: torch.Tensor, num_results: int = 100, query_chunk: int = 1 << 16):
         """Batched top-k: returns ``(scores [Q,k] f32, ids [Q,k] int64)``."""
@@ -73,7 +80,7 @@ class BruteForceIndex:
         k = min(num_results, self._items.shape[0])
         s_out, i_out = [], []
         for s in range(0, q.shape[0], query_chunk):
-            sc, ix = score_topk(q[s:s + query_chunk], self._items, k)
+            sc, ix = score_topk(q[s:s + query_chunk], self._items, k, precision=self._precision, items_bf16=self._items_bf16)
             s_out.append(sc)
             i_out.append(ix)
         scores, idx = torch.cat(s_out), torch.cat(i_out)
