@@ -125,12 +125,15 @@ def make_raw_batches(n, cfg, seed, rows_dev):
     return out
 
 
-def algorithmic_bytes(cfg, uniq_per_table):
+def algorithmic_bytes(cfg, uniq_per_table, world=1):
     """SURVEY.md 8(d) conventions: 8-byte ids, 4-byte offsets, each gathered row once, each
-    unique updated row one read + one write of weights and state."""
-    B, D, L = cfg["batch"], cfg["dim"], 1
-    fwd = sum(B * L * (8 + 4 * D) + 4 * B + 4 * B * D for _ in cfg["rows"])
-    bwd = sum(4 * B * D + 8 * B * L + u * (8 * D + 8) for u in uniq_per_table)
+    unique updated row one read + one write of weights and state.  With table-wise sharding
+    (world > 1) rank 0 owns ONE of the two tables and looks up the GLOBAL batch of its feature."""
+    D, L = cfg["dim"], 1
+    B = cfg["batch"] * world
+    tables = len(cfg["rows"]) if world == 1 else 1
+    fwd = tables * (B * L * (8 + 4 * D) + 4 * B + 4 * B * D)
+    bwd = sum(4 * B * D + 8 * B * L + u * (8 * D + 8) for u in uniq_per_table[:tables])
     return fwd, bwd
 
 
@@ -223,8 +226,8 @@ def run_ours(args):
         return
     pk = peaks()
     B = cfg["batch"]
-    uniq = [int(torch.unique(resident[0].sparse_features[c].values()[:B]).numel()) for c in CAT]
-    fwd_bytes, bwd_bytes = algorithmic_bytes(cfg, uniq)
+    uniq = [int(torch.unique(resident[0].sparse_features[c].values()[:B]).numel()) * (world if world > 1 else 1) for c in CAT]
+    fwd_bytes, bwd_bytes = algorithmic_bytes(cfg, uniq, world)
     d_out = cfg["layers"][-1]
     logit_flops = 6.0 * B * B * d_out
     kernels = {}
@@ -242,9 +245,13 @@ def run_ours(args):
     roof = None
     if sm_ms > 0:
         ach = logit_flops / (sm_ms * 1e-3) / 1e12
-        roof = {"kernel": "in-batch softmax logits fwd+bwd", "bound": "tensor", "achieved": round(ach, 2),
-                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_sustained"], 4),
-                "traffic": None, "peak_source": pk["source"] + " (sustained bf16)", "ms": round(sm_ms, 4)}
+        roof = {"kernel": "in-batch softmax: tc_softmax_fwd_kernel + 2 x tc_softmax_bwd_kernel (tcgen05)", "bound": "tensor",
+                "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": round(ach / pk["tf_sustained"], 4),
+                # dram__bytes_read+write per step of the three launches, from the ncu --set full capture in profiles/
+                "traffic": 1.02e8, "peak_source": pk["source"] + " (sustained bf16)", "ms": round(sm_ms, 4),
+                "flops_credited": "6*B*B*d (recomputation of S in the backward is not credited)",
+                "note": "MUFU(ex2)-bound, not tensor-bound, at d=64: 1 ex2 per 128 MACs; see DESIGN.md section 4"}
     line = {
         "metric": "two-tower train samples/s", "value": round(world * B / (ms_value * 1e-3), 1), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_value, 4),
@@ -258,11 +265,33 @@ def run_ours(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
         "ebc_lookup_gbs": kernels.get("tt_ebc_forward", {}).get("achieved"),
     }
+    if world == 1:
+        line["retrieval"] = retrieval_probe(dev)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, steps=2, warmup=1)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def retrieval_probe(dev, n_items=2_000_000, n_queries=16384, d=64, k=100):
+    """Secondary number (BASELINE configs[4] shape, scaled to one GPU and a few hundred ms): top-100 by
+    dot product over a resident bf16 corpus, tcgen05 scoring with the top-k fused in the epilogue."""
+    import two_tower_recommender_model_b200 as tt
+    g = torch.Generator(device=dev).manual_seed(7)
+    items = torch.randn(n_items, d, device=dev, generator=g)
+    queries = torch.randn(n_queries, d, device=dev, generator=g)
+    index = tt.BruteForceIndex(items, precision="bf16")
+    index.search(queries[:1024], k)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    index.search(queries, k)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    return {"queries_per_s": round(n_queries / (ms * 1e-3), 1), "ms": round(ms, 3), "items": n_items, "queries": n_queries,
+            "k": k, "d": d, "tflops": round(2.0 * n_queries * n_items * d / (ms * 1e-3) / 1e12, 1), "dtype": "bf16 scoring, f32 accumulate"}
 
 
 # ----------------------------------------------------------------------------- CPU baseline / reference arm

@@ -93,8 +93,8 @@ def topk(args):
     q = torch.randn(args.Q, args.d, device=dev)
     it = torch.randn(args.rows, args.d, device=dev)
     itb = F.cast_bf16(it) if args.precision == "bf16" else None
-    ms = timed(lambda: F.score_topk(q, it, 100, precision=args.precision, items_bf16=itb), args.iters, warmup=1)
-    print(f"top-100 of {args.rows} items for {args.Q} queries: {ms:.3f} ms, {2.0 * args.Q * args.rows * args.d / ms / 1e9:.2f} TFLOP/s")
+    ms = timed(lambda: F.score_topk(q, it, args.k, precision=args.precision, items_bf16=itb), args.iters, warmup=1)
+    print(f"top-{args.k} of {args.rows} items for {args.Q} queries: {ms:.3f} ms, {2.0 * args.Q * args.rows * args.d / ms / 1e9:.2f} TFLOP/s")
 
 
 if __name__ == "__main__":
@@ -104,6 +104,7 @@ if __name__ == "__main__":
     ap.add_argument("--d", type=int, default=64)
     ap.add_argument("--L", type=int, default=1)
     ap.add_argument("--Q", type=int, default=4096)
+    ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)

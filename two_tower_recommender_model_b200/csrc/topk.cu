@@ -175,6 +175,35 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int* __restrict__
 // ---------------------------------------------------------------------------
 namespace tc {
 
+// warp_insert on __shared__ lists (the pointers keep their address space, so the compiler emits
+// LDS/STS instead of generic accesses) with the rank found by ballots over the lanes' entries
+// instead of a shuffle reduction: the insert is a latency chain, so fewer dependent steps matter.
+__device__ __forceinline__ int warp_insert_smem(float* __restrict__ ls, int* __restrict__ li, int cnt, int k, float s,
+                                                int id, int lane) {
+  float es[kTkMaxK / 32];
+  int ei[kTkMaxK / 32];
+  int pos = 0;
+#pragma unroll
+  for (int t = 0; t < kTkMaxK / 32; ++t) {
+    const int e = lane + 32 * t;
+    const bool in = e < cnt;
+    es[t] = in ? ls[e] : -INFINITY;
+    ei[t] = in ? li[e] : 0;
+    pos += __popc(__ballot_sync(0xffffffffu, in && es[t] >= s));
+  }
+  if (pos >= k) return cnt;
+  const int last = min(cnt, k - 1);  // entries [pos, last) move one slot right
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < kTkMaxK / 32; ++t) {
+    const int e = lane + 32 * t;
+    if (e >= pos && e < last) { ls[e + 1] = es[t]; li[e + 1] = ei[t]; }
+  }
+  if (lane == 0) { ls[pos] = s; li[pos] = id; }
+  __syncwarp();
+  return min(cnt + 1, k);
+}
+
 constexpr int kTcTkThreads = 192;
 constexpr int kTcTkNT = 128;        // items per tile
 constexpr int kTcTkAcc = 4;         // TMEM ring (4 x 128 columns)
@@ -189,21 +218,22 @@ template <int kTcTkStages>   // smem ring depth: 3, or 2 when k > 100 needs the 
 __global__ void __launch_bounds__(kTcTkThreads, 1)
 tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmI, int Q, int N,
                      int k, int items_per_split, float* __restrict__ cand_scores, int* __restrict__ cand_idx) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sI = smem + 128 * 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sI + kTcTkStages * kTcTkNT * 128);
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  // lists and candidate buffers first, addressed straight off the __shared__ array (LDS/STS);
+  // the TMA tiles follow at the next 1024-byte boundary.
+  float* lscore = reinterpret_cast<float*>(smem_raw);             // [128][k]
+  int* lidx = reinterpret_cast<int*>(lscore + 128 * k);           // [128][k]
+  float* bscore = reinterpret_cast<float*>(lidx + 128 * k);       // [128][cap]
+  int* bidx = reinterpret_cast<int*>(bscore + 128 * kTcTkCap);    // [128][cap]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bidx + 128 * kTcTkCap);
   uint64_t* q_full = bars;
   uint64_t* i_full = bars + 1;                    // [stages]
   uint64_t* i_empty = i_full + kTcTkStages;       // [stages]
   uint64_t* acc_full = i_empty + kTcTkStages;     // [4]
   uint64_t* acc_empty = acc_full + kTcTkAcc;      // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kTcTkAcc);
-  float* lscore = reinterpret_cast<float*>(bars + 32);            // [128][k]
-  int* lidx = reinterpret_cast<int*>(lscore + 128 * k);           // [128][k]
-  float* bscore = reinterpret_cast<float*>(lidx + 128 * k);       // [128][cap]
-  int* bidx = reinterpret_cast<int*>(bscore + 128 * kTcTkCap);    // [128][cap]
+  uint8_t* sQ = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars + 32) + 1023) & ~uintptr_t(1023));
+  uint8_t* sI = sQ + 128 * 128;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
@@ -277,7 +307,7 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int* bi = bidx + rr * kTcTkCap;
         for (int e = 0; e < c; ++e) {
           const float s = bs[e];
-          if (lc < k || s > ls[k - 1]) lc = warp_insert(ls, li, lc, k, s, bi[e], lane);
+          if (lc < k || s > ls[k - 1]) lc = warp_insert_smem(ls, li, lc, k, s, bi[e], lane);
         }
         if (lane == r) lcnt = lc;
       }
