@@ -174,9 +174,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    use_graph = world == 1 and not args.no_graph
+    graph_step = None
+    launches_per_step = None
+    if use_graph:
+        # single GPU: the whole step (device KJT build, lookup, towers, loss, backward + fused update,
+        # Adam) is one CUDA graph; warm-up calls run eagerly on real batches, the 4th call captures
+        graph_step = tt.CudaGraphTrainStep(model, opt, CAT, cfg["rows"], cfg["batch"], dev, warmup_steps=3)
+        dev_raw = [(b.ids.to(dev), b.labels.to(dev)) for b in raw]
+        for i in range(3):
+            graph_step(*dev_raw[i % nb])
+        l_before = lib.tt_kernel_launch_count()
+        graph_step(*dev_raw[3 % nb])          # capture (+ first replay)
+        launches_per_step = int(lib.tt_kernel_launch_count() - l_before)
+        torch.cuda.synchronize()
+
     # ---- value: inputs resident in HBM
     for i in range(args.warmup):
-        step(resident[i % nb])
+        graph_step(*dev_raw[i % nb]) if use_graph else step(resident[i % nb])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -185,26 +200,40 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        step(resident[i % nb])
+        graph_step(*dev_raw[i % nb]) if use_graph else step(resident[i % nb])
     e1.record()
     barrier()
-    launches = lib.tt_kernel_launch_count() - l0
+    launches = launches_per_step * args.steps if use_graph else lib.tt_kernel_launch_count() - l0
     ms_value = e0.elapsed_time(e1) / args.steps
 
-    # ---- e2e: pinned host -> device -> step -> loss to host, through TrainPipelineSparseDist
-    pipe = tt.TrainPipelineSparseDist(model, opt, dev)
+    # ---- e2e: pinned host -> device -> step -> loss to host
     total = args.warmup + args.steps
-    it = iter(raw[i % nb] for i in range(total))
-    for _ in range(args.warmup):
-        float(pipe.progress(it)[0])
-    barrier()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    last = None
-    for _ in range(args.steps):
-        last = float(pipe.progress(it)[0])  # .item(): device -> host read of the loss
-    t1.record()
-    barrier()
+    if use_graph:
+        e2e_api = "CudaGraphTrainStep(ids_pinned, labels_pinned) + float(loss)"
+        for i in range(args.warmup):
+            float(graph_step(raw[i % nb].ids, raw[i % nb].labels)[0])
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        last = None
+        for i in range(args.steps):
+            last = float(graph_step(raw[i % nb].ids, raw[i % nb].labels)[0])  # device -> host read of the loss
+        t1.record()
+        barrier()
+    else:
+        e2e_api = "TrainPipelineSparseDist.progress(iterator of pinned raw batches) + float(loss)"
+        pipe = tt.TrainPipelineSparseDist(model, opt, dev)
+        it = iter(raw[i % nb] for i in range(total))
+        for _ in range(args.warmup):
+            float(pipe.progress(it)[0])
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        last = None
+        for _ in range(args.steps):
+            last = float(pipe.progress(it)[0])  # .item(): device -> host read of the loss
+        t1.record()
+        barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = t0.elapsed_time(t1) / args.steps
 
@@ -259,9 +288,9 @@ def run_ours(args):
         "dtype": "bf16 tower + logits GEMMs (fp32 accumulate, fp32 master weights) + f32 embeddings/optimizers", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1] on %d GPU(s): 2 tables 10M x 64 fp32, per-rank batch 65536, MLP 64-128-64, "
                                "in-batch softmax, fused row-wise Adagrad, Adam" % world,
-                   "per_rank_batch": B, "global_batch": B * world, "l2": "tables 5.12 GB >> 126 MB L2, random ids; no flush needed"},
+                   "per_rank_batch": B, "global_batch": B * world, "cuda_graph": bool(use_graph), "l2": "tables 5.12 GB >> 126 MB L2, random ids; no flush needed"},
         "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(ms_e2e, 4),
-                "h2d_bytes_per_step": raw[0].nbytes(), "d2h_bytes_per_step": 4, "last_loss": last},
+                "h2d_bytes_per_step": raw[0].nbytes(), "d2h_bytes_per_step": 4, "last_loss": last, "api": e2e_api},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
         "ebc_lookup_gbs": kernels.get("tt_ebc_forward", {}).get("achieved"),
     }
@@ -348,6 +377,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="N=1: run the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

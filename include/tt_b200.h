@@ -264,6 +264,11 @@ int tt_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg
                  float lr, float beta1, float beta2, float eps, float bias_correction1,
                  float bias_correction2, void* stream);
 
+/* Same update with the 1-based step counter kept in device memory (*step is incremented first, on
+ * the same stream), so that the call has constant arguments and can live in a CUDA graph. */
+int tt_adam_flat_devstep(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                         float lr, float beta1, float beta2, float eps, float* step, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Retrieval (04_evaluate_retrieval.py:134-141: similarity_search, k = 100)
  * ------------------------------------------------------------------------- */

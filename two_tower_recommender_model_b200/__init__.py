@@ -8,6 +8,7 @@ from .distributed import DistributedModelParallel, TrainPipelineSparseDist, get_
 from .distributed.comm import get_local_size  # noqa: F401
 from .distributed.planner import EmbeddingShardingPlanner, ParameterConstraints, Topology  # noqa: F401
 from .distributed.planner.storage_reservations import HeuristicalStorageReservation  # noqa: F401
+from .graph import CudaGraphTrainStep  # noqa: F401
 from .modules import MLP, EmbeddingBagCollection, EmbeddingBagConfig, PoolingType  # noqa: F401
 from .optim import FlatAdam, KeyedOptimizerWrapper, RowWiseAdagrad, RowWiseAdam  # noqa: F401
 from .retrieval import BruteForceIndex, create_keyed_jagged_tensor, embed_corpus, process_embeddings, retrieval_metrics  # noqa: F401

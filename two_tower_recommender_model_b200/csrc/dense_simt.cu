@@ -343,6 +343,26 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
   p[i] = p[i] - (lr / bc1) * (mi / denom);
 }
 
+// Adam with the step counter on the device: the launch arguments stay constant from step to step,
+// so the call can be captured in a CUDA graph.  step_inc_kernel runs first on the same stream.
+__global__ void step_inc_kernel(float* step) { *step += 1.0f; }
+
+__global__ void adam_flat_devstep_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                         float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                         const float* __restrict__ step) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t = *step;
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+  p[i] = p[i] - (lr / bc1) * (mi / denom);
+}
+
 static int launch_gemm(bool a_t, bool b_t, const float* A, int64_t lda, const float* Amask, const float* B,
                        int64_t ldb, const float* bias, float* C, int64_t ldc, int M, int N, int K, int relu,
                        int splits, int k_chunk, cudaStream_t s) {
@@ -484,6 +504,20 @@ int tt_inbatch_softmax_backward_f32(const float* q, const float* c, const float*
 #undef TT_SB
   ++g_kernel_launches;  // two launches above, one check below
   TT_CHECK_LAUNCH("inbatch_softmax_bwd");
+  return TT_OK;
+}
+
+int tt_adam_flat_devstep(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                         float beta1, float beta2, float eps, float* step, void* stream) {
+  TT_CHECK_ARG(n >= 0 && step, "adam_flat_devstep: bad args");
+  cudaStream_t s = as_stream(stream);
+  step_inc_kernel<<<1, 1, 0, s>>>(step);
+  TT_CHECK_LAUNCH("step_inc");
+  if (n == 0) return TT_OK;
+  TT_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "adam_flat_devstep: null pointer");
+  adam_flat_devstep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                     beta2, eps, step);
+  TT_CHECK_LAUNCH("adam_flat_devstep");
   return TT_OK;
 }
 

@@ -1,0 +1,73 @@
+"""Whole-step CUDA graph for the single-GPU train loop.
+
+The step (device batch construction from raw id columns, EBC lookup, towers, loss, backward with the
+fused row-wise update, dense optimizer) is a fixed sequence of ~50 kernel launches whose arguments do
+not change from step to step once the inputs live in static buffers.  ``CudaGraphTrainStep`` runs the
+first calls eagerly (warm-up with REAL batches, so nothing is trained on dummy data), then captures
+one step and replays it: per step the host issues two async copies and one graph launch.
+
+Requirements: static shapes (batches given as raw id columns ``[F, B]`` + labels ``[B]``), a
+single-GPU (unsharded) model, sparse optimizer RowWiseAdagrad or SGD (row-wise Adam's bias correction
+is host-computed), dense optimizer ``FlatAdam`` (device-side step counter) or SGD.
+"""
+from typing import List, Optional, Sequence
+
+import torch
+
+from .datasets.utils import Batch
+from .sparse.jagged_tensor import KeyedJaggedTensor
+
+
+class CudaGraphTrainStep:
+    def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, keys: Sequence[str],
+                 num_embeddings: Sequence[int], batch_size: int, device: torch.device, warmup_steps: int = 3) -> None:
+        self._model, self._opt = model, optimizer
+        self._keys = list(keys)
+        self._dev = torch.device(device)
+        F = len(self._keys)
+        self._ids = torch.zeros(F, batch_size, dtype=torch.int64, device=self._dev)
+        self._labels = torch.zeros(batch_size, dtype=torch.int32, device=self._dev)
+        self._rows = torch.tensor(list(num_embeddings), dtype=torch.int64, device=self._dev)
+        self._dense = torch.zeros(1, device=self._dev)
+        self._warmup = warmup_steps
+        self._calls = 0
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._out = None
+        self._stream = torch.cuda.Stream(device=self._dev)
+
+    def _step(self):
+        kjt = KeyedJaggedTensor.from_id_columns(self._keys, self._ids, self._rows)
+        batch = Batch(dense_features=self._dense, sparse_features=kjt, labels=self._labels)
+        self._opt.zero_grad()
+        loss, out = self._model(batch)
+        loss.backward()
+        self._opt.step()
+        return out
+
+    def __call__(self, ids: torch.Tensor, labels: torch.Tensor):
+        """``ids`` [F, B] int64 and ``labels`` [B] int32 (pinned host or device).  Returns the model's
+        second output ``(loss, logits, labels)``; the tensors are static buffers, overwritten by the next call."""
+        self._ids.copy_(ids, non_blocking=True)
+        self._labels.copy_(labels, non_blocking=True)
+        self._calls += 1
+        cur = torch.cuda.current_stream(self._dev)
+        if self._calls <= self._warmup:
+            # eager warm-up on the SAME side stream the capture will use (autograd's stream
+            # bookkeeping for the persistent .grad buffers must not point at another stream)
+            self._stream.wait_stream(cur)
+            with torch.cuda.stream(self._stream):
+                out = self._step()
+            cur.wait_stream(self._stream)
+            return out
+        if self._graph is None:
+            torch.cuda.synchronize(self._dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._stream):
+                self._out = self._step()
+            self._graph = g
+        self._graph.replay()
+        return self._out
+
+    @property
+    def captured(self) -> bool:
+        return self._graph is not None

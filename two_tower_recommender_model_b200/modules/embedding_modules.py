@@ -138,8 +138,17 @@ class EmbeddingBagCollection(nn.Module):
         offsets = features.offsets()
         if offsets.dtype != torch.int32:
             offsets = offsets.to(torch.int32)
+        if self._in_backward_kind() is not None and torch.is_grad_enabled():
+            # Fused optimizer: the tables never receive a gradient, so they are not autograd inputs.
+            # A fresh zero-size leaf keeps backward() reaching the lookup (TorchRec does the same);
+            # unlike the parameters' long-lived AccumulateGrad nodes (pinned by
+            # apply_optimizer_in_backward to the stream they were created on) it belongs to the
+            # current stream, which keeps the step capturable in a CUDA graph.
+            anchors = (torch.zeros(0, dtype=torch.float32, device=values.device, requires_grad=True),)
+        else:
+            anchors = tuple(weights)
         pooled = EbcLookup.apply(self, tuple(features.keys()), values.contiguous(), offsets.contiguous(),
-                                 features.stride(), *weights)
+                                 features.stride(), *anchors)
         return KeyedTensor(keys=self._slot_feature, length_per_key=self._slot_dim, values=pooled)
 
     # ---- plumbing for functional.EbcLookup

@@ -27,6 +27,8 @@ class FlatAdam(Optimizer):
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.step_count = 0
+        # the same counter on the device: keeps step() free of host-computed arguments (CUDA graphs)
+        self.step_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         off = 0
         with torch.no_grad():
             for p in ps:
@@ -54,7 +56,6 @@ class FlatAdam(Optimizer):
         g = self.param_groups[0]
         self.step_count += 1
         b1, b2 = g["betas"]
-        N.call("tt_adam_flat", N.ptr(self.flat_param), N.ptr(self.flat_grad), N.ptr(self.exp_avg),
+        N.call("tt_adam_flat_devstep", N.ptr(self.flat_param), N.ptr(self.flat_grad), N.ptr(self.exp_avg),
                N.ptr(self.exp_avg_sq), self.flat_param.numel(), float(g["lr"]), float(b1), float(b2),
-               float(g["eps"]), 1.0 - b1 ** self.step_count, 1.0 - b2 ** self.step_count,
-               N.stream_ptr(self.flat_param.device))
+               float(g["eps"]), N.ptr(self.step_dev), N.stream_ptr(self.flat_param.device))
