@@ -21,13 +21,12 @@
 namespace tt {
 namespace tc {
 
-constexpr int kLgThreads = 320;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
 // named barrier private to one softmax group (ids 1 and 2), 128 threads
 __device__ __forceinline__ void group_bar_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
-__device__ __forceinline__ void all_softmax_bar_sync() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
+__device__ __forceinline__ void softmax_bar_sync_all(int nthreads) { asm volatile("bar.sync 5, %0;" ::"r"(nthreads) : "memory"); }
 // one MUFU op; inputs are finite or -inf, flush-to-zero is what we want for tiny probabilities
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -98,12 +97,18 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 // ------------------------------------------------------------------ forward
 template <int KB>
 struct FwdCfg {
-  static constexpr int NT = KB <= 2 ? 256 : 128;        // C rows (logit columns) per tile
+#ifndef TT_FWD_GROUPS
+#define TT_FWD_GROUPS 4
+#endif
+  static constexpr int NG = TT_FWD_GROUPS;              // softmax warpgroups; group g takes tiles t = g (mod NG)
+  static constexpr int NT = (KB <= 2 && NG == 2) ? 256 : 128;   // C rows (logit columns) per tile
   static constexpr int NACC = 512 / NT;                 // TMEM accumulator stages (NACC x NT = 512 columns)
+  static constexpr int THREADS = 64 + NG * 128;
   static constexpr int STAGES = KB == 1 ? 4 : (KB == 3 ? 3 : 2);
+  static_assert(NACC % NG == 0 || NG % NACC == 0, "stage ownership");
   static constexpr int Q_BYTES = KB * 128 * 128;       // KB sub-tiles of [128 x 64] bf16
   static constexpr int C_BYTES = KB * NT * 128;        // KB sub-tiles of [NT x 64] bf16
-  static constexpr int SMEM = Q_BYTES + STAGES * C_BYTES + 1024 + 256 + 1024;  // + merge scratch [128][2]
+  static constexpr int SMEM = Q_BYTES + STAGES * C_BYTES + 1024 + 256 + 4096;  // + merge scratch [NG-1][128][2]
 };
 
 // running (max, sum) update over one 32-column chunk; TAIL masks columns >= B
@@ -142,7 +147,7 @@ __device__ __forceinline__ void lse_chunk(const uint32_t (&v)[32], int col0, int
 }
 
 template <int KB>
-__global__ void __launch_bounds__(kLgThreads, 1)
+__global__ void __launch_bounds__(FwdCfg<KB>::THREADS, 1)
 tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, int B,
                       float scale2, const float* __restrict__ diag, float* __restrict__ lse,
                       float* __restrict__ partial_loss, float* __restrict__ ml_out) {
@@ -224,7 +229,7 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int row = m0 + r_in;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float m = -INFINITY, l = 0.f;                   // running max / sum, log2 domain
-    for (int t = g; t < T; t += 2) {
+    for (int t = g; t < T; t += Cfg::NG) {
       const int as = t % Cfg::NACC;
       const uint32_t tcol = trow + as * NT;
       mbar_wait(&acc_full[as], (t / Cfg::NACC) & 1);
@@ -247,12 +252,17 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     // merge the two groups' partial (max, sum) of every row, then this CTA's loss partial
     float* mrg = reinterpret_cast<float*>(bars + 32);  // [128][2], own scratch (the C ring may still be in use)
-    if (g == 1) { mrg[r_in * 2] = m; mrg[r_in * 2 + 1] = l; }
-    all_softmax_bar_sync();
+    if (g > 0) { mrg[((g - 1) * 128 + r_in) * 2] = m; mrg[((g - 1) * 128 + r_in) * 2 + 1] = l; }
+    softmax_bar_sync_all(Cfg::NG * 128);
     if (g == 0) {
-      const float m1 = mrg[r_in * 2], l1 = mrg[r_in * 2 + 1];
-      const float mn = fmaxf(m, m1);
-      const float lt = l * ex2(m - mn) + ((m1 == -INFINITY) ? 0.f : l1 * ex2(m1 - mn));
+      float mn = m, lt = l;
+#pragma unroll
+      for (int og = 1; og < Cfg::NG; ++og) {
+        const float m1 = mrg[((og - 1) * 128 + r_in) * 2], l1 = mrg[((og - 1) * 128 + r_in) * 2 + 1];
+        const float m2 = fmaxf(mn, m1);
+        lt = ((mn == -INFINITY) ? 0.f : lt * ex2(mn - m2)) + ((m1 == -INFINITY) ? 0.f : l1 * ex2(m1 - m2));
+        mn = m2;
+      }
       float contrib = 0.f;
       if (row < B) {
         if (gridDim.y == 1) {
@@ -267,7 +277,7 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       contrib = warp_sum(contrib);
       if (lane == 0) red[q] = contrib;
     }
-    all_softmax_bar_sync();
+    softmax_bar_sync_all(Cfg::NG * 128);
     if (warp == 2 && lane == 0 && gridDim.y == 1) partial_loss[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
     tc_fence_before();
   }
@@ -282,8 +292,13 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 template <int KB>
 struct BwdCfg {
   static constexpr int D = KB * 64;
+#ifdef TT_BWD_NT64
+  static constexpr int NT = 64;
+  static constexpr int NSP = 4;
+#else
   static constexpr int NT = KB <= 2 ? 128 : 64;          // Y rows per tile = S/P columns per TMEM stage
   static constexpr int NSP = KB <= 2 ? 3 : 4;            // TMEM S/P stages: columns [NT*a, NT*a + NT)
+#endif
   static constexpr int NKB2 = NT / 64;                   // K blocks of the second GEMM
 #ifndef TT_BWD_GROUPS
 #define TT_BWD_GROUPS 3
@@ -578,7 +593,7 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tcm, int B, floa
     attr = true;
   }
   dim3 grid((B + 127) / 128, splits);
-  tc_softmax_fwd_kernel<KB><<<grid, kLgThreads, FwdCfg<KB>::SMEM, s>>>(tq, tcm, B, scale2, diag, lse, partial, ml);
+  tc_softmax_fwd_kernel<KB><<<grid, FwdCfg<KB>::THREADS, FwdCfg<KB>::SMEM, s>>>(tq, tcm, B, scale2, diag, lse, partial, ml);
   TT_CHECK_LAUNCH("tc_softmax_fwd");
   return TT_OK;
 }
@@ -627,7 +642,7 @@ int tt_inbatch_softmax_forward_bf16(const void* q_bf16, int64_t ldq, const void*
   if (!ws || ws_bytes < tt_inbatch_softmax_bf16_workspace_bytes(B)) return fail(TT_ERR_WORKSPACE, "inbatch_softmax_bf16: workspace too small");
   cudaStream_t s = as_stream(stream);
   const int KB = (int)((d + 63) / 64);
-  const int NT = KB <= 2 ? 256 : 128;
+  const int NT = KB <= 2 ? FwdCfg<1>::NT : 128;
   const int splits = column_splits(B, NT);
   CUtensorMap tq, tcm;
   int rc = make_tmap_bf16_2d(&tq, q_bf16, B, d, ldq, 128);
@@ -669,7 +684,7 @@ int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void
   cudaStream_t s = as_stream(stream);
   const int KB = (int)((d + 63) / 64);
   const int D = KB * 64;
-  const int NT = KB <= 2 ? 128 : 64;
+  const int NT = KB <= 2 ? BwdCfg<1>::NT : 64;
   const int splits = column_splits(B, NT);
   const float scale2 = inv_t * kLog2e;
   const float out_scale = grad_scale * inv_t / (float)B;
