@@ -308,28 +308,88 @@ ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
   Vec<VEC> g[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) g[v].zero();
-  for (int64_t j = gid; j < n; ++j) {
-    if (j > gid && keys[j] != key) break;
-    const uint32_t bag = payload[j];
+  unsigned mask = 0xffffffffu;
+  int gshift = 0;
+  if constexpr (G < 32) {
+    gshift = (threadIdx.x & 31) / G * G;
+    mask = ((1u << (G & 31)) - 1u) << gshift;
+  }
+  // geometry of one occurrence: where its gradient row starts and its mean divisor (0 = none)
+  auto locate = [&](uint32_t bag, int64_t& goff, float& flen) {
     const int sl = bag / B;
     const int b = bag - sl * B;
-    bool div = false;
-    float flen = 1.0f;
+    flen = 0.f;
     if (plan.pooling[sl] == TT_POOL_MEAN) {
       const int64_t kb = (int64_t)plan.kjt_index[sl] * B + b;
       const int len = offsets[kb + 1] - offsets[kb];
-      if (len > 1) { div = true; flen = (float)len; }
+      if (len > 1) flen = (float)len;
     }
-    const float* go = grad_out + (int64_t)b * plan.out_stride + plan.out_col[sl];
+    goff = (int64_t)b * plan.out_stride + plan.out_col[sl];
+  };
+  auto accumulate = [&](int64_t goff, float flen) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const int c = l + v * G;
       if (c < units) {
         Vec<VEC> x;
-        x.load(go + c * VEC);
-        if (div) x.div(flen);
+        x.load(grad_out + goff + c * VEC);
+        if (flen > 0.f) x.div(flen);
         g[v].add(x);
       }
+    }
+  };
+  {  // the head occurrence
+    int64_t goff;
+    float flen;
+    locate(payload[gid], goff, flen);
+    accumulate(goff, flen);
+  }
+  int64_t j = gid + 1;
+  if (j < n && keys[j] == key) {
+    // The run continues (duplicate ids; hot rows of small tables have thousands of occurrences).
+    // The group reads G (key, bag) pairs with one coalesced load, every lane resolves the geometry
+    // of ITS occurrence, and the gradient rows are then fetched two at a time in run order: the
+    // per-occurrence chain key -> bag -> offsets -> row becomes one round trip per G occurrences.
+    constexpr unsigned full = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+    bool more = true;
+    while (more) {
+      const int64_t pos = j + l;
+      const bool mine = pos < n && keys[pos] == key;
+      int64_t goff = 0;
+      float flen = 0.f;
+      if (mine) locate(payload[pos], goff, flen);
+      const unsigned same = (__ballot_sync(mask, mine) >> gshift) & full;
+      const int cnt = same == full ? G : __ffs(~same) - 1;   // length of the leading run of matches
+      more = cnt == G;
+      for (int e = 0; e < cnt; e += 2) {
+        const int64_t g0 = __shfl_sync(mask, goff, e, G);
+        const float f0 = __shfl_sync(mask, flen, e, G);
+        const int e1 = e + 1 < G ? e + 1 : e;
+        const int64_t g1 = __shfl_sync(mask, goff, e1, G);
+        const float f1 = __shfl_sync(mask, flen, e1, G);
+        Vec<VEC> x0[NV], x1[NV];
+        const bool two = e + 1 < cnt;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = l + v * G;
+          if (c < units) {
+            x0[v].load(grad_out + g0 + c * VEC);
+            if (two) x1[v].load(grad_out + g1 + c * VEC);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (l + v * G < units) {
+            if (f0 > 0.f) x0[v].div(f0);
+            g[v].add(x0[v]);
+            if (two) {
+              if (f1 > 0.f) x1[v].div(f1);
+              g[v].add(x1[v]);
+            }
+          }
+        }
+      }
+      j += G;
     }
   }
 
@@ -338,8 +398,6 @@ ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
 #pragma unroll
   for (int v = 0; v < NV; ++v)
     if (l + v * G < units) ss += g[v].sumsq();
-  unsigned mask = 0xffffffffu;
-  if constexpr (G < 32) mask = ((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G);
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(mask, ss, o);
   const float msq = ss / (float)D;
