@@ -246,7 +246,7 @@ def test_cuda_graph_step_equals_eager(cuda):
         loss, _ = m1(batch)
         loss.backward()
         o1.step()
-        losses1.append(float(loss))
+        losses1.append(float(loss.detach()))
     step = tt.CudaGraphTrainStep(m2, o2, CAT, emb, B, cuda, warmup_steps=3)
     losses2 = [float(step(ids.pin_memory(), y.pin_memory())[0]) for ids, y in data]
     assert step.captured
