@@ -235,24 +235,41 @@ cast_bf16_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
   }
 }
 
-// partial[z][c] = sum over the rows of chunk z of x[r, c] (bf16 in, fp32 accumulate)
+// partial[z][c] = sum over the rows of chunk z of x[r, c] (bf16 in, fp32 accumulate).
+// A warp reads 64 consecutive columns of a row (bf16x2 per lane = 128 B per row), 8 rows per CTA pass.
 __global__ void __launch_bounds__(256)
 colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int rows, int cols, int rows_per_chunk,
                            float* __restrict__ partial) {
-  __shared__ float red[8][33];
+  __shared__ float red[8][65];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
+  const int c = blockIdx.x * 64 + tx * 2;
   const int r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
-  float s = 0.f;
-  if (c < cols)
-    for (int r = r0 + ty; r < r1; r += 8) s += __bfloat162float(x[(int64_t)r * ldx + c]);
-  red[ty][tx] = s;
+  float s0 = 0.f, s1 = 0.f;
+  const bool pair = (c + 1 < cols) && ((ldx & 1) == 0);
+  if (c < cols) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const __nv_bfloat16* p = x + (int64_t)r * ldx + c;
+      if (pair) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(p);
+        s0 += __low2float(v);
+        s1 += __high2float(v);
+      } else {
+        s0 += __bfloat162float(p[0]);
+        if (c + 1 < cols) s1 += __bfloat162float(p[1]);
+      }
+    }
+  }
+  red[ty][tx * 2] = s0;
+  red[ty][tx * 2 + 1] = s1;
   __syncthreads();
-  if (ty == 0 && c < cols) {
-    float t = 0.f;
+  if (threadIdx.x < 64) {
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < cols) {
+      float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][tx];
-    partial[(int64_t)blockIdx.y * cols + c] = t;
+      for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+      partial[(int64_t)blockIdx.y * cols + cc] = t;
+    }
   }
 }
 
@@ -339,7 +356,7 @@ int tt_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t
 static int splitk_splits(int64_t M, int64_t N, int64_t K, int bn) {
   const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
   const int64_t total_kb = (K + kBK - 1) / kBK;
-  int64_t want = (2 * kNumSMs + tiles - 1) / tiles;      // about two waves of CTAs
+  int64_t want = (kNumSMs + tiles - 1) / tiles;          // one wave of CTAs (fewer partials to reduce)
   if (want > total_kb / 4) want = total_kb / 4;          // at least 4 K-blocks per slice
   if (want < 1) want = 1;
   return (int)want;
@@ -380,7 +397,7 @@ int tt_gemm_bf16_splitk(const void* a, int64_t lda, const void* b, int64_t ldb, 
 }
 
 size_t tt_colsum_bf16_workspace_bytes(int64_t rows, int64_t cols) {
-  const int64_t chunks = (rows + 1023) / 1024;
+  const int64_t chunks = (rows + 255) / 256;
   return align_up((size_t)chunks * cols * 4, 256) + 256;
 }
 
@@ -388,11 +405,11 @@ size_t tt_colsum_bf16_workspace_bytes(int64_t rows, int64_t cols) {
 int tt_colsum_bf16(const void* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* ws, size_t ws_bytes,
                    void* stream) {
   TT_CHECK_ARG(rows > 0 && cols > 0 && x && out, "colsum_bf16: bad args");
-  const int chunks = (int)((rows + 1023) / 1024);
+  const int chunks = (int)((rows + 255) / 256);
   if (!ws || ws_bytes < (size_t)chunks * cols * 4) return fail(TT_ERR_WORKSPACE, "colsum_bf16: workspace too small");
   cudaStream_t s = as_stream(stream);
-  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)chunks);
-  colsum_bf16_partial_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ldx, (int)rows, (int)cols, 1024,
+  dim3 grid((unsigned)((cols + 63) / 64), (unsigned)chunks);
+  colsum_bf16_partial_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ldx, (int)rows, (int)cols, 256,
                                                   static_cast<float*>(ws));
   TT_CHECK_LAUNCH("colsum_bf16_partial");
   tc_reduce_partials_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(static_cast<float*>(ws), chunks, cols, out);
