@@ -91,7 +91,8 @@ def build_model(cfg, dev):
     ebc = tt.EmbeddingBagCollection(tables=eb, device=torch.device("meta"))
     task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, cfg["layers"], device=dev, precision=cfg.get("precision", "bf16")), loss=cfg["loss"], precision=cfg.get("precision", "bf16"))
     apply_optimizer_in_backward(tt.RowWiseAdagrad, task.two_tower.ebc.parameters(), {"lr": cfg["sparse_lr"]})
-    model = tt.DistributedModelParallel(module=task, device=dev)
+    peer = cfg.get("exchange", "nccl") == "peer" and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+    model = tt.DistributedModelParallel(module=task, device=dev, sharding_kwargs={"peer_exchange": True} if peer else None)
     opt = tt.KeyedOptimizerWrapper(dict(model.named_parameters()), lambda p: tt.FlatAdam(p, lr=cfg["dense_lr"]))
     return model, opt
 
@@ -150,6 +151,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = dict(CFG2)
+    cfg["exchange"] = args.exchange
     lib = N.load()
     model, opt = build_model(cfg, dev)
     model.train()
@@ -288,7 +290,8 @@ def run_ours(args):
         "dtype": "bf16 tower + logits GEMMs (fp32 accumulate, fp32 master weights) + f32 embeddings/optimizers", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1] on %d GPU(s): 2 tables 10M x 64 fp32, per-rank batch 65536, MLP 64-128-64, "
                                "in-batch softmax, fused row-wise Adagrad, Adam" % world,
-                   "per_rank_batch": B, "global_batch": B * world, "cuda_graph": bool(use_graph), "l2": "tables 5.12 GB >> 126 MB L2, random ids; no flush needed"},
+                   "per_rank_batch": B, "global_batch": B * world, "cuda_graph": bool(use_graph),
+                   "exchange": (cfg["exchange"] if world > 1 else None), "l2": "tables 5.12 GB >> 126 MB L2, random ids; no flush needed"},
         "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(ms_e2e, 4),
                 "h2d_bytes_per_step": raw[0].nbytes(), "d2h_bytes_per_step": 4, "last_loss": last, "api": e2e_api},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
@@ -377,6 +380,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default=os.environ.get("TT_EXCHANGE", "nccl"), choices=["nccl", "peer"],
+                    help="N>1: table-wise output exchange by NCCL all-to-all, or fused into the lookup kernels over NVLink peer memory")
     ap.add_argument("--no-graph", action="store_true", help="N=1: run the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -128,10 +128,28 @@ typedef struct {
   int32_t slot_of_kjt[TT_MAX_FEATURES]; /* inverse of kjt_index; -1 = unused key */
 } tt_ebc_plan;
 
+/* A [world * rows_per_peer, stride] fp32 matrix striped over the GPUs of one box: rows
+ * [r*rows_per_peer, (r+1)*rows_per_peer) live in rank r's buffer ptr[r], which is mapped into this
+ * process (CUDA peer / symmetric memory over NVLink 5), so kernels reach it with plain ld/st. */
+#define TT_MAX_PEERS 16
+typedef struct {
+  int32_t world;
+  int32_t rows_per_peer;
+  void* ptr[TT_MAX_PEERS];
+} tt_peer_buffers;
+
 /* pooled[b, out_col[s] : +dim[s]] = sum (or mean) over ids of bag (s, b) of
  * weights[s][id].  Empty bag -> zeros.  values int64, offsets int32 [F*B+1]. */
 int tt_ebc_forward(const tt_ebc_plan* h_plan, const int64_t* values, const int32_t* offsets,
                    float* pooled, void* stream);
+
+/* Table-wise sharded lookup fused with its output exchange (TorchRec PooledEmbeddingsAllToAll,
+ * reached from pipeline.progress, utils/model_training.py:305): the owner of a table looks up the
+ * GLOBAL batch (batch_size = world * rows_per_peer bags) and stores every pooled row straight into
+ * the buffer of the rank the sample belongs to -- no all-to-all, no pack kernel.  The caller
+ * brackets the launch with a cross-rank barrier. */
+int tt_ebc_forward_peer(const tt_ebc_plan* h_plan, const int64_t* values, const int32_t* offsets,
+                        const tt_peer_buffers* h_peers, void* stream);
 
 typedef struct {
   int32_t kind;   /* TT_OPT_* */
@@ -153,6 +171,13 @@ size_t tt_ebc_backward_workspace_bytes(int64_t num_values);
 int tt_ebc_backward_fused(const tt_ebc_plan* h_plan, const tt_sparse_optimizer* h_opt,
                           const int64_t* values, int64_t num_values, const int32_t* offsets,
                           const float* grad_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Same with the gradient rows read straight from the peers' buffers (the reverse exchange of
+ * tt_ebc_forward_peer): row b of the global batch is at h_peer_grads->ptr[b / rows_per_peer]. */
+int tt_ebc_backward_fused_peer(const tt_ebc_plan* h_plan, const tt_sparse_optimizer* h_opt,
+                               const int64_t* values, int64_t num_values, const int32_t* offsets,
+                               const tt_peer_buffers* h_peer_grads, void* ws, size_t ws_bytes,
+                               void* stream);
 
 /* Stable LSD radix sort of (key, payload) pairs on keys < 2^key_bits; exposed
  * for the dedup parity tests.  Result lands in keys_out / vals_out. */

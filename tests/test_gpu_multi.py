@@ -44,9 +44,11 @@ def _worker(rank, world, port, sharding, errq):
                                                 for i, c in enumerate(CAT)], device=torch.device("meta"))
         task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, LAYERS, device=dev))
         apply_optimizer_in_backward(tt.RowWiseAdagrad, task.two_tower.ebc.parameters(), {"lr": LR})
+        peer = sharding == "table_wise_peer"   # table-wise with the exchange fused into the lookup kernels (NVLink peer memory)
+        sharding = "table_wise" if peer else sharding
         cons = {f"t_{c}": ParameterConstraints(sharding_types=[sharding]) for c in CAT} if sharding != "planner" else None
         plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world), constraints=cons).collective_plan(task, tt.get_default_sharders(), dist.GroupMember.WORLD)
-        model = tt.DistributedModelParallel(module=task, device=dev, plan=plan)
+        model = tt.DistributedModelParallel(module=task, device=dev, plan=plan, sharding_kwargs={"peer_exchange": True} if peer else None)
         model.module.two_tower.load_state_dict(ref.torchrec_state_dict())
         opt = tt.KeyedOptimizerWrapper(dict(model.named_parameters()), lambda p: torch.optim.SGD(p, lr=LR))
         pipe = tt.TrainPipelineSparseDist(model, opt, dev)
@@ -82,13 +84,13 @@ def _worker(rank, world, port, sharding, errq):
         raise
 
 
-@pytest.mark.parametrize("sharding", ["table_wise", "row_wise"])
+@pytest.mark.parametrize("sharding", ["table_wise", "row_wise", "table_wise_peer"])
 def test_two_rank_sharded_training_matches_oracle(sharding):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     ctx = mp.get_context("spawn")
     errq = ctx.SimpleQueue()
-    port = 29800 + os.getpid() % 100 + (0 if sharding == "table_wise" else 1)
+    port = 29800 + os.getpid() % 100 + ["table_wise", "row_wise", "table_wise_peer"].index(sharding)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, sharding, errq)) for r in range(2)]
     for p in procs:
         p.start()

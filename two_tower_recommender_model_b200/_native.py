@@ -38,6 +38,13 @@ class EbcPlan(Structure):
     ]
 
 
+TT_MAX_PEERS = 16
+
+
+class PeerBuffers(Structure):
+    _fields_ = [("world", c_int32), ("rows_per_peer", c_int32), ("ptr", c_void_p * TT_MAX_PEERS)]
+
+
 class SparseOptimizer(Structure):
     _fields_ = [
         ("kind", c_int32), ("lr", c_float), ("eps", c_float), ("beta1", c_float), ("beta2", c_float),
@@ -61,6 +68,8 @@ SIGNATURES = {
     "tt_kjt_bucketize_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
     "tt_kjt_block_bucketize": (c_int32, [_P, _P, _P, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, c_size_t, _P]),
     "tt_ebc_forward": (c_int32, [POINTER(EbcPlan), _P, _P, _P, _P]),
+    "tt_ebc_forward_peer": (c_int32, [POINTER(EbcPlan), _P, _P, POINTER(PeerBuffers), _P]),
+    "tt_ebc_backward_fused_peer": (c_int32, [POINTER(EbcPlan), POINTER(SparseOptimizer), _P, c_int64, _P, POINTER(PeerBuffers), _P, c_size_t, _P]),
     "tt_ebc_backward_workspace_bytes": (c_size_t, [c_int64]),
     "tt_ebc_backward_fused": (c_int32, [POINTER(EbcPlan), POINTER(SparseOptimizer), _P, c_int64, _P, _P, _P, c_size_t, _P]),
     "tt_sort_pairs_workspace_bytes": (c_size_t, [c_int64]),

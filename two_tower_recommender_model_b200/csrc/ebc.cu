@@ -73,14 +73,24 @@ struct SlotClasses {
   int id[TT_MAX_FEATURES];
 };
 
+// Row `row` of a [rows, stride] fp32 matrix that is either local (peers.world == 0) or striped
+// over the GPUs of the box in blocks of rows_per_peer rows: peers.ptr[s] is rank s's buffer, mapped
+// into this process (NVLink peer memory), so a plain ld/st reaches it.
+__device__ __forceinline__ float* peer_row(const tt_peer_buffers& peers, float* local_base, int64_t row, int stride) {
+  if (peers.world == 0) return local_base + row * stride;
+  const int s = (int)(row / peers.rows_per_peer);
+  const int64_t b = row - (int64_t)s * peers.rows_per_peer;
+  return static_cast<float*>(peers.ptr[s]) + b * stride;
+}
+
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
 template <int VEC, int G, int NV>
 __global__ void __launch_bounds__(kEbcThreads)
 ebc_forward_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_constant__ SlotClasses cls,
-                   const int64_t* __restrict__ values, const int32_t* __restrict__ offsets,
-                   float* __restrict__ pooled, int tiles_per_slot) {
+                   const __grid_constant__ tt_peer_buffers peers, const int64_t* __restrict__ values,
+                   const int32_t* __restrict__ offsets, float* __restrict__ pooled, int tiles_per_slot) {
   constexpr int NG = kEbcThreads / G;                   // bag groups per CTA
   constexpr int UB = NV >= 4 ? 1 : (NV == 2 ? 2 : 4);   // bags in flight per group
   const int slot = blockIdx.x / tiles_per_slot;
@@ -101,7 +111,7 @@ ebc_forward_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_consta
   const float* __restrict__ W = static_cast<const float*>(plan.weights[slot]);
   const uint64_t R = (uint64_t)plan.num_rows[slot];
   const bool mean = plan.pooling[slot] == TT_POOL_MEAN;
-  float* out = pooled + (int64_t)bag0 * plan.out_stride + plan.out_col[slot];
+  const int ocol = plan.out_col[slot];
   const int g = threadIdx.x / G, l = threadIdx.x % G;
 
   for (int bb = g; bb < nb; bb += NG * UB) {
@@ -177,7 +187,7 @@ ebc_forward_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_consta
             }
           }
         }
-        float* o = out + (int64_t)bi * plan.out_stride;
+        float* o = peer_row(peers, pooled, bag0 + bi, plan.out_stride) + ocol;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const int c = l + v * G;
@@ -193,7 +203,7 @@ ebc_forward_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_consta
     for (int u = 0; u < UB; ++u) {
       const int bi = bb + u * NG;
       if (bi < nb) {
-        float* o = out + (int64_t)bi * plan.out_stride;
+        float* o = peer_row(peers, pooled, bag0 + bi, plan.out_stride) + ocol;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const int c = l + v * G;
@@ -270,7 +280,7 @@ ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
                            const __grid_constant__ tt_sparse_optimizer opt,
                            const uint32_t* __restrict__ keys, const uint32_t* __restrict__ payload,
                            int64_t n, const int32_t* __restrict__ offsets,
-                           const float* __restrict__ grad_out) {
+                           const float* __restrict__ grad_out, const __grid_constant__ tt_peer_buffers peers) {
   const int64_t gid = ((int64_t)blockIdx.x * kEbcThreads + threadIdx.x) / G;
   const int l = threadIdx.x % G;
   if (gid >= n) return;
@@ -324,7 +334,8 @@ ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
       const int len = offsets[kb + 1] - offsets[kb];
       if (len > 1) flen = (float)len;
     }
-    goff = (int64_t)b * plan.out_stride + plan.out_col[sl];
+    // "offset" of the gradient row, as a pointer value: the row may live on another GPU
+    goff = reinterpret_cast<int64_t>(peer_row(peers, const_cast<float*>(grad_out), b, plan.out_stride) + plan.out_col[sl]);
   };
   auto accumulate = [&](int64_t goff, float flen) {
 #pragma unroll
@@ -332,7 +343,7 @@ ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
       const int c = l + v * G;
       if (c < units) {
         Vec<VEC> x;
-        x.load(grad_out + goff + c * VEC);
+        x.load(reinterpret_cast<const float*>(goff) + c * VEC);
         if (flen > 0.f) x.div(flen);
         g[v].add(x);
       }
@@ -373,8 +384,8 @@ ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
         for (int v = 0; v < NV; ++v) {
           const int c = l + v * G;
           if (c < units) {
-            x0[v].load(grad_out + g0 + c * VEC);
-            if (two) x1[v].load(grad_out + g1 + c * VEC);
+            x0[v].load(reinterpret_cast<const float*>(g0) + c * VEC);
+            if (two) x1[v].load(reinterpret_cast<const float*>(g1) + c * VEC);
           }
         }
 #pragma unroll
@@ -542,21 +553,36 @@ using namespace tt;
 
 extern "C" {
 
-int tt_ebc_forward(const tt_ebc_plan* h_plan, const int64_t* values, const int32_t* offsets,
-                   float* pooled, void* stream) {
+static int check_peers(const tt_peer_buffers* p, tt_peer_buffers* out, bool* all_vec4) {
+  memset(out, 0, sizeof(*out));
+  if (!p) return TT_OK;
+  if (p->world < 1 || p->world > TT_MAX_PEERS || p->rows_per_peer < 1) return fail(TT_ERR_INVALID, "peer buffers: bad world / rows_per_peer");
+  for (int i = 0; i < p->world; ++i) {
+    if (!p->ptr[i]) return fail(TT_ERR_INVALID, "peer buffers: null pointer for rank %d", i);
+    if ((reinterpret_cast<uintptr_t>(p->ptr[i]) & 15) != 0) *all_vec4 = false;
+  }
+  *out = *p;
+  return TT_OK;
+}
+
+static int ebc_forward_impl(const tt_ebc_plan* h_plan, const int64_t* values, const int32_t* offsets,
+                            float* pooled, const tt_peer_buffers* h_peers, void* stream) {
   bool all_vec4;
   int rc = validate_plan(h_plan, &all_vec4);
   if (rc) return rc;
-  TT_CHECK_ARG(offsets && pooled, "ebc_forward: null pointer");
+  tt_peer_buffers peers;
+  rc = check_peers(h_peers, &peers, &all_vec4);
+  if (rc) return rc;
+  TT_CHECK_ARG(offsets && (pooled || h_peers), "ebc_forward: null pointer");
   if (h_plan->num_slots == 0 || h_plan->batch_size == 0) return TT_OK;
-  if ((reinterpret_cast<uintptr_t>(pooled) & 15) != 0) all_vec4 = false;
+  if (!h_peers && (reinterpret_cast<uintptr_t>(pooled) & 15) != 0) all_vec4 = false;
   cudaStream_t s = as_stream(stream);
   const int tiles = (h_plan->batch_size + kBagsPerCta - 1) / kBagsPerCta;
   const unsigned grid = (unsigned)(tiles * h_plan->num_slots);
   SlotClasses cls;
   return for_each_class(h_plan, all_vec4, &cls, [&](int id) -> int {
 #define TT_LAUNCH_FWD(V, G, N)                                                                       \
-  ebc_forward_kernel<V, G, N><<<grid, kEbcThreads, 0, s>>>(*h_plan, cls, values, offsets, pooled, tiles)
+  ebc_forward_kernel<V, G, N><<<grid, kEbcThreads, 0, s>>>(*h_plan, cls, peers, values, offsets, pooled, tiles)
     TT_DISPATCH_CLASS(id, TT_LAUNCH_FWD);
 #undef TT_LAUNCH_FWD
     TT_CHECK_LAUNCH("ebc_forward");
@@ -564,18 +590,33 @@ int tt_ebc_forward(const tt_ebc_plan* h_plan, const int64_t* values, const int32
   });
 }
 
+int tt_ebc_forward(const tt_ebc_plan* h_plan, const int64_t* values, const int32_t* offsets,
+                   float* pooled, void* stream) {
+  return ebc_forward_impl(h_plan, values, offsets, pooled, nullptr, stream);
+}
+
+int tt_ebc_forward_peer(const tt_ebc_plan* h_plan, const int64_t* values, const int32_t* offsets,
+                        const tt_peer_buffers* h_peers, void* stream) {
+  TT_CHECK_ARG(h_peers != nullptr, "ebc_forward_peer: null peer buffers");
+  return ebc_forward_impl(h_plan, values, offsets, nullptr, h_peers, stream);
+}
+
 size_t tt_ebc_backward_workspace_bytes(int64_t n) {
   if (n < 1) n = 1;
   return 4 * align_up((size_t)n * 4, 256) + sort_workspace_bytes(n) + 1024;
 }
 
-int tt_ebc_backward_fused(const tt_ebc_plan* h_plan, const tt_sparse_optimizer* h_opt,
-                          const int64_t* values, int64_t n, const int32_t* offsets,
-                          const float* grad_out, void* ws, size_t ws_bytes, void* stream) {
+static int ebc_backward_impl(const tt_ebc_plan* h_plan, const tt_sparse_optimizer* h_opt,
+                             const int64_t* values, int64_t n, const int32_t* offsets,
+                             const float* grad_out, const tt_peer_buffers* h_peers, void* ws, size_t ws_bytes,
+                             void* stream) {
   bool all_vec4;
   int rc = validate_plan(h_plan, &all_vec4);
   if (rc) return rc;
-  TT_CHECK_ARG(h_opt && offsets && grad_out && n >= 0, "ebc_backward: bad args");
+  tt_peer_buffers peers;
+  rc = check_peers(h_peers, &peers, &all_vec4);
+  if (rc) return rc;
+  TT_CHECK_ARG(h_opt && offsets && (grad_out || h_peers) && n >= 0, "ebc_backward: bad args");
   TT_CHECK_ARG(h_opt->kind >= TT_OPT_DENSE_GRAD && h_opt->kind <= TT_OPT_SGD, "ebc_backward: bad optimizer kind");
   TT_CHECK_ARG(h_opt->weight_decay == 0.0f, "ebc_backward: weight_decay not supported");
   if (n == 0 || h_plan->num_slots == 0 || h_plan->batch_size == 0) return TT_OK;
@@ -588,7 +629,7 @@ int tt_ebc_backward_fused(const tt_ebc_plan* h_plan, const tt_sparse_optimizer* 
     if (h_opt->kind == TT_OPT_ROWWISE_ADAM || h_opt->kind == TT_OPT_DENSE_GRAD)
       TT_CHECK_ARG(h_plan->state1[sl] != nullptr, "ebc_backward: null state1 for slot %d", sl);
   }
-  if ((reinterpret_cast<uintptr_t>(grad_out) & 15) != 0) all_vec4 = false;
+  if (!h_peers && (reinterpret_cast<uintptr_t>(grad_out) & 15) != 0) all_vec4 = false;
   cudaStream_t s = as_stream(stream);
   Workspace w(ws, ws_bytes);
   uint32_t* keys = w.take<uint32_t>(n);
@@ -621,11 +662,24 @@ int tt_ebc_backward_fused(const tt_ebc_plan* h_plan, const tt_sparse_optimizer* 
   const unsigned grid = (unsigned)((threads + kEbcThreads - 1) / kEbcThreads);
 #define TT_LAUNCH_BWD(V, G, N)                                                                        \
   ebc_backward_update_kernel<V, G, N><<<grid, kEbcThreads, 0, s>>>(*h_plan, *h_opt, skeys, spayload, n, \
-                                                                   offsets, grad_out)
+                                                                   offsets, grad_out, peers)
   TT_DISPATCH_CLASS(id, TT_LAUNCH_BWD);
 #undef TT_LAUNCH_BWD
   TT_CHECK_LAUNCH("ebc_backward_update");
   return TT_OK;
+}
+
+int tt_ebc_backward_fused(const tt_ebc_plan* h_plan, const tt_sparse_optimizer* h_opt,
+                          const int64_t* values, int64_t n, const int32_t* offsets,
+                          const float* grad_out, void* ws, size_t ws_bytes, void* stream) {
+  return ebc_backward_impl(h_plan, h_opt, values, n, offsets, grad_out, nullptr, ws, ws_bytes, stream);
+}
+
+int tt_ebc_backward_fused_peer(const tt_ebc_plan* h_plan, const tt_sparse_optimizer* h_opt,
+                               const int64_t* values, int64_t n, const int32_t* offsets,
+                               const tt_peer_buffers* h_peer_grads, void* ws, size_t ws_bytes, void* stream) {
+  TT_CHECK_ARG(h_peer_grads != nullptr, "ebc_backward_fused_peer: null peer buffers");
+  return ebc_backward_impl(h_plan, h_opt, values, n, offsets, nullptr, h_peer_grads, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -72,6 +72,89 @@ class _ReduceScatterRows(torch.autograd.Function):
         return out, None
 
 
+class PeerExchange:
+    """Symmetric (NVLink peer-mapped) buffers for the table-wise exchange: one ``[B, D_tw]`` fp32 matrix
+    for pooled rows and one for their gradients on every rank, each mapped into every process of the
+    group.  The owner of a table writes its pooled rows straight into the buffer of the rank the
+    sample belongs to (``tt_ebc_forward_peer``) and reads the gradient rows straight from it
+    (``tt_ebc_backward_fused_peer``): the lookup kernel IS the all-to-all.  Allocation is collective."""
+
+    def __init__(self, rows: int, cols: int, device: torch.device, pg: Any) -> None:
+        import torch.distributed._symmetric_memory as symm
+        from .. import _native as N
+        self.rows, self.cols, self.pg = rows, cols, pg
+        self.world = dist.get_world_size(pg)
+        if self.world > N.TT_MAX_PEERS:
+            raise ValueError(f"peer exchange supports up to {N.TT_MAX_PEERS} ranks")
+        group = pg if pg is not None else dist.group.WORLD
+        self.pooled = symm.empty(rows, cols, dtype=torch.float32, device=device)
+        self.grad = symm.empty(rows, cols, dtype=torch.float32, device=device)
+        self._h_pooled = symm.rendezvous(self.pooled, group)
+        self._h_grad = symm.rendezvous(self.grad, group)
+        self.pooled_peers = self._peers(self._h_pooled)
+        self.grad_peers = self._peers(self._h_grad)
+
+    def _peers(self, handle):
+        from .. import _native as N
+        pb = N.PeerBuffers()
+        pb.world, pb.rows_per_peer = self.world, self.rows
+        for r, p in enumerate(handle.buffer_ptrs):
+            pb.ptr[r] = p
+        return pb
+
+    def barrier_pooled(self) -> None:
+        self._h_pooled.barrier(channel=0)
+
+    def barrier_grad(self) -> None:
+        self._h_grad.barrier(channel=0)
+
+
+class _PeerTwLookup(torch.autograd.Function):
+    """Table-wise lookup over the global batch whose stores are the output exchange and whose
+    backward reads the gradient from the peers (see ``PeerExchange``).  ``ebc`` is None on a rank
+    that owns no table-wise table: it still takes part in the barriers and stages its gradient."""
+
+    @staticmethod
+    def forward(ctx, ex, ebc, layout, kjt_keys, values, offsets, *anchors):
+        from ctypes import byref
+        from .. import _native as N
+        ex.barrier_pooled()           # every rank is done with the previous contents of the buffers
+        if ebc is not None:
+            dev = values.device
+            plan, _ = ebc._build_plan(kjt_keys, ex.world * ex.rows, with_state=False, out_layout=layout)
+            N.call("tt_ebc_forward_peer", byref(plan), N.ptr(values), N.ptr(offsets), byref(ex.pooled_peers), N.stream_ptr(dev))
+            ctx.save_for_backward(values, offsets)
+        ex.barrier_pooled()           # every owner's rows have landed here
+        ctx.ex, ctx.ebc, ctx.layout, ctx.kjt_keys, ctx.n_anchors = ex, ebc, layout, kjt_keys, len(anchors)
+        return ex.pooled.clone()
+
+    @staticmethod
+    def backward(ctx, grad):
+        from ctypes import byref
+        from .. import _native as N
+        ex, ebc = ctx.ex, ctx.ebc
+        ex.grad.copy_(grad)
+        ex.barrier_grad()             # every rank's gradient rows are staged
+        grads = (None,) * ctx.n_anchors
+        if ebc is not None:
+            values, offsets = ctx.saved_tensors
+            dev = values.device
+            spec = ebc._sparse_optimizer_spec(advance_step=True)
+            dense_grads = None
+            if spec is None:
+                dense_grads = ebc._alloc_dense_grads()
+                spec = N.SparseOptimizer(kind=N.OPT_DENSE_GRAD)
+            plan, _ = ebc._build_plan(ctx.kjt_keys, ex.world * ex.rows, with_state=True, dense_grads=dense_grads, out_layout=ctx.layout)
+            n = values.numel()
+            ws = N.workspace(N.load().tt_ebc_backward_workspace_bytes(n), dev)
+            N.call("tt_ebc_backward_fused_peer", byref(plan), byref(spec), N.ptr(values), n, N.ptr(offsets),
+                   byref(ex.grad_peers), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+            if dense_grads is not None:
+                grads = tuple(dense_grads)
+        ex.barrier_grad()             # nobody still reads this rank's gradient rows
+        return (None,) * 6 + grads
+
+
 def _native_bucketize(lengths, offsets, values, num_rows, F, B, W):
     from ..functional import block_bucketize
     return block_bucketize(lengths, offsets, values, num_rows, F, B, W)
@@ -98,8 +181,12 @@ class _Group:
 class ShardedEmbeddingBagCollection(nn.Module):
     def __init__(self, ebc: EmbeddingBagCollection, plan: Dict[str, ParameterSharding], device: torch.device, pg: Any = None,
                  local_ebc_factory: Callable[[List[EmbeddingBagConfig], torch.device], nn.Module] = _default_local_ebc,
-                 bucketize_fn: Callable = _native_bucketize) -> None:
+                 bucketize_fn: Callable = _native_bucketize, peer_exchange: bool = False) -> None:
+        """``peer_exchange=True`` replaces the table-wise output all-to-all (and its backward) by
+        stores / loads over NVLink peer memory issued by the lookup kernels themselves."""
         super().__init__()
+        self._peer_exchange = bool(peer_exchange)
+        self._peer: Optional[PeerExchange] = None
         self._pg = pg
         self._rank = dist.get_rank(pg)
         self._world = dist.get_world_size(pg)
@@ -260,7 +347,9 @@ class ShardedEmbeddingBagCollection(nn.Module):
         cols: Dict[str, torch.Tensor] = {}
         # table-wise: lookup over the global batch, rows go home by all-to-all
         d_by_rank = [sum(self._tw.feat_dim[f] for f in d) for d in self._tw.dest_features]
-        if self._tw.features:
+        if self._tw.features and self._peer_exchange:
+            cols.update(self._tw_forward_peer(ctx, B))
+        elif self._tw.features:
             d_loc = d_by_rank[self._rank]
             if ctx["tw"] is not None:
                 pooled = self.tw_ebc(ctx["tw"]).values()            # [W*B, d_loc]
@@ -297,6 +386,29 @@ class ShardedEmbeddingBagCollection(nn.Module):
                 c0 += d
         values = torch.cat([cols[f] for f in self._out_features], dim=1)
         return KeyedTensor(keys=self._out_features, length_per_key=self._out_dims, values=values)
+
+    def _tw_forward_peer(self, ctx, B: int) -> Dict[str, torch.Tensor]:
+        tw_out = [f for f in self._out_features if f in self._tw.feat_dim]
+        col, layout_cols = 0, {}
+        for f in tw_out:
+            layout_cols[f] = col
+            col += self._tw.feat_dim[f]
+        if self._peer is None or self._peer.rows != B:
+            self._peer = PeerExchange(B, col, self._device, self._pg)   # collective: B is the same on every rank
+        kjt, ebc = ctx["tw"], self.tw_ebc
+        if kjt is None:
+            ebc, keys = None, ()
+            values = offsets = None
+            anchors = (torch.zeros(0, dtype=torch.float32, device=self._device, requires_grad=torch.is_grad_enabled()),)
+        else:
+            keys = tuple(kjt.keys())
+            values, offsets = kjt.values().contiguous(), kjt.offsets().to(torch.int32).contiguous()
+            if ebc._in_backward_kind() is not None and torch.is_grad_enabled():
+                anchors = (torch.zeros(0, dtype=torch.float32, device=self._device, requires_grad=True),)
+            else:
+                anchors = tuple(ebc.embedding_bags[c.name].weight for c in ebc.embedding_bag_configs())
+        out = _PeerTwLookup.apply(self._peer, ebc, (col, layout_cols), keys, values, offsets, *anchors)
+        return {f: out[:, layout_cols[f]:layout_cols[f] + self._tw.feat_dim[f]] for f in tw_out}
 
     # ---- checkpoint surface: ShardedTensor entries named like the unsharded module --------------
     def _local_weight(self, name: str) -> Optional[torch.Tensor]:

@@ -153,7 +153,10 @@ class EmbeddingBagCollection(nn.Module):
 
     # ---- plumbing for functional.EbcLookup
     def _build_plan(self, kjt_keys: Tuple[str, ...], batch: int, with_state: bool,
-                    dense_grads: Optional[List[torch.Tensor]] = None) -> Tuple[N.EbcPlan, int]:
+                    dense_grads: Optional[List[torch.Tensor]] = None,
+                    out_layout: Optional[Tuple[int, Dict[str, int]]] = None) -> Tuple[N.EbcPlan, int]:
+        """``out_layout`` = (row stride, first column per feature) places the pooled columns in a wider
+        matrix than this collection's own (the sharded module's exchange buffer)."""
         plan = N.EbcPlan()
         nk = len(kjt_keys)
         if nk > N.TT_MAX_FEATURES:
@@ -161,7 +164,7 @@ class EmbeddingBagCollection(nn.Module):
         plan.num_slots = len(self._slot_feature)
         plan.batch_size = batch
         plan.num_kjt_keys = nk
-        plan.out_stride = self._total_dim
+        plan.out_stride = self._total_dim if out_layout is None else out_layout[0]
         key_pos = {k: i for i, k in enumerate(kjt_keys)}
         row_base, acc = [], 0
         for cfg in self._embedding_bag_configs:
@@ -183,7 +186,7 @@ class EmbeddingBagCollection(nn.Module):
             plan.dim[s] = cfg.embedding_dim
             plan.kjt_index[s] = key_pos[feat]
             plan.slot_of_kjt[key_pos[feat]] = s
-            plan.out_col[s] = col
+            plan.out_col[s] = col if out_layout is None else out_layout[1][feat]
             plan.pooling[s] = N.POOL_MEAN if cfg.pooling == PoolingType.MEAN else N.POOL_SUM
             col += cfg.embedding_dim
             if with_state:
