@@ -43,6 +43,23 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t 
   return TT_OK;
 }
 
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(TT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 4) != 0)
+    return fail(TT_ERR_INVALID, "TMA fp32 operand must be 16-byte aligned with a row pitch that is a multiple of 4 elements");
+  if (rows <= 0 || cols <= 0 || box_rows <= 0 || box_rows > 256) return fail(TT_ERR_INVALID, "bad TMA shape");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TT_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed (%d)", (int)r);
+  return TT_OK;
+}
+
 // ------------------------------------------------------------------ kernel
 struct GemmEpilogue {
   const float* bias;        // [N] or null

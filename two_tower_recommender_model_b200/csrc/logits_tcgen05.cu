@@ -16,6 +16,9 @@
 // warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2-5 / 6-9: softmax groups 0 / 1.
 // Both kernels are bound by the MUFU (ex2) pipe, not the tensor pipe, at d = 64: a 128 x 256
 // logits tile costs 512 tensor cycles but 2048 MUFU cycles (16 ex2 / clk / SM).
+#include <stdlib.h>
+#include <string.h>
+
 #include "tc_common.cuh"
 
 namespace tt {
@@ -519,6 +522,314 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------ fused backward (d <= 64)
+// ONE pass over the [B, B] probabilities gives both gradients: every P tile is computed once
+// (one exponential per logit instead of two) and feeds two tensor-core products,
+//     accX[r, :] += sum_c P(r, c) Y[c, :]        accY[c, :] += sum_r P(r, c) X[r, :].
+// A CTA owns RT = 2 row tiles of X (256 rows, accX resident in TMEM) and a chunk of the column tiles;
+// accY of each column tile is complete within the CTA after its two row tiles and leaves through a
+// TMA reduce-add (fp32 add in L2), accX leaves the same way once per CTA.  P goes TMEM -> registers ->
+// bf16 in shared memory (128-byte swizzle) and is read by the tensor core twice: K-major as the A
+// operand of P.Y and MN-major ("transposed") as the A operand of P^T.X; the X and Y tiles TMA loaded
+// for S = X Y^T double as the MN-major B operands, so no transposed copies of X / Y exist.
+//   warpgroup 0: warp 0 TMA, warp 1 MMA issuer | warpgroups 1-4: softmax groups (row tile i, 64-column half h) |
+//   warpgroup 5: flush.  A softmax thread pulls its 64 columns of the S row into registers at once, which frees
+//   the TMEM stage for the next S a whole tile early; setmaxnreg moves registers from warpgroup 0 to the others.
+//   TMEM: S stage of row tile i [128i, 128i+128) | accX_i [256+64i, +64) | accY double buffer [384+64b, +64)
+// The sums are finished by softmax_bwd_finalize_kernel: out = gate * out_scale * (acc - other side's row).
+struct FusedCfg {
+  static constexpr int RT = 2, NT = 128, YS = 3, PB = 4;     // PB: P buffers, two private to each softmax group
+  static constexpr int CH = 2;                           // softmax groups per row tile (each takes NT/CH columns of the row)
+  static constexpr int THREADS = 128 * (2 + RT * CH);    // warpgroups: {TMA, MMA, -, -} | RT*CH softmax groups | flush
+  static constexpr int REGS_CTRL = 40, REGS_SOFTMAX = 96, REGS_FLUSH = 56;   // setmaxnreg: 40 + 4*96 + 56 = 6 * 80 (launch value)
+  static constexpr int REGS_LAUNCH = (65536 / THREADS) / 8 * 8;   // what every warp owns when the kernel starts
+  static_assert(REGS_CTRL + RT * CH * REGS_SOFTMAX + REGS_FLUSH <= REGS_LAUNCH * (THREADS / 128),
+                "setmaxnreg.inc only draws from what setmaxnreg.dec released inside the CTA");
+  static constexpr int TILE = 128 * 128;                 // one [128 x 64] bf16 tile, bytes
+  static constexpr int X_BYTES = RT * TILE;
+  static constexpr int P_BYTES = 2 * TILE;               // two panels [128 r x 64 c]
+  static constexpr int STG_BYTES = TILE;                 // one box [128 rows x 32 fp32]: accumulators leave in two halves
+  static constexpr int SMEM = X_BYTES + YS * TILE + PB * P_BYTES + STG_BYTES + 1024 + 512;
+  static constexpr int ACCX_COL = 256, ACCY_COL = 384;
+};
+
+// one 32-column chunk of S -> P -> four 16-byte pieces of the swizzled bf16 row in shared memory
+__device__ __forceinline__ void p_chunk_smem(const uint32_t (&v)[32], uint32_t row_addr, int slot0, int r7, float lrow,
+                                             float scale2) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    float p[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x = fmaf(__uint_as_float(v[m * 8 + e]), scale2, -lrow);
+      p[e] = use_poly<kPolyBwd>(m * 8 + e) ? ex2_poly<3>(x) : ex2(x);
+    }
+    st_shared_v4(row_addr + (((slot0 + m) ^ r7) << 4), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]),
+                 pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+  }
+}
+
+__device__ __forceinline__ void flush_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// 64 fp32 accumulator columns of this thread's TMEM lane -> swizzled staging box -> TMA reduce-add, 32 columns at a time
+__device__ __forceinline__ void flush_acc(uint32_t taddr, uint32_t stg, int r_in, bool leader, const CUtensorMap* tm,
+                                          int row0, int d, uint64_t* release_bar) {
+  const uint32_t rowa = stg + r_in * 128;
+  const int r7 = r_in & 7;
+  const int halves = d > 32 ? 2 : 1;
+#pragma unroll 1
+  for (int h = 0; h < halves; ++h) {
+    uint32_t a[32];
+    tmem_ld32(taddr + 32 * h, a);
+    tmem_ld_wait();
+    if (h == halves - 1 && release_bar != nullptr) {
+      tc_fence_before();
+      mbar_arrive(release_bar);
+    }
+    if (leader) bulk_wait_group_read0();   // the previous reduce has finished reading the staging box
+    flush_bar_sync();
+#pragma unroll
+    for (int m = 0; m < 8; ++m) st_shared_v4(rowa + ((m ^ r7) << 4), a[4 * m], a[4 * m + 1], a[4 * m + 2], a[4 * m + 3]);
+    fence_proxy_async_smem();
+    flush_bar_sync();
+#ifndef TT_FUSED_NO_REDUCE   // diagnostic builds only: time the kernel without the L2 reduce traffic
+    if (leader) {
+      tma_reduce_add_2d(tm, reinterpret_cast<const void*>(__cvta_shared_to_generic(stg)), 32 * h, row0);
+      bulk_commit_group();
+    }
+#endif
+  }
+}
+
+__global__ void __launch_bounds__(FusedCfg::THREADS, 1)
+tc_softmax_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                            const __grid_constant__ CUtensorMap tmAccX, const __grid_constant__ CUtensorMap tmAccY,
+                            int B, int d, float scale2, const float* __restrict__ lse) {
+  using Cfg = FusedCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sX = smem;
+  uint8_t* sY = sX + Cfg::X_BYTES;
+  uint8_t* sP = sY + Cfg::YS * Cfg::TILE;
+  uint8_t* sStg = sP + Cfg::PB * Cfg::P_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + Cfg::STG_BYTES);
+  uint64_t* x_full = bars;
+  uint64_t* y_full = x_full + 1;            // [YS]
+  uint64_t* y_empty = y_full + Cfg::YS;     // [YS]
+  uint64_t* s_full = y_empty + Cfg::YS;     // [RT]
+  uint64_t* s_empty = s_full + Cfg::RT;     // [RT]
+  uint64_t* p_full = s_empty + Cfg::RT;     // [PB]
+  uint64_t* p_empty = p_full + Cfg::PB;     // [PB]
+  uint64_t* ay_full = p_empty + Cfg::PB;    // [2]
+  uint64_t* ay_empty = ay_full + 2;         // [2]
+  uint64_t* ax_full = ay_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ax_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * (Cfg::RT * 128);
+  const int Tall = (B + 127) / 128;
+  const int Tper = (Tall + gridDim.y - 1) / gridDim.y;
+  const int t0 = blockIdx.y * Tper;
+  const int T = max(0, min(Tper, Tall - t0));       // the host guarantees T >= 1
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmY);
+    prefetch_tmap(&tmAccX);
+    prefetch_tmap(&tmAccY);
+    mbar_init(x_full, 1);
+    for (int s = 0; s < Cfg::YS; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
+    for (int s = 0; s < Cfg::RT; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 128 * Cfg::CH); }
+    for (int s = 0; s < Cfg::PB; ++s) { mbar_init(&p_full[s], 128 * Cfg::CH); mbar_init(&p_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&ay_full[s], 1); mbar_init(&ay_empty[s], 128); }
+    mbar_init(ax_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int wg = warp >> 2;
+  if (wg == 0) {
+    setmaxnreg_dec<Cfg::REGS_CTRL>();
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_expect_tx(x_full, Cfg::X_BYTES);
+        for (int i = 0; i < Cfg::RT; ++i) tma_load_2d(sX + i * Cfg::TILE, &tmX, x_full, 0, m0 + i * 128);
+        for (int t = 0; t < T; ++t) {
+          const int s = t % Cfg::YS;
+          mbar_wait_relaxed(&y_empty[s], ((t / Cfg::YS) & 1) ^ 1);
+          mbar_expect_tx(&y_full[s], Cfg::TILE);
+          tma_load_2d(sY + s * Cfg::TILE, &tmY, &y_full[s], 0, (t0 + t) * 128);
+        }
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idescS = idesc_bf16_f32(128, 128);
+      constexpr uint32_t idescX = idesc_bf16_f32(128, 64) | kIdescBMnMajor;                    // P . Y
+      constexpr uint32_t idescY = idesc_bf16_f32(128, 64) | kIdescAMnMajor | kIdescBMnMajor;   // P^T . X
+      if (elect_one()) {
+        const uint32_t aX = smem_u32(sX), aY = smem_u32(sY), aP = smem_u32(sP);
+        auto ready = [&](uint64_t* bar, uint32_t parity) -> bool {   // non-blocking phase test
+          uint32_t ok;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+              : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+          return ok != 0;
+        };
+        auto issue_s = [&](int i, int j) {
+          const int ys = j % Cfg::YS;
+          tc_fence_after();
+          const uint64_t da = smem_desc_k_sw128(aX + i * Cfg::TILE);
+          const uint64_t db = smem_desc_k_sw128(aY + ys * Cfg::TILE);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(tmem_base + i * 128, da + 2 * k, db + 2 * k, idescS, k != 0);
+          tc_commit(&s_full[i]);
+        };
+        // products of P(i, j); `first` / `last`: first / second of the two row tiles to reach column tile j
+        auto consume = [&](int i, int j, bool first, bool last) {
+          const int n = 2 * j + i, pb = n % Cfg::PB, b = j & 1, ys = j % Cfg::YS;
+          tc_fence_after();
+          const uint32_t P = aP + pb * Cfg::P_BYTES, Y = aY + ys * Cfg::TILE, X = aX + i * Cfg::TILE;
+#ifndef TT_FUSED_SKIP_DX
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {      // accX_i += P[r, 16kk..] . Y[16kk.., :]
+            const uint64_t da = smem_desc_k_sw128(P + (kk >> 2) * Cfg::TILE) + 2 * (kk & 3);
+            const uint64_t db = smem_desc_mn_sw128(Y + kk * 2048, 1024, 1024);
+            mma_ss(tmem_base + Cfg::ACCX_COL + 64 * i, da, db, idescX, (j | kk) != 0);
+          }
+#endif
+#ifndef TT_FUSED_SKIP_DY
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {      // accY_j += P[16kk.., c]^T . X[16kk.., :]
+            const uint64_t da = smem_desc_mn_sw128(P + kk * 2048, Cfg::TILE, 1024);
+            const uint64_t db = smem_desc_mn_sw128(X + kk * 2048, 1024, 1024);
+            mma_ss(tmem_base + Cfg::ACCY_COL + 64 * b, da, db, idescY, (first ? kk : 1) != 0);
+          }
+#endif
+          tc_commit(&p_empty[pb]);
+          if (last) {
+            tc_commit(&ay_full[b]);
+            tc_commit(&y_empty[ys]);
+          }
+        };
+        mbar_wait_relaxed(x_full, 0);
+        // Event driven: issue whatever is ready, S tiles first (a softmax group frees its S stage at the
+        // start of a tile, so S(i, j+1) can be a whole tile early); tcgen05.mma executes in issue order.
+        int js[2] = {0, 0}, jc[2] = {0, 0};
+        while (jc[0] < T || jc[1] < T) {
+          bool progress = false;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int j = js[i];
+            if (j < T && ready(&y_full[j % Cfg::YS], (j / Cfg::YS) & 1) && ready(&s_empty[i], (j & 1) ^ 1)) {
+              issue_s(i, j);
+              js[i] = j + 1;
+              progress = true;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int j = jc[i];
+            if (j >= T) continue;
+            const int n = 2 * j + i;
+            const bool first = jc[1 - i] <= j;         // the other row tile has not reached column tile j yet
+            if (!ready(&p_full[n % Cfg::PB], (n / Cfg::PB) & 1)) continue;
+            if (first && !ready(&ay_empty[j & 1], ((j >> 1) & 1) ^ 1)) continue;   // flush group still reads accY(j-2)
+            consume(i, j, first, !first);
+            jc[i] = j + 1;
+            progress = true;
+          }
+          if (!progress) __nanosleep(32);
+        }
+        tc_commit(ax_full);
+      }
+    }
+  } else if (wg <= Cfg::RT * Cfg::CH) {
+    setmaxnreg_inc<Cfg::REGS_SOFTMAX>();
+    const int q = warp & 3;
+    const int i = (wg - 1) / Cfg::CH;                // row tile of this softmax group
+    const int h = (wg - 1) % Cfg::CH;                // its 64-column half of every S tile = panel h of P
+    const int r_in = q * 32 + lane;
+    const int row = m0 + i * 128 + r_in;
+    const uint32_t ts = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + i * 128 + h * 64;
+    const float lrow = row < B ? lse[row] * kLog2e : 0.f;   // rows >= B: X row is zero, contributes nothing
+    const int r7 = r_in & 7;
+    const uint32_t prow0 = smem_u32(sP) + h * Cfg::TILE + r_in * 128;
+    for (int j = 0; j < T; ++j) {
+      const int n = 2 * j + i, pb = n % Cfg::PB;
+      const uint32_t prow = prow0 + pb * Cfg::P_BYTES;
+      uint32_t va[32], vb[32];
+      mbar_wait(&s_full[i], j & 1);
+      tc_fence_after();
+      tmem_ld32(ts, va);
+      tmem_ld32(ts + 32, vb);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[i]);                            // the row is in registers: S stage free for tile j+1
+      mbar_wait(&p_empty[pb], ((n / Cfg::PB) & 1) ^ 1);    // the products of the tile that used this buffer are done
+      p_chunk_smem(va, prow, 0, r7, lrow, scale2);
+      p_chunk_smem(vb, prow, 4, r7, lrow, scale2);
+      fence_proxy_async_smem();
+      mbar_arrive(&p_full[pb]);
+    }
+  } else {
+    setmaxnreg_dec<Cfg::REGS_FLUSH>();
+    const int q = warp & 3;
+    const int r_in = q * 32 + lane;
+    const bool leader = threadIdx.x == (1 + Cfg::RT * Cfg::CH) * 128;
+    const uint32_t tl = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t stg = smem_u32(sStg);
+    for (int j = 0; j < T; ++j) {
+      const int b = j & 1;
+      mbar_wait_relaxed(&ay_full[b], (j >> 1) & 1);
+      tc_fence_after();
+      flush_acc(tl + Cfg::ACCY_COL + 64 * b, stg, r_in, leader, &tmAccY, (t0 + j) * 128, d, &ay_empty[b]);
+    }
+    mbar_wait_relaxed(ax_full, 0);
+    tc_fence_after();
+    for (int i = 0; i < Cfg::RT; ++i)
+      if (m0 + i * 128 < B) flush_acc(tl + Cfg::ACCX_COL + 64 * i, stg, r_in, leader, &tmAccX, m0 + i * 128, d, nullptr);
+    if (leader) bulk_wait_group0();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// out = gate * out_scale * (acc - other), in place over the accumulated sums (4 columns per thread)
+template <int VEC>
+__global__ void __launch_bounds__(256)
+softmax_bwd_finalize_kernel(float* __restrict__ out, int64_t ld_out, const float* __restrict__ other, int64_t ld_other,
+                            const float* __restrict__ mask, int64_t ld_mask, float out_scale, int B, int d) {
+  const int per_row = (d + VEC - 1) / VEC;
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (int64_t)B * per_row) return;
+  const int row = (int)(idx / per_row), c0 = (int)(idx % per_row) * VEC;
+  if (VEC == 4) {
+    float4 a = *reinterpret_cast<const float4*>(out + (int64_t)row * ld_out + c0);
+    const float4 o = *reinterpret_cast<const float4*>(other + (int64_t)row * ld_other + c0);
+    a.x = out_scale * (a.x - o.x); a.y = out_scale * (a.y - o.y); a.z = out_scale * (a.z - o.z); a.w = out_scale * (a.w - o.w);
+    if (mask != nullptr) {
+      const float4 g = *reinterpret_cast<const float4*>(mask + (int64_t)row * ld_mask + c0);
+      a.x = g.x > 0.f ? a.x : 0.f; a.y = g.y > 0.f ? a.y : 0.f; a.z = g.z > 0.f ? a.z : 0.f; a.w = g.w > 0.f ? a.w : 0.f;
+    }
+    *reinterpret_cast<float4*>(out + (int64_t)row * ld_out + c0) = a;
+  } else {
+    float a = out_scale * (out[(int64_t)row * ld_out + c0] - other[(int64_t)row * ld_other + c0]);
+    if (mask != nullptr && !(mask[(int64_t)row * ld_mask + c0] > 0.f)) a = 0.f;
+    out[(int64_t)row * ld_out + c0] = a;
+  }
+}
+
 // diag[b] = inv_t * sum_k bf16(q[b,k]) * bf16(c[b,k])   (what the tensor core computes for S_bb)
 __global__ void __launch_bounds__(256)
 rowdot_bf16_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ c, int64_t ldc,
@@ -620,6 +931,62 @@ static int launch_bwd(const CUtensorMap& tx, const CUtensorMap& ty, const CUtens
   return TT_OK;
 }
 
+// Column chunks of the fused backward: minimise waves x (tiles per CTA + fixed cost), fixed cost ~ 3 tiles
+static int fused_chunks(int64_t B) {
+  const int64_t sb = (B + 255) / 256, tall = (B + 127) / 128;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int ch = 1; ch <= 64 && ch <= tall; ++ch) {
+    const int64_t tper = (tall + ch - 1) / ch;
+    if ((int64_t)(ch - 1) * tper >= tall) continue;     // an empty chunk
+    const int64_t waves = (sb * ch + kNumSMs - 1) / kNumSMs;
+    const double cost = (double)waves * (double)(tper + 3);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = ch; }
+  }
+  return best;
+}
+
+static int finalize_grad(float* out, int64_t ld_out, const float* other, int64_t ld_other, const float* mask, int64_t ld_mask,
+                         float out_scale, int B, int d, cudaStream_t s) {
+  const bool vec = (d % 4) == 0 && (ld_out % 4) == 0 && (ld_other % 4) == 0 && (mask == nullptr || (ld_mask % 4) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(other) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
+  if (vec) {
+    const int64_t n = (int64_t)B * (d / 4);
+    softmax_bwd_finalize_kernel<4><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, ld_out, other, ld_other, mask, ld_mask, out_scale, B, d);
+  } else {
+    const int64_t n = (int64_t)B * d;
+    softmax_bwd_finalize_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, ld_out, other, ld_other, mask, ld_mask, out_scale, B, d);
+  }
+  TT_CHECK_LAUNCH("softmax_bwd_finalize");
+  return TT_OK;
+}
+
+static int launch_bwd_fused(const void* q_bf16, int64_t ldq, const void* c_bf16, int64_t ldc, const float* q_f32, int64_t ldqf,
+                            const float* c_f32, int64_t ldcf, const float* lse, int B, int d, float scale2, float out_scale,
+                            const float* gate_q, const float* gate_c, float* dq, int64_t lddq, float* dc, int64_t lddc,
+                            cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_softmax_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM);
+    if (e != cudaSuccess) return fail(TT_ERR_CUDA, "softmax_bwd_fused smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  CUtensorMap tq, tcm, tdq, tdc;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tq, q_bf16, B, d, ldq, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tcm, c_bf16, B, d, ldc, 128))) return rc;
+  if ((rc = make_tmap_f32_2d(&tdq, dq, B, d, lddq, 128))) return rc;
+  if ((rc = make_tmap_f32_2d(&tdc, dc, B, d, lddc, 128))) return rc;
+  cudaError_t e = cudaMemset2DAsync(dq, (size_t)lddq * 4, 0, (size_t)d * 4, (size_t)B, s);
+  if (e == cudaSuccess) e = cudaMemset2DAsync(dc, (size_t)lddc * 4, 0, (size_t)d * 4, (size_t)B, s);
+  if (e != cudaSuccess) return fail(TT_ERR_CUDA, "softmax_bwd_fused memset: %s", cudaGetErrorString(e));
+  dim3 grid((unsigned)((B + 255) / 256), (unsigned)fused_chunks(B));
+  tc_softmax_bwd_fused_kernel<<<grid, FusedCfg::THREADS, FusedCfg::SMEM, s>>>(tq, tcm, tdq, tdc, B, d, scale2, lse);
+  TT_CHECK_LAUNCH("tc_softmax_bwd_fused");
+  if ((rc = finalize_grad(dq, lddq, c_f32, ldcf, gate_q, ldqf, out_scale, B, d, s))) return rc;
+  return finalize_grad(dc, lddc, q_f32, ldqf, gate_c, ldcf, out_scale, B, d, s);
+}
+
 }  // namespace tc
 }  // namespace tt
 
@@ -698,6 +1065,12 @@ int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void
   if ((rc = make_tmap_bf16_2d(&tct, ct_bf16, d, B, ldct, D))) return rc;
   const float* gate_q = relu_gate ? q_f32 : nullptr;
   const float* gate_c = relu_gate ? c_f32 : nullptr;
+  // d <= 64: one pass over P for both gradients.  TT_SOFTMAX_BWD=split keeps the two-pass kernels (A/B runs).
+  static const bool force_split = [] { const char* v = getenv("TT_SOFTMAX_BWD"); return v != nullptr && strcmp(v, "split") == 0; }();
+  if (KB == 1 && !force_split && (lddq % 4) == 0 && (lddc % 4) == 0 &&
+      ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dc)) & 15) == 0)
+    return launch_bwd_fused(q_bf16, ldq, c_bf16, ldc, q_f32, ldqf, c_f32, ldcf, lse, (int)B, (int)d, scale2, out_scale, gate_q,
+                            gate_c, dq, lddq, dc, lddc, s);
 #define TT_LB(KBV)                                                                                              \
   do {                                                                                                          \
     rc = launch_bwd<KBV, true>(tq128, tcn, tct, (int)B, (int)d, scale2, lse, c_f32, ldcf, gate_q, ldqf, out_scale, dq, lddq, splits, s); \

@@ -156,16 +156,47 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                          // SWIZZLE_128B
   return d;
 }
+// MN-major operand tile, 128-byte swizzle: the SAME bytes TMA SWIZZLE_128B writes for a row-major
+// [K rows][64 MN elements] bf16 tile, read "transposed" by the tensor core.  Atom = 64 MN elements
+// (128 B) x 8 K rows (1024 B); lbo = distance between atoms along MN, sbo = along K.  One
+// tcgen05.mma (K = 16) spans two K atoms; advancing K by 16 rows = +2048 bytes on the start address.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // kind::f16, A = B = bf16, D = f32, both operands K-major
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+constexpr uint32_t kIdescAMnMajor = 1u << 15;   // A operand is MN-major (default: K-major)
+constexpr uint32_t kIdescBMnMajor = 1u << 16;   // B operand is MN-major
+
+// ---- TMA reduce-add (shared -> global, fp32 add performed in L2), bulk-group completion
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c_inner, int c_outer) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ------------------------------------------------------------------ host: tensor maps
 // Row-major bf16 matrix [rows, cols] (cols contiguous, row pitch ld elements);
 // box = box_rows x 64 columns (128 B), SWIZZLE_128B, out-of-bounds reads give zeros.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+// Row-major fp32 matrix; box = box_rows x 32 columns (128 B), SWIZZLE_128B (target of tma_reduce_add_2d).
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
 }  // namespace tc
 }  // namespace tt
