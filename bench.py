@@ -276,13 +276,14 @@ def run_ours(args):
     roof = None
     if sm_ms > 0:
         ach = logit_flops / (sm_ms * 1e-3) / 1e12
-        roof = {"kernel": "in-batch softmax: tc_softmax_fwd_kernel + 2 x tc_softmax_bwd_kernel (tcgen05)", "bound": "tensor",
+        roof = {"kernel": "in-batch softmax: tc_softmax_fwd_kernel + tc_softmax_bwd_fused_kernel (tcgen05)", "bound": "tensor",
                 "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(ach / pk["tf_sustained"], 4),
                 # dram__bytes_read+write per step of the three launches, from the ncu --set full capture in profiles/
                 "traffic": 1.02e8, "peak_source": pk["source"] + " (sustained bf16)", "ms": round(sm_ms, 4),
                 "flops_credited": "6*B*B*d (recomputation of S in the backward is not credited)",
-                "note": "MUFU(ex2)-bound, not tensor-bound, at d=64: 1 ex2 per 128 MACs; see DESIGN.md section 4"}
+                "note": "at d=64 the forward is MUFU(ex2)-bound (1 ex2 per 64 MACs) and the one-pass backward is bound by shared-memory "
+                        "operand bandwidth of its N=64 tcgen05.mma (ncu: tc+lsu smem wavefronts ~90%); see DESIGN.md section 4"}
     line = {
         "metric": "two-tower train samples/s", "value": round(world * B / (ms_value * 1e-3), 1), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_value, 4),

@@ -269,7 +269,10 @@ int tt_inbatch_softmax_backward_f32(const float* q, const float* c, const float*
  * forward: lse[B], diag[B] (= S_bb / T as the tensor core sees it), loss[1].
  * backward: dq = g*(P c - c)/(B T), dc = g*(P^T q - q)/(B T), P = exp(S/T - lse);
  *   relu_gate != 0 additionally zeroes dq where q_f32 <= 0 and dc where c_f32 <= 0
- *   (the towers end in a ReLU: utils/model_training.py:95-96 / torchrec MLP). */
+ *   (the towers end in a ReLU: utils/model_training.py:95-96 / torchrec MLP).
+ *   d <= 64: ONE pass over P yields both gradients (each P tile feeds P.c and P^T.q; partial
+ *   sums meet in L2 through TMA reduce-add, so the low bits depend on CTA order); the
+ *   transposed copies qt / ct are not read and may be null.  d > 64: two passes, qt / ct needed. */
 size_t tt_inbatch_softmax_bf16_workspace_bytes(int64_t B);
 int tt_inbatch_softmax_forward_bf16(const void* q_bf16, int64_t ldq, const void* c_bf16, int64_t ldc,
                                     int64_t B, int64_t d, float inv_temperature, float* lse,

@@ -1045,7 +1045,7 @@ int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void
                                      const float* q_f32, int64_t ldqf, const float* c_f32, int64_t ldcf,
                                      const float* lse, int64_t B, int64_t d, float inv_t, float grad_scale,
                                      int32_t relu_gate, float* dq, int64_t lddq, float* dc, int64_t lddc, void* stream) {
-  TT_CHECK_ARG(B > 0 && d > 0 && q_bf16 && c_bf16 && qt_bf16 && ct_bf16 && q_f32 && c_f32 && lse && dq && dc,
+  TT_CHECK_ARG(B > 0 && d > 0 && q_bf16 && c_bf16 && q_f32 && c_f32 && lse && dq && dc,
                "inbatch_softmax_backward_bf16: bad args");
   if (d > 256) return fail(TT_ERR_UNSUPPORTED, "inbatch_softmax_backward_bf16: d > 256");
   cudaStream_t s = as_stream(stream);
@@ -1055,6 +1055,13 @@ int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void
   const int splits = column_splits(B, NT);
   const float scale2 = inv_t * kLog2e;
   const float out_scale = grad_scale * inv_t / (float)B;
+  // d <= 64: one pass over P for both gradients.  TT_SOFTMAX_BWD=split keeps the two-pass kernels (A/B runs).
+  static const bool force_split = [] { const char* v = getenv("TT_SOFTMAX_BWD"); return v != nullptr && strcmp(v, "split") == 0; }();
+  if (KB == 1 && !force_split && (lddq % 4) == 0 && (lddc % 4) == 0 &&
+      ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dc)) & 15) == 0)
+    return launch_bwd_fused(q_bf16, ldq, c_bf16, ldc, q_f32, ldqf, c_f32, ldcf, lse, (int)B, (int)d, scale2, out_scale,
+                            relu_gate ? q_f32 : nullptr, relu_gate ? c_f32 : nullptr, dq, lddq, dc, lddc, s);
+  TT_CHECK_ARG(qt_bf16 && ct_bf16, "inbatch_softmax_backward_bf16: the two-pass kernels need the transposed copies");
   CUtensorMap tq128, tc128, tqn, tcn, tqt, tct;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tq128, q_bf16, B, d, ldq, 128))) return rc;
@@ -1065,12 +1072,6 @@ int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void
   if ((rc = make_tmap_bf16_2d(&tct, ct_bf16, d, B, ldct, D))) return rc;
   const float* gate_q = relu_gate ? q_f32 : nullptr;
   const float* gate_c = relu_gate ? c_f32 : nullptr;
-  // d <= 64: one pass over P for both gradients.  TT_SOFTMAX_BWD=split keeps the two-pass kernels (A/B runs).
-  static const bool force_split = [] { const char* v = getenv("TT_SOFTMAX_BWD"); return v != nullptr && strcmp(v, "split") == 0; }();
-  if (KB == 1 && !force_split && (lddq % 4) == 0 && (lddc % 4) == 0 &&
-      ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dc)) & 15) == 0)
-    return launch_bwd_fused(q_bf16, ldq, c_bf16, ldc, q_f32, ldqf, c_f32, ldcf, lse, (int)B, (int)d, scale2, out_scale, gate_q,
-                            gate_c, dq, lddq, dc, lddc, s);
 #define TT_LB(KBV)                                                                                              \
   do {                                                                                                          \
     rc = launch_bwd<KBV, true>(tq128, tcn, tct, (int)B, (int)d, scale2, lse, c_f32, ldcf, gate_q, ldqf, out_scale, dq, lddq, splits, s); \

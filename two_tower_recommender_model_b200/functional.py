@@ -7,6 +7,8 @@ refuse CPU tensors: there is no CPU path.
 from ctypes import byref
 from typing import Optional, Tuple
 
+import os
+
 import torch
 
 from . import _native as N
@@ -194,8 +196,14 @@ class InBatchSoftmaxLossTC(torch.autograd.Function):
         c = _f32c(c, "candidate_embedding")
         B, d = q.shape
         dev = q.device
-        qb, qbt = cast_bf16(q, both=True)
-        cb, cbt = cast_bf16(c, both=True)
+        # d <= 64: the fused one-pass backward reads q / c row-major only (MN-major tcgen05 operands);
+        # wider embeddings use the two-pass kernels, which want the transposed copies as well
+        if d > 64 or os.environ.get("TT_SOFTMAX_BWD") == "split":
+            qb, qbt = cast_bf16(q, both=True)
+            cb, cbt = cast_bf16(c, both=True)
+        else:
+            qb, cb = cast_bf16(q), cast_bf16(c)
+            qbt = cbt = None
         lse = torch.empty(B, dtype=torch.float32, device=dev)
         diag = torch.empty(B, dtype=torch.float32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -214,7 +222,8 @@ class InBatchSoftmaxLossTC(torch.autograd.Function):
         dq = torch.empty_like(q)
         dc = torch.empty_like(c)
         N.call("tt_inbatch_softmax_backward_bf16", N.ptr(qb), qb.stride(0), N.ptr(cb), cb.stride(0),
-               N.ptr(qbt), qbt.stride(0), N.ptr(cbt), cbt.stride(0), N.ptr(q), q.stride(0), N.ptr(c), c.stride(0),
+               N.ptr(qbt), qbt.stride(0) if qbt is not None else 0, N.ptr(cbt), cbt.stride(0) if cbt is not None else 0,
+               N.ptr(q), q.stride(0), N.ptr(c), c.stride(0),
                N.ptr(lse), B, d, ctx.inv_t, 1.0, 0, N.ptr(dq), d, N.ptr(dc), d, N.stream_ptr(q.device))
         return dq * g_loss, dc * g_loss, None
 
