@@ -273,6 +273,10 @@ int tt_inbatch_softmax_backward_f32(const float* q, const float* c, const float*
  *   d <= 64: ONE pass over P yields both gradients (each P tile feeds P.c and P^T.q; partial
  *   sums meet in L2 through TMA reduce-add, so the low bits depend on CTA order); the
  *   transposed copies qt / ct are not read and may be null.  d > 64: two passes, qt / ct needed. */
+/* mode 0 (default): pick the fastest backward; mode 1: always the two-pass kernels, whose results are
+ * bit-reproducible from run to run (the one-pass kernel adds partial sums in L2 in CTA arrival order).
+ * The environment variable TT_SOFTMAX_BWD=split selects mode 1 at load time. */
+int tt_set_softmax_backward_mode(int32_t mode);
 size_t tt_inbatch_softmax_bf16_workspace_bytes(int64_t B);
 int tt_inbatch_softmax_forward_bf16(const void* q_bf16, int64_t ldq, const void* c_bf16, int64_t ldc,
                                     int64_t B, int64_t d, float inv_temperature, float* lse,

@@ -17,6 +17,8 @@ def timed(fn, iters, warmup=3):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
+    if N._timing is not None:
+        N.enable_timing(True)   # drop the warm-up calls (first-call attribute / module-load costs)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(iters):

@@ -76,21 +76,23 @@ struct GemmEpilogue {
 
 constexpr int kBM = 128, kBK = 64, kStages = 4, kGemmThreadsTc = 192;
 
+// Shared memory follows the K extent: a short-K GEMM (the towers: K = 64 / 128) takes one or two stages, so
+// three CTAs share an SM and one CTA's TMA / MMA latency hides behind another's epilogue.
 template <int BN>
-constexpr int gemm_smem_bytes() {
-  return kStages * (kBM * kBK * 2 + BN * kBK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int gemm_smem_bytes(int stages) {
+  return stages * (kBM * kBK * 2 + BN * kBK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kGemmThreadsTc, 1)
+__global__ void __launch_bounds__(kGemmThreadsTc, BN <= 128 ? 3 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmEpilogue ep, int M, int N, int K) {
+               const GemmEpilogue ep, int M, int N, int K, int stages) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int A_BYTES = kBM * kBK * 2, B_BYTES = BN * kBK * 2;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kStages * B_BYTES);
+  uint8_t* sB = smem + stages * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + stages * B_BYTES);
   uint64_t* full = bars;                 // [kStages]
   uint64_t* empty = bars + kStages;      // [kStages]
   uint64_t* acc_full = bars + 2 * kStages;
@@ -118,8 +120,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (elect_one()) {
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
         tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], (kb0 + kb) * kBK, m0);
@@ -129,8 +131,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     constexpr uint32_t idesc = idesc_bf16_f32(kBM, BN);
     for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % kStages;
-      const uint32_t ph = (kb / kStages) & 1;
+      const int s = kb % stages;
+      const uint32_t ph = (kb / stages) & 1;
       mbar_wait(&full[s], ph);
       tc_fence_after();
       if (elect_one()) {
@@ -303,14 +305,16 @@ template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
                        int splits, cudaStream_t s) {
   static bool attr = false;
-  constexpr int smem = gemm_smem_bytes<BN>();
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         gemm_smem_bytes<BN>(kStages));
     if (e != cudaSuccess) return fail(TT_ERR_CUDA, "tc_gemm smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
+  const int kb_cta = ep.kb_per_split;                       // K blocks one CTA walks through
+  const int stages = kb_cta < kStages ? (kb_cta < 1 ? 1 : kb_cta) : kStages;
   dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM, splits);
-  tc_gemm_kernel<BN><<<grid, kGemmThreadsTc, smem, s>>>(ta, tb, ep, M, N, K);
+  tc_gemm_kernel<BN><<<grid, kGemmThreadsTc, gemm_smem_bytes<BN>(stages), s>>>(ta, tb, ep, M, N, K, stages);
   TT_CHECK_LAUNCH("tc_gemm");
   return TT_OK;
 }

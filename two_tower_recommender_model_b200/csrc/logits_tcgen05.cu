@@ -50,6 +50,47 @@ __device__ __forceinline__ float ex2_poly(float x) {
   else p = fmaf(fmaf(fmaf(fmaf(0.009582853f, f, 0.055906426f), f, 0.24024099f), f, 0.69312418f), f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // * 2^round(x)
 }
+// The same on two values at once with the packed fp32x2 FMA / ADD of sm_100 (FFMA2 / FADD2: one issue slot
+// for two lanes' worth of work -- the softmax loops are short of issue slots as well as of MUFU throughput).
+template <int DEG>
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));
+  const float2 r = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(r, make_float2(-1.f, -1.f), x);
+  float2 p;
+  if (DEG == 3) {
+    p = __ffma2_rn(make_float2(0.05500893f, 0.05500893f), f, make_float2(0.24221095f, 0.24221095f));
+    p = __ffma2_rn(p, f, make_float2(0.6932829f, 0.6932829f));
+  } else {
+    p = __ffma2_rn(make_float2(0.009582853f, 0.009582853f), f, make_float2(0.055906426f, 0.055906426f));
+    p = __ffma2_rn(p, f, make_float2(0.24024099f, 0.24024099f));
+    p = __ffma2_rn(p, f, make_float2(0.69312418f, 0.69312418f));
+  }
+  p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return p;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3
+  return r;
+}
+// exp2 of 8 consecutive scaled logits x = v * scale + shift, N8 of them (in pairs) on the FMA pipe
+template <int N8, int DEG>
+__device__ __forceinline__ void ex2_8(const uint32_t* v, float2 sc, float2 sh, float2 (&e)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), sc, sh);
+    const bool both = (N8 >= 2 && k == 3) || (N8 >= 4 && k == 1) || (N8 >= 6 && k == 2);
+    const bool one = (N8 == 1 && k == 3) || (N8 == 3 && k == 1) || (N8 == 5 && k == 2);
+    if (both) e[k] = ex2_poly2<DEG>(x);
+    else if (one) e[k] = make_float2(ex2(x.x), ex2_poly<DEG>(x.y));
+    else e[k] = make_float2(ex2(x.x), ex2(x.y));
+  }
+}
 // which of every 8 consecutive elements go to the polynomial: N8 of 8
 template <int N8>
 __device__ __forceinline__ constexpr bool use_poly(int j) {
@@ -67,14 +108,14 @@ __device__ __forceinline__ constexpr bool use_poly(int j) {
 constexpr int kPolyFwd = TT_POLY_FWD, kPolyBwd = TT_POLY_BWD;
 
 __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
-  float a[16];
+  float a[10], b[4];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) a[i] = fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 16]));
-#pragma unroll
-  for (int w = 8; w > 0; w >>= 1)
-#pragma unroll
-    for (int i = 0; i < w; ++i) a[i] = fmaxf(a[i], a[i + w]);
-  return a[0];
+  for (int i = 0; i < 10; ++i) a[i] = fmax3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+  b[0] = fmax3(a[0], a[1], a[2]);
+  b[1] = fmax3(a[3], a[4], a[5]);
+  b[2] = fmax3(a[6], a[7], a[8]);
+  b[3] = fmax3(a[9], __uint_as_float(v[30]), __uint_as_float(v[31]));
+  return fmaxf(fmax3(b[0], b[1], b[2]), b[3]);
 }
 // Producer / MMA-issuer waits: these warps share a scheduler with softmax warps, so back off
 // instead of burning issue slots in a try_wait spin.
@@ -128,23 +169,23 @@ __device__ __forceinline__ void lse_chunk(const uint32_t (&v)[32], int col0, int
     if (mx == -INFINITY) return;  // chunk entirely past the last column
   }
   const float mn = fmaxf(m, mx);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const float2 sc = make_float2(scale2, scale2), sh = make_float2(-mn, -mn);
+  float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float x0 = fmaf(__uint_as_float(v[j]), scale2, -mn), x1 = fmaf(__uint_as_float(v[j + 1]), scale2, -mn);
-    const float x2 = fmaf(__uint_as_float(v[j + 2]), scale2, -mn), x3 = fmaf(__uint_as_float(v[j + 3]), scale2, -mn);
-    float e0 = use_poly<kPolyFwd>(j) ? ex2_poly<4>(x0) : ex2(x0);
-    float e1 = use_poly<kPolyFwd>(j + 1) ? ex2_poly<4>(x1) : ex2(x1);
-    float e2 = use_poly<kPolyFwd>(j + 2) ? ex2_poly<4>(x2) : ex2(x2);
-    float e3 = use_poly<kPolyFwd>(j + 3) ? ex2_poly<4>(x3) : ex2(x3);
+  for (int j = 0; j < 32; j += 8) {
+    float2 e[4];
+    ex2_8<kPolyFwd, 4>(&v[j], sc, sh, e);
     if (TAIL) {
-      e0 = (col0 + j < B) ? e0 : 0.f;
-      e1 = (col0 + j + 1 < B) ? e1 : 0.f;
-      e2 = (col0 + j + 2 < B) ? e2 : 0.f;
-      e3 = (col0 + j + 3 < B) ? e3 : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        e[k].x = (col0 + j + 2 * k < B) ? e[k].x : 0.f;
+        e[k].y = (col0 + j + 2 * k + 1 < B) ? e[k].y : 0.f;
+      }
     }
-    a0 += e0; a1 += e1; a2 += e2; a3 += e3;
+    acc0 = __fadd2_rn(acc0, __fadd2_rn(e[0], e[1]));
+    acc1 = __fadd2_rn(acc1, __fadd2_rn(e[2], e[3]));
   }
+  const float a0 = acc0.x, a1 = acc0.y, a2 = acc1.x, a3 = acc1.y;
   l = l * ex2(m - mn) + ((a0 + a1) + (a2 + a3));
   m = mn;
 }
@@ -184,7 +225,7 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     prefetch_tmap(&tmC);
     mbar_init(q_full, 1);
     for (int s = 0; s < S; ++s) { mbar_init(&c_full[s], 1); mbar_init(&c_empty[s], 1); }
-    for (int s = 0; s < Cfg::NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < Cfg::NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], (Cfg::NG == 4 && NT == 128) ? 256 : 128); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -232,6 +273,33 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int row = m0 + r_in;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float m = -INFINITY, l = 0.f;                   // running max / sum, log2 domain
+    if (Cfg::NG == 4 && NT == 128) {
+      // Groups work in pairs: pair g/2 takes the tiles t = g/2 (mod 2), group g%2 of the pair the 64-column half
+      // g%2 of each.  A thread pulls its 64 columns into registers in one go and releases the TMEM stage at once,
+      // so the MMA issuer refills it while the exponentials run (with four stages it stays two tiles ahead).
+      const int h = g & 1;
+      for (int t = g >> 1; t < T; t += 2) {
+        const int as = t % Cfg::NACC;
+        const uint32_t tcol = trow + as * NT + h * 64;
+        mbar_wait(&acc_full[as], (t / Cfg::NACC) & 1);
+        tc_fence_after();
+        const int n0 = (t0 + t) * NT + h * 64;
+        const bool tail = n0 + 64 > B;
+        uint32_t va[32], vb[32];
+        tmem_ld32(tcol, va);
+        tmem_ld32(tcol + 32, vb);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&acc_empty[as]);
+        if (!tail) {
+          lse_chunk<false>(va, n0, B, scale2, m, l);
+          lse_chunk<false>(vb, n0 + 32, B, scale2, m, l);
+        } else {
+          lse_chunk<true>(va, n0, B, scale2, m, l);
+          lse_chunk<true>(vb, n0 + 32, B, scale2, m, l);
+        }
+      }
+    } else
     for (int t = g; t < T; t += Cfg::NG) {
       const int as = t % Cfg::NACC;
       const uint32_t tcol = trow + as * NT;
@@ -556,16 +624,13 @@ struct FusedCfg {
 // one 32-column chunk of S -> P -> four 16-byte pieces of the swizzled bf16 row in shared memory
 __device__ __forceinline__ void p_chunk_smem(const uint32_t (&v)[32], uint32_t row_addr, int slot0, int r7, float lrow,
                                              float scale2) {
+  const float2 sc = make_float2(scale2, scale2), sh = make_float2(-lrow, -lrow);
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
-    float p[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float x = fmaf(__uint_as_float(v[m * 8 + e]), scale2, -lrow);
-      p[e] = use_poly<kPolyBwd>(m * 8 + e) ? ex2_poly<3>(x) : ex2(x);
-    }
-    st_shared_v4(row_addr + (((slot0 + m) ^ r7) << 4), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]),
-                 pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+    float2 e[4];
+    ex2_8<kPolyBwd, 3>(&v[m * 8], sc, sh, e);
+    st_shared_v4(row_addr + (((slot0 + m) ^ r7) << 4), pack_bf16(e[0].x, e[0].y), pack_bf16(e[1].x, e[1].y),
+                 pack_bf16(e[2].x, e[2].y), pack_bf16(e[3].x, e[3].y));
   }
 }
 
@@ -993,7 +1058,15 @@ static int launch_bwd_fused(const void* q_bf16, int64_t ldq, const void* c_bf16,
 using namespace tt;
 using namespace tt::tc;
 
+static int g_softmax_bwd_mode = [] { const char* v = getenv("TT_SOFTMAX_BWD"); return (v != nullptr && strcmp(v, "split") == 0) ? 1 : 0; }();
+
 extern "C" {
+
+int tt_set_softmax_backward_mode(int32_t mode) {
+  TT_CHECK_ARG(mode == 0 || mode == 1, "set_softmax_backward_mode: mode must be 0 (auto) or 1 (two-pass, deterministic)");
+  g_softmax_bwd_mode = mode;
+  return TT_OK;
+}
 
 size_t tt_inbatch_softmax_bf16_workspace_bytes(int64_t B) {
   return align_up((size_t)((B + 127) / 128 + 1) * 4, 256) + align_up((size_t)B * 2 * 2 * 4, 256) + 256;
@@ -1055,9 +1128,8 @@ int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void
   const int splits = column_splits(B, NT);
   const float scale2 = inv_t * kLog2e;
   const float out_scale = grad_scale * inv_t / (float)B;
-  // d <= 64: one pass over P for both gradients.  TT_SOFTMAX_BWD=split keeps the two-pass kernels (A/B runs).
-  static const bool force_split = [] { const char* v = getenv("TT_SOFTMAX_BWD"); return v != nullptr && strcmp(v, "split") == 0; }();
-  if (KB == 1 && !force_split && (lddq % 4) == 0 && (lddc % 4) == 0 &&
+  // d <= 64: one pass over P for both gradients, unless the deterministic two-pass kernels were asked for
+  if (KB == 1 && g_softmax_bwd_mode == 0 && (lddq % 4) == 0 && (lddc % 4) == 0 &&
       ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dc)) & 15) == 0)
     return launch_bwd_fused(q_bf16, ldq, c_bf16, ldc, q_f32, ldqf, c_f32, ldcf, lse, (int)B, (int)d, scale2, out_scale,
                             relu_gate ? q_f32 : nullptr, relu_gate ? c_f32 : nullptr, dq, lddq, dc, lddc, s);

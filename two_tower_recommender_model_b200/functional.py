@@ -185,6 +185,18 @@ class InBatchSoftmaxLoss(torch.autograd.Function):
         return dq * g_loss, dc * g_loss, None
 
 
+_deterministic_softmax_backward = os.environ.get("TT_SOFTMAX_BWD") == "split"
+
+
+def set_deterministic_softmax_backward(on: bool) -> None:
+    """``True``: the bf16 in-batch softmax backward always runs the two-pass kernels, which are bit-reproducible
+    from run to run; ``False`` (default): d <= 64 uses the one-pass kernel (about 1.7x faster), whose partial
+    sums meet in L2 in CTA arrival order, so the low bits of the gradients vary between runs."""
+    global _deterministic_softmax_backward
+    N.call("tt_set_softmax_backward_mode", 1 if on else 0)
+    _deterministic_softmax_backward = bool(on)
+
+
 class InBatchSoftmaxLossTC(torch.autograd.Function):
     """Same loss on the tensor cores (tcgen05): bf16 operands, fp32 accumulation in TMEM,
     softmax out of TMEM; the backward recomputes S tile by tile and feeds P back to the tensor
@@ -198,7 +210,7 @@ class InBatchSoftmaxLossTC(torch.autograd.Function):
         dev = q.device
         # d <= 64: the fused one-pass backward reads q / c row-major only (MN-major tcgen05 operands);
         # wider embeddings use the two-pass kernels, which want the transposed copies as well
-        if d > 64 or os.environ.get("TT_SOFTMAX_BWD") == "split":
+        if d > 64 or _deterministic_softmax_backward:
             qb, qbt = cast_bf16(q, both=True)
             cb, cbt = cast_bf16(c, both=True)
         else:
