@@ -227,6 +227,37 @@ int tt_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t
                  const void* mask_bf16, int64_t ld_mask_bf16, float* out_f32, int64_t ld_f32,
                  void* out_bf16, int64_t ld_bf16, void* out_bf16_t, int64_t ld_bf16_t, void* stream);
 
+/* The two ReLU towers (query_proj / candidate_proj: MLP(embedding_dim, [hidden, out]) = Linear+ReLU,
+ * Linear+ReLU; utils/model_training.py:95-96, forward at :103-110) as ONE launch per direction:
+ * both towers side by side, both layers fused per 128-sample tile, hidden activations never leave
+ * the SM in the forward, all weight / bias gradients accumulated on chip in the backward.
+ * Shapes: in <= 64, hidden <= 128, out <= 64, multiples of 8 (else TT_ERR_UNSUPPORTED: use tt_gemm_bf16).
+ * x / y / dy / dx are fp32 and may be column windows of wider matrices (pitch in elements, multiple of
+ * 4, 16-byte aligned); w*_bf16 are bf16 copies of nn.Linear.weight ([out_features, in_features],
+ * pitch ldw multiple of 8); xb [B,64], hb [B,128], yb [B,64] are bf16 activations the forward saves
+ * for the backward (fixed pitches, zero padded). */
+#define TT_MAX_TOWERS 2
+typedef struct {
+  const float* x; int64_t ldx;
+  const void* w1_bf16; int64_t ldw1; const float* b1;   /* b1 / b2 may be null (bias=False) */
+  const void* w2_bf16; int64_t ldw2; const float* b2;
+  void* xb; void* hb; void* yb;
+  float* y; int64_t ldy;
+} tt_tower_forward;
+typedef struct {
+  const float* dy; int64_t lddy;          /* gradient of the tower output */
+  const void* w1_bf16; int64_t ldw1;
+  const void* w2_bf16; int64_t ldw2;
+  const void* xb; const void* hb; const void* yb;
+  float* dx; int64_t lddx;                /* gradient of the tower input, or null */
+  float* dw1; float* dw2; float* db1; float* db2;   /* [hidden,in], [out,hidden], [hidden], [out]; any may be null */
+} tt_tower_backward;
+int tt_towers_forward_fused(const tt_tower_forward* towers, int32_t n_towers, int64_t B, int32_t in_dim,
+                            int32_t hidden, int32_t out_dim, void* stream);
+size_t tt_towers_backward_workspace_bytes(int64_t B);
+int tt_towers_backward_fused(const tt_tower_backward* towers, int32_t n_towers, int64_t B, int32_t in_dim,
+                             int32_t hidden, int32_t out_dim, void* ws, size_t ws_bytes, void* stream);
+
 /* Weight gradient shape: C[M,N] fp32 = A[M,K] . B[N,K]^T with M, N small and K = batch.
  * The K reduction is split over ~2 waves of CTAs; partials land in ws and are reduced in
  * slice order (deterministic). */

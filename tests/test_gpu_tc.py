@@ -192,3 +192,37 @@ def test_topk_tensor_core_random_normal(cuda):
     torch.testing.assert_close(s.cpu(), ws, rtol=1e-5, atol=1e-5)
     recall = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(i.cpu(), wi)) / wi.numel()
     assert recall >= 0.999
+
+
+@pytest.mark.parametrize("B,i,h,o", [(1000, 64, 128, 64), (4096, 32, 64, 32), (130, 8, 8, 8), (65536, 64, 128, 64), (777, 48, 96, 24)])
+def test_fused_towers_match_per_layer_path(cuda, B, i, h, o):
+    """One-launch fused towers (tt_towers_forward_fused / tt_towers_backward_fused) against the per-layer
+    tcgen05 path (MlpTC: cast + tt_gemm_bf16 + split-K + colsum) on the same inputs.  Same bf16 operand
+    rounding and fp32 accumulation in both, so activations agree to fp32 round-off (a bf16 re-rounding flip
+    of h can move an output by ~2^-9 of one term: rtol 2e-3); gradients are long sums in different orders."""
+    from two_tower_recommender_model_b200.functional import FusedTowersTC, MlpTC
+    g = torch.Generator().manual_seed(B + i)
+    pooled = (torch.randn(B, 2 * i, generator=g) * 0.5).to(cuda)
+    params = []
+    for t in range(2):
+        params += [(torch.randn(h, i, generator=g) / i ** 0.5).to(cuda), (torch.randn(h, generator=g) * 0.1).to(cuda),
+                   (torch.randn(o, h, generator=g) / h ** 0.5).to(cuda), (torch.randn(o, generator=g) * 0.1).to(cuda)]
+    dys = [torch.randn(B, o, generator=g).to(cuda) for _ in range(2)]
+
+    def run(fused):
+        p = pooled.clone().requires_grad_(True)
+        ps = [x.clone().requires_grad_(True) for x in params]
+        if fused:
+            ys = FusedTowersTC.apply(p, (0, i), i, *ps)
+        else:
+            ys = [MlpTC.apply(p.narrow(1, t * i, i), *ps[4 * t: 4 * t + 4]) for t in range(2)]
+        torch.autograd.backward(list(ys), dys)
+        return [y.detach() for y in ys], p.grad, [x.grad for x in ps]
+
+    ya, dpa, ga = run(True)
+    yb, dpb, gb = run(False)
+    for a, b in zip(ya, yb):
+        torch.testing.assert_close(a, b, rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(dpa, dpb, rtol=2e-2, atol=2e-2 * float(dpb.abs().max()))
+    for k, (a, b) in enumerate(zip(ga, gb)):
+        torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-2 * float(b.abs().max()), msg=lambda m: f"param {k}: {m}")

@@ -39,6 +39,19 @@ class EbcPlan(Structure):
 
 
 TT_MAX_PEERS = 16
+TT_MAX_TOWERS = 2
+
+
+class TowerForward(Structure):
+    _fields_ = [("x", c_void_p), ("ldx", c_int64), ("w1_bf16", c_void_p), ("ldw1", c_int64), ("b1", c_void_p),
+                ("w2_bf16", c_void_p), ("ldw2", c_int64), ("b2", c_void_p), ("xb", c_void_p), ("hb", c_void_p),
+                ("yb", c_void_p), ("y", c_void_p), ("ldy", c_int64)]
+
+
+class TowerBackward(Structure):
+    _fields_ = [("dy", c_void_p), ("lddy", c_int64), ("w1_bf16", c_void_p), ("ldw1", c_int64), ("w2_bf16", c_void_p),
+                ("ldw2", c_int64), ("xb", c_void_p), ("hb", c_void_p), ("yb", c_void_p), ("dx", c_void_p), ("lddx", c_int64),
+                ("dw1", c_void_p), ("dw2", c_void_p), ("db1", c_void_p), ("db2", c_void_p)]
 
 
 class PeerBuffers(Structure):
@@ -89,6 +102,9 @@ SIGNATURES = {
     "tt_inbatch_softmax_workspace_bytes": (c_size_t, [c_int64]),
     "tt_inbatch_softmax_forward_f32": (c_int32, [_P, _P, c_int64, c_int64, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "tt_inbatch_softmax_backward_f32": (c_int32, [_P, _P, _P, c_int64, c_int64, c_float, c_float, _P, _P, _P]),
+    "tt_towers_forward_fused": (c_int32, [POINTER(TowerForward), c_int32, c_int64, c_int32, c_int32, c_int32, _P]),
+    "tt_towers_backward_workspace_bytes": (c_size_t, [c_int64]),
+    "tt_towers_backward_fused": (c_int32, [POINTER(TowerBackward), c_int32, c_int64, c_int32, c_int32, c_int32, _P, c_size_t, _P]),
     "tt_set_softmax_backward_mode": (c_int32, [c_int32]),
     "tt_inbatch_softmax_bf16_workspace_bytes": (c_size_t, [c_int64]),
     "tt_inbatch_softmax_forward_bf16": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_float, _P, _P, _P, _P, c_size_t, _P]),

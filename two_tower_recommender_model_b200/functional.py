@@ -384,6 +384,85 @@ def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def fused_towers_supported(in_dims, hidden, out_dim, n_layers) -> bool:
+    """Shapes ``tt_towers_forward_fused`` takes: two-layer towers, in <= 64, hidden <= 128, out <= 64, multiples of 8."""
+    return (n_layers == 2 and len(in_dims) <= N.TT_MAX_TOWERS and len(set(in_dims)) == 1 and 8 <= in_dims[0] <= 64
+            and 8 <= hidden <= 128 and 8 <= out_dim <= 64 and (in_dims[0] | hidden | out_dim) % 8 == 0)
+
+
+class FusedTowersTC(torch.autograd.Function):
+    """Both two-layer ReLU towers in ONE launch per direction (``tt_towers_forward_fused`` /
+    ``tt_towers_backward_fused``): ``pooled`` is the [B, sum D] matrix of pooled embeddings, tower t reads the
+    column window ``[cols[t], cols[t] + in_dim)`` of it and gets parameters ``params[4t : 4t+4]`` =
+    (W1, b1, W2, b2).  Returns one fp32 [B, out] embedding per tower.  bf16 operands, fp32 accumulation,
+    fp32 master weights and gradients, same numerics as ``MlpTC``."""
+
+    @staticmethod
+    def forward(ctx, pooled, cols, in_dim, *params):
+        pooled = _rows(pooled, "pooled embeddings")
+        T = len(cols)
+        B = pooled.shape[0]
+        dev = pooled.device
+        hidden, out_dim = params[0].shape[0], params[2].shape[0]
+        ys = [torch.empty(B, out_dim, dtype=torch.float32, device=dev) for _ in range(T)]
+        xb = torch.empty(T, B, 64, dtype=torch.bfloat16, device=dev)
+        hb = torch.empty(T, B, 128, dtype=torch.bfloat16, device=dev)
+        yb = torch.empty(T, B, 64, dtype=torch.bfloat16, device=dev)
+        wbs = []
+        arr = (N.TowerForward * T)()
+        for t in range(T):
+            w1, b1, w2, b2 = params[4 * t: 4 * t + 4]
+            w1b, w2b = cast_bf16(_f32c(w1, "weight")), cast_bf16(_f32c(w2, "weight"))
+            wbs += [w1b, w2b]
+            a = arr[t]
+            a.x, a.ldx = pooled.data_ptr() + 4 * cols[t], pooled.stride(0)
+            a.w1_bf16, a.ldw1, a.b1 = w1b.data_ptr(), w1b.stride(0), (0 if b1 is None else _f32c(b1, "bias").data_ptr())
+            a.w2_bf16, a.ldw2, a.b2 = w2b.data_ptr(), w2b.stride(0), (0 if b2 is None else _f32c(b2, "bias").data_ptr())
+            a.xb, a.hb, a.yb = xb[t].data_ptr(), hb[t].data_ptr(), yb[t].data_ptr()
+            a.y, a.ldy = ys[t].data_ptr(), out_dim
+        N.call("tt_towers_forward_fused", arr, T, B, in_dim, hidden, out_dim, N.stream_ptr(dev))
+        ctx.cols, ctx.in_dim, ctx.shape, ctx.width = cols, in_dim, (B, hidden, out_dim), pooled.shape[1]
+        ctx.saved = (xb, hb, yb, wbs)
+        ctx.has_bias = [p is not None for p in params]
+        ctx.save_for_backward(*[p for p in params if p is not None])
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        xb, hb, yb, wbs = ctx.saved
+        B, hidden, out_dim = ctx.shape
+        T, in_dim = len(ctx.cols), ctx.in_dim
+        dev = xb.device
+        need_dx = ctx.needs_input_grad[0]
+        covered = sorted(ctx.cols) == list(range(0, ctx.width, in_dim))     # the windows tile the pooled matrix
+        d_pooled = None
+        if need_dx:
+            d_pooled = (torch.empty if covered else torch.zeros)(B, ctx.width, dtype=torch.float32, device=dev)
+        grads = []
+        arr = (N.TowerBackward * T)()
+        keep = []
+        for t in range(T):
+            dy = _f32c(dys[t], "grad of tower output") if dys[t] is not None else torch.zeros(B, out_dim, dtype=torch.float32, device=dev)
+            keep.append(dy)
+            gw1 = torch.empty(hidden, in_dim, dtype=torch.float32, device=dev)
+            gw2 = torch.empty(out_dim, hidden, dtype=torch.float32, device=dev)
+            gb1 = torch.empty(hidden, dtype=torch.float32, device=dev) if ctx.has_bias[4 * t + 1] else None
+            gb2 = torch.empty(out_dim, dtype=torch.float32, device=dev) if ctx.has_bias[4 * t + 3] else None
+            grads += [gw1, gb1, gw2, gb2]
+            a = arr[t]
+            a.dy, a.lddy = dy.data_ptr(), dy.stride(0)
+            a.w1_bf16, a.ldw1 = wbs[2 * t].data_ptr(), wbs[2 * t].stride(0)
+            a.w2_bf16, a.ldw2 = wbs[2 * t + 1].data_ptr(), wbs[2 * t + 1].stride(0)
+            a.xb, a.hb, a.yb = xb[t].data_ptr(), hb[t].data_ptr(), yb[t].data_ptr()
+            a.dx, a.lddx = (d_pooled.data_ptr() + 4 * ctx.cols[t], d_pooled.stride(0)) if need_dx else (0, 0)
+            a.dw1, a.dw2 = gw1.data_ptr(), gw2.data_ptr()
+            a.db1, a.db2 = (0 if gb1 is None else gb1.data_ptr()), (0 if gb2 is None else gb2.data_ptr())
+        ws = N.workspace(N.load().tt_towers_backward_workspace_bytes(B), dev)
+        N.call("tt_towers_backward_fused", arr, T, B, in_dim, hidden, out_dim, N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+        ctx.saved = None
+        return (d_pooled, None, None, *grads)
+
+
 class MlpTC(torch.autograd.Function):
     """A whole ReLU tower on the tensor cores: ``x -> relu(x W1^T + b1) -> ... -> relu(. WL^T + bL)``.
     Operands are bf16 (activations are produced in bf16 by the GEMM epilogues, together with the

@@ -57,10 +57,13 @@ class MLP(nn.Module):
             for i in range(len(layer_sizes))
         ])
 
+    def all_relu(self) -> bool:
+        return all(p._activation_fn is torch.relu or p._activation_fn is torch.nn.functional.relu
+                   or isinstance(p._activation_fn, nn.ReLU) for p in self._mlp)
+
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         layers = list(self._mlp)
-        relu_all = all(p._activation_fn is torch.relu or p._activation_fn is torch.nn.functional.relu
-                       or isinstance(p._activation_fn, nn.ReLU) for p in layers)
+        relu_all = self.all_relu()
         if self.precision == "bf16" and relu_all and input.shape[0] > 0:
             params = []
             for p in layers:

@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from .datasets.utils import Batch
-from .functional import dot_bce_loss, in_batch_softmax_loss
+from .functional import FusedTowersTC, dot_bce_loss, fused_towers_supported, in_batch_softmax_loss
 from .modules.embedding_modules import EmbeddingBagCollection
 from .modules.mlp import MLP
 from .sparse.jagged_tensor import KeyedJaggedTensor, KeyedTensor
@@ -51,8 +51,30 @@ class TwoTower(nn.Module):
             return pooled.values().narrow(1, col, width)
         return torch.cat([pooled[f] for f in features], dim=1)
 
+    def _fused_plan(self, pooled: KeyedTensor):
+        """(column offsets, in_dim, parameters) when both towers fit the one-launch fused kernels, else None."""
+        towers = (self.query_proj, self.candidate_proj)
+        if any(m.precision != "bf16" or not m.all_relu() for m in towers) or pooled.values().shape[0] == 0:
+            return None
+        layers = [list(m._mlp) for m in towers]
+        wins = [pooled.columns(f) for f in (self._feature_names_query, self._candidate_feature_names)]
+        dims = [(l[0]._in_size, l[0]._out_size, l[-1]._out_size) for l in layers]
+        v = pooled.values()
+        if (any(c < 0 for c, _ in wins) or dims[0] != dims[1] or not fused_towers_supported([w for _, w in wins], dims[0][1], dims[0][2], len(layers[0]))
+                or len(layers[1]) != 2 or any(c % 4 for c, _ in wins) or v.stride(0) % 4 or v.stride(1) != 1 or v.data_ptr() % 16):
+            return None
+        params = []
+        for l in layers:
+            for pc in l:
+                params += [pc._linear.weight, pc._linear.bias]
+        return [c for c, _ in wins], wins[0][1], params
+
     def forward(self, kjt: KeyedJaggedTensor) -> Tuple[torch.Tensor, torch.Tensor]:
         pooled_embeddings = self.ebc(kjt)
+        plan = self._fused_plan(pooled_embeddings)
+        if plan is not None:
+            cols, in_dim, params = plan
+            return FusedTowersTC.apply(pooled_embeddings.values(), tuple(cols), in_dim, *params)
         query_embedding = self.query_proj(self._tower_input(pooled_embeddings, self._feature_names_query))
         candidate_embedding = self.candidate_proj(self._tower_input(pooled_embeddings, self._candidate_feature_names))
         return query_embedding, candidate_embedding
