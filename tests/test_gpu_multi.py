@@ -44,8 +44,11 @@ def _worker(rank, world, port, sharding, errq):
                                                 for i, c in enumerate(CAT)], device=torch.device("meta"))
         task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, LAYERS, device=dev))
         apply_optimizer_in_backward(tt.RowWiseAdagrad, task.two_tower.ebc.parameters(), {"lr": LR})
-        peer = sharding == "table_wise_peer"   # table-wise with the exchange fused into the lookup kernels (NVLink peer memory)
-        sharding = "table_wise" if peer else sharding
+        # *_peer: output exchange fused into the lookup kernels (NVLink peer memory);
+        # *_dense*: batches arrive as dense id columns (from_id_columns) -> single all-to-all input dist, no host sync
+        peer = sharding.endswith("_peer")
+        dense_ids = "_dense" in sharding
+        sharding = "table_wise" if sharding.startswith("table_wise") else sharding
         cons = {f"t_{c}": ParameterConstraints(sharding_types=[sharding]) for c in CAT} if sharding != "planner" else None
         plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world), constraints=cons).collective_plan(task, tt.get_default_sharders(), dist.GroupMember.WORLD)
         model = tt.DistributedModelParallel(module=task, device=dev, plan=plan, sharding_kwargs={"peer_exchange": True} if peer else None)
@@ -53,7 +56,20 @@ def _worker(rank, world, port, sharding, errq):
         opt = tt.KeyedOptimizerWrapper(dict(model.named_parameters()), lambda p: torch.optim.SGD(p, lr=LR))
         pipe = tt.TrainPipelineSparseDist(model, opt, dev)
 
+        class RawIds:
+            """Host-side batch of raw id columns; the KJT is built on the device (as bench.py does)."""
+
+            def __init__(self, b):
+                self.ids = torch.tensor([b[c] for c in CAT], dtype=torch.int64).pin_memory()
+                self.labels = torch.tensor(b["label"], dtype=torch.int32).pin_memory()
+
+            def to(self, device, non_blocking=False):
+                kjt = tt.KeyedJaggedTensor.from_id_columns(CAT, self.ids.to(device, non_blocking=non_blocking), torch.tensor(EMB))
+                return tt.Batch(torch.zeros(1, device=device), kjt, self.labels.to(device, non_blocking=non_blocking))
+
         def transform(b):
+            if dense_ids:
+                return RawIds(b)
             v, l, y = oracle.transform_to_torchrec_batch(b, CAT, EMB)
             return tt.Batch(torch.zeros(1), tt.KeyedJaggedTensor.from_lengths_sync(CAT, v, l), y)
 
@@ -84,13 +100,16 @@ def _worker(rank, world, port, sharding, errq):
         raise
 
 
-@pytest.mark.parametrize("sharding", ["table_wise", "row_wise", "table_wise_peer"])
+MODES = ["table_wise", "row_wise", "table_wise_peer", "table_wise_dense", "table_wise_dense_peer"]
+
+
+@pytest.mark.parametrize("sharding", MODES)
 def test_two_rank_sharded_training_matches_oracle(sharding):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     ctx = mp.get_context("spawn")
     errq = ctx.SimpleQueue()
-    port = 29800 + os.getpid() % 100 + ["table_wise", "row_wise", "table_wise_peer"].index(sharding)
+    port = 29800 + os.getpid() % 100 + MODES.index(sharding)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, sharding, errq)) for r in range(2)]
     for p in procs:
         p.start()

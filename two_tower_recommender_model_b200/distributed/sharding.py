@@ -255,6 +255,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
                 for a, v in tags.get(name, {}).items():
                     setattr(bag.weight, a, v)
         self._prefetched: Dict[int, Any] = {}
+        self._local_rows_dev: Dict[str, torch.Tensor] = {}
 
     # ---- surface shared with EmbeddingBagCollection
     def embedding_bag_configs(self) -> List[EmbeddingBagConfig]:
@@ -278,6 +279,9 @@ class ShardedEmbeddingBagCollection(nn.Module):
         keys = kjt.keys()
         if not grp.features:
             return None
+        dense = getattr(kjt, "_id_columns", None)
+        if dense is not None and grp.kind == "table_wise" and dense[0].is_cuda:
+            return self._dist_dense_ids(grp, keys, dense[0], B)
         sub = kjt.permute([keys.index(f) for f in grp.features])
         lengths, values = sub.lengths(), sub.values()
         if grp.kind == "row_wise":
@@ -319,6 +323,27 @@ class ShardedEmbeddingBagCollection(nn.Module):
             recv = self._permute_no_sync(recv, perm, sum(recv_v))
         return KeyedJaggedTensor(keys=list(grp.local_features), values=recv.values(), lengths=recv.lengths(),
                                  offsets=recv._offsets, stride=W * B)
+
+    def _dist_dense_ids(self, grp: _Group, keys: List[str], ids: torch.Tensor, B: int):
+        """Table-wise input dist for batches that arrived as dense id columns (``KeyedJaggedTensor.from_id_columns``,
+        the reference's one-id-per-bag format): the [F, B] id columns themselves are exchanged -- every split is
+        known on the host, so there is ONE all-to-all, no count / length exchange and no host sync -- and the
+        key-major KJT over the global batch is built by ``tt_kjt_from_columns`` where the ids land."""
+        W, pg = self._world, self._pg
+        n_local = len(grp.dest_features[self._rank])
+        order = [keys.index(f) for f in grp.features]
+        send = ids if order == list(range(ids.shape[0])) else ids[torch.tensor(order, device=ids.device)]
+        recv = ids.new_empty(W * n_local * B)
+        dist.all_to_all_single(recv, send.contiguous().view(-1), output_split_sizes=[n_local * B] * W,
+                               input_split_sizes=[len(d) * B for d in grp.dest_features], group=pg)
+        if n_local == 0:
+            return None
+        cols = recv.view(W, n_local, B).permute(1, 0, 2).reshape(n_local, W * B)
+        rows = self._local_rows_dev.get(grp.kind)
+        if rows is None:
+            rows = torch.tensor([grp.feat_rows[f] for f in grp.local_features], dtype=torch.int64, device=ids.device)
+            self._local_rows_dev[grp.kind] = rows
+        return KeyedJaggedTensor.from_id_columns(list(grp.local_features), cols, rows)
 
     @staticmethod
     def _permute_no_sync(kjt: KeyedJaggedTensor, perm: List[int], total: int) -> KeyedJaggedTensor:

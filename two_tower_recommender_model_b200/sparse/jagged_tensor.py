@@ -129,6 +129,9 @@ class KeyedJaggedTensor:
                N.ptr(ws), ws.numel(), N.stream_ptr(dev))
         kjt = KeyedJaggedTensor(keys=keys, values=values, lengths=lengths, offsets=offsets, stride=B)
         kjt._values_padded = True
+        # kept for model-parallel input dists: single-id features can travel as dense id columns
+        # (fixed sizes: no count exchange, no host sync) and be turned into a KJT where they land
+        kjt._id_columns = (ids, ne)
         return kjt
 
     # ---- accessors
