@@ -176,7 +176,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph
     graph_step = None
     launches_per_step = None
     if use_graph:
@@ -252,8 +252,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_value, ms_e2e = t.tolist()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave(world)
         return
     pk = peaks()
     B = cfg["batch"]
@@ -303,8 +302,17 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, steps=2, warmup=1)
     print(json.dumps(line))
+    leave(world)
+
+
+def leave(world):
+    """Multi-rank exit: the captured graphs hold NCCL kernels and tearing the communicator down under them can
+    block, so flush and exit the process without the (purely cosmetic) process-group teardown."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def retrieval_probe(dev, n_items=2_000_000, n_queries=16384, d=64, k=100):
@@ -381,10 +389,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default=os.environ.get("TT_EXCHANGE", "nccl"), choices=["nccl", "peer"],
+    ap.add_argument("--exchange", default=os.environ.get("TT_EXCHANGE", "peer"), choices=["nccl", "peer"],
                     help="N>1: table-wise output exchange by NCCL all-to-all, or fused into the lookup kernels over NVLink peer memory")
-    ap.add_argument("--no-graph", action="store_true", help="N=1: run the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly (N>1: through TrainPipelineSparseDist) instead of replaying a CUDA graph")
     args = ap.parse_args()
+    # a wedged collective / capture must not hold the box: the default run takes well under two minutes
+    wd = threading.Timer(float(os.environ.get("TT_BENCH_WATCHDOG_S", "900")), lambda: (sys.stderr.write("bench.py: watchdog expired\n"), os._exit(3)))
+    wd.daemon = True
+    wd.start()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -255,7 +255,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
                 for a, v in tags.get(name, {}).items():
                     setattr(bag.weight, a, v)
         self._prefetched: Dict[int, Any] = {}
-        self._local_rows_dev: Dict[str, torch.Tensor] = {}
+        self._local_rows_dev: Dict[Any, torch.Tensor] = {}
 
     # ---- surface shared with EmbeddingBagCollection
     def embedding_bag_configs(self) -> List[EmbeddingBagConfig]:
@@ -332,7 +332,14 @@ class ShardedEmbeddingBagCollection(nn.Module):
         W, pg = self._world, self._pg
         n_local = len(grp.dest_features[self._rank])
         order = [keys.index(f) for f in grp.features]
-        send = ids if order == list(range(ids.shape[0])) else ids[torch.tensor(order, device=ids.device)]
+        if order == list(range(ids.shape[0])):
+            send = ids
+        else:
+            sel = self._local_rows_dev.get(("order", grp.kind, tuple(order)))    # cached: no H2D copy per step
+            if sel is None:
+                sel = torch.tensor(order, dtype=torch.int64, device=ids.device)
+                self._local_rows_dev[("order", grp.kind, tuple(order))] = sel
+            send = ids.index_select(0, sel)
         recv = ids.new_empty(W * n_local * B)
         dist.all_to_all_single(recv, send.contiguous().view(-1), output_split_sizes=[n_local * B] * W,
                                input_split_sizes=[len(d) * B for d in grp.dest_features], group=pg)

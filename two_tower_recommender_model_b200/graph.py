@@ -1,4 +1,6 @@
-"""Whole-step CUDA graph for the single-GPU train loop.
+"""Whole-step CUDA graph for the train loop (one GPU, or one rank of a DistributedModelParallel job: the
+NCCL / peer-memory exchanges of the sharded embedding path are captured with the rest -- table-wise sharding
+with id-column batches has no host sync in its input dist, so every rank replays the same fixed sequence).
 
 The step (device batch construction from raw id columns, EBC lookup, towers, loss, backward with the
 fused row-wise update, dense optimizer) is a fixed sequence of ~50 kernel launches whose arguments do
@@ -6,8 +8,7 @@ not change from step to step once the inputs live in static buffers.  ``CudaGrap
 first calls eagerly (warm-up with REAL batches, so nothing is trained on dummy data), then captures
 one step and replays it: per step the host issues two async copies and one graph launch.
 
-Requirements: static shapes (batches given as raw id columns ``[F, B]`` + labels ``[B]``), a
-single-GPU (unsharded) model, sparse optimizer RowWiseAdagrad or SGD (row-wise Adam's bias correction
+Requirements: static shapes (batches given as raw id columns ``[F, B]`` + labels ``[B]``), sparse optimizer RowWiseAdagrad or SGD (row-wise Adam's bias correction
 is host-computed), dense optimizer ``FlatAdam`` (device-side step counter) or SGD.
 """
 from typing import List, Optional, Sequence
@@ -41,6 +42,9 @@ class CudaGraphTrainStep:
         self._opt.zero_grad()
         loss, out = self._model(batch)
         loss.backward()
+        sync = getattr(self._model, "sync_dense_grads", None)   # DistributedModelParallel: all-reduce of the tower gradients
+        if sync is not None:
+            sync()
         self._opt.step()
         return out
 
