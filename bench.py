@@ -92,7 +92,14 @@ def build_model(cfg, dev):
     task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, cfg["layers"], device=dev, precision=cfg.get("precision", "bf16")), loss=cfg["loss"], precision=cfg.get("precision", "bf16"))
     apply_optimizer_in_backward(tt.RowWiseAdagrad, task.two_tower.ebc.parameters(), {"lr": cfg["sparse_lr"]})
     peer = cfg.get("exchange", "nccl") == "peer" and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
-    model = tt.DistributedModelParallel(module=task, device=dev, sharding_kwargs={"peer_exchange": True} if peer else None)
+    plan = None
+    if not peer and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        # the NCCL exchange path is benchmarked table-wise (its row-wise input dist needs a host sync per step)
+        from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
+        cons = {f"t_{c}": ParameterConstraints(sharding_types=["table_wise"]) for c in CAT}
+        plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=torch.distributed.get_world_size()), constraints=cons
+                                           ).collective_plan(task, tt.get_default_sharders(), torch.distributed.GroupMember.WORLD)
+    model = tt.DistributedModelParallel(module=task, device=dev, plan=plan, sharding_kwargs={"peer_exchange": True} if peer else None)
     opt = tt.KeyedOptimizerWrapper(dict(model.named_parameters()), lambda p: tt.FlatAdam(p, lr=cfg["dense_lr"]))
     return model, opt
 

@@ -74,6 +74,11 @@ int tt_kjt_lengths_to_offsets(const int32_t* lengths, int32_t* offsets, int64_t 
  * offsets [F*B+1] and the compacted values (capacity F*B).  The number of
  * values is offsets[F*B] (stays on the device). */
 size_t tt_kjt_from_columns_workspace_bytes(int64_t num_features, int64_t batch);
+/* Same for one row-wise shard: after the modulo only ids in [row_lo[f], row_hi[f]) are kept (value =
+ * id - row_lo[f]); all other bags are empty here -- they belong to another rank's rows. */
+int tt_kjt_from_columns_range(const int64_t* ids, const int64_t* num_embeddings, const int64_t* row_lo,
+                              const int64_t* row_hi, int64_t num_features, int64_t batch, int64_t* values,
+                              int32_t* lengths, int32_t* offsets, void* ws, size_t ws_bytes, void* stream);
 int tt_kjt_from_columns(const int64_t* ids, const int64_t* num_embeddings /* device [F] */,
                         int64_t num_features, int64_t batch, int64_t* values,
                         int32_t* lengths, int32_t* offsets, void* ws, size_t ws_bytes,
@@ -135,8 +140,15 @@ typedef struct {
 typedef struct {
   int32_t world;
   int32_t rows_per_peer;
+  int32_t flags;          /* TT_PEER_* (forward only) */
+  int32_t reserved;
   void* ptr[TT_MAX_PEERS];
 } tt_peer_buffers;
+/* Row-wise sharding: every rank holds a row range of the table and looks up the ids of the GLOBAL batch that
+ * fall into it.  Bags without a local id are skipped, the others are ADDED (red.global.add over NVLink) into
+ * buffers the caller zeroed: the sum over shards of a multi-id bag is formed in the destination's memory,
+ * and only rows that exist travel (TorchRec's row-wise output dist is a reduce-scatter of [W*B, D] partials). */
+#define TT_PEER_SCATTER_ADD 1
 
 /* pooled[b, out_col[s] : +dim[s]] = sum (or mean) over ids of bag (s, b) of
  * weights[s][id].  Empty bag -> zeros.  values int64, offsets int32 [F*B+1]. */

@@ -48,7 +48,7 @@ def _worker(rank, world, port, sharding, errq):
         # *_dense*: batches arrive as dense id columns (from_id_columns) -> single all-to-all input dist, no host sync
         peer = sharding.endswith("_peer")
         dense_ids = "_dense" in sharding
-        sharding = "table_wise" if sharding.startswith("table_wise") else sharding
+        sharding = "table_wise" if sharding.startswith("table_wise") else ("row_wise" if sharding.startswith("row_wise") else sharding)
         cons = {f"t_{c}": ParameterConstraints(sharding_types=[sharding]) for c in CAT} if sharding != "planner" else None
         plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world), constraints=cons).collective_plan(task, tt.get_default_sharders(), dist.GroupMember.WORLD)
         model = tt.DistributedModelParallel(module=task, device=dev, plan=plan, sharding_kwargs={"peer_exchange": True} if peer else None)
@@ -100,7 +100,7 @@ def _worker(rank, world, port, sharding, errq):
         raise
 
 
-MODES = ["table_wise", "row_wise", "table_wise_peer", "table_wise_dense", "table_wise_dense_peer"]
+MODES = ["table_wise", "row_wise", "table_wise_peer", "table_wise_dense", "table_wise_dense_peer", "row_wise_dense_peer"]
 
 
 @pytest.mark.parametrize("sharding", MODES)

@@ -40,6 +40,7 @@ class EbcPlan(Structure):
 
 TT_MAX_PEERS = 16
 TT_MAX_TOWERS = 2
+TT_PEER_SCATTER_ADD = 1
 
 
 class TowerForward(Structure):
@@ -55,7 +56,8 @@ class TowerBackward(Structure):
 
 
 class PeerBuffers(Structure):
-    _fields_ = [("world", c_int32), ("rows_per_peer", c_int32), ("ptr", c_void_p * TT_MAX_PEERS)]
+    _fields_ = [("world", c_int32), ("rows_per_peer", c_int32), ("flags", c_int32), ("reserved", c_int32),
+                ("ptr", c_void_p * TT_MAX_PEERS)]
 
 
 class SparseOptimizer(Structure):
@@ -76,6 +78,7 @@ SIGNATURES = {
     "tt_kjt_lengths_to_offsets": (c_int32, [_P, _P, c_int64, _P, c_size_t, _P]),
     "tt_kjt_from_columns_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "tt_kjt_from_columns": (c_int32, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),
+    "tt_kjt_from_columns_range": (c_int32, [_P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),
     "tt_kjt_permute_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "tt_kjt_permute_2d": (c_int32, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "tt_kjt_bucketize_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),

@@ -24,6 +24,7 @@ struct Vec<4> {
   __device__ __forceinline__ void load_stream(const float* p) { v = ld_stream_f4(p); }
   __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
   __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+  __device__ __forceinline__ void atomic_add(float* p) const { atomicAdd(reinterpret_cast<float4*>(p), v); }   // red.global.add.v4.f32
   __device__ __forceinline__ void add(const Vec& o) { v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w; }
   __device__ __forceinline__ void add_scaled(const Vec& o, float s) {
     v.x += s * o.v.x; v.y += s * o.v.y; v.z += s * o.v.z; v.w += s * o.v.w;
@@ -42,6 +43,7 @@ struct Vec<1> {
   __device__ __forceinline__ void load_stream(const float* p) { v = __ldg(p); }
   __device__ __forceinline__ void load(const float* p) { v = *p; }
   __device__ __forceinline__ void store(float* p) const { *p = v; }
+  __device__ __forceinline__ void atomic_add(float* p) const { atomicAdd(p, v); }
   __device__ __forceinline__ void add(const Vec& o) { v += o.v; }
   __device__ __forceinline__ void add_scaled(const Vec& o, float s) { v += s * o.v; }
   __device__ __forceinline__ void div(float s) { v /= s; }
@@ -113,6 +115,7 @@ ebc_forward_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_consta
   const bool mean = plan.pooling[slot] == TT_POOL_MEAN;
   const int ocol = plan.out_col[slot];
   const int g = threadIdx.x / G, l = threadIdx.x % G;
+  const bool scatter_add = (peers.flags & TT_PEER_SCATTER_ADD) != 0;
 
   for (int bb = g; bb < nb; bb += NG * UB) {
     int s[UB], len[UB];
@@ -187,13 +190,14 @@ ebc_forward_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_consta
             }
           }
         }
+        if (scatter_add && ln == 0) continue;      // row-wise shard: another rank holds this bag's rows
         float* o = peer_row(peers, pooled, bag0 + bi, plan.out_stride) + ocol;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const int c = l + v * G;
           if (c < units) {
             if (mean && ln > 1) a1[v].div((float)ln);
-            a1[v].store(o + c * VEC);
+            if (scatter_add) a1[v].atomic_add(o + c * VEC); else a1[v].store(o + c * VEC);
           }
         }
       }
@@ -202,14 +206,14 @@ ebc_forward_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_consta
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
       const int bi = bb + u * NG;
-      if (bi < nb) {
+      if (bi < nb && !(scatter_add && len[u] == 0)) {
         float* o = peer_row(peers, pooled, bag0 + bi, plan.out_stride) + ocol;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const int c = l + v * G;
           if (c < units) {
             if (mean && len[u] > 1) acc[u][v].div((float)len[u]);
-            acc[u][v].store(o + c * VEC);
+            if (scatter_add) acc[u][v].atomic_add(o + c * VEC); else acc[u][v].store(o + c * VEC);
           }
         }
       }
@@ -557,6 +561,7 @@ static int check_peers(const tt_peer_buffers* p, tt_peer_buffers* out, bool* all
   memset(out, 0, sizeof(*out));
   if (!p) return TT_OK;
   if (p->world < 1 || p->world > TT_MAX_PEERS || p->rows_per_peer < 1) return fail(TT_ERR_INVALID, "peer buffers: bad world / rows_per_peer");
+  if ((p->flags & ~TT_PEER_SCATTER_ADD) != 0) return fail(TT_ERR_INVALID, "peer buffers: unknown flags");
   for (int i = 0; i < p->world; ++i) {
     if (!p->ptr[i]) return fail(TT_ERR_INVALID, "peer buffers: null pointer for rank %d", i);
     if ((reinterpret_cast<uintptr_t>(p->ptr[i]) & 15) != 0) *all_vec4 = false;

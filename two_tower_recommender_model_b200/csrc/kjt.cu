@@ -173,6 +173,37 @@ __global__ void columns_lengths_kernel(const int64_t* __restrict__ ids, int32_t*
   if (i < n) lengths[i] = ids[i] != 0 ? 1 : 0;
 }
 
+__device__ __forceinline__ int64_t python_mod(int64_t id, int64_t R) {
+  int64_t r = id % R;
+  if (r != 0 && ((r < 0) != (R < 0))) r += R;
+  return r;
+}
+
+// row-wise shard: 1 where the (modulo) id falls into this rank's row range
+__global__ void columns_lengths_range_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ num_embeddings,
+                                             const int64_t* __restrict__ lo, const int64_t* __restrict__ hi,
+                                             int32_t* __restrict__ lengths, int64_t batch, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t id = ids[i];
+  int len = 0;
+  if (id != 0) {
+    const int64_t f = i / batch, r = python_mod(id, num_embeddings[f]);
+    len = (r >= lo[f] && r < hi[f]) ? 1 : 0;
+  }
+  lengths[i] = len;
+}
+
+__global__ void columns_values_range_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ num_embeddings,
+                                            const int64_t* __restrict__ lo, const int32_t* __restrict__ lengths,
+                                            const int32_t* __restrict__ offsets, int64_t* __restrict__ values,
+                                            int64_t batch, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || lengths[i] == 0) return;
+  const int64_t f = i / batch;
+  values[offsets[i]] = python_mod(ids[i], num_embeddings[f]) - lo[f];
+}
+
 __global__ void columns_values_kernel(const int64_t* __restrict__ ids,
                                       const int64_t* __restrict__ num_embeddings,
                                       const int32_t* __restrict__ offsets, int64_t* __restrict__ values,
@@ -291,6 +322,25 @@ int tt_kjt_from_columns(const int64_t* ids, const int64_t* num_embeddings, int64
   if (n > 0) {
     columns_values_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, num_embeddings, offsets, values, B, n);
     TT_CHECK_LAUNCH("columns_values");
+  }
+  return TT_OK;
+}
+
+int tt_kjt_from_columns_range(const int64_t* ids, const int64_t* num_embeddings, const int64_t* row_lo,
+                              const int64_t* row_hi, int64_t F, int64_t B, int64_t* values, int32_t* lengths,
+                              int32_t* offsets, void* ws, size_t ws_bytes, void* stream) {
+  TT_CHECK_ARG(F >= 0 && B >= 0 && lengths && offsets && num_embeddings && row_lo && row_hi, "from_columns_range: bad args");
+  cudaStream_t s = as_stream(stream);
+  int64_t n = F * B;
+  if (n > 0) {
+    columns_lengths_range_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, num_embeddings, row_lo, row_hi, lengths, B, n);
+    TT_CHECK_LAUNCH("columns_lengths_range");
+  }
+  int rc = scan_impl(lengths, offsets, n, nullptr, 1, ws, ws_bytes, s);
+  if (rc) return rc;
+  if (n > 0) {
+    columns_values_range_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, num_embeddings, row_lo, lengths, offsets, values, B, n);
+    TT_CHECK_LAUNCH("columns_values_range");
   }
   return TT_OK;
 }

@@ -128,6 +128,11 @@ class EmbeddingShardingPlanner:
                 nbytes = _table_bytes(cfg)
                 if want is None:
                     want = ShardingType.TABLE_WISE.value if (nbytes <= budget or W == 1) else ShardingType.ROW_WISE.value
+                    # Fewer tables than ranks: table-wise would leave ranks without embedding work while the owners
+                    # look up (and update) the global batch; row-wise spreads both evenly (TorchRec's planner reaches
+                    # the same verdict through its perf estimates).
+                    if W > len(cfgs) and cfg.num_embeddings >= W * 4096:
+                        want = ShardingType.ROW_WISE.value
                 if want == ShardingType.TABLE_WISE.value:
                     r = min(range(W), key=lambda i: (load[i], i))
                     if load[r] + nbytes > budget:

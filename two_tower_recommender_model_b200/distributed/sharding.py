@@ -92,12 +92,13 @@ class PeerExchange:
         self._h_pooled = symm.rendezvous(self.pooled, group)
         self._h_grad = symm.rendezvous(self.grad, group)
         self.pooled_peers = self._peers(self._h_pooled)
+        self.pooled_peers_scatter = self._peers(self._h_pooled, N.TT_PEER_SCATTER_ADD)
         self.grad_peers = self._peers(self._h_grad)
 
-    def _peers(self, handle):
+    def _peers(self, handle, flags: int = 0):
         from .. import _native as N
         pb = N.PeerBuffers()
-        pb.world, pb.rows_per_peer = self.world, self.rows
+        pb.world, pb.rows_per_peer, pb.flags = self.world, self.rows, flags
         for r, p in enumerate(handle.buffer_ptrs):
             pb.ptr[r] = p
         return pb
@@ -115,14 +116,17 @@ class _PeerTwLookup(torch.autograd.Function):
     that owns no table-wise table: it still takes part in the barriers and stages its gradient."""
 
     @staticmethod
-    def forward(ctx, ex, ebc, layout, kjt_keys, values, offsets, *anchors):
+    def forward(ctx, ex, ebc, layout, kjt_keys, values, offsets, scatter_add, *anchors):
         from ctypes import byref
         from .. import _native as N
+        if scatter_add:
+            ex.pooled.zero_()         # row-wise shards ADD their rows; bags nobody holds stay zero
         ex.barrier_pooled()           # every rank is done with the previous contents of the buffers
         if ebc is not None:
             dev = values.device
             plan, _ = ebc._build_plan(kjt_keys, ex.world * ex.rows, with_state=False, out_layout=layout)
-            N.call("tt_ebc_forward_peer", byref(plan), N.ptr(values), N.ptr(offsets), byref(ex.pooled_peers), N.stream_ptr(dev))
+            peers = ex.pooled_peers_scatter if scatter_add else ex.pooled_peers
+            N.call("tt_ebc_forward_peer", byref(plan), N.ptr(values), N.ptr(offsets), byref(peers), N.stream_ptr(dev))
             ctx.save_for_backward(values, offsets)
         ex.barrier_pooled()           # every owner's rows have landed here
         ctx.ex, ctx.ebc, ctx.layout, ctx.kjt_keys, ctx.n_anchors = ex, ebc, layout, kjt_keys, len(anchors)
@@ -152,7 +156,7 @@ class _PeerTwLookup(torch.autograd.Function):
             if dense_grads is not None:
                 grads = tuple(dense_grads)
         ex.barrier_grad()             # nobody still reads this rank's gradient rows
-        return (None,) * 6 + grads
+        return (None,) * 7 + grads
 
 
 def _native_bucketize(lengths, offsets, values, num_rows, F, B, W):
@@ -186,7 +190,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
         stores / loads over NVLink peer memory issued by the lookup kernels themselves."""
         super().__init__()
         self._peer_exchange = bool(peer_exchange)
-        self._peer: Optional[PeerExchange] = None
+        self._peer: Dict[str, PeerExchange] = {}
         self._pg = pg
         self._rank = dist.get_rank(pg)
         self._world = dist.get_world_size(pg)
@@ -282,6 +286,8 @@ class ShardedEmbeddingBagCollection(nn.Module):
         dense = getattr(kjt, "_id_columns", None)
         if dense is not None and grp.kind == "table_wise" and dense[0].is_cuda:
             return self._dist_dense_ids(grp, keys, dense[0], B)
+        if dense is not None and grp.kind == "row_wise" and self._peer_exchange and dense[0].is_cuda:
+            return self._dist_dense_ids_rw(grp, keys, dense[0], B)
         sub = kjt.permute([keys.index(f) for f in grp.features])
         lengths, values = sub.lengths(), sub.values()
         if grp.kind == "row_wise":
@@ -352,6 +358,34 @@ class ShardedEmbeddingBagCollection(nn.Module):
             self._local_rows_dev[grp.kind] = rows
         return KeyedJaggedTensor.from_id_columns(list(grp.local_features), cols, rows)
 
+    def _cached(self, key, make):
+        t = self._local_rows_dev.get(key)
+        if t is None:
+            t = make()
+            self._local_rows_dev[key] = t
+        return t
+
+    def _dist_dense_ids_rw(self, grp: _Group, keys: List[str], ids: torch.Tensor, B: int):
+        """Row-wise input dist for dense id columns with the peer-memory exchange: the [F, B] id columns are
+        ALL-GATHERED (8 bytes per id, fixed size, no host sync) and every rank keeps the ids of its own row range
+        (``tt_kjt_from_columns_range``); all other bags of the global batch are empty on this rank."""
+        W, pg, dev = self._world, self._pg, ids.device
+        F = len(grp.features)
+        order = [keys.index(f) for f in grp.features]
+        send = ids if order == list(range(ids.shape[0])) else ids.index_select(
+            0, self._cached(("order", grp.kind, tuple(order)), lambda: torch.tensor(order, dtype=torch.int64, device=dev)))
+        gathered = ids.new_empty(W * F * B)
+        dist.all_gather_into_tensor(gathered, send.contiguous().view(-1), group=pg)
+        cols = gathered.view(W, F, B).permute(1, 0, 2).reshape(F, W * B)
+        rows = self._cached(("rows", grp.kind), lambda: torch.tensor([grp.feat_rows[f] for f in grp.features], dtype=torch.int64, device=dev))
+        table_of = {f: c.name for c in self._configs for f in c.feature_names}
+        lo = self._cached(("lo", grp.kind), lambda: torch.tensor([self._shard_info[table_of[f]][1] for f in grp.features], dtype=torch.int64, device=dev))
+        hi = self._cached(("hi", grp.kind), lambda: torch.tensor([self._shard_info[table_of[f]][1] + self._shard_info[table_of[f]][2]
+                                                                 for f in grp.features], dtype=torch.int64, device=dev))
+        kjt = KeyedJaggedTensor.from_id_columns(list(grp.local_features), cols, rows, row_range=(lo, hi))
+        kjt._peer_scatter = True
+        return kjt
+
     @staticmethod
     def _permute_no_sync(kjt: KeyedJaggedTensor, perm: List[int], total: int) -> KeyedJaggedTensor:
         # KJT.permute needs length_per_key only to size the output; a true permutation keeps the total.
@@ -380,7 +414,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
         # table-wise: lookup over the global batch, rows go home by all-to-all
         d_by_rank = [sum(self._tw.feat_dim[f] for f in d) for d in self._tw.dest_features]
         if self._tw.features and self._peer_exchange:
-            cols.update(self._tw_forward_peer(ctx, B))
+            cols.update(self._group_forward_peer(self._tw, ctx["tw"], self.tw_ebc, B, False))
         elif self._tw.features:
             d_loc = d_by_rank[self._rank]
             if ctx["tw"] is not None:
@@ -402,7 +436,10 @@ class ShardedEmbeddingBagCollection(nn.Module):
                     cols[f] = blk[:, c0:c0 + self._tw.feat_dim[f]]
                     c0 += self._tw.feat_dim[f]
         # row-wise: partial pools over the global batch, summed by reduce-scatter
-        if self._rw.features:
+        if self._rw.features and getattr(ctx["rw"], "_peer_scatter", False):
+            # one id per bag at most (dense id columns): mean pooling == sum pooling, nothing to divide
+            cols.update(self._group_forward_peer(self._rw, ctx["rw"], self.rw_ebc, B, True))
+        elif self._rw.features:
             part = self.rw_ebc(ctx["rw"]).values()                  # [W*B, sum D_rw]
             pooled = _ReduceScatterRows.apply(part, pg)             # [B, sum D_rw]
             c0 = 0
@@ -419,15 +456,19 @@ class ShardedEmbeddingBagCollection(nn.Module):
         values = torch.cat([cols[f] for f in self._out_features], dim=1)
         return KeyedTensor(keys=self._out_features, length_per_key=self._out_dims, values=values)
 
-    def _tw_forward_peer(self, ctx, B: int) -> Dict[str, torch.Tensor]:
-        tw_out = [f for f in self._out_features if f in self._tw.feat_dim]
+    def _group_forward_peer(self, grp: _Group, kjt, ebc, B: int, scatter_add: bool) -> Dict[str, torch.Tensor]:
+        """Lookup of one sharding group whose output exchange (and its backward) is done by the lookup kernels
+        themselves over NVLink peer memory: table-wise owners STORE rows into the sample's rank, row-wise shards
+        ADD theirs (``scatter_add``)."""
+        feats = [f for f in self._out_features if f in grp.feat_dim]
         col, layout_cols = 0, {}
-        for f in tw_out:
+        for f in feats:
             layout_cols[f] = col
-            col += self._tw.feat_dim[f]
-        if self._peer is None or self._peer.rows != B:
-            self._peer = PeerExchange(B, col, self._device, self._pg)   # collective: B is the same on every rank
-        kjt, ebc = ctx["tw"], self.tw_ebc
+            col += grp.feat_dim[f]
+        ex = self._peer.get(grp.kind)
+        if ex is None or ex.rows != B:
+            ex = PeerExchange(B, col, self._device, self._pg)   # collective: B is the same on every rank
+            self._peer[grp.kind] = ex
         if kjt is None:
             ebc, keys = None, ()
             values = offsets = None
@@ -439,8 +480,8 @@ class ShardedEmbeddingBagCollection(nn.Module):
                 anchors = (torch.zeros(0, dtype=torch.float32, device=self._device, requires_grad=True),)
             else:
                 anchors = tuple(ebc.embedding_bags[c.name].weight for c in ebc.embedding_bag_configs())
-        out = _PeerTwLookup.apply(self._peer, ebc, (col, layout_cols), keys, values, offsets, *anchors)
-        return {f: out[:, layout_cols[f]:layout_cols[f] + self._tw.feat_dim[f]] for f in tw_out}
+        out = _PeerTwLookup.apply(ex, ebc, (col, layout_cols), keys, values, offsets, scatter_add, *anchors)
+        return {f: out[:, layout_cols[f]:layout_cols[f] + grp.feat_dim[f]] for f in feats}
 
     # ---- checkpoint surface: ShardedTensor entries named like the unsharded module --------------
     def _local_weight(self, name: str) -> Optional[torch.Tensor]:

@@ -111,7 +111,8 @@ class KeyedJaggedTensor:
         return kjt
 
     @staticmethod
-    def from_id_columns(keys: List[str], ids: torch.Tensor, num_embeddings: torch.Tensor) -> "KeyedJaggedTensor":
+    def from_id_columns(keys: List[str], ids: torch.Tensor, num_embeddings: torch.Tensor,
+                        row_range: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> "KeyedJaggedTensor":
         """Device-side ``transform_to_torchrec_batch`` (utils/model_training.py:43-61):
         ``ids`` is ``[F, B]`` int64 on CUDA; id 0 -> empty bag, else
         ``id % num_embeddings[f]`` with length 1.  No host sync: ``values`` keeps
@@ -125,6 +126,14 @@ class KeyedJaggedTensor:
         offsets = torch.empty(F * B + 1, dtype=torch.int32, device=dev)
         ne = num_embeddings.to(device=dev, dtype=torch.int64).contiguous()
         ws = N.workspace(N.load().tt_kjt_from_columns_workspace_bytes(F, B), dev)
+        if row_range is not None:
+            # one row-wise shard: keep the ids of rows [lo[f], hi[f]) (values become shard-local), other bags are empty
+            lo, hi = row_range
+            N.call("tt_kjt_from_columns_range", N.ptr(ids), N.ptr(ne), N.ptr(lo), N.ptr(hi), F, B, N.ptr(values), N.ptr(lengths),
+                   N.ptr(offsets), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+            kjt = KeyedJaggedTensor(keys=keys, values=values, lengths=lengths, offsets=offsets, stride=B)
+            kjt._values_padded = True
+            return kjt
         N.call("tt_kjt_from_columns", N.ptr(ids), N.ptr(ne), F, B, N.ptr(values), N.ptr(lengths), N.ptr(offsets),
                N.ptr(ws), ws.numel(), N.stream_ptr(dev))
         kjt = KeyedJaggedTensor(keys=keys, values=values, lengths=lengths, offsets=offsets, stride=B)
