@@ -76,18 +76,37 @@ def ebc(args):
 
 
 def towers(args):
+    """Both towers (64 -> 128 -> 64), forward + backward.  precision bf16: the one-launch fused kernels
+    (bytes per sample: fwd 4*64 + 2*256 + 4*64 + (bf16 y) = 1152 B... see towers_tcgen05.cu); fp32: CUDA-core path."""
     dev = torch.device("cuda:0")
     B = args.B
-    mlp = tt.MLP(64, [128, 64], device=dev)
-    x = torch.randn(B, 64, device=dev, requires_grad=True)
     N.enable_timing(True)
+    if args.precision == "bf16":
+        mlps = [tt.MLP(64, [128, 64], device=dev, precision="bf16") for _ in range(2)]
+        params = []
+        for m in mlps:
+            for p in m._mlp:
+                params += [p._linear.weight, p._linear.bias]
+        pooled = torch.randn(B, 128, device=dev, requires_grad=True)
+        dys = [torch.randn(B, 64, device=dev) for _ in range(2)]
 
-    def run():
-        mlp(x).sum().backward()
+        def run():
+            ys = F.FusedTowersTC.apply(pooled, (0, 64), 64, *params)
+            torch.autograd.backward(list(ys), dys)
+        fwd_bytes = 2 * B * (4 * 64 + 2 * 64 + 2 * 128 + 4 * 64 + 2 * 64)
+        bwd_bytes = 2 * B * (4 * 64 + 2 * 64 + 2 * 128 + 2 * 64 + 4 * 64)
+    else:
+        mlp = tt.MLP(64, [128, 64], device=dev)
+        x = torch.randn(B, 64, device=dev, requires_grad=True)
+
+        def run():
+            mlp(x).sum().backward()
+        fwd_bytes = bwd_bytes = 0
     ms = timed(run, args.iters, warmup=args.warmup)
     for k, v in N.timing_summary().items():
-        print(f"{k:42s} {v['ms'] * 1e3:9.1f} us  x{v['calls']}")
-    print(f"one tower fwd+bwd {ms:.3f} ms")
+        by = fwd_bytes if "forward_fused" in k else (bwd_bytes if "backward_fused" in k else 0)
+        print(f"{k:42s} {v['ms'] * 1e3:9.1f} us  x{v['calls']}" + (f"  {by / v['ms'] / 1e6:8.1f} GB/s algorithmic" if by else ""))
+    print(f"towers fwd+bwd {ms:.3f} ms")
 
 
 def topk(args):
