@@ -146,3 +146,102 @@ def test_sparse_equals_dense_adagrad():
     rows = torch.unique(ids)
     oracle.rowwise_adagrad_sparse(w2, s2, rows, grad[rows], lr=0.1)
     torch.testing.assert_close(w1, w2); torch.testing.assert_close(s1, s2)
+
+
+# ------------------------------------------------------------------ peer-memory entry points on ONE GPU
+# tt_ebc_forward_peer / tt_ebc_backward_fused_peer only see pointers: three buffers on the same device stand in
+# for the ranks of a box, which checks the (rank, local row) addressing without a multi-GPU machine
+# (tests/test_gpu_multi.py runs the real thing over NVLink).
+def _peer_struct(N, bufs, rows_per_peer, flags=0):
+    pb = N.PeerBuffers()
+    pb.world, pb.rows_per_peer, pb.flags = len(bufs), rows_per_peer, flags
+    for i, b in enumerate(bufs):
+        pb.ptr[i] = b.data_ptr()
+    return pb
+
+
+@pytest.mark.parametrize("dims,rows,pooling,Bl,L", [([64, 64], [2000, 500], ["sum", "sum"], 300, 1),
+                                                     ([128, 36], [700, 90], ["mean", "sum"], 129, 6)])
+def test_peer_forward_and_backward_virtual_ranks(cuda, dims, rows, pooling, Bl, L):
+    from ctypes import byref
+    import two_tower_recommender_model_b200 as tt
+    from two_tower_recommender_model_b200 import _native as N
+    W = 3
+    B = W * Bl                                            # global batch, rank s owns rows [s*Bl, (s+1)*Bl)
+    specs, ebc, weights = build(cuda, dims, rows, pooling)
+    keys = [f"f{i}" for i in range(len(dims))]
+    v, l = random_kjt(keys, rows, B, L, seed=11 + L)
+    want = oracle.ebc_forward(specs, weights, keys, v, l)
+    kjt = tt.KeyedJaggedTensor.from_lengths_sync(keys, v.to(cuda), l.to(cuda))
+    vals, offs = kjt.values().contiguous(), kjt.offsets().to(torch.int32).contiguous()
+    D = sum(dims)
+    stride = D + 8                                        # wider buffer: columns start at 4
+    layout = (stride, {k: 4 + sum(dims[:i]) for i, k in enumerate(keys)})
+    bufs = [torch.full((Bl, stride), float("nan"), device=cuda) for _ in range(W)]
+    plan, _ = ebc._build_plan(tuple(keys), B, with_state=False, out_layout=layout)
+    pb = _peer_struct(N, bufs, Bl)
+    N.call("tt_ebc_forward_peer", byref(plan), N.ptr(vals), N.ptr(offs), byref(pb), N.stream_ptr(cuda))
+    got = torch.cat([b[:, 4:4 + D] for b in bufs]).cpu()
+    torch.testing.assert_close(got, want, rtol=RTOL, atol=ATOL)
+    assert all(bool(torch.isnan(b[:, :4]).all()) and bool(torch.isnan(b[:, 4 + D:]).all()) for b in bufs)   # nothing else touched
+
+    # backward: gradients read from the virtual ranks == gradients read from one matrix (same kernel, same order: exact)
+    apply_optimizer_in_backward(tt.RowWiseAdagrad, ebc.parameters(), {"lr": 0.05})
+    g = torch.randn(B, stride, device=cuda)
+    gbufs = [g[s * Bl:(s + 1) * Bl].clone() for s in range(W)]
+
+    def run(peer):
+        for i, s in enumerate(specs):
+            ebc.embedding_bags[s.name].weight.data.copy_(weights[i])
+        ebc._fused_state.clear()
+        spec = ebc._sparse_optimizer_spec(advance_step=True)
+        plan, _ = ebc._build_plan(tuple(keys), B, with_state=True, out_layout=layout)
+        n = vals.numel()
+        ws = N.workspace(N.load().tt_ebc_backward_workspace_bytes(n), cuda)
+        if peer:
+            pg = _peer_struct(N, gbufs, Bl)
+            N.call("tt_ebc_backward_fused_peer", byref(plan), byref(spec), N.ptr(vals), n, N.ptr(offs), byref(pg), N.ptr(ws), ws.numel(), N.stream_ptr(cuda))
+        else:
+            N.call("tt_ebc_backward_fused", byref(plan), byref(spec), N.ptr(vals), n, N.ptr(offs), N.ptr(g), N.ptr(ws), ws.numel(), N.stream_ptr(cuda))
+        return [ebc.embedding_bags[s.name].weight.detach().clone() for s in specs]
+
+    for a, b in zip(run(True), run(False)):
+        assert torch.equal(a, b)
+
+
+def test_peer_scatter_add_row_shards(cuda):
+    """Row-wise sharding over peer memory on one GPU: two 'ranks' hold row ranges of the tables, each looks up the ids of
+    ITS range for the global batch (tt_kjt_from_columns_range) and ADDS its rows into the zeroed per-rank buffers
+    (TT_PEER_SCATTER_ADD).  The union must equal the unsharded lookup; ids 0 are empty bags, ids >= rows wrap."""
+    from ctypes import byref
+    import two_tower_recommender_model_b200 as tt
+    from two_tower_recommender_model_b200 import _native as N
+    rows, D, Bl, W = [1001, 333], 64, 257, 2
+    B = W * Bl
+    specs, ebc, weights = build(cuda, [D, D], rows, ["sum", "mean"])
+    keys = ["f0", "f1"]
+    g = torch.Generator().manual_seed(5)
+    ids = torch.stack([torch.randint(0, 2 * r, (B,), generator=g) for r in rows])
+    ids[:, ::9] = 0
+    # oracle on the reference's transform (id 0 -> empty, else id % rows)
+    lens = (ids != 0).to(torch.int32).reshape(-1)
+    vals = torch.cat([(ids[f][ids[f] != 0] % rows[f]) for f in range(2)])
+    want = oracle.ebc_forward(specs, weights, keys, vals, lens)
+    bufs = [torch.zeros(Bl, 2 * D, device=cuda) for _ in range(W)]
+    pb = _peer_struct(N, bufs, Bl, N.TT_PEER_SCATTER_ADD)
+    rows_dev = torch.tensor(rows, device=cuda)
+    for s in range(W):                                    # shard s: rows [s*block, (s+1)*block) of every table
+        block = [-(-r // W) for r in rows]
+        lo = torch.tensor([s * b for b in block], device=cuda)
+        hi = torch.tensor([min((s + 1) * b, r) for b, r in zip(block, rows)], device=cuda)
+        kjt = tt.KeyedJaggedTensor.from_id_columns(keys, ids.to(cuda), rows_dev, row_range=(lo, hi))
+        n_live = int(kjt.offsets()[-1])
+        assert bool((kjt.values()[:n_live] >= 0).all()) and bool((kjt.values()[:n_live] < (hi - lo).max()).all())
+        shard = tt.EmbeddingBagCollection(tables=[tt.EmbeddingBagConfig(name=sp.name, embedding_dim=D, num_embeddings=int(hi[i] - lo[i]),
+                                                                        feature_names=list(sp.feature_names)) for i, sp in enumerate(specs)], device=cuda)
+        for i, sp in enumerate(specs):
+            shard.embedding_bags[sp.name].weight.data.copy_(weights[i][int(lo[i]):int(hi[i])])
+        plan, _ = shard._build_plan(tuple(keys), B, with_state=False)
+        N.call("tt_ebc_forward_peer", byref(plan), N.ptr(kjt.values()), N.ptr(kjt.offsets().to(torch.int32).contiguous()), byref(pb), N.stream_ptr(cuda))
+    got = torch.cat(bufs).cpu()
+    torch.testing.assert_close(got, want, rtol=RTOL, atol=ATOL)

@@ -75,6 +75,33 @@ def test_block_bucketize(cuda, F, B, L, W, rows):
     assert torch.equal((nv.cpu() + w_of * blocks[f_of])[unb.cpu()], v)
 
 
+@pytest.mark.parametrize("F,B,W,rows", [(2, 1000, 4, [1500, 900]), (1, 9, 2, [10]), (3, 4097, 8, [100_000_000, 50, 12345])])
+def test_from_id_columns_range_is_one_bucket_of_block_bucketize(cuda, F, B, W, rows):
+    """tt_kjt_from_columns_range (row-wise shard of a dense id-column batch) == the reference transform
+    (utils/model_training.py:43-61) followed by bucket `w` of fbgemm::block_bucketize_sparse_features."""
+    import two_tower_recommender_model_b200 as tt
+    g = torch.Generator().manual_seed(F * B + W)
+    ids = torch.stack([torch.randint(0, 3 * r, (B,), generator=g) for r in rows])
+    ids[:, ::5] = 0
+    raw = {f"f{i}": ids[i].tolist() for i in range(F)}
+    raw["label"] = [0] * B
+    keys = [f"f{i}" for i in range(F)]
+    v, l, _ = oracle.transform_to_torchrec_batch(raw, keys, rows)
+    nl, nv, _ = block_bucketize_vectorized(l, v, rows, W, B)
+    noff = oracle.lengths_to_offsets(nl).long()
+    rows_dev = torch.tensor(rows, device=cuda)
+    for w in range(W):
+        blocks = [-(-r // W) for r in rows]
+        lo = torch.tensor([w * b for b in blocks], device=cuda)
+        hi = torch.tensor([min((w + 1) * b, r) for b, r in zip(blocks, rows)], device=cuda)
+        kjt = tt.KeyedJaggedTensor.from_id_columns(keys, ids.to(cuda), rows_dev, row_range=(lo, hi))
+        want_l = nl[w * F * B:(w + 1) * F * B]
+        want_v = nv[int(noff[w * F * B]):int(noff[(w + 1) * F * B])]
+        assert torch.equal(kjt.lengths().cpu(), want_l)
+        assert torch.equal(kjt.offsets().cpu().long(), oracle.lengths_to_offsets(want_l).long())
+        assert torch.equal(kjt.values()[:want_v.numel()].cpu(), want_v)
+
+
 @pytest.mark.parametrize("n,bits", [(1, 8), (31, 5), (2048, 16), (2049, 25), (131072, 25), (1_300_000, 28), (70000, 32)])
 def test_radix_sort_stable(cuda, n, bits):
     from two_tower_recommender_model_b200.functional import sort_pairs
