@@ -93,6 +93,11 @@ def build_model(cfg, dev):
     apply_optimizer_in_backward(tt.RowWiseAdagrad, task.two_tower.ebc.parameters(), {"lr": cfg["sparse_lr"]})
     peer = cfg.get("exchange", "nccl") == "peer" and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
     plan = None
+    if peer and os.environ.get("TT_BENCH_SHARDING") and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints   # diagnostics: force a sharding type
+        cons = {f"t_{c}": ParameterConstraints(sharding_types=[os.environ["TT_BENCH_SHARDING"]]) for c in CAT}
+        plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=torch.distributed.get_world_size()), constraints=cons
+                                           ).collective_plan(task, tt.get_default_sharders(), torch.distributed.GroupMember.WORLD)
     if not peer and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
         # the NCCL exchange path is benchmarked table-wise (its row-wise input dist needs a host sync per step)
         from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
@@ -307,6 +312,7 @@ def run_ours(args):
         "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(ms_e2e, 4),
                 "h2d_bytes_per_step": raw[0].nbytes(), "d2h_bytes_per_step": 4, "last_loss": last, "api": e2e_api},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
+        "calls_ms": {k: round(v["ms"], 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1]["ms"])},
         "ebc_lookup_gbs": kernels.get("tt_ebc_forward", kernels.get("tt_ebc_forward_peer", {})).get("achieved"),
     }
     if world == 1:
