@@ -57,7 +57,13 @@ def ebc(args):
     e = tt.EmbeddingBagCollection(tables=cfgs, device=dev)
     aob(tt.RowWiseAdagrad, e.parameters(), {"lr": 0.01})
     lens = torch.full((2 * B,), L, dtype=torch.int32, device=dev)
-    kjts = [tt.KeyedJaggedTensor.from_lengths_sync(["f0", "f1"], torch.randint(0, R, (2 * B * L,), device=dev), lens) for _ in range(4)]
+    def draw():
+        if args.zipf > 0:   # Zipf(alpha) ids expose hot-row handling in the fused update
+            r = torch.arange(1, min(R, 1 << 22) + 1, device=dev, dtype=torch.float64)
+            pmf = r.pow(-args.zipf)
+            return torch.multinomial((pmf / pmf.sum()).float(), 2 * B * L, replacement=True)
+        return torch.randint(0, R, (2 * B * L,), device=dev)
+    kjts = [tt.KeyedJaggedTensor.from_lengths_sync(["f0", "f1"], draw(), lens) for _ in range(4)]
     go = torch.randn(B, 2 * D, device=dev)
     N.enable_timing(True)
     i = [0]
@@ -72,7 +78,7 @@ def ebc(args):
     bwd_bytes = 2 * (4 * B * D + 8 * B * L) + uniq * (8 * D + 8)
     for k, v in N.timing_summary().items():
         by = fwd_bytes if "forward" in k else bwd_bytes
-        print(f"{k:42s} {v['ms'] * 1e3:9.1f} us  x{v['calls']}  {by / v['ms'] / 1e6:8.1f} GB/s algorithmic ({by / 1e6:.1f} MB)")
+        print(f"{k:42s} {v['ms'] * 1e3:9.1f} us  x{v['calls']}  {by / v['ms'] / 1e6:8.1f} GB/s algorithmic ({by / 1e6:.1f} MB; unique rows {uniq})")
 
 
 def towers(args):
@@ -130,5 +136,6 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--zipf", type=float, default=0.0, help="ebc: draw ids from Zipf(alpha) instead of uniform")
     a = ap.parse_args()
     {"softmax": softmax, "ebc": ebc, "towers": towers, "topk": topk}[a.what](a)

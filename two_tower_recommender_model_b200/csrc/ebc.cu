@@ -278,136 +278,16 @@ __global__ void ebc_backward_tail_kernel(const int32_t* __restrict__ offsets, in
 #ifndef TT_EBC_UPD_MINB
 #define TT_EBC_UPD_MINB 8
 #endif
+constexpr int kHotSeg = 128;          // positions per segment of the fused backward (power of two)
+constexpr int kHotRowFloats = 1024;   // widest embedding row the scratch is sized for
+
+// One row's update from its summed gradient g (held across the G lanes of the group): row-wise Adagrad / Adam, SGD,
+// or accumulation into a dense gradient.
 template <int VEC, int G, int NV>
-__global__ void __launch_bounds__(kEbcThreads, NV == 1 ? TT_EBC_UPD_MINB : 1)
-ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
-                           const __grid_constant__ tt_sparse_optimizer opt,
-                           const uint32_t* __restrict__ keys, const uint32_t* __restrict__ payload,
-                           int64_t n, const int32_t* __restrict__ offsets,
-                           const float* __restrict__ grad_out, const __grid_constant__ tt_peer_buffers peers) {
-  const int64_t gid = ((int64_t)blockIdx.x * kEbcThreads + threadIdx.x) / G;
-  const int l = threadIdx.x % G;
-  if (gid >= n) return;
-  const uint32_t key = keys[gid];
-  if (key >= (uint32_t)plan.total_rows) return;        // sentinel (unused key / bad id)
-  if (gid > 0 && keys[gid - 1] == key) return;         // not the head of its run
-  int slot = 0;
-  for (int i = 0; i < plan.num_slots; ++i)
-    if ((int64_t)key >= plan.row_base[i] && (int64_t)key < plan.row_base[i] + plan.num_rows[i]) {
-      slot = i;
-      break;
-    }
-  const int64_t row = (int64_t)key - plan.row_base[slot];
+__device__ __forceinline__ void apply_row(const tt_ebc_plan& plan, const tt_sparse_optimizer& opt, int slot, int64_t row,
+                                          int l, unsigned mask, Vec<VEC> (&g)[NV]) {
   const int D = plan.dim[slot];
   const int units = D / VEC;
-  const int B = plan.batch_size;
-
-  // The weight row (and Adam's first-moment row) is a random DRAM read whose address is known as
-  // soon as the key is: start pulling it into L2 now, so its latency overlaps the walk over the
-  // run's gradient rows below (prefetch costs no registers, unlike an early load).
-#ifdef TT_EBC_UPD_PREFETCH
-  {
-    const char* wrow = reinterpret_cast<const char*>(static_cast<const float*>(plan.weights[slot]) + row * D);
-    const int bytes = D * 4;
-    for (int o = l * 128; o < bytes; o += G * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(wrow + o));
-    if (opt.kind == TT_OPT_ROWWISE_ADAM || opt.kind == TT_OPT_DENSE_GRAD) {
-      const char* mrow = reinterpret_cast<const char*>(static_cast<const float*>(plan.state1[slot]) + row * D);
-      for (int o = l * 128; o < bytes; o += G * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(mrow + o));
-    }
-    if (l == 0 && (opt.kind == TT_OPT_ROWWISE_ADAGRAD || opt.kind == TT_OPT_ROWWISE_ADAM))
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const float*>(plan.state0[slot]) + row));
-  }
-#endif
-
-  Vec<VEC> g[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) g[v].zero();
-  unsigned mask = 0xffffffffu;
-  int gshift = 0;
-  if constexpr (G < 32) {
-    gshift = (threadIdx.x & 31) / G * G;
-    mask = ((1u << (G & 31)) - 1u) << gshift;
-  }
-  // geometry of one occurrence: where its gradient row starts and its mean divisor (0 = none)
-  auto locate = [&](uint32_t bag, int64_t& goff, float& flen) {
-    const int sl = bag / B;
-    const int b = bag - sl * B;
-    flen = 0.f;
-    if (plan.pooling[sl] == TT_POOL_MEAN) {
-      const int64_t kb = (int64_t)plan.kjt_index[sl] * B + b;
-      const int len = offsets[kb + 1] - offsets[kb];
-      if (len > 1) flen = (float)len;
-    }
-    // "offset" of the gradient row, as a pointer value: the row may live on another GPU
-    goff = reinterpret_cast<int64_t>(peer_row(peers, const_cast<float*>(grad_out), b, plan.out_stride) + plan.out_col[sl]);
-  };
-  auto accumulate = [&](int64_t goff, float flen) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = l + v * G;
-      if (c < units) {
-        Vec<VEC> x;
-        x.load(reinterpret_cast<const float*>(goff) + c * VEC);
-        if (flen > 0.f) x.div(flen);
-        g[v].add(x);
-      }
-    }
-  };
-  {  // the head occurrence
-    int64_t goff;
-    float flen;
-    locate(payload[gid], goff, flen);
-    accumulate(goff, flen);
-  }
-  int64_t j = gid + 1;
-  if (j < n && keys[j] == key) {
-    // The run continues (duplicate ids; hot rows of small tables have thousands of occurrences).
-    // The group reads G (key, bag) pairs with one coalesced load, every lane resolves the geometry
-    // of ITS occurrence, and the gradient rows are then fetched two at a time in run order: the
-    // per-occurrence chain key -> bag -> offsets -> row becomes one round trip per G occurrences.
-    constexpr unsigned full = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
-    bool more = true;
-    while (more) {
-      const int64_t pos = j + l;
-      const bool mine = pos < n && keys[pos] == key;
-      int64_t goff = 0;
-      float flen = 0.f;
-      if (mine) locate(payload[pos], goff, flen);
-      const unsigned same = (__ballot_sync(mask, mine) >> gshift) & full;
-      const int cnt = same == full ? G : __ffs(~same) - 1;   // length of the leading run of matches
-      more = cnt == G;
-      for (int e = 0; e < cnt; e += 2) {
-        const int64_t g0 = __shfl_sync(mask, goff, e, G);
-        const float f0 = __shfl_sync(mask, flen, e, G);
-        const int e1 = e + 1 < G ? e + 1 : e;
-        const int64_t g1 = __shfl_sync(mask, goff, e1, G);
-        const float f1 = __shfl_sync(mask, flen, e1, G);
-        Vec<VEC> x0[NV], x1[NV];
-        const bool two = e + 1 < cnt;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int c = l + v * G;
-          if (c < units) {
-            x0[v].load(reinterpret_cast<const float*>(g0) + c * VEC);
-            if (two) x1[v].load(reinterpret_cast<const float*>(g1) + c * VEC);
-          }
-        }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          if (l + v * G < units) {
-            if (f0 > 0.f) x0[v].div(f0);
-            g[v].add(x0[v]);
-            if (two) {
-              if (f1 > 0.f) x1[v].div(f1);
-              g[v].add(x1[v]);
-            }
-          }
-        }
-      }
-      j += G;
-    }
-  }
-
   // mean over D of g^2 (group reduction)
   float ss = 0.f;
 #pragma unroll
@@ -483,6 +363,175 @@ ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
   }
 }
 
+template <int VEC, int G, int NV>
+__global__ void __launch_bounds__(kEbcThreads, NV == 1 ? TT_EBC_UPD_MINB : 1)
+ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
+                           const __grid_constant__ tt_sparse_optimizer opt,
+                           const uint32_t* __restrict__ keys, const uint32_t* __restrict__ payload,
+                           int64_t n, const int32_t* __restrict__ offsets,
+                           const float* __restrict__ grad_out, const __grid_constant__ tt_peer_buffers peers,
+                           float* __restrict__ hot, int hot_stride) {
+  constexpr int64_t hot_seg = kHotSeg;
+  const int64_t gid = ((int64_t)blockIdx.x * kEbcThreads + threadIdx.x) / G;
+  const int l = threadIdx.x % G;
+  if (gid >= n) return;
+  const uint32_t key = keys[gid];
+  if (key >= (uint32_t)plan.total_rows) return;        // sentinel (unused key / bad id)
+  // A group works on one SEGMENT of a run: from the run's head, or from a position that is a multiple of hot_seg
+  // inside a run, up to the next such boundary.  Bounded work per group whatever the id distribution: a row hit
+  // by 100 000 ids of the batch (Zipf) is summed by ~800 groups all over the GPU instead of by one.
+  if (gid > 0 && keys[gid - 1] == key && (gid & (hot_seg - 1)) != 0) return;   // neither a head nor on a boundary
+  const int64_t lim = min(n, (gid | (hot_seg - 1)) + 1);
+  int slot = 0;
+  for (int i = 0; i < plan.num_slots; ++i)
+    if ((int64_t)key >= plan.row_base[i] && (int64_t)key < plan.row_base[i] + plan.num_rows[i]) {
+      slot = i;
+      break;
+    }
+  const int64_t row = (int64_t)key - plan.row_base[slot];
+  const int D = plan.dim[slot];
+  const int units = D / VEC;
+  const int B = plan.batch_size;
+
+  // The weight row (and Adam's first-moment row) is a random DRAM read whose address is known as
+  // soon as the key is: start pulling it into L2 now, so its latency overlaps the walk over the
+  // run's gradient rows below (prefetch costs no registers, unlike an early load).
+#ifdef TT_EBC_UPD_PREFETCH
+  {
+    const char* wrow = reinterpret_cast<const char*>(static_cast<const float*>(plan.weights[slot]) + row * D);
+    const int bytes = D * 4;
+    for (int o = l * 128; o < bytes; o += G * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(wrow + o));
+    if (opt.kind == TT_OPT_ROWWISE_ADAM || opt.kind == TT_OPT_DENSE_GRAD) {
+      const char* mrow = reinterpret_cast<const char*>(static_cast<const float*>(plan.state1[slot]) + row * D);
+      for (int o = l * 128; o < bytes; o += G * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(mrow + o));
+    }
+    if (l == 0 && (opt.kind == TT_OPT_ROWWISE_ADAGRAD || opt.kind == TT_OPT_ROWWISE_ADAM))
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const float*>(plan.state0[slot]) + row));
+  }
+#endif
+
+  Vec<VEC> g[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) g[v].zero();
+  unsigned mask = 0xffffffffu;
+  int gshift = 0;
+  if constexpr (G < 32) {
+    gshift = (threadIdx.x & 31) / G * G;
+    mask = ((1u << (G & 31)) - 1u) << gshift;
+  }
+  // geometry of one occurrence: where its gradient row starts and its mean divisor (0 = none)
+  auto locate = [&](uint32_t bag, int64_t& goff, float& flen) {
+    const int sl = bag / B;
+    const int b = bag - sl * B;
+    flen = 0.f;
+    if (plan.pooling[sl] == TT_POOL_MEAN) {
+      const int64_t kb = (int64_t)plan.kjt_index[sl] * B + b;
+      const int len = offsets[kb + 1] - offsets[kb];
+      if (len > 1) flen = (float)len;
+    }
+    // "offset" of the gradient row, as a pointer value: the row may live on another GPU
+    goff = reinterpret_cast<int64_t>(peer_row(peers, const_cast<float*>(grad_out), b, plan.out_stride) + plan.out_col[sl]);
+  };
+  auto accumulate = [&](int64_t goff, float flen) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = l + v * G;
+      if (c < units) {
+        Vec<VEC> x;
+        x.load(reinterpret_cast<const float*>(goff) + c * VEC);
+        if (flen > 0.f) x.div(flen);
+        g[v].add(x);
+      }
+    }
+  };
+  {  // the head occurrence
+    int64_t goff;
+    float flen;
+    locate(payload[gid], goff, flen);
+    accumulate(goff, flen);
+  }
+  int64_t j = gid + 1;
+  int64_t run_end = j;                                 // one past the last occurrence this group summed
+  if (j < lim && keys[j] == key) {
+    // The run continues (duplicate ids; hot rows of small tables have thousands of occurrences).
+    // The group reads G (key, bag) pairs with one coalesced load, every lane resolves the geometry
+    // of ITS occurrence, and the gradient rows are then fetched two at a time in run order: the
+    // per-occurrence chain key -> bag -> offsets -> row becomes one round trip per G occurrences.
+    constexpr unsigned full = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+    bool more = true;
+    while (more) {
+      const int64_t pos = j + l;
+      const bool mine = pos < lim && keys[pos] == key;
+      int64_t goff = 0;
+      float flen = 0.f;
+      if (mine) locate(payload[pos], goff, flen);
+      const unsigned same = (__ballot_sync(mask, mine) >> gshift) & full;
+      const int cnt = same == full ? G : __ffs(~same) - 1;   // length of the leading run of matches
+      more = cnt == G;
+      run_end = j + cnt;
+      for (int e = 0; e < cnt; e += 2) {
+        const int64_t g0 = __shfl_sync(mask, goff, e, G);
+        const float f0 = __shfl_sync(mask, flen, e, G);
+        const int e1 = e + 1 < G ? e + 1 : e;
+        const int64_t g1 = __shfl_sync(mask, goff, e1, G);
+        const float f1 = __shfl_sync(mask, flen, e1, G);
+        Vec<VEC> x0[NV], x1[NV];
+        const bool two = e + 1 < cnt;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = l + v * G;
+          if (c < units) {
+            x0[v].load(reinterpret_cast<const float*>(g0) + c * VEC);
+            if (two) x1[v].load(reinterpret_cast<const float*>(g1) + c * VEC);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (l + v * G < units) {
+            if (f0 > 0.f) x0[v].div(f0);
+            g[v].add(x0[v]);
+            if (two) {
+              if (f1 > 0.f) x1[v].div(f1);
+              g[v].add(x1[v]);
+            }
+          }
+        }
+      }
+      j += G;
+    }
+  }
+
+  // A run that crosses an aligned segment boundary is summed by several groups: every part is added to the
+  // run's scratch row (red.global.add) and ebc_backward_hot_apply_kernel applies the optimizer once.
+  const bool head = gid == 0 || keys[gid - 1] != key;
+  const int64_t seg_end = (gid | (hot_seg - 1)) + 1;
+  // only a segment filled up to its boundary can continue in the next one (one extra key load, rarely)
+  const bool continues = run_end == seg_end && seg_end < n && keys[seg_end] == key;
+  if (head && !continues) {
+    apply_row<VEC, G, NV>(plan, opt, slot, row, l, mask, g);
+    return;
+  }
+  int64_t h = gid;                                   // position of the run's head
+  if (!head) {
+    if (gid > hot_seg && keys[gid - hot_seg - 1] == key) {   // older than the previous segment: lower_bound(key)
+      int64_t lo = 0, hi = gid - hot_seg - 1;          // keys[hi] == key
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      h = lo;
+    } else {
+      h = gid - hot_seg;                               // any position of the previous segment gives the same scratch row
+    }
+  }
+  float* acc = hot + (h / hot_seg + 1) * (int64_t)hot_stride;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = l + v * G;
+    if (c < units) g[v].atomic_add(acc + c * VEC);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -551,6 +600,43 @@ static int for_each_class(const tt_ebc_plan* p, bool all_vec4, SlotClasses* cls,
     default: return fail(TT_ERR_UNSUPPORTED, "ebc: no kernel for shape class %d", ID); \
   }
 
+// Runs that crossed a segment boundary: slot b (1-based) holds the complete gradient sum of the run whose FIRST
+// crossed boundary is b * hot_seg.  One group per boundary applies the optimizer for it.
+template <int VEC, int G, int NV>
+__global__ void __launch_bounds__(kEbcThreads)
+ebc_backward_hot_apply_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_constant__ tt_sparse_optimizer opt,
+                              const uint32_t* __restrict__ keys, int64_t n, const float* __restrict__ hot, int hot_stride,
+                              int64_t num_bounds) {
+  constexpr int64_t hot_seg = kHotSeg;
+  const int64_t b = ((int64_t)blockIdx.x * kEbcThreads + threadIdx.x) / G + 1;
+  const int l = threadIdx.x % G;
+  if (b > num_bounds) return;
+  const int64_t q = b * hot_seg;
+  if (q >= n) return;
+  const uint32_t key = keys[q];
+  if (key >= (uint32_t)plan.total_rows || keys[q - 1] != key) return;           // no run crosses this boundary
+  if (b > 1 && keys[q - hot_seg - 1] == key) return;                            // the run crossed an earlier boundary first
+  int slot = 0;
+  for (int i = 0; i < plan.num_slots; ++i)
+    if ((int64_t)key >= plan.row_base[i] && (int64_t)key < plan.row_base[i] + plan.num_rows[i]) {
+      slot = i;
+      break;
+    }
+  const int64_t row = (int64_t)key - plan.row_base[slot];
+  const int units = plan.dim[slot] / VEC;
+  unsigned mask = 0xffffffffu;
+  if constexpr (G < 32) mask = ((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G);
+  Vec<VEC> g[NV];
+  const float* acc = hot + b * (int64_t)hot_stride;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = l + v * G;
+    g[v].zero();
+    if (c < units) g[v].load(acc + c * VEC);
+  }
+  apply_row<VEC, G, NV>(plan, opt, slot, row, l, mask, g);
+}
+
 }  // namespace tt
 
 using namespace tt;
@@ -608,7 +694,8 @@ int tt_ebc_forward_peer(const tt_ebc_plan* h_plan, const int64_t* values, const 
 
 size_t tt_ebc_backward_workspace_bytes(int64_t n) {
   if (n < 1) n = 1;
-  return 4 * align_up((size_t)n * 4, 256) + sort_workspace_bytes(n) + 1024;
+  return 4 * align_up((size_t)n * 4, 256) + sort_workspace_bytes(n) + 1024 +
+         align_up((size_t)(n / kHotSeg + 2) * kHotRowFloats * 4, 256);
 }
 
 static int ebc_backward_impl(const tt_ebc_plan* h_plan, const tt_sparse_optimizer* h_opt,
@@ -641,7 +728,8 @@ static int ebc_backward_impl(const tt_ebc_plan* h_plan, const tt_sparse_optimize
   uint32_t* payload = w.take<uint32_t>(n);
   uint32_t* skeys = w.take<uint32_t>(n);
   uint32_t* spayload = w.take<uint32_t>(n);
-  if (!keys || !payload || !skeys || !spayload) return fail(TT_ERR_WORKSPACE, "ebc_backward: workspace too small");
+  float* hot = w.take<float>((size_t)(n / kHotSeg + 2) * kHotRowFloats);
+  if (!keys || !payload || !skeys || !spayload || !hot) return fail(TT_ERR_WORKSPACE, "ebc_backward: workspace too small");
 
   const int tiles = (h_plan->batch_size + kBagsPerCta - 1) / kBagsPerCta;
   ebc_backward_keys_kernel<<<(unsigned)(tiles * h_plan->num_kjt_keys), kEbcThreads, 0, s>>>(
@@ -665,12 +753,28 @@ static int ebc_backward_impl(const tt_ebc_plan* h_plan, const tt_sparse_optimize
   const int id = class_id(c.vec, c.g, c.nv);
   const int64_t threads = n * c.g;
   const unsigned grid = (unsigned)((threads + kEbcThreads - 1) / kEbcThreads);
+  if (max_dim > kHotRowFloats) return fail(TT_ERR_UNSUPPORTED, "ebc_backward: embedding_dim %d > %d", max_dim, kHotRowFloats);
+  const int hot_stride = (max_dim + 3) / 4 * 4;
+  const int64_t num_bounds = (n - 1) / kHotSeg;          // boundaries kHotSeg, 2*kHotSeg, ... inside [1, n)
+  if (num_bounds > 0) {
+    cudaError_t e = cudaMemsetAsync(hot, 0, (size_t)(num_bounds + 1) * hot_stride * 4, s);
+    if (e != cudaSuccess) return fail(TT_ERR_CUDA, "ebc_backward memset: %s", cudaGetErrorString(e));
+  }
 #define TT_LAUNCH_BWD(V, G, N)                                                                        \
   ebc_backward_update_kernel<V, G, N><<<grid, kEbcThreads, 0, s>>>(*h_plan, *h_opt, skeys, spayload, n, \
-                                                                   offsets, grad_out, peers)
+                                                                   offsets, grad_out, peers, hot, hot_stride)
   TT_DISPATCH_CLASS(id, TT_LAUNCH_BWD);
 #undef TT_LAUNCH_BWD
   TT_CHECK_LAUNCH("ebc_backward_update");
+  if (num_bounds > 0) {
+    const unsigned hgrid = (unsigned)((num_bounds * c.g + kEbcThreads - 1) / kEbcThreads);
+#define TT_LAUNCH_HOT(V, G, N)                                                                              \
+  ebc_backward_hot_apply_kernel<V, G, N><<<hgrid, kEbcThreads, 0, s>>>(*h_plan, *h_opt, skeys, n, hot, hot_stride, \
+                                                                       num_bounds)
+    TT_DISPATCH_CLASS(id, TT_LAUNCH_HOT);
+#undef TT_LAUNCH_HOT
+    TT_CHECK_LAUNCH("ebc_backward_hot_apply");
+  }
   return TT_OK;
 }
 
