@@ -264,3 +264,50 @@ def _graph_vs_eager(cuda, tt):
     assert losses1 == pytest.approx(losses2, rel=1e-6)
     for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
         torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7, msg=lambda m: f"{k}: {m}")
+
+
+def test_ray_tune_variant_towers(cuda):
+    from helpers import random_kjt
+    """ray_tune_optuna_tuning_alex_test.py:227-306: several features per tower, different layer stacks per tower and
+    dense features concatenated to the tower inputs; forward against plain torch on the same weights (fp32 path)."""
+    import two_tower_recommender_model_b200 as tt
+    feats_u, feats_i = ["u_a", "u_b"], ["i_a"]
+    dims = {"u_a": 36, "u_b": 4, "i_a": 36}
+    rows = {"u_a": 100, "u_b": 7, "i_a": 90}
+    cfgs = [tt.EmbeddingBagConfig(name=f"t_{k}", embedding_dim=dims[k], num_embeddings=rows[k], feature_names=[k]) for k in dims]
+    ebc = tt.EmbeddingBagCollection(tables=cfgs, device=cuda)
+    model = tt.TwoTower(ebc, [[64, 16], [32, 16]], device=cuda, query_features=feats_u, candidate_features=feats_i,
+                        dense_index=3, dense_dim=5)
+    task = tt.TwoTowerTrainTask(model)
+    B = 97
+    g = torch.Generator().manual_seed(0)
+    keys = list(dims)
+    v, l = random_kjt(keys, [rows[k] for k in keys], B, 1, seed=5)
+    dense = torch.randn(B, 5, generator=g)
+    labels = torch.randint(0, 2, (B,), generator=g, dtype=torch.int32)
+    batch = tt.Batch(dense.to(cuda), tt.KeyedJaggedTensor.from_lengths_sync(keys, v.to(cuda), l.to(cuda)), labels.to(cuda))
+    loss, (_, logits, _) = task(batch)
+    # plain torch
+    sd = {k: t.detach().cpu() for k, t in model.state_dict().items()}
+    offs = oracle.lengths_to_offsets(l).long()
+    pooled = {}
+    for i, k in enumerate(keys):
+        w = sd[f"ebc.embedding_bags.t_{k}.weight"]
+        out = torch.zeros(B, dims[k])
+        for b in range(B):
+            for p in range(int(offs[i * B + b]), int(offs[i * B + b + 1])):
+                out[b] += w[v[p]]
+        pooled[k] = out
+
+    def mlp(x, prefix, n):
+        for j in range(n):
+            x = torch.relu(x @ sd[f"{prefix}._mlp.{j}._linear.weight"].t() + sd[f"{prefix}._mlp.{j}._linear.bias"])
+        return x
+    q = mlp(torch.cat([pooled["u_a"], pooled["u_b"], dense[:, :3]], 1), "query_proj", 2)
+    c = mlp(torch.cat([pooled["i_a"], dense[:, 3:]], 1), "candidate_proj", 2)
+    want_logits = (q * c).sum(1)
+    want = torch.nn.functional.binary_cross_entropy_with_logits(want_logits, labels.float())
+    torch.testing.assert_close(logits.cpu(), want_logits, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(loss.detach().cpu(), want, rtol=1e-5, atol=1e-6)
+    loss.backward()
+    assert model.query_proj._mlp[0]._linear.weight.grad is not None

@@ -21,9 +21,14 @@ from .sparse.jagged_tensor import KeyedJaggedTensor, KeyedTensor
 
 
 class TwoTower(nn.Module):
-    def __init__(self, embedding_bag_collection: EmbeddingBagCollection, layer_sizes: List[int],
+    def __init__(self, embedding_bag_collection: EmbeddingBagCollection, layer_sizes,
                  device: Optional[torch.device] = None, query_features: Optional[List[str]] = None,
-                 candidate_features: Optional[List[str]] = None, precision: str = "fp32") -> None:
+                 candidate_features: Optional[List[str]] = None, precision: str = "fp32",
+                 dense_index: Optional[int] = None, dense_dim: int = 0) -> None:
+        """``layer_sizes``: one list for both towers or ``[query_layers, candidate_layers]``;
+        ``dense_index`` / ``dense_dim``: the Ray-Tune variant of the reference
+        (ray_tune_optuna_tuning_alex_test.py:227-306) concatenates ``batch.dense_features[:, :dense_index]`` to the
+        query tower's input and ``[:, dense_index:dense_dim]`` to the candidate tower's; call ``forward(batch)`` then."""
         super().__init__()
         cfgs = embedding_bag_collection.embedding_bag_configs()
         if query_features is None and candidate_features is None:
@@ -37,10 +42,18 @@ class TwoTower(nn.Module):
         self._feature_names_query: List[str] = list(query_features)
         self._candidate_feature_names: List[str] = list(candidate_features)
         self.ebc = embedding_bag_collection
-        self.query_proj = MLP(in_size=sum(dim_of[f] for f in self._feature_names_query),
-                              layer_sizes=layer_sizes, device=device, precision=precision)
-        self.candidate_proj = MLP(in_size=sum(dim_of[f] for f in self._candidate_feature_names),
-                                  layer_sizes=layer_sizes, device=device, precision=precision)
+        per_tower = any(isinstance(x, (list, tuple)) for x in layer_sizes)
+        q_layers, c_layers = (list(layer_sizes[0]), list(layer_sizes[1])) if per_tower else (list(layer_sizes), list(layer_sizes))
+        self.dense_index = dense_index
+        self._dense_dim = dense_dim if dense_index is not None else 0
+        q_dense = dense_index if dense_index is not None else 0
+        c_dense = self._dense_dim - q_dense
+        if dense_index is not None and (q_dense < 0 or c_dense < 0):
+            raise ValueError("dense_index must lie inside [0, dense_dim]")
+        self.query_proj = MLP(in_size=sum(dim_of[f] for f in self._feature_names_query) + q_dense,
+                              layer_sizes=q_layers, device=device, precision=precision)
+        self.candidate_proj = MLP(in_size=sum(dim_of[f] for f in self._candidate_feature_names) + c_dense,
+                                  layer_sizes=c_layers, device=device, precision=precision)
 
     @staticmethod
     def _tower_input(pooled: KeyedTensor, features: List[str]) -> torch.Tensor:
@@ -54,6 +67,8 @@ class TwoTower(nn.Module):
     def _fused_plan(self, pooled: KeyedTensor):
         """(column offsets, in_dim, parameters) when both towers fit the one-launch fused kernels, else None."""
         towers = (self.query_proj, self.candidate_proj)
+        if self.dense_index is not None:
+            return None
         if any(m.precision != "bf16" or not m.all_relu() for m in towers) or pooled.values().shape[0] == 0:
             return None
         layers = [list(m._mlp) for m in towers]
@@ -69,8 +84,20 @@ class TwoTower(nn.Module):
                 params += [pc._linear.weight, pc._linear.bias]
         return [c for c, _ in wins], wins[0][1], params
 
-    def forward(self, kjt: KeyedJaggedTensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def forward(self, kjt) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``kjt``: the KeyedJaggedTensor (reference, utils/model_training.py:99) or the whole ``Batch`` (Ray-Tune variant)."""
+        batch = None
+        if isinstance(kjt, Batch):
+            batch, kjt = kjt, kjt.sparse_features
         pooled_embeddings = self.ebc(kjt)
+        if self.dense_index is not None:
+            if batch is None:
+                raise ValueError("this TwoTower concatenates dense features: call it with the Batch, not the KeyedJaggedTensor")
+            dense = batch.dense_features.to(torch.float32)
+            q_in = torch.cat([self._tower_input(pooled_embeddings, self._feature_names_query), dense[:, :self.dense_index]], dim=1)
+            c_in = torch.cat([self._tower_input(pooled_embeddings, self._candidate_feature_names),
+                              dense[:, self.dense_index:self._dense_dim]], dim=1)
+            return self.query_proj(q_in), self.candidate_proj(c_in)
         plan = self._fused_plan(pooled_embeddings)
         if plan is not None:
             cols, in_dim, params = plan
@@ -100,7 +127,8 @@ class TwoTowerTrainTask(nn.Module):
         self.loss_fn: nn.Module = nn.BCEWithLogitsLoss()  # kept for API parity; the fused kernel computes it
 
     def forward(self, batch: Batch) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
-        query_embedding, candidate_embedding = self.two_tower(batch.sparse_features)
+        uses_dense = getattr(self.two_tower, "dense_index", None) is not None
+        query_embedding, candidate_embedding = self.two_tower(batch if uses_dense else batch.sparse_features)
         if self.loss_kind == "bce":
             loss, logits = dot_bce_loss(query_embedding, candidate_embedding, batch.labels)
         else:
