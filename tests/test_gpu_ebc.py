@@ -248,3 +248,33 @@ def test_peer_scatter_add_row_shards(cuda):
         N.call("tt_ebc_forward_peer", byref(plan), N.ptr(kjt.values()), N.ptr(kjt.offsets().to(torch.int32).contiguous()), byref(pb), N.stream_ptr(cuda))
     got = torch.cat(bufs).cpu()
     torch.testing.assert_close(got, want, rtol=RTOL, atol=ATOL)
+
+
+def test_full_size_gather_and_update_checksum(cuda):
+    """BASELINE configs[1] size: one 10M x 64 table, 65536 one-id bags.  Forward must equal a plain row gather
+    (bit-exact); the fused SGD update with an all-ones gradient must lower the checksum of the table by exactly
+    lr * (#ids) * D, and touch nothing but the looked-up rows."""
+    import two_tower_recommender_model_b200 as tt
+    R, D, B, lr = 10_000_000, 64, 65536, 0.5
+    ebc = tt.EmbeddingBagCollection(tables=[tt.EmbeddingBagConfig(name="t", embedding_dim=D, num_embeddings=R, feature_names=["f"])], device=cuda)
+    apply_optimizer_in_backward(torch.optim.SGD, ebc.parameters(), {"lr": lr})
+    w = ebc.embedding_bags["t"].weight
+    g = torch.Generator(device=cuda).manual_seed(9)
+    ids = torch.randint(1, R, (1, B), device=cuda, generator=g)
+    ids[0, :1000] = ids[0, 1000:2000]                                  # duplicates: their gradients must add up
+    kjt = tt.KeyedJaggedTensor.from_id_columns(["f"], ids, torch.tensor([R]))
+    before = w.detach().double().sum()
+    rows_before = w.detach()[ids[0]].clone()
+    out = ebc(kjt).values()
+    assert torch.equal(out, rows_before)
+    out.backward(torch.ones_like(out))
+    after = w.detach().double().sum()
+    assert abs(float(before - after) - lr * B * D) < 1e-6 * lr * B * D
+    uniq, counts = torch.unique(ids[0], return_counts=True)
+    torch.testing.assert_close(w.detach()[uniq], rows_before_unique(rows_before, ids[0], uniq) - lr * counts.unsqueeze(1).float(), rtol=0, atol=1e-6)
+
+
+def rows_before_unique(rows_before, ids, uniq):
+    first = torch.full((int(ids.max()) + 1,), -1, dtype=torch.long, device=ids.device)
+    first[ids] = torch.arange(ids.numel(), device=ids.device)
+    return rows_before[first[uniq]]

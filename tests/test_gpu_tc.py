@@ -226,3 +226,27 @@ def test_fused_towers_match_per_layer_path(cuda, B, i, h, o):
     torch.testing.assert_close(dpa, dpb, rtol=2e-2, atol=2e-2 * float(dpb.abs().max()))
     for k, (a, b) in enumerate(zip(ga, gb)):
         torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-2 * float(b.abs().max()), msg=lambda m: f"param {k}: {m}")
+
+
+def test_in_batch_softmax_full_size_closed_form(cuda):
+    """BASELINE configs[1] size (B = 65536, d = 64), where an O(B^2) reference is out of reach: with every candidate
+    equal to one vector c0 the logits of a row are constant, so P = 1/B exactly and everything has a closed form:
+        loss = log B,   dq = 0,   dc_j = (mean_i q_i - q_j) / (B T).
+    Exercises forward + the one-pass backward (P.c, P^T.q, TMA reduce-add over 256 row blocks) at full size."""
+    import math
+    from two_tower_recommender_model_b200.functional import in_batch_softmax_loss
+    B, d, T = 65536, 64, 0.5
+    g = torch.Generator().manual_seed(1)
+    q = (torch.rand(B, d, generator=g) * 0.25).bfloat16().float()        # exactly representable operands
+    c0 = (torch.rand(d, generator=g) * 0.25).bfloat16().float()
+    c = c0.repeat(B, 1)
+    qd, cd = q.to(cuda).requires_grad_(True), c.to(cuda).requires_grad_(True)
+    loss, diag = in_batch_softmax_loss(qd, cd, T, precision="bf16")
+    loss.backward()
+    assert abs(float(loss) - math.log(B)) < 1e-4 * math.log(B)
+    torch.testing.assert_close(diag.cpu().double(), (q.double() @ c0.double()) / T, rtol=1e-5, atol=1e-6)
+    scale = 1.0 / (B * T)
+    # P is rounded to bf16 before the gradient products (1/65536 is exact), so the only error is fp32 accumulation
+    assert float(qd.grad.abs().max()) <= 2e-3 * scale * float(c0.abs().max())
+    want_dc = (q.double().mean(0, keepdim=True) - q.double()) * scale
+    torch.testing.assert_close(cd.grad.cpu().double(), want_dc, rtol=1e-3, atol=2e-3 * scale * float(q.abs().max()))
