@@ -75,6 +75,7 @@ struct TowerFwdArgs {
 };
 struct TowerFwdParams {
   CUtensorMap w1[kMaxTowers], w2[kMaxTowers];
+  CUtensorMap xb[kMaxTowers], hb[kMaxTowers], yb[kMaxTowers], y[kMaxTowers];   // outputs leave through TMA stores
   TowerFwdArgs a[kMaxTowers];
   int B, in_dim, hidden, out_dim, tiles;
 };
@@ -106,6 +107,7 @@ towers_fwd_fused_kernel(const __grid_constant__ TowerFwdParams p) {
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.w1[tw]);
     prefetch_tmap(&p.w2[tw]);
+    prefetch_tmap(&p.xb[tw]); prefetch_tmap(&p.hb[tw]); prefetch_tmap(&p.yb[tw]); prefetch_tmap(&p.y[tw]);
     mbar_init(w_full, 1);
     mbar_init(x_ready, 128);
     mbar_init(h_full, 1);
@@ -148,35 +150,49 @@ towers_fwd_fused_kernel(const __grid_constant__ TowerFwdParams p) {
       }
     }
   } else {
+    // All global traffic of the workers is coalesced: x is read a row per warp instruction (lane = column pair), and
+    // the outputs leave as TMA stores of tiles that sit in shared memory anyway -- the bf16 operand tiles of the two
+    // GEMMs ARE xb and hb; y / yb are staged over them once the GEMMs are done.  (Thread-per-row global accesses cost
+    // 32 L1 wavefronts per request: the first version of this kernel ran at 18 % of DRAM bandwidth because of it.)
     const int q = warp & 3;
     const int r = q * 32 + lane, r7 = r & 7;
+    const int wq = warp - 2;                          // row block of the coalesced x load
+    const bool leader = threadIdx.x == 64;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t xrow = smem_u32(sX) + r * 128, hrow = smem_u32(sH) + r * 128;
+    const uint32_t aX = smem_u32(sX), aH = smem_u32(sH);
+    const uint32_t xrow = aX + r * 128, hrow = aH + r * 128;
     sB1[r] = (r < p.hidden && a.b1 != nullptr) ? a.b1[r] : 0.f;
     if (r < 64) sB2[r] = (r < p.out_dim && a.b2 != nullptr) ? a.b2[r] : 0.f;
     worker_bar_sync();
     for (int it = 0; it < n_it; ++it) {
-      const int64_t row = (int64_t)(blockIdx.x + it * gridDim.x) * 128 + r;
-      const bool valid = row < p.B;
-      // ---- x (fp32) -> bf16: shared memory (A of GEMM 1) + the copy the backward reads
-      {
-        const float* xr = a.x + row * a.ldx;
-        __nv_bfloat16* xo = a.xb + row * 64;
+      const int row0 = (blockIdx.x + it * gridDim.x) * 128;
+      // ---- x (fp32) -> bf16 tile in shared memory = A of GEMM 1 = the xb output
+      if (leader) bulk_wait_group_read0();            // the y / yb stores of the previous tile have read sH / sX
+      worker_bar_sync();
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          float4 u = make_float4(0.f, 0.f, 0.f, 0.f), w = u;
-          if (valid && m * 8 < p.in_dim) {
-            u = __ldg(reinterpret_cast<const float4*>(xr + m * 8));
-            w = __ldg(reinterpret_cast<const float4*>(xr + m * 8 + 4));
-          }
-          const uint4 pk = make_uint4(pack_bf16(u.x, u.y), pack_bf16(u.z, u.w), pack_bf16(w.x, w.y), pack_bf16(w.z, w.w));
-          st_shared_v4(xrow + ((m ^ r7) << 4), pk.x, pk.y, pk.z, pk.w);
-          if (valid) *reinterpret_cast<uint4*>(xo + m * 8) = pk;
+      for (int rr = 0; rr < 32; rr += 8) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int64_t row = (int64_t)row0 + wq * 32 + rr + u;
+          v[u] = make_float2(0.f, 0.f);
+          if (row < p.B && 2 * lane < p.in_dim) v[u] = __ldg(reinterpret_cast<const float2*>(a.x + row * a.ldx + 2 * lane));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int rl = wq * 32 + rr + u;
+          const uint32_t addr = aX + rl * 128 + ((((lane >> 2) ^ (rl & 7))) << 4) + (lane & 3) * 4;
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16(v[u].x, v[u].y)) : "memory");
         }
       }
       fence_proxy_async_smem();
       mbar_arrive(x_ready);
-      // ---- h = relu(acc1 + b1) -> bf16: shared memory (A of GEMM 2) + saved copy
+      worker_bar_sync();
+      if (leader) {
+        tma_store_2d(&p.xb[tw], aX, 0, row0);
+        bulk_commit_group();
+      }
+      // ---- h = relu(acc1 + b1) -> bf16 tile = A of GEMM 2 = the hb output
       mbar_wait(h_full, it & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -195,18 +211,21 @@ towers_fwd_fused_kernel(const __grid_constant__ TowerFwdParams p) {
 #pragma unroll
         for (int m = 0; m < 4; ++m)
           st_shared_v4(prow + ((((c & 1) * 4 + m) ^ r7) << 4), pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
-        if (valid) {
-          uint4* ho = reinterpret_cast<uint4*>(a.hb + row * 128 + 32 * c);
-#pragma unroll
-          for (int m = 0; m < 4; ++m) ho[m] = make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
-        }
       }
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(h_ready);
-      // ---- y = relu(acc2 + b2): fp32 output + bf16 copy (mask of the backward, operand of the loss)
+      worker_bar_sync();
+      if (leader) {
+        tma_store_2d(&p.hb[tw], aH, 0, row0);
+        if (p.hidden > 64) tma_store_2d(&p.hb[tw], aH + kPanel, 64, row0);
+        bulk_commit_group();
+      }
+      // ---- y = relu(acc2 + b2): staged over the (now idle) operand tiles, fp32 in the h panels, bf16 in the x tile
       mbar_wait(y_full, it & 1);
       tc_fence_after();
+      if (leader) bulk_wait_group_read0();            // the xb / hb stores have read the tiles
+      worker_bar_sync();
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
@@ -221,20 +240,26 @@ towers_fwd_fused_kernel(const __grid_constant__ TowerFwdParams p) {
           f[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + b.z, 0.f);
           f[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + b.w, 0.f);
         }
-        if (valid) {
-          float* yo = a.y + row * a.ldy + 32 * c;
-          uint4* yb = reinterpret_cast<uint4*>(a.yb + row * 64 + 32 * c);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (32 * c + j < p.out_dim) *reinterpret_cast<float4*>(yo + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        for (int m = 0; m < 8; ++m)      // fp32 box c: [128 rows x 32 columns], 128-byte swizzle
+          st_shared_v4(hrow + c * kPanel + ((m ^ r7) << 4), __float_as_uint(f[4 * m]), __float_as_uint(f[4 * m + 1]),
+                       __float_as_uint(f[4 * m + 2]), __float_as_uint(f[4 * m + 3]));
 #pragma unroll
-          for (int m = 0; m < 4; ++m)
-            yb[m] = make_uint4(pack_bf16(f[8 * m], f[8 * m + 1]), pack_bf16(f[8 * m + 2], f[8 * m + 3]),
-                               pack_bf16(f[8 * m + 4], f[8 * m + 5]), pack_bf16(f[8 * m + 6], f[8 * m + 7]));
-        }
+        for (int m = 0; m < 4; ++m)      // bf16 tile: columns 32c .. 32c+31 are 16-byte slots 4c .. 4c+3
+          st_shared_v4(xrow + (((4 * c + m) ^ r7) << 4), pack_bf16(f[8 * m], f[8 * m + 1]), pack_bf16(f[8 * m + 2], f[8 * m + 3]),
+                       pack_bf16(f[8 * m + 4], f[8 * m + 5]), pack_bf16(f[8 * m + 6], f[8 * m + 7]));
       }
       tc_fence_before();
+      fence_proxy_async_smem();
+      worker_bar_sync();
+      if (leader) {
+        tma_store_2d(&p.y[tw], aH, 0, row0);
+        if (p.out_dim > 32) tma_store_2d(&p.y[tw], aH + kPanel, 32, row0);
+        tma_store_2d(&p.yb[tw], aX, 0, row0);
+        bulk_commit_group();
+      }
     }
+    if (leader) bulk_wait_group0();
   }
   __syncthreads();
   if (warp == 1) {
@@ -250,7 +275,7 @@ struct TowerBwdArgs {
   float* ws;                       // partials: [ctas][128][64] dW1, [ctas][128][64] dW2^T, [ctas][4][192] bias sums
 };
 struct TowerBwdParams {
-  CUtensorMap w1[kMaxTowers], w2[kMaxTowers], yb[kMaxTowers], hb[kMaxTowers], xb[kMaxTowers];
+  CUtensorMap w1[kMaxTowers], w2[kMaxTowers], yb[kMaxTowers], hb[kMaxTowers], xb[kMaxTowers], dx[kMaxTowers];
   TowerBwdArgs a[kMaxTowers];
   int B, in_dim, hidden, out_dim, tiles;
 };
@@ -269,12 +294,12 @@ towers_bwd_fused_kernel(const __grid_constant__ TowerBwdParams p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(sX + kPanel);
   uint64_t* w_full = bars;
   uint64_t* in_full = bars + 1;    // TMA -> workers
-  uint64_t* in_empty = bars + 2;   // MMA -> TMA: every product of the tile has read its operands
+  uint64_t* in_empty = bars + 2;   // workers' leader -> TMA: products done AND the dx store has read its staging (the h tile)
   uint64_t* z2_ready = bars + 3;   // workers -> MMA
   uint64_t* dh_full = bars + 4;    // MMA -> workers
   uint64_t* w2_done = bars + 5;    // MMA -> workers: h may be overwritten by dz1
   uint64_t* z1_ready = bars + 6;
-  uint64_t* dx_full = bars + 7;
+  uint64_t* dx_full = bars + 7;    // MMA -> workers: ALL products of the tile are done (dx complete, operand tiles idle)
   uint64_t* all_done = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   constexpr uint32_t kWork = 0, kAccW1 = 128, kAccW2 = 192;   // TMEM columns
@@ -286,6 +311,7 @@ towers_bwd_fused_kernel(const __grid_constant__ TowerBwdParams p) {
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.w1[tw]); prefetch_tmap(&p.w2[tw]); prefetch_tmap(&p.yb[tw]); prefetch_tmap(&p.hb[tw]); prefetch_tmap(&p.xb[tw]);
+    if (p.a[tw].dx != nullptr) prefetch_tmap(&p.dx[tw]);
     mbar_init(w_full, 1);
     mbar_init(in_full, 1);
     mbar_init(in_empty, 1);
@@ -344,12 +370,11 @@ towers_bwd_fused_kernel(const __grid_constant__ TowerBwdParams p) {
         for (int kk = 0; kk < 8; ++kk)    // dx[r, i] = sum_h dz1[r, h] W1[h, i]
           mma_ss(tmem_base + kWork, smem_desc_k_sw128(aH + (kk >> 2) * kPanel) + 2 * (kk & 3),
                  smem_desc_mn_sw128(aW1 + kk * 2048, 1024, 1024), idescDx, kk != 0);
-        tc_commit(dx_full);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)    // dW1[h, i] += sum_r dz1[r, h] x[r, i]
           mma_ss(tmem_base + kAccW1, smem_desc_mn_sw128(aH + kk * 2048, kPanel, 1024), smem_desc_mn_sw128(aX + kk * 2048, 1024, 1024),
                  idescDw, (it | kk) != 0);
-        tc_commit(in_empty);
+        tc_commit(dx_full);
       }
       tc_commit(all_done);
     }
@@ -358,39 +383,35 @@ towers_bwd_fused_kernel(const __grid_constant__ TowerBwdParams p) {
     const int r = q * 32 + lane, r7 = r & 7;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t zrow = smem_u32(sZ2) + r * 128, hrow = smem_u32(sH) + r * 128;
-    float db[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // lane = column: chunks 0-1 of dz2, 0-3 of dz1
+    float db[4] = {0.f, 0.f, 0.f, 0.f};             // column sums of dz1: lane = column of chunk c
+    float db2_lo = 0.f, db2_hi = 0.f;                // column sums of dz2: lane = column pair (2 lane, 2 lane + 1)
+    const int wq = warp - 2;                          // row block of the coalesced dy pass
+    const bool leader = threadIdx.x == 64;
+    const uint32_t aZ2 = smem_u32(sZ2), aHs = smem_u32(sH);
     for (int it = 0; it < n_it; ++it) {
-      const int64_t row = (int64_t)(blockIdx.x + it * gridDim.x) * 128 + r;
-      const bool valid = row < p.B;
+      const int row0 = (blockIdx.x + it * gridDim.x) * 128;
       mbar_wait(in_full, it & 1);
-      // ---- dz2 = dy * (y > 0) -> bf16, in place over the y tile
-      {
-        const float* dyr = a.dy + row * a.lddy;
+      // ---- dz2 = dy * (y > 0) -> bf16, in place over the y tile.  Coalesced: one dy row per warp instruction
+      // (lane = column pair), the matching bf16 pair of y sits at a bank-conflict-free word of the swizzled tile.
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float f[32];
+      for (int rr = 0; rr < 32; rr += 8) {
+        float2 v[8];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const uint32_t addr = zrow + (((c * 4 + m) ^ r7) << 4);
-            const uint4 yv = ld_shared_v4(addr);
-            float4 u = make_float4(0.f, 0.f, 0.f, 0.f), w = u;
-            if (valid && c * 32 + m * 8 < p.out_dim) {
-              u = __ldg(reinterpret_cast<const float4*>(dyr + c * 32 + m * 8));
-              w = __ldg(reinterpret_cast<const float4*>(dyr + c * 32 + m * 8 + 4));
-            }
-            const uint32_t p0 = pack_bf16(bf16_pos_lo(yv.x) ? u.x : 0.f, bf16_pos_hi(yv.x) ? u.y : 0.f);
-            const uint32_t p1 = pack_bf16(bf16_pos_lo(yv.y) ? u.z : 0.f, bf16_pos_hi(yv.y) ? u.w : 0.f);
-            const uint32_t p2 = pack_bf16(bf16_pos_lo(yv.z) ? w.x : 0.f, bf16_pos_hi(yv.z) ? w.y : 0.f);
-            const uint32_t p3 = pack_bf16(bf16_pos_lo(yv.w) ? w.z : 0.f, bf16_pos_hi(yv.w) ? w.w : 0.f);
-            st_shared_v4(addr, p0, p1, p2, p3);
-            const uint32_t pk[4] = {p0, p1, p2, p3};
+        for (int u = 0; u < 8; ++u) {
+          const int64_t row = (int64_t)row0 + wq * 32 + rr + u;
+          v[u] = make_float2(0.f, 0.f);
+          if (row < p.B && 2 * lane < p.out_dim) v[u] = __ldg(reinterpret_cast<const float2*>(a.dy + row * a.lddy + 2 * lane));
+        }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {           // the bias gradient sums what the tensor core sees (bf16)
-              f[m * 8 + 2 * e] = __uint_as_float(pk[e] << 16);
-              f[m * 8 + 2 * e + 1] = __uint_as_float(pk[e] & 0xffff0000u);
-            }
-          }
-          db[c] += warp_column_sums(f, lane);
+        for (int u = 0; u < 8; ++u) {
+          const int rl = wq * 32 + rr + u;
+          const uint32_t addr = aZ2 + rl * 128 + (((lane >> 2) ^ (rl & 7)) << 4) + (lane & 3) * 4;
+          uint32_t yv;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(yv) : "r"(addr));
+          const uint32_t pk = pack_bf16(bf16_pos_lo(yv) ? v[u].x : 0.f, bf16_pos_hi(yv) ? v[u].y : 0.f);
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pk) : "memory");
+          db2_lo += __uint_as_float(pk << 16);          // the bias gradient sums what the tensor core sees (bf16)
+          db2_hi += __uint_as_float(pk & 0xffff0000u);
         }
       }
       fence_proxy_async_smem();
@@ -422,30 +443,41 @@ towers_bwd_fused_kernel(const __grid_constant__ TowerBwdParams p) {
           }
           st_shared_v4(addr, pk[0], pk[1], pk[2], pk[3]);
         }
-        db[2 + c] += warp_column_sums(f, lane);
+        db[c] += warp_column_sums(f, lane);
       }
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(z1_ready);
-      // ---- dx out
+      // ---- dx out: staged as two fp32 boxes over the (now idle) h tile, one TMA store; the producer may refill the
+      // operand tiles only after that store has read its staging
       mbar_wait(dx_full, it & 1);
       tc_fence_after();
+      if (a.dx != nullptr) {
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(trow + kWork + 32 * c, v);
-        tmem_ld_wait();
-        if (valid && a.dx != nullptr) {
-          float* o = a.dx + row * a.lddx + 32 * c;
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(trow + kWork + 32 * c, v);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (32 * c + j < p.in_dim)
-              *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          for (int m = 0; m < 8; ++m)
+            st_shared_v4(hrow + c * kPanel + ((m ^ r7) << 4), v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]);
         }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        worker_bar_sync();
+        if (leader) {
+          tma_store_2d(&p.dx[tw], aHs, 0, row0);
+          if (p.in_dim > 32) tma_store_2d(&p.dx[tw], aHs + kPanel, 32, row0);
+          bulk_commit_group();
+          bulk_wait_group_read0();
+          mbar_arrive(in_empty);
+        }
+      } else {
+        worker_bar_sync();
+        if (leader) mbar_arrive(in_empty);
       }
-      tc_fence_before();
     }
+    if (leader) bulk_wait_group0();
     // ---- this CTA's weight / bias gradient partials
     mbar_wait(all_done, 0);
     tc_fence_after();
@@ -462,8 +494,10 @@ towers_bwd_fused_kernel(const __grid_constant__ TowerBwdParams p) {
         *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
     }
     float* wsb = a.ws + 2 * (int64_t)gridDim.x * kWsW + (int64_t)blockIdx.x * kWsB + q * 192;
+    wsb[2 * lane] = db2_lo;
+    wsb[2 * lane + 1] = db2_hi;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) wsb[32 * c + lane] = db[c];
+    for (int c = 0; c < 4; ++c) wsb[64 + 32 * c + lane] = db[c];
     tc_fence_before();
   }
   __syncthreads();
@@ -557,6 +591,10 @@ int tt_towers_forward_fused(const tt_tower_forward* towers, int32_t n_towers, in
       return fail(TT_ERR_INVALID, "towers_forward: x / y must be 16-byte aligned with pitches that are multiples of 4");
     if ((rc = make_tmap_bf16_2d(&p.w1[t], s.w1_bf16, hidden, in_dim, s.ldw1, 128))) return rc;
     if ((rc = make_tmap_bf16_2d(&p.w2[t], s.w2_bf16, out_dim, hidden, s.ldw2, 64))) return rc;
+    if ((rc = make_tmap_bf16_2d(&p.xb[t], s.xb, B, 64, 64, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d(&p.hb[t], s.hb, B, 128, 128, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d(&p.yb[t], s.yb, B, 64, 64, 128))) return rc;
+    if ((rc = make_tmap_f32_2d(&p.y[t], s.y, B, out_dim, s.ldy, 128))) return rc;
     p.a[t] = TowerFwdArgs{s.x, s.ldx, s.b1, s.b2, static_cast<__nv_bfloat16*>(s.xb), static_cast<__nv_bfloat16*>(s.hb),
                           static_cast<__nv_bfloat16*>(s.yb), s.y, s.ldy};
   }
@@ -596,6 +634,7 @@ int tt_towers_backward_fused(const tt_tower_backward* towers, int32_t n_towers, 
     if ((rc = make_tmap_bf16_2d(&p.yb[t], s.yb, B, 64, 64, 128))) return rc;
     if ((rc = make_tmap_bf16_2d(&p.hb[t], s.hb, B, 128, 128, 128))) return rc;
     if ((rc = make_tmap_bf16_2d(&p.xb[t], s.xb, B, 64, 64, 128))) return rc;
+    if (s.dx && (rc = make_tmap_f32_2d(&p.dx[t], s.dx, B, in_dim, s.lddx, 128))) return rc;
     float* wst = reinterpret_cast<float*>(static_cast<char*>(ws) + t * per_tower);
     p.a[t] = TowerBwdArgs{s.dy, s.lddy, s.dx, s.lddx, wst};
     g.t[t] = TowerGradOut{wst, s.dw1, s.dw2, s.db1, s.db2};
