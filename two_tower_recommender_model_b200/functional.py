@@ -203,7 +203,7 @@ class InBatchSoftmaxLossTC(torch.autograd.Function):
     core from TMEM.  Nothing of size [B, B] is ever written to HBM."""
 
     @staticmethod
-    def forward(ctx, q, c, temperature: float):
+    def forward(ctx, q, c, temperature: float, q_bf16=None, c_bf16=None):
         q = _f32c(q, "query_embedding")
         c = _f32c(c, "candidate_embedding")
         B, d = q.shape
@@ -214,7 +214,9 @@ class InBatchSoftmaxLossTC(torch.autograd.Function):
             qb, qbt = cast_bf16(q, both=True)
             cb, cbt = cast_bf16(c, both=True)
         else:
-            qb, cb = cast_bf16(q), cast_bf16(c)
+            # the fused towers already produced the bf16 copies (same rounding): no cast kernels
+            qb = q_bf16 if q_bf16 is not None else cast_bf16(q)
+            cb = c_bf16 if c_bf16 is not None else cast_bf16(c)
             qbt = cbt = None
         lse = torch.empty(B, dtype=torch.float32, device=dev)
         diag = torch.empty(B, dtype=torch.float32, device=dev)
@@ -237,13 +239,18 @@ class InBatchSoftmaxLossTC(torch.autograd.Function):
                N.ptr(qbt), qbt.stride(0) if qbt is not None else 0, N.ptr(cbt), cbt.stride(0) if cbt is not None else 0,
                N.ptr(q), q.stride(0), N.ptr(c), c.stride(0),
                N.ptr(lse), B, d, ctx.inv_t, 1.0, 0, N.ptr(dq), d, N.ptr(dc), d, N.stream_ptr(q.device))
-        return dq * g_loss, dc * g_loss, None
+        return dq * g_loss, dc * g_loss, None, None, None
 
 
 def in_batch_softmax_loss(q: torch.Tensor, c: torch.Tensor, temperature: float = 1.0, precision: str = "fp32"):
     """``precision="fp32"``: CUDA-core path, exact fp32.  ``"bf16"``: tcgen05 tensor-core path."""
     if precision == "bf16":
-        return InBatchSoftmaxLossTC.apply(q, c, temperature)
+        def bf16_of(t):   # bf16 copy attached by FusedTowersTC ([B, 64], zero padded), valid for the tensor it came with
+            b = getattr(t, "_tt_bf16", None)
+            ok = (b is not None and b.dtype == torch.bfloat16 and b.shape[0] == t.shape[0] and b.shape[1] >= t.shape[1]
+                  and b.device == t.device and getattr(t, "_tt_bf16_version", None) == t._version)
+            return b if ok else None
+        return InBatchSoftmaxLossTC.apply(q, c, temperature, bf16_of(q), bf16_of(c))
     return InBatchSoftmaxLoss.apply(q, c, temperature)
 
 
@@ -425,10 +432,12 @@ class FusedTowersTC(torch.autograd.Function):
         ctx.saved = (xb, hb, yb, wbs)
         ctx.has_bias = [p is not None for p in params]
         ctx.save_for_backward(*[p for p in params if p is not None])
-        return tuple(ys)
+        ctx.mark_non_differentiable(yb)
+        return (*ys, yb)
 
     @staticmethod
     def backward(ctx, *dys):
+        dys = dys[:-1]                      # the last output is the (non-differentiable) bf16 copy
         xb, hb, yb, wbs = ctx.saved
         B, hidden, out_dim = ctx.shape
         T, in_dim = len(ctx.cols), ctx.in_dim

@@ -101,7 +101,11 @@ class TwoTower(nn.Module):
         plan = self._fused_plan(pooled_embeddings)
         if plan is not None:
             cols, in_dim, params = plan
-            return FusedTowersTC.apply(pooled_embeddings.values(), tuple(cols), in_dim, *params)
+            q, c, yb = FusedTowersTC.apply(pooled_embeddings.values(), tuple(cols), in_dim, *params)
+            # the towers' bf16 copies of their outputs ride along: the tensor-core loss takes them instead of casting again
+            q._tt_bf16, q._tt_bf16_version = yb[0], q._version
+            c._tt_bf16, c._tt_bf16_version = yb[1], c._version
+            return q, c
         query_embedding = self.query_proj(self._tower_input(pooled_embeddings, self._feature_names_query))
         candidate_embedding = self.candidate_proj(self._tower_input(pooled_embeddings, self._candidate_feature_names))
         return query_embedding, candidate_embedding
