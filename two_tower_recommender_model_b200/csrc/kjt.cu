@@ -60,18 +60,42 @@ __global__ void __launch_bounds__(1024) scan_single_block_kernel(const int32_t* 
                                                                   int32_t* total_out, int complete) {
   __shared__ int smem[33];
   int carry = 0;
-  for (int base = 0; base < n; base += 1024 * 4) {
-    int idx = base + threadIdx.x * 4;
-    int v[4];
+  // 16 consecutive elements per thread and pass (four 16-byte loads in flight): the radix sort's 256 x 64 block
+  // histograms are ONE pass, i.e. one round of loads, one block scan, one round of stores
+  constexpr int kItems = 16;
+  const bool vec = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  for (int base = 0; base < n; base += 1024 * kItems) {
+    const int idx = base + threadIdx.x * kItems;
+    int v[kItems];
+    if (vec && idx + kItems <= n) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = (idx + j < n) ? in[idx + j] : 0;
-    int tsum = v[0] + v[1] + v[2] + v[3];
+      for (int j = 0; j < kItems; j += 4) {
+        const int4 t = *reinterpret_cast<const int4*>(in + idx + j);
+        v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kItems; ++j) v[j] = (idx + j < n) ? in[idx + j] : 0;
+    }
+    int tsum = 0;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) tsum += v[j];
     int total;
     int ex = block_exclusive_scan(tsum, &total, smem) + carry;
+    if (vec && idx + kItems <= n) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (idx + j < n) out[idx + j] = ex;
-      ex += v[j];
+      for (int j = 0; j < kItems; j += 4) {
+        int4 t;
+        t.x = ex; t.y = ex + v[j]; t.z = t.y + v[j + 1]; t.w = t.z + v[j + 2];
+        ex = t.w + v[j + 3];
+        *reinterpret_cast<int4*>(out + idx + j) = t;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kItems; ++j) {
+        if (idx + j < n) out[idx + j] = ex;
+        ex += v[j];
+      }
     }
     carry += total;
   }

@@ -526,11 +526,14 @@ towers_grad_reduce_kernel(const __grid_constant__ TowerGradParams p) {
       const float* base;
       if (e < n1) base = t.ws + (int64_t)(e / p.in_dim) * 64 + (e % p.in_dim);
       else { const int o = (e - n1) / p.hidden, h = (e - n1) % p.hidden; base = t.ws + (int64_t)p.ctas * kWsW + (int64_t)h * 64 + o; }
-      float s0 = 0.f, s1 = 0.f;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // four loads in flight; fixed order, so the result is reproducible
       int c = z;
-      for (; c + 4 < p.ctas; c += 8) { s0 += base[(int64_t)c * kWsW]; s1 += base[(int64_t)(c + 4) * kWsW]; }
-      if (c < p.ctas) s0 += base[(int64_t)c * kWsW];
-      s = s0 + s1;
+      for (; c + 12 < p.ctas; c += 16) {
+        s0 += base[(int64_t)c * kWsW]; s1 += base[(int64_t)(c + 4) * kWsW];
+        s2 += base[(int64_t)(c + 8) * kWsW]; s3 += base[(int64_t)(c + 12) * kWsW];
+      }
+      for (; c < p.ctas; c += 4) s0 += base[(int64_t)c * kWsW];
+      s = (s0 + s1) + (s2 + s3);
     } else {
       const int col = e < n1 + n2 + n3 ? 64 + (e - n1 - n2) : (e - n1 - n2 - n3);
       const float* base = t.ws + 2 * (int64_t)p.ctas * kWsW + col;
