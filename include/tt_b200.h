@@ -329,7 +329,8 @@ int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void
                                      const float* q_f32, int64_t ldqf, const float* c_f32, int64_t ldcf,
                                      const float* lse, int64_t B, int64_t d, float inv_temperature,
                                      float grad_scale, int32_t relu_gate, float* dq, int64_t lddq,
-                                     float* dc, int64_t lddc, void* stream);
+                                     float* dc, int64_t lddc, const float* grad_scale_dev /* device scalar multiplied into both gradients (the incoming dLoss), or null; one-pass path only */,
+                                     void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Dense optimizer: torch.optim.Adam defaults (03_model_training.py:826-829),

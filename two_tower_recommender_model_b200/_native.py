@@ -112,7 +112,7 @@ SIGNATURES = {
     "tt_inbatch_softmax_bf16_workspace_bytes": (c_size_t, [c_int64]),
     "tt_inbatch_softmax_forward_bf16": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "tt_inbatch_softmax_backward_bf16": (c_int32, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64,
-                                                   _P, c_int64, c_int64, c_float, c_float, c_int32, _P, c_int64, _P, c_int64, _P]),
+                                                   _P, c_int64, c_int64, c_float, c_float, c_int32, _P, c_int64, _P, c_int64, _P, _P]),
     "tt_adam_flat":(c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, _P]),
     "tt_adam_flat_devstep": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, _P]),
     "tt_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),

@@ -874,7 +874,9 @@ tc_softmax_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __gri
 template <int VEC>
 __global__ void __launch_bounds__(256)
 softmax_bwd_finalize_kernel(float* __restrict__ out, int64_t ld_out, const float* __restrict__ other, int64_t ld_other,
-                            const float* __restrict__ mask, int64_t ld_mask, float out_scale, int B, int d) {
+                            const float* __restrict__ mask, int64_t ld_mask, float out_scale, const float* __restrict__ scale_dev,
+                            int B, int d) {
+  if (scale_dev != nullptr) out_scale *= *scale_dev;      // the incoming dLoss (a device scalar): no separate multiply kernel
   const int per_row = (d + VEC - 1) / VEC;
   const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (int64_t)B * per_row) return;
@@ -1012,15 +1014,15 @@ static int fused_chunks(int64_t B) {
 }
 
 static int finalize_grad(float* out, int64_t ld_out, const float* other, int64_t ld_other, const float* mask, int64_t ld_mask,
-                         float out_scale, int B, int d, cudaStream_t s) {
+                         float out_scale, const float* scale_dev, int B, int d, cudaStream_t s) {
   const bool vec = (d % 4) == 0 && (ld_out % 4) == 0 && (ld_other % 4) == 0 && (mask == nullptr || (ld_mask % 4) == 0) &&
                    ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(other) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
   if (vec) {
     const int64_t n = (int64_t)B * (d / 4);
-    softmax_bwd_finalize_kernel<4><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, ld_out, other, ld_other, mask, ld_mask, out_scale, B, d);
+    softmax_bwd_finalize_kernel<4><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, ld_out, other, ld_other, mask, ld_mask, out_scale, scale_dev, B, d);
   } else {
     const int64_t n = (int64_t)B * d;
-    softmax_bwd_finalize_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, ld_out, other, ld_other, mask, ld_mask, out_scale, B, d);
+    softmax_bwd_finalize_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, ld_out, other, ld_other, mask, ld_mask, out_scale, scale_dev, B, d);
   }
   TT_CHECK_LAUNCH("softmax_bwd_finalize");
   return TT_OK;
@@ -1029,7 +1031,7 @@ static int finalize_grad(float* out, int64_t ld_out, const float* other, int64_t
 static int launch_bwd_fused(const void* q_bf16, int64_t ldq, const void* c_bf16, int64_t ldc, const float* q_f32, int64_t ldqf,
                             const float* c_f32, int64_t ldcf, const float* lse, int B, int d, float scale2, float out_scale,
                             const float* gate_q, const float* gate_c, float* dq, int64_t lddq, float* dc, int64_t lddc,
-                            cudaStream_t s) {
+                            const float* scale_dev, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(tc_softmax_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM);
@@ -1048,8 +1050,8 @@ static int launch_bwd_fused(const void* q_bf16, int64_t ldq, const void* c_bf16,
   dim3 grid((unsigned)((B + 255) / 256), (unsigned)fused_chunks(B));
   tc_softmax_bwd_fused_kernel<<<grid, FusedCfg::THREADS, FusedCfg::SMEM, s>>>(tq, tcm, tdq, tdc, B, d, scale2, lse);
   TT_CHECK_LAUNCH("tc_softmax_bwd_fused");
-  if ((rc = finalize_grad(dq, lddq, c_f32, ldcf, gate_q, ldqf, out_scale, B, d, s))) return rc;
-  return finalize_grad(dc, lddc, q_f32, ldqf, gate_c, ldcf, out_scale, B, d, s);
+  if ((rc = finalize_grad(dq, lddq, c_f32, ldcf, gate_q, ldqf, out_scale, scale_dev, B, d, s))) return rc;
+  return finalize_grad(dc, lddc, q_f32, ldqf, gate_c, ldcf, out_scale, scale_dev, B, d, s);
 }
 
 }  // namespace tc
@@ -1117,7 +1119,8 @@ int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void
                                      const void* qt_bf16, int64_t ldqt, const void* ct_bf16, int64_t ldct,
                                      const float* q_f32, int64_t ldqf, const float* c_f32, int64_t ldcf,
                                      const float* lse, int64_t B, int64_t d, float inv_t, float grad_scale,
-                                     int32_t relu_gate, float* dq, int64_t lddq, float* dc, int64_t lddc, void* stream) {
+                                     int32_t relu_gate, float* dq, int64_t lddq, float* dc, int64_t lddc,
+                                     const float* grad_scale_dev, void* stream) {
   TT_CHECK_ARG(B > 0 && d > 0 && q_bf16 && c_bf16 && q_f32 && c_f32 && lse && dq && dc,
                "inbatch_softmax_backward_bf16: bad args");
   if (d > 256) return fail(TT_ERR_UNSUPPORTED, "inbatch_softmax_backward_bf16: d > 256");
@@ -1132,7 +1135,8 @@ int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void
   if (KB == 1 && g_softmax_bwd_mode == 0 && (lddq % 4) == 0 && (lddc % 4) == 0 &&
       ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dc)) & 15) == 0)
     return launch_bwd_fused(q_bf16, ldq, c_bf16, ldc, q_f32, ldqf, c_f32, ldcf, lse, (int)B, (int)d, scale2, out_scale,
-                            relu_gate ? q_f32 : nullptr, relu_gate ? c_f32 : nullptr, dq, lddq, dc, lddc, s);
+                            relu_gate ? q_f32 : nullptr, relu_gate ? c_f32 : nullptr, dq, lddq, dc, lddc, grad_scale_dev, s);
+  if (grad_scale_dev != nullptr) return fail(TT_ERR_UNSUPPORTED, "inbatch_softmax_backward_bf16: grad_scale_dev needs the one-pass path (d <= 64)");
   TT_CHECK_ARG(qt_bf16 && ct_bf16, "inbatch_softmax_backward_bf16: the two-pass kernels need the transposed copies");
   CUtensorMap tq128, tc128, tqn, tcn, tqt, tct;
   int rc;

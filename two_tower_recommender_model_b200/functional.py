@@ -210,7 +210,7 @@ class InBatchSoftmaxLossTC(torch.autograd.Function):
         dev = q.device
         # d <= 64: the fused one-pass backward reads q / c row-major only (MN-major tcgen05 operands);
         # wider embeddings use the two-pass kernels, which want the transposed copies as well
-        if d > 64 or _deterministic_softmax_backward:
+        if d > 64 or d % 4 != 0 or _deterministic_softmax_backward:
             qb, qbt = cast_bf16(q, both=True)
             cb, cbt = cast_bf16(c, both=True)
         else:
@@ -235,10 +235,15 @@ class InBatchSoftmaxLossTC(torch.autograd.Function):
         B, d = q.shape
         dq = torch.empty_like(q)
         dc = torch.empty_like(c)
+        # one-pass path (d <= 64): the incoming dLoss is multiplied in by the finalize kernel (device scalar, no sync)
+        fused = qbt is None and g_loss.numel() == 1 and g_loss.dtype == torch.float32 and g_loss.is_cuda
+        gs = g_loss.contiguous() if fused else None
         N.call("tt_inbatch_softmax_backward_bf16", N.ptr(qb), qb.stride(0), N.ptr(cb), cb.stride(0),
                N.ptr(qbt), qbt.stride(0) if qbt is not None else 0, N.ptr(cbt), cbt.stride(0) if cbt is not None else 0,
                N.ptr(q), q.stride(0), N.ptr(c), c.stride(0),
-               N.ptr(lse), B, d, ctx.inv_t, 1.0, 0, N.ptr(dq), d, N.ptr(dc), d, N.stream_ptr(q.device))
+               N.ptr(lse), B, d, ctx.inv_t, 1.0, 0, N.ptr(dq), d, N.ptr(dc), d, N.ptr(gs), N.stream_ptr(q.device))
+        if fused:
+            return dq, dc, None, None, None
         return dq * g_loss, dc * g_loss, None, None, None
 
 
