@@ -152,7 +152,7 @@ struct FwdCfg {
   static_assert(NACC % NG == 0 || NG % NACC == 0, "stage ownership");
   static constexpr int Q_BYTES = KB * 128 * 128;       // KB sub-tiles of [128 x 64] bf16
   static constexpr int C_BYTES = KB * NT * 128;        // KB sub-tiles of [NT x 64] bf16
-  static constexpr int SMEM = Q_BYTES + STAGES * C_BYTES + 1024 + 256 + 4096;  // + merge scratch [NG-1][128][2]
+  static constexpr int SMEM = Q_BYTES + STAGES * C_BYTES + 1024 + 256 + 4096 + 256;  // + merge scratch [NG-1][128][2] + path flags
 };
 
 // running (max, sum) update over one 32-column chunk; TAIL masks columns >= B
@@ -190,11 +190,38 @@ __device__ __forceinline__ void lse_chunk(const uint32_t (&v)[32], int col0, int
   m = mn;
 }
 
+// The same with a shift fixed for the whole row (an upper bound of its logits): no maximum, no rescaling, no
+// dependency between chunks -- just sum += 2^(s*scale - shift).
+#ifndef TT_POLY_FWD_FIXED
+#define TT_POLY_FWD_FIXED 3
+#endif
+template <bool TAIL>
+__device__ __forceinline__ void lse_chunk_fixed(const uint32_t (&v)[32], int col0, int B, float scale2, float shift, float& l) {
+  const float2 sc = make_float2(scale2, scale2), sh = make_float2(-shift, -shift);
+  float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    float2 e[4];
+    ex2_8<TT_POLY_FWD_FIXED, 4>(&v[j], sc, sh, e);
+    if (TAIL) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        e[k].x = (col0 + j + 2 * k < B) ? e[k].x : 0.f;
+        e[k].y = (col0 + j + 2 * k + 1 < B) ? e[k].y : 0.f;
+      }
+    }
+    acc0 = __fadd2_rn(acc0, __fadd2_rn(e[0], e[1]));
+    acc1 = __fadd2_rn(acc1, __fadd2_rn(e[2], e[3]));
+  }
+  l += (acc0.x + acc0.y) + (acc1.x + acc1.y);
+}
+
 template <int KB>
 __global__ void __launch_bounds__(FwdCfg<KB>::THREADS, 1)
 tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, int B,
                       float scale2, const float* __restrict__ diag, float* __restrict__ lse,
-                      float* __restrict__ partial_loss, float* __restrict__ ml_out) {
+                      float* __restrict__ partial_loss, float* __restrict__ ml_out,
+                      const float* __restrict__ qn2, const unsigned int* __restrict__ cmax2) {
   // gridDim.y > 1: the logit columns are split between gridDim.y CTAs per row block (so that the
   // grid is ~7 waves of 148 instead of 3.46); each writes its (max, sum) pair to ml_out and
   // lse_merge_kernel finishes the job.
@@ -278,6 +305,45 @@ tc_softmax_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       // g%2 of each.  A thread pulls its 64 columns into registers in one go and releases the TMEM stage at once,
       // so the MMA issuer refills it while the exponentials run (with four stages it stays two tiles ahead).
       const int h = g & 1;
+      // Fixed-shift path: valid when, for EVERY row of the CTA, bound - S_ii <= 60 (log2 units): the diagonal term alone
+      // then keeps the sum above 2^-60, far from underflow, and what the polynomial's clamp at 2^-125 adds is below
+      // 2^-49 of it.  Decided per CTA (the four groups see the same 128 rows, so they agree); otherwise the
+      // online-max path below.
+      bool fixed = false;
+      float shift = 0.f;
+      if (qn2 != nullptr) {
+        shift = row < B ? sqrtf(qn2[row] * __uint_as_float(*cmax2)) * fabsf(scale2) : 0.f;
+        const bool ok = row >= B || (shift - diag[row] * kLog2e <= 60.f && shift < 1e30f);
+        int* flags = reinterpret_cast<int*>(bars + 32) + 1024;       // [NG][4], past the merge scratch
+        const int all_ok = __all_sync(0xffffffffu, ok);
+        if (lane == 0) flags[g * 4 + q] = all_ok;
+        group_bar_sync(g);
+        fixed = (flags[g * 4] & flags[g * 4 + 1] & flags[g * 4 + 2] & flags[g * 4 + 3]) != 0;
+      }
+      if (fixed) {
+        m = shift;
+        for (int t = g >> 1; t < T; t += 2) {
+          const int as = t % Cfg::NACC;
+          const uint32_t tcol = trow + as * NT + h * 64;
+          mbar_wait(&acc_full[as], (t / Cfg::NACC) & 1);
+          tc_fence_after();
+          const int n0 = (t0 + t) * NT + h * 64;
+          uint32_t va[32], vb[32];
+          tmem_ld32(tcol, va);
+          tmem_ld32(tcol + 32, vb);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&acc_empty[as]);
+          if (n0 + 64 <= B) {
+            lse_chunk_fixed<false>(va, n0, B, scale2, shift, l);
+            lse_chunk_fixed<false>(vb, n0 + 32, B, scale2, shift, l);
+          } else {
+            lse_chunk_fixed<true>(va, n0, B, scale2, shift, l);
+            lse_chunk_fixed<true>(vb, n0 + 32, B, scale2, shift, l);
+          }
+        }
+        if (l == 0.f) m = -INFINITY;      // this thread saw no valid column (tail): neutral element of the merge
+      } else
       for (int t = g >> 1; t < T; t += 2) {
         const int as = t % Cfg::NACC;
         const uint32_t tcol = trow + as * NT + h * 64;
@@ -899,15 +965,28 @@ softmax_bwd_finalize_kernel(float* __restrict__ out, int64_t ld_out, const float
 
 // diag[b] = inv_t * sum_k bf16(q[b,k]) * bf16(c[b,k])   (what the tensor core computes for S_bb)
 __global__ void __launch_bounds__(256)
+// Also |q_b|^2 per row and max_b |c_b|^2 (atomicMax on the bit pattern of a non-negative float; zeroed by the caller):
+// by Cauchy-Schwarz |S_bj| <= |q_b| max|c|, a row-wise upper bound the forward uses as a FIXED softmax shift.
 rowdot_bf16_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ c, int64_t ldc,
-                   int B, int d, float inv_t, float* __restrict__ diag) {
+                   int B, int d, float inv_t, float* __restrict__ diag, float* __restrict__ qn2, unsigned int* __restrict__ cmax2) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
-  float s = 0.f;
-  for (int k = lane; k < d; k += 32) s = fmaf(__bfloat162float(q[(int64_t)b * ldq + k]), __bfloat162float(c[(int64_t)b * ldc + k]), s);
+  float s = 0.f, sq = 0.f, scn = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    const float qv = __bfloat162float(q[(int64_t)b * ldq + k]), cv = __bfloat162float(c[(int64_t)b * ldc + k]);
+    s = fmaf(qv, cv, s);
+    sq = fmaf(qv, qv, sq);
+    scn = fmaf(cv, cv, scn);
+  }
   s = warp_sum(s);
-  if (lane == 0) diag[b] = s * inv_t;
+  sq = warp_sum(sq);
+  scn = warp_sum(scn);
+  if (lane == 0) {
+    diag[b] = s * inv_t;
+    qn2[b] = sq;
+    atomicMax(cmax2, __float_as_uint(scn));
+  }
 }
 
 __global__ void __launch_bounds__(1024)
@@ -962,7 +1041,7 @@ static int column_splits(int64_t B, int NT) {
 
 template <int KB>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tcm, int B, float scale2, const float* diag, float* lse,
-                      float* partial, float* ml, int splits, cudaStream_t s) {
+                      float* partial, float* ml, int splits, const float* qn2, const unsigned int* cmax2, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(tc_softmax_fwd_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -971,7 +1050,7 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tcm, int B, floa
     attr = true;
   }
   dim3 grid((B + 127) / 128, splits);
-  tc_softmax_fwd_kernel<KB><<<grid, FwdCfg<KB>::THREADS, FwdCfg<KB>::SMEM, s>>>(tq, tcm, B, scale2, diag, lse, partial, ml);
+  tc_softmax_fwd_kernel<KB><<<grid, FwdCfg<KB>::THREADS, FwdCfg<KB>::SMEM, s>>>(tq, tcm, B, scale2, diag, lse, partial, ml, qn2, cmax2);
   TT_CHECK_LAUNCH("tc_softmax_fwd");
   return TT_OK;
 }
@@ -1071,7 +1150,7 @@ int tt_set_softmax_backward_mode(int32_t mode) {
 }
 
 size_t tt_inbatch_softmax_bf16_workspace_bytes(int64_t B) {
-  return align_up((size_t)((B + 127) / 128 + 1) * 4, 256) + align_up((size_t)B * 2 * 2 * 4, 256) + 256;
+  return align_up((size_t)((B + 127) / 128 + 1) * 4, 256) + align_up((size_t)B * 2 * 2 * 4, 256) + align_up((size_t)B * 4, 256) + 512;
 }
 
 int tt_inbatch_softmax_forward_bf16(const void* q_bf16, int64_t ldq, const void* c_bf16, int64_t ldc, int64_t B,
@@ -1091,18 +1170,23 @@ int tt_inbatch_softmax_forward_bf16(const void* q_bf16, int64_t ldq, const void*
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tcm, c_bf16, B, d, ldc, NT);
   if (rc) return rc;
-  rowdot_bf16_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(q_bf16), ldq,
-                                                            static_cast<const __nv_bfloat16*>(c_bf16), ldc, (int)B,
-                                                            (int)d, inv_t, diag);
-  TT_CHECK_LAUNCH("rowdot_bf16");
   float* partial = static_cast<float*>(ws);
   float* ml = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up((size_t)(blocks + 1) * 4, 256));
+  float* qn2 = reinterpret_cast<float*>(reinterpret_cast<char*>(ml) + align_up((size_t)B * 2 * 2 * 4, 256));
+  unsigned int* cmax2 = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(qn2) + align_up((size_t)B * 4, 256));
+  static const bool no_fixed = [] { const char* v = getenv("TT_SOFTMAX_FWD"); return v != nullptr && strcmp(v, "online") == 0; }();
+  if (cudaMemsetAsync(cmax2, 0, 4, s) != cudaSuccess) return fail(TT_ERR_CUDA, "inbatch_softmax_forward_bf16: memset failed");
+  rowdot_bf16_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(q_bf16), ldq,
+                                                            static_cast<const __nv_bfloat16*>(c_bf16), ldc, (int)B,
+                                                            (int)d, inv_t, diag, qn2, cmax2);
+  TT_CHECK_LAUNCH("rowdot_bf16");
+  const float* qn2_arg = no_fixed ? nullptr : qn2;      // TT_SOFTMAX_FWD=online: always the online-max path (A/B runs)
   const float scale2 = inv_t * kLog2e;
   switch (KB) {
-    case 1: rc = launch_fwd<1>(tq, tcm, (int)B, scale2, diag, lse, partial, ml, splits, s); break;
-    case 2: rc = launch_fwd<2>(tq, tcm, (int)B, scale2, diag, lse, partial, ml, splits, s); break;
-    case 3: rc = launch_fwd<3>(tq, tcm, (int)B, scale2, diag, lse, partial, ml, splits, s); break;
-    default: rc = launch_fwd<4>(tq, tcm, (int)B, scale2, diag, lse, partial, ml, splits, s); break;
+    case 1: rc = launch_fwd<1>(tq, tcm, (int)B, scale2, diag, lse, partial, ml, splits, qn2_arg, cmax2, s); break;
+    case 2: rc = launch_fwd<2>(tq, tcm, (int)B, scale2, diag, lse, partial, ml, splits, qn2_arg, cmax2, s); break;
+    case 3: rc = launch_fwd<3>(tq, tcm, (int)B, scale2, diag, lse, partial, ml, splits, qn2_arg, cmax2, s); break;
+    default: rc = launch_fwd<4>(tq, tcm, (int)B, scale2, diag, lse, partial, ml, splits, qn2_arg, cmax2, s); break;
   }
   if (rc) return rc;
   if (splits > 1) {
