@@ -100,7 +100,7 @@ __device__ __forceinline__ constexpr bool use_poly(int j) {
 #define TT_POLY_FWD 2
 #endif
 #ifndef TT_POLY_BWD
-#define TT_POLY_BWD 1
+#define TT_POLY_BWD 3
 #endif
 #ifndef TT_MMA_SLEEP_NS
 #define TT_MMA_SLEEP_NS 64
