@@ -195,6 +195,9 @@ __device__ __forceinline__ void lse_chunk(const uint32_t (&v)[32], int col0, int
 #ifndef TT_POLY_FWD_FIXED
 #define TT_POLY_FWD_FIXED 3
 #endif
+#ifndef TT_POLY_FWD_FIXED_DEG
+#define TT_POLY_FWD_FIXED_DEG 4
+#endif
 template <bool TAIL>
 __device__ __forceinline__ void lse_chunk_fixed(const uint32_t (&v)[32], int col0, int B, float scale2, float shift, float& l) {
   const float2 sc = make_float2(scale2, scale2), sh = make_float2(-shift, -shift);
@@ -202,7 +205,7 @@ __device__ __forceinline__ void lse_chunk_fixed(const uint32_t (&v)[32], int col
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     float2 e[4];
-    ex2_8<TT_POLY_FWD_FIXED, 4>(&v[j], sc, sh, e);
+    ex2_8<TT_POLY_FWD_FIXED, TT_POLY_FWD_FIXED_DEG>(&v[j], sc, sh, e);
     if (TAIL) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
