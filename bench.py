@@ -318,8 +318,9 @@ def run_ours(args):
         roof = {"kernel": "in-batch softmax: tc_softmax_fwd_kernel + tc_softmax_bwd_fused_kernel (tcgen05)", "bound": "tensor",
                 "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(ach / pk["tf_sustained"], 4),
-                # dram__bytes_read+write per step of the three launches, from the ncu --set full capture in profiles/
-                "traffic": 1.02e8, "peak_source": pk["source"] + " (sustained bf16)", "ms": round(sm_ms, 4),
+                # dram__bytes_read+write per step of the two launches, from the ncu --set full capture
+                # profiles/r01_ncu_softmax_final2_summary.txt (17.3 MB forward + 50.8 MB one-pass backward)
+                "traffic": 6.82e7, "peak_source": pk["source"] + " (sustained bf16)", "ms": round(sm_ms, 4),
                 "flops_credited": "6*B*B*d (recomputation of S in the backward is not credited)",
                 "note": "at d=64 the forward is MUFU(ex2)-bound (1 ex2 per 64 MACs) and the one-pass backward is bound by shared-memory "
                         "operand bandwidth of its N=64 tcgen05.mma (ncu: tc+lsu smem wavefronts ~90%); see DESIGN.md section 4"}
