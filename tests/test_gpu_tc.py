@@ -251,3 +251,33 @@ def test_in_batch_softmax_full_size_closed_form(cuda):
     assert float(qd.grad.abs().max()) <= 2e-3 * scale * float(c0.abs().max())
     want_dc = (q.double().mean(0, keepdim=True) - q.double()) * scale
     torch.testing.assert_close(cd.grad.cpu().double(), want_dc, rtol=1e-3, atol=2e-3 * scale * float(q.abs().max()))
+
+
+def test_fused_towers_without_bias_and_unused_tower(cuda):
+    """bias=False towers (null b1 / b2 pointers, no bias gradients) and a tower whose output receives no gradient."""
+    from two_tower_recommender_model_b200.functional import FusedTowersTC, MlpTC
+    g = torch.Generator().manual_seed(4)
+    B, i, h, o = 515, 64, 128, 64
+    pooled = (torch.randn(B, 2 * i, generator=g) * 0.5).to(cuda)
+    ws = [(torch.randn(h, i, generator=g) / i ** 0.5).to(cuda), None, (torch.randn(o, h, generator=g) / h ** 0.5).to(cuda), None] * 2
+    dy0 = torch.randn(B, o, generator=g).to(cuda)
+
+    def run(fused):
+        p = pooled.clone().requires_grad_(True)
+        ps = [None if x is None else x.clone().requires_grad_(True) for x in ws]
+        if fused:
+            ys = FusedTowersTC.apply(p, (0, i), i, *ps)[:2]
+        else:
+            ys = [MlpTC.apply(p.narrow(1, t * i, i), *ps[4 * t: 4 * t + 4]) for t in range(2)]
+        ys[0].backward(dy0)                      # tower 1 gets no gradient at all
+        return ys[0].detach(), ys[1].detach(), p.grad, [None if x is None else x.grad for x in ps]
+
+    a, b = run(True), run(False)
+    torch.testing.assert_close(a[0], b[0], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(a[1], b[1], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(a[2][:, :i], b[2][:, :i], rtol=2e-2, atol=2e-2 * float(b[2].abs().max()))
+    assert float(a[2][:, i:].abs().max()) == 0.0
+    for k in (0, 2):
+        torch.testing.assert_close(a[3][k], b[3][k], rtol=2e-2, atol=2e-2 * float(b[3][k].abs().max()))
+    for k in (4, 6):                              # the unused tower: zero weight gradients (or none on the per-layer path)
+        assert a[3][k] is None or float(a[3][k].abs().max()) == 0.0
