@@ -191,6 +191,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
         super().__init__()
         self._peer_exchange = bool(peer_exchange)
         self._peer: Dict[str, PeerExchange] = {}
+        self._whole: Optional[torch.Tensor] = None
         self._pg = pg
         self._rank = dist.get_rank(pg)
         self._world = dist.get_world_size(pg)
@@ -453,7 +454,8 @@ class ShardedEmbeddingBagCollection(nn.Module):
                     col = col / ln.unsqueeze(1)
                 cols[f] = col
                 c0 += d
-        values = torch.cat([cols[f] for f in self._out_features], dim=1)
+        whole, self._whole = self._whole, None
+        values = whole if whole is not None else torch.cat([cols[f] for f in self._out_features], dim=1)
         return KeyedTensor(keys=self._out_features, length_per_key=self._out_dims, values=values)
 
     def _group_forward_peer(self, grp: _Group, kjt, ebc, B: int, scatter_add: bool) -> Dict[str, torch.Tensor]:
@@ -481,6 +483,8 @@ class ShardedEmbeddingBagCollection(nn.Module):
             else:
                 anchors = tuple(ebc.embedding_bags[c.name].weight for c in ebc.embedding_bag_configs())
         out = _PeerTwLookup.apply(ex, ebc, (col, layout_cols), keys, values, offsets, scatter_add, *anchors)
+        if feats == self._out_features:
+            self._whole = out          # this group alone is the module's output, already in output order: no concat copy
         return {f: out[:, layout_cols[f]:layout_cols[f] + grp.feat_dim[f]] for f in feats}
 
     # ---- checkpoint surface: ShardedTensor entries named like the unsharded module --------------
