@@ -36,6 +36,37 @@ def transform_to_torchrec_batch(
     return values, lengths, labels
 
 
+def transform_row_shard(
+    batch: Dict[str, Sequence[int]],
+    cat_cols: List[str],
+    num_embeddings_per_feature: List[int],
+    world_size: int,
+    rank: int,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """What one rank of a ROW-WISE sharded table sees of a batch: the reference transform
+    (utils/model_training.py:43-61) followed by the bucket ``rank`` of TorchRec's row-wise input dist
+    (``block = ceil(R / W)``; ids with ``id // block == rank`` stay, as ``id - rank * block``; every other bag is
+    empty on this rank).  Returns ``(values int64, lengths int32)`` in the same key-major order.  This is the
+    semantics of ``tt_kjt_from_columns_range``; it equals slicing ``block_bucketize_sparse_features`` at ``rank``."""
+    values: List[int] = []
+    lengths: List[int] = []
+    for col_idx, col_name in enumerate(cat_cols):
+        rows = int(num_embeddings_per_feature[col_idx])
+        block = -(-rows // world_size)
+        for value in batch[col_name]:
+            value = int(value)
+            keep = False
+            if value:
+                r = value % rows
+                keep = r // block == rank
+            if keep:
+                values.append(r - rank * block)
+                lengths.append(1)
+            else:
+                lengths.append(0)
+    return torch.tensor(values, dtype=torch.int64), torch.tensor(lengths, dtype=torch.int32)
+
+
 def lengths_to_offsets(lengths: torch.Tensor) -> torch.Tensor:
     """``fbgemm::asynchronous_complete_cumsum`` as used by
     ``KeyedJaggedTensor.from_lengths_sync`` (utils/model_training.py:57)."""

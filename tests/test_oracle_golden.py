@@ -31,6 +31,20 @@ def test_transform_negative_and_modulo():
     assert v.tolist() == [2, 2, 0] and l.tolist() == [1, 1, 0, 1]  # Python modulo; 5 % 5 == 0 stays a length-1 bag
 
 
+def test_transform_row_shard_kat():
+    """Hand-computed: rows=10, W=3 -> block 4: rank 0 holds rows 0-3, rank 1 rows 4-7, rank 2 rows 8-9.
+    ids [13, 0, 4, 9, 20] -> rows [3, -, 4, 9, 0]."""
+    b = {"a": [13, 0, 4, 9, 20], "label": [0] * 5}
+    want = {0: ([3, 0], [1, 0, 0, 0, 1]), 1: ([0], [0, 0, 1, 0, 0]), 2: ([1], [0, 0, 0, 1, 0])}
+    v_all, l_all, _ = oracle.transform_to_torchrec_batch(b, ["a"], [10])
+    nl, nv, _ = oracle.block_bucketize_sparse_features(l_all, v_all, [10], 3, 5)
+    off = oracle.lengths_to_offsets(nl).tolist()
+    for r in range(3):
+        v, l = oracle.transform_row_shard(b, ["a"], [10], 3, r)
+        assert (v.tolist(), l.tolist()) == want[r]
+        assert l.tolist() == nl[r * 5:(r + 1) * 5].tolist() and v.tolist() == nv[off[r * 5]:off[(r + 1) * 5]].tolist()
+
+
 def test_permute_kat():
     c = G["permute_kat"]
     ol, ov, _ = oracle.permute_2d_sparse_data(c["permute"], T(c["lengths"], dtype=torch.int32).view(c["T"], c["B"]), T(c["values"]))
