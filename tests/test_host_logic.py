@@ -155,3 +155,25 @@ def test_header_is_plain_c():
     hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "tt_b200.h")
     r = subprocess.run(["gcc", "-x", "c", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", hdr], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_planner_prefers_row_wise_when_ranks_outnumber_tables():
+    """Two big tables on 8 ranks: table-wise would leave six ranks without embedding work -> row-wise; with as many
+    tables as ranks, or tables too small to split, table-wise (largest first onto the least-loaded rank)."""
+    import two_tower_recommender_model_b200 as tt
+    from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
+
+    def plan_for(world, rows, constraints=None):
+        cfgs = [tt.EmbeddingBagConfig(name=f"t{i}", embedding_dim=64, num_embeddings=r, feature_names=[f"f{i}"]) for i, r in enumerate(rows)]
+        ebc = tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("meta"))
+        p = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world), constraints=constraints).plan(torch.nn.ModuleDict({"ebc": ebc}))
+        return {k: (v.sharding_type, v.ranks) for k, v in p.plan["ebc"].items()}
+
+    p8 = plan_for(8, [10_000_000, 10_000_000])
+    assert all(st == "row_wise" and ranks == list(range(8)) for st, ranks in p8.values())
+    p2 = plan_for(2, [10_000_000, 5_000_000])
+    assert p2["t0"] == ("table_wise", [0]) and p2["t1"] == ("table_wise", [1])
+    small = plan_for(8, [134, 21])
+    assert all(st == "table_wise" for st, _ in small.values())
+    forced = plan_for(8, [10_000_000, 10_000_000], {"t0": ParameterConstraints(sharding_types=["table_wise"])})
+    assert forced["t0"][0] == "table_wise" and forced["t1"][0] == "row_wise"
