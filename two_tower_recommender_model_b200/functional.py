@@ -438,6 +438,7 @@ class FusedTowersTC(torch.autograd.Function):
         ctx.has_bias = [p is not None for p in params]
         ctx.save_for_backward(*[p for p in params if p is not None])
         ctx.mark_non_differentiable(yb)
+        ctx.set_materialize_grads(False)      # no 17 MB zero "gradient" for the bf16 copy; unused towers arrive as None
         return (*ys, yb)
 
     @staticmethod
