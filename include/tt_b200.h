@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TT_ABI_VERSION 1
+#define TT_ABI_VERSION 2
 #define TT_MAX_FEATURES 32
 
 typedef enum {
@@ -169,9 +169,13 @@ typedef struct {
   float eps;
   float beta1;
   float beta2;
-  float bias_correction1; /* 1 - beta1^step (host-computed; adam only) */
-  float bias_correction2; /* 1 - beta2^step                            */
-  float weight_decay;     /* reserved, must be 0 */
+  float bias_correction1; /* 1 - beta1^step, host-computed; used when step_dev == NULL (adam only) */
+  float bias_correction2; /* 1 - beta2^step                                                        */
+  float grad_scale;       /* every gradient row is multiplied by this before the optimizer sees it; 0 means 1.
+                           * 1/world = TorchRec's gradient division in the pooled all-to-all / reduce-scatter backward */
+  float* step_dev;        /* adam: DEVICE pointer to the 1-based step count (float).  Non-NULL: the call increments it
+                           * and derives both bias corrections from it on the device, so the launch has no
+                           * host-computed argument that changes from step to step (CUDA-graph capturable). */
 } tt_sparse_optimizer;
 
 /* Fused backward + optimizer (FBGEMM split_embedding_backward_*_exact reached

@@ -138,9 +138,12 @@ class OracleTwoTower(nn.Module):
         return F.cross_entropy(s, torch.arange(q.shape[0])), s.diagonal()
 
     # ---- one data-parallel step as W ranks would do it: every rank's loss is the mean over ITS
-    # batch; embedding gradients of all ranks are SUMMED into the (model-parallel) tables, tower
-    # gradients are AVERAGED (DDP), then both optimizers step once.
-    def train_step_ranks(self, keys, batches) -> List[torch.Tensor]:
+    # batch; tower gradients are AVERAGED (DDP); embedding gradients of all ranks meet in the
+    # (model-parallel) tables and are divided by W as well -- TorchRec's pooled all-to-all /
+    # reduce-scatter backward divides by the world size (comm_ops GRADIENT_DIVISION, default on) --
+    # i.e. both see the gradient of (1/W) * sum_r loss_r; then both optimizers step once.
+    # ``gradient_division=False`` reproduces set_gradient_division(False): embedding gradients summed.
+    def train_step_ranks(self, keys, batches, gradient_division: bool = True) -> List[torch.Tensor]:
         self.dense_opt.zero_grad(set_to_none=True)
         for eb in self.embedding_bags.values():
             eb.weight.grad = None
@@ -162,7 +165,8 @@ class OracleTwoTower(nn.Module):
                 if w.grad is None:
                     continue
                 assert self.sparse_optimizer == "rowwise_adagrad"
-                rowwise_adagrad_dense(w, self.sparse_state[t.name]["sum"], w.grad, lr=self.sparse_lr, eps=self.sparse_eps)
+                g = w.grad / W if gradient_division else w.grad
+                rowwise_adagrad_dense(w, self.sparse_state[t.name]["sum"], g, lr=self.sparse_lr, eps=self.sparse_eps)
                 w.grad = None
         self.dense_opt.step()
         return losses

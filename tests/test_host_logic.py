@@ -29,7 +29,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(N.EbcPlan) == 16 + 8 + 32 * (8 * 5 + 4 * 5)
-    assert ctypes.sizeof(N.SparseOptimizer) == 32
+    assert ctypes.sizeof(N.SparseOptimizer) == 40   # 8 x 4 bytes + the device step pointer
 
 
 def test_no_cpu_fallback():

@@ -33,7 +33,7 @@ class _OracleLookup(torch.autograd.Function):
     def backward(ctx, g):
         values, lengths = ctx.saved_tensors
         mod = ctx.mod
-        grads = oracle.ebc_dense_grads(mod.specs, ctx.keys, values, lengths, g)
+        grads = oracle.ebc_dense_grads(mod.specs, ctx.keys, values, lengths, g * getattr(mod, "_grad_scale", 1.0))
         for s, gr in zip(mod.specs, grads):  # "fused": row-wise Adagrad applied in backward
             w = mod.embedding_bags[s.name].weight
             oracle.rowwise_adagrad_dense(w.data, mod.state[s.name], gr, lr=w._optimizer_kwargs[0]["lr"])
@@ -111,6 +111,7 @@ def _worker(rank, world, port, errq):
                                             sharding_kwargs=dict(local_ebc_factory=OracleLocalEbc, bucketize_fn=oracle_bucketize))
         assert model._plan is plan and "t_c" in str(model._plan)
         sharded = model.module["ebc"]
+        assert sharded.tw_ebc._grad_scale == 0.5 and sharded.rw_ebc._grad_scale == 0.5
         sharded.load_state_dict({f"embedding_bags.{k}.weight": v for k, v in full.items()})
 
         # ---- forward: every rank's output == unsharded lookup of ITS batch
@@ -132,7 +133,8 @@ def _worker(rank, world, port, errq):
             for acc, gr in zip(dense, oracle.ebc_dense_grads(SPECS, KEYS, v_r, l_r, g_r)):
                 acc += gr
         for s, gr in zip(SPECS, dense):
-            oracle.rowwise_adagrad_dense(ref[s.name], torch.zeros(s.num_embeddings), gr, lr=LR)
+            # TorchRec's gradient division: the tables see sum_r grad_r / W
+            oracle.rowwise_adagrad_dense(ref[s.name], torch.zeros(s.num_embeddings), gr / world, lr=LR)
 
         # ---- state dict: ShardedTensor per table, gathered as utils/model_training.py:161-182 does
         sd = model.state_dict()

@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 TT_MAX_FEATURES = 32
-TT_ABI_VERSION = 1
+TT_ABI_VERSION = 2
 
 POOL_SUM, POOL_MEAN = 0, 1
 OPT_DENSE_GRAD, OPT_ROWWISE_ADAGRAD, OPT_ROWWISE_ADAM, OPT_SGD = 0, 1, 2, 3
@@ -63,7 +63,8 @@ class PeerBuffers(Structure):
 class SparseOptimizer(Structure):
     _fields_ = [
         ("kind", c_int32), ("lr", c_float), ("eps", c_float), ("beta1", c_float), ("beta2", c_float),
-        ("bias_correction1", c_float), ("bias_correction2", c_float), ("weight_decay", c_float),
+        ("bias_correction1", c_float), ("bias_correction2", c_float), ("grad_scale", c_float),
+        ("step_dev", c_void_p),
     ]
 
 

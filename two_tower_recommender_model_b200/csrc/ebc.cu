@@ -30,6 +30,7 @@ struct Vec<4> {
     v.x += s * o.v.x; v.y += s * o.v.y; v.z += s * o.v.z; v.w += s * o.v.w;
   }
   __device__ __forceinline__ void div(float s) { v.x /= s; v.y /= s; v.z /= s; v.w /= s; }
+  __device__ __forceinline__ void scale(float s) { v.x *= s; v.y *= s; v.z *= s; v.w *= s; }
   __device__ __forceinline__ float sumsq() const { return v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
   template <typename F>
   __device__ __forceinline__ void map2(const Vec& a, F f) {  // this = f(this, a) elementwise
@@ -47,6 +48,7 @@ struct Vec<1> {
   __device__ __forceinline__ void add(const Vec& o) { v += o.v; }
   __device__ __forceinline__ void add_scaled(const Vec& o, float s) { v += s * o.v; }
   __device__ __forceinline__ void div(float s) { v /= s; }
+  __device__ __forceinline__ void scale(float s) { v *= s; }
   __device__ __forceinline__ float sumsq() const { return v * v; }
   template <typename F>
   __device__ __forceinline__ void map2(const Vec& a, F f) { v = f(v, a.v); }
@@ -227,7 +229,15 @@ ebc_forward_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_consta
 __global__ void __launch_bounds__(kEbcThreads)
 ebc_backward_keys_kernel(const __grid_constant__ tt_ebc_plan plan, const int64_t* __restrict__ values,
                          const int32_t* __restrict__ offsets, uint32_t* __restrict__ keys,
-                         uint32_t* __restrict__ payload, int tiles_per_key) {
+                         uint32_t* __restrict__ payload, int tiles_per_key,
+                         float* __restrict__ adam_step, float beta1, float beta2, float* __restrict__ adam_bc) {
+  if (adam_step != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    // device-side Adam step counter (no host-computed bias correction in the launch arguments)
+    const float st = *adam_step + 1.0f;
+    *adam_step = st;
+    adam_bc[0] = (float)(1.0 - pow((double)beta1, (double)st));
+    adam_bc[1] = (float)(1.0 - pow((double)beta2, (double)st));
+  }
   const int f = blockIdx.x / tiles_per_key;  // KJT key index
   const int tile = blockIdx.x - f * tiles_per_key;
   const int B = plan.batch_size;
@@ -285,9 +295,13 @@ constexpr int kHotRowFloats = 1024;   // widest embedding row the scratch is siz
 // or accumulation into a dense gradient.
 template <int VEC, int G, int NV>
 __device__ __forceinline__ void apply_row(const tt_ebc_plan& plan, const tt_sparse_optimizer& opt, int slot, int64_t row,
-                                          int l, unsigned mask, Vec<VEC> (&g)[NV]) {
+                                          int l, unsigned mask, Vec<VEC> (&g)[NV], const float* __restrict__ adam_bc) {
   const int D = plan.dim[slot];
   const int units = D / VEC;
+  if (opt.grad_scale != 0.f && opt.grad_scale != 1.f) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) g[v].scale(opt.grad_scale);
+  }
   // mean over D of g^2 (group reduction)
   float ss = 0.f;
 #pragma unroll
@@ -321,8 +335,10 @@ __device__ __forceinline__ void apply_row(const tt_ebc_plan& plan, const tt_spar
     const float vnew = opt.beta2 * (*vst) + (1.0f - opt.beta2) * msq;
     __syncwarp(mask);
     if (l == 0) *vst = vnew;
-    const float denom = sqrtf(vnew / opt.bias_correction2) + opt.eps;
-    const float b1 = opt.beta1, omb1 = 1.0f - opt.beta1, bc1 = opt.bias_correction1, lr = opt.lr;
+    const float bc2 = opt.step_dev != nullptr ? adam_bc[1] : opt.bias_correction2;
+    const float denom = sqrtf(vnew / bc2) + opt.eps;
+    const float b1 = opt.beta1, omb1 = 1.0f - opt.beta1, lr = opt.lr;
+    const float bc1 = opt.step_dev != nullptr ? adam_bc[0] : opt.bias_correction1;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const int c = l + v * G;
@@ -370,7 +386,7 @@ ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
                            const uint32_t* __restrict__ keys, const uint32_t* __restrict__ payload,
                            int64_t n, const int32_t* __restrict__ offsets,
                            const float* __restrict__ grad_out, const __grid_constant__ tt_peer_buffers peers,
-                           float* __restrict__ hot, int hot_stride) {
+                           float* __restrict__ hot, int hot_stride, const float* __restrict__ adam_bc) {
   constexpr int64_t hot_seg = kHotSeg;
   const int64_t gid = ((int64_t)blockIdx.x * kEbcThreads + threadIdx.x) / G;
   const int l = threadIdx.x % G;
@@ -508,7 +524,7 @@ ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
   // only a segment filled up to its boundary can continue in the next one (one extra key load, rarely)
   const bool continues = run_end == seg_end && seg_end < n && keys[seg_end] == key;
   if (head && !continues) {
-    apply_row<VEC, G, NV>(plan, opt, slot, row, l, mask, g);
+    apply_row<VEC, G, NV>(plan, opt, slot, row, l, mask, g, adam_bc);
     return;
   }
   int64_t h = gid;                                   // position of the run's head
@@ -606,7 +622,7 @@ template <int VEC, int G, int NV>
 __global__ void __launch_bounds__(kEbcThreads)
 ebc_backward_hot_apply_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_constant__ tt_sparse_optimizer opt,
                               const uint32_t* __restrict__ keys, int64_t n, const float* __restrict__ hot, int hot_stride,
-                              int64_t num_bounds) {
+                              int64_t num_bounds, const float* __restrict__ adam_bc) {
   constexpr int64_t hot_seg = kHotSeg;
   const int64_t b = ((int64_t)blockIdx.x * kEbcThreads + threadIdx.x) / G + 1;
   const int l = threadIdx.x % G;
@@ -634,7 +650,7 @@ ebc_backward_hot_apply_kernel(const __grid_constant__ tt_ebc_plan plan, const __
     g[v].zero();
     if (c < units) g[v].load(acc + c * VEC);
   }
-  apply_row<VEC, G, NV>(plan, opt, slot, row, l, mask, g);
+  apply_row<VEC, G, NV>(plan, opt, slot, row, l, mask, g, adam_bc);
 }
 
 }  // namespace tt
@@ -694,7 +710,7 @@ int tt_ebc_forward_peer(const tt_ebc_plan* h_plan, const int64_t* values, const 
 
 size_t tt_ebc_backward_workspace_bytes(int64_t n) {
   if (n < 1) n = 1;
-  return 4 * align_up((size_t)n * 4, 256) + sort_workspace_bytes(n) + 1024 +
+  return 4 * align_up((size_t)n * 4, 256) + sort_workspace_bytes(n) + 1024 + 256 /* adam bias corrections */ +
          align_up((size_t)(n / kHotSeg + 2) * kHotRowFloats * 4, 256);
 }
 
@@ -710,7 +726,7 @@ static int ebc_backward_impl(const tt_ebc_plan* h_plan, const tt_sparse_optimize
   if (rc) return rc;
   TT_CHECK_ARG(h_opt && offsets && (grad_out || h_peers) && n >= 0, "ebc_backward: bad args");
   TT_CHECK_ARG(h_opt->kind >= TT_OPT_DENSE_GRAD && h_opt->kind <= TT_OPT_SGD, "ebc_backward: bad optimizer kind");
-  TT_CHECK_ARG(h_opt->weight_decay == 0.0f, "ebc_backward: weight_decay not supported");
+  TT_CHECK_ARG(h_opt->grad_scale >= 0.0f, "ebc_backward: negative grad_scale");
   if (n == 0 || h_plan->num_slots == 0 || h_plan->batch_size == 0) return TT_OK;
   if (n >= ((int64_t)1 << 31)) return fail(TT_ERR_UNSUPPORTED, "ebc_backward: too many ids");
   if ((int64_t)h_plan->num_slots * h_plan->batch_size >= ((int64_t)1 << 32))
@@ -729,11 +745,13 @@ static int ebc_backward_impl(const tt_ebc_plan* h_plan, const tt_sparse_optimize
   uint32_t* skeys = w.take<uint32_t>(n);
   uint32_t* spayload = w.take<uint32_t>(n);
   float* hot = w.take<float>((size_t)(n / kHotSeg + 2) * kHotRowFloats);
-  if (!keys || !payload || !skeys || !spayload || !hot) return fail(TT_ERR_WORKSPACE, "ebc_backward: workspace too small");
+  float* adam_bc = w.take<float>(2);
+  if (!keys || !payload || !skeys || !spayload || !hot || !adam_bc) return fail(TT_ERR_WORKSPACE, "ebc_backward: workspace too small");
 
   const int tiles = (h_plan->batch_size + kBagsPerCta - 1) / kBagsPerCta;
   ebc_backward_keys_kernel<<<(unsigned)(tiles * h_plan->num_kjt_keys), kEbcThreads, 0, s>>>(
-      *h_plan, values, offsets, keys, payload, tiles);
+      *h_plan, values, offsets, keys, payload, tiles,
+      h_opt->kind == TT_OPT_ROWWISE_ADAM ? h_opt->step_dev : nullptr, h_opt->beta1, h_opt->beta2, adam_bc);
   TT_CHECK_LAUNCH("ebc_backward_keys");
   ebc_backward_tail_kernel<<<64, 256, 0, s>>>(offsets, (int64_t)h_plan->num_kjt_keys * h_plan->batch_size, n,
                                               (uint32_t)h_plan->total_rows, keys, payload);
@@ -762,7 +780,7 @@ static int ebc_backward_impl(const tt_ebc_plan* h_plan, const tt_sparse_optimize
   }
 #define TT_LAUNCH_BWD(V, G, N)                                                                        \
   ebc_backward_update_kernel<V, G, N><<<grid, kEbcThreads, 0, s>>>(*h_plan, *h_opt, skeys, spayload, n, \
-                                                                   offsets, grad_out, peers, hot, hot_stride)
+                                                                   offsets, grad_out, peers, hot, hot_stride, adam_bc)
   TT_DISPATCH_CLASS(id, TT_LAUNCH_BWD);
 #undef TT_LAUNCH_BWD
   TT_CHECK_LAUNCH("ebc_backward_update");
@@ -770,7 +788,7 @@ static int ebc_backward_impl(const tt_ebc_plan* h_plan, const tt_sparse_optimize
     const unsigned hgrid = (unsigned)((num_bounds * c.g + kEbcThreads - 1) / kEbcThreads);
 #define TT_LAUNCH_HOT(V, G, N)                                                                              \
   ebc_backward_hot_apply_kernel<V, G, N><<<hgrid, kEbcThreads, 0, s>>>(*h_plan, *h_opt, skeys, n, hot, hot_stride, \
-                                                                       num_bounds)
+                                                                       num_bounds, adam_bc)
     TT_DISPATCH_CLASS(id, TT_LAUNCH_HOT);
 #undef TT_LAUNCH_HOT
     TT_CHECK_LAUNCH("ebc_backward_hot_apply");

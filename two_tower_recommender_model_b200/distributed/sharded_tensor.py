@@ -13,12 +13,13 @@ except Exception:  # pragma: no cover
 
 
 def make_row_sharded(local_rows: Optional[torch.Tensor], row_offset: int, global_shape, pg=None):
-    """Wraps this rank's block of rows (or nothing) of a ``[R, D]`` table as a ShardedTensor."""
+    """Wraps this rank's block of rows (or nothing) of a ``[R, D]`` table -- or of a per-row ``[R]`` optimizer
+    state -- as a ShardedTensor."""
     shards: List = []
     if local_rows is not None and local_rows.numel() > 0:
         rank = dist.get_rank(pg)
         dev = local_rows.device
-        md = ShardMetadata(shard_offsets=[row_offset, 0], shard_sizes=list(local_rows.shape),
+        md = ShardMetadata(shard_offsets=[row_offset] + [0] * (local_rows.dim() - 1), shard_sizes=list(local_rows.shape),
                            placement=f"rank:{rank}/{dev}")
         shards.append(Shard(tensor=local_rows, metadata=md))
     return ShardedTensor._init_from_local_shards(shards, *global_shape, process_group=pg)

@@ -35,6 +35,24 @@ from ..sparse.jagged_tensor import KeyedJaggedTensor, KeyedTensor
 from .planner import ParameterSharding, ShardingPlan
 
 
+# TorchRec divides the gradient that flows back through the pooled-embedding all-to-all / reduce-scatter by the
+# world size (torchrec.distributed.comm_ops, GRADIENT_DIVISION = True by default): every rank's loss is the mean over
+# ITS batch, the data-parallel towers average their gradients over ranks, and the tables must see the gradient of
+# the same global objective (1/W) * sum_r loss_r.  Here the division is folded into the fused embedding backward
+# (tt_sparse_optimizer.grad_scale = 1/W on every local shard), so it costs nothing.
+_GRADIENT_DIVISION = True
+
+
+def set_gradient_division(val: bool) -> None:
+    """``torchrec.distributed.comm_ops.set_gradient_division``; read when a module is sharded."""
+    global _GRADIENT_DIVISION
+    _GRADIENT_DIVISION = bool(val)
+
+
+def get_gradient_division() -> bool:
+    return _GRADIENT_DIVISION
+
+
 # --------------------------------------------------------------------------- differentiable collectives
 class _AllToAllRows(torch.autograd.Function):
     """``all_to_all_single`` over flattened row blocks; backward is the reverse exchange."""
@@ -253,6 +271,10 @@ class ShardedEmbeddingBagCollection(nn.Module):
         object.__setattr__(self, "tw_ebc", tw_ebc)
         object.__setattr__(self, "rw_ebc", rw_ebc)
         self._tw.local_ebc, self._rw.local_ebc = tw_ebc, rw_ebc
+        self._gradient_division = get_gradient_division()
+        for local in (tw_ebc, rw_ebc):
+            if local is not None:
+                local._grad_scale = 1.0 / W if self._gradient_division else 1.0
         for local in (tw_ebc, rw_ebc):
             if local is None or not hasattr(local, "embedding_bags"):
                 continue
@@ -495,29 +517,87 @@ class ShardedEmbeddingBagCollection(nn.Module):
         local = self.tw_ebc if kind == "table_wise" else self.rw_ebc
         return local.embedding_bags[name].weight.detach()[:rows]
 
+    def include_optimizer_state(self, on: bool = True) -> "ShardedEmbeddingBagCollection":
+        """``True``: ``state_dict()`` also carries the fused row-wise optimizer state of every table
+        (``embedding_bags.<t>.{sum | exp_avg | exp_avg_sq}``, row-sharded like the weights) and the Adam step, and
+        ``load_state_dict`` restores them; default ``False`` = the reference's weights-only format."""
+        self._state_dict_with_optimizer = bool(on)
+        return self
+
+    def _local_ebc_of(self, name: str):
+        return self.tw_ebc if self._shard_info[name][0] == "table_wise" else self.rw_ebc
+
     def state_dict(self, *args, destination=None, prefix: str = "", keep_vars: bool = False):
+        from .. import _native as N
         from .sharded_tensor import make_row_sharded
         destination = {} if destination is None else destination
         for c in self._configs:
             _kind, off, _rows = self._shard_info[c.name]
             destination[f"{prefix}embedding_bags.{c.name}.weight"] = make_row_sharded(
                 self._local_weight(c.name), off, (c.num_embeddings, c.embedding_dim), self._pg)
+        if getattr(self, "_state_dict_with_optimizer", False):
+            step = 0
+            for c in self._configs:
+                _kind, off, rows = self._shard_info[c.name]
+                local = self._local_ebc_of(c.name)
+                kind = next((l._in_backward_kind() for l in (self.tw_ebc, self.rw_ebc) if l is not None), None)
+                names = {N.OPT_ROWWISE_ADAGRAD: ("sum",), N.OPT_ROWWISE_ADAM: ("exp_avg", "exp_avg_sq")}.get(kind, ())
+                for k in names:
+                    st = None
+                    if rows > 0:
+                        cfg = next(x for x in local.embedding_bag_configs() if x.name == c.name)
+                        st = local._state_for(cfg, local.embedding_bags[c.name].weight, kind)[k][:rows]
+                    shape = (c.num_embeddings, c.embedding_dim) if k == "exp_avg" else (c.num_embeddings,)
+                    destination[f"{prefix}embedding_bags.{c.name}.{k}"] = make_row_sharded(st, off, shape, self._pg)
+            for l in (self.tw_ebc, self.rw_ebc):
+                if l is not None and hasattr(l, "fused_step"):
+                    step = max(step, l.fused_step())
+            destination[f"{prefix}fused_optimizer_step"] = torch.tensor(float(step), dtype=torch.float32)
         return destination
 
+    def _rows_from(self, src, off: int, rows: int, name: str) -> torch.Tensor:
+        """This rank's rows [off, off + rows) out of a checkpoint entry: a full tensor, or the ShardedTensor this
+        module itself writes (same row split -> the local shard is the answer, no communication)."""
+        from .sharded_tensor import ShardedTensor
+        if ShardedTensor is not None and isinstance(src, ShardedTensor):
+            for sh in src.local_shards():
+                if sh.metadata.shard_offsets[0] == off and sh.metadata.shard_sizes[0] == rows:
+                    return sh.tensor
+            raise RuntimeError(f"{name}: the ShardedTensor in the checkpoint is split differently from this module's plan "
+                               f"(need rows [{off}, {off + rows}) on this rank); gather it to a full tensor first "
+                               "(utils/model_training.py:161-182 does) and load that")
+        return src[off:off + rows]
+
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
-        """Accepts FULL (unsharded) tensors under the TorchRec key names and keeps this rank's rows."""
+        """Accepts, under the TorchRec key names, FULL (unsharded) tensors -- every rank keeps its rows -- or the
+        ShardedTensors of this module's own ``state_dict()`` (resume of a sharded job without a gather)."""
         for c in self._configs:
             key = f"{prefix}embedding_bags.{c.name}.weight"
             if key not in state_dict:
                 if strict:
                     missing_keys.append(key)
                 continue
-            full = state_dict[key]
             w = self._local_weight(c.name)
+            _kind, off, rows = self._shard_info[c.name]
             if w is not None:
-                _kind, off, rows = self._shard_info[c.name]
                 with torch.no_grad():
-                    w.copy_(full[off:off + rows].to(w.device))
+                    w.copy_(self._rows_from(state_dict[key], off, rows, key).to(w.device))
+            for k in ("sum", "exp_avg", "exp_avg_sq"):
+                skey = f"{prefix}embedding_bags.{c.name}.{k}"
+                if skey in state_dict and rows > 0:
+                    local = self._local_ebc_of(c.name)
+                    part = self._rows_from(state_dict[skey], off, rows, skey).detach().to(device=w.device, dtype=torch.float32)
+                    full_rows = local.embedding_bags[c.name].weight.shape[0]
+                    if part.shape[0] != full_rows:      # a row-wise shard padded to >= 1 row
+                        pad = torch.zeros((full_rows - part.shape[0],) + tuple(part.shape[1:]), dtype=part.dtype, device=part.device)
+                        part = torch.cat([part, pad])
+                    local._fused_state.setdefault(c.name, {})[k] = part.clone()
+        skey = f"{prefix}fused_optimizer_step"
+        if skey in state_dict:
+            for l in (self.tw_ebc, self.rw_ebc):
+                if l is not None and hasattr(l, "_fused_step"):
+                    l._fused_step = int(round(float(state_dict[skey])))
+                    l._fused_step_dev = None
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         missing: List[str] = []

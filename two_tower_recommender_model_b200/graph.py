@@ -8,8 +8,11 @@ not change from step to step once the inputs live in static buffers.  ``CudaGrap
 first calls eagerly (warm-up with REAL batches, so nothing is trained on dummy data), then captures
 one step and replays it: per step the host issues two async copies and one graph launch.
 
-Requirements: static shapes (batches given as raw id columns ``[F, B]`` + labels ``[B]``), sparse optimizer RowWiseAdagrad or SGD (row-wise Adam's bias correction
-is host-computed), dense optimizer ``FlatAdam`` (device-side step counter) or SGD.
+Requirements: static shapes (batches given as raw id columns ``[F, B]`` + labels ``[B]``); sparse optimizer
+RowWiseAdagrad, RowWiseAdam or SGD (row-wise Adam keeps its step counter on the device: ``tt_sparse_optimizer.step_dev``
+is incremented by the fused backward itself, so the replayed launch arguments never go stale); dense optimizer
+``FlatAdam`` (device-side step counter) or SGD -- ``torch.optim.Adam`` computes its bias correction on the host
+and is refused.
 """
 from typing import List, Optional, Sequence
 
@@ -23,6 +26,7 @@ class CudaGraphTrainStep:
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, keys: Sequence[str],
                  num_embeddings: Sequence[int], batch_size: int, device: torch.device, warmup_steps: int = 3) -> None:
         self._model, self._opt = model, optimizer
+        self._check_capturable(optimizer)
         self._keys = list(keys)
         self._dev = torch.device(device)
         F = len(self._keys)
@@ -35,6 +39,15 @@ class CudaGraphTrainStep:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._out = None
         self._stream = torch.cuda.Stream(device=self._dev)
+
+    @staticmethod
+    def _check_capturable(optimizer) -> None:
+        """An optimizer whose step() bakes host-computed, step-dependent scalars into its launches would replay
+        them frozen: refuse it instead of training silently wrong."""
+        inner = getattr(optimizer, "_optimizer", optimizer)
+        if isinstance(inner, (torch.optim.Adam, torch.optim.AdamW)) and not any(g.get("capturable") for g in inner.param_groups):
+            raise ValueError("CudaGraphTrainStep: torch.optim.Adam keeps its step count on the host; use tt.FlatAdam "
+                             "(device-side step counter), torch.optim.SGD, or Adam(capturable=True)")
 
     def _step(self):
         kjt = KeyedJaggedTensor.from_id_columns(self._keys, self._ids, self._rows)

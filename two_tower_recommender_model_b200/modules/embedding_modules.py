@@ -96,6 +96,15 @@ class EmbeddingBagCollection(nn.Module):
         self._total_dim = sum(self._slot_dim)
         self._fused_state: Dict[str, Dict[str, torch.Tensor]] = {}
         self._fused_step = 0
+        # Adam's step counter also lives on the device (float32 [1]): the fused backward increments it and derives
+        # the bias corrections from it, so a captured CUDA graph keeps stepping (graph.py)
+        self._fused_step_dev: Optional[torch.Tensor] = None
+        # every gradient row is multiplied by this inside the fused backward; the sharded module sets 1/world
+        # (TorchRec's gradient division in the pooled all-to-all / reduce-scatter backward)
+        self._grad_scale = 1.0
+        # False (default): state_dict() is weights-only, the reference's checkpoint format
+        # (utils/model_training.py:161-189); True adds the fused optimizer state, see include_optimizer_state()
+        self._state_dict_with_optimizer = False
 
     # ---- TorchRec surface
     def embedding_bag_configs(self) -> List[EmbeddingBagConfig]:
@@ -124,6 +133,8 @@ class EmbeddingBagCollection(nn.Module):
         for st in self._fused_state.values():
             for k in list(st.keys()):
                 st[k] = fn(st[k])
+        if self._fused_step_dev is not None:
+            self._fused_step_dev = fn(self._fused_step_dev)
         return out
 
     def forward(self, features: KeyedJaggedTensor) -> KeyedTensor:
@@ -238,6 +249,7 @@ class EmbeddingBagCollection(nn.Module):
         if kw.get("weight_decay", 0.0) != 0.0 or kw.get("lr_decay", 0.0) != 0.0:
             raise NotImplementedError("weight_decay / lr_decay are not supported by the fused sparse optimizers")
         spec = N.SparseOptimizer(kind=kind)
+        spec.grad_scale = float(self._grad_scale)
         if kind == N.OPT_ROWWISE_ADAGRAD:
             spec.lr = float(kw.get("lr", RowWiseAdagrad.DEFAULT_LR))
             spec.eps = float(kw.get("eps", RowWiseAdagrad.DEFAULT_EPS))
@@ -251,6 +263,13 @@ class EmbeddingBagCollection(nn.Module):
             step = max(self._fused_step, 1)
             spec.bias_correction1 = 1.0 - float(b1) ** step
             spec.bias_correction2 = 1.0 - float(b2) ** step
+            if advance_step:
+                # the kernel increments the device counter itself and uses IT (the host values above are the
+                # same numbers while the step runs eagerly; a replayed CUDA graph only has the device counter)
+                w = self.embedding_bags[self._embedding_bag_configs[0].name].weight
+                if self._fused_step_dev is None or self._fused_step_dev.device != w.device:
+                    self._fused_step_dev = torch.full((1,), float(self._fused_step - 1), dtype=torch.float32, device=w.device)
+                spec.step_dev = self._fused_step_dev.data_ptr()
         else:
             spec.lr = float(kw.get("lr", 1e-3))
         return spec
@@ -277,8 +296,58 @@ class EmbeddingBagCollection(nn.Module):
         checkpoints; exposed so a resume can be exact)."""
         return self._fused_state
 
+    def fused_step(self) -> int:
+        """Number of fused Adam steps taken (read from the device counter when a CUDA graph advanced it)."""
+        if self._fused_step_dev is not None:
+            return int(round(float(self._fused_step_dev.item())))
+        return self._fused_step
+
     def load_fused_optimizer_state(self, state: Dict[str, Dict[str, torch.Tensor]], step: int = 0) -> None:
         for name, st in state.items():
             w = self.embedding_bags[name].weight
             self._fused_state[name] = {k: v.to(w.device).clone() for k, v in st.items()}
-        self._fused_step = step
+        self._fused_step = int(step)
+        self._fused_step_dev = None
+
+    # ---- optimizer state inside the checkpoint (SURVEY 8(f) N3; the reference's own checkpoints are weights-only)
+    def include_optimizer_state(self, on: bool = True) -> "EmbeddingBagCollection":
+        """``True``: ``state_dict()`` also carries the fused optimizer's state as
+        ``embedding_bags.<table>.{sum | exp_avg | exp_avg_sq}`` plus ``fused_optimizer_step``, and
+        ``load_state_dict`` restores it, so save -> reload -> next step is identical.  Default ``False`` keeps the
+        reference's weights-only format (utils/model_training.py:161-189)."""
+        self._state_dict_with_optimizer = bool(on)
+        return self
+
+    def _optimizer_state_entries(self) -> Dict[str, torch.Tensor]:
+        out: Dict[str, torch.Tensor] = {}
+        kind = self._in_backward_kind()
+        if kind in (N.OPT_ROWWISE_ADAGRAD, N.OPT_ROWWISE_ADAM):
+            for cfg in self._embedding_bag_configs:
+                w = self.embedding_bags[cfg.name].weight
+                if w.device.type == "meta":
+                    continue
+                for k, v in self._state_for(cfg, w, kind).items():
+                    out[f"embedding_bags.{cfg.name}.{k}"] = v
+            out["fused_optimizer_step"] = torch.tensor(float(self.fused_step()), dtype=torch.float32)
+        return out
+
+    def state_dict(self, *args, destination=None, prefix: str = "", keep_vars: bool = False):
+        destination = super().state_dict(*args, destination=destination, prefix=prefix, keep_vars=keep_vars)
+        if self._state_dict_with_optimizer:
+            for k, v in self._optimizer_state_entries().items():
+                destination[prefix + k] = v if keep_vars else v.detach()
+        return destination
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        # optimizer-state entries are optional on load (a weights-only checkpoint of the reference still loads)
+        names = {f"{prefix}embedding_bags.{c.name}.{k}": (c, k) for c in self._embedding_bag_configs
+                 for k in ("sum", "exp_avg", "exp_avg_sq")}
+        for key in [k for k in state_dict if k in names]:
+            cfg, k = names[key]
+            w = self.embedding_bags[cfg.name].weight
+            self._fused_state.setdefault(cfg.name, {})[k] = state_dict.pop(key).detach().to(device=w.device, dtype=torch.float32).clone()
+        step_key = prefix + "fused_optimizer_step"
+        if step_key in state_dict:
+            self._fused_step = int(round(float(state_dict.pop(step_key))))
+            self._fused_step_dev = None
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)

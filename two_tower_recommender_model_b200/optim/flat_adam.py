@@ -16,6 +16,8 @@ class FlatAdam(Optimizer):
                  betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8) -> None:
         params = [p for p in params]
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        if len(self.param_groups) != 1:
+            raise ValueError("FlatAdam updates ONE flat buffer with one (lr, betas, eps): give it a single parameter group")
         ps = [p for g in self.param_groups for p in g["params"]]
         if not ps:
             raise ValueError("FlatAdam got no parameters")
@@ -50,6 +52,33 @@ class FlatAdam(Optimizer):
             if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + off * 4:
                 p.grad = self.flat_grad[off:off + k].view(p.shape)
             off += k
+
+    def add_param_group(self, param_group) -> None:
+        if getattr(self, "param_groups", None):
+            raise ValueError("FlatAdam supports a single parameter group")
+        super().add_param_group(param_group)
+
+    # The moments and the step counter live in flat buffers outside ``Optimizer.state``; they ARE the optimizer
+    # state, so they travel in state_dict() (a resume that silently restarted Adam would not be a resume).
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["flat_adam"] = {"exp_avg": self.exp_avg.detach().clone(), "exp_avg_sq": self.exp_avg_sq.detach().clone(),
+                           "step": float(self.step_dev.item())}
+        return sd
+
+    def load_state_dict(self, state_dict) -> None:
+        state_dict = dict(state_dict)
+        flat = state_dict.pop("flat_adam", None)
+        super().load_state_dict(state_dict)
+        if len(self.param_groups) != 1:
+            raise ValueError("FlatAdam supports a single parameter group")
+        if flat is not None:
+            if flat["exp_avg"].numel() != self.exp_avg.numel():
+                raise ValueError("FlatAdam state does not match the parameters")
+            self.exp_avg.copy_(flat["exp_avg"])
+            self.exp_avg_sq.copy_(flat["exp_avg_sq"])
+            self.step_dev.fill_(float(flat["step"]))
+            self.step_count = int(flat["step"])
 
     @torch.no_grad()
     def step(self, closure: Any = None) -> None:
