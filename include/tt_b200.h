@@ -366,6 +366,11 @@ int tt_score_topk_f32(const float* queries, const float* items, int64_t num_quer
 /* Tensor-core variant (tcgen05 scoring, top-k fused into the TMEM epilogue): operands are the
  * bf16 copies made by tt_cast_f32_to_bf16; d <= 64, k <= 128.  Same ordering rule. */
 size_t tt_topk_bf16_workspace_bytes(int64_t num_queries, int64_t num_items, int64_t k);
+/* Tuning aid: per-role cycle counters of tt_score_topk_bf16 (sums over CTAs of clock64 deltas).  All zero unless
+ * the library was built with -DTT_TOPK_PROFILE.  [0] epilogue waits on scores, [1] on tcgen05.ld, [3] compaction,
+ * [4] epilogue total; [8] issuer waits on item tiles, [9] on free TMEM stages, [11] issuer total; [12] TMA
+ * producer waits on free smem stages, [13] producer total.  h_out is a HOST array of n <= 16 entries. */
+int tt_debug_read_counters(uint64_t* h_out, int32_t n, int32_t reset);
 int tt_score_topk_bf16(const void* queries_bf16, int64_t ldq, const void* items_bf16, int64_t ldi,
                        int64_t num_queries, int64_t num_items, int64_t d, int64_t k,
                        int64_t item_index_base, float* out_scores, int64_t* out_indices, void* ws,

@@ -32,7 +32,21 @@ def run(n_items, n_queries, d=64, k=100, kind="randn", reps=2):
         b.record()
         torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b))
-    return {"items": n_items, "queries": n_queries, "k": k, "d": d, "data": kind, "ms": round(best, 3),
+    prof = None
+    if os.environ.get("TT_TOPK_PROFILE"):
+        import ctypes
+        from two_tower_recommender_model_b200 import _native as N
+        buf = (ctypes.c_uint64 * 16)()
+        N.load().tt_debug_read_counters(buf, 16, 1)
+        index.search(queries, k, query_chunk=1 << 17)
+        torch.cuda.synchronize()
+        N.load().tt_debug_read_counters(buf, 16, 1)
+        c = list(buf)
+        ep, mm, tm = max(c[4], 1), max(c[11], 1), max(c[13], 1)
+        prof = {"epilogue": {"wait_scores": round(c[0] / ep, 3), "wait_tmem_ld": round(c[1] / ep, 3), "compaction": round(c[3] / ep, 3)},
+                "issuer": {"wait_items": round(c[8] / mm, 3), "wait_free_tmem": round(c[9] / mm, 3)},
+                "producer": {"wait_free_smem": round(c[12] / tm, 3)}, "issuer_clk": c[11], "epilogue_clk_per_warp": c[4]}
+    return {"profile": prof, "items": n_items, "queries": n_queries, "k": k, "d": d, "data": kind, "ms": round(best, 3),
             "queries_per_s": round(n_queries / best * 1e3, 1), "tflops": round(2.0 * n_queries * n_items * d / best / 1e9, 1),
             "top1_score_mean": float(s[:, 0].mean())}
 

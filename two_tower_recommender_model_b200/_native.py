@@ -116,6 +116,7 @@ SIGNATURES = {
                                                    _P, c_int64, c_int64, c_float, c_float, c_int32, _P, c_int64, _P, c_int64, _P, _P]),
     "tt_adam_flat":(c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, _P]),
     "tt_adam_flat_devstep": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, _P]),
+    "tt_debug_read_counters": (c_int32, [_P, c_int32, c_int32]),
     "tt_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "tt_topk_bf16_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "tt_score_topk_bf16": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_size_t, _P]),

@@ -173,36 +173,53 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int* __restrict__
 
 // ---------------------------------------------------------------------------
 // Tensor-core scoring (tcgen05) with the top-k fused into the epilogue.
-//   CTA = 256 queries (two 128-row tiles) x one contiguous item range.  The query tiles are RESIDENT IN TMEM
-//   (bf16 pairs, 32 columns each) and feed tcgen05.mma as the A operand from there (TS form): only the item tile
-//   is read from shared memory, 2 KB per 128x64x16 MMA = 64 B/clk, half of the shared-memory pipe (SS-form
-//   N=64 MMAs would need 192 B/clk and stall on it).  Item tiles of 128 rows stream through a 4-stage TMA ring
-//   and are used TWICE (one MMA group per query tile, M=128, N=2x64, K=64), which halves the L2 -> SM operand
-//   traffic per flop; scores land in a TMEM ring of 3 stages of 64 columns per query tile.  A stage goes back to the MMA issuer as soon as its 64 columns sit in
-//   the epilogue's registers (before they are processed), so the issuer runs up to two item tiles ahead.
-//   Epilogue: 8 warps (two per scheduler), thread = query row.  Per 32-score chunk a 3-input max tree (FMNMX3,
-//   ~0.5 instruction per score) gives four 8-score group maxima; only groups that beat the row's threshold are
-//   scanned.  Survivors are APPENDED to an unsorted per-row buffer (128 entries, global memory, L2 resident) --
-//   no sorted insertion.  The threshold is the row's k-th best score as of the last compaction, so it is stale
-//   by at most one buffer; the number of appends over a pass stays O(k log(n/k)).  When a buffer of the warp
-//   is about to run full the warp compacts all 32 rows cooperatively: bitonic sort of the 128 pending entries
-//   in registers (64-bit keys = ordered score | inverted index, so ties go to the lower index), bitonic merge
-//   with the row's sorted top-k list, write back, new threshold.  Same tie rule as the fp32 path.
+//   CTA = 256 queries (two 128-row tiles, resident in smem as bf16) x one contiguous item range.  Item tiles of
+//   128 rows stream through a 4-stage TMA ring and are used TWICE (one tcgen05.mma group per query tile,
+//   M=128, N=128, K=64), which halves the L2 -> SM operand traffic per flop; score tiles land in a TMEM ring of
+//   2 stages per query tile (4 x 128 columns).
+//   Warpgroup 0 = {TMA producer, MMA issuer}; warpgroups 1-2 = 8 epilogue warps (two per scheduler), thread =
+//   query row; setmaxnreg moves registers from warpgroup 0 to the epilogue.  An epilogue thread pulls ALL 128
+//   scores of its row into registers and hands the TMEM stage back BEFORE it looks at them, so the issuer refills
+//   the stage while the scores are filtered (one barrier round trip per 128 scores, and it overlaps the work).
+//   Filter: a 3-input max tree (FMNMX3, ~0.5 instruction per score) gives sixteen 8-score group maxima and the
+//   row maximum; one warp vote per tile; only groups that beat the row's threshold are scanned.  Survivors are
+//   APPENDED to an unsorted per-row buffer (256 entries, global memory, L2 resident) -- no sorted insertion.  The
+//   threshold is the row's k-th best score as of the last compaction, so it is stale by at most one buffer; the
+//   number of appends over a pass stays O(k log(n/k)).  When a buffer of the warp passes 96 entries the warp
+//   compacts all 32 rows cooperatively: bitonic sort of 128 pending entries in registers (64-bit keys = ordered
+//   score | inverted index, so ties go to the lower index), bitonic merge with the row's sorted top-k list, write
+//   back, new threshold.  Same tie rule as the fp32 path.
 // ---------------------------------------------------------------------------
 namespace tc {
 
-constexpr int kTcTkThreads = 320;   // warp 0: TMA, warp 1: MMA issuer, warps 2..9: epilogue
-constexpr int kTcTkNT = 128;        // items per tile
+// Per-role cycle accounting (build with -DTT_TOPK_PROFILE; read with tt_debug_read_counters): where the
+// epilogue warps, the MMA issuer and the TMA producer spend their time.  Compiled out otherwise.
+__device__ unsigned long long g_topk_prof[16];
+#ifdef TT_TOPK_PROFILE
+#define TT_PROF_DECL(n) long long n = 0
+#define TT_PROF_T0(t) const long long t = clock64()
+#define TT_PROF_ADD(acc, t) acc += clock64() - t
+#define TT_PROF_FLUSH(i, acc) atomicAdd(&g_topk_prof[i], (unsigned long long)(acc))
+#else
+#define TT_PROF_DECL(n)
+#define TT_PROF_T0(t)
+#define TT_PROF_ADD(acc, t)
+#define TT_PROF_FLUSH(i, acc)
+#endif
+
+constexpr int kTcTkThreads = 384;   // warpgroup 0: warp 0 TMA, warps 1-2 MMA issuers (one per query tile); warpgroups 1-2: epilogue
+constexpr int kTcTkNT = 128;        // items per tile = columns per TMEM stage
 constexpr int kTcTkQT = 2;          // query tiles (128 rows each) per CTA
-constexpr int kTcTkHalf = 64;        // columns per TMEM stage: the 128-item tile is scored as two N=64 MMA groups
-constexpr int kTcTkAcc = 3;         // TMEM stages (64 columns each) per query tile (2 x 3 x 64 = 384 columns)
-constexpr int kTcTkACol = kTcTkQT * kTcTkAcc * kTcTkHalf;   // the query tiles themselves live in TMEM from here (32 columns each)
-constexpr int kTcTkStages = 4;      // smem ring depth for item tiles
-constexpr int kTcTkPend = 128;      // pending-buffer entries per row
+constexpr int kTcTkAcc = 2;         // TMEM stages per query tile (2 x 2 x 128 = 512 columns)
+constexpr int kTcTkStages = 8;      // smem ring depth for item tiles (16 KB each): covers the L2 / HBM latency of the stream
+constexpr int kTcTkPend = 256;      // pending-buffer entries per row (a tile adds at most 128)
+constexpr int kTcTkTrig = 96;       // compact when a row of the warp holds more pending entries than this
 constexpr int kTcTkRows = 128 * kTcTkQT;
+constexpr int kTcTkRegsCtrl = 56, kTcTkRegsEpi = 224;   // setmaxnreg: 56 + 2 * 224 = 504 <= 3 * 168 (launch value)
+static_assert(kTcTkRegsCtrl + 2 * kTcTkRegsEpi <= 3 * ((65536 / kTcTkThreads) / 8 * 8), "setmaxnreg budget");
 
 __host__ __device__ inline size_t tc_topk_smem() {
-  return (size_t)kTcTkStages * kTcTkNT * 128 /*ring*/ + 1024 /*align*/ + 256 /*barriers*/;
+  return (size_t)kTcTkQT * 128 * 128 /*Q*/ + (size_t)kTcTkStages * kTcTkNT * 128 /*ring*/ + 1024 /*align*/ + 256 /*barriers*/;
 }
 
 // monotone map float -> uint32 (larger float <-> larger integer), and back
@@ -254,9 +271,87 @@ __device__ __forceinline__ void bitonic128_desc(unsigned long long (&key)[4], in
   }
 }
 
+struct RowState {
+  float thr;      // the row's k-th best score as of the last compaction (-inf until the list holds k entries)
+  int pcnt;       // pending (unsorted) entries
+  int lcnt;       // entries of the sorted list
+};
+
+// Merge every row's pending entries into its sorted top-k list (whole warp, one row at a time, 128 pending
+// entries per round).  final = true also writes the (-inf, -1) padding of short lists that the cross-split
+// merge expects.  One copy in the binary (noinline): the bitonic networks are ~5000 instructions, and inlined
+// at every call site they pushed the scoring loop out of the instruction cache.
+__device__ __noinline__ RowState compact_rows(RowState st, bool final, int wrow0, int Q, int k, int splits, int split, int lane,
+                                              float* __restrict__ cand_scores, int* __restrict__ cand_idx,
+                                              const float2* __restrict__ pend) {
+  float thr = st.thr;
+  int pcnt = st.pcnt, lcnt = st.lcnt;
+  __syncwarp();
+#pragma unroll 1
+  for (int r = 0; r < 32; ++r) {
+    const int c = __shfl_sync(0xffffffffu, pcnt, r);
+    const int lc = __shfl_sync(0xffffffffu, lcnt, r);
+    if (wrow0 + r >= Q) break;
+    if (c == 0 && !final) continue;
+    const int64_t slot = (int64_t)(wrow0 + r) * splits + split;
+    float* ls = cand_scores + slot * k;
+    int* li = cand_idx + slot * k;
+    unsigned long long key[4], lst[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = lane * 4 + i;
+      lst[i] = e < lc ? key_of(__ldcg(ls + e), __ldcg(li + e)) : 0ull;
+    }
+#pragma unroll 1
+    for (int base = 0; base < c; base += 128) {
+      const float4* pp = reinterpret_cast<const float4*>(pend + slot * kTcTkPend + base);
+      const float4 p01 = __ldcg(pp + lane * 2), p23 = __ldcg(pp + lane * 2 + 1);   // entries 4 lane .. 4 lane + 3
+      const int e = base + lane * 4;
+      key[0] = e + 0 < c ? key_of(p01.x, __float_as_int(p01.y)) : 0ull;
+      key[1] = e + 1 < c ? key_of(p01.z, __float_as_int(p01.w)) : 0ull;
+      key[2] = e + 2 < c ? key_of(p23.x, __float_as_int(p23.y)) : 0ull;
+      key[3] = e + 3 < c ? key_of(p23.z, __float_as_int(p23.w)) : 0ull;
+      bitonic128_desc<2>(key, lane);
+      // the list is sorted descending: max(new[E], list[127 - E]) is a bitonic sequence holding the best 128
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const unsigned long long o = __shfl_sync(0xffffffffu, lst[3 - i], 31 - lane);
+        key[i] = key[i] > o ? key[i] : o;
+      }
+      bitonic128_desc<128>(key, lane);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) lst[i] = key[i];
+    }
+    const int nc = min(lc + c, k);
+    float kth = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = lane * 4 + i;
+      const float sc = float_of_ord(static_cast<uint32_t>(lst[i] >> 32));
+      const int id = static_cast<int>(~static_cast<uint32_t>(lst[i]));
+      if (e < nc) { __stcg(ls + e, sc); __stcg(li + e, id); }
+      else if (final && e < k) { __stcg(ls + e, -INFINITY); __stcg(li + e, -1); }
+      if (e == k - 1) kth = sc;
+    }
+    kth = __shfl_sync(0xffffffffu, kth, (k - 1) >> 2);
+    if (lane == r) {
+      lcnt = nc;
+      pcnt = 0;
+      if (nc == k) thr = kth;
+    }
+  }
+  __syncwarp();
+  return RowState{thr, pcnt, lcnt};
+}
+
+template <int N>
+__device__ __forceinline__ void tk_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void tk_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 __global__ void __launch_bounds__(kTcTkThreads, 1)
-tc_score_topk_kernel(const __nv_bfloat16* __restrict__ queries, int ldq, int d, const __grid_constant__ CUtensorMap tmI,
-                     int Q, int N, int k, int items_per_split, float* __restrict__ cand_scores, int* __restrict__ cand_idx,
+tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmI, int Q, int N,
+                     int k, int items_per_split, float* __restrict__ cand_scores, int* __restrict__ cand_idx,
                      float2* __restrict__ pend) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -266,7 +361,9 @@ tc_score_topk_kernel(const __nv_bfloat16* __restrict__ queries, int ldq, int d, 
   uint64_t* acc_full = i_empty + kTcTkStages;          // [QT][Acc]
   uint64_t* acc_empty = acc_full + kTcTkQT * kTcTkAcc; // [QT][Acc]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kTcTkQT * kTcTkAcc);
-  uint8_t* sI = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars + 32) + 1023) & ~uintptr_t(1023));
+  volatile uint32_t* compact_epoch = tmem_slot + 1;   // bumped by a warp that must compact: all epilogue warps follow
+  uint8_t* sQ = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars + 32) + 1023) & ~uintptr_t(1023));
+  uint8_t* sI = sQ + kTcTkQT * 128 * 128;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kTcTkRows;
@@ -276,9 +373,11 @@ tc_score_topk_kernel(const __nv_bfloat16* __restrict__ queries, int ldq, int d, 
   const int T = n_end > n_begin ? (n_end - n_begin + kTcTkNT - 1) / kTcTkNT : 0;
 
   if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ);
     prefetch_tmap(&tmI);
-    mbar_init(q_full, kTcTkRows);          // every epilogue thread arrives once its query row sits in TMEM
-    for (int s = 0; s < kTcTkStages; ++s) { mbar_init(&i_full[s], 1); mbar_init(&i_empty[s], 1); }
+    mbar_init(q_full, 1);
+    *compact_epoch = 0;
+    for (int s = 0; s < kTcTkStages; ++s) { mbar_init(&i_full[s], 1); mbar_init(&i_empty[s], kTcTkQT); }
     for (int s = 0; s < kTcTkQT * kTcTkAcc; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
     fence_barrier_init();
   }
@@ -288,210 +387,185 @@ tc_score_topk_kernel(const __nv_bfloat16* __restrict__ queries, int ldq, int d, 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (elect_one()) {
-      for (int t = 0; t < T; ++t) {
-        const int s = t % kTcTkStages;
-        mbar_wait(&i_empty[s], ((t / kTcTkStages) & 1) ^ 1);
-        mbar_expect_tx(&i_full[s], kTcTkNT * 128);
-        tma_load_2d(sI + s * kTcTkNT * 128, &tmI, &i_full[s], 0, n_begin + t * kTcTkNT);
-      }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc = idesc_bf16_f32(128, kTcTkHalf);
-    if (elect_one()) {
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      for (int t = 0; t < T; ++t) {
-        const int s = t % kTcTkStages;
-        mbar_wait(&i_full[s], (t / kTcTkStages) & 1);
+  if (warp < 4) {
+    tk_setmaxnreg_dec<kTcTkRegsCtrl>();
+    if (warp == 0) {
+      if (elect_one()) {
+        TT_PROF_DECL(p_wait);
+        TT_PROF_T0(p_all);
+        mbar_expect_tx(q_full, kTcTkQT * 128 * 128);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int hs = (2 * t + h) % kTcTkAcc;
-          const uint32_t par = (((2 * t + h) / kTcTkAcc) & 1) ^ 1;
-          // item rows [64h, 64h + 64) of the tile: 64 rows x 128 B = 8 KB further into the stage
-          const uint64_t db = smem_desc_k_sw128(smem_u32(sI + s * kTcTkNT * 128 + h * kTcTkHalf * 128));
-#pragma unroll
-          for (int qt = 0; qt < kTcTkQT; ++qt) {
-            mbar_wait(&acc_empty[qt * kTcTkAcc + hs], par);
-            tc_fence_after();
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              mma_ts(tmem_base + (qt * kTcTkAcc + hs) * kTcTkHalf, tmem_base + kTcTkACol + qt * 32 + kk * 8, db + 2 * kk, idesc,
-                     kk != 0);
-            tc_commit(&acc_full[qt * kTcTkAcc + hs]);
-          }
+        for (int qt = 0; qt < kTcTkQT; ++qt) tma_load_2d(sQ + qt * 128 * 128, &tmQ, q_full, 0, q0 + qt * 128);
+        for (int t = 0; t < T; ++t) {
+          const int s = t % kTcTkStages;
+          TT_PROF_T0(p0);
+          mbar_wait(&i_empty[s], ((t / kTcTkStages) & 1) ^ 1);
+          TT_PROF_ADD(p_wait, p0);
+          mbar_expect_tx(&i_full[s], kTcTkNT * 128);
+          tma_load_2d(sI + s * kTcTkNT * 128, &tmI, &i_full[s], 0, n_begin + t * kTcTkNT);
         }
-        tc_commit(&i_empty[s]);
+        TT_PROF_FLUSH(12, p_wait);
+        TT_PROF_FLUSH(13, clock64() - p_all);
+      }
+    } else if (warp <= kTcTkQT) {
+      // one MMA issuer per query tile (warps 1 and 2): each waits only for ITS TMEM stages, so a query tile whose
+      // epilogue is busy (compaction) does not hold the other one back, and the serial wait -> issue -> commit
+      // chain of a single thread (about as long as the MMAs themselves) is split in two
+      constexpr uint32_t idesc = idesc_bf16_f32(128, kTcTkNT);
+      const int qt = warp - 1;
+      if (elect_one()) {
+        mbar_wait(q_full, 0);
+        TT_PROF_DECL(m_wi);
+        TT_PROF_DECL(m_we);
+        TT_PROF_T0(m_all);
+        const uint64_t da = smem_desc_k_sw128(smem_u32(sQ + qt * 128 * 128));
+        for (int t = 0; t < T; ++t) {
+          const int s = t % kTcTkStages, as = t % kTcTkAcc;
+          TT_PROF_T0(m0);
+          mbar_wait(&i_full[s], (t / kTcTkStages) & 1);
+          TT_PROF_ADD(m_wi, m0);
+          const uint64_t db = smem_desc_k_sw128(smem_u32(sI + s * kTcTkNT * 128));
+          TT_PROF_T0(m1);
+          mbar_wait(&acc_empty[qt * kTcTkAcc + as], ((t / kTcTkAcc) & 1) ^ 1);
+          TT_PROF_ADD(m_we, m1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_ss(tmem_base + (qt * kTcTkAcc + as) * kTcTkNT, da + 2 * kk, db + 2 * kk, idesc, kk != 0);
+          tc_commit(&acc_full[qt * kTcTkAcc + as]);
+          tc_commit(&i_empty[s]);          // the stage is free once BOTH issuers' MMAs on it are done (count 2)
+        }
+        if (qt == 0) {
+          TT_PROF_FLUSH(8, m_wi);
+          TT_PROF_FLUSH(9, m_we);
+          TT_PROF_FLUSH(11, clock64() - m_all);
+        }
       }
     }
   } else {
-    const int ew = warp - 2;                // 0..7
-    const int qt = ew >> 2;                 // query tile of this warp
+    tk_setmaxnreg_inc<kTcTkRegsEpi>();
+    const int qt = (warp - 4) >> 2;         // query tile of this warp
     const int qd = warp & 3;                // TMEM lane quarter this warp may read
-    const int r_in = qd * 32 + lane;
     const int wrow0 = q0 + qt * 128 + qd * 32;          // first query row of this warp
     const int qrow = wrow0 + lane;
     const bool row_ok = qrow < Q;
     const int64_t slot_me = (int64_t)qrow * gridDim.y + split;      // (query, split) slot
     float2* my_pend = pend + slot_me * kTcTkPend;     // unsorted (score, index bits) entries
-    {
-      // this thread's query row -> TMEM (A operand of every MMA of the CTA): 64 bf16 = 32 columns, zero beyond d / Q
-      uint32_t a[32];
-      const uint4* src = reinterpret_cast<const uint4*>(queries + (int64_t)qrow * ldq);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint4 x = make_uint4(0u, 0u, 0u, 0u);
-        if (row_ok && j * 8 < d) x = __ldg(src + j);
-        a[4 * j] = x.x; a[4 * j + 1] = x.y; a[4 * j + 2] = x.z; a[4 * j + 3] = x.w;
-      }
-      if (d & 7) {                                  // the pad elements of the last 16-byte group are not zero in memory
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          if (2 * c + 1 >= d) a[c] = 2 * c < d ? (a[c] & 0xffffu) : 0u;
-        }
-      }
-      const uint32_t tdst = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + kTcTkACol + qt * 32;
-      tmem_st16(tdst, reinterpret_cast<const uint32_t(&)[16]>(a[0]));
-      tmem_st16(tdst + 16, reinterpret_cast<const uint32_t(&)[16]>(a[16]));
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(q_full);
-    }
     float thr = row_ok ? -INFINITY : INFINITY;     // rows beyond Q never fire
     int pcnt = 0, lcnt = 0;
+    uint32_t seen_epoch = 0;
+    TT_PROF_DECL(e_wf);
+    TT_PROF_DECL(e_ld);
+    TT_PROF_DECL(e_cp);
 
-    // Merge every row's pending entries into its sorted top-k list (whole warp, one row at a time).
-    // final = true also writes the (-inf, -1) padding of short lists that the cross-split merge expects.
     auto compact = [&](bool final) {
-      __syncwarp();
-#pragma unroll 1
-      for (int r = 0; r < 32; ++r) {
-        const int c = __shfl_sync(0xffffffffu, pcnt, r);
-        const int lc = __shfl_sync(0xffffffffu, lcnt, r);
-        if (wrow0 + r >= Q) break;
-        if (c == 0 && !final) continue;
-        const int64_t slot = (int64_t)(wrow0 + r) * gridDim.y + split;
-        const float4* pp = reinterpret_cast<const float4*>(pend + slot * kTcTkPend);
-        float* ls = cand_scores + slot * k;
-        int* li = cand_idx + slot * k;
-        unsigned long long key[4], old[4];
-        {
-          const float4 p01 = __ldcg(pp + lane * 2), p23 = __ldcg(pp + lane * 2 + 1);   // entries 4 lane .. 4 lane + 3
-          const int e = lane * 4;
-          key[0] = e + 0 < c ? key_of(p01.x, __float_as_int(p01.y)) : 0ull;
-          key[1] = e + 1 < c ? key_of(p01.z, __float_as_int(p01.w)) : 0ull;
-          key[2] = e + 2 < c ? key_of(p23.x, __float_as_int(p23.y)) : 0ull;
-          key[3] = e + 3 < c ? key_of(p23.z, __float_as_int(p23.w)) : 0ull;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int e = lane * 4 + i;
-          old[i] = e < lc ? key_of(__ldcg(ls + e), __ldcg(li + e)) : 0ull;
-        }
-        bitonic128_desc<2>(key, lane);
-        // old list is sorted descending: max(new[E], old[127 - E]) is a bitonic sequence holding the best 128
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const unsigned long long o = __shfl_sync(0xffffffffu, old[3 - i], 31 - lane);
-          key[i] = key[i] > o ? key[i] : o;
-        }
-        bitonic128_desc<128>(key, lane);
-        const int nc = min(lc + c, k);
-        float kth = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int e = lane * 4 + i;
-          const float sc = float_of_ord(static_cast<uint32_t>(key[i] >> 32));
-          const int id = static_cast<int>(~static_cast<uint32_t>(key[i]));
-          if (e < nc) { __stcg(ls + e, sc); __stcg(li + e, id); }
-          else if (final && e < k) { __stcg(ls + e, -INFINITY); __stcg(li + e, -1); }
-          if (e == k - 1) kth = sc;
-        }
-        kth = __shfl_sync(0xffffffffu, kth, (k - 1) >> 2);
-        if (lane == r) {
-          lcnt = nc;
-          pcnt = 0;
-          if (nc == k) thr = kth;
-        }
-      }
-      __syncwarp();
+      TT_PROF_T0(c0);
+      const RowState ns = compact_rows(RowState{thr, pcnt, lcnt}, final, wrow0, Q, k, (int)gridDim.y, split, lane, cand_scores, cand_idx, pend);
+      thr = ns.thr; pcnt = ns.pcnt; lcnt = ns.lcnt;
+      TT_PROF_ADD(e_cp, c0);
     };
 
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + qt * kTcTkAcc * kTcTkHalf;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + qt * kTcTkAcc * kTcTkNT;
     uint64_t* my_full = acc_full + qt * kTcTkAcc;
     uint64_t* my_empty = acc_empty + qt * kTcTkAcc;
-
-    // One 32-score chunk: group maxima by a 3-input max tree; groups that beat the threshold are scanned.
-    auto process = [&](uint32_t(&v)[32], int n0) {
-      if (n0 + 32 > n_end) {                     // last (partial) tile: columns beyond the range do not exist
+    TT_PROF_T0(e_all);
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+      const int as = t % kTcTkAcc;
+      const int n0 = n_begin + t * kTcTkNT;
+      uint32_t v[128];
+      {
+        TT_PROF_T0(w0);
+        mbar_wait(&my_full[as], (t / kTcTkAcc) & 1);
+        TT_PROF_ADD(e_wf, w0);
+      }
+      tc_fence_after();
+      {
+        TT_PROF_T0(l0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
+        for (int c = 0; c < 4; ++c) tmem_ld32(trow + as * kTcTkNT + c * 32, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
+        tmem_ld_wait();
+        TT_PROF_ADD(e_ld, l0);
+      }
+      tc_fence_before();
+      mbar_arrive(&my_empty[as]);                // the whole row slice is in registers: hand the stage back
+      if (n0 + kTcTkNT > n_end) {                // last (partial) tile: columns beyond the range do not exist
+#pragma unroll
+        for (int j = 0; j < 128; ++j)
           if (n0 + j >= n_end) v[j] = __float_as_uint(-INFINITY);
       }
-      float m[4];
+      float m[16], qm[4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < 16; ++g) {
         const float* f = reinterpret_cast<const float*>(&v[g * 8]);
         const float a = fmaxf(fmaxf(f[0], f[1]), f[2]);
         const float b = fmaxf(fmaxf(f[3], f[4]), f[5]);
         m[g] = fmaxf(fmaxf(a, b), fmaxf(f[6], f[7]));
       }
-      const float top = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qm[i] = fmaxf(fmaxf(m[4 * i], m[4 * i + 1]), fmaxf(m[4 * i + 2], m[4 * i + 3]));
+      const float top = fmaxf(fmaxf(qm[0], qm[1]), fmaxf(qm[2], qm[3]));
       if (__any_sync(0xffffffffu, top > thr)) {
+        // usually one or two (lane, group) pairs of the warp fire: descend by warp-uniform votes (32-score quads,
+        // then 8-score groups) so that the groups nobody needs cost one vote, not a divergent branch each
+        bool uq[4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (m[g] > thr) {
-            const float* f = reinterpret_cast<const float*>(&v[g * 8]);
-            unsigned hit = 0;
+        for (int i = 0; i < 4; ++i) uq[i] = __any_sync(0xffffffffu, qm[i] > thr);     // four independent votes: they pipeline
 #pragma unroll
-            for (int j = 0; j < 8; ++j) hit |= (f[j] > thr ? 1u : 0u) << j;
-            if ((hit & (hit - 1)) == 0) {
-              // exactly one score of the group beats the threshold (the usual case): it is the group maximum
-              __stcg(my_pend + pcnt, make_float2(m[g], __int_as_float(n0 + g * 8 + (__ffs(hit) - 1))));
-              ++pcnt;
-            } else {
+        for (int i = 0; i < 4; ++i) {
+          if (!uq[i]) continue;
+          bool ug[4];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (hit & (1u << j)) {
-                  __stcg(my_pend + pcnt, make_float2(f[j], __int_as_float(n0 + g * 8 + j)));
-                  ++pcnt;
+          for (int g = 0; g < 4; ++g) ug[g] = __any_sync(0xffffffffu, m[4 * i + g] > thr);
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            const int g = 4 * i + gg;
+            if (!ug[gg]) continue;
+            if (m[g] > thr) {
+              const float* f = reinterpret_cast<const float*>(&v[g * 8]);
+              unsigned hit = 0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) hit |= (f[j] > thr ? 1u : 0u) << j;
+              if ((hit & (hit - 1)) == 0) {
+                // exactly one score of the group beats the threshold (the usual case): it is the group maximum
+                __stcg(my_pend + pcnt, make_float2(m[g], __int_as_float(n0 + g * 8 + (__ffs(hit) - 1))));
+                ++pcnt;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (hit & (1u << j)) {
+                    __stcg(my_pend + pcnt, make_float2(f[j], __int_as_float(n0 + g * 8 + j)));
+                    ++pcnt;
+                  }
                 }
               }
             }
           }
         }
-        if (__any_sync(0xffffffffu, pcnt > kTcTkPend - 32)) compact(false);
+        // A compaction takes as long as dozens of tiles and stalls the CTA's MMA pipeline (the stage this warp
+        // holds is not refilled).  All warps fill their buffers at the same rate, so make them compact TOGETHER:
+        // one stall per round instead of one per warp.  The warp that must compact bumps a shared epoch; every
+        // warp looks at the epoch whenever one of its rows took a candidate (in the regime where compactions
+        // matter that is nearly every tile; a tile without candidates pays nothing).
+        const bool must = __any_sync(0xffffffffu, pcnt > kTcTkTrig);
+        if (must && lane == 0) atomicAdd(const_cast<uint32_t*>(compact_epoch), 1u);
+        __syncwarp();
+        const uint32_t ep = *compact_epoch;
+        if (must || ep != seen_epoch) {
+          seen_epoch = ep;
+          compact(false);
+        }
       }
-    };
-    // 64-column stage hs of this query tile -> chunk pair; the flat chunk index ci walks 4 chunks per item tile
-    const int total_chunks = 4 * T;
-    uint32_t va[32], vb[32];
-    if (total_chunks > 0) {
-      mbar_wait(&my_full[0], 0);
-      tc_fence_after();
-      tmem_ld32(trow, va);
-    }
-#pragma unroll 1
-    for (int ci = 0; ci < total_chunks; ci += 2) {
-      const int half = ci >> 1;                         // 64-column half tile index = 2 t + h
-      const int hs = half % kTcTkAcc;
-      const int n0 = n_begin + half * kTcTkHalf;
-      tmem_ld_wait();                                   // chunk ci is in va
-      tmem_ld32(trow + hs * kTcTkHalf + 32, vb);
-      process(va, n0);
-      tmem_ld_wait();                                   // chunk ci + 1 is in vb: the whole stage is in registers
-      tc_fence_before();
-      mbar_arrive(&my_empty[hs]);
-      if (ci + 2 < total_chunks) {
-        const int nh = half + 1;
-        mbar_wait(&my_full[nh % kTcTkAcc], (nh / kTcTkAcc) & 1);
-        tc_fence_after();
-        tmem_ld32(trow + (nh % kTcTkAcc) * kTcTkHalf, va);
-      }
-      process(vb, n0 + 32);
     }
     compact(true);
+#ifdef TT_TOPK_PROFILE
+    if (lane == 0) {
+      TT_PROF_FLUSH(0, e_wf);
+      TT_PROF_FLUSH(1, e_ld);
+      TT_PROF_FLUSH(3, e_cp);
+      TT_PROF_FLUSH(4, clock64() - e_all);
+    }
+#endif
     tc_fence_before();
   }
   __syncthreads();
@@ -580,6 +654,20 @@ static void tc_topk_plan(int64_t Q, int64_t N, int64_t* splits_out, int64_t* per
   *per_out = per > 0 ? per : 128;
 }
 
+int tt_debug_read_counters(uint64_t* h_out, int32_t n, int32_t reset) {
+  TT_CHECK_ARG(h_out && n > 0 && n <= 16, "debug_read_counters: bad arguments");
+  unsigned long long tmp[16];
+  cudaError_t e = cudaMemcpyFromSymbol(tmp, tc::g_topk_prof, sizeof(tmp));
+  if (e != cudaSuccess) return fail(TT_ERR_CUDA, "debug_read_counters: %s", cudaGetErrorString(e));
+  for (int i = 0; i < n; ++i) h_out[i] = tmp[i];
+  if (reset) {
+    memset(tmp, 0, sizeof(tmp));
+    e = cudaMemcpyToSymbol(tc::g_topk_prof, tmp, sizeof(tmp));
+    if (e != cudaSuccess) return fail(TT_ERR_CUDA, "debug_read_counters: %s", cudaGetErrorString(e));
+  }
+  return TT_OK;
+}
+
 size_t tt_topk_bf16_workspace_bytes(int64_t Q, int64_t N, int64_t k) {
   int64_t splits, per;
   tc_topk_plan(Q, N > 0 ? N : 1, &splits, &per);
@@ -606,10 +694,10 @@ int tt_score_topk_bf16(const void* queries_bf16, int64_t ldq, const void* items_
   int* ci = w.take<int>((size_t)Q * splits * k);
   float2* pend = w.take<float2>((size_t)Q * splits * tc::kTcTkPend);
   if (!cs || !ci || !pend) return fail(TT_ERR_WORKSPACE, "score_topk_bf16: workspace too small");
-  TT_CHECK_ARG(ldq % 8 == 0 && (reinterpret_cast<uintptr_t>(queries_bf16) & 15) == 0,
-               "score_topk_bf16: query rows must be 16-byte aligned (pitch a multiple of 8)");
-  CUtensorMap ti;
-  int rc = tc::make_tmap_bf16_2d(&ti, items_bf16, N, d, ldi, tc::kTcTkNT);
+  CUtensorMap tq, ti;
+  int rc = tc::make_tmap_bf16_2d(&tq, queries_bf16, Q, d, ldq, 128);
+  if (rc) return rc;
+  rc = tc::make_tmap_bf16_2d(&ti, items_bf16, N, d, ldi, tc::kTcTkNT);
   if (rc) return rc;
   const size_t smem = tc::tc_topk_smem();
   dim3 grid((unsigned)qtiles, (unsigned)splits);
@@ -619,8 +707,7 @@ int tt_score_topk_bf16(const void* queries_bf16, int64_t ldq, const void* items_
     if (e != cudaSuccess) { cudaGetLastError(); return fail(TT_ERR_CUDA, "score_topk_bf16 smem attr (%zu B): %s", smem, cudaGetErrorString(e)); }
     attr_set = true;
   }
-  tc::tc_score_topk_kernel<<<grid, tc::kTcTkThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(queries_bf16), (int)ldq, (int)d, ti,
-                                                                 (int)Q, (int)N, (int)k, (int)per, cs, ci, pend);
+  tc::tc_score_topk_kernel<<<grid, tc::kTcTkThreads, smem, s>>>(tq, ti, (int)Q, (int)N, (int)k, (int)per, cs, ci, pend);
   TT_CHECK_LAUNCH("tc_score_topk");
   topk_merge_kernel<<<(unsigned)((Q + 7) / 8), kTkThreads, 0, s>>>(cs, ci, (int)Q, (int)splits, (int)k, item_index_base,
                                                                  out_scores, out_indices);
