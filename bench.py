@@ -5,17 +5,22 @@ lookup HBM GB/s and the dominant kernel's roofline.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (N=1): BASELINE.json configs[1] on ONE GPU -- two 10M-row x 64 fp32 tables
-(user_id / product_id, 5.12 GB, far larger than the 126 MB L2, uniform random ids, so no L2
-flush is needed between iterations), per-rank batch 65536, towers 64->128->64, in-batch
-softmax loss, row-wise Adagrad fused into the embedding backward, Adam on the towers.
-Synthetic ids, random-init weights (no network for datasets).
+Workload = BASELINE.json configs[1]: two 10M-row x 64 fp32 tables (user_id / product_id, 5.12 GB,
+far larger than the 126 MB L2, uniform random ids, so no L2 flush is needed between iterations),
+batch 65536, towers 64->128->64, in-batch softmax loss, row-wise Adagrad fused into the embedding
+backward, Adam on the towers.  Synthetic ids, random-init weights (no network for datasets).
+
+  N = 1 : the whole config on one GPU.
+  N > 1 : `value` is the config AS STATED -- GLOBAL batch 65536 (per-rank 65536/N, "strong" scaling),
+          tables sharded table-wise; the same with row-wise sharding and the weak-scaling run
+          (per-rank batch 65536) are timed beside it (`strong_row_wise`, `weak`).  Before anything is
+          timed the sharded path is CHECKED: 3 train steps of the same sharded module / exchange mode
+          on small tables against an unsharded replica on rank 0 (`parity`; rc 4 on failure).
 
 One "step" = forward + backward + both optimizers on one batch.
   value : samples/s with the batch already resident in HBM (max over ranks, CUDA events).
-  e2e   : the same through the public API (TrainPipelineSparseDist.progress): every step
-          copies that step's raw id columns + labels from pinned host memory, builds the
-          KeyedJaggedTensor on the device, trains, and reads the loss back to the host.
+  e2e   : the same through the public API: every step copies that step's raw id columns + labels from
+          pinned host memory, builds the KeyedJaggedTensor on the device, trains, and reads the loss back.
   roofline / kernels : per-kernel CUDA-event times from a second, instrumented pass.
   cpu_baseline : the oracle port of the reference's CPU path on this box's host cores.
 """
@@ -37,6 +42,7 @@ import torch  # noqa: E402
 CAT = ["user_id", "product_id"]
 CFG2 = dict(rows=[10_000_000, 10_000_000], dim=64, layers=[128, 64], batch=65536, loss="in_batch_softmax",
             sparse_lr=0.01, dense_lr=0.001)
+CFG1 = dict(rows=[200_000, 50_000], dim=64, layers=[128, 64], batch=1024, loss="bce", sparse_lr=0.01, dense_lr=0.001)
 
 
 def peaks():
@@ -46,6 +52,18 @@ def peaks():
             d = json.load(f)
         return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+def measured_traffic(kernel_key):
+    """DRAM bytes per launch from the committed ncu capture (profiles/r02_dram_traffic.json, written by
+    tools/ncu_traffic.py from an `ncu --set full` report); None when no capture exists for the key."""
+    p = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    e = d.get(kernel_key)
+    return (e["dram_bytes"], "profiles/r02_dram_traffic.json:" + kernel_key) if e else (None, None)
 
 
 class ClockSampler:
@@ -58,7 +76,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -83,30 +101,42 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- ours
-def build_model(cfg, dev):
+def build_model(cfg, dev, sharding=None, exchange="peer", fused_sparse=True, dense_opt="flat_adam"):
+    """The reference's init sequence (03_model_training.py:770-829) against this package."""
     from torch.distributed.optim import _apply_optimizer_in_backward as apply_optimizer_in_backward
+    import torch.distributed as dist
     import two_tower_recommender_model_b200 as tt
+    from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
     eb = [tt.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=cfg["dim"], num_embeddings=cfg["rows"][i], feature_names=[c])
           for i, c in enumerate(CAT)]
     ebc = tt.EmbeddingBagCollection(tables=eb, device=torch.device("meta"))
-    task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, cfg["layers"], device=dev, precision=cfg.get("precision", "bf16")), loss=cfg["loss"], precision=cfg.get("precision", "bf16"))
-    apply_optimizer_in_backward(tt.RowWiseAdagrad, task.two_tower.ebc.parameters(), {"lr": cfg["sparse_lr"]})
-    peer = cfg.get("exchange", "nccl") == "peer" and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
-    plan = None
-    if peer and os.environ.get("TT_BENCH_SHARDING") and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-        from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints   # diagnostics: force a sharding type
-        cons = {f"t_{c}": ParameterConstraints(sharding_types=[os.environ["TT_BENCH_SHARDING"]]) for c in CAT}
-        plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=torch.distributed.get_world_size()), constraints=cons
-                                           ).collective_plan(task, tt.get_default_sharders(), torch.distributed.GroupMember.WORLD)
-    if not peer and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-        # the NCCL exchange path is benchmarked table-wise (its row-wise input dist needs a host sync per step)
-        from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
-        cons = {f"t_{c}": ParameterConstraints(sharding_types=["table_wise"]) for c in CAT}
-        plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=torch.distributed.get_world_size()), constraints=cons
-                                           ).collective_plan(task, tt.get_default_sharders(), torch.distributed.GroupMember.WORLD)
-    model = tt.DistributedModelParallel(module=task, device=dev, plan=plan, sharding_kwargs={"peer_exchange": True} if peer else None)
-    opt = tt.KeyedOptimizerWrapper(dict(model.named_parameters()), lambda p: tt.FlatAdam(p, lr=cfg["dense_lr"]))
+    prec = cfg.get("precision", "bf16")
+    task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, cfg["layers"], device=dev, precision=prec), loss=cfg["loss"], precision=prec)
+    if fused_sparse:
+        apply_optimizer_in_backward(tt.RowWiseAdagrad, task.two_tower.ebc.parameters(), {"lr": cfg["sparse_lr"]})
+    multi = dist.is_initialized() and dist.get_world_size() > 1
+    plan, kw = None, None
+    if multi:
+        W = dist.get_world_size()
+        cons = None
+        if sharding is not None:
+            cons = {f"t_{c}": ParameterConstraints(sharding_types=[sharding]) for c in CAT}
+        plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=W), constraints=cons
+                                           ).collective_plan(task, tt.get_default_sharders(), dist.GroupMember.WORLD)
+        kw = {"peer_exchange": True} if exchange == "peer" else None
+    model = tt.DistributedModelParallel(module=task, device=dev, plan=plan, sharding_kwargs=kw)
+    if dense_opt == "flat_adam":
+        opt = tt.KeyedOptimizerWrapper(dict(model.named_parameters()), lambda p: tt.FlatAdam(p, lr=cfg["dense_lr"]))
+    else:
+        opt = tt.KeyedOptimizerWrapper(dict(model.named_parameters()), lambda p: torch.optim.SGD(p, lr=cfg["dense_lr"]))
     return model, opt
+
+
+def plan_kinds(model):
+    try:
+        return sorted({ps.sharding_type for tables in model._plan.plan.values() for ps in tables.values()})
+    except Exception:
+        return None
 
 
 class RawBatch:
@@ -128,50 +158,128 @@ class RawBatch:
         return tt.Batch(dense_features=torch.zeros(1, device=device), sparse_features=kjt, labels=labels)
 
 
-def make_raw_batches(n, cfg, seed, rows_dev):
+def make_raw_batches(n, cfg, seed, rows_dev, batch=None):
     g = torch.Generator().manual_seed(seed)
+    B = batch or cfg["batch"]
     out = []
     for _ in range(n):
-        ids = torch.stack([torch.randint(1, r, (cfg["batch"],), generator=g) for r in cfg["rows"]]).pin_memory()
-        labels = torch.randint(0, 2, (cfg["batch"],), generator=g, dtype=torch.int32).pin_memory()
+        ids = torch.stack([torch.randint(1, r, (B,), generator=g) for r in cfg["rows"]]).pin_memory()
+        labels = torch.randint(0, 2, (B,), generator=g, dtype=torch.int32).pin_memory()
         out.append(RawBatch(ids, labels, rows_dev))
     return out
 
 
-def algorithmic_bytes(cfg, uniq_per_table, world=1):
-    """SURVEY.md 8(d) conventions: 8-byte ids, 4-byte offsets, each gathered row once, each
-    unique updated row one read + one write of weights and state.  world > 1: table-wise (2 ranks, 2
-    tables) rank 0 owns ONE table and looks up the GLOBAL batch of its feature; row-wise (more ranks than
-    tables) every rank scans the offsets of the global batch and serves ~1/world of the ids of BOTH tables.
-    Either way the rows a rank gathers / updates add up to one per-rank batch per table."""
+def algorithmic_bytes(cfg, B, uniq_per_table):
+    """SURVEY.md 8(d) conventions: 8-byte ids, 4-byte offsets, each gathered row once, each unique updated row
+    one read + one write of weights and state.  Per rank the rows gathered / updated add up to one per-rank
+    batch per table whatever the sharding (table-wise: an owner looks up the global batch of ITS table)."""
     D, L, F = cfg["dim"], 1, len(cfg["rows"])
-    B = cfg["batch"]
-    scan = 4 * B * F * (world if world > F else 1)          # offsets of every bag this rank walks over
-    fwd = F * (B * L * (8 + 4 * D) + 4 * B * D) + scan
-    bwd = sum(4 * B * D + 8 * B * L + u * (8 * D + 8) for u in uniq_per_table[:F]) + scan
+    fwd = F * (B * L * (8 + 4 * D) + 4 * B + 4 * B * D)
+    bwd = sum(4 * B * D + 8 * B * L + u * (8 * D + 8) for u in uniq_per_table[:F])
     return fwd, bwd
 
 
-def run_ours(args):
+# ---- sharded-vs-unsharded parity, run by the driver's own N > 1 launches (the driver never runs pytest on > 1 GPU)
+def parity_check(world, rank, dev, sharding, exchange, steps=3):
+    """Trains `steps` steps of the SAME sharded module / exchange mode the timed run uses (small tables, in-batch
+    softmax with per-rank negatives, fused row-wise Adagrad, deterministic softmax backward) and, on rank 0, an
+    UNSHARDED replica of the same model fed every rank's batch: its table gradients are accumulated densely
+    (no fused optimizer), divided by the world size like the tower gradients (TorchRec's gradient division) and
+    applied with the row-wise Adagrad formula in plain torch.  Compared: every rank's loss at every step, the
+    gathered tables (ShardedTensor.gather, utils/model_training.py:161-182) and the tower weights at the end."""
+    import torch.distributed as dist
+    import two_tower_recommender_model_b200 as tt
+    small = dict(rows=[3001, 1777], dim=64, layers=[128, 64], batch=256, loss="in_batch_softmax", sparse_lr=0.05, dense_lr=0.05)
+    tt.functional.set_deterministic_softmax_backward(True)
+    try:
+        torch.manual_seed(1234)
+        model, opt = build_model(small, dev, sharding=sharding, exchange=exchange, dense_opt="sgd")
+        kinds = plan_kinds(model)
+        ref = None
+        # gather the sharded model's initial weights so that the unsharded replica starts from the same point
+        sd0 = model.module.two_tower.state_dict()
+        full0 = {}
+        from torch.distributed._shard.sharded_tensor import ShardedTensor
+        for k, t in sd0.items():
+            if isinstance(t, ShardedTensor):
+                out = torch.zeros(t.size(), device=dev) if rank == 0 else None
+                t.gather(0, out)
+                full0[k] = out
+            else:
+                full0[k] = t.detach().clone()
+        if rank == 0:
+            eb = [tt.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=small["dim"], num_embeddings=small["rows"][i], feature_names=[c])
+                  for i, c in enumerate(CAT)]
+            ebc = tt.EmbeddingBagCollection(tables=eb, device=dev)
+            ref = tt.TwoTowerTrainTask(tt.TwoTower(ebc, small["layers"], device=dev, precision="bf16"), loss=small["loss"], precision="bf16")
+            ref.two_tower.load_state_dict(full0)
+            state = {c: torch.zeros(small["rows"][i], device=dev) for i, c in enumerate(CAT)}
+        rows_dev = torch.tensor(small["rows"], dtype=torch.int64, device=dev)
+        B = small["batch"]
+        max_loss_err = 0.0
+        model.train()
+        for s in range(steps):
+            raws = [make_raw_batches(1, small, 7000 + 100 * s + r, rows_dev, B)[0] for r in range(world)]
+            opt.zero_grad()
+            loss, _ = model(raws[rank].to(dev))
+            loss.backward()
+            model.sync_dense_grads()
+            opt.step()
+            losses = [torch.zeros((), device=dev) for _ in range(world)]
+            dist.all_gather(losses, loss.detach())
+            if rank == 0:
+                dense = [p for n, p in ref.named_parameters() if "embedding_bags" not in n]
+                tabs = [ref.two_tower.ebc.embedding_bags[f"t_{c}"].weight for c in CAT]
+                for p in dense + tabs:
+                    p.grad = None
+                for r in range(world):
+                    l_r, _ = ref(raws[r].to(dev))
+                    l_r.backward()
+                    max_loss_err = max(max_loss_err, abs(float(l_r) - float(losses[r])))
+                with torch.no_grad():
+                    for p in dense:
+                        p -= small["dense_lr"] * p.grad / world
+                    for c, w in zip(CAT, tabs):
+                        g = w.grad / world                                   # gradient division (comm_ops default)
+                        state[c] += g.pow(2).mean(dim=1)
+                        w -= small["sparse_lr"] * g / (state[c].sqrt() + 1e-10).unsqueeze(1)
+        sd = model.module.two_tower.state_dict()
+        max_w_err, max_w = 0.0, 0.0
+        for k, t in sd.items():
+            if isinstance(t, ShardedTensor):
+                out = torch.zeros(t.size(), device=dev) if rank == 0 else None
+                t.gather(0, out)
+            else:
+                out = t
+            if rank == 0:
+                want = ref.two_tower.state_dict()[k]
+                max_w_err = max(max_w_err, float((out - want).abs().max()))
+                max_w = max(max_w, float(want.abs().max()))
+        res = {"mode": f"{'+'.join(kinds or [])}/{exchange}", "world": world, "steps": steps, "batch_per_rank": B,
+               "rows": small["rows"], "max_abs_err_loss": max_loss_err, "max_abs_err_weights": max_w_err,
+               "weights_max_abs": max_w, "tol_loss": 2e-4, "tol_weights": 2e-4,
+               "reference": "unsharded replica on rank 0 (same kernels, dense table gradients / world, row-wise Adagrad in torch)"}
+        ok = torch.tensor([1 if (rank != 0 or (max_loss_err <= 2e-4 and max_w_err <= 2e-4)) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        res["ok"] = bool(ok.item())
+        del model, opt, ref
+        torch.cuda.empty_cache()
+        return res
+    finally:
+        tt.functional.set_deterministic_softmax_backward(False)
+
+
+def time_block(cfg, B, dev, rank, world, local, args, sharding, exchange, lib, with_kernels):
+    """Builds the model for one (per-rank batch, sharding) point, captures the step as a CUDA graph and times the
+    device-resident and the end-to-end loops.  Returns a dict (max over ranks applied by the caller)."""
     import torch.distributed as dist
     import two_tower_recommender_model_b200 as tt
     from two_tower_recommender_model_b200 import _native as N
-
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    cfg = dict(CFG2)
-    cfg["exchange"] = args.exchange
-    lib = N.load()
-    model, opt = build_model(cfg, dev)
+    model, opt = build_model(cfg, dev, sharding=sharding, exchange=exchange)
     model.train()
     rows_dev = torch.tensor(cfg["rows"], dtype=torch.int64, device=dev)
     nb = 4
-    raw = make_raw_batches(nb, cfg, 1234 + rank, rows_dev)
+    raw = make_raw_batches(nb, cfg, 1234 + rank, rows_dev, B)
     resident = [b.to(dev) for b in raw]
     torch.cuda.synchronize()
 
@@ -191,12 +299,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     use_graph = not args.no_graph
-    graph_step = None
     launches_per_step = None
+    graph_step = None
     if use_graph:
-        # single GPU: the whole step (device KJT build, lookup, towers, loss, backward + fused update,
-        # Adam) is one CUDA graph; warm-up calls run eagerly on real batches, the 4th call captures
-        graph_step = tt.CudaGraphTrainStep(model, opt, CAT, cfg["rows"], cfg["batch"], dev, warmup_steps=3)
+        graph_step = tt.CudaGraphTrainStep(model, opt, CAT, cfg["rows"], B, dev, warmup_steps=3)
         dev_raw = [(b.ids.to(dev), b.labels.to(dev)) for b in raw]
         for i in range(3):
             graph_step(*dev_raw[i % nb])
@@ -205,7 +311,6 @@ def run_ours(args):
         launches_per_step = int(lib.tt_kernel_launch_count() - l_before)
         torch.cuda.synchronize()
 
-    # ---- value: inputs resident in HBM
     for i in range(args.warmup):
         graph_step(*dev_raw[i % nb]) if use_graph else step(resident[i % nb])
     barrier()
@@ -222,7 +327,6 @@ def run_ours(args):
     launches = launches_per_step * args.steps if use_graph else lib.tt_kernel_launch_count() - l0
     ms_value = e0.elapsed_time(e1) / args.steps
 
-    # ---- e2e: pinned host -> device -> step -> loss to host
     total = args.warmup + args.steps
     if use_graph:
         e2e_api = "CudaGraphTrainStep(ids_pinned, labels_pinned) + float(loss)"
@@ -247,32 +351,32 @@ def run_ours(args):
         t0.record()
         last = None
         for _ in range(args.steps):
-            last = float(pipe.progress(it)[0])  # .item(): device -> host read of the loss
+            last = float(pipe.progress(it)[0])
         t1.record()
         barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = t0.elapsed_time(t1) / args.steps
 
-    # ---- instrumented pass: per-library-call CUDA events
-    N.enable_timing(True)
-    for i in range(min(args.steps, 5)):
-        step(resident[i % nb])
-    torch.cuda.synchronize()
-    per_call = N.timing_summary()
-    N.enable_timing(False)
+    per_call = {}
+    if with_kernels:
+        N.enable_timing(True)
+        for i in range(min(args.steps, 5)):
+            step(resident[i % nb])
+        torch.cuda.synchronize()
+        per_call = N.timing_summary()
+        N.enable_timing(False)
 
-    # ---- EBC lookup alone (BASELINE's second metric): 40 back-to-back lookups over rotating batches, one event pair
-    # around the loop, so the figure is the kernel's duration and not one launch + event overhead (the lookup is a
-    # 20 us kernel at this size; tables are 5 GB of random rows, nothing is L2-resident between launches)
     ebc_only_ms = None
-    if world == 1:
+    if with_kernels and world == 1:
+        # EBC lookup alone (BASELINE's second metric): 40 back-to-back lookups over rotating batches, one event pair
+        # around the loop (the lookup is a ~15 us kernel; tables are 5 GB of random rows, nothing is L2-resident)
         from ctypes import byref
         ebc_mod = model.module.two_tower.ebc
         kj = [resident[i].sparse_features for i in range(nb)]
-        plan, total_dim = ebc_mod._build_plan(tuple(kj[0].keys()), cfg["batch"], with_state=False)   # built once: the loop is launches only
+        plan, total_dim = ebc_mod._build_plan(tuple(kj[0].keys()), B, with_state=False)
         vals = [k.values().contiguous() for k in kj]
         offs = [k.offsets().to(torch.int32).contiguous() for k in kj]
-        pooled = torch.empty(cfg["batch"], total_dim, dtype=torch.float32, device=dev)
+        pooled = torch.empty(B, total_dim, dtype=torch.float32, device=dev)
         sp = N.stream_ptr(dev)
         for i in range(4):
             N.call("tt_ebc_forward", byref(plan), N.ptr(vals[i % nb]), N.ptr(offs[i % nb]), N.ptr(pooled), sp)
@@ -289,13 +393,68 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_value, ms_e2e = t.tolist()
+    uniq = [int(torch.unique(resident[0].sparse_features[c].values()[:B]).numel()) for c in CAT]
+    out = {"ms_value": ms_value, "ms_e2e": ms_e2e, "launches": int(launches), "clocks": clocks, "per_call": per_call,
+           "ebc_only_ms": ebc_only_ms, "uniq": uniq, "last_loss": last, "e2e_api": e2e_api, "h2d": raw[0].nbytes(),
+           "sharding": plan_kinds(model) if world > 1 else None, "cuda_graph": bool(use_graph), "batch": B}
+    del model, opt, graph_step, resident, raw
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from two_tower_recommender_model_b200 import _native as N
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = dict(CFG2)
+    lib = N.load()
+    pk = peaks()
+    G = cfg["batch"]                     # configs[1]: batch 65536
+
+    parity = []
+    extra = {}
+    if world == 1:
+        main = time_block(cfg, G, dev, rank, world, local, args, None, None, lib, with_kernels=True)
+        workload = ("BASELINE configs[1] on 1 GPU: 2 tables 10M x 64 fp32, batch 65536, MLP 64-128-64, in-batch softmax, "
+                    "fused row-wise Adagrad, Adam")
+        scaling = "strong"
+    else:
+        if G % world != 0:
+            raise SystemExit("world size must divide 65536")
+        # sharded-path parity first, on exactly the (sharding, exchange) pairs that are timed below
+        for sh in ("table_wise", "row_wise"):
+            p = parity_check(world, rank, dev, sh, args.exchange)
+            parity.append(p)
+            if not p["ok"]:
+                if rank == 0:
+                    print(json.dumps({"metric": "two-tower train samples/s", "error": "sharded parity check failed", "parity": parity}))
+                leave(world, 4)
+        main = time_block(cfg, G // world, dev, rank, world, local, args, "table_wise", args.exchange, lib, with_kernels=True)
+        srw = time_block(cfg, G // world, dev, rank, world, local, args, "row_wise", args.exchange, lib, with_kernels=False)
+        weak = time_block(cfg, G, dev, rank, world, local, args, None, args.exchange, lib, with_kernels=False)
+        extra["strong_row_wise"] = {"value": round(G / (srw["ms_value"] * 1e-3), 1), "ms_per_step": round(srw["ms_value"], 4),
+                                    "e2e": round(G / (srw["ms_e2e"] * 1e-3), 1), "global_batch": G, "per_rank_batch": G // world,
+                                    "sharding": srw["sharding"]}
+        extra["weak"] = {"value": round(world * G / (weak["ms_value"] * 1e-3), 1), "ms_per_step": round(weak["ms_value"], 4),
+                         "e2e": round(world * G / (weak["ms_e2e"] * 1e-3), 1), "global_batch": G * world, "per_rank_batch": G,
+                         "sharding": weak["sharding"], "note": "per-rank batch fixed at 65536 (round 1's headline)"}
+        workload = ("BASELINE configs[1] on %d GPUs as stated: 2 tables 10M x 64 fp32 table-wise sharded, GLOBAL batch 65536 "
+                    "(per-rank %d), MLP 64-128-64, in-batch softmax (per-rank negatives), fused row-wise Adagrad, Adam" % (world, G // world))
+        scaling = "strong"
     if rank != 0:
         leave(world)
         return
-    pk = peaks()
-    B = cfg["batch"]
-    uniq = [int(torch.unique(resident[0].sparse_features[c].values()[:B]).numel()) for c in CAT]
-    fwd_bytes, bwd_bytes = algorithmic_bytes(cfg, uniq, world)
+
+    B = main["batch"]
+    per_call = main["per_call"]
+    fwd_bytes, bwd_bytes = algorithmic_bytes(cfg, B, main["uniq"])
     d_out = cfg["layers"][-1]
     logit_flops = 6.0 * B * B * d_out
     kernels = {}
@@ -315,79 +474,91 @@ def run_ours(args):
     roof = None
     if sm_ms > 0:
         ach = logit_flops / (sm_ms * 1e-3) / 1e12
+        traffic, traffic_src = measured_traffic("softmax_fwd_bwd_B%d_d%d" % (B, d_out))
         roof = {"kernel": "in-batch softmax: tc_softmax_fwd_kernel + tc_softmax_bwd_fused_kernel (tcgen05)", "bound": "tensor",
                 "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(ach / pk["tf_sustained"], 4),
-                # dram__bytes_read+write per step of the two launches, from the ncu --set full capture
-                # profiles/r01_ncu_softmax_final2_summary.txt (17.3 MB forward + 50.8 MB one-pass backward)
-                "traffic": 6.82e7, "peak_source": pk["source"] + " (sustained bf16)", "ms": round(sm_ms, 4),
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": pk["source"] + " (sustained bf16)", "ms": round(sm_ms, 4),
                 "flops_credited": "6*B*B*d (recomputation of S in the backward is not credited)",
                 "note": "at d=64 the forward is MUFU(ex2)-bound (1 ex2 per 64 MACs) and the one-pass backward is bound by shared-memory "
-                        "operand bandwidth of its N=64 tcgen05.mma (ncu: tc+lsu smem wavefronts ~90%); see DESIGN.md section 4"}
+                        "operand bandwidth of its N=64 tcgen05.mma; see DESIGN.md section 4"}
+    total_batch = G
     line = {
-        "metric": "two-tower train samples/s", "value": round(world * B / (ms_value * 1e-3), 1), "unit": "samples/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_value, 4),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": "two-tower train samples/s", "value": round(total_batch / (main["ms_value"] * 1e-3), 1), "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(main["ms_value"], 4),
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "bf16 tower + logits GEMMs (fp32 accumulate, fp32 master weights) + f32 embeddings/optimizers", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1] on %d GPU(s): 2 tables 10M x 64 fp32, per-rank batch 65536, MLP 64-128-64, "
-                               "in-batch softmax, fused row-wise Adagrad, Adam" % world,
-                   "per_rank_batch": B, "global_batch": B * world, "cuda_graph": bool(use_graph),
-                   "exchange": (cfg["exchange"] if world > 1 else None),
-                   "sharding": (None if world == 1 else ("row_wise" if (world > len(CAT) and cfg["exchange"] == "peer") else "table_wise")), "l2": "tables 5.12 GB >> 126 MB L2, random ids; no flush needed"},
-        "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(ms_e2e, 4),
-                "h2d_bytes_per_step": raw[0].nbytes(), "d2h_bytes_per_step": 4, "last_loss": last, "api": e2e_api},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
+        "config": {"workload": workload, "per_rank_batch": B, "global_batch": total_batch, "cuda_graph": main["cuda_graph"],
+                   "exchange": (args.exchange if world > 1 else None), "sharding": main["sharding"],
+                   "l2": "tables 5.12 GB >> 126 MB L2, random ids; no flush needed"},
+        "e2e": {"value": round(total_batch / (main["ms_e2e"] * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(main["ms_e2e"], 4),
+                "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": 4, "last_loss": main["last_loss"], "api": main["e2e_api"]},
+        "gpu_launches": main["launches"], "clocks": main["clocks"], "roofline": roof, "kernels": kernels,
         "calls_ms": {k: round(v["ms"], 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1]["ms"])},
         "ebc_lookup_gbs": kernels.get("tt_ebc_forward", kernels.get("tt_ebc_forward_peer", {})).get("achieved"),
     }
-    if ebc_only_ms:
-        line["ebc_lookup"] = {"gbs": round(fwd_bytes / (ebc_only_ms * 1e-3) / 1e9, 1), "us": round(ebc_only_ms * 1e3, 2), "peak_gbs": pk["hbm"],
-                              "frac": round(fwd_bytes / (ebc_only_ms * 1e-3) / 1e9 / pk["hbm"], 4), "bytes": int(fwd_bytes),
+    if parity:
+        line["parity"] = parity
+    line.update(extra)
+    if main["ebc_only_ms"]:
+        ms = main["ebc_only_ms"]
+        line["ebc_lookup"] = {"gbs": round(fwd_bytes / (ms * 1e-3) / 1e9, 1), "us": round(ms * 1e3, 2), "peak_gbs": pk["hbm"],
+                              "frac": round(fwd_bytes / (ms * 1e-3) / 1e9 / pk["hbm"], 4), "bytes": int(fwd_bytes),
                               "how": "40 back-to-back tt_ebc_forward launches over 4 rotating batches, CUDA events around the loop"}
         line["ebc_lookup_gbs"] = line["ebc_lookup"]["gbs"]
     if world == 1:
         line["retrieval"] = retrieval_probe(dev)
+        line["retrieval_large"] = retrieval_probe(dev, n_items=10_000_000, n_queries=131072)
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(cfg, steps=2, warmup=1)
+        line["cpu_baseline"] = cpu_baseline(cfg, steps=1, warmup=1)
+        line["cpu_baseline_cfg1"] = cpu_baseline_cfg1()
     print(json.dumps(line))
     leave(world)
 
 
-def leave(world):
+def leave(world, rc=0):
     """Multi-rank exit: the captured graphs hold NCCL kernels and tearing the communicator down under them can
     block, so flush and exit the process without the (purely cosmetic) process-group teardown."""
     sys.stdout.flush()
     sys.stderr.flush()
     if world > 1:
         torch.cuda.synchronize()
-        os._exit(0)
+        os._exit(rc)
+    if rc:
+        sys.exit(rc)
 
 
 def retrieval_probe(dev, n_items=2_000_000, n_queries=16384, d=64, k=100):
-    """Secondary number (BASELINE configs[4] shape, scaled to one GPU and a few hundred ms): top-100 by
-    dot product over a resident bf16 corpus, tcgen05 scoring with the top-k fused in the epilogue."""
+    """Secondary number (BASELINE configs[4] shape): top-100 by dot product over a resident bf16 corpus of
+    RANDOM-NORMAL vectors (trained-like: distinct scores, the candidate path is exercised), tcgen05 scoring
+    with the top-k fused in the epilogue.  The large call is one GPU's share of configs[4] on 8 GPUs."""
     import two_tower_recommender_model_b200 as tt
     g = torch.Generator(device=dev).manual_seed(7)
     items = torch.randn(n_items, d, device=dev, generator=g)
     queries = torch.randn(n_queries, d, device=dev, generator=g)
     index = tt.BruteForceIndex(items, precision="bf16")
+    del items
     index.search(queries[:1024], k)
-    index.search(queries, k)           # same shape as the timed call: workspace allocation / launch attributes settled
+    index.search(queries, k, query_chunk=1 << 17)           # same shape as the timed call: allocations settled
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    index.search(queries, k)
+    s, _ = index.search(queries, k, query_chunk=1 << 17)
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
+    tf = 2.0 * n_queries * n_items * d / (ms * 1e-3) / 1e12
+    pk = peaks()
     return {"queries_per_s": round(n_queries / (ms * 1e-3), 1), "ms": round(ms, 3), "items": n_items, "queries": n_queries,
-            "k": k, "d": d, "tflops": round(2.0 * n_queries * n_items * d / (ms * 1e-3) / 1e12, 1), "dtype": "bf16 scoring, f32 accumulate"}
+            "k": k, "d": d, "tflops": round(tf, 1), "frac_of_sustained_bf16_peak": round(tf / pk["tf_sustained"], 4),
+            "data": "randn", "top1_score_mean": round(float(s[:, 0].mean()), 3), "dtype": "bf16 scoring, f32 accumulate"}
 
 
 # ----------------------------------------------------------------------------- CPU baseline / reference arm
-def cpu_baseline(cfg, steps, warmup, sample_batch=8192):
-    """Oracle port of the reference's unsharded CPU path (dense [R,D] embedding gradient +
-    row-wise Adagrad over the whole table each step, as nn.EmbeddingBag + a grad hook do)."""
+def cpu_baseline(cfg, steps, warmup, sample_batch=None):
+    """Oracle port of the reference's unsharded CPU path (dense [R,D] embedding gradient + row-wise Adagrad over
+    the whole table each step, as nn.EmbeddingBag + a grad hook do) at the FULL configs[1] batch."""
     import oracle
     from oracle.ebc import TableSpec
     cores = os.cpu_count() or 1
@@ -396,7 +567,7 @@ def cpu_baseline(cfg, steps, warmup, sample_batch=8192):
     m = oracle.OracleTwoTower(specs, cfg["layers"], loss="softmax" if cfg["loss"] != "bce" else "bce",
                               sparse_lr=cfg["sparse_lr"], dense_lr=cfg["dense_lr"], seed=0)
     g = torch.Generator().manual_seed(0)
-    Bs = min(sample_batch, cfg["batch"])
+    Bs = min(sample_batch or cfg["batch"], cfg["batch"])
     times = []
     for i in range(warmup + steps):
         vals = torch.cat([torch.randint(1, r, (Bs,), generator=g) for r in cfg["rows"]])
@@ -409,7 +580,39 @@ def cpu_baseline(cfg, steps, warmup, sample_batch=8192):
     sec = sum(times) / len(times)
     return {"value": round(Bs / sec, 1), "unit": "samples/s", "cores": cores, "kind": "port", "ms_per_step": round(sec * 1e3, 2),
             "sample": f"{Bs} of the {cfg['batch']}-sample batch per step (in-batch negatives = {Bs}), full 10M-row tables, "
-                      f"{steps} timed steps after {warmup} warm-up"}
+                      f"{steps} timed step(s) after {warmup} warm-up"}
+
+
+def cpu_baseline_cfg1(steps=30, warmup=5):
+    """configs[0] (B 1024, 200k / 50k rows, BCE, CPU) -- the reference's own CPU-runnable case --
+    plus the separate timing of transform_to_torchrec_batch (utils/model_training.py:43-69), whose Python loop is a
+    large share of the reference's real step."""
+    import oracle
+    from oracle.ebc import TableSpec
+    cfg = CFG1
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    specs = [TableSpec(f"t_{c}", cfg["rows"][i], cfg["dim"], [c]) for i, c in enumerate(CAT)]
+    m = oracle.OracleTwoTower(specs, cfg["layers"], loss="bce", sparse_lr=cfg["sparse_lr"], dense_lr=cfg["dense_lr"], seed=0)
+    g = torch.Generator().manual_seed(1234)
+    B = cfg["batch"]
+    t_step, t_tr = [], []
+    for i in range(warmup + steps):
+        raw = {c: torch.randint(1, cfg["rows"][j], (B,), generator=g).tolist() for j, c in enumerate(CAT)}
+        raw["label"] = torch.randint(0, 2, (B,), generator=g).tolist()
+        t0 = time.perf_counter()
+        vals, lens, y = oracle.transform_to_torchrec_batch(raw, CAT, cfg["rows"])
+        t1 = time.perf_counter()
+        m.train_step(CAT, vals, lens, y)
+        t2 = time.perf_counter()
+        if i >= warmup:
+            t_tr.append(t1 - t0)
+            t_step.append(t2 - t1)
+    st, tr = sum(t_step) / len(t_step), sum(t_tr) / len(t_tr)
+    return {"value": round(B / (st + tr), 1), "unit": "samples/s", "cores": cores, "kind": "port", "batch": B,
+            "ms_per_step_model": round(st * 1e3, 3), "ms_per_step_transform_to_torchrec_batch": round(tr * 1e3, 3),
+            "sample": f"configs[0]: B={B}, tables {cfg['rows']} x {cfg['dim']}, BCE, {steps} timed steps after {warmup} warm-up, "
+                      "transform (Python loop of the reference) + train step"}
 
 
 def run_reference(args):
@@ -418,13 +621,20 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = dict(CFG2)
-    steps = max(1, min(args.steps, 3))
-    cb = cpu_baseline(cfg, steps=steps, warmup=1)
+    # the FULL configs[1] batch per step, as many steps as asked for but bounded to a few minutes of CPU time:
+    # one probe step sizes the run
+    probe = cpu_baseline(cfg, steps=1, warmup=0)
+    per_step = probe["ms_per_step"] * 1e-3
+    budget_s = float(os.environ.get("TT_REFERENCE_BUDGET_S", "175"))
+    steps = max(1, min(args.steps, int(budget_s / max(per_step, 1e-3))))
+    warmup = 0 if steps < args.steps else min(args.warmup, 1)
+    cb = cpu_baseline(cfg, steps=steps, warmup=warmup) if steps > 1 else probe
     line = {"impl": "reference", "metric": "two-tower train samples/s", "value": cb["value"], "unit": "samples/s",
-            "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1] (CPU port of the reference's unsharded TorchRec path; torchrec/fbgemm "
-                                   "are not installable here)", "per_rank_batch": cfg["batch"]},
+                                   "are not installable here)", "per_rank_batch": cfg["batch"], "global_batch": cfg["batch"],
+                       "steps_requested": args.steps, "steps_note": "bounded so that the CPU run ends within a few minutes"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -439,10 +649,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default=os.environ.get("TT_EXCHANGE", "peer"), choices=["nccl", "peer"],
-                    help="N>1: table-wise output exchange by NCCL all-to-all, or fused into the lookup kernels over NVLink peer memory")
+                    help="N>1: output exchange by NCCL all-to-all, or fused into the lookup kernels over NVLink peer memory")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly (N>1: through TrainPipelineSparseDist) instead of replaying a CUDA graph")
     args = ap.parse_args()
-    # a wedged collective / capture must not hold the box: the default run takes well under two minutes
+    # a wedged collective / capture must not hold the box: the default run takes a few minutes
     wd = threading.Timer(float(os.environ.get("TT_BENCH_WATCHDOG_S", "900")), lambda: (sys.stderr.write("bench.py: watchdog expired\n"), os._exit(3)))
     wd.daemon = True
     wd.start()

@@ -46,3 +46,44 @@ def adam_step(
     bc2 = 1.0 - beta2 ** step
     denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
     p.addcdiv_(m, denom, value=-lr / bc1)
+
+
+class _ChunkedInBatchSoftmax(torch.autograd.Function):
+    """Same loss and gradients as :func:`in_batch_softmax_loss`, computed over row chunks so that the
+    ``[B, B]`` logits never exist at once (at B = 65 536 they are 17 GB in fp32, and autograd would
+    keep several copies).  Used by the CPU baseline at BASELINE configs[1]'s full batch; checked
+    equal to the plain form in tests/test_oracle_golden.py."""
+
+    @staticmethod
+    def forward(ctx, q, c, temperature: float, chunk: int):
+        B = q.shape[0]
+        inv_t = 1.0 / temperature
+        dq = torch.empty_like(q)
+        dc = torch.zeros_like(c)
+        loss = torch.zeros((), dtype=torch.float64)
+        diag = torch.empty(B, dtype=q.dtype)
+        for s in range(0, B, chunk):
+            e = min(B, s + chunk)
+            logits = (q[s:e] @ c.t()) * inv_t                         # [chunk, B]
+            lse = torch.logsumexp(logits, dim=1)
+            d = logits[torch.arange(e - s), torch.arange(s, e)]
+            diag[s:e] = d
+            loss += (lse - d).double().sum()
+            p = torch.exp(logits - lse.unsqueeze(1))                  # softmax rows
+            p[torch.arange(e - s), torch.arange(s, e)] -= 1.0         # dL/dlogits * B
+            p *= inv_t / B
+            dq[s:e] = p @ c
+            dc += p.t() @ q[s:e]
+        ctx.save_for_backward(dq, dc)
+        ctx.mark_non_differentiable(diag)
+        return (loss / B).to(q.dtype), diag
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_diag):
+        dq, dc = ctx.saved_tensors
+        return dq * g_loss, dc * g_loss, None, None
+
+
+def in_batch_softmax_loss_chunked(q: torch.Tensor, c: torch.Tensor, temperature: float = 1.0,
+                                  chunk: int = 4096) -> Tuple[torch.Tensor, torch.Tensor]:
+    return _ChunkedInBatchSoftmax.apply(q, c, temperature, chunk)

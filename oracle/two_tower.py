@@ -134,6 +134,10 @@ class OracleTwoTower(nn.Module):
         if self.loss_kind == "bce":
             logits = (q * c).sum(dim=1).squeeze()
             return F.binary_cross_entropy_with_logits(logits, labels.float()), logits
+        if q.shape[0] > 16384:
+            # same loss / gradients, row-chunked: the [B, B] logits (17 GB at B = 65 536) never exist at once
+            from .dense import in_batch_softmax_loss_chunked
+            return in_batch_softmax_loss_chunked(q, c, self.temperature)
         s = (q @ c.t()) / self.temperature
         return F.cross_entropy(s, torch.arange(q.shape[0])), s.diagonal()
 

@@ -161,3 +161,20 @@ def test_retrieval_metrics_known_answer():
     import math
     assert abs(m["precision_at_4"] - 0.25) < 1e-9 and abs(m["recall_at_4"] - 0.5) < 1e-9
     assert abs(m["ndcg_at_4"] - (1 / math.log2(3)) / (1 + 1 / math.log2(3))) < 1e-9
+
+
+def test_chunked_in_batch_softmax_equals_plain():
+    """The row-chunked form the CPU baseline uses at B = 65 536 is the same function (loss and both gradients)."""
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(300, 16, generator=g, requires_grad=True)
+    c = torch.randn(300, 16, generator=g, requires_grad=True)
+    l0, d0 = oracle.in_batch_softmax_loss(q, c, 0.7)
+    (l0 * 1.5).backward()
+    gq, gc = q.grad.clone(), c.grad.clone()
+    q.grad = c.grad = None
+    l1, d1 = oracle.in_batch_softmax_loss_chunked(q, c, 0.7, chunk=64)
+    (l1 * 1.5).backward()
+    torch.testing.assert_close(l1, l0, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(d1, d0, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(q.grad, gq, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(c.grad, gc, rtol=1e-5, atol=1e-7)
