@@ -195,6 +195,16 @@ int tt_ebc_backward_fused_peer(const tt_ebc_plan* h_plan, const tt_sparse_optimi
                                const tt_peer_buffers* h_peer_grads, void* ws, size_t ws_bytes,
                                void* stream);
 
+/* dedup (north_star lists it among the bit-exact ops): the unique linearised (table,row) keys of a batch,
+ * ascending, with their counts and the inverse map -- torch.unique(sorted=True, return_inverse=True,
+ * return_counts=True) over key = row_base[slot] + id -- built from the same key construction and radix sort as
+ * the fused backward.  unique_keys / counts / inverse hold num_values entries (the first *num_unique of the first
+ * two are valid); inverse[p] = -1 for an id outside its table.  Exposed for the parity tests. */
+size_t tt_ebc_dedup_workspace_bytes(int64_t num_values);
+int tt_ebc_dedup(const tt_ebc_plan* h_plan, const int64_t* values, int64_t num_values, const int32_t* offsets,
+                 int64_t* unique_keys, int32_t* counts, int32_t* inverse, int32_t* num_unique /* device */,
+                 void* ws, size_t ws_bytes, void* stream);
+
 /* Stable LSD radix sort of (key, payload) pairs on keys < 2^key_bits; exposed
  * for the dedup parity tests.  Result lands in keys_out / vals_out. */
 size_t tt_sort_pairs_workspace_bytes(int64_t n);

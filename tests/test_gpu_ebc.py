@@ -278,3 +278,28 @@ def rows_before_unique(rows_before, ids, uniq):
     first = torch.full((int(ids.max()) + 1,), -1, dtype=torch.long, device=ids.device)
     first[ids] = torch.arange(ids.numel(), device=ids.device)
     return rows_before[first[uniq]]
+
+
+@pytest.mark.parametrize("rows,B,L,dup", [([2000, 500], 1024, 1, 0), ([50, 40], 4096, 4, 8), ([10_000_000, 10_000_000], 65536, 1, 0),
+                                          ([100, 90, 7], 129, 3, 0), ([33], 5, 0, 0)])
+def test_dedup_matches_torch_unique(cuda, rows, B, L, dup):
+    """north_star lists dedup among the BIT-EXACT ops: the unique (table,row) keys, their counts and the inverse
+    map produced by the fused backward's own key construction + radix sort (tt_ebc_dedup) must equal
+    oracle.dedup_rows (= torch.unique(sorted, return_inverse, return_counts)) on the linearised keys."""
+    import two_tower_recommender_model_b200 as tt
+    from two_tower_recommender_model_b200.functional import dedup_rows
+    keys = [f"f{i}" for i in range(len(rows))]
+    cfgs = [tt.EmbeddingBagConfig(name=f"t_f{i}", embedding_dim=4, num_embeddings=rows[i], feature_names=[keys[i]]) for i in range(len(rows))]
+    ebc = tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("meta"))        # no table memory needed: keys only
+    v, l = random_kjt(keys, rows, B, L, seed=B + L + len(rows), dup_pool=dup)
+    off = oracle.lengths_to_offsets(l).to(torch.int64)
+    base, acc = [], 0
+    for r in rows:
+        base.append(acc)
+        acc += r
+    lin = torch.cat([v[int(off[f * B]):int(off[(f + 1) * B])] + base[f] for f in range(len(rows))]) if v.numel() else v
+    want_u, want_inv, want_c = oracle.dedup_rows(lin)
+    for bag in ebc.embedding_bags.values():          # _build_plan reads data_ptr(): give the meta tables a dummy allocation
+        bag.weight = torch.nn.Parameter(torch.zeros(1, 4, device=cuda))
+    got_u, got_inv, got_c = dedup_rows(ebc, tt.KeyedJaggedTensor.from_lengths_sync(keys, v.to(cuda), l.to(cuda)))
+    assert torch.equal(got_u.cpu(), want_u) and torch.equal(got_c.cpu(), want_c) and torch.equal(got_inv.cpu(), want_inv)

@@ -281,3 +281,40 @@ def test_fused_towers_without_bias_and_unused_tower(cuda):
         torch.testing.assert_close(a[3][k], b[3][k], rtol=2e-2, atol=2e-2 * float(b[3][k].abs().max()))
     for k in (4, 6):                              # the unused tower: zero weight gradients (or none on the per-layer path)
         assert a[3][k] is None or float(a[3][k].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,i,h,o", [(1000, 64, 128, 64), (8192, 64, 128, 64), (777, 48, 96, 24)])
+def test_fused_towers_against_float64_emulation(cuda, B, i, h, o):
+    """tt_towers_forward_fused / tt_towers_backward_fused against a float64 emulation of the SAME pipeline
+    (x, h, dz2, dz1 rounded to bf16 where the kernels round them; ReLU gates from the rounded activations; fp32 y):
+    outputs, dx, dW1, dW2, db1, db2 of both towers.  This pins the fused kernels to an oracle, not to the
+    repo's own per-layer path.  Tolerance: relative Frobenius error 2e-3 on y, 1e-2 on gradients."""
+    from two_tower_recommender_model_b200.functional import FusedTowersTC
+    g = torch.Generator().manual_seed(3 * B + i)
+    pooled = torch.randn(B, 2 * i, generator=g) * 0.5
+    params = []
+    for t in range(2):
+        params += [torch.randn(h, i, generator=g) / i ** 0.5, torch.randn(h, generator=g) * 0.1,
+                   torch.randn(o, h, generator=g) / h ** 0.5, torch.randn(o, generator=g) * 0.1]
+    dys = [torch.randn(B, o, generator=g) for _ in range(2)]
+    bf = lambda t: t.float().bfloat16().double()
+    p = pooled.to(cuda).requires_grad_(True)
+    ps = [x.to(cuda).requires_grad_(True) for x in params]
+    ys = FusedTowersTC.apply(p, (0, i), i, *ps)[:2]
+    torch.autograd.backward(list(ys), [d.to(cuda) for d in dys])
+    rel = lambda a, b: float((a.double().cpu() - b).norm() / (b.norm() + 1e-30))
+    for t in range(2):
+        W1, b1, W2, b2 = params[4 * t: 4 * t + 4]
+        x = bf(pooled[:, t * i:(t + 1) * i])
+        hh = bf(torch.relu(x @ bf(W1).t() + b1.double()))
+        y = torch.relu(hh @ bf(W2).t() + b2.double())
+        dz2 = bf(dys[t].double() * (y > 0))
+        dW2, db2 = dz2.t() @ hh, dz2.sum(0)
+        dz1 = bf((dz2 @ bf(W2)) * (hh > 0))
+        dW1, db1 = dz1.t() @ x, dz1.sum(0)
+        dx = dz1 @ bf(W1)
+        assert rel(ys[t].detach(), y) < 2e-3, (t, rel(ys[t].detach(), y))
+        assert rel(p.grad[:, t * i:(t + 1) * i], dx) < 1e-2, (t, "dx", rel(p.grad[:, t * i:(t + 1) * i], dx))
+        for name, got, want in (("dW1", ps[4 * t].grad, dW1), ("db1", ps[4 * t + 1].grad, db1),
+                                ("dW2", ps[4 * t + 2].grad, dW2), ("db2", ps[4 * t + 3].grad, db2)):
+            assert rel(got, want) < 1e-2, (t, name, rel(got, want))

@@ -89,6 +89,8 @@ SIGNATURES = {
     "tt_ebc_backward_fused_peer": (c_int32, [POINTER(EbcPlan), POINTER(SparseOptimizer), _P, c_int64, _P, POINTER(PeerBuffers), _P, c_size_t, _P]),
     "tt_ebc_backward_workspace_bytes": (c_size_t, [c_int64]),
     "tt_ebc_backward_fused": (c_int32, [POINTER(EbcPlan), POINTER(SparseOptimizer), _P, c_int64, _P, _P, _P, c_size_t, _P]),
+    "tt_ebc_dedup_workspace_bytes": (c_size_t, [c_int64]),
+    "tt_ebc_dedup": (c_int32, [POINTER(EbcPlan), _P, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "tt_sort_pairs_workspace_bytes": (c_size_t, [c_int64]),
     "tt_sort_pairs_u32": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, _P, c_size_t, _P]),
     "tt_linear_forward_f32": (c_int32, [_P, c_int64, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P]),

@@ -70,6 +70,13 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* tota
 
 // Radix sort (radix_sort.cu).
 size_t sort_workspace_bytes(int64_t n);
+constexpr int kSortTileKeys = 2048;                  // keys per sort tile (= kSortTile)
+int sort_digit_bits(int key_bits);
+bool sort_uses_fused_path(int64_t n);                // small inputs: one kernel per pass, no scan kernels
+size_t sort_fused_hist_ints(int64_t n, int key_bits);
+int sort_pairs_u32_fused(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                         uint32_t* tmp_k, uint32_t* tmp_v, int64_t n, int key_bits, int32_t* tile_hists, bool prefilled0,
+                         cudaStream_t stream);
 int sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
                    uint32_t* vals_out, int64_t n, int key_bits, void* ws, size_t ws_bytes,
                    cudaStream_t stream);

@@ -23,6 +23,7 @@ struct Vec<4> {
   __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ void load_stream(const float* p) { v = ld_stream_f4(p); }
   __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void load_cg(const float* p) { v = __ldcg(reinterpret_cast<const float4*>(p)); }
   __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
   __device__ __forceinline__ void atomic_add(float* p) const { atomicAdd(reinterpret_cast<float4*>(p), v); }   // red.global.add.v4.f32
   __device__ __forceinline__ void add(const Vec& o) { v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w; }
@@ -43,6 +44,7 @@ struct Vec<1> {
   __device__ __forceinline__ void zero() { v = 0.f; }
   __device__ __forceinline__ void load_stream(const float* p) { v = __ldg(p); }
   __device__ __forceinline__ void load(const float* p) { v = *p; }
+  __device__ __forceinline__ void load_cg(const float* p) { v = __ldcg(p); }
   __device__ __forceinline__ void store(float* p) const { *p = v; }
   __device__ __forceinline__ void atomic_add(float* p) const { atomicAdd(p, v); }
   __device__ __forceinline__ void add(const Vec& o) { v += o.v; }
@@ -226,11 +228,15 @@ ebc_forward_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_consta
 // ---------------------------------------------------------------------------
 // backward: key construction
 // ---------------------------------------------------------------------------
+// hist0 != nullptr (small inputs, fused sort): the kernel also counts the first radix digit of every key into the
+// [tile][radix] matrix of the sort's first pass and parks the unused tail of an over-allocated values array on
+// the sentinel (extra CTAs beyond the bag tiles), so that neither a histogram nor a tail kernel is launched.
 __global__ void __launch_bounds__(kEbcThreads)
 ebc_backward_keys_kernel(const __grid_constant__ tt_ebc_plan plan, const int64_t* __restrict__ values,
                          const int32_t* __restrict__ offsets, uint32_t* __restrict__ keys,
-                         uint32_t* __restrict__ payload, int tiles_per_key,
-                         float* __restrict__ adam_step, float beta1, float beta2, float* __restrict__ adam_bc) {
+                         uint32_t* __restrict__ payload, int tiles_per_key, int64_t n,
+                         float* __restrict__ adam_step, float beta1, float beta2, float* __restrict__ adam_bc,
+                         int32_t* __restrict__ hist0, int radix_mask, int radix) {
   if (adam_step != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
     // device-side Adam step counter (no host-computed bias correction in the launch arguments)
     const float st = *adam_step + 1.0f;
@@ -238,9 +244,23 @@ ebc_backward_keys_kernel(const __grid_constant__ tt_ebc_plan plan, const int64_t
     adam_bc[0] = (float)(1.0 - pow((double)beta1, (double)st));
     adam_bc[1] = (float)(1.0 - pow((double)beta2, (double)st));
   }
+  const int B = plan.batch_size;
+  const uint32_t sentinel = (uint32_t)plan.total_rows;
+  const int bag_ctas = tiles_per_key * plan.num_kjt_keys;
+  if ((int)blockIdx.x >= bag_ctas) {
+    // values may be over-allocated (KeyedJaggedTensor.from_id_columns keeps capacity F*B and the live count on
+    // the device): park the unused tail on the sentinel
+    const int64_t live = offsets[(int64_t)plan.num_kjt_keys * B];
+    const int extra = gridDim.x - bag_ctas;
+    for (int64_t p = live + (int64_t)(blockIdx.x - bag_ctas) * kEbcThreads + threadIdx.x; p < n; p += (int64_t)extra * kEbcThreads) {
+      keys[p] = sentinel;
+      payload[p] = 0;
+      if (hist0 != nullptr) atomicAdd(&hist0[(p / kSortTileKeys) * radix + (sentinel & radix_mask)], 1);
+    }
+    return;
+  }
   const int f = blockIdx.x / tiles_per_key;  // KJT key index
   const int tile = blockIdx.x - f * tiles_per_key;
-  const int B = plan.batch_size;
   const int bag0 = tile * kBagsPerCta;
   const int nb = min(kBagsPerCta, B - bag0);
   if (nb <= 0) return;
@@ -250,27 +270,26 @@ ebc_backward_keys_kernel(const __grid_constant__ tt_ebc_plan plan, const int64_t
   __syncthreads();
   const int p0 = s_off[0], p1 = s_off[nb];
   const int slot = plan.slot_of_kjt[f];
-  const uint32_t sentinel = (uint32_t)plan.total_rows;
   for (int p = p0 + threadIdx.x; p < p1; p += kEbcThreads) {
-    if (slot < 0) {
-      keys[p] = sentinel;
-      payload[p] = 0;
-      continue;
+    uint32_t key = sentinel, pay = 0;
+    if (slot >= 0) {
+      int lo = 0, hi = nb;  // invariant: s_off[lo] <= p < s_off[hi]
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= p) lo = mid; else hi = mid;
+      }
+      const int64_t id = values[p];
+      const bool ok = (uint64_t)id < (uint64_t)plan.num_rows[slot];
+      key = ok ? (uint32_t)(plan.row_base[slot] + id) : sentinel;
+      pay = (uint32_t)(slot * B + bag0 + lo);
     }
-    int lo = 0, hi = nb;  // invariant: s_off[lo] <= p < s_off[hi]
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (s_off[mid] <= p) lo = mid; else hi = mid;
-    }
-    const int64_t id = values[p];
-    const bool ok = (uint64_t)id < (uint64_t)plan.num_rows[slot];
-    keys[p] = ok ? (uint32_t)(plan.row_base[slot] + id) : sentinel;
-    payload[p] = (uint32_t)(slot * B + bag0 + lo);
+    keys[p] = key;
+    payload[p] = pay;
+    if (hist0 != nullptr) atomicAdd(&hist0[(p / kSortTileKeys) * radix + (key & radix_mask)], 1);
   }
 }
 
-// values may be over-allocated (KeyedJaggedTensor.from_id_columns keeps capacity
-// F*B and the live count on the device): park the unused tail on the sentinel.
+// Generic path: park the unused tail (see above) with a separate small launch.
 __global__ void ebc_backward_tail_kernel(const int32_t* __restrict__ offsets, int64_t num_bags, int64_t n,
                                          uint32_t sentinel, uint32_t* __restrict__ keys,
                                          uint32_t* __restrict__ payload) {
@@ -380,13 +399,67 @@ __device__ __forceinline__ void apply_row(const tt_ebc_plan& plan, const tt_spar
 }
 
 template <int VEC, int G, int NV>
+__device__ __forceinline__ void update_body(const tt_ebc_plan& plan, const tt_sparse_optimizer& opt,
+                                            const uint32_t* __restrict__ keys, const uint32_t* __restrict__ payload,
+                                            int64_t n, const int32_t* __restrict__ offsets,
+                                            const float* __restrict__ grad_out, const tt_peer_buffers& peers,
+                                            float* __restrict__ hot, int hot_stride, const float* __restrict__ adam_bc,
+                                            int32_t* __restrict__ worklist);
+
+template <int VEC, int G, int NV>
 __global__ void __launch_bounds__(kEbcThreads, NV == 1 ? TT_EBC_UPD_MINB : 1)
 ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
                            const __grid_constant__ tt_sparse_optimizer opt,
                            const uint32_t* __restrict__ keys, const uint32_t* __restrict__ payload,
                            int64_t n, const int32_t* __restrict__ offsets,
                            const float* __restrict__ grad_out, const __grid_constant__ tt_peer_buffers peers,
-                           float* __restrict__ hot, int hot_stride, const float* __restrict__ adam_bc) {
+                           float* __restrict__ hot, int hot_stride, const float* __restrict__ adam_bc,
+                           int32_t* __restrict__ worklist /* null: ebc_backward_hot_apply_kernel finishes hot runs */) {
+  update_body<VEC, G, NV>(plan, opt, keys, payload, n, offsets, grad_out, peers, hot, hot_stride, adam_bc, worklist);
+  if (worklist == nullptr) return;
+  // Small inputs (one launch less): the LAST CTA to finish applies the optimizer for the (few) runs that crossed a
+  // segment boundary; their heads queued the boundary index in the worklist.  worklist[0] = ticket, [1] = count.
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&worklist[0], 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int count = *reinterpret_cast<volatile int32_t*>(&worklist[1]);
+  const int l = threadIdx.x % G;
+  unsigned mask = 0xffffffffu;
+  if constexpr (G < 32) mask = ((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G);
+  for (int w = threadIdx.x / G; w < count; w += kEbcThreads / G) {
+    const int64_t b = *reinterpret_cast<volatile int32_t*>(&worklist[2 + w]);
+    const uint32_t key = keys[b * kHotSeg];
+    int slot = 0;
+    for (int i = 0; i < plan.num_slots; ++i)
+      if ((int64_t)key >= plan.row_base[i] && (int64_t)key < plan.row_base[i] + plan.num_rows[i]) {
+        slot = i;
+        break;
+      }
+    const int64_t row = (int64_t)key - plan.row_base[slot];
+    const int units = plan.dim[slot] / VEC;
+    Vec<VEC> g[NV];
+    const float* acc = hot + b * (int64_t)hot_stride;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = l + v * G;
+      g[v].zero();
+      if (c < units) g[v].load_cg(acc + c * VEC);
+    }
+    apply_row<VEC, G, NV>(plan, opt, slot, row, l, mask, g, adam_bc);
+  }
+}
+
+template <int VEC, int G, int NV>
+__device__ __forceinline__ void update_body(const tt_ebc_plan& plan, const tt_sparse_optimizer& opt,
+                                            const uint32_t* __restrict__ keys, const uint32_t* __restrict__ payload,
+                                            int64_t n, const int32_t* __restrict__ offsets,
+                                            const float* __restrict__ grad_out, const tt_peer_buffers& peers,
+                                            float* __restrict__ hot, int hot_stride, const float* __restrict__ adam_bc,
+                                            int32_t* __restrict__ worklist) {
   constexpr int64_t hot_seg = kHotSeg;
   const int64_t gid = ((int64_t)blockIdx.x * kEbcThreads + threadIdx.x) / G;
   const int l = threadIdx.x % G;
@@ -546,6 +619,7 @@ ebc_backward_update_kernel(const __grid_constant__ tt_ebc_plan plan,
     const int c = l + v * G;
     if (c < units) g[v].atomic_add(acc + c * VEC);
   }
+  if (worklist != nullptr && head && l == 0) worklist[2 + atomicAdd(&worklist[1], 1)] = (int32_t)(h / hot_seg + 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -653,6 +727,37 @@ ebc_backward_hot_apply_kernel(const __grid_constant__ tt_ebc_plan plan, const __
   apply_row<VEC, G, NV>(plan, opt, slot, row, l, mask, g, adam_bc);
 }
 
+
+// ---------------------------------------------------------------------------
+// dedup (parity surface): unique linearised (table,row) keys of a batch, ascending, with counts and the inverse
+// map -- torch.unique(sorted=True, return_inverse=True, return_counts=True) -- built from the SAME key
+// construction and radix sort the fused backward uses.
+// ---------------------------------------------------------------------------
+__global__ void dedup_iota_kernel(uint32_t* __restrict__ payload, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    payload[i] = (uint32_t)i;
+}
+__global__ void dedup_flag_kernel(const uint32_t* __restrict__ skeys, int64_t n, uint32_t sentinel, int32_t* __restrict__ flag) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    flag[i] = (skeys[i] < sentinel && (i == 0 || skeys[i - 1] != skeys[i])) ? 1 : 0;
+}
+__global__ void dedup_emit_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ spos,
+                                  const int32_t* __restrict__ flag, const int32_t* __restrict__ excl, int64_t n,
+                                  uint32_t sentinel, int64_t* __restrict__ unique_keys, int32_t* __restrict__ counts,
+                                  int32_t* __restrict__ inverse) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t key = skeys[i];
+    if (key >= sentinel) {
+      inverse[spos[i]] = -1;                           // id outside its table: no row
+      continue;
+    }
+    const int u = excl[i] + flag[i] - 1;               // index of this key among the unique keys
+    if (flag[i]) unique_keys[u] = (int64_t)key;
+    atomicAdd(&counts[u], 1);
+    inverse[spos[i]] = u;
+  }
+}
+
 }  // namespace tt
 
 using namespace tt;
@@ -710,8 +815,8 @@ int tt_ebc_forward_peer(const tt_ebc_plan* h_plan, const int64_t* values, const 
 
 size_t tt_ebc_backward_workspace_bytes(int64_t n) {
   if (n < 1) n = 1;
-  return 4 * align_up((size_t)n * 4, 256) + sort_workspace_bytes(n) + 1024 + 256 /* adam bias corrections */ +
-         align_up((size_t)(n / kHotSeg + 2) * kHotRowFloats * 4, 256);
+  return 4 * align_up((size_t)n * 4, 256) + sort_workspace_bytes(n) + 2048 + 256 /* adam bias corrections */ +
+         2 * align_up((size_t)(n / kHotSeg + 2) * kHotRowFloats * 4, 256) + align_up((size_t)(n / kHotSeg + 8) * 4, 256);
 }
 
 static int ebc_backward_impl(const tt_ebc_plan* h_plan, const tt_sparse_optimizer* h_opt,
@@ -744,23 +849,53 @@ static int ebc_backward_impl(const tt_ebc_plan* h_plan, const tt_sparse_optimize
   uint32_t* payload = w.take<uint32_t>(n);
   uint32_t* skeys = w.take<uint32_t>(n);
   uint32_t* spayload = w.take<uint32_t>(n);
-  float* hot = w.take<float>((size_t)(n / kHotSeg + 2) * kHotRowFloats);
+  float* hot = w.take<float>((size_t)(n / kHotSeg + 2) * kHotRowFloats);   // generic path (the fused path carves its own, zeroed with the rest)
   float* adam_bc = w.take<float>(2);
   if (!keys || !payload || !skeys || !spayload || !hot || !adam_bc) return fail(TT_ERR_WORKSPACE, "ebc_backward: workspace too small");
 
-  const int tiles = (h_plan->batch_size + kBagsPerCta - 1) / kBagsPerCta;
-  ebc_backward_keys_kernel<<<(unsigned)(tiles * h_plan->num_kjt_keys), kEbcThreads, 0, s>>>(
-      *h_plan, values, offsets, keys, payload, tiles,
-      h_opt->kind == TT_OPT_ROWWISE_ADAM ? h_opt->step_dev : nullptr, h_opt->beta1, h_opt->beta2, adam_bc);
-  TT_CHECK_LAUNCH("ebc_backward_keys");
-  ebc_backward_tail_kernel<<<64, 256, 0, s>>>(offsets, (int64_t)h_plan->num_kjt_keys * h_plan->batch_size, n,
-                                              (uint32_t)h_plan->total_rows, keys, payload);
-  TT_CHECK_LAUNCH("ebc_backward_tail");
-
   int key_bits = 1;
   while (key_bits < 32 && ((uint64_t)h_plan->total_rows >> key_bits) != 0) ++key_bits;  // sentinel == total_rows
-  rc = sort_pairs_u32(keys, payload, skeys, spayload, n, key_bits, w.base + w.used, w.size - w.used, s);
-  if (rc) return rc;
+  const int tiles = (h_plan->batch_size + kBagsPerCta - 1) / kBagsPerCta;
+  const bool fused_sort = sort_uses_fused_path(n);
+  int max_dim0 = 0;
+  for (int sl = 0; sl < h_plan->num_slots; ++sl) max_dim0 = h_plan->dim[sl] > max_dim0 ? h_plan->dim[sl] : max_dim0;
+  const int64_t num_bounds0 = (n - 1) / kHotSeg;
+  int32_t* worklist = nullptr;
+  if (fused_sort) {
+    // Small inputs: 5 launches + 1 memset in all (keys+histogram+tail | one kernel per sort pass | update+hot apply).
+    // One memset clears the sort's digit-count matrices, the hot-row scratch and the worklist header together.
+    const size_t hist_ints = sort_fused_hist_ints(n, key_bits);
+    const size_t hot_floats = (size_t)(num_bounds0 + 1) * ((max_dim0 + 3) / 4 * 4);
+    Workspace wz(w.base + w.used, w.size - w.used);
+    int32_t* th = wz.take<int32_t>(hist_ints);
+    float* hot_z = wz.take<float>(hot_floats > 0 ? hot_floats : 1);
+    worklist = wz.take<int32_t>((size_t)num_bounds0 + 4);
+    uint32_t* tk = wz.take<uint32_t>(n);
+    uint32_t* tv = wz.take<uint32_t>(n);
+    if (!th || !hot_z || !worklist || !tk || !tv) return fail(TT_ERR_WORKSPACE, "ebc_backward: workspace too small");
+    hot = hot_z;
+    const size_t zero_bytes = reinterpret_cast<char*>(worklist) + 8 - reinterpret_cast<char*>(th);   // hists, scratch, ticket + count
+    cudaError_t e = cudaMemsetAsync(th, 0, zero_bytes, s);
+    if (e != cudaSuccess) return fail(TT_ERR_CUDA, "ebc_backward memset: %s", cudaGetErrorString(e));
+    const int bits = sort_digit_bits(key_bits);
+    ebc_backward_keys_kernel<<<(unsigned)(tiles * h_plan->num_kjt_keys + 16), kEbcThreads, 0, s>>>(
+        *h_plan, values, offsets, keys, payload, tiles, n,
+        h_opt->kind == TT_OPT_ROWWISE_ADAM ? h_opt->step_dev : nullptr, h_opt->beta1, h_opt->beta2, adam_bc,
+        th, (1 << bits) - 1, 1 << bits);
+    TT_CHECK_LAUNCH("ebc_backward_keys");
+    rc = sort_pairs_u32_fused(keys, payload, skeys, spayload, tk, tv, n, key_bits, th, true, s);
+    if (rc) return rc;
+  } else {
+    ebc_backward_keys_kernel<<<(unsigned)(tiles * h_plan->num_kjt_keys), kEbcThreads, 0, s>>>(
+        *h_plan, values, offsets, keys, payload, tiles, n,
+        h_opt->kind == TT_OPT_ROWWISE_ADAM ? h_opt->step_dev : nullptr, h_opt->beta1, h_opt->beta2, adam_bc, nullptr, 0, 0);
+    TT_CHECK_LAUNCH("ebc_backward_keys");
+    ebc_backward_tail_kernel<<<64, 256, 0, s>>>(offsets, (int64_t)h_plan->num_kjt_keys * h_plan->batch_size, n,
+                                                (uint32_t)h_plan->total_rows, keys, payload);
+    TT_CHECK_LAUNCH("ebc_backward_tail");
+    rc = sort_pairs_u32(keys, payload, skeys, spayload, n, key_bits, w.base + w.used, w.size - w.used, s);
+    if (rc) return rc;
+  }
 
   // one shape class for the whole launch: the widest table decides
   int max_dim = 0;
@@ -774,17 +909,17 @@ static int ebc_backward_impl(const tt_ebc_plan* h_plan, const tt_sparse_optimize
   if (max_dim > kHotRowFloats) return fail(TT_ERR_UNSUPPORTED, "ebc_backward: embedding_dim %d > %d", max_dim, kHotRowFloats);
   const int hot_stride = (max_dim + 3) / 4 * 4;
   const int64_t num_bounds = (n - 1) / kHotSeg;          // boundaries kHotSeg, 2*kHotSeg, ... inside [1, n)
-  if (num_bounds > 0) {
+  if (num_bounds > 0 && !fused_sort) {
     cudaError_t e = cudaMemsetAsync(hot, 0, (size_t)(num_bounds + 1) * hot_stride * 4, s);
     if (e != cudaSuccess) return fail(TT_ERR_CUDA, "ebc_backward memset: %s", cudaGetErrorString(e));
   }
 #define TT_LAUNCH_BWD(V, G, N)                                                                        \
   ebc_backward_update_kernel<V, G, N><<<grid, kEbcThreads, 0, s>>>(*h_plan, *h_opt, skeys, spayload, n, \
-                                                                   offsets, grad_out, peers, hot, hot_stride, adam_bc)
+                                                                   offsets, grad_out, peers, hot, hot_stride, adam_bc, worklist)
   TT_DISPATCH_CLASS(id, TT_LAUNCH_BWD);
 #undef TT_LAUNCH_BWD
   TT_CHECK_LAUNCH("ebc_backward_update");
-  if (num_bounds > 0) {
+  if (num_bounds > 0 && !fused_sort) {
     const unsigned hgrid = (unsigned)((num_bounds * c.g + kEbcThreads - 1) / kEbcThreads);
 #define TT_LAUNCH_HOT(V, G, N)                                                                              \
   ebc_backward_hot_apply_kernel<V, G, N><<<hgrid, kEbcThreads, 0, s>>>(*h_plan, *h_opt, skeys, n, hot, hot_stride, \
@@ -793,6 +928,55 @@ static int ebc_backward_impl(const tt_ebc_plan* h_plan, const tt_sparse_optimize
 #undef TT_LAUNCH_HOT
     TT_CHECK_LAUNCH("ebc_backward_hot_apply");
   }
+  return TT_OK;
+}
+
+size_t tt_ebc_dedup_workspace_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  return 4 * align_up((size_t)n * 4, 256) + 2 * align_up((size_t)(n + 1) * 4, 256) + sort_workspace_bytes(n) +
+         scan_workspace_bytes(n) + 2048;
+}
+
+int tt_ebc_dedup(const tt_ebc_plan* h_plan, const int64_t* values, int64_t n, const int32_t* offsets,
+                 int64_t* unique_keys, int32_t* counts, int32_t* inverse, int32_t* num_unique, void* ws,
+                 size_t ws_bytes, void* stream) {
+  bool all_vec4;
+  int rc = validate_plan(h_plan, &all_vec4);
+  if (rc) return rc;
+  TT_CHECK_ARG(offsets && unique_keys && counts && inverse && num_unique && n >= 0, "ebc_dedup: bad args");
+  cudaStream_t s = as_stream(stream);
+  if (n == 0 || h_plan->batch_size == 0) {
+    cudaError_t e = cudaMemsetAsync(num_unique, 0, 4, s);
+    return e == cudaSuccess ? TT_OK : fail(TT_ERR_CUDA, "ebc_dedup: %s", cudaGetErrorString(e));
+  }
+  if (n >= ((int64_t)1 << 31)) return fail(TT_ERR_UNSUPPORTED, "ebc_dedup: too many ids");
+  Workspace w(ws, ws_bytes);
+  uint32_t* keys = w.take<uint32_t>(n);
+  uint32_t* pos = w.take<uint32_t>(n);
+  uint32_t* skeys = w.take<uint32_t>(n);
+  uint32_t* spos = w.take<uint32_t>(n);
+  int32_t* flag = w.take<int32_t>(n + 1);
+  int32_t* excl = w.take<int32_t>(n + 1);
+  if (!keys || !pos || !skeys || !spos || !flag || !excl) return fail(TT_ERR_WORKSPACE, "ebc_dedup: workspace too small");
+  const int tiles = (h_plan->batch_size + kBagsPerCta - 1) / kBagsPerCta;
+  ebc_backward_keys_kernel<<<(unsigned)(tiles * h_plan->num_kjt_keys + 16), kEbcThreads, 0, s>>>(
+      *h_plan, values, offsets, keys, pos, tiles, n, nullptr, 0.f, 0.f, nullptr, nullptr, 0, 0);
+  TT_CHECK_LAUNCH("ebc_dedup_keys");
+  dedup_iota_kernel<<<148, 256, 0, s>>>(pos, n);
+  TT_CHECK_LAUNCH("ebc_dedup_iota");
+  int key_bits = 1;
+  while (key_bits < 32 && ((uint64_t)h_plan->total_rows >> key_bits) != 0) ++key_bits;
+  rc = sort_pairs_u32(keys, pos, skeys, spos, n, key_bits, w.base + w.used, w.size - w.used, s);
+  if (rc) return rc;
+  dedup_flag_kernel<<<148, 256, 0, s>>>(skeys, n, (uint32_t)h_plan->total_rows, flag);
+  TT_CHECK_LAUNCH("ebc_dedup_flag");
+  Workspace w2(w.base + w.used, w.size - w.used);
+  rc = exclusive_scan_i32(flag, excl, n, num_unique, w2.base, w2.size, s);
+  if (rc) return rc;
+  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)n * 4, s);
+  if (e != cudaSuccess) return fail(TT_ERR_CUDA, "ebc_dedup memset: %s", cudaGetErrorString(e));
+  dedup_emit_kernel<<<148, 256, 0, s>>>(skeys, spos, flag, excl, n, (uint32_t)h_plan->total_rows, unique_keys, counts, inverse);
+  TT_CHECK_LAUNCH("ebc_dedup_emit");
   return TT_OK;
 }
 

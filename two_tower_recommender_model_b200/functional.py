@@ -280,6 +280,29 @@ def block_bucketize(lengths: torch.Tensor, offsets: torch.Tensor, values: torch.
     return new_len, new_off, new_val, unb
 
 
+def dedup_rows(ebc, kjt):
+    """Unique linearised (table,row) keys of a batch, ascending, with counts and the inverse map --
+    ``torch.unique(sorted=True, return_inverse=True, return_counts=True)`` over ``row_base[table] + id`` -- from
+    the key construction and radix sort of the fused backward (``tt_ebc_dedup``).  Returns
+    ``(unique_keys int64 [U], inverse int64 [nnz], counts int64 [U])``; ids outside their table map to -1."""
+    values = kjt.values()
+    N.require_cuda(values, "KeyedJaggedTensor.values")
+    dev = values.device
+    values = values.to(torch.int64).contiguous()
+    offsets = kjt.offsets().to(torch.int32).contiguous()
+    n = values.numel()
+    plan, _ = ebc._build_plan(tuple(kjt.keys()), kjt.stride(), with_state=False)
+    uk = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    cnt = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    inv = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    nu = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = N.workspace(N.load().tt_ebc_dedup_workspace_bytes(n), dev)
+    N.call("tt_ebc_dedup", byref(plan), N.ptr(values), n, N.ptr(offsets), N.ptr(uk), N.ptr(cnt), N.ptr(inv), N.ptr(nu),
+           N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    u = int(nu.item())
+    return uk[:u], inv[:n].to(torch.int64), cnt[:u].to(torch.int64)
+
+
 def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, key_bits: int = 32):
     """Stable radix sort of (uint32 key, uint32 payload) pairs held in int32 tensors."""
     N.require_cuda(keys, "keys")
