@@ -111,7 +111,8 @@ def build_model(cfg, dev, sharding=None, exchange="peer", fused_sparse=True, den
           for i, c in enumerate(CAT)]
     ebc = tt.EmbeddingBagCollection(tables=eb, device=torch.device("meta"))
     prec = cfg.get("precision", "bf16")
-    task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, cfg["layers"], device=dev, precision=prec), loss=cfg["loss"], precision=prec)
+    task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, cfg["layers"], device=dev, precision=prec), loss=cfg["loss"], precision=prec,
+                                negatives=cfg.get("negatives", "local"))
     if fused_sparse:
         apply_optimizer_in_backward(tt.RowWiseAdagrad, task.two_tower.ebc.parameters(), {"lr": cfg["sparse_lr"]})
     multi = dist.is_initialized() and dist.get_world_size() > 1
@@ -439,6 +440,14 @@ def run_ours(args):
         main = time_block(cfg, G // world, dev, rank, world, local, args, "table_wise", args.exchange, lib, with_kernels=True)
         srw = time_block(cfg, G // world, dev, rank, world, local, args, "row_wise", args.exchange, lib, with_kernels=False)
         weak = time_block(cfg, G, dev, rank, world, local, args, None, args.exchange, lib, with_kernels=False)
+        gcfg = dict(cfg, negatives="global")
+        sgl = time_block(gcfg, G // world, dev, rank, world, local, args, "table_wise", args.exchange, lib, with_kernels=False)
+        extra["strong_global_negatives"] = {
+            "value": round(G / (sgl["ms_value"] * 1e-3), 1), "ms_per_step": round(sgl["ms_value"], 4), "e2e": round(G / (sgl["ms_e2e"] * 1e-3), 1),
+            "global_batch": G, "per_rank_batch": G // world, "sharding": sgl["sharding"], "last_loss": sgl["last_loss"],
+            "note": "every rank's candidates are negatives for every rank's queries (all-gather + reduce-scatter): the SAME loss "
+                    "function as the 1-GPU run at global batch 65536; per-rank logits flops = 1/N of the 1-GPU step"}
+        extra["retrieval"] = retrieval_probe_sharded(dev, rank, world)
         extra["strong_row_wise"] = {"value": round(G / (srw["ms_value"] * 1e-3), 1), "ms_per_step": round(srw["ms_value"], 4),
                                     "e2e": round(G / (srw["ms_e2e"] * 1e-3), 1), "global_batch": G, "per_rank_batch": G // world,
                                     "sharding": srw["sharding"]}
@@ -553,6 +562,44 @@ def retrieval_probe(dev, n_items=2_000_000, n_queries=16384, d=64, k=100):
     return {"queries_per_s": round(n_queries / (ms * 1e-3), 1), "ms": round(ms, 3), "items": n_items, "queries": n_queries,
             "k": k, "d": d, "tflops": round(tf, 1), "frac_of_sustained_bf16_peak": round(tf / pk["tf_sustained"], 4),
             "data": "randn", "top1_score_mean": round(float(s[:, 0].mean()), 3), "dtype": "bf16 scoring, f32 accumulate"}
+
+
+def retrieval_probe_sharded(dev, rank, world, n_items=10_000_000, q_per_rank=131072, d=64, k=100):
+    """BASELINE configs[4] on N GPUs: the corpus lives sharded (each rank holds the embeddings of a contiguous id
+    range), is all-gathered once as bf16, and every rank answers its own 131072 queries (8 x 131072 = 1M queries on
+    8 GPUs).  Timed: the search (max over ranks); the one-off all-gather is reported separately."""
+    import torch.distributed as dist
+    import two_tower_recommender_model_b200 as tt
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    per = -(-n_items // world)
+    n_local = max(0, min(per, n_items - rank * per))
+    local = torch.randn(n_local, d, device=dev, generator=g)
+    queries = torch.randn(q_per_rank, d, device=dev, generator=g)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    index = tt.BruteForceIndex.from_sharded(local, precision="bf16")
+    torch.cuda.synchronize()
+    gather_s = time.perf_counter() - t0
+    del local
+    index.search(queries[:1024], k)
+    index.search(queries, k, query_chunk=1 << 17)
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    s, _ = index.search(queries, k, query_chunk=1 << 17)
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    tf = 2.0 * q_per_rank * n_items * d / (ms * 1e-3) / 1e12
+    pk = peaks()
+    return {"queries_per_s_total": round(world * q_per_rank / (ms * 1e-3), 1), "queries_per_s_per_gpu": round(q_per_rank / (ms * 1e-3), 1),
+            "ms": round(ms, 3), "items": n_items, "queries_total": world * q_per_rank, "k": k, "d": d,
+            "tflops_per_gpu": round(tf, 1), "frac_of_sustained_bf16_peak": round(tf / pk["tf_sustained"], 4), "data": "randn",
+            "corpus_all_gather_s": round(gather_s, 3), "how": "queries sharded over ranks, bf16 corpus all-gathered once"}
 
 
 # ----------------------------------------------------------------------------- CPU baseline / reference arm

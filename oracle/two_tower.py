@@ -147,12 +147,26 @@ class OracleTwoTower(nn.Module):
     # reduce-scatter backward divides by the world size (comm_ops GRADIENT_DIVISION, default on) --
     # i.e. both see the gradient of (1/W) * sum_r loss_r; then both optimizers step once.
     # ``gradient_division=False`` reproduces set_gradient_division(False): embedding gradients summed.
-    def train_step_ranks(self, keys, batches, gradient_division: bool = True) -> List[torch.Tensor]:
+    # ``negatives="global"`` (softmax loss): rank r's queries see the candidates of EVERY rank,
+    # loss_r = CE(q_r @ cat(c_0..c_{W-1})^T / T, r*B + arange(B)) -- the gradient w.r.t. another rank's
+    # candidates flows back into the shared towers / tables (all-gather forward, reduce-scatter backward).
+    def train_step_ranks(self, keys, batches, gradient_division: bool = True, negatives: str = "local") -> List[torch.Tensor]:
         self.dense_opt.zero_grad(set_to_none=True)
         for eb in self.embedding_bags.values():
             eb.weight.grad = None
         losses = []
-        for values, lengths, labels in batches:
+        if negatives == "global":
+            assert self.loss_kind != "bce"
+            qs, cs = zip(*[self.forward(keys, v, l) for v, l, _ in batches])
+            c_all = torch.cat(cs)
+            total = 0
+            for r, q in enumerate(qs):
+                B = q.shape[0]
+                loss = F.cross_entropy((q @ c_all.t()) / self.temperature, r * B + torch.arange(B))
+                losses.append(loss.detach())
+                total = total + loss
+            total.backward()
+        for values, lengths, labels in (batches if negatives != "global" else []):
             q, c = self.forward(keys, values, lengths)
             loss, _ = self.loss(q, c, labels)
             loss.backward()

@@ -214,7 +214,7 @@ def test_fused_towers_match_per_layer_path(cuda, B, i, h, o):
         p = pooled.clone().requires_grad_(True)
         ps = [x.clone().requires_grad_(True) for x in params]
         if fused:
-            ys = FusedTowersTC.apply(p, (0, i), i, *ps)[:2]
+            ys = FusedTowersTC.apply(p, (0, i), i, None, *ps)[:2]
         else:
             ys = [MlpTC.apply(p.narrow(1, t * i, i), *ps[4 * t: 4 * t + 4]) for t in range(2)]
         torch.autograd.backward(list(ys), dys)
@@ -266,7 +266,7 @@ def test_fused_towers_without_bias_and_unused_tower(cuda):
         p = pooled.clone().requires_grad_(True)
         ps = [None if x is None else x.clone().requires_grad_(True) for x in ws]
         if fused:
-            ys = FusedTowersTC.apply(p, (0, i), i, *ps)[:2]
+            ys = FusedTowersTC.apply(p, (0, i), i, None, *ps)[:2]
         else:
             ys = [MlpTC.apply(p.narrow(1, t * i, i), *ps[4 * t: 4 * t + 4]) for t in range(2)]
         ys[0].backward(dy0)                      # tower 1 gets no gradient at all
@@ -300,7 +300,7 @@ def test_fused_towers_against_float64_emulation(cuda, B, i, h, o):
     bf = lambda t: t.float().bfloat16().double()
     p = pooled.to(cuda).requires_grad_(True)
     ps = [x.to(cuda).requires_grad_(True) for x in params]
-    ys = FusedTowersTC.apply(p, (0, i), i, *ps)[:2]
+    ys = FusedTowersTC.apply(p, (0, i), i, None, *ps)[:2]
     torch.autograd.backward(list(ys), [d.to(cuda) for d in dys])
     rel = lambda a, b: float((a.double().cpu() - b).norm() / (b.norm() + 1e-30))
     for t in range(2):

@@ -97,7 +97,7 @@ def towers(args):
         dys = [torch.randn(B, 64, device=dev) for _ in range(2)]
 
         def run():
-            ys = F.FusedTowersTC.apply(pooled, (0, 64), 64, *params)[:2]
+            ys = F.FusedTowersTC.apply(pooled, (0, 64), 64, None, *params)[:2]
             torch.autograd.backward(list(ys), dys)
         fwd_bytes = 2 * B * (4 * 64 + 2 * 64 + 2 * 128 + 4 * 64 + 2 * 64)
         bwd_bytes = 2 * B * (4 * 64 + 2 * 64 + 2 * 128 + 2 * 64 + 4 * 64)

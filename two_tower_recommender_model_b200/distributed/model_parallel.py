@@ -66,6 +66,11 @@ class DistributedModelParallel(nn.Module):
         if world > 1 and init_data_parallel:
             from .sharding import DenseGradSync
             self._dense_sync = DenseGradSync(module, pg)
+            # start the towers' gradient all-reduce as soon as their backward is done, concurrent with the
+            # embedding backward (TorchRec's DDP overlaps its buckets with the backward in the same way)
+            for m in module.modules():
+                if hasattr(m, "set_pre_backward"):
+                    m.set_pre_backward(self._dense_sync.start_async)
 
     @property
     def module(self) -> nn.Module:

@@ -91,11 +91,17 @@ class _ReduceScatterRows(torch.autograd.Function):
 
 
 class PeerExchange:
-    """Symmetric (NVLink peer-mapped) buffers for the table-wise exchange: one ``[B, D_tw]`` fp32 matrix
-    for pooled rows and one for their gradients on every rank, each mapped into every process of the
-    group.  The owner of a table writes its pooled rows straight into the buffer of the rank the
-    sample belongs to (``tt_ebc_forward_peer``) and reads the gradient rows straight from it
-    (``tt_ebc_backward_fused_peer``): the lookup kernel IS the all-to-all.  Allocation is collective."""
+    """Symmetric (NVLink peer-mapped) buffers for the fused exchange: per rank TWO ``[B, D]`` fp32 matrices for pooled
+    rows and two for their gradients (double buffered, alternating every step), each mapped into every process of
+    the group.  The owner of a table writes its pooled rows straight into the buffer of the rank the sample belongs
+    to (``tt_ebc_forward_peer``) and reads the gradient rows straight from it (``tt_ebc_backward_fused_peer``): the
+    lookup kernel IS the all-to-all.  Allocation is collective.
+
+    Why two buffers: with one, a step needs four cross-rank barriers (nobody still uses the old pooled rows | rows
+    landed | gradients staged | nobody still reads the gradients) and two staging copies.  With two, "rows landed"
+    of step i+1 already implies every rank is done with step i-1's buffer, and the same for the gradients, so a
+    step has TWO barriers, the module's output IS the exchange buffer (no clone) and the towers' backward writes
+    its input gradient straight into the gradient buffer (no copy)."""
 
     def __init__(self, rows: int, cols: int, device: torch.device, pg: Any) -> None:
         import torch.distributed._symmetric_memory as symm
@@ -105,21 +111,45 @@ class PeerExchange:
         if self.world > N.TT_MAX_PEERS:
             raise ValueError(f"peer exchange supports up to {N.TT_MAX_PEERS} ranks")
         group = pg if pg is not None else dist.group.WORLD
-        self.pooled = symm.empty(rows, cols, dtype=torch.float32, device=device)
-        self.grad = symm.empty(rows, cols, dtype=torch.float32, device=device)
-        self._h_pooled = symm.rendezvous(self.pooled, group)
-        self._h_grad = symm.rendezvous(self.grad, group)
-        self.pooled_peers = self._peers(self._h_pooled)
-        self.pooled_peers_scatter = self._peers(self._h_pooled, N.TT_PEER_SCATTER_ADD)
-        self.grad_peers = self._peers(self._h_grad)
+        self._pooled2 = symm.empty(2, rows, cols, dtype=torch.float32, device=device)
+        self._grad2 = symm.empty(2, rows, cols, dtype=torch.float32, device=device)
+        self._h_pooled = symm.rendezvous(self._pooled2, group)
+        self._h_grad = symm.rendezvous(self._grad2, group)
+        nbytes = rows * cols * 4
+        self._pooled_peers = [self._peers(self._h_pooled, b * nbytes) for b in range(2)]
+        self._pooled_peers_scatter = [self._peers(self._h_pooled, b * nbytes, N.TT_PEER_SCATTER_ADD) for b in range(2)]
+        self._grad_peers = [self._peers(self._h_grad, b * nbytes) for b in range(2)]
+        self.cur = 0                    # buffer of the step in flight (flipped at the start of every forward)
+        # row-wise shards ADD into pre-zeroed buffers: both start zeroed; afterwards a forward zeroes the OTHER buffer
+        # for the next step (the gradient barrier of the step in between orders that against the peers' adds).
+        # no_backward_since_forward: two forwards in a row (eval) have no such barrier in between -> take one.
+        self._pooled2.zero_()
+        self.no_backward_since_forward = False
+        dist.barrier(group=pg)
 
-    def _peers(self, handle, flags: int = 0):
+    def _peers(self, handle, byte_offset: int = 0, flags: int = 0):
         from .. import _native as N
         pb = N.PeerBuffers()
         pb.world, pb.rows_per_peer, pb.flags = self.world, self.rows, flags
         for r, p in enumerate(handle.buffer_ptrs):
-            pb.ptr[r] = p
+            pb.ptr[r] = p + byte_offset
         return pb
+
+    def flip(self) -> int:
+        self.cur ^= 1
+        return self.cur
+
+    def pooled(self, b: int) -> torch.Tensor:
+        return self._pooled2[b]
+
+    def grad(self, b: int) -> torch.Tensor:
+        return self._grad2[b]
+
+    def pooled_peers(self, b: int, scatter_add: bool):
+        return (self._pooled_peers_scatter if scatter_add else self._pooled_peers)[b]
+
+    def grad_peers(self, b: int):
+        return self._grad_peers[b]
 
     def barrier_pooled(self) -> None:
         self._h_pooled.barrier(channel=0)
@@ -129,33 +159,46 @@ class PeerExchange:
 
 
 class _PeerTwLookup(torch.autograd.Function):
-    """Table-wise lookup over the global batch whose stores are the output exchange and whose
-    backward reads the gradient from the peers (see ``PeerExchange``).  ``ebc`` is None on a rank
-    that owns no table-wise table: it still takes part in the barriers and stages its gradient."""
+    """Lookup over the global batch whose stores are the output exchange and whose backward reads the gradient from
+    the peers (see ``PeerExchange``).  ``ebc`` is None on a rank that owns no table of the group: it still takes
+    part in the barriers and stages its gradient.  ``pre_backward`` (optional callable) runs right before the
+    embedding backward is launched -- the data-parallel towers start their gradient all-reduce there, on a side
+    stream, so that it overlaps the embedding update."""
 
     @staticmethod
-    def forward(ctx, ex, ebc, layout, kjt_keys, values, offsets, scatter_add, *anchors):
+    def forward(ctx, ex, ebc, layout, kjt_keys, values, offsets, scatter_add, pre_backward, *anchors):
         from ctypes import byref
         from .. import _native as N
-        if scatter_add:
-            ex.pooled.zero_()         # row-wise shards ADD their rows; bags nobody holds stay zero
-        ex.barrier_pooled()           # every rank is done with the previous contents of the buffers
+        b = ex.flip()
+        pooled = ex.pooled(b)
+        if scatter_add and ex.no_backward_since_forward:
+            ex.barrier_pooled()       # eval: the zeroing issued by the previous forward must be ordered against the adds below
         if ebc is not None:
             dev = values.device
             plan, _ = ebc._build_plan(kjt_keys, ex.world * ex.rows, with_state=False, out_layout=layout)
-            peers = ex.pooled_peers_scatter if scatter_add else ex.pooled_peers
-            N.call("tt_ebc_forward_peer", byref(plan), N.ptr(values), N.ptr(offsets), byref(peers), N.stream_ptr(dev))
+            N.call("tt_ebc_forward_peer", byref(plan), N.ptr(values), N.ptr(offsets), byref(ex.pooled_peers(b, scatter_add)),
+                   N.stream_ptr(dev))
             ctx.save_for_backward(values, offsets)
         ex.barrier_pooled()           # every owner's rows have landed here
-        ctx.ex, ctx.ebc, ctx.layout, ctx.kjt_keys, ctx.n_anchors = ex, ebc, layout, kjt_keys, len(anchors)
-        return ex.pooled.clone()
+        if scatter_add:
+            ex.pooled(b ^ 1).zero_()  # row-wise shards ADD their rows: the next step's buffer starts from zero
+        ex.no_backward_since_forward = True
+        ctx.ex, ctx.ebc, ctx.layout, ctx.kjt_keys, ctx.n_anchors, ctx.buf = ex, ebc, layout, kjt_keys, len(anchors), b
+        ctx.pre_backward = pre_backward
+        out = pooled.view(ex.rows, ex.cols)
+        return out
 
     @staticmethod
     def backward(ctx, grad):
         from ctypes import byref
         from .. import _native as N
-        ex, ebc = ctx.ex, ctx.ebc
-        ex.grad.copy_(grad)
+        ex, ebc, b = ctx.ex, ctx.ebc, ctx.buf
+        ex.no_backward_since_forward = False
+        gbuf = ex.grad(b)
+        if grad.data_ptr() != gbuf.data_ptr():
+            gbuf.copy_(grad)          # the producer did not write in place (see FusedTowersTC grad_dst)
+        if ctx.pre_backward is not None:
+            ctx.pre_backward()
         ex.barrier_grad()             # every rank's gradient rows are staged
         grads = (None,) * ctx.n_anchors
         if ebc is not None:
@@ -166,15 +209,15 @@ class _PeerTwLookup(torch.autograd.Function):
             if spec is None:
                 dense_grads = ebc._alloc_dense_grads()
                 spec = N.SparseOptimizer(kind=N.OPT_DENSE_GRAD)
+                spec.grad_scale = float(getattr(ebc, "_grad_scale", 1.0))
             plan, _ = ebc._build_plan(ctx.kjt_keys, ex.world * ex.rows, with_state=True, dense_grads=dense_grads, out_layout=ctx.layout)
             n = values.numel()
             ws = N.workspace(N.load().tt_ebc_backward_workspace_bytes(n), dev)
             N.call("tt_ebc_backward_fused_peer", byref(plan), byref(spec), N.ptr(values), n, N.ptr(offsets),
-                   byref(ex.grad_peers), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+                   byref(ex.grad_peers(b)), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
             if dense_grads is not None:
                 grads = tuple(dense_grads)
-        ex.barrier_grad()             # nobody still reads this rank's gradient rows
-        return (None,) * 7 + grads
+        return (None,) * 8 + grads
 
 
 def _native_bucketize(lengths, offsets, values, num_rows, F, B, W):
@@ -293,6 +336,11 @@ class ShardedEmbeddingBagCollection(nn.Module):
 
     def shard_info(self) -> Dict[str, Tuple[str, int, int]]:
         return dict(self._shard_info)
+
+    def set_pre_backward(self, fn) -> None:
+        """``fn()`` is called right before the embedding backward is launched (tower gradients are complete by
+        then): DistributedModelParallel starts the dense all-reduce there so that it overlaps the update."""
+        self._pre_backward = fn
 
     def local_parameters(self):
         for local in (self.tw_ebc, self.rw_ebc):
@@ -504,9 +552,11 @@ class ShardedEmbeddingBagCollection(nn.Module):
                 anchors = (torch.zeros(0, dtype=torch.float32, device=self._device, requires_grad=True),)
             else:
                 anchors = tuple(ebc.embedding_bags[c.name].weight for c in ebc.embedding_bag_configs())
-        out = _PeerTwLookup.apply(ex, ebc, (col, layout_cols), keys, values, offsets, scatter_add, *anchors)
+        out = _PeerTwLookup.apply(ex, ebc, (col, layout_cols), keys, values, offsets, scatter_add,
+                                  getattr(self, "_pre_backward", None), *anchors)
         if feats == self._out_features:
             self._whole = out          # this group alone is the module's output, already in output order: no concat copy
+            out._tt_grad_dst = ex.grad(ex.cur)   # a producer of d(out) may write it straight into the exchange buffer
         return {f: out[:, layout_cols[f]:layout_cols[f] + grp.feat_dim[f]] for f in feats}
 
     # ---- checkpoint surface: ShardedTensor entries named like the unsharded module --------------
@@ -633,26 +683,63 @@ class DenseGradSync:
     def __init__(self, module: nn.Module, pg: Any = None) -> None:
         self._pg = pg
         self._params = [p for n, p in module.named_parameters() if "embedding_bags" not in n]
-        self._flat: Optional[torch.Tensor] = None
+        self._side: Optional[torch.cuda.Stream] = None
+        self._pending = False
         # identical initial dense weights on every rank
         for p in self._params:
             dist.broadcast(p.data, src=0, group=pg)
 
-    def all_reduce(self) -> None:
-        W = dist.get_world_size(self._pg)
+    def _flat(self):
         grads = [p.grad for p in self._params if p.grad is not None]
         if not grads:
-            return
+            return None, grads
         base = grads[0].untyped_storage()
-        same = all(g.untyped_storage().data_ptr() == base.data_ptr() for g in grads)
-        if same:  # FlatAdam: one contiguous buffer already
-            flat = torch.empty(0, dtype=grads[0].dtype, device=grads[0].device).set_(base, 0, (base.nbytes() // 4,))
-            dist.all_reduce(flat, group=self._pg)
-            flat.div_(W)
+        if all(g.untyped_storage().data_ptr() == base.data_ptr() for g in grads):   # FlatAdam: one contiguous buffer already
+            return torch.empty(0, dtype=grads[0].dtype, device=grads[0].device).set_(base, 0, (base.nbytes() // 4,)), grads
+        return None, grads
+
+    def _avg_op(self, t: torch.Tensor):
+        # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum, then divide
+        return dist.ReduceOp.AVG if t.is_cuda else dist.ReduceOp.SUM
+
+    def start_async(self) -> None:
+        """Issues the all-reduce of the (flat) tower gradients on a side stream; ``all_reduce()`` then only joins.
+        Called from the sharded module's pre-backward hook, i.e. after the towers' backward and before the
+        embedding backward, which it overlaps.  Falls back to doing nothing when the gradients are not one flat
+        CUDA buffer (``all_reduce()`` then does the whole job)."""
+        if self._pending:
+            return                   # a module with several sharding groups calls the hook once per group
+        flat, _ = self._flat()
+        if flat is None or not flat.is_cuda:
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=flat.device)
+        cur = torch.cuda.current_stream(flat.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self._pg)
+        self._pending = True
+
+    def all_reduce(self) -> None:
+        W = dist.get_world_size(self._pg)
+        if self._pending:
+            self._pending = False
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+            return
+        flat, grads = self._flat()
+        if not grads:
+            return
+        if flat is not None:
+            op = self._avg_op(flat)
+            dist.all_reduce(flat, op=op, group=self._pg)
+            if op != dist.ReduceOp.AVG:
+                flat.div_(W)
             return
         flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat, group=self._pg)
-        flat.div_(W)
+        op = self._avg_op(flat)
+        dist.all_reduce(flat, op=op, group=self._pg)
+        if op != dist.ReduceOp.AVG:
+            flat.div_(W)
         off = 0
         for g in grads:
             n = g.numel()

@@ -247,15 +247,90 @@ class InBatchSoftmaxLossTC(torch.autograd.Function):
         return dq * g_loss, dc * g_loss, None, None, None
 
 
-def in_batch_softmax_loss(q: torch.Tensor, c: torch.Tensor, temperature: float = 1.0, precision: str = "fp32"):
-    """``precision="fp32"``: CUDA-core path, exact fp32.  ``"bf16"``: tcgen05 tensor-core path."""
+class InBatchSoftmaxGlobalTC(torch.autograd.Function):
+    """In-batch softmax with GLOBAL negatives over a process group: rank r scores its queries against the
+    candidates of EVERY rank, ``loss_r = mean_i CE(q_i . [c_0; ...; c_{W-1}]^T / T, r*B + i)`` -- the same function
+    of the global batch as the single-GPU loss (all-gather of the candidate embeddings, reduce-scatter
+    of their gradient).  The [B, W*B] logits are processed as W square [B, B] blocks with the tcgen05 kernels
+    (``tt_inbatch_softmax_forward_bf16`` gives each block's row log-sum-exp; the row's global one is the
+    log-sum-exp of those; ``tt_inbatch_softmax_backward_bf16`` takes it back in), so per rank the flops are
+    ``6 B (W B) d`` = 1/W of the single-GPU loss at the same global batch.  The positive-pair term is subtracted
+    only in the block of the rank's own candidates (the other blocks pass zeros as the "other side")."""
+
+    @staticmethod
+    def forward(ctx, q, c, temperature: float, pg, q_bf16=None, c_bf16=None):
+        from torch import distributed as dist
+        q = _f32c(q, "query_embedding")
+        c = _f32c(c, "candidate_embedding")
+        B, d = q.shape
+        dev = q.device
+        W, r = dist.get_world_size(pg), dist.get_rank(pg)
+        if d > 64 or d % 4 != 0:
+            raise NotImplementedError("global in-batch negatives run on the one-pass tcgen05 kernels: d <= 64, d % 4 == 0")
+        qb = q_bf16 if q_bf16 is not None else cast_bf16(q)
+        cb = c_bf16 if c_bf16 is not None else cast_bf16(c)
+        cb = cb if (cb.stride(0) == cb.shape[1] and cb.is_contiguous()) else cb.contiguous()
+        cb_all = torch.empty(W, B, cb.shape[1], dtype=torch.bfloat16, device=dev)
+        dist.all_gather_into_tensor(cb_all.view(W * B, cb.shape[1]), cb, group=pg)
+        lses = torch.empty(W, B, dtype=torch.float32, device=dev)
+        diags = torch.empty(W, B, dtype=torch.float32, device=dev)
+        scratch = torch.empty((), dtype=torch.float32, device=dev)
+        ws = N.workspace(N.load().tt_inbatch_softmax_bf16_workspace_bytes(B), dev)
+        for w in range(W):
+            N.call("tt_inbatch_softmax_forward_bf16", N.ptr(qb), qb.stride(0), N.ptr(cb_all[w]), cb_all.stride(1), B, d,
+                   1.0 / temperature, N.ptr(lses[w]), N.ptr(diags[w]), N.ptr(scratch), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+        lse = torch.logsumexp(lses, dim=0)
+        diag = diags[r].clone()
+        loss = (lse - diag).mean()
+        ctx.inv_t, ctx.pg, ctx.W, ctx.r = 1.0 / temperature, pg, W, r
+        ctx.save_for_backward(q, c, qb, cb_all, lse)
+        ctx.mark_non_differentiable(diag)
+        return loss, diag
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_diag):
+        from torch import distributed as dist
+        q, c, qb, cb_all, lse = ctx.saved_tensors
+        B, d = q.shape
+        dev = q.device
+        W, r = ctx.W, ctx.r
+        zeros = torch.zeros(B, d, dtype=torch.float32, device=dev)
+        dq_w = torch.empty(W, B, d, dtype=torch.float32, device=dev)
+        dc_all = torch.empty(W, B, d, dtype=torch.float32, device=dev)
+        gs = g_loss.contiguous() if (g_loss.numel() == 1 and g_loss.dtype == torch.float32 and g_loss.is_cuda) else None
+        for w in range(W):
+            own = w == r
+            N.call("tt_inbatch_softmax_backward_bf16", N.ptr(qb), qb.stride(0), N.ptr(cb_all[w]), cb_all.stride(1),
+                   None, 0, None, 0, N.ptr(q if own else zeros), d, N.ptr(c if own else zeros), d,
+                   N.ptr(lse), B, d, ctx.inv_t, 1.0, 0, N.ptr(dq_w[w]), d, N.ptr(dc_all[w]), d, N.ptr(gs), N.stream_ptr(dev))
+        dq = dq_w.sum(dim=0)
+        dc = torch.empty(B, d, dtype=torch.float32, device=dev)
+        dist.reduce_scatter_tensor(dc, dc_all.view(W * B, d), op=dist.ReduceOp.SUM, group=ctx.pg)
+        if gs is None:
+            dq, dc = dq * g_loss, dc * g_loss
+        return dq, dc, None, None, None, None
+
+
+def in_batch_softmax_loss(q: torch.Tensor, c: torch.Tensor, temperature: float = 1.0, precision: str = "fp32",
+                          negatives: str = "local", pg=None):
+    """``precision="fp32"``: CUDA-core path, exact fp32.  ``"bf16"``: tcgen05 tensor-core path.
+    ``negatives="global"`` (bf16 only, inside a process group): every rank's candidates are negatives for every
+    rank's queries (all-gather + reduce-scatter); ``"local"``: per-rank negatives, no collective."""
     if precision == "bf16":
         def bf16_of(t):   # bf16 copy attached by FusedTowersTC ([B, 64], zero padded), valid for the tensor it came with
             b = getattr(t, "_tt_bf16", None)
             ok = (b is not None and b.dtype == torch.bfloat16 and b.shape[0] == t.shape[0] and b.shape[1] >= t.shape[1]
                   and b.device == t.device and getattr(t, "_tt_bf16_version", None) == t._version)
             return b if ok else None
+        if negatives == "global":
+            from torch import distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(pg) > 1:
+                return InBatchSoftmaxGlobalTC.apply(q, c, temperature, pg, bf16_of(q), bf16_of(c))
         return InBatchSoftmaxLossTC.apply(q, c, temperature, bf16_of(q), bf16_of(c))
+    if negatives == "global":
+        from torch import distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(pg) > 1:
+            raise NotImplementedError("global in-batch negatives need precision='bf16' (tcgen05 path)")
     return InBatchSoftmaxLoss.apply(q, c, temperature)
 
 
@@ -433,7 +508,11 @@ class FusedTowersTC(torch.autograd.Function):
     fp32 master weights and gradients, same numerics as ``MlpTC``."""
 
     @staticmethod
-    def forward(ctx, pooled, cols, in_dim, *params):
+    def forward(ctx, pooled, cols, in_dim, grad_dst, *params):
+        """``grad_dst``: optional fp32 ``[B, width]`` buffer that receives d(pooled) (the sharded module passes its
+        NVLink exchange buffer, so the gradient needs no staging copy); only used when the towers' windows tile
+        the whole matrix."""
+        ctx.grad_dst = grad_dst
         pooled = _rows(pooled, "pooled embeddings")
         T = len(cols)
         B = pooled.shape[0]
@@ -475,7 +554,12 @@ class FusedTowersTC(torch.autograd.Function):
         covered = sorted(ctx.cols) == list(range(0, ctx.width, in_dim))     # the windows tile the pooled matrix
         d_pooled = None
         if need_dx:
-            d_pooled = (torch.empty if covered else torch.zeros)(B, ctx.width, dtype=torch.float32, device=dev)
+            gd = ctx.grad_dst
+            if (covered and gd is not None and gd.shape == (B, ctx.width) and gd.dtype == torch.float32 and gd.is_contiguous()
+                    and gd.device == dev):
+                d_pooled = gd
+            else:
+                d_pooled = (torch.empty if covered else torch.zeros)(B, ctx.width, dtype=torch.float32, device=dev)
         grads = []
         arr = (N.TowerBackward * T)()
         keep = []
@@ -498,7 +582,7 @@ class FusedTowersTC(torch.autograd.Function):
         ws = N.workspace(N.load().tt_towers_backward_workspace_bytes(B), dev)
         N.call("tt_towers_backward_fused", arr, T, B, in_dim, hidden, out_dim, N.ptr(ws), ws.numel(), N.stream_ptr(dev))
         ctx.saved = None
-        return (d_pooled, None, None, *grads)
+        return (d_pooled, None, None, None, *grads)
 
 
 class MlpTC(torch.autograd.Function):

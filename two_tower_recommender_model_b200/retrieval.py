@@ -58,6 +58,27 @@ def embed_corpus(two_tower_model, cat_cols: List[str], key: str, num_embeddings:
     return torch.cat(outs, dim=0)
 
 
+def embed_corpus_sharded(two_tower_model, cat_cols: List[str], key: str, num_embeddings: int, device, pg=None,
+                         chunk: int = 1 << 18):
+    """Corpus embedding with a SHARDED model (03_model_training.py:1095-1122 run against the trained -- here
+    table-wise / row-wise sharded -- tables): rank r embeds the contiguous id range
+    ``[r * ceil(N / W), (r + 1) * ceil(N / W))`` through the sharded EmbeddingBagCollection (a collective: every
+    rank calls it with the same chunk size; ids past a rank's range are clamped and their rows dropped) and its
+    tower.  Returns ``(local_embeddings [n_r, d_out], first_id)``; ``BruteForceIndex.from_sharded`` all-gathers."""
+    from torch import distributed as dist
+    W, r = (dist.get_world_size(pg), dist.get_rank(pg)) if dist.is_available() and dist.is_initialized() else (1, 0)
+    per = -(-num_embeddings // W)
+    lo, hi = min(r * per, num_embeddings), min((r + 1) * per, num_embeddings)
+    chunk = min(chunk, per)
+    outs = []
+    for s in range(0, per, chunk):                      # the same number of calls on every rank
+        kjt = create_keyed_jagged_tensor(chunk, cat_cols, key, device, start=lo + s)
+        kjt._values = kjt._values.clamp_(max=num_embeddings - 1)
+        e = process_embeddings(two_tower_model, kjt, key)
+        outs.append(e[:max(0, min(chunk, hi - (lo + s)))])
+    return (torch.cat(outs, dim=0) if outs else torch.empty(0, 0, device=device)), lo
+
+
 class BruteForceIndex:
     """Exact inner-product index over an item-embedding corpus resident in HBM."""
 
@@ -74,10 +95,55 @@ class BruteForceIndex:
             from .functional import cast_bf16
             self._items_bf16 = cast_bf16(self._items)
 
+    @classmethod
+    def from_sharded(cls, local_item_embeddings: torch.Tensor, pg=None, primary_key: str = "product_id",
+                     precision: str = "fp32") -> "BruteForceIndex":
+        """Multi-GPU retrieval (BASELINE configs[4]): every rank holds the embeddings of a contiguous id
+        range (rank order = id order, see ``embed_corpus_sharded``); the corpus is ALL-GATHERED once (10 M x 64 bf16 =
+        1.28 GB) and every rank then answers ITS OWN queries against the full corpus with ``search`` -- queries are
+        sharded, so no per-query merge across ranks exists.  ``precision="bf16"`` gathers the bf16 copy."""
+        from torch import distributed as dist
+        x = local_item_embeddings.contiguous().float()
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(pg) == 1:
+            return cls(x, primary_key=primary_key, precision=precision)
+        W = dist.get_world_size(pg)
+        dev = x.device
+        sizes = torch.zeros(W, dtype=torch.int64, device=dev)
+        sizes[dist.get_rank(pg)] = x.shape[0]
+        dist.all_reduce(sizes, group=pg)
+        sizes = sizes.tolist()
+        mx, d = max(sizes), x.shape[1]
+        index = cls.__new__(cls)
+        index._ids, index._pk, index._precision = None, primary_key, precision
+        if precision == "bf16":
+            from .functional import cast_bf16
+            xb = cast_bf16(x) if x.shape[0] > 0 else torch.empty(0, (d + 7) // 8 * 8, dtype=torch.bfloat16, device=dev)
+            pw = (d + 7) // 8 * 8
+            pad = torch.zeros(mx, pw, dtype=torch.bfloat16, device=dev)
+            if x.shape[0] > 0:
+                pad[:x.shape[0], :d] = xb
+            allb = torch.empty(W * mx, pw, dtype=torch.bfloat16, device=dev)
+            dist.all_gather_into_tensor(allb, pad, group=pg)
+            full = torch.cat([allb[w * mx:w * mx + sizes[w]] for w in range(W)]) if any(s != mx for s in sizes) else allb
+            index._items_bf16 = full[:, :d]
+            index._items = None
+            index._n, index._dev = full.shape[0], dev
+        else:
+            pad = torch.zeros(mx, d, dtype=torch.float32, device=dev)
+            pad[:x.shape[0]] = x
+            allf = torch.empty(W * mx, d, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(allf, pad, group=pg)
+            full = torch.cat([allf[w * mx:w * mx + sizes[w]] for w in range(W)]) if any(s != mx for s in sizes) else allf
+            index._items, index._items_bf16 = full.contiguous(), None
+            index._n, index._dev = full.shape[0], dev
+        return index
+
     def search(self, query_embeddings: torch.Tensor, num_results: int = 100, query_chunk: int = 1 << 16):
         """Batched top-k: returns ``(scores [Q,k] f32, ids [Q,k] int64)``."""
-        q = query_embeddings.to(self._items.device).float().contiguous()
-        k = min(num_results, self._items.shape[0])
+        dev = self._items.device if self._items is not None else self._items_bf16.device
+        n_items = self._items.shape[0] if self._items is not None else self._items_bf16.shape[0]
+        q = query_embeddings.to(dev).float().contiguous()
+        k = min(num_results, n_items)
         s_out, i_out = [], []
         for s in range(0, q.shape[0], query_chunk):
             sc, ix = score_topk(q[s:s + query_chunk], self._items, k, precision=self._precision, items_bf16=self._items_bf16)
@@ -92,7 +158,8 @@ class BruteForceIndex:
                           num_results: int = 100, **unused) -> Dict:
         """One query, Vector-Search-shaped response (04_evaluate_retrieval.py:117-123
         reads ``response['manifest']['columns']`` and ``response['result']['data_array']``)."""
-        q = torch.as_tensor(query_vector, dtype=torch.float32, device=self._items.device).view(1, -1)
+        dev = self._items.device if self._items is not None else self._items_bf16.device
+        q = torch.as_tensor(query_vector, dtype=torch.float32, device=dev).view(1, -1)
         scores, idx = self.search(q, num_results)
         rows = [[int(i), float(s)] for i, s in zip(idx[0].tolist(), scores[0].tolist())]
         return {"manifest": {"column_count": 2, "columns": [{"name": self._pk}, {"name": "score"}]},

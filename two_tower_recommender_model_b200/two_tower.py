@@ -101,7 +101,8 @@ class TwoTower(nn.Module):
         plan = self._fused_plan(pooled_embeddings)
         if plan is not None:
             cols, in_dim, params = plan
-            q, c, yb = FusedTowersTC.apply(pooled_embeddings.values(), tuple(cols), in_dim, *params)
+            pv = pooled_embeddings.values()
+            q, c, yb = FusedTowersTC.apply(pv, tuple(cols), in_dim, getattr(pv, "_tt_grad_dst", None), *params)
             # the towers' bf16 copies of their outputs ride along: the tensor-core loss takes them instead of casting again
             q._tt_bf16, q._tt_bf16_version = yb[0], q._version
             c._tt_bf16, c._tt_bf16_version = yb[1], c._version
@@ -118,12 +119,17 @@ class TwoTowerTrainTask(nn.Module):
     mode are the positive-pair logits (the diagonal)."""
 
     def __init__(self, two_tower: TwoTower, loss: str = "bce", temperature: float = 1.0,
-                 precision: str = "fp32") -> None:
+                 precision: str = "fp32", negatives: str = "local", pg=None) -> None:
         super().__init__()
         if loss not in ("bce", "in_batch_softmax"):
             raise ValueError(f"unknown loss {loss}")
         if precision not in ("fp32", "bf16"):
             raise ValueError(f"unknown precision {precision}")
+        if negatives not in ("local", "global"):
+            raise ValueError(f"unknown negatives {negatives}")
+        # in-batch softmax inside a process group: "local" = per-rank negatives (no collective); "global" = the
+        # candidates of every rank (all-gather + reduce-scatter), i.e. the single-GPU loss of the global batch
+        self.negatives, self._pg = negatives, pg
         self.precision = precision  # "bf16": logits GEMM + softmax on tcgen05 (bf16 operands, fp32 accumulate)
         self.two_tower = two_tower
         self.loss_kind = loss
@@ -136,5 +142,6 @@ class TwoTowerTrainTask(nn.Module):
         if self.loss_kind == "bce":
             loss, logits = dot_bce_loss(query_embedding, candidate_embedding, batch.labels)
         else:
-            loss, logits = in_batch_softmax_loss(query_embedding, candidate_embedding, self.temperature, self.precision)
+            loss, logits = in_batch_softmax_loss(query_embedding, candidate_embedding, self.temperature, self.precision,
+                                                 self.negatives, self._pg)
         return loss, (loss.detach(), logits.detach(), batch.labels.detach())
