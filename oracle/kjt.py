@@ -98,6 +98,16 @@ def permute_2d_sparse_data(
     return out_len, pv, pw
 
 
+def _bucket_of(v: int, block: int, world_size: int) -> Tuple[int, int]:
+    """(bucket, local index) of one id.  fbgemm reads ids as unsigned (``uindex_t``) and sends an id past
+    ``block * W`` to bucket ``id % W`` with local index ``id / W`` -- so a bucket is always in ``[0, W)``."""
+    u = v % (1 << 64)
+    if block > 0 and u < block * world_size:
+        return u // block, u % block
+    q = u // world_size
+    return u % world_size, q - (1 << 64) if q >= (1 << 63) else q
+
+
 def block_bucketize_sparse_features(
     lengths: torch.Tensor, values: torch.Tensor, num_rows_per_feature: Sequence[int],
     world_size: int, batch_size: int,
@@ -122,7 +132,7 @@ def block_bucketize_sparse_features(
         block = -(-int(num_rows_per_feature[f]) // world_size)
         for b in range(B):
             for p in range(int(offsets[f * B + b]), int(offsets[f * B + b + 1])):
-                w = int(values[p]) // block
+                w, _ = _bucket_of(int(values[p]), block, world_size)
                 buckets_of.append(w)
                 new_lengths[(w * F + f) * B + b] += 1
     new_offsets = lengths_to_offsets(new_lengths).to(torch.int64)
@@ -138,7 +148,7 @@ def block_bucketize_sparse_features(
                 slot = (w * F + f) * B + b
                 dst = int(cursor[slot])
                 cursor[slot] += 1
-                new_values[dst] = int(values[p]) - w * block
+                new_values[dst] = _bucket_of(int(values[p]), block, world_size)[1]
                 unbucketize[p] = dst
     return new_lengths, new_values, unbucketize
 
@@ -161,6 +171,8 @@ def block_bucketize_vectorized(
     blk = block[f]
     w = values // blk
     local = values - w * blk
+    for p in torch.nonzero((values < 0) | (values >= blk * world_size)).flatten().tolist():   # fbgemm's fallback
+        w[p], local[p] = _bucket_of(int(values[p]), int(blk[p]), world_size)
     slot = (w * F + f) * B + b
     new_lengths = torch.bincount(slot, minlength=world_size * F * B).to(lengths.dtype)
     order = torch.argsort(slot, stable=True)

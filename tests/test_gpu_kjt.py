@@ -75,6 +75,26 @@ def test_block_bucketize(cuda, F, B, L, W, rows):
     assert torch.equal((nv.cpu() + w_of * blocks[f_of])[unb.cpu()], v)
 
 
+def test_block_bucketize_out_of_range_ids(cuda):
+    """Ids outside [0, block*W) (a KJT built without the reference's modulo, negative ids) take fbgemm's fallback
+    bucket = id % W, local = id / W on unsigned ids: no out-of-bounds write, same answer as the oracle."""
+    from two_tower_recommender_model_b200.functional import block_bucketize
+    F, B, W, rows = 2, 300, 4, [1000, 37]
+    v, l = random_kjt(["a", "b"], rows, B, 5, seed=3)
+    g = torch.Generator().manual_seed(4)
+    bad = torch.randperm(v.numel(), generator=g)[: v.numel() // 3]
+    v[bad] = torch.randint(-5000, 5000, (bad.numel(),), generator=g)
+    v[bad[:4]] = torch.tensor([-1, -(2 ** 63), 2 ** 63 - 1, 4000])
+    want = block_bucketize_vectorized(l, v, rows, W, B)
+    loop = oracle.block_bucketize_sparse_features(l, v, rows, W, B)
+    assert all(torch.equal(a, b) for a, b in zip(want, loop))
+    off = oracle.lengths_to_offsets(l)
+    guard = torch.full((W * F * B + 64,), -7, dtype=torch.int32, device=cuda)     # nothing may land past new_lengths
+    nl, no, nv, unb = block_bucketize(l.to(cuda), off.to(cuda), v.to(cuda), torch.tensor(rows), F, B, W)
+    assert torch.equal(nl.cpu(), want[0]) and torch.equal(nv.cpu(), want[1]) and torch.equal(unb.cpu(), want[2])
+    assert int(nl.sum()) == v.numel() and bool((guard == -7).all())
+
+
 @pytest.mark.parametrize("F,B,W,rows", [(2, 1000, 4, [1500, 900]), (1, 9, 2, [10]), (3, 4097, 8, [100_000_000, 50, 12345])])
 def test_from_id_columns_range_is_one_bucket_of_block_bucketize(cuda, F, B, W, rows):
     """tt_kjt_from_columns_range (row-wise shard of a dense id-column batch) == the reference transform

@@ -58,6 +58,20 @@ def test_bucketize_kat():
         assert nl.tolist() == c["new_lengths"] and nv.tolist() == c["new_values"] and unb.tolist() == c["unbucketize"]
 
 
+def test_bucketize_out_of_range_ids_kat():
+    """fbgemm's fallback, hand-computed: rows=10, W=3 -> block 4, block*W = 12.  id 11 is still in the block range
+    (bucket 2, local 3); id 12 and 100 are past it: bucket id % 3, local id // 3; id -1 is read as 2^64-1:
+    bucket (2^64-1) % 3 = 0, local (2^64-1) // 3 = 6148914691236517205."""
+    v = T([11, 12, 100, -1])
+    l = T([1, 1, 1, 1], dtype=torch.int32)
+    for fn in (oracle.block_bucketize_sparse_features, block_bucketize_vectorized):
+        nl, nv, unb = fn(l, v, [10], 3, 4)
+        #            w=0: b0 b1 b2 b3 | w=1          | w=2
+        assert nl.tolist() == [0, 1, 0, 1, 0, 0, 1, 0, 1, 0, 0, 0]
+        assert nv.tolist() == [4, 6148914691236517205, 33, 3]
+        assert unb.tolist() == [3, 0, 2, 1]
+
+
 @pytest.mark.parametrize("seed", range(5))
 def test_bucketize_loop_equals_vectorized(seed):
     F_, B, W = 3, 17, 4

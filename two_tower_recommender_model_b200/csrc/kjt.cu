@@ -272,7 +272,21 @@ __global__ void permute_values_kernel(const int32_t* __restrict__ permute,
 // ---------------------------------------------------------------------------
 // block_bucketize_sparse_features: one thread owns one input bag (f,b) and with
 // it every output bag (w,f,b), so counters need no atomics and order is stable.
+// Ids are taken as UNSIGNED, as fbgemm's uindex_t does: an id past block*W (or a
+// negative one) goes to bucket id % W with local index id / W -- fbgemm's
+// fallback -- so the bucket always lies in [0, W) and nothing is written out of bounds.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void bucket_of_id(int64_t id, int64_t block, int64_t W, int64_t* w, int64_t* local) {
+  const uint64_t u = (uint64_t)id, ub = (uint64_t)block, uw = (uint64_t)W;
+  if (ub != 0 && u < ub * uw) {
+    *w = (int64_t)(u / ub);
+    *local = (int64_t)(u - (u / ub) * ub);
+  } else {
+    *w = (int64_t)(u % uw);
+    *local = (int64_t)(u / uw);
+  }
+}
+
 __global__ void bucketize_count_kernel(const int32_t* __restrict__ offsets,
                                        const int64_t* __restrict__ values,
                                        const int64_t* __restrict__ num_rows, int64_t F, int64_t B,
@@ -283,7 +297,8 @@ __global__ void bucketize_count_kernel(const int32_t* __restrict__ offsets,
   int64_t f = bag / B, b = bag - f * B;
   int64_t block = (num_rows[f] + W - 1) / W;
   for (int p = offsets[bag]; p < offsets[bag + 1]; ++p) {
-    int64_t w = values[p] / block;
+    int64_t w, local;
+    bucket_of_id(values[p], block, W, &w, &local);
     bucket_of[p] = (int32_t)w;
     new_lengths[(w * F + f) * B + b] += 1;
   }
@@ -300,11 +315,12 @@ __global__ void bucketize_scatter_kernel(const int32_t* __restrict__ offsets,
   int64_t f = bag / B, b = bag - f * B;
   int64_t block = (num_rows[f] + W - 1) / W;
   for (int p = offsets[bag]; p < offsets[bag + 1]; ++p) {
-    int64_t w = bucket_of[p];
+    int64_t w, local;
+    bucket_of_id(values[p], block, W, &w, &local);
     int64_t slot = (w * F + f) * B + b;
     int dst = cursor[slot];
     cursor[slot] = dst + 1;
-    new_values[dst] = values[p] - w * block;
+    new_values[dst] = local;
     if (unbucketize) unbucketize[p] = dst;
   }
 }

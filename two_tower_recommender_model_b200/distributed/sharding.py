@@ -271,6 +271,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
         tw_local_cfgs: List[EmbeddingBagConfig] = []
         rw_local_cfgs: List[EmbeddingBagConfig] = []
         self._rw_block: Dict[str, int] = {}
+        self._rw_feat_block: Dict[str, int] = {}
         self._shard_info: Dict[str, Tuple[str, int, int]] = {}   # table -> (kind, row offset, local rows)
         for c in self._configs:
             ps = plan[c.name]
@@ -292,6 +293,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
                 local_rows = max(0, min(block, c.num_embeddings - r * block))
                 for f in c.feature_names:
                     self._rw.features.append(f)
+                    self._rw_feat_block[f] = block
                     self._rw.feat_dim[f], self._rw.feat_rows[f] = c.embedding_dim, c.num_embeddings
                     if c.pooling == PoolingType.MEAN:
                         self._rw.mean_features.append(f)
@@ -363,7 +365,8 @@ class ShardedEmbeddingBagCollection(nn.Module):
         lengths, values = sub.lengths(), sub.values()
         if grp.kind == "row_wise":
             F = len(grp.features)
-            rows = torch.tensor([grp.feat_rows[f] for f in grp.features], dtype=torch.int64)
+            # the kernel derives block = ceil(rows / W): hand it block * W so that a plan's own block_size is honoured
+            rows = torch.tensor([self._rw_feat_block[f] * W for f in grp.features], dtype=torch.int64)
             new_len, _new_off, new_val, _unb = self._bucketize(lengths, sub.offsets(), values, rows, F, B, W)
             lengths, values = new_len, new_val
             seg_per_dest = [F] * W
