@@ -334,6 +334,11 @@ int tt_inbatch_softmax_backward_f32(const float* q, const float* c, const float*
  * bit-reproducible from run to run (the one-pass kernel adds partial sums in L2 in CTA arrival order).
  * The environment variable TT_SOFTMAX_BWD=split selects mode 1 at load time. */
 int tt_set_softmax_backward_mode(int32_t mode);
+/* 64 < d <= 256: on = 1 (default) runs the TS-form kernels -- the CTA's own rows are stored once into TMEM as the
+ * A operand, the streamed tile is the only shared-memory operand and doubles as the MN-major B operand of the
+ * second product, so qt / ct are not read and may be null; on = 0 keeps the SS-form kernels (qt / ct needed).
+ * The environment variable TT_SOFTMAX_WIDE=0 selects 0 at load time. */
+int tt_set_softmax_wide_mode(int32_t on);
 size_t tt_inbatch_softmax_bf16_workspace_bytes(int64_t B);
 int tt_inbatch_softmax_forward_bf16(const void* q_bf16, int64_t ldq, const void* c_bf16, int64_t ldc,
                                     int64_t B, int64_t d, float inv_temperature, float* lse,

@@ -56,6 +56,7 @@ def test_gemm_bf16_epilogues(cuda, M, N, K):
 @pytest.mark.parametrize("B,d,T", [(128, 64, 1.0), (256, 64, 1.0), (1000, 64, 0.5), (4096, 64, 1.0), (777, 128, 1.0),
                                    (300, 36, 2.0), (513, 256, 1.0), (640, 192, 1.0), (65, 8, 1.0), (2000, 48, 1.0),
                                    (8192, 64, 0.25), (3001, 20, 1.0), (200, 30, 1.0),
+                                   (8192, 256, 1.0), (4100, 200, 0.5), (8200, 128, 1.0), (2050, 100, 1.0), (129, 256, 1.0),   # cfg4's width
                                    (1000, 64, 0.01), (4096, 64, 0.03)])   # small T: logits up to 400 -> the online-max forward path
 def test_in_batch_softmax_tensor_core(cuda, B, d, T):
     """bf16 tensor-core softmax vs float64 math on the bf16-rounded q, c.
@@ -229,17 +230,41 @@ def test_fused_towers_match_per_layer_path(cuda, B, i, h, o):
         torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-2 * float(b.abs().max()), msg=lambda m: f"param {k}: {m}")
 
 
-def test_in_batch_softmax_full_size_closed_form(cuda):
-    """BASELINE configs[1] size (B = 65536, d = 64), where an O(B^2) reference is out of reach: with every candidate
+@pytest.mark.parametrize("B,d", [(3000, 256), (1025, 136), (2048, 192)])
+def test_in_batch_softmax_wide_kernels_match_ss_form(cuda, B, d):
+    """64 < d <= 256: the TS-form backward (X resident in TMEM, streamed tile reused as MN-major B) against the SS-form
+    kernels of round 1 on the same inputs.  Same math, same bf16 rounding of P, different accumulation order only."""
+    from two_tower_recommender_model_b200 import functional as F
+    g = torch.Generator().manual_seed(B)
+    q = (torch.rand(B, d, generator=g) * (2.0 / d ** 0.5)).to(cuda)
+    c = (torch.rand(B, d, generator=g) * (2.0 / d ** 0.5)).to(cuda)
+    out = {}
+    try:
+        for wide in (True, False):
+            F.set_softmax_wide(wide)
+            qd, cd = q.clone().requires_grad_(True), c.clone().requires_grad_(True)
+            loss, _ = F.in_batch_softmax_loss(qd, cd, 1.0, precision="bf16")
+            loss.backward()
+            out[wide] = (loss.detach(), qd.grad, cd.grad)
+    finally:
+        F.set_softmax_wide(True)
+    assert torch.equal(out[True][0], out[False][0])                      # same forward kernel
+    for a, b in zip(out[True][1:], out[False][1:]):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()))
+
+
+@pytest.mark.parametrize("B,d", [(65536, 64), (32768, 256)])
+def test_in_batch_softmax_full_size_closed_form(cuda, B, d):
+    """BASELINE configs[1] size (B = 65536, d = 64) and cfg4's width (d = 256), where an O(B^2) reference is out of reach: with every candidate
     equal to one vector c0 the logits of a row are constant, so P = 1/B exactly and everything has a closed form:
         loss = log B,   dq = 0,   dc_j = (mean_i q_i - q_j) / (B T).
     Exercises forward + the one-pass backward (P.c, P^T.q, TMA reduce-add over 256 row blocks) at full size."""
     import math
     from two_tower_recommender_model_b200.functional import in_batch_softmax_loss
-    B, d, T = 65536, 64, 0.5
+    T = 0.5
     g = torch.Generator().manual_seed(1)
     q = (torch.rand(B, d, generator=g) * 0.25).bfloat16().float()        # exactly representable operands
-    c0 = (torch.rand(d, generator=g) * 0.25).bfloat16().float()
+    c0 = (torch.rand(d, generator=g) * (16.0 / d)).bfloat16().float()
     c = c0.repeat(B, 1)
     qd, cd = q.to(cuda).requires_grad_(True), c.to(cuda).requires_grad_(True)
     loss, diag = in_batch_softmax_loss(qd, cd, T, precision="bf16")

@@ -115,6 +115,31 @@ def towers(args):
     print(f"towers fwd+bwd {ms:.3f} ms")
 
 
+def mlp(args):
+    """One tower of arbitrary widths through the per-layer tcgen05 GEMM path (cfg4: --din 128 --layers 1024,512,256),
+    forward + backward, per-call times and the TFLOP/s of the GEMM calls (2*M*N*K each)."""
+    dev = torch.device("cuda:0")
+    B = args.B
+    layers = [int(x) for x in args.layers.split(",")]
+    m = tt.MLP(args.din, layers, device=dev, precision=args.precision)
+    x = torch.randn(B, args.din, device=dev, requires_grad=True)
+    dy = torch.randn(B, layers[-1], device=dev)
+    N.enable_timing(True)
+
+    def run():
+        m(x).backward(dy)
+    ms = timed(run, args.iters, warmup=args.warmup)
+    dims = [args.din] + layers
+    flops = sum(2.0 * B * a * b for a, b in zip(dims[:-1], dims[1:]))
+    gemm_ms = 0.0
+    for k, v in N.timing_summary().items():
+        print(f"{k:42s} {v['ms'] * 1e3:9.1f} us  x{v['calls']}")
+        if "gemm" in k:
+            gemm_ms += v["ms"] * v["calls"] / max(args.iters, 1)
+    print(f"mlp {dims} B={B}: fwd+bwd {ms:.3f} ms = {3 * flops / ms / 1e9:.1f} TFLOP/s over the whole call chain (3 GEMMs per layer); "
+          f"GEMM calls alone {gemm_ms:.3f} ms = {3 * flops / max(gemm_ms, 1e-9) / 1e9:.1f} TFLOP/s")
+
+
 def topk(args):
     dev = torch.device("cuda:0")
     q = torch.randn(args.Q, args.d, device=dev)
@@ -126,10 +151,12 @@ def topk(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["softmax", "ebc", "towers", "topk"])
+    ap.add_argument("what", choices=["softmax", "ebc", "towers", "mlp", "topk"])
     ap.add_argument("--B", type=int, default=65536)
     ap.add_argument("--d", type=int, default=64)
     ap.add_argument("--L", type=int, default=1)
+    ap.add_argument("--din", type=int, default=128)
+    ap.add_argument("--layers", default="1024,512,256")
     ap.add_argument("--Q", type=int, default=4096)
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--rows", type=int, default=10_000_000)
@@ -138,4 +165,4 @@ if __name__ == "__main__":
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--zipf", type=float, default=0.0, help="ebc: draw ids from Zipf(alpha) instead of uniform")
     a = ap.parse_args()
-    {"softmax": softmax, "ebc": ebc, "towers": towers, "topk": topk}[a.what](a)
+    {"softmax": softmax, "ebc": ebc, "towers": towers, "mlp": mlp, "topk": topk}[a.what](a)

@@ -112,6 +112,7 @@ SIGNATURES = {
     "tt_towers_backward_workspace_bytes": (c_size_t, [c_int64]),
     "tt_towers_backward_fused": (c_int32, [POINTER(TowerBackward), c_int32, c_int64, c_int32, c_int32, c_int32, _P, c_size_t, _P]),
     "tt_set_softmax_backward_mode": (c_int32, [c_int32]),
+    "tt_set_softmax_wide_mode": (c_int32, [c_int32]),
     "tt_inbatch_softmax_bf16_workspace_bytes": (c_size_t, [c_int64]),
     "tt_inbatch_softmax_forward_bf16": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "tt_inbatch_softmax_backward_bf16": (c_int32, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64,

@@ -1038,6 +1038,237 @@ lse_merge_kernel(const float* __restrict__ ml, int splits, int B, const float* _
   }
 }
 
+// ------------------------------------------------------------------ wide embeddings (64 < d <= 256): A operand resident in TMEM
+// At d = 256 a [128 x 256] bf16 operand tile is 64 KB.  The SS-form kernels above re-read the CTA's own Q / X tile from
+// shared memory for every column tile (A = 4 KB per tcgen05.mma) next to the B reads.  Here the CTA's rows are stored ONCE
+// into TMEM as bf16 (D/2 columns per 128 rows) and every S product is a TS-form MMA (A from TMEM), so shared memory carries
+// only the streamed operand and the 64 KB the X tile occupied become two more pipeline stages:
+// (The forward keeps the SS form: its N = 128 products read 8 KB per 64 tensor clocks, exactly what the pipe delivers, and it
+// measures 1330-1370 TFLOP/s at d = 256 = 95 % of the sustained bf16 peak.  The SS-form backward measured 51 %: its N = 64
+// S products are operand-bound and, worse, 64 KB stages left room for only two of them, so every tile waited out a TMA
+// round trip.)
+//   backward: one row tile per CTA; TMEM = O [0, D) | X [D, 3D/2) | S/P stages.  The streamed Y tile [NT x D] (K-major B of
+//             S = X Y^T) is ALSO the B operand of O += P Y through an MN-major descriptor, so neither a transposed copy of
+//             Y in HBM nor a second TMA load exists: 32 KB write + 64 KB reads per 1024 tensor clocks (d = 256, NT = 64).
+// The two softmax groups split every S tile by columns (group h takes columns [h NT/2, (h+1) NT/2)) so that P is back in
+// TMEM half a tile time after S lands; P is written in place over the group's OWN S columns.
+template <int KB>
+struct WideBwdCfg {
+  static constexpr int D = KB * 64;
+  static constexpr int NT = KB <= 2 ? 128 : 64;            // Y rows per tile = S columns per TMEM stage
+  static constexpr int NSP = KB == 3 ? 3 : 2;              // S/P stages
+  static constexpr int O_COL = 0, X_COL = D;
+  static constexpr int S_COL = 512 - NSP * NT;
+  static_assert(X_COL + D / 2 <= S_COL, "TMEM budget");
+  static constexpr int THREADS = 64 + 2 * 128;
+  static constexpr int Y_BYTES = KB * NT * 128;            // KB sub-tiles [NT x 64] bf16, 128-byte swizzle
+  static constexpr int STAGES = 4;
+  static constexpr int LOOKAHEAD = NSP - 1;
+  static constexpr int SMEM = STAGES * Y_BYTES + 1024 + 256 + 2 * 128 * 4 + 256;
+};
+
+// this thread's row of a row-major bf16 matrix -> TMEM columns [tcol, tcol + ncols/2) of its lane, ncols a multiple of 32;
+// elements at or past `d` (and whole rows when !valid) are zero
+__device__ __forceinline__ void row_to_tmem(const __nv_bfloat16* __restrict__ row, bool valid, int d, int col0, int ncols,
+                                            uint32_t tcol, bool vec_ok) {
+#pragma unroll 1
+  for (int c = col0; c < col0 + ncols; c += 32) {
+    uint32_t w[16];
+    if (valid && vec_ok && c + 32 <= d) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const uint4 x = *reinterpret_cast<const uint4*>(row + c + v * 8);
+        w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int e = c + 2 * j;
+        const uint32_t lo = (valid && e < d) ? static_cast<uint32_t>(__bfloat16_as_ushort(row[e])) : 0u;
+        const uint32_t hi = (valid && e + 1 < d) ? static_cast<uint32_t>(__bfloat16_as_ushort(row[e + 1])) : 0u;
+        w[j] = lo | (hi << 16);
+      }
+    }
+    tmem_st16(tcol + ((c - col0) >> 1), w);
+  }
+}
+
+template <int KB, bool ROW>
+__global__ void __launch_bounds__(WideBwdCfg<KB>::THREADS, 1)
+tc_softmax_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmY, const __nv_bfloat16* __restrict__ x_rows, int64_t ldx,
+                           int B, int d, float scale2, const float* __restrict__ lse, const float* __restrict__ yf,
+                           int64_t ld_yf, const float* __restrict__ relu_mask, int64_t ld_mask, float out_scale,
+                           float* __restrict__ out, int64_t ld_out) {
+  using Cfg = WideBwdCfg<KB>;
+  constexpr int NT = Cfg::NT, S = Cfg::STAGES, D = Cfg::D, HC = NT / 2;   // HC: S columns per softmax group
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sY = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sY + S * Cfg::Y_BYTES);
+  uint64_t* x_ready = bars;
+  uint64_t* y_full = bars + 1;           // [S]
+  uint64_t* y_empty = y_full + S;        // [S]
+  uint64_t* s_full = y_empty + S;        // [NSP]
+  uint64_t* p_full = s_full + Cfg::NSP;  // [NSP]
+  uint64_t* o_full = p_full + Cfg::NSP;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float* lse_tile = reinterpret_cast<float*>(bars + 32);      // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  const int Tall = (B + NT - 1) / NT;
+  const int Tper = (Tall + gridDim.y - 1) / gridDim.y;
+  const int t0 = blockIdx.y * Tper;
+  const int T = max(0, min(Tper, Tall - t0));             // the host guarantees T >= 1
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmY);
+    mbar_init(x_ready, 256);
+    for (int s = 0; s < S; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
+    for (int s = 0; s < Cfg::NSP; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256); }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int t = 0; t < T; ++t) {
+        const int s = t % S;
+        uint8_t* st = sY + s * Cfg::Y_BYTES;
+        mbar_wait_relaxed(&y_empty[s], ((t / S) & 1) ^ 1);
+        mbar_expect_tx(&y_full[s], Cfg::Y_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(st + kb * NT * 128, &tmY, &y_full[s], kb * 64, (t0 + t) * NT);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc1 = idesc_bf16_f32(128, NT);
+    constexpr uint32_t idesc2 = idesc_bf16_f32(128, D) | kIdescBMnMajor;
+    if (elect_one()) {
+      auto issue_gemm1 = [&](int t) {
+        const int s = t % S, as = t % Cfg::NSP;
+        mbar_wait_relaxed(&y_full[s], (t / S) & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(sY + s * Cfg::Y_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t db = smem_desc_k_sw128(st + kb * NT * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ts(tmem_base + Cfg::S_COL + as * NT, tmem_base + Cfg::X_COL + kb * 32 + k * 8, db + 2 * k, idesc1, (kb | k) != 0);
+        }
+        tc_commit(&s_full[as]);
+      };
+      mbar_wait_relaxed(x_ready, 0);
+      tc_fence_after();
+      for (int i = 0; i < Cfg::LOOKAHEAD && i < T; ++i) issue_gemm1(i);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % S, as = t % Cfg::NSP;
+        // S(t + LOOKAHEAD) overwrites the stage whose P was consumed by the O-product issued one iteration ago
+        // (tcgen05.mma executes in issue order), and keeps the tensor pipe busy while the softmax groups turn S(t) into P(t)
+        if (t + Cfg::LOOKAHEAD < T) issue_gemm1(t + Cfg::LOOKAHEAD);
+        mbar_wait_relaxed(&p_full[as], (t / Cfg::NSP) & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(sY + s * Cfg::Y_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < NT / 16; ++kk) {     // O[128, D] += P[:, 16kk..16kk+16) . Y[16kk..16kk+16, :]
+          // P columns of softmax group h live at stage columns [h * HC, h * HC + HC / 2) (bf16 pairs)
+          const uint32_t pa = tmem_base + Cfg::S_COL + as * NT + (kk / (HC / 16)) * HC + (kk % (HC / 16)) * 8;
+          const uint64_t db = smem_desc_mn_sw128(st + kk * 2048, NT * 128, 1024);
+          mma_ts(tmem_base + Cfg::O_COL, pa, db, idesc2, (t | kk) != 0);
+        }
+        tc_commit(&y_empty[s]);
+        if (t == T - 1) tc_commit(o_full);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;                   // softmax group = column half of every S tile
+    const int r_in = q * 32 + lane;
+    const int row = m0 + r_in;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    // ---- this CTA's rows -> TMEM (bf16, A operand of every S product): group h stores column half h
+    {
+      const bool vec_ok = (ldx % 8) == 0 && (reinterpret_cast<uintptr_t>(x_rows) & 15) == 0;
+      row_to_tmem(x_rows + (int64_t)row * ldx, row < B, d, h * (D / 2), D / 2, trow + Cfg::X_COL + h * (D / 4), vec_ok);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(x_ready);
+    }
+    const float lrow = (ROW && row < B) ? lse[row] * kLog2e : 0.f;
+    float* lse_g = lse_tile + h * 128;
+    for (int t = 0; t < T; ++t) {
+      const int n0 = (t0 + t) * NT + h * HC;          // first logit column of this group
+      const int as = t % Cfg::NSP;
+      const uint32_t tsp = trow + Cfg::S_COL + as * NT + h * HC;
+      if (!ROW) {
+        if (r_in < HC) lse_g[r_in] = (n0 + r_in < B) ? lse[n0 + r_in] * kLog2e : 0.f;
+        group_bar_sync(h);
+      }
+      mbar_wait(&s_full[as], (t / Cfg::NSP) & 1);
+      tc_fence_after();
+      const bool tail = n0 + HC > B;
+      uint32_t va[32];
+      if (HC == 32) {
+        tmem_ld32(tsp, va);
+        tmem_ld_wait();
+        if (!tail) p_chunk<ROW, false>(va, tsp, lse_g, lrow, scale2, n0, B);
+        else p_chunk<ROW, true>(va, tsp, lse_g, lrow, scale2, n0, B);
+      } else {
+        uint32_t vb[32];
+        tmem_ld32(tsp, va);
+        tmem_ld32(tsp + 32, vb);
+        tmem_ld_wait();                                // both chunks are in registers before P overwrites their columns
+        if (!tail) {
+          p_chunk<ROW, false>(va, tsp, lse_g, lrow, scale2, n0, B);
+          p_chunk<ROW, false>(vb, tsp + 16, lse_g + 32, lrow, scale2, n0 + 32, B);
+        } else {
+          p_chunk<ROW, true>(va, tsp, lse_g, lrow, scale2, n0, B);
+          p_chunk<ROW, true>(vb, tsp + 16, lse_g + 32, lrow, scale2, n0 + 32, B);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[as]);
+      if (!ROW) group_bar_sync(h);   // lse_g is rewritten at the top of the next iteration
+    }
+    // ---- O -> out = out_scale * (O - Y_r), optionally gated by relu_mask > 0 (the groups alternate 32-column chunks)
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = h * 32; c0 < D; c0 += 64) {
+      if (c0 >= d) break;
+      uint32_t v[32];
+      tmem_ld32(trow + Cfg::O_COL + c0, v);
+      tmem_ld_wait();
+      if (row < B) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = c0 + j;
+          if (col < d) {
+            float o = __uint_as_float(v[j]);
+            if (blockIdx.y == 0) o -= yf[(int64_t)row * ld_yf + col];
+            o *= out_scale;
+            if (relu_mask != nullptr && !(relu_mask[(int64_t)row * ld_mask + col] > 0.f)) o = 0.f;
+            if (gridDim.y == 1) out[(int64_t)row * ld_out + col] = o;
+            else atomicAdd(&out[(int64_t)row * ld_out + col], o);   // two addends: order-independent
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // Two column splits once there are at least two tiles per split and enough row blocks to matter.
 static int column_splits(int64_t B, int NT) {
   const int64_t tall = (B + NT - 1) / NT;
@@ -1079,6 +1310,28 @@ static int launch_bwd(const CUtensorMap& tx, const CUtensorMap& ty, const CUtens
   tc_softmax_bwd_kernel<KB, ROW><<<grid, BwdCfg<KB>::THREADS, BwdCfg<KB>::SMEM, s>>>(
       tx, ty, tyt, B, d, scale2, lse, yf, ld_yf, mask, ld_mask, out_scale, out, ld_out);
   TT_CHECK_LAUNCH("tc_softmax_bwd");
+  return TT_OK;
+}
+
+template <int KB, bool ROW>
+static int launch_bwd_wide(const CUtensorMap& ty, const void* x_bf16, int64_t ldx, int B, int d, float scale2, const float* lse,
+                           const float* yf, int64_t ld_yf, const float* mask, int64_t ld_mask, float out_scale, float* out,
+                           int64_t ld_out, int splits, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_softmax_bwd_wide_kernel<KB, ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         WideBwdCfg<KB>::SMEM);
+    if (e != cudaSuccess) return fail(TT_ERR_CUDA, "softmax_bwd_wide smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  if (splits > 1) {  // the splits accumulate into `out`
+    cudaError_t e = cudaMemset2DAsync(out, (size_t)ld_out * 4, 0, (size_t)d * 4, (size_t)B, s);
+    if (e != cudaSuccess) return fail(TT_ERR_CUDA, "softmax_bwd_wide memset: %s", cudaGetErrorString(e));
+  }
+  dim3 grid((B + 127) / 128, splits);
+  tc_softmax_bwd_wide_kernel<KB, ROW><<<grid, WideBwdCfg<KB>::THREADS, WideBwdCfg<KB>::SMEM, s>>>(
+      ty, static_cast<const __nv_bfloat16*>(x_bf16), ldx, B, d, scale2, lse, yf, ld_yf, mask, ld_mask, out_scale, out, ld_out);
+  TT_CHECK_LAUNCH("tc_softmax_bwd_wide");
   return TT_OK;
 }
 
@@ -1146,7 +1399,16 @@ using namespace tt::tc;
 
 static int g_softmax_bwd_mode = [] { const char* v = getenv("TT_SOFTMAX_BWD"); return (v != nullptr && strcmp(v, "split") == 0) ? 1 : 0; }();
 
+// 64 < d <= 256: the TS-form kernels (A operand resident in TMEM); TT_SOFTMAX_WIDE=0 keeps the SS-form kernels (A/B runs)
+static int g_softmax_wide = [] { const char* v = getenv("TT_SOFTMAX_WIDE"); return (v != nullptr && strcmp(v, "0") == 0) ? 0 : 1; }();
+
 extern "C" {
+
+int tt_set_softmax_wide_mode(int32_t on) {
+  TT_CHECK_ARG(on == 0 || on == 1, "set_softmax_wide_mode: 0 (SS-form kernels) or 1 (TS-form kernels for d > 64)");
+  g_softmax_wide = on;
+  return TT_OK;
+}
 
 int tt_set_softmax_backward_mode(int32_t mode) {
   TT_CHECK_ARG(mode == 0 || mode == 1, "set_softmax_backward_mode: mode must be 0 (auto) or 1 (two-pass, deterministic)");
@@ -1226,6 +1488,30 @@ int tt_inbatch_softmax_backward_bf16(const void* q_bf16, int64_t ldq, const void
     return launch_bwd_fused(q_bf16, ldq, c_bf16, ldc, q_f32, ldqf, c_f32, ldcf, lse, (int)B, (int)d, scale2, out_scale,
                             relu_gate ? q_f32 : nullptr, relu_gate ? c_f32 : nullptr, dq, lddq, dc, lddc, grad_scale_dev, s);
   if (grad_scale_dev != nullptr) return fail(TT_ERR_UNSUPPORTED, "inbatch_softmax_backward_bf16: grad_scale_dev needs the one-pass path (d <= 64)");
+  if (KB >= 2 && g_softmax_wide) {
+    // TS-form two-pass kernels: row-major operands only (the streamed tile doubles as the MN-major B of the second product)
+    const int NTW = KB <= 2 ? 128 : 64;
+    const int sp = column_splits(B, NTW);
+    CUtensorMap tqn, tcn;
+    int rc;
+    if ((rc = make_tmap_bf16_2d(&tqn, q_bf16, B, d, ldq, NTW))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tcn, c_bf16, B, d, ldc, NTW))) return rc;
+    const float* gq = relu_gate ? q_f32 : nullptr;
+    const float* gc = relu_gate ? c_f32 : nullptr;
+#define TT_LBW(KBV)                                                                                                          \
+  do {                                                                                                                       \
+    rc = launch_bwd_wide<KBV, true>(tcn, q_bf16, ldq, (int)B, (int)d, scale2, lse, c_f32, ldcf, gq, ldqf, out_scale, dq, lddq, sp, s); \
+    if (rc) return rc;                                                                                                       \
+    rc = launch_bwd_wide<KBV, false>(tqn, c_bf16, ldc, (int)B, (int)d, scale2, lse, q_f32, ldqf, gc, ldcf, out_scale, dc, lddc, sp, s); \
+  } while (0)
+    switch (KB) {
+      case 2: TT_LBW(2); break;
+      case 3: TT_LBW(3); break;
+      default: TT_LBW(4); break;
+    }
+#undef TT_LBW
+    return rc;
+  }
   TT_CHECK_ARG(qt_bf16 && ct_bf16, "inbatch_softmax_backward_bf16: the two-pass kernels need the transposed copies");
   CUtensorMap tq128, tc128, tqn, tcn, tqt, tct;
   int rc;

@@ -197,6 +197,17 @@ def set_deterministic_softmax_backward(on: bool) -> None:
     _deterministic_softmax_backward = bool(on)
 
 
+_softmax_wide = os.environ.get("TT_SOFTMAX_WIDE") != "0"
+
+
+def set_softmax_wide(on: bool) -> None:
+    """``True`` (default): in-batch softmax with 64 < d <= 256 runs the TS-form kernels (the CTA's rows resident in
+    TMEM, no transposed operand copies); ``False``: the SS-form kernels of round 1 (kept for A/B comparisons)."""
+    global _softmax_wide
+    N.call("tt_set_softmax_wide_mode", 1 if on else 0)
+    _softmax_wide = bool(on)
+
+
 class InBatchSoftmaxLossTC(torch.autograd.Function):
     """Same loss on the tensor cores (tcgen05): bf16 operands, fp32 accumulation in TMEM,
     softmax out of TMEM; the backward recomputes S tile by tile and feeds P back to the tensor
@@ -208,15 +219,15 @@ class InBatchSoftmaxLossTC(torch.autograd.Function):
         c = _f32c(c, "candidate_embedding")
         B, d = q.shape
         dev = q.device
-        # d <= 64: the fused one-pass backward reads q / c row-major only (MN-major tcgen05 operands);
-        # wider embeddings use the two-pass kernels, which want the transposed copies as well
-        if d > 64 or d % 4 != 0 or _deterministic_softmax_backward:
+        # d <= 64: the fused one-pass backward reads q / c row-major only (MN-major tcgen05 operands), and so do the
+        # TS-form kernels for wider embeddings; the SS-form two-pass kernels want the transposed copies as well
+        if (d > 64 and not _softmax_wide) or (d <= 64 and (d % 4 != 0 or _deterministic_softmax_backward)):
             qb, qbt = cast_bf16(q, both=True)
             cb, cbt = cast_bf16(c, both=True)
         else:
             # the fused towers already produced the bf16 copies (same rounding): no cast kernels
-            qb = q_bf16 if q_bf16 is not None else cast_bf16(q)
-            cb = c_bf16 if c_bf16 is not None else cast_bf16(c)
+            qb = q_bf16 if (q_bf16 is not None and d <= 64) else cast_bf16(q)
+            cb = c_bf16 if (c_bf16 is not None and d <= 64) else cast_bf16(c)
             qbt = cbt = None
         lse = torch.empty(B, dtype=torch.float32, device=dev)
         diag = torch.empty(B, dtype=torch.float32, device=dev)
@@ -236,7 +247,7 @@ class InBatchSoftmaxLossTC(torch.autograd.Function):
         dq = torch.empty_like(q)
         dc = torch.empty_like(c)
         # one-pass path (d <= 64): the incoming dLoss is multiplied in by the finalize kernel (device scalar, no sync)
-        fused = qbt is None and g_loss.numel() == 1 and g_loss.dtype == torch.float32 and g_loss.is_cuda
+        fused = qbt is None and d <= 64 and g_loss.numel() == 1 and g_loss.dtype == torch.float32 and g_loss.is_cuda
         gs = g_loss.contiguous() if fused else None
         N.call("tt_inbatch_softmax_backward_bf16", N.ptr(qb), qb.stride(0), N.ptr(cb), cb.stride(0),
                N.ptr(qbt), qbt.stride(0) if qbt is not None else 0, N.ptr(cbt), cbt.stride(0) if cbt is not None else 0,
