@@ -519,6 +519,13 @@ def run_ours(args):
     if world == 1:
         line["retrieval"] = retrieval_probe(dev)
         line["retrieval_large"] = retrieval_probe(dev, n_items=10_000_000, n_queries=131072)
+    if world == 1 and not args.no_other_configs:
+        # BASELINE configs[2] and configs[3] at full size on this GPU (eager steps, CUDA events); configs[1] stays the `value`
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import run_configs
+        torch.cuda.empty_cache()
+        line["cfg3"] = run_configs.config3()
+        line["cfg4"] = run_configs.config4()
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, steps=1, warmup=1)
         line["cpu_baseline_cfg1"] = cpu_baseline_cfg1()
@@ -695,6 +702,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the configs[2] / configs[3] blocks (102 GB of tables)")
     ap.add_argument("--exchange", default=os.environ.get("TT_EXCHANGE", "peer"), choices=["nccl", "peer"],
                     help="N>1: output exchange by NCCL all-to-all, or fused into the lookup kernels over NVLink peer memory")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly (N>1: through TrainPipelineSparseDist) instead of replaying a CUDA graph")

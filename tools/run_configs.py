@@ -34,8 +34,31 @@ def timed_steps(fn, steps=5, warmup=2):
     return a.elapsed_time(b) / steps
 
 
-def config3():
+def _peaks():
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d["hbm_gbs"], d["bf16_tflops_sustained"], "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+def _instrumented(step, n=2):
+    """Per-call device times (CUDA events around every library call) over n steps: name -> (ms per call, calls per step)."""
+    N.enable_timing(True)
+    for _ in range(n):
+        step()
+    torch.cuda.synchronize()
+    per = {k: (v["ms"], v["calls"] / n) for k, v in N.timing_summary().items()}
+    N.enable_timing(False)
+    return per
+
+
+def config3(steps=5, warmup=2):
+    """configs[2] on one GPU: multi-hot user history (pooling factor 20, mean) + product / aisle / department features,
+    two 100M-row x 128 fp32 tables (51 GB each) + two tiny ones, B = 65536, towers 128 -> [128, 64], in-batch softmax."""
     B, D, L = 65536, 128, 20
+    hbm, tf, src = _peaks()
     rows = {"hist": 100_000_000, "product": 100_000_000, "aisle": 134, "department": 21}
     cfgs = [tt.EmbeddingBagConfig(name=f"t_{k}", embedding_dim=D, num_embeddings=r, feature_names=[k],
                                   pooling=tt.PoolingType.MEAN if k == "hist" else tt.PoolingType.SUM) for k, r in rows.items()]
@@ -47,12 +70,13 @@ def config3():
     opt = tt.KeyedOptimizerWrapper(dict(task.named_parameters()), lambda p: tt.FlatAdam(p, lr=1e-3))
     keys = list(rows)
     g = torch.Generator(device=dev).manual_seed(3)
-    batches = []
+    batches, uniq = [], 0
     for _ in range(3):
         lens = torch.cat([torch.full((B,), L, dtype=torch.int32, device=dev), torch.ones(3 * B, dtype=torch.int32, device=dev)])
-        vals = torch.cat([torch.randint(0, rows["hist"], (B * L,), device=dev, generator=g), torch.randint(0, rows["product"], (B,), device=dev, generator=g),
-                          torch.randint(0, 134, (B,), device=dev, generator=g), torch.randint(0, 21, (B,), device=dev, generator=g)])
-        batches.append(tt.Batch(torch.zeros(1, device=dev), tt.KeyedJaggedTensor.from_lengths_sync(keys, vals, lens),
+        cols = [torch.randint(0, rows["hist"], (B * L,), device=dev, generator=g), torch.randint(0, rows["product"], (B,), device=dev, generator=g),
+                torch.randint(0, 134, (B,), device=dev, generator=g), torch.randint(0, 21, (B,), device=dev, generator=g)]
+        uniq = sum(int(torch.unique(c).numel()) for c in cols)
+        batches.append(tt.Batch(torch.zeros(1, device=dev), tt.KeyedJaggedTensor.from_lengths_sync(keys, torch.cat(cols), lens),
                                 torch.zeros(B, dtype=torch.int32, device=dev)))
     i = [0]
 
@@ -61,20 +85,34 @@ def config3():
         loss, _ = task(batches[i[0] % 3]); i[0] += 1
         loss.backward()
         opt.step()
-    ms = timed_steps(step)
-    N.enable_timing(True)
-    step(); step()
-    torch.cuda.synchronize()
-    per = {k: round(v["ms"], 4) for k, v in N.timing_summary().items() if k.startswith("tt_ebc")}
-    N.enable_timing(False)
-    fwd_bytes = B * L * (8 + 4 * D) + 4 * B + 4 * B * D + 3 * (B * (8 + 4 * D) + 4 * B + 4 * B * D)
-    return {"config": 3, "what": "L=20 mean history + product/aisle/department, 2 x 100M x 128 fp32 tables (102 GB), B=65536, one GPU",
-            "ms_per_step": round(ms, 3), "samples_per_s": round(B / ms * 1e3), "ebc_ms": per,
-            "ebc_forward_gbs": round(fwd_bytes / (per["tt_ebc_forward"] * 1e-3) / 1e9, 1), "hbm_gb_allocated": round(torch.cuda.memory_allocated() / 1e9, 1)}
+    ms = timed_steps(step, steps=steps, warmup=warmup)
+    per = _instrumented(step)
+    nnz = B * L + 3 * B
+    fwd_bytes = nnz * (8 + 4 * D) + 4 * (4 * B) + 4 * B * D * 4           # ids + rows, offsets, pooled output
+    bwd_bytes = 4 * B * D * 4 + 8 * nnz + uniq * (8 * D + 8)               # 4BD + 8BL + U(8D + 8) per feature
+    fwd_ms, bwd_ms = per["tt_ebc_forward"][0], per["tt_ebc_backward_fused"][0]
+    sm_ms = sum(v[0] * v[1] for k, v in per.items() if "softmax" in k)
+    out = {"config": 3, "what": "configs[2] on 1 GPU: L=20 mean history + product/aisle/department, 2 x 100M x 128 fp32 tables (102 GB), "
+                                "B=65536, towers 128-[128,64], in-batch softmax, fused row-wise Adagrad, eager step",
+           "ms_per_step": round(ms, 3), "samples_per_s": round(B / ms * 1e3),
+           "calls_ms": {k: round(v[0] * v[1], 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1][0] * kv[1][1])},
+           "ebc_lookup": {"ms": round(fwd_ms, 4), "bytes": fwd_bytes, "gbs": round(fwd_bytes / fwd_ms / 1e6, 1), "peak_gbs": hbm,
+                          "frac": round(fwd_bytes / fwd_ms / 1e6 / hbm, 4)},
+           "ebc_update": {"ms": round(bwd_ms, 4), "bytes": bwd_bytes, "unique_rows": uniq, "gbs": round(bwd_bytes / bwd_ms / 1e6, 1),
+                          "peak_gbs": hbm, "frac": round(bwd_bytes / bwd_ms / 1e6 / hbm, 4)},
+           "softmax": {"ms": round(sm_ms, 4), "tflops_credited": round(6.0 * B * B * 64 / sm_ms / 1e9, 1), "peak": tf,
+                       "frac": round(6.0 * B * B * 64 / sm_ms / 1e9 / tf, 4)},
+           "peak_source": src, "hbm_gb_allocated": round(torch.cuda.memory_allocated() / 1e9, 1)}
+    del task, tower, ebc, opt, batches
+    torch.cuda.empty_cache()
+    return out
 
 
-def config4():
+def config4(steps=3, warmup=1):
+    """configs[3] on one GPU: batch 262144, bf16 towers 128 -> 1024 -> 512 -> 256 (both towers), in-batch softmax over
+    d = 256, fused row-wise Adam on two 10M x 128 tables."""
     B, D = 262144, 128
+    hbm, tf, src = _peaks()
     rows = [10_000_000, 10_000_000]
     cat = ["user_id", "product_id"]
     cfgs = [tt.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=D, num_embeddings=rows[i], feature_names=[c]) for i, c in enumerate(cat)]
@@ -96,10 +134,33 @@ def config4():
         loss, _ = task(batches[i[0] % 2]); i[0] += 1
         loss.backward()
         opt.step()
-    ms = timed_steps(step, steps=3, warmup=1)
-    flops = 6.0 * B * B * 256 + 3 * 2 * (128 * 1024 + 1024 * 512 + 512 * 256) * B * 2
-    return {"config": 4, "what": "B=262144, bf16 towers 128-1024-512-256, in-batch softmax d=256, fused row-wise Adam, one GPU",
-            "ms_per_step": round(ms, 2), "samples_per_s": round(B / ms * 1e3), "credited_tflops": round(flops / (ms * 1e-3) / 1e12, 1)}
+    ms = timed_steps(step, steps=steps, warmup=warmup)
+    per = _instrumented(step)
+    sm = {k: v for k, v in per.items() if "softmax" in k}
+    sm_ms = sum(v[0] * v[1] for v in sm.values())
+    fwd_ms = sum(v[0] * v[1] for k, v in sm.items() if "forward" in k)
+    bwd_ms = sum(v[0] * v[1] for k, v in sm.items() if "backward" in k)
+    gemm_ms = sum(v[0] * v[1] for k, v in per.items() if "gemm" in k or "towers" in k)
+    layer_flops = 2.0 * B * (128 * 1024 + 1024 * 512 + 512 * 256) * 2           # both towers, one GEMM per layer
+    tower_flops = 3 * layer_flops                                               # y, dX (the embeddings train), dW per layer
+    logit_flops = 6.0 * B * B * 256
+    out = {"config": 4, "what": "configs[3] on 1 GPU: B=262144, bf16 towers 128-1024-512-256, in-batch softmax d=256, 2 x 10M x 128 tables, "
+                                "fused row-wise Adam, eager step",
+           "ms_per_step": round(ms, 2), "samples_per_s": round(B / ms * 1e3),
+           "calls_ms": {k: round(v[0] * v[1], 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1][0] * kv[1][1])},
+           "roofline": {"kernel": "in-batch softmax d=256: tc_softmax_fwd_kernel<4> + 2 x tc_softmax_bwd_wide_kernel<4> (tcgen05)",
+                        "bound": "tensor", "ms": round(sm_ms, 3), "achieved": round(logit_flops / sm_ms / 1e9, 1), "unit": "TFLOP/s",
+                        "peak": tf, "frac": round(logit_flops / sm_ms / 1e9 / tf, 4),
+                        "executed_tflops": round(10.0 * B * B * 256 / sm_ms / 1e9, 1), "executed_frac": round(10.0 * B * B * 256 / sm_ms / 1e9 / tf, 4),
+                        "forward_tflops": round(2.0 * B * B * 256 / max(fwd_ms, 1e-9) / 1e9, 1), "backward_tflops_executed": round(8.0 * B * B * 256 / max(bwd_ms, 1e-9) / 1e9, 1),
+                        "flops_credited": "6*B*B*d; executed 10*B*B*d (S recomputed by both backward passes: accX + accY of a one-pass "
+                                          "scheme need 2 x 256 TMEM columns, which leaves none for S)"},
+           "tower_gemms": {"ms": round(gemm_ms, 3), "tflops": round(tower_flops / max(gemm_ms, 1e-9) / 1e9, 1), "peak": tf,
+                           "frac": round(tower_flops / max(gemm_ms, 1e-9) / 1e9 / tf, 4), "flops": "3 GEMMs (y, dX, dW) x 3 layers x 2 towers"},
+           "whole_step_tflops_credited": round((logit_flops + tower_flops) / (ms * 1e-3) / 1e12, 1), "peak_source": src}
+    del task, ebc, opt, batches
+    torch.cuda.empty_cache()
+    return out
 
 
 def config5():
