@@ -13,6 +13,10 @@
 namespace tt {
 
 constexpr int kBagsPerCta = 128;
+constexpr int kMaxBagsPerCta = 512;     // forward only: one-id bags take larger tiles (fewer, longer-lived CTAs: one wave)
+#ifndef TT_EBC_UB1
+#define TT_EBC_UB1 4
+#endif
 constexpr int kEbcThreads = 256;
 
 template <int VEC>
@@ -96,18 +100,19 @@ template <int VEC, int G, int NV>
 __global__ void __launch_bounds__(kEbcThreads)
 ebc_forward_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_constant__ SlotClasses cls,
                    const __grid_constant__ tt_peer_buffers peers, const int64_t* __restrict__ values,
-                   const int32_t* __restrict__ offsets, float* __restrict__ pooled, int tiles_per_slot) {
+                   const int32_t* __restrict__ offsets, float* __restrict__ pooled, int tiles_per_slot,
+                   int bags_per_cta) {
   constexpr int NG = kEbcThreads / G;                   // bag groups per CTA
-  constexpr int UB = NV >= 4 ? 1 : (NV == 2 ? 2 : 4);   // bags in flight per group
+  constexpr int UB = NV >= 4 ? 1 : (NV == 2 ? 2 : TT_EBC_UB1);   // bags in flight per group
   const int slot = blockIdx.x / tiles_per_slot;
   if (cls.id[slot] != class_id(VEC, G, NV)) return;
   const int tile = blockIdx.x - slot * tiles_per_slot;
   const int B = plan.batch_size;
-  const int bag0 = tile * kBagsPerCta;
-  const int nb = min(kBagsPerCta, B - bag0);
+  const int bag0 = tile * bags_per_cta;
+  const int nb = min(bags_per_cta, B - bag0);
   if (nb <= 0) return;
 
-  __shared__ int s_off[kBagsPerCta + 1];
+  __shared__ int s_off[kMaxBagsPerCta + 1];
   const int32_t* off = offsets + (int64_t)plan.kjt_index[slot] * B + bag0;
   for (int i = threadIdx.x; i <= nb; i += kEbcThreads) s_off[i] = off[i];
   __syncthreads();
@@ -135,18 +140,18 @@ ebc_forward_kernel(const __grid_constant__ tt_ebc_plan plan, const __grid_consta
       for (int v = 0; v < NV; ++v) acc[u][v].zero();
     }
     if (maxlen <= 1) {
-      // one id per bag (the reference's shape): UB independent rows in flight per group
+      // one id per bag (the reference's shape): the UB ids first (independent loads), then UB rows in flight per group
+      int64_t id[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) id[u] = len[u] > 0 ? values[s[u]] : (int64_t)-1;
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
-        if (len[u] > 0) {
-          const int64_t id = values[s[u]];
-          if ((uint64_t)id < R) {
-            const float* row = W + id * D;
+        if ((uint64_t)id[u] < R) {
+          const float* row = W + id[u] * D;
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              const int c = l + v * G;
-              if (c < units) acc[u][v].load_stream(row + c * VEC);
-            }
+          for (int v = 0; v < NV; ++v) {
+            const int c = l + v * G;
+            if (c < units) acc[u][v].load_stream(row + c * VEC);
           }
         }
       }
@@ -789,12 +794,15 @@ static int ebc_forward_impl(const tt_ebc_plan* h_plan, const int64_t* values, co
   if (h_plan->num_slots == 0 || h_plan->batch_size == 0) return TT_OK;
   if (!h_peers && (reinterpret_cast<uintptr_t>(pooled) & 15) != 0) all_vec4 = false;
   cudaStream_t s = as_stream(stream);
-  const int tiles = (h_plan->batch_size + kBagsPerCta - 1) / kBagsPerCta;
+  static const int env_bags = [] { const char* v = getenv("TT_EBC_FWD_BAGS"); return v ? atoi(v) : 0; }();
+  int bags = kBagsPerCta;
+  if (env_bags >= 16 && env_bags <= kMaxBagsPerCta) bags = env_bags;
+  const int tiles = (h_plan->batch_size + bags - 1) / bags;
   const unsigned grid = (unsigned)(tiles * h_plan->num_slots);
   SlotClasses cls;
   return for_each_class(h_plan, all_vec4, &cls, [&](int id) -> int {
 #define TT_LAUNCH_FWD(V, G, N)                                                                       \
-  ebc_forward_kernel<V, G, N><<<grid, kEbcThreads, 0, s>>>(*h_plan, cls, peers, values, offsets, pooled, tiles)
+  ebc_forward_kernel<V, G, N><<<grid, kEbcThreads, 0, s>>>(*h_plan, cls, peers, values, offsets, pooled, tiles, bags)
     TT_DISPATCH_CLASS(id, TT_LAUNCH_FWD);
 #undef TT_LAUNCH_FWD
     TT_CHECK_LAUNCH("ebc_forward");

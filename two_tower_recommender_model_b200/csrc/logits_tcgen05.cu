@@ -674,6 +674,13 @@ tc_softmax_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 //   the TMEM stage for the next S a whole tile early; setmaxnreg moves registers from warpgroup 0 to the others.
 //   TMEM: S stage of row tile i [128i, 128i+128) | accX_i [256+64i, +64) | accY double buffer [384+64b, +64)
 // The sums are finished by softmax_bwd_finalize_kernel: out = gate * out_scale * (acc - other side's row).
+// Measured dead ends of round 2 (tools/mma_rate.cu, profiles/r02_mma_rate.txt, profiles/r02_softmax_bwd_ts_form_attempts.txt):
+// a tcgen05.mma with M = 128, K = 16 never takes less than ~48 (TS) / ~53 (SS) clocks whatever N is, so the N = 64
+// gradient products run at 60-66 % of the tensor rate in either form and smaller S tiles only add instructions.  A TS-form
+// variant (X resident in TMEM, P written back in place as the A operand of P.Y: 152 KB instead of 200 KB of shared-memory
+// traffic per tile) was built, passed every parity test and was SLOWER (1.90 ms with one 64-column stage per softmax group,
+// 2.39 / 2.01 ms with two 32-column stages; this kernel: 1.58 ms): in-place P keeps the S stage busy until P.Y has run, the
+// look-ahead below is lost, and more, narrower MMAs cost 48 clocks each.
 struct FusedCfg {
   static constexpr int RT = 2, NT = 128, YS = 3, PB = 4;     // PB: P buffers, two private to each softmax group
   static constexpr int CH = 2;                           // softmax groups per row tile (each takes NT/CH columns of the row)
