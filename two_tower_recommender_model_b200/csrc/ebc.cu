@@ -64,15 +64,23 @@ struct Vec<1> {
 struct ShapeClass {
   int vec, g, nv;
 };
-static bool classify(int dim, bool all_vec4, ShapeClass* out) {
+// `lookup`: the forward takes half as many lanes per row and two vectors per lane for 9..32 vector units (D = 64 / 128 with
+// float4): twice as many bags per warp, i.e. twice the row reads in flight per SM at the same occupancy -- measured
+// L=20/D=128 5.1 -> 6.1 TB/s, L=20/D=64 5.2 -> 6.2, L=5/D=128 4.1 -> 5.4 (profiles/r02_ebc_lookup_variants.txt).  The
+// fused update keeps one vector per lane: its occupancy is register-bound (32 registers), and the same change cost it 50 %.
+static bool classify(int dim, bool all_vec4, ShapeClass* out, bool lookup = false) {
   int vec = all_vec4 ? 4 : 1;
   int units = dim / vec;
   if (units * vec != dim || units <= 0) return false;
   static const int gs[9] = {1, 2, 4, 8, 16, 32, 32, 32, 32};
   static const int nvs[9] = {1, 1, 1, 1, 1, 1, 2, 4, 8};
+  static const int gs_l[9] = {1, 2, 4, 8, 8, 16, 32, 32, 32};
+  static const int nvs_l[9] = {1, 1, 1, 1, 2, 2, 2, 4, 8};
+  const int* G = (lookup && vec == 4) ? gs_l : gs;
+  const int* NV = (lookup && vec == 4) ? nvs_l : nvs;
   for (int i = 0; i < 9; ++i)
-    if (units <= gs[i] * nvs[i]) {
-      *out = {vec, gs[i], nvs[i]};
+    if (units <= G[i] * NV[i]) {
+      *out = {vec, G[i], NV[i]};
       return true;
     }
   return false;
@@ -651,12 +659,12 @@ static int validate_plan(const tt_ebc_plan* p, bool* all_vec4) {
 }
 
 template <typename Launch>
-static int for_each_class(const tt_ebc_plan* p, bool all_vec4, SlotClasses* cls, Launch launch) {
+static int for_each_class(const tt_ebc_plan* p, bool all_vec4, SlotClasses* cls, bool lookup, Launch launch) {
   int seen[TT_MAX_FEATURES];
   int nseen = 0;
   for (int s = 0; s < p->num_slots; ++s) {
     ShapeClass c;
-    if (!classify(p->dim[s], all_vec4, &c))
+    if (!classify(p->dim[s], all_vec4, &c, lookup))
       return fail(TT_ERR_UNSUPPORTED, "ebc: embedding_dim %d not supported (max %d)", p->dim[s],
                   all_vec4 ? 1024 : 256);
     cls->id[s] = class_id(c.vec, c.g, c.nv);
@@ -672,8 +680,12 @@ static int for_each_class(const tt_ebc_plan* p, bool all_vec4, SlotClasses* cls,
   return TT_OK;
 }
 
-#define TT_DISPATCH_CLASS(ID, MACRO)                 \
+#define TT_DISPATCH_CLASS(ID, MACRO) TT_DISPATCH_CLASS_(ID, MACRO, )
+#define TT_DISPATCH_CLASS_LOOKUP(ID, MACRO) \
+  TT_DISPATCH_CLASS_(ID, MACRO, case class_id(4, 8, 2): MACRO(4, 8, 2); break; case class_id(4, 16, 2): MACRO(4, 16, 2); break;)
+#define TT_DISPATCH_CLASS_(ID, MACRO, EXTRA)         \
   switch (ID) {                                      \
+    EXTRA                                            \
     case class_id(4, 1, 1): MACRO(4, 1, 1); break;   \
     case class_id(4, 2, 1): MACRO(4, 2, 1); break;   \
     case class_id(4, 4, 1): MACRO(4, 4, 1); break;   \
@@ -800,10 +812,10 @@ static int ebc_forward_impl(const tt_ebc_plan* h_plan, const int64_t* values, co
   const int tiles = (h_plan->batch_size + bags - 1) / bags;
   const unsigned grid = (unsigned)(tiles * h_plan->num_slots);
   SlotClasses cls;
-  return for_each_class(h_plan, all_vec4, &cls, [&](int id) -> int {
+  return for_each_class(h_plan, all_vec4, &cls, true, [&](int id) -> int {
 #define TT_LAUNCH_FWD(V, G, N)                                                                       \
   ebc_forward_kernel<V, G, N><<<grid, kEbcThreads, 0, s>>>(*h_plan, cls, peers, values, offsets, pooled, tiles, bags)
-    TT_DISPATCH_CLASS(id, TT_LAUNCH_FWD);
+    TT_DISPATCH_CLASS_LOOKUP(id, TT_LAUNCH_FWD);
 #undef TT_LAUNCH_FWD
     TT_CHECK_LAUNCH("ebc_forward");
     return TT_OK;
