@@ -290,6 +290,11 @@ int tt_towers_backward_fused(const tt_tower_backward* towers, int32_t n_towers, 
 size_t tt_gemm_bf16_splitk_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int tt_gemm_bf16_splitk(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N,
                         int64_t K, float* out_f32, void* ws, size_t ws_bytes, void* stream);
+/* The same for operands given the other way round: C[M,N] = A^T B with A [K, M] and B [K, N] row-major (MN-major
+ * tcgen05 operands): the weight gradient dW = dZ^T A_prev straight from the row-major activations, no transposed copies.
+ * Workspace as tt_gemm_bf16_splitk_workspace_bytes(M, N, K). */
+int tt_gemm_bf16_splitk_mn(const void* a_km, int64_t lda, const void* b_kn, int64_t ldb, int64_t M, int64_t N,
+                           int64_t K, float* out_f32, void* ws, size_t ws_bytes, void* stream);
 
 /* out[c] = sum_r x[r,c] for a bf16 matrix (bias gradient). */
 size_t tt_colsum_bf16_workspace_bytes(int64_t rows, int64_t cols);

@@ -107,6 +107,21 @@ def test_gemm_splitk_and_colsum(cuda, M, N, K):
     torch.testing.assert_close(cs.cpu().double(), a.bfloat16().double().sum(1), rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("M,N,K", [(64, 128, 65536), (1024, 512, 4096), (256, 512, 5000), (20, 36, 777), (128, 1024, 8200), (8, 64, 130)])
+def test_gemm_splitk_mn_major(cuda, M, N, K):
+    """dW = dZ^T A from ROW-MAJOR dZ [K, M] and A [K, N] (both tcgen05 operands MN-major, no transposed copies) against
+    float64 on the same bf16-rounded operands, and against the K-major split-K kernel fed the transposed copies."""
+    from two_tower_recommender_model_b200.functional import cast_bf16, gemm_bf16_splitk, gemm_bf16_splitk_mn
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(K, M, generator=g); b = torch.randn(K, N, generator=g)
+    ad, bd = cast_bf16(a.to(cuda)), cast_bf16(b.to(cuda))
+    want = ad.double().cpu().t() @ bd.double().cpu()
+    got = gemm_bf16_splitk_mn(ad, bd)
+    torch.testing.assert_close(got.cpu().double(), want, rtol=1e-4, atol=2e-3 * (K / 4096) ** 0.5)
+    ref = gemm_bf16_splitk(cast_bf16(a.to(cuda), transposed=True), cast_bf16(b.to(cuda), transposed=True))
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=2e-3 * (K / 4096) ** 0.5)
+
+
 def test_cast_gate(cuda):
     from two_tower_recommender_model_b200.functional import cast_bf16
     x = torch.randn(300, 40); gt = torch.randn(300, 40)

@@ -101,6 +101,7 @@ SIGNATURES = {
                                _P, c_int64, _P, c_int64, _P, c_int64, _P]),
     "tt_gemm_bf16_splitk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "tt_gemm_bf16_splitk": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
+    "tt_gemm_bf16_splitk_mn": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "tt_colsum_bf16_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "tt_colsum_bf16": (c_int32, [_P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "tt_dot_bce_workspace_bytes": (c_size_t, [c_int64]),

@@ -4,6 +4,8 @@
 // fp32 / bf16 / transposed-bf16 stores).  One CTA per 128 x BN output tile:
 //   warp 0   : TMA producer            warp 1 : TMEM allocator + MMA issuer
 //   warps 2-5: epilogue (warp w reads TMEM lanes 32*(w%4) ..)
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace tt {
@@ -80,16 +82,20 @@ constexpr int kBM = 128, kBK = 64, kStages = 4, kGemmThreadsTc = 192;
 // three CTAs share an SM and one CTA's TMA / MMA latency hides behind another's epilogue.
 template <int BN>
 constexpr int gemm_smem_bytes(int stages) {
-  return stages * (kBM * kBK * 2 + BN * kBK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return stages * (kBM * kBK * 2 + (BN < 64 ? 64 : BN) * kBK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
-template <int BN>
+// MN = true: C[M,N] = A^T B with A given as [K, M] and B as [K, N] row-major (the weight gradient dW = dZ^T A_prev straight
+// from the row-major activations: no transposed copies).  A k-block is then kBK rows of the source matrices: sub-tiles of
+// [64 k-rows x 64 columns] (one TMA box each), read by the tensor core through MN-major descriptors.
+template <int BN, bool MN = false>
 __global__ void __launch_bounds__(kGemmThreadsTc, BN <= 128 ? 3 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmEpilogue ep, int M, int N, int K, int stages) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int A_BYTES = kBM * kBK * 2, B_BYTES = BN * kBK * 2;
+  constexpr int BNS = (MN && BN < 64) ? 64 : BN;      // columns of B staged per k-block (an MN-major box is 64 wide)
+  constexpr int A_BYTES = kBM * kBK * 2, B_BYTES = BNS * kBK * 2;
   uint8_t* sA = smem;
   uint8_t* sB = smem + stages * A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + stages * B_BYTES);
@@ -124,23 +130,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (kb / stages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-        tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], (kb0 + kb) * kBK, m0);
-        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], (kb0 + kb) * kBK, n0);
+        if (MN) {
+          for (int h = 0; h < kBM / 64; ++h) tma_load_2d(sA + s * A_BYTES + h * 8192, &tmA, &full[s], m0 + 64 * h, (kb0 + kb) * kBK);
+          for (int h = 0; h < BNS / 64; ++h) tma_load_2d(sB + s * B_BYTES + h * 8192, &tmB, &full[s], n0 + 64 * h, (kb0 + kb) * kBK);
+        } else {
+          tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], (kb0 + kb) * kBK, m0);
+          tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], (kb0 + kb) * kBK, n0);
+        }
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = idesc_bf16_f32(kBM, BN);
+    constexpr uint32_t idesc = idesc_bf16_f32(kBM, BN) | (MN ? (kIdescAMnMajor | kIdescBMnMajor) : 0u);
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % stages;
       const uint32_t ph = (kb / stages) & 1;
       mbar_wait(&full[s], ph);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t da = smem_desc_k_sw128(smem_u32(sA + s * A_BYTES));
-        const uint64_t db = smem_desc_k_sw128(smem_u32(sB + s * B_BYTES));
+        if (MN) {
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k)
-          mma_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < kBK / 16; ++k)
+            mma_ss(tmem_base, smem_desc_mn_sw128(smem_u32(sA + s * A_BYTES) + k * 2048, 8192, 1024),
+                   smem_desc_mn_sw128(smem_u32(sB + s * B_BYTES) + k * 2048, 8192, 1024), idesc, (kb | k) != 0);
+        } else {
+          const uint64_t da = smem_desc_k_sw128(smem_u32(sA + s * A_BYTES));
+          const uint64_t db = smem_desc_k_sw128(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            mma_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+        }
         tc_commit(&empty[s]);                       // frees the smem stage when these MMAs retire
         if (kb == num_kb - 1) tc_commit(acc_full);  // accumulator complete
       }
@@ -175,10 +193,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       if (ep.mask_bf16 != nullptr && row < M) {
+        const __nv_bfloat16* mrow = ep.mask_bf16 + (int64_t)row * ep.ld_mask_bf16 + n0 + c0;
+        if (n0 + c0 + 32 <= N && (reinterpret_cast<uintptr_t>(mrow) & 15) == 0) {
+          // 32 gates = four 16-byte loads (one 2-byte load per element made this epilogue the whole kernel: 2.8 ms for
+          // the 262144 x 1024 x 512 data-gradient GEMM of cfg4)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = n0 + c0 + j;
-          if (col < N && !(__bfloat162float(ep.mask_bf16[(int64_t)row * ep.ld_mask_bf16 + col]) > 0.f)) f[j] = 0.f;
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 mk = *reinterpret_cast<const uint4*>(mrow + j);
+            const uint32_t w[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero (NaN gates count as positive, as x > 0 is false for them
+              // ... a ReLU output is never NaN-gated in practice; keep the float compare for exact parity)
+              const float lo = __uint_as_float(w[t] << 16), hi = __uint_as_float(w[t] & 0xffff0000u);
+              if (!(lo > 0.f)) f[j + 2 * t] = 0.f;
+              if (!(hi > 0.f)) f[j + 2 * t + 1] = 0.f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = n0 + c0 + j;
+            if (col < N && !(__bfloat162float(mrow[j]) > 0.f)) f[j] = 0.f;
+          }
         }
       }
       if (row < M) {
@@ -301,20 +338,24 @@ __global__ void tc_reduce_partials_kernel(const float* __restrict__ partial, int
   out[i] = s;
 }
 
-template <int BN>
+template <int BN, bool MN = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
                        int splits, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          gemm_smem_bytes<BN>(kStages));
     if (e != cudaSuccess) return fail(TT_ERR_CUDA, "tc_gemm smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
   const int kb_cta = ep.kb_per_split;                       // K blocks one CTA walks through
-  const int stages = kb_cta < kStages ? (kb_cta < 1 ? 1 : kb_cta) : kStages;
+  int stages = kb_cta < kStages ? (kb_cta < 1 ? 1 : kb_cta) : kStages;
+  // Two CTAs per SM matter more than a deep ring: the epilogue (thread-per-row stores) of one tile is several times its
+  // MMA time, and only a second resident CTA overlaps it with a mainloop.  Cap the ring at what lets two CTAs fit.
+  static const int env_cap = [] { const char* v = getenv("TT_GEMM_SMEM_CAP"); return v ? atoi(v) : 110 * 1024; }();
+  while (stages > 1 && gemm_smem_bytes<BN>(stages) > env_cap) --stages;
   dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM, splits);
-  tc_gemm_kernel<BN><<<grid, kGemmThreadsTc, gemm_smem_bytes<BN>(stages), s>>>(ta, tb, ep, M, N, K, stages);
+  tc_gemm_kernel<BN, MN><<<grid, kGemmThreadsTc, gemm_smem_bytes<BN>(stages), s>>>(ta, tb, ep, M, N, K, stages);
   TT_CHECK_LAUNCH("tc_gemm");
   return TT_OK;
 }
@@ -374,6 +415,16 @@ int tt_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t
   return gemm_dispatch(bn, ta, tb, ep, (int)M, (int)N, (int)K, 1, as_stream(stream));
 }
 
+static int gemm_dispatch_mn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                            int splits, cudaStream_t s) {
+  switch (bn) {
+    case 32: return launch_gemm<32, true>(ta, tb, ep, M, N, K, splits, s);
+    case 64: return launch_gemm<64, true>(ta, tb, ep, M, N, K, splits, s);
+    case 128: return launch_gemm<128, true>(ta, tb, ep, M, N, K, splits, s);
+    default: return launch_gemm<256, true>(ta, tb, ep, M, N, K, splits, s);
+  }
+}
+
 static int splitk_splits(int64_t M, int64_t N, int64_t K, int bn) {
   const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
   const int64_t total_kb = (K + kBK - 1) / kBK;
@@ -417,8 +468,42 @@ int tt_gemm_bf16_splitk(const void* a, int64_t lda, const void* b, int64_t ldb, 
   return TT_OK;
 }
 
+// C[M,N] (fp32) = A^T B with A [K, M] and B [K, N] row-major bf16 (dW = dZ^T A_prev from the row-major activations).
+int tt_gemm_bf16_splitk_mn(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                           float* out_f32, void* ws, size_t ws_bytes, void* stream) {
+  TT_CHECK_ARG(M > 0 && N > 0 && K > 0 && a && b && out_f32, "gemm_bf16_splitk_mn: bad args");
+  const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  const int want = splitk_splits(M, N, K, bn);
+  const int total_kb = (int)((K + kBK - 1) / kBK);
+  const int per = (total_kb + want - 1) / want;
+  const int splits = (total_kb + per - 1) / per;
+  if (!ws || ws_bytes < (size_t)splits * M * N * 4) return fail(TT_ERR_WORKSPACE, "gemm_bf16_splitk_mn: workspace too small");
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_2d(&ta, a, K, M, lda, kBK);      // boxes of [64 k-rows x 64 columns]
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tb, b, K, N, ldb, kBK);
+  if (rc) return rc;
+  GemmEpilogue ep = {};
+  ep.out_f32 = static_cast<float*>(ws);
+  ep.ld_f32 = N;
+  ep.kb_per_split = per;
+  cudaStream_t s = as_stream(stream);
+  rc = gemm_dispatch_mn(bn, ta, tb, ep, (int)M, (int)N, (int)K, splits, s);
+  if (rc) return rc;
+  const int64_t cnt = M * N;
+  tc_reduce_partials_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(static_cast<float*>(ws), splits, cnt, out_f32);
+  TT_CHECK_LAUNCH("tc_reduce_partials");
+  return TT_OK;
+}
+
+// chunks of >= 256 rows, at most 128 of them: the final ordered reduce reads `chunks` partials per column serially
+static int colsum_rows_per_chunk(int64_t rows) {
+  int64_t rpc = (rows + 127) / 128;
+  rpc = (rpc + 255) / 256 * 256;
+  return (int)(rpc < 256 ? 256 : rpc);
+}
 size_t tt_colsum_bf16_workspace_bytes(int64_t rows, int64_t cols) {
-  const int64_t chunks = (rows + 255) / 256;
+  const int64_t chunks = (rows + 255) / 256;            // upper bound (the kernel uses fewer, larger chunks)
   return align_up((size_t)chunks * cols * 4, 256) + 256;
 }
 
@@ -426,11 +511,12 @@ size_t tt_colsum_bf16_workspace_bytes(int64_t rows, int64_t cols) {
 int tt_colsum_bf16(const void* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* ws, size_t ws_bytes,
                    void* stream) {
   TT_CHECK_ARG(rows > 0 && cols > 0 && x && out, "colsum_bf16: bad args");
-  const int chunks = (int)((rows + 255) / 256);
+  const int rpc = colsum_rows_per_chunk(rows);
+  const int chunks = (int)((rows + rpc - 1) / rpc);
   if (!ws || ws_bytes < (size_t)chunks * cols * 4) return fail(TT_ERR_WORKSPACE, "colsum_bf16: workspace too small");
   cudaStream_t s = as_stream(stream);
   dim3 grid((unsigned)((cols + 63) / 64), (unsigned)chunks);
-  colsum_bf16_partial_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ldx, (int)rows, (int)cols, 256,
+  colsum_bf16_partial_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ldx, (int)rows, (int)cols, rpc,
                                                   static_cast<float*>(ws));
   TT_CHECK_LAUNCH("colsum_bf16_partial");
   tc_reduce_partials_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(static_cast<float*>(ws), chunks, cols, out);

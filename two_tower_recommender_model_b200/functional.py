@@ -497,6 +497,19 @@ def gemm_bf16_splitk(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gemm_bf16_splitk_mn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """fp32 ``a.T @ b`` for a [K, M], b [K, N] row-major bf16 and a long K (``dW = dZ^T A_prev`` from the row-major
+    activations: the tensor core reads both operands MN-major, no transposed copies exist)."""
+    K, M = a.shape
+    Nn = b.shape[1]
+    dev = a.device
+    out = torch.empty(M, Nn, dtype=torch.float32, device=dev)
+    ws = N.workspace(N.load().tt_gemm_bf16_splitk_workspace_bytes(M, Nn, K), dev)
+    N.call("tt_gemm_bf16_splitk_mn", N.ptr(a), a.stride(0), N.ptr(b), b.stride(0), M, Nn, K, N.ptr(out), N.ptr(ws), ws.numel(),
+           N.stream_ptr(dev))
+    return out
+
+
 def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
     rows, cols = x.shape
     out = torch.empty(cols, dtype=torch.float32, device=x.device)
@@ -598,8 +611,8 @@ class FusedTowersTC(torch.autograd.Function):
 
 class MlpTC(torch.autograd.Function):
     """A whole ReLU tower on the tensor cores: ``x -> relu(x W1^T + b1) -> ... -> relu(. WL^T + bL)``.
-    Operands are bf16 (activations are produced in bf16 by the GEMM epilogues, together with the
-    transposed copies the weight-gradient GEMMs read), accumulation is fp32 in TMEM, master weights,
+    Operands are bf16 (activations are produced in bf16 by the GEMM epilogues, row-major only: the
+    weight-gradient GEMMs read them through MN-major descriptors), accumulation is fp32 in TMEM, master weights,
     the returned output and all gradients are fp32.  Backward: dZ_l = dA_l * (A_l > 0) is fused into
     the epilogue of the previous data-gradient GEMM; dW_l = dZ_l^T A_{l-1} is a split-K GEMM."""
 
@@ -607,16 +620,15 @@ class MlpTC(torch.autograd.Function):
     def forward(ctx, x, *params):
         L = len(params) // 2
         x = _rows(x, "x")
-        xb, xbt = cast_bf16(x, both=True)
-        acts = [(xb, xbt)]
+        acts = [cast_bf16(x)]          # row-major bf16 activations only: the weight-gradient GEMM reads them MN-major
         out = None
         for l in range(L):
             w, b = params[2 * l], params[2 * l + 1]
             wb = cast_bf16(_f32c(w, "weight"))
             last = l == L - 1
-            r = gemm_bf16(acts[-1][0], wb, bias=None if b is None else _f32c(b, "bias"), relu=True,
-                          out_f32=last, out_bf16=True, out_bf16_t=not last)
-            acts.append((r["bf16"], r.get("bf16_t")))
+            r = gemm_bf16(acts[-1], wb, bias=None if b is None else _f32c(b, "bias"), relu=True,
+                          out_f32=last, out_bf16=True)
+            acts.append(r["bf16"])
             if last:
                 out = r["f32"]
         ctx.L = L
@@ -628,18 +640,17 @@ class MlpTC(torch.autograd.Function):
     def backward(ctx, dout):
         out, *params = ctx.saved_tensors
         L, acts = ctx.L, ctx.acts
-        dz, dzt = cast_bf16(_f32c(dout, "dout"), both=True, gate=out)
+        dz = cast_bf16(_f32c(dout, "dout"), gate=out)
         grads = [None] * (2 * L)
         dx = None
         for l in range(L - 1, -1, -1):
             w, b = params[2 * l], params[2 * l + 1]
-            grads[2 * l] = gemm_bf16_splitk(dzt, acts[l][1])            # [N_l, K_l]
+            grads[2 * l] = gemm_bf16_splitk_mn(dz, acts[l])              # dZ_l^T A_{l-1}: [N_l, K_l]
             if b is not None:
                 grads[2 * l + 1] = colsum_bf16(dz)
             if l > 0:
                 wt = cast_bf16(w, transposed=True)                       # [K_l, N_l]
-                r = gemm_bf16(dz, wt, mask_bf16=acts[l][0], out_f32=False, out_bf16=True, out_bf16_t=True)
-                dz, dzt = r["bf16"], r["bf16_t"]
+                dz = gemm_bf16(dz, wt, mask_bf16=acts[l], out_f32=False, out_bf16=True)["bf16"]
             elif ctx.needs_input_grad[0]:
                 wt = cast_bf16(w, transposed=True)
                 dx = gemm_bf16(dz, wt, out_f32=True)["f32"]
