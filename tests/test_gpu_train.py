@@ -311,3 +311,52 @@ def test_ray_tune_variant_towers(cuda):
     torch.testing.assert_close(loss.detach().cpu(), want, rtol=1e-5, atol=1e-6)
     loss.backward()
     assert model.query_proj._mlp[0]._linear.weight.grad is not None
+
+
+def test_cuda_graph_multi_hot_kjt_step_equals_eager(cuda):
+    """CudaGraphTrainStep in kjt_capacity mode: multi-hot batches (mean-pooled history + single-id features, the shape of
+    BASELINE configs[2]) whose number of ids CHANGES from step to step replay through one captured graph and train
+    exactly like the eager loop (deterministic softmax backward, see above)."""
+    import two_tower_recommender_model_b200 as tt
+    from two_tower_recommender_model_b200 import functional as F
+    F.set_deterministic_softmax_backward(True)
+    try:
+        keys, rows, D, B, Lmax = ["hist", "item"], [4000, 900], 128, 512, 7
+
+        def build():
+            torch.manual_seed(1)
+            cfgs = [tt.EmbeddingBagConfig(name="t_hist", embedding_dim=D, num_embeddings=rows[0], feature_names=["hist"], pooling=tt.PoolingType.MEAN),
+                    tt.EmbeddingBagConfig(name="t_item", embedding_dim=D, num_embeddings=rows[1], feature_names=["item"])]
+            ebc = tt.EmbeddingBagCollection(tables=cfgs, device=cuda)
+            tower = tt.TwoTower(ebc, [128, 64], device=cuda, query_features=["hist"], candidate_features=["item"], precision="bf16")
+            task = tt.TwoTowerTrainTask(tower, loss="in_batch_softmax", precision="bf16")
+            apply_optimizer_in_backward(tt.RowWiseAdagrad, ebc.parameters(), {"lr": 0.01})
+            return task, tt.KeyedOptimizerWrapper(dict(task.named_parameters()), lambda p: tt.FlatAdam(p, lr=1e-3))
+
+        g = torch.Generator().manual_seed(9)
+        data = []
+        for _ in range(8):
+            lens = torch.cat([torch.randint(0, Lmax + 1, (B,), generator=g), torch.ones(B, dtype=torch.int64)]).to(torch.int32)
+            n_h = int(lens[:B].sum())
+            vals = torch.cat([torch.randint(0, rows[0], (n_h,), generator=g), torch.randint(0, rows[1], (B,), generator=g)])
+            data.append((vals, lens, torch.zeros(B, dtype=torch.int32)))
+        assert len({v.numel() for v, _, _ in data}) > 1          # the id count really varies
+        m1, o1 = build()
+        m2, o2 = build()
+        m2.load_state_dict(m1.state_dict())
+        losses1 = []
+        for vals, lens, y in data:
+            batch = tt.Batch(torch.zeros(1, device=cuda), tt.KeyedJaggedTensor.from_lengths_sync(keys, vals.to(cuda), lens.to(cuda)), y.to(cuda))
+            o1.zero_grad()
+            loss, _ = m1(batch)
+            loss.backward()
+            o1.step()
+            losses1.append(float(loss.detach()))
+        step = tt.CudaGraphTrainStep(m2, o2, keys, rows, B, cuda, warmup_steps=3, kjt_capacity=B * (Lmax + 1))
+        losses2 = [float(step.step_kjt(v.pin_memory(), l.pin_memory(), y.pin_memory())[0]) for v, l, y in data]
+        assert step.captured
+        assert losses1 == pytest.approx(losses2, rel=1e-6)
+        for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+            torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7, msg=lambda m: f"{k}: {m}")
+    finally:
+        F.set_deterministic_softmax_backward(False)

@@ -8,7 +8,11 @@ not change from step to step once the inputs live in static buffers.  ``CudaGrap
 first calls eagerly (warm-up with REAL batches, so nothing is trained on dummy data), then captures
 one step and replays it: per step the host issues two async copies and one graph launch.
 
-Requirements: static shapes (batches given as raw id columns ``[F, B]`` + labels ``[B]``); sparse optimizer
+Requirements: static shapes -- batches given as raw id columns ``[F, B]`` + labels ``[B]``, or (``kjt_capacity=``,
+one GPU) as multi-hot KJT pieces: ``values`` of any length up to the capacity and ``lengths [F*B]``; the values live in a
+fixed-capacity buffer, the offsets are scanned on the device inside the graph, and the kernels take the live count from
+``offsets[-1]`` (the lookup never looks past it, the fused backward parks the unused tail on its sentinel key), so a
+batch's number of ids may change from step to step without a re-capture; sparse optimizer
 RowWiseAdagrad, RowWiseAdam or SGD (row-wise Adam keeps its step counter on the device: ``tt_sparse_optimizer.step_dev``
 is incremented by the fused backward itself, so the replayed launch arguments never go stale); dense optimizer
 ``FlatAdam`` (device-side step counter) or SGD -- ``torch.optim.Adam`` computes its bias correction on the host
@@ -24,7 +28,8 @@ from .sparse.jagged_tensor import KeyedJaggedTensor
 
 class CudaGraphTrainStep:
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, keys: Sequence[str],
-                 num_embeddings: Sequence[int], batch_size: int, device: torch.device, warmup_steps: int = 3) -> None:
+                 num_embeddings: Sequence[int], batch_size: int, device: torch.device, warmup_steps: int = 3,
+                 kjt_capacity: Optional[int] = None) -> None:
         self._model, self._opt = model, optimizer
         self._check_capturable(optimizer)
         self._keys = list(keys)
@@ -34,6 +39,11 @@ class CudaGraphTrainStep:
         self._labels = torch.zeros(batch_size, dtype=torch.int32, device=self._dev)
         self._rows = torch.tensor(list(num_embeddings), dtype=torch.int64, device=self._dev)
         self._dense = torch.zeros(1, device=self._dev)
+        # multi-hot mode: the KJT's values (fixed capacity) and lengths are the static inputs instead of id columns
+        self._values = self._lengths = None
+        if kjt_capacity is not None:
+            self._values = torch.zeros(int(kjt_capacity), dtype=torch.int64, device=self._dev)
+            self._lengths = torch.zeros(F * batch_size, dtype=torch.int32, device=self._dev)
         self._warmup = warmup_steps
         self._calls = 0
         self._graph: Optional[torch.cuda.CUDAGraph] = None
@@ -50,7 +60,11 @@ class CudaGraphTrainStep:
                              "(device-side step counter), torch.optim.SGD, or Adam(capturable=True)")
 
     def _step(self):
-        kjt = KeyedJaggedTensor.from_id_columns(self._keys, self._ids, self._rows)
+        if self._values is not None:
+            kjt = KeyedJaggedTensor(keys=self._keys, values=self._values, lengths=self._lengths)
+            kjt._values_padded = True
+        else:
+            kjt = KeyedJaggedTensor.from_id_columns(self._keys, self._ids, self._rows)
         batch = Batch(dense_features=self._dense, sparse_features=kjt, labels=self._labels)
         self._opt.zero_grad()
         loss, out = self._model(batch)
@@ -66,6 +80,23 @@ class CudaGraphTrainStep:
         second output ``(loss, logits, labels)``; the tensors are static buffers, overwritten by the next call."""
         self._ids.copy_(ids, non_blocking=True)
         self._labels.copy_(labels, non_blocking=True)
+        return self._run()
+
+    def step_kjt(self, values: torch.Tensor, lengths: torch.Tensor, labels: torch.Tensor):
+        """Multi-hot batch (``kjt_capacity`` mode): ``values`` int64 [n <= capacity] in key-major KJT order, ``lengths``
+        int32 [F*B], ``labels`` [B] (pinned host or device).  ``sum(lengths)`` must equal ``n``; what lies past ``n`` in
+        the static buffer is never read as an id."""
+        if self._values is None:
+            raise ValueError("CudaGraphTrainStep.step_kjt needs kjt_capacity= at construction")
+        n = values.numel()
+        if n > self._values.numel():
+            raise ValueError(f"batch holds {n} ids, capacity is {self._values.numel()}")
+        self._values[:n].copy_(values, non_blocking=True)
+        self._lengths.copy_(lengths, non_blocking=True)
+        self._labels.copy_(labels, non_blocking=True)
+        return self._run()
+
+    def _run(self):
         self._calls += 1
         cur = torch.cuda.current_stream(self._dev)
         if self._calls <= self._warmup:
