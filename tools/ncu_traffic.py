@@ -26,7 +26,7 @@ COMPOSITES = {
 
 def short(name: str) -> str:
     name = re.sub(r"^void\s+", "", name)
-    name = re.sub(r"^tt::", "", name)
+    name = re.sub(r"^(tt::)?(tc::)?", "", name)
     return re.split(r"[<(]", name)[0]
 
 
