@@ -303,3 +303,75 @@ def test_dedup_matches_torch_unique(cuda, rows, B, L, dup):
         bag.weight = torch.nn.Parameter(torch.zeros(1, 4, device=cuda))
     got_u, got_inv, got_c = dedup_rows(ebc, tt.KeyedJaggedTensor.from_lengths_sync(keys, v.to(cuda), l.to(cuda)))
     assert torch.equal(got_u.cpu(), want_u) and torch.equal(got_c.cpu(), want_c) and torch.equal(got_inv.cpu(), want_inv)
+
+
+@pytest.mark.parametrize("W,Bl,rows,D", [(8, 256, 1777, 64), (8, 256, 3001, 64), (4, 256, 1777, 64), (8, 512, 90, 64), (8, 300, 50000, 128)])
+def test_table_wise_owner_at_world_8_virtual_ranks(cuda, W, Bl, rows, D):
+    """What the owner of ONE table does in an 8-rank table-wise job, on one GPU: the key-major KJT over the GLOBAL batch
+    (W * Bl bags, built on the device from id columns, so `values` is over-allocated and the live count sits in the
+    offsets) -> fused backward reading every sample's gradient row from the buffer of the rank that owns the sample
+    (W virtual peers) -> row-wise Adagrad with grad_scale 1/W.  Three steps against the oracle's dense formula.
+    (bench.py's N = 8 parity check once reported 8e-4 on the gathered tables where N = 2 / 4 gave 3e-8.)"""
+    from ctypes import byref
+    import two_tower_recommender_model_b200 as tt
+    from two_tower_recommender_model_b200 import _native as N
+    B = W * Bl
+    specs, ebc, weights = build(cuda, [D], [rows], ["sum"])
+    apply_optimizer_in_backward(tt.RowWiseAdagrad, ebc.parameters(), {"lr": 0.05})
+    ebc._grad_scale = 1.0 / W
+    w_ref = weights[0].clone()
+    state = torch.zeros(rows)
+    rows_dev = torch.tensor([rows], device=cuda)
+    for step in range(3):
+        g = torch.Generator().manual_seed(100 * step + W + rows)
+        ids = torch.randint(0 if step == 1 else 1, 2 * rows, (1, B), generator=g)      # step 1: id 0 -> empty bags too
+        go = torch.randn(B, D, generator=g)
+        kjt = tt.KeyedJaggedTensor.from_id_columns(["f0"], ids.to(cuda), rows_dev)
+        vals, offs = kjt.values().contiguous(), kjt.offsets().to(torch.int32).contiguous()
+        gbufs = [go[s * Bl:(s + 1) * Bl].clone().to(cuda) for s in range(W)]
+        spec = ebc._sparse_optimizer_spec(advance_step=True)
+        plan, _ = ebc._build_plan(("f0",), B, with_state=True)
+        n = vals.numel()
+        ws = N.workspace(N.load().tt_ebc_backward_workspace_bytes(n), cuda)
+        pg = _peer_struct(N, gbufs, Bl)
+        N.call("tt_ebc_backward_fused_peer", byref(plan), byref(spec), N.ptr(vals), n, N.ptr(offs), byref(pg), N.ptr(ws), ws.numel(), N.stream_ptr(cuda))
+        # oracle: dense gradient of the table / W, row-wise Adagrad
+        v, l, _ = oracle.transform_to_torchrec_batch({"f0": ids[0].tolist(), "label": [0] * B}, ["f0"], [rows])
+        dense = oracle.ebc_dense_grads(specs, ["f0"], v, l, go)[0] / W
+        oracle.rowwise_adagrad_dense(w_ref, state, dense, lr=0.05, eps=1e-10)
+        got = ebc.embedding_bags["t_f0"].weight.detach().cpu()
+        torch.testing.assert_close(got, w_ref, rtol=2e-5, atol=2e-6, msg=lambda m: f"step {step}: {m}")
+
+
+@pytest.mark.parametrize("B", [256, 1024, 2048])
+@pytest.mark.parametrize("mode", ["dense_grad", "adagrad"])
+def test_short_runs_across_segment_boundaries(cuda, B, mode):
+    """One id per bag, two small tables (the shape of bench.py's sharded parity check): with 2*B keys over 3001 + 1777 rows
+    many rows are hit 2-7 times and some of those short runs straddle a multiple of 128 in the sorted key array, so
+    their sum is formed by two groups through the hot-row scratch.  Dense gradients and the fused Adagrad update must
+    still equal the oracle's to rounding."""
+    import two_tower_recommender_model_b200 as tt
+    rows, D = [3001, 1777], 64
+    specs, ebc, weights = build(cuda, [D, D], rows, ["sum", "sum"])
+    keys = ["f0", "f1"]
+    if mode == "adagrad":
+        apply_optimizer_in_backward(tt.RowWiseAdagrad, ebc.parameters(), {"lr": 0.05})
+    state = [torch.zeros(r) for r in rows]
+    rows_dev = torch.tensor(rows, device=cuda)
+    for step in range(3):
+        g = torch.Generator().manual_seed(7000 + 100 * step + B)
+        ids = torch.stack([torch.randint(1, r, (B,), generator=g) for r in rows])
+        go = torch.randn(B, 2 * D, generator=g)
+        v, l, _ = oracle.transform_to_torchrec_batch({"f0": ids[0].tolist(), "f1": ids[1].tolist(), "label": [0] * B}, keys, rows)
+        want = oracle.ebc_dense_grads(specs, keys, v, l, go)
+        for p in ebc.parameters():
+            p.grad = None
+        kt = ebc(tt.KeyedJaggedTensor.from_id_columns(keys, ids.to(cuda), rows_dev))
+        kt.values().backward(go.to(cuda))
+        for i, s in enumerate(specs):
+            p = ebc.embedding_bags[s.name].weight
+            if mode == "dense_grad":
+                torch.testing.assert_close(p.grad.cpu(), want[i], rtol=1e-5, atol=1e-6, msg=lambda m: f"step {step} table {i}: {m}")
+            else:
+                oracle.rowwise_adagrad_dense(weights[i], state[i], want[i], lr=0.05, eps=1e-10)
+                torch.testing.assert_close(p.detach().cpu(), weights[i], rtol=2e-5, atol=2e-6, msg=lambda m: f"step {step} table {i}: {m}")

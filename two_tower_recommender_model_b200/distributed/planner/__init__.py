@@ -95,9 +95,20 @@ def _find_ebcs(module: nn.Module):
             yield path, m
 
 
-def _table_bytes(cfg) -> int:
-    # weights + one fp32 of row-wise state per row (Adagrad); Adam adds a full-size first moment
-    return cfg.num_embeddings * cfg.embedding_dim * 4 + cfg.num_embeddings * 4
+def _table_bytes(cfg, adam: bool = False) -> int:
+    # weights + one fp32 of row-wise state per row (Adagrad's sum / Adam's second moment); row-wise Adam adds a
+    # full-size first moment, i.e. the footprint of the table doubles
+    nbytes = cfg.num_embeddings * cfg.embedding_dim * 4 + cfg.num_embeddings * 4
+    return nbytes + (cfg.num_embeddings * cfg.embedding_dim * 4 if adam else 0)
+
+
+def _uses_rowwise_adam(ebc) -> bool:
+    """True when ``apply_optimizer_in_backward(RowWiseAdam, ebc.parameters(), ...)`` tagged this collection."""
+    try:
+        from ... import _native as N
+        return ebc._in_backward_kind() == N.OPT_ROWWISE_ADAM
+    except Exception:
+        return False
 
 
 class EmbeddingShardingPlanner:
@@ -119,13 +130,14 @@ class EmbeddingShardingPlanner:
         plan: Dict[str, Dict[str, ParameterSharding]] = {}
         for path, ebc in _find_ebcs(module):
             tables: Dict[str, ParameterSharding] = {}
-            cfgs = sorted(ebc.embedding_bag_configs(), key=lambda c: (-_table_bytes(c), c.name))
+            adam = _uses_rowwise_adam(ebc)
+            cfgs = sorted(ebc.embedding_bag_configs(), key=lambda c: (-_table_bytes(c, adam), c.name))
             for cfg in cfgs:
                 want = None
                 c = self._constraints.get(cfg.name)
                 if c is not None and c.sharding_types:
                     want = c.sharding_types[0]
-                nbytes = _table_bytes(cfg)
+                nbytes = _table_bytes(cfg, adam)
                 if want is None:
                     want = ShardingType.TABLE_WISE.value if (nbytes <= budget or W == 1) else ShardingType.ROW_WISE.value
                     # Fewer tables than ranks: table-wise would leave ranks without embedding work while the owners
