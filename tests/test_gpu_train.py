@@ -311,6 +311,24 @@ def test_ray_tune_variant_towers(cuda):
     torch.testing.assert_close(loss.detach().cpu(), want, rtol=1e-5, atol=1e-6)
     loss.backward()
     assert model.query_proj._mlp[0]._linear.weight.grad is not None
+    # backward of the same variant: plain-torch autograd on the same weights (tower parameters, dense tables' gradients)
+    leaf = {k: t.clone().requires_grad_(True) for k, t in sd.items()}
+
+    def mlp_g(x, prefix, n):
+        for j in range(n):
+            x = torch.relu(x @ leaf[f"{prefix}._mlp.{j}._linear.weight"].t() + leaf[f"{prefix}._mlp.{j}._linear.bias"])
+        return x
+    pooled_g = {}
+    for i, k in enumerate(keys):
+        bag = torch.repeat_interleave(torch.arange(B), l[i * B:(i + 1) * B].long())
+        rows_k = v[int(offs[i * B]):int(offs[(i + 1) * B])]
+        pooled_g[k] = torch.zeros(B, dims[k]).index_add(0, bag, leaf[f"ebc.embedding_bags.t_{k}.weight"][rows_k])
+    qg = mlp_g(torch.cat([pooled_g["u_a"], pooled_g["u_b"], dense[:, :3]], 1), "query_proj", 2)
+    cg = mlp_g(torch.cat([pooled_g["i_a"], dense[:, 3:]], 1), "candidate_proj", 2)
+    torch.nn.functional.binary_cross_entropy_with_logits((qg * cg).sum(1), labels.float()).backward()
+    for k, p in model.state_dict(keep_vars=True).items():
+        assert p.grad is not None, k
+        torch.testing.assert_close(p.grad.cpu(), leaf[k].grad, rtol=1e-4, atol=1e-6, msg=lambda m: f"grad of {k}: {m}")
 
 
 def test_cuda_graph_multi_hot_kjt_step_equals_eager(cuda):
