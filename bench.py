@@ -72,7 +72,11 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t_mark = [], None, index, None
+
+    def mark(self):
+        """Samples that arrive before this call (nvidia-smi start-up, warm-up) are dropped."""
+        self.t_mark = time.time()
 
     def start(self):
         try:
@@ -84,7 +88,8 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            if self.t_mark is not None and time.time() >= self.t_mark:
+                self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
         if self.proc is not None:
@@ -335,12 +340,15 @@ def time_block(cfg, B, dev, rank, world, local, args, sharding, exchange, lib, w
         launches_per_step = int(lib.tt_kernel_launch_count() - l_before)
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        graph_step(*dev_raw[i % nb]) if use_graph else step(resident[i % nb])
-    barrier()
+    # the sampler starts BEFORE the warm-up (nvidia-smi needs ~0.1 s to deliver its first line) and keeps what arrives
+    # from the start of the timed region on
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        graph_step(*dev_raw[i % nb]) if use_graph else step(resident[i % nb])
+    barrier()
+    sampler.mark()
     l0 = lib.tt_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -378,8 +386,16 @@ def time_block(cfg, B, dev, rank, world, local, args, sharding, exchange, lib, w
             last = float(pipe.progress(it)[0])
         t1.record()
         barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    # K steps of a few ms give nvidia-smi (20 ms period) only a handful of samples: keep replaying the SAME step under the
+    # sampler until it has covered >= 0.5 s of this load (all ranks run the same count: the sharded step has collectives)
     ms_e2e = t0.elapsed_time(t1) / args.steps
+    extra = max(0, int(500.0 / max(ms_e2e, 1e-3)) - 2 * args.steps)
+    for i in range(extra):
+        graph_step(*dev_raw[i % nb]) if use_graph else step(resident[i % nb])
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "timed region (device-resident + e2e steps) + %d further replays of the same step" % extra
 
     per_call = {}
     if with_kernels:

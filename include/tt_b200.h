@@ -96,6 +96,19 @@ int tt_kjt_permute_2d(const int32_t* permute /* device [T_out] */, int64_t num_o
                       int32_t* out_lengths, int32_t* out_offsets, int64_t* out_values,
                       void* ws, size_t ws_bytes, void* stream);
 
+/* Sync-free row-wise input dist for multi-hot KJTs (TorchRec: block_bucketize + counts / lengths / values
+ * all-to-alls + permute, torchrec.distributed.dist_data.KJTAllToAll).  Every rank all-gathers its key-major KJT
+ * with `values` padded to a fixed `capacity` and its offsets [F*B+1]; this call keeps, for the calling rank's row
+ * range [row_lo[f], row_hi[f]) (device arrays), the ids of every source bag in order, rebased to the shard:
+ * output = key-major KJT over the GLOBAL batch, bag index f*(W*B) + r*B + b, out_values capacity W*capacity.
+ * Equals bucket `rank` of tt_kjt_block_bucketize on the concatenated batch (bit-exact). */
+size_t tt_kjt_gathered_range_workspace_bytes(int64_t world, int64_t num_features, int64_t batch);
+int tt_kjt_gathered_range(const int64_t* gathered_values /* [W, capacity] */, int64_t capacity,
+                          const int32_t* gathered_offsets /* [W, F*B+1] */, const int64_t* row_lo,
+                          const int64_t* row_hi, int64_t world, int64_t num_features, int64_t batch,
+                          int64_t* out_values, int32_t* out_lengths, int32_t* out_offsets, void* ws,
+                          size_t ws_bytes, void* stream);
+
 /* fbgemm::block_bucketize_sparse_features (TorchRec row-wise input_dist):
  * block=ceil(R_f/W); bucket=id/block; local=id-bucket*block.  Output is
  * bucket-major: new_lengths[(w*F+f)*B+b]; order inside a bag is preserved.

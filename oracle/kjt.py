@@ -182,6 +182,29 @@ def block_bucketize_vectorized(
     return new_lengths, new_values, unbucketize
 
 
+def gathered_range_shard(values_per_rank: Sequence[torch.Tensor], lengths_per_rank: Sequence[torch.Tensor],
+                         row_lo: Sequence[int], row_hi: Sequence[int], batch_size: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """What one rank holds after TorchRec's sparse input dist (``torchrec.distributed.dist_data.KJTAllToAll`` after
+    ``block_bucketize_sparse_features`` for row-wise tables; plain feature routing for table-wise ones), written as a
+    filter over every rank's key-major KJT: the key-major KJT over the GLOBAL batch (bag ``f*(W*B) + r*B + b``) with,
+    in source order, the ids of bag ``(r, f, b)`` that fall into ``[row_lo[f], row_hi[f])``, rebased to ``row_lo[f]``.
+    For ``row_lo/hi`` = a block range this is bucket ``w`` of :func:`block_bucketize_sparse_features` on the
+    concatenated batch (checked in tests/test_oracle_golden.py).  Restates include/tt_b200.h::tt_kjt_gathered_range."""
+    W, F, B = len(values_per_rank), len(row_lo), batch_size
+    out_vals: List[int] = []
+    out_len = torch.zeros(F * W * B, dtype=torch.int32)
+    offs = [lengths_to_offsets(l).tolist() for l in lengths_per_rank]
+    for f in range(F):
+        for r in range(W):
+            for b in range(B):
+                for p in range(offs[r][f * B + b], offs[r][f * B + b + 1]):
+                    v = int(values_per_rank[r][p])
+                    if row_lo[f] <= v < row_hi[f]:
+                        out_vals.append(v - row_lo[f])
+                        out_len[f * W * B + r * B + b] += 1
+    return torch.tensor(out_vals, dtype=torch.int64), out_len
+
+
 def dedup_rows(linear_ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Unique (table,row) keys, ascending, with inverse map and counts
     (``torch.unique(sorted=True, return_inverse=True, return_counts=True)``)."""

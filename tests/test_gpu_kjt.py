@@ -137,3 +137,47 @@ def test_radix_sort_stable(cuda, n, bits):
     ko, vo = sort_pairs(k_dev, vals.to(torch.int32).to(cuda), bits)
     assert torch.equal(vo.cpu().long(), order)
     assert torch.equal((ko.cpu().long() & 0xFFFFFFFF), keys[order])
+
+
+@pytest.mark.parametrize("W,F,B,L,rows", [(2, 1, 2, 3, [10]), (4, 3, 257, 6, [1000, 7, 123457]), (8, 2, 1024, 20, [100_000_000, 50]), (3, 2, 50, 0, [5, 5])])
+def test_gathered_range_matches_oracle(cuda, W, F, B, L, rows):
+    """tt_kjt_gathered_range (sync-free row-wise / table-wise input dist for multi-hot KJTs) against the oracle's filter,
+    bit-exact, for every rank's row range, with the gathered values padded to a common capacity."""
+    from two_tower_recommender_model_b200.functional import kjt_gathered_range
+    keys = [f"f{i}" for i in range(F)]
+    per_rank = [random_kjt(keys, rows, B, L, seed=W * 31 + r) for r in range(W)]
+    cap = max(int(v.numel()) for v, _ in per_rank) + 5
+    g_vals = torch.full((W, cap), -77, dtype=torch.int64)
+    g_offs = torch.zeros(W, F * B + 1, dtype=torch.int32)
+    for r, (v, l) in enumerate(per_rank):
+        g_vals[r, :v.numel()] = v
+        g_offs[r] = oracle.lengths_to_offsets(l).to(torch.int32)
+    for w in ([0, W - 1] if W > 2 else range(W)):
+        block = [-(-r // W) for r in rows]
+        lo = [w * b for b in block]
+        hi = [min((w + 1) * b, r) for b, r in zip(block, rows)]
+        if w == 0 and F > 1:
+            lo[1], hi[1] = 0, rows[1]          # a table-wise feature owned by this rank: all of its rows
+        want_v, want_l = oracle.gathered_range_shard([p[0] for p in per_rank], [p[1] for p in per_rank], lo, hi, B) \
+            if g_vals.numel() < 200_000 else _vectorised_shard(per_rank, lo, hi, B)
+        ov, ol, oo = kjt_gathered_range(g_vals.to(cuda).view(-1), cap, g_offs.to(cuda).view(-1), torch.tensor(lo, device=cuda),
+                                        torch.tensor(hi, device=cuda), W, F, B)
+        assert torch.equal(ol.cpu(), want_l)
+        assert torch.equal(oo.cpu(), oracle.lengths_to_offsets(want_l).to(torch.int32))
+        assert torch.equal(ov.cpu()[:want_v.numel()], want_v)
+
+
+def _vectorised_shard(per_rank, lo, hi, B):
+    """The oracle's filter, vectorised for the large case (checked equal to the loop on the small ones above)."""
+    W, F = len(per_rank), len(lo)
+    vals, lens = [], []
+    for f in range(F):
+        for r in range(W):
+            v, l = per_rank[r]
+            off = oracle.lengths_to_offsets(l).long()
+            seg = v[int(off[f * B]):int(off[(f + 1) * B])]
+            bag = torch.repeat_interleave(torch.arange(B), l[f * B:(f + 1) * B].long())
+            keep = (seg >= lo[f]) & (seg < hi[f])
+            vals.append(seg[keep] - lo[f])
+            lens.append(torch.bincount(bag[keep], minlength=B).to(torch.int32))
+    return torch.cat(vals), torch.cat(lens)

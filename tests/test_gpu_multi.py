@@ -281,3 +281,76 @@ def test_two_rank_global_negatives_and_sharded_retrieval(sharding):
         pytest.skip("needs >= 2 GPUs")
     port = 29900 + os.getpid() % 90 + (0 if sharding == "table_wise" else 1)
     _run_ranks(_worker_global, lambda r: (r, 2, port, sharding))
+
+
+# ------------------------------------------------------------------ multi-hot KJTs: sync-free input dist + peer exchange + CUDA graph
+def _worker_multi_hot(rank, world, port, sharding, errq):
+    """Mean-pooled multi-hot history (the shape of BASELINE configs[2]) + a single-id item feature, sharded row-wise or
+    table-wise with the peer-memory exchange; the batches arrive as fixed-capacity KJTs (CudaGraphTrainStep.step_kjt), so
+    the input dist is the all-gather + tt_kjt_gathered_range route (no host sync) and steps 3.. replay ONE captured
+    graph.  Losses of every step and the gathered tables against the unsharded CPU oracle."""
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+        dev = torch.device("cuda", rank)
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        import oracle
+        from oracle.ebc import TableSpec
+        import two_tower_recommender_model_b200 as tt
+        from torch.distributed.optim import _apply_optimizer_in_backward as apply_optimizer_in_backward
+        from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
+
+        keys, rows, Bm, Lmax, steps = ["hist", "item"], [1500, 900], 256, 6, 5
+        specs = [TableSpec("t_hist", rows[0], DIM, ["hist"], "mean"), TableSpec("t_item", rows[1], DIM, ["item"], "sum")]
+        ref = oracle.OracleTwoTower(specs, LAYERS, loss="bce", sparse_lr=LR, dense_lr=LR, seed=5, dense_optimizer="sgd")
+        ebc = tt.EmbeddingBagCollection(tables=[
+            tt.EmbeddingBagConfig(name="t_hist", embedding_dim=DIM, num_embeddings=rows[0], feature_names=["hist"], pooling=tt.PoolingType.MEAN),
+            tt.EmbeddingBagConfig(name="t_item", embedding_dim=DIM, num_embeddings=rows[1], feature_names=["item"])], device=torch.device("meta"))
+        task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, LAYERS, device=dev))
+        apply_optimizer_in_backward(tt.RowWiseAdagrad, task.two_tower.ebc.parameters(), {"lr": LR})
+        cons = {t: ParameterConstraints(sharding_types=[sharding]) for t in ("t_hist", "t_item")}
+        plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world), constraints=cons).collective_plan(task, tt.get_default_sharders(), dist.GroupMember.WORLD)
+        model = tt.DistributedModelParallel(module=task, device=dev, plan=plan, sharding_kwargs={"peer_exchange": True})
+        model.module.two_tower.load_state_dict(ref.torchrec_state_dict())
+        opt = tt.KeyedOptimizerWrapper(dict(model.named_parameters()), lambda p: torch.optim.SGD(p, lr=LR))
+
+        def raw(r, s):
+            g = torch.Generator().manual_seed(2000 * s + r)
+            lens = torch.cat([torch.randint(0, Lmax + 1, (Bm,), generator=g), torch.ones(Bm, dtype=torch.int64)]).to(torch.int32)
+            vals = torch.cat([torch.randint(0, rows[0], (int(lens[:Bm].sum()),), generator=g), torch.randint(0, rows[1], (Bm,), generator=g)])
+            return vals, lens, torch.randint(0, 2, (Bm,), generator=g, dtype=torch.int32)
+
+        step = tt.CudaGraphTrainStep(model, opt, keys, rows, Bm, dev, warmup_steps=2, kjt_capacity=Bm * (Lmax + 1))
+        model.train()
+        for s in range(steps):
+            per_rank = [raw(r, s) for r in range(world)]
+            losses = ref.train_step_ranks(keys, per_rank)
+            v, l, y = per_rank[rank]
+            loss_d = step.step_kjt(v.pin_memory(), l.pin_memory(), y.pin_memory())[0]
+            torch.testing.assert_close(loss_d.cpu(), losses[rank], rtol=1e-4, atol=1e-6, msg=lambda m: f"step {s}: {m}")
+        assert step.captured
+        from torch.distributed._shard.sharded_tensor import ShardedTensor
+        want = ref.torchrec_state_dict()
+        sd = model.module.two_tower.state_dict()
+        for k, t in sd.items():
+            if isinstance(t, ShardedTensor):
+                full = torch.zeros(t.size(), device=dev) if rank == 0 else None
+                t.gather(0, full)
+            else:
+                full = t
+            if rank == 0:
+                torch.testing.assert_close(full.cpu(), want[k], rtol=1e-4, atol=1e-5, msg=lambda m: f"{k}: {m}")
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)          # the captured graph holds NCCL kernels: skip the (cosmetic) process-group teardown
+    except Exception:
+        errq.put(f"rank {rank}:\n{traceback.format_exc()}")
+        os._exit(1)
+
+
+@pytest.mark.parametrize("sharding", ["row_wise", "table_wise"])
+def test_two_rank_multi_hot_sync_free_input_dist_and_graph(sharding):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    port = 29950 + os.getpid() % 40 + (0 if sharding == "row_wise" else 1)
+    _run_ranks(_worker_multi_hot, lambda r: (r, 2, port, sharding))

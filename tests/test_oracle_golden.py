@@ -192,3 +192,33 @@ def test_chunked_in_batch_softmax_equals_plain():
     torch.testing.assert_close(d1, d0, rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(q.grad, gq, rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(c.grad, gc, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_gathered_range_shard_is_one_bucket_of_block_bucketize(seed):
+    """The sync-free input dist's filter, restated in the oracle, against the oracle's block_bucketize on the
+    concatenated batch: rank w's shard == bucket w (lengths and values), for every w."""
+    W, B, F = 3, 11, 2
+    rows = [40, 9]
+    per_rank = [random_kjt(["a", "b"], rows, B, 5, seed * 10 + r) for r in range(W)]
+    # concatenated key-major batch: feature f = rank 0's bags, then rank 1's, ...
+    cat_len = torch.cat([per_rank[r][1][f * B:(f + 1) * B] for f in range(F) for r in range(W)])
+    offs = [oracle.lengths_to_offsets(l).tolist() for _, l in per_rank]
+    cat_val = torch.cat([per_rank[r][0][offs[r][f * B]:offs[r][(f + 1) * B]] for f in range(F) for r in range(W)])
+    nl, nv, _ = oracle.block_bucketize_sparse_features(cat_len, cat_val, rows, W, W * B)
+    noff = oracle.lengths_to_offsets(nl).tolist()
+    for w in range(W):
+        block = [-(-r // W) for r in rows]
+        lo = [w * b for b in block]
+        hi = [min((w + 1) * b, r) for b, r in zip(block, rows)]
+        v, l = oracle.gathered_range_shard([p[0] for p in per_rank], [p[1] for p in per_rank], lo, hi, B)
+        n = F * W * B
+        assert l.tolist() == nl[w * n:(w + 1) * n].tolist()
+        assert v.tolist() == nv[noff[w * n]:noff[(w + 1) * n]].tolist()
+
+
+def test_gathered_range_shard_kat():
+    """Hand-computed: W = 2 ranks, B = 2, one feature, rows 10, this rank holds rows [5, 10).
+    rank 0 bags: [7, 1], [9]; rank 1 bags: [], [5, 4, 6]  ->  global bags [7-5], [9-5], [], [5-5, 6-5]."""
+    v, l = oracle.gathered_range_shard([T([7, 1, 9]), T([5, 4, 6])], [T([2, 1], dtype=torch.int32), T([0, 3], dtype=torch.int32)], [5], [10], 2)
+    assert v.tolist() == [2, 4, 0, 1] and l.tolist() == [1, 1, 0, 2]

@@ -83,6 +83,8 @@ SIGNATURES = {
     "tt_kjt_permute_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "tt_kjt_permute_2d": (c_int32, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "tt_kjt_bucketize_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
+    "tt_kjt_gathered_range_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "tt_kjt_gathered_range": (c_int32, [_P, c_int64, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),
     "tt_kjt_block_bucketize": (c_int32, [_P, _P, _P, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, c_size_t, _P]),
     "tt_ebc_forward": (c_int32, [POINTER(EbcPlan), _P, _P, _P, _P]),
     "tt_ebc_forward_peer": (c_int32, [POINTER(EbcPlan), _P, _P, POINTER(PeerBuffers), _P]),

@@ -243,6 +243,47 @@ __global__ void columns_values_kernel(const int64_t* __restrict__ ids,
 }
 
 // ---------------------------------------------------------------------------
+// Row-wise shard of W gathered KJTs (sync-free multi-hot input dist): every rank contributes its key-major KJT
+// (values padded to a fixed capacity, offsets [F*B+1]); the output is this rank's key-major KJT over the GLOBAL
+// batch -- bag (f, r*B + b) keeps, in order, the ids of source bag (r, f, b) that fall into [lo[f], hi[f]),
+// rebased to the shard.  Equals bucket `rank` of block_bucketize_sparse_features on the concatenated batch.
+// One thread per output bag: bags are short (pooling factor ~20), ids of a bag are contiguous.
+// ---------------------------------------------------------------------------
+__global__ void gathered_range_count_kernel(const int64_t* __restrict__ values, const int32_t* __restrict__ offsets,
+                                            const int64_t* __restrict__ lo, const int64_t* __restrict__ hi,
+                                            int32_t* __restrict__ lengths, int64_t W, int64_t F, int64_t B, int64_t cap) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // output bag: f * (W*B) + r * B + b
+  if (o >= F * W * B) return;
+  const int64_t f = o / (W * B), rb = o - f * (W * B), r = rb / B, b = rb - r * B;
+  const int32_t* off = offsets + r * (F * B + 1) + f * B + b;
+  const int64_t* v = values + r * cap;
+  const int64_t l = lo[f], h = hi[f];
+  int cnt = 0;
+  for (int p = off[0]; p < off[1]; ++p) {
+    const int64_t id = v[p];
+    cnt += (id >= l && id < h) ? 1 : 0;
+  }
+  lengths[o] = cnt;
+}
+
+__global__ void gathered_range_scatter_kernel(const int64_t* __restrict__ values, const int32_t* __restrict__ offsets,
+                                              const int64_t* __restrict__ lo, const int64_t* __restrict__ hi,
+                                              const int32_t* __restrict__ out_offsets, int64_t* __restrict__ out_values,
+                                              int64_t W, int64_t F, int64_t B, int64_t cap) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= F * W * B) return;
+  const int64_t f = o / (W * B), rb = o - f * (W * B), r = rb / B, b = rb - r * B;
+  const int32_t* off = offsets + r * (F * B + 1) + f * B + b;
+  const int64_t* v = values + r * cap;
+  const int64_t l = lo[f], h = hi[f];
+  int dst = out_offsets[o];
+  for (int p = off[0]; p < off[1]; ++p) {
+    const int64_t id = v[p];
+    if (id >= l && id < h) out_values[dst++] = id - l;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // permute_2D_sparse_data
 // ---------------------------------------------------------------------------
 __global__ void permute_lengths_kernel(const int32_t* __restrict__ permute,
@@ -381,6 +422,30 @@ int tt_kjt_from_columns_range(const int64_t* ids, const int64_t* num_embeddings,
   if (n > 0) {
     columns_values_range_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, num_embeddings, row_lo, lengths, offsets, values, B, n);
     TT_CHECK_LAUNCH("columns_values_range");
+  }
+  return TT_OK;
+}
+
+size_t tt_kjt_gathered_range_workspace_bytes(int64_t W, int64_t F, int64_t B) { return scan_workspace_bytes(W * F * B) + 256; }
+
+int tt_kjt_gathered_range(const int64_t* values, int64_t capacity, const int32_t* offsets, const int64_t* row_lo,
+                          const int64_t* row_hi, int64_t W, int64_t F, int64_t B, int64_t* out_values,
+                          int32_t* out_lengths, int32_t* out_offsets, void* ws, size_t ws_bytes, void* stream) {
+  TT_CHECK_ARG(W >= 1 && F >= 0 && B >= 0 && capacity >= 0 && offsets && row_lo && row_hi && out_lengths && out_offsets,
+               "kjt_gathered_range: bad args");
+  cudaStream_t s = as_stream(stream);
+  const int64_t n = W * F * B;
+  if (n >= ((int64_t)1 << 31) || W * capacity >= ((int64_t)1 << 31)) return fail(TT_ERR_UNSUPPORTED, "kjt_gathered_range: too large");
+  if (n > 0) {
+    gathered_range_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(values, offsets, row_lo, row_hi, out_lengths, W, F, B, capacity);
+    TT_CHECK_LAUNCH("gathered_range_count");
+  }
+  int rc = scan_impl(out_lengths, out_offsets, n, nullptr, 1, ws, ws_bytes, s);
+  if (rc) return rc;
+  if (n > 0) {
+    gathered_range_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(values, offsets, row_lo, row_hi, out_offsets, out_values,
+                                                                             W, F, B, capacity);
+    TT_CHECK_LAUNCH("gathered_range_scatter");
   }
   return TT_OK;
 }

@@ -328,6 +328,8 @@ class ShardedEmbeddingBagCollection(nn.Module):
                     setattr(bag.weight, a, v)
         self._prefetched: Dict[int, Any] = {}
         self._local_rows_dev: Dict[Any, torch.Tensor] = {}
+        self._gather_cache: Dict[Any, Any] = {}       # (lo, hi) device arrays of the sync-free KJT gather, per key set
+        self._gathered: Any = None                    # (id(kjt), values, offsets) all-gathered once per batch, both groups use it
 
     # ---- surface shared with EmbeddingBagCollection
     def embedding_bag_configs(self) -> List[EmbeddingBagConfig]:
@@ -361,6 +363,8 @@ class ShardedEmbeddingBagCollection(nn.Module):
             return self._dist_dense_ids(grp, keys, dense[0], B)
         if dense is not None and grp.kind == "row_wise" and self._peer_exchange and dense[0].is_cuda:
             return self._dist_dense_ids_rw(grp, keys, dense[0], B)
+        if self._peer_exchange and getattr(kjt, "_values_padded", False) and kjt.values().is_cuda:
+            return self._dist_kjt_gather(grp, kjt, B)
         sub = kjt.permute([keys.index(f) for f in grp.features])
         lengths, values = sub.lengths(), sub.values()
         if grp.kind == "row_wise":
@@ -460,6 +464,56 @@ class ShardedEmbeddingBagCollection(nn.Module):
         kjt._peer_scatter = True
         return kjt
 
+    def _dist_kjt_gather(self, grp: _Group, kjt: KeyedJaggedTensor, B: int):
+        """Sync-free input dist for multi-hot KJTs whose ``values`` sit in a FIXED-CAPACITY buffer (the same capacity on
+        every rank: ``CudaGraphTrainStep.step_kjt``, or any KJT flagged ``_values_padded``): the whole KJT (padded values +
+        offsets) is ALL-GATHERED -- two fixed-size collectives, no count exchange, no host sync, so the step can be
+        captured -- and ``tt_kjt_gathered_range`` keeps what this rank stores: its row range of every row-wise table,
+        all rows of the table-wise tables it owns, nothing of the rest (those bags are empty here).  TorchRec reaches
+        the same KJT through block_bucketize + three all-to-alls + permute (KJTAllToAll), with a host sync for the
+        split sizes; the ids a rank receives that it does not keep cost 8 bytes each on NVLink."""
+        from ..functional import kjt_gathered_range
+        W, pg, dev = self._world, self._pg, kjt.values().device
+        keys = list(kjt.keys())
+        F = len(keys)
+        cap = kjt.values().numel()
+        key = (grp.kind, tuple(keys), B, cap)
+        st = self._gather_cache.get(key)
+        if st is None:
+            table_of = {f: c.name for c in self._configs for f in c.feature_names}
+            lo, hi = [], []
+            for f in keys:
+                if f not in grp.feat_dim:
+                    lo.append(0); hi.append(0)                       # not a feature of this sharding group
+                elif grp.kind == "row_wise":
+                    _k, off, rows = self._shard_info[table_of[f]]
+                    lo.append(off); hi.append(off + rows)
+                else:
+                    owned = f in grp.dest_features[self._rank]
+                    lo.append(0); hi.append(grp.feat_rows[f] if owned else 0)
+            st = (torch.tensor(lo, dtype=torch.int64, device=dev), torch.tensor(hi, dtype=torch.int64, device=dev))
+            self._gather_cache[key] = st
+        lo, hi = st
+        if self._gathered is not None and self._gathered[0] is kjt:
+            _, g_vals, g_offs = self._gathered
+        else:
+            vals = kjt.values().contiguous()
+            offs = kjt.offsets().to(torch.int32).contiguous()
+            g_vals = vals.new_empty(W * cap)
+            g_offs = offs.new_empty(W * (F * B + 1))
+            dist.all_gather_into_tensor(g_vals, vals, group=pg)
+            dist.all_gather_into_tensor(g_offs, offs, group=pg)
+            self._gathered = (kjt, g_vals, g_offs)
+        if grp.kind == "table_wise" and not grp.dest_features[self._rank]:
+            return None
+        out_v, out_l, out_o = kjt_gathered_range(g_vals, cap, g_offs, lo, hi, W, F, B)
+        out = KeyedJaggedTensor(keys=keys, values=out_v, lengths=out_l, offsets=out_o, stride=W * B)
+        out._values_padded = True
+        if grp.kind == "row_wise":
+            out._peer_scatter = True
+            out._multi_hot = True
+        return out
+
     @staticmethod
     def _permute_no_sync(kjt: KeyedJaggedTensor, perm: List[int], total: int) -> KeyedJaggedTensor:
         # KJT.permute needs length_per_key only to size the output; a true permutation keeps the total.
@@ -470,8 +524,11 @@ class ShardedEmbeddingBagCollection(nn.Module):
         return kjt.permute(perm)
 
     def input_dist(self, kjt: KeyedJaggedTensor):
-        return {"B": kjt.stride(), "lengths": kjt.lengths(), "keys": kjt.keys(),
-                "tw": self._dist_group(self._tw, kjt), "rw": self._dist_group(self._rw, kjt)}
+        try:
+            return {"B": kjt.stride(), "lengths": kjt.lengths(), "keys": kjt.keys(),
+                    "tw": self._dist_group(self._tw, kjt), "rw": self._dist_group(self._rw, kjt)}
+        finally:
+            self._gathered = None
 
     def prefetch_input_dist(self, batch, ready_event=None) -> None:
         """Called by TrainPipelineSparseDist one batch ahead: issues the KJT exchange early."""
@@ -511,8 +568,17 @@ class ShardedEmbeddingBagCollection(nn.Module):
                     c0 += self._tw.feat_dim[f]
         # row-wise: partial pools over the global batch, summed by reduce-scatter
         if self._rw.features and getattr(ctx["rw"], "_peer_scatter", False):
-            # one id per bag at most (dense id columns): mean pooling == sum pooling, nothing to divide
-            cols.update(self._group_forward_peer(self._rw, ctx["rw"], self.rw_ebc, B, True))
+            # dense id columns: one id per bag at most, mean pooling == sum pooling, nothing to divide
+            rw_cols = self._group_forward_peer(self._rw, ctx["rw"], self.rw_ebc, B, True)
+            if getattr(ctx["rw"], "_multi_hot", False) and self._rw.mean_features:
+                # the shards ADD their partial sums into this rank's buffer; the mean divides by the bag's FULL length
+                keys = ctx["keys"]
+                for f in self._rw.mean_features:
+                    k = keys.index(f)
+                    ln = ctx["lengths"][k * B:(k + 1) * B].to(torch.float32).clamp(min=1.0)
+                    rw_cols[f] = rw_cols[f] / ln.unsqueeze(1)
+                self._whole = None            # the output is no longer the exchange buffer itself: concat below
+            cols.update(rw_cols)
         elif self._rw.features:
             part = self.rw_ebc(ctx["rw"]).values()                  # [W*B, sum D_rw]
             pooled = _ReduceScatterRows.apply(part, pg)             # [B, sum D_rw]

@@ -366,6 +366,24 @@ def block_bucketize(lengths: torch.Tensor, offsets: torch.Tensor, values: torch.
     return new_len, new_off, new_val, unb
 
 
+def kjt_gathered_range(values: torch.Tensor, capacity: int, offsets: torch.Tensor, row_lo: torch.Tensor, row_hi: torch.Tensor,
+                       world: int, num_features: int, batch: int):
+    """Row-range shard of ``world`` gathered KJTs (``tt_kjt_gathered_range``): ``values`` [world * capacity] int64 and
+    ``offsets`` [world * (F*B + 1)] int32 as all-gathered; returns ``(values [world*capacity], lengths [F*world*B],
+    offsets [F*world*B + 1])`` of the key-major KJT over the global batch that holds the ids in ``[row_lo[f], row_hi[f])``,
+    rebased to ``row_lo``.  No host sync: the live count stays in ``offsets[-1]``."""
+    N.require_cuda(values, "values")
+    dev = values.device
+    n = world * num_features * batch
+    out_v = torch.empty(world * capacity, dtype=torch.int64, device=dev)
+    out_l = torch.empty(n, dtype=torch.int32, device=dev)
+    out_o = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    ws = N.workspace(N.load().tt_kjt_gathered_range_workspace_bytes(world, num_features, batch), dev)
+    N.call("tt_kjt_gathered_range", N.ptr(values), capacity, N.ptr(offsets), N.ptr(row_lo), N.ptr(row_hi), world, num_features, batch,
+           N.ptr(out_v), N.ptr(out_l), N.ptr(out_o), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    return out_v, out_l, out_o
+
+
 def dedup_rows(ebc, kjt):
     """Unique linearised (table,row) keys of a batch, ascending, with counts and the inverse map --
     ``torch.unique(sorted=True, return_inverse=True, return_counts=True)`` over ``row_base[table] + id`` -- from
