@@ -120,9 +120,10 @@ class PeerExchange:
         self._pooled_peers_scatter = [self._peers(self._h_pooled, b * nbytes, N.TT_PEER_SCATTER_ADD) for b in range(2)]
         self._grad_peers = [self._peers(self._h_grad, b * nbytes) for b in range(2)]
         self.cur = 0                    # buffer of the step in flight (flipped at the start of every forward)
-        # row-wise shards ADD into pre-zeroed buffers: both start zeroed; afterwards a forward zeroes the OTHER buffer
-        # for the next step (the gradient barrier of the step in between orders that against the peers' adds).
-        # no_backward_since_forward: two forwards in a row (eval) have no such barrier in between -> take one.
+        # row-wise shards ADD into pre-zeroed buffers: both start zeroed; afterwards the backward of a step clears the
+        # buffer the step used (ordered against the peers' next adds by the gradient barrier).
+        # no_backward_since_forward: two forwards in a row (eval) have no backward in between -> the forward clears
+        # its buffer itself and takes one more barrier.
         self._pooled2.zero_()
         self.no_backward_since_forward = False
         dist.barrier(group=pg)
@@ -172,7 +173,10 @@ class _PeerTwLookup(torch.autograd.Function):
         b = ex.flip()
         pooled = ex.pooled(b)
         if scatter_add and ex.no_backward_since_forward:
-            ex.barrier_pooled()       # eval: the zeroing issued by the previous forward must be ordered against the adds below
+            # two forwards in a row (eval): no backward has cleared this buffer since it was last used -- clear it now
+            # and make sure every rank has done so before anybody adds
+            pooled.zero_()
+            ex.barrier_pooled()
         if ebc is not None:
             dev = values.device
             plan, _ = ebc._build_plan(kjt_keys, ex.world * ex.rows, with_state=False, out_layout=layout)
@@ -180,10 +184,9 @@ class _PeerTwLookup(torch.autograd.Function):
                    N.stream_ptr(dev))
             ctx.save_for_backward(values, offsets)
         ex.barrier_pooled()           # every owner's rows have landed here
-        if scatter_add:
-            ex.pooled(b ^ 1).zero_()  # row-wise shards ADD their rows: the next step's buffer starts from zero
         ex.no_backward_since_forward = True
         ctx.ex, ctx.ebc, ctx.layout, ctx.kjt_keys, ctx.n_anchors, ctx.buf = ex, ebc, layout, kjt_keys, len(anchors), b
+        ctx.scatter_add = scatter_add
         ctx.pre_backward = pre_backward
         out = pooled.view(ex.rows, ex.cols)
         return out
@@ -197,6 +200,12 @@ class _PeerTwLookup(torch.autograd.Function):
         gbuf = ex.grad(b)
         if grad.data_ptr() != gbuf.data_ptr():
             gbuf.copy_(grad)          # the producer did not write in place (see FusedTowersTC grad_dst)
+        if ctx.scatter_add:
+            # Row-wise shards ADD their rows, so the buffer must be zero before its next use.  This node runs after every
+            # consumer of the pooled rows (it is the last one of the towers' backward), and the peers' next adds come after
+            # the gradient barrier below, which this rank reaches after the clear.  Clearing HERE -- not "the other buffer in
+            # the next forward" -- is what keeps a captured step correct: a CUDA graph replays with ONE fixed buffer index.
+            ex.pooled(b).zero_()
         if ctx.pre_backward is not None:
             ctx.pre_backward()
         ex.barrier_grad()             # every rank's gradient rows are staged
