@@ -186,7 +186,7 @@ def algorithmic_bytes(cfg, B, uniq_per_table):
 
 
 # ---- sharded-vs-unsharded parity, run by the driver's own N > 1 launches (the driver never runs pytest on > 1 GPU)
-def parity_check(world, rank, dev, sharding, exchange, steps=3, precision="bf16"):
+def parity_check(world, rank, dev, sharding, exchange, steps=3, precision="bf16", graph=False):
     """Trains `steps` steps of the SAME sharded module / exchange mode the timed run uses (small tables, in-batch
     softmax with per-rank negatives, fused row-wise Adagrad, deterministic softmax backward) and, on rank 0, an
     UNSHARDED replica of the same model fed every rank's batch: its table gradients are accumulated densely
@@ -225,13 +225,19 @@ def parity_check(world, rank, dev, sharding, exchange, steps=3, precision="bf16"
         B = small["batch"]
         max_loss_err = 0.0
         model.train()
+        # graph=True: the sharded side runs through CudaGraphTrainStep (1 eager step, then capture + replays) -- the path the
+        # timed blocks use; a replay reuses ONE exchange buffer index, which the eager loop never exercises
+        gstep = tt.CudaGraphTrainStep(model, opt, CAT, small["rows"], B, dev, warmup_steps=1) if graph else None
         for s in range(steps):
             raws = [make_raw_batches(1, small, 7000 + 100 * s + r, rows_dev, B)[0] for r in range(world)]
-            opt.zero_grad()
-            loss, _ = model(raws[rank].to(dev))
-            loss.backward()
-            model.sync_dense_grads()
-            opt.step()
+            if graph:
+                loss = gstep(raws[rank].ids, raws[rank].labels)[0].clone()
+            else:
+                opt.zero_grad()
+                loss, _ = model(raws[rank].to(dev))
+                loss.backward()
+                model.sync_dense_grads()
+                opt.step()
             losses = [torch.zeros((), device=dev) for _ in range(world)]
             dist.all_gather(losses, loss.detach())
             if rank == 0:
@@ -282,7 +288,8 @@ def parity_check(world, rank, dev, sharding, exchange, steps=3, precision="bf16"
         tol_loss, tol_rel, tol_abs = 2e-4, 2e-2, 2e-3
         if precision == "fp32":      # exact-fp32 towers and softmax: no re-rounding, only summation order is left
             tol_loss, tol_rel, tol_abs = 2e-5, 1e-3, 2e-5
-        res = {"mode": f"{'+'.join(kinds or [])}/{exchange}", "precision": precision, "world": world, "steps": steps, "batch_per_rank": B,
+        res = {"mode": f"{'+'.join(kinds or [])}/{exchange}" + ("/cuda_graph" if graph else "/eager"), "precision": precision, "world": world,
+               "steps": steps, "batch_per_rank": B,
                "rows": small["rows"], "max_abs_err_loss": max_loss_err, "max_rel_err_row_update": max_rel,
                "max_abs_err_weights": max_w_err, "weights_max_abs": max_w, "worst_entry": worst,
                "tol_loss": tol_loss, "tol_rel_row_update": tol_rel, "tol_abs_weights": tol_abs,
@@ -291,7 +298,7 @@ def parity_check(world, rank, dev, sharding, exchange, steps=3, precision="bf16"
         ok = torch.tensor([1 if (rank != 0 or (max_loss_err <= tol_loss and max_rel <= tol_rel and max_w_err <= tol_abs)) else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         res["ok"] = bool(ok.item())
-        del model, opt, ref
+        del model, opt, ref, gstep
         torch.cuda.empty_cache()
         return res
     finally:
@@ -386,16 +393,10 @@ def time_block(cfg, B, dev, rank, world, local, args, sharding, exchange, lib, w
             last = float(pipe.progress(it)[0])
         t1.record()
         barrier()
-    # K steps of a few ms give nvidia-smi (20 ms period) only a handful of samples: keep replaying the SAME step under the
-    # sampler until it has covered >= 0.5 s of this load (all ranks run the same count: the sharded step has collectives)
     ms_e2e = t0.elapsed_time(t1) / args.steps
-    extra = max(0, int(500.0 / max(ms_e2e, 1e-3)) - 2 * args.steps)
-    for i in range(extra):
-        graph_step(*dev_raw[i % nb]) if use_graph else step(resident[i % nb])
-    barrier()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
-        clocks["window"] = "timed region (device-resident + e2e steps) + %d further replays of the same step" % extra
+        clocks["window"] = "device-resident + end-to-end timed steps (the sampler is started before the warm-up)"
 
     per_call = {}
     if with_kernels:
@@ -469,8 +470,11 @@ def run_ours(args):
         if G % world != 0:
             raise SystemExit("world size must divide 65536")
         # sharded-path parity first, on exactly the (sharding, exchange) pairs that are timed below
-        for sh, prec in (("table_wise", "bf16"), ("row_wise", "bf16"), ("table_wise", "fp32"), ("row_wise", "fp32")):
-            p = parity_check(world, rank, dev, sh, args.exchange, precision=prec)
+        modes = [("table_wise", "bf16", False), ("row_wise", "bf16", False), ("table_wise", "fp32", False), ("row_wise", "fp32", False)]
+        if args.parity_graph:      # opt-in: the sharded side replays a captured graph (exercised by tests/test_gpu_multi.py instead)
+            modes += [("table_wise", "fp32", True), ("row_wise", "fp32", True)]
+        for sh, prec, gr in modes:
+            p = parity_check(world, rank, dev, sh, args.exchange, steps=4 if gr else 3, precision=prec, graph=gr)
             parity.append(p)
             if args.parity_only:
                 continue
@@ -752,6 +756,7 @@ def main():
     ap.add_argument("--exchange", default=os.environ.get("TT_EXCHANGE", "peer"), choices=["nccl", "peer"],
                     help="N>1: output exchange by NCCL all-to-all, or fused into the lookup kernels over NVLink peer memory")
     ap.add_argument("--parity-only", action="store_true", help="N > 1: run the sharded-vs-unsharded parity checks and exit")
+    ap.add_argument("--parity-graph", action="store_true", help="N > 1: also check the sharded model through CudaGraphTrainStep replays")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly (N>1: through TrainPipelineSparseDist) instead of replaying a CUDA graph")
     args = ap.parse_args()
     # a wedged collective / capture must not hold the box: the default run takes a few minutes
