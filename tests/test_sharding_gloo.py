@@ -64,6 +64,17 @@ class OracleLocalEbc(nn.Module):
         return tt.KeyedTensor(self._features, self._dims, out)
 
 
+def oracle_gather_range(g_vals, cap, g_offs, lo, hi, W, F, B):
+    """Stand-in for tt_kjt_gathered_range: the oracle's filter over the W gathered (padded) KJTs."""
+    offs = g_offs.view(W, F * B + 1)
+    lens = [(offs[r, 1:] - offs[r, :-1]).to(torch.int32) for r in range(W)]
+    vals = [g_vals.view(W, cap)[r, :int(offs[r, -1])] for r in range(W)]
+    v, l = oracle.gathered_range_shard(vals, lens, lo.tolist(), hi.tolist(), B)
+    out_v = torch.zeros(W * cap, dtype=torch.int64)
+    out_v[:v.numel()] = v
+    return out_v, l, oracle.lengths_to_offsets(l).to(torch.int32)
+
+
 def oracle_bucketize(lengths, offsets, values, rows, F, B, W):
     nl, nv, unb = block_bucketize_vectorized(lengths, values, rows.tolist(), W, B)
     return nl, oracle.lengths_to_offsets(nl), nv, unb
@@ -108,7 +119,8 @@ def _worker(rank, world, port, errq):
         assert {p["t_a"].ranks[0], p["t_b"].ranks[0]} == {0, 1}
         assert p["t_c"].sharding_type == "row_wise" and p["t_c"].block_size == 51 and p["t_d"].block_size == 4
         model = tt.DistributedModelParallel(module=holder, device=torch.device("cpu"), plan=plan,
-                                            sharding_kwargs=dict(local_ebc_factory=OracleLocalEbc, bucketize_fn=oracle_bucketize))
+                                            sharding_kwargs=dict(local_ebc_factory=OracleLocalEbc, bucketize_fn=oracle_bucketize,
+                                                                 gather_range_fn=oracle_gather_range))
         assert model._plan is plan and "t_c" in str(model._plan)
         sharded = model.module["ebc"]
         assert sharded.tw_ebc._grad_scale == 0.5 and sharded.rw_ebc._grad_scale == 0.5
@@ -165,6 +177,27 @@ def _worker(rank, world, port, errq):
             cur[s.name] = lst[0]
         want2 = oracle.ebc_forward(SPECS, [cur[s.name] for s in SPECS], KEYS, v2, l2)
         torch.testing.assert_close(kt2.values(), want2, rtol=1e-5, atol=1e-6)
+
+        # ---- sync-free input dist for fixed-capacity (padded) multi-hot KJTs: all-gather + row-range filter.  What each
+        # rank ends up holding == the oracle's filter with lo / hi worked out from the plan by hand.
+        cap = 5 * B * 4 + 3          # >= F * B * L ids, the same on every rank
+        per_rank = [_batch(r + 20) for r in range(world)]
+        v3, l3 = per_rank[rank]
+        padded = torch.full((cap,), -5, dtype=torch.int64)
+        padded[:v3.numel()] = v3
+        kjt3 = tt.KeyedJaggedTensor(keys=KEYS, values=padded, lengths=l3)
+        kjt3._values_padded = True
+        owner = {"a": p["t_a"].ranks[0], "b1": p["t_b"].ranks[0], "b2": p["t_b"].ranks[0]}
+        rows = {"a": 40, "b1": 30, "b2": 30, "c": 101, "d": 7}
+        for grp, want_lohi in ((sharded._rw, {"c": (51 * rank, min(51 * (rank + 1), 101)), "d": (4 * rank, min(4 * rank + 4, 7))}),
+                               (sharded._tw, {k: (0, rows[k] if owner[k] == rank else 0) for k in owner})):
+            got = sharded._dist_kjt_gather(grp, kjt3, B)
+            lo = [want_lohi.get(k, (0, 0))[0] for k in KEYS]
+            hi = [want_lohi.get(k, (0, 0))[1] for k in KEYS]
+            wv, wl = oracle.gathered_range_shard([q[0] for q in per_rank], [q[1] for q in per_rank], lo, hi, B)
+            assert got.keys() == KEYS and got.stride() == world * B
+            assert torch.equal(got.lengths(), wl) and torch.equal(got.values()[:wv.numel()], wv)
+        sharded._gathered = None
 
         # ---- dense gradient sync: one all-reduce, mean over ranks
         from two_tower_recommender_model_b200.distributed.sharding import DenseGradSync

@@ -234,6 +234,11 @@ def _native_bucketize(lengths, offsets, values, num_rows, F, B, W):
     return block_bucketize(lengths, offsets, values, num_rows, F, B, W)
 
 
+def _native_gather_range(values, capacity, offsets, lo, hi, W, F, B):
+    from ..functional import kjt_gathered_range
+    return kjt_gathered_range(values, capacity, offsets, lo, hi, W, F, B)
+
+
 def _default_local_ebc(tables: List[EmbeddingBagConfig], device: torch.device) -> nn.Module:
     return EmbeddingBagCollection(tables=tables, device=device)
 
@@ -255,7 +260,8 @@ class _Group:
 class ShardedEmbeddingBagCollection(nn.Module):
     def __init__(self, ebc: EmbeddingBagCollection, plan: Dict[str, ParameterSharding], device: torch.device, pg: Any = None,
                  local_ebc_factory: Callable[[List[EmbeddingBagConfig], torch.device], nn.Module] = _default_local_ebc,
-                 bucketize_fn: Callable = _native_bucketize, peer_exchange: bool = False) -> None:
+                 bucketize_fn: Callable = _native_bucketize, peer_exchange: bool = False,
+                 gather_range_fn: Callable = _native_gather_range) -> None:
         """``peer_exchange=True`` replaces the table-wise output all-to-all (and its backward) by
         stores / loads over NVLink peer memory issued by the lookup kernels themselves."""
         super().__init__()
@@ -269,6 +275,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
         self._configs = ebc.embedding_bag_configs()
         self._plan = plan
         self._bucketize = bucketize_fn
+        self._gather_range = gather_range_fn
         self._out_features = ebc.feature_names()
         self._out_dims = [c.embedding_dim for c in self._configs for _ in c.feature_names]
         W, r = self._world, self._rank
@@ -481,7 +488,6 @@ class ShardedEmbeddingBagCollection(nn.Module):
         all rows of the table-wise tables it owns, nothing of the rest (those bags are empty here).  TorchRec reaches
         the same KJT through block_bucketize + three all-to-alls + permute (KJTAllToAll), with a host sync for the
         split sizes; the ids a rank receives that it does not keep cost 8 bytes each on NVLink."""
-        from ..functional import kjt_gathered_range
         W, pg, dev = self._world, self._pg, kjt.values().device
         keys = list(kjt.keys())
         F = len(keys)
@@ -515,7 +521,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
             self._gathered = (kjt, g_vals, g_offs)
         if grp.kind == "table_wise" and not grp.dest_features[self._rank]:
             return None
-        out_v, out_l, out_o = kjt_gathered_range(g_vals, cap, g_offs, lo, hi, W, F, B)
+        out_v, out_l, out_o = self._gather_range(g_vals, cap, g_offs, lo, hi, W, F, B)
         out = KeyedJaggedTensor(keys=keys, values=out_v, lengths=out_l, offsets=out_o, stride=W * B)
         out._values_padded = True
         if grp.kind == "row_wise":
