@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TT_ABI_VERSION 2
+#define TT_ABI_VERSION 3
 #define TT_MAX_FEATURES 32
 
 typedef enum {

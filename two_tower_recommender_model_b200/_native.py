@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 TT_MAX_FEATURES = 32
-TT_ABI_VERSION = 2
+TT_ABI_VERSION = 3
 
 POOL_SUM, POOL_MEAN = 0, 1
 OPT_DENSE_GRAD, OPT_ROWWISE_ADAGRAD, OPT_ROWWISE_ADAM, OPT_SGD = 0, 1, 2, 3
