@@ -53,6 +53,44 @@ def test_block_bucketize_properties(j, W):
                 assert torch.equal(local + w * block, v[src])
 
 
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 4), st.integers(1, 3), st.integers(1, 6), st.integers(0, 2 ** 31 - 1))
+def test_gathered_range_shard_properties(W, F, B, seed):
+    """The sync-free input dist's filter (oracle.gathered_range_shard): over the W shards of a block partition every id
+    of every rank's batch is kept exactly once, stays in its (feature, rank, sample) bag in source order, and
+    local + lo gives it back; shard w equals bucket w of block_bucketize on the concatenated batch."""
+    g = torch.Generator().manual_seed(seed)
+    rows = [int(torch.randint(1, 40, (1,), generator=g)) for _ in range(F)]
+    per_rank = []
+    for _ in range(W):
+        lens = torch.randint(0, 4, (F * B,), generator=g).to(torch.int32)
+        vals = torch.cat([torch.randint(0, rows[f], (int(lens[f * B:(f + 1) * B].sum()),), generator=g) for f in range(F)]) \
+            if int(lens.sum()) else torch.zeros(0, dtype=torch.int64)
+        per_rank.append((vals, lens))
+    total = sum(int(v.numel()) for v, _ in per_rank)
+    block = [-(-r // W) for r in rows]
+    kept = 0
+    cat_len = torch.cat([per_rank[r][1][f * B:(f + 1) * B] for f in range(F) for r in range(W)])
+    offs = [oracle.lengths_to_offsets(l).tolist() for _, l in per_rank]
+    cat_val = torch.cat([per_rank[r][0][offs[r][f * B]:offs[r][(f + 1) * B]] for f in range(F) for r in range(W)])
+    nl, nv, _ = oracle.block_bucketize_sparse_features(cat_len, cat_val, rows, W, W * B)
+    noff = oracle.lengths_to_offsets(nl).tolist()
+    n = F * W * B
+    for w in range(W):
+        lo = [w * b for b in block]
+        hi = [min((w + 1) * b, r) for b, r in zip(block, rows)]
+        v, l = oracle.gathered_range_shard([p[0] for p in per_rank], [p[1] for p in per_rank], lo, hi, B)
+        assert int(l.sum()) == v.numel()
+        kept += int(v.numel())
+        assert (l <= cat_len).all()                                  # a bag only ever loses ids
+        o = oracle.lengths_to_offsets(l).tolist()
+        for f in range(F):
+            seg = v[o[f * W * B]:o[(f + 1) * W * B]]
+            assert ((seg >= 0) & (seg < max(hi[f] - lo[f], 0) + (1 if seg.numel() == 0 else 0))).all()
+        assert l.tolist() == nl[w * n:(w + 1) * n].tolist() and v.tolist() == nv[noff[w * n]:noff[(w + 1) * n]].tolist()
+    assert kept == total
+
+
 @settings(max_examples=60, deadline=None)
 @given(jagged(), st.data())
 def test_permute_2d_properties(j, data):
