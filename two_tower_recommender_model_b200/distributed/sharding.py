@@ -122,10 +122,13 @@ class PeerExchange:
         self.cur = 0                    # buffer of the step in flight (flipped at the start of every forward)
         # row-wise shards ADD into pre-zeroed buffers: both start zeroed; afterwards the backward of a step clears the
         # buffer the step used (ordered against the peers' next adds by the gradient barrier).
-        # no_backward_since_forward: two forwards in a row (eval) have no backward in between -> the forward clears
-        # its buffer itself and takes one more barrier.
+        # dirty[b]: buffer b holds sums that no backward has cleared (a forward without a backward: eval, or training
+        # resumed after eval) -> the next forward that uses it clears it itself and takes one more barrier.  Tracked
+        # PER BUFFER: after train -> eval -> train the step that follows the first training step lands on the buffer the
+        # last-but-one eval forward left behind.  Every rank runs the same forward / backward sequence, so the flags (and
+        # with them the number of barriers) agree across ranks.
         self._pooled2.zero_()
-        self.no_backward_since_forward = False
+        self.dirty = [False, False]
         dist.barrier(group=pg)
 
     def _peers(self, handle, byte_offset: int = 0, flags: int = 0):
@@ -152,6 +155,17 @@ class PeerExchange:
     def grad_peers(self, b: int):
         return self._grad_peers[b]
 
+    def clean(self) -> None:
+        """Clears every scatter-add buffer a backward-less forward left dirty (collective: one barrier when anything
+        was dirty).  ``CudaGraphTrainStep`` calls it before a replay: the captured step assumes a clean buffer."""
+        if not any(self.dirty):
+            return
+        for b in (0, 1):
+            if self.dirty[b]:
+                self.pooled(b).zero_()
+                self.dirty[b] = False
+        self.barrier_pooled()
+
     def barrier_pooled(self) -> None:
         self._h_pooled.barrier(channel=0)
 
@@ -172,9 +186,9 @@ class _PeerTwLookup(torch.autograd.Function):
         from .. import _native as N
         b = ex.flip()
         pooled = ex.pooled(b)
-        if scatter_add and ex.no_backward_since_forward:
-            # two forwards in a row (eval): no backward has cleared this buffer since it was last used -- clear it now
-            # and make sure every rank has done so before anybody adds
+        if scatter_add and ex.dirty[b]:
+            # no backward has cleared this buffer since a forward last added into it (eval forwards, or the training
+            # steps right after them) -- clear it now and make sure every rank has done so before anybody adds
             pooled.zero_()
             ex.barrier_pooled()
         if ebc is not None:
@@ -184,7 +198,8 @@ class _PeerTwLookup(torch.autograd.Function):
                    N.stream_ptr(dev))
             ctx.save_for_backward(values, offsets)
         ex.barrier_pooled()           # every owner's rows have landed here
-        ex.no_backward_since_forward = True
+        if scatter_add:
+            ex.dirty[b] = True
         ctx.ex, ctx.ebc, ctx.layout, ctx.kjt_keys, ctx.n_anchors, ctx.buf = ex, ebc, layout, kjt_keys, len(anchors), b
         ctx.scatter_add = scatter_add
         ctx.pre_backward = pre_backward
@@ -196,7 +211,6 @@ class _PeerTwLookup(torch.autograd.Function):
         from ctypes import byref
         from .. import _native as N
         ex, ebc, b = ctx.ex, ctx.ebc, ctx.buf
-        ex.no_backward_since_forward = False
         gbuf = ex.grad(b)
         if grad.data_ptr() != gbuf.data_ptr():
             gbuf.copy_(grad)          # the producer did not write in place (see FusedTowersTC grad_dst)
@@ -206,6 +220,7 @@ class _PeerTwLookup(torch.autograd.Function):
             # the gradient barrier below, which this rank reaches after the clear.  Clearing HERE -- not "the other buffer in
             # the next forward" -- is what keeps a captured step correct: a CUDA graph replays with ONE fixed buffer index.
             ex.pooled(b).zero_()
+            ex.dirty[b] = False
         if ctx.pre_backward is not None:
             ctx.pre_backward()
         ex.barrier_grad()             # every rank's gradient rows are staged

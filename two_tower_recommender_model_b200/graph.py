@@ -49,6 +49,16 @@ class CudaGraphTrainStep:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._out = None
         self._stream = torch.cuda.Stream(device=self._dev)
+        # sharded modules whose row-wise peer exchange adds into pre-cleared buffers (see PeerExchange.clean)
+        self._sharded = [m for m in model.modules() if isinstance(getattr(m, "_peer", None), dict)]
+
+    def _clean_exchanges(self) -> None:
+        """A captured step assumes the scatter-add buffer it was captured with is clear; eager forwards without a
+        backward in between replays (an evaluation pass) leave theirs dirty -- clear those first.  Every rank runs
+        the same sequence of calls, so either all ranks take the barrier inside or none does."""
+        for m in self._sharded:
+            for ex in m._peer.values():
+                ex.clean()
 
     @staticmethod
     def _check_capturable(optimizer) -> None:
@@ -107,6 +117,7 @@ class CudaGraphTrainStep:
                 out = self._step()
             cur.wait_stream(self._stream)
             return out
+        self._clean_exchanges()
         if self._graph is None:
             torch.cuda.synchronize(self._dev)
             g = torch.cuda.CUDAGraph()
