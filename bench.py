@@ -40,6 +40,8 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 CAT = ["user_id", "product_id"]
+# rank 0's line once the headline block is measured + the block in flight: what the watchdog prints if a later block wedges
+_PARTIAL = {"line": None, "stage": "headline"}
 CFG2 = dict(rows=[10_000_000, 10_000_000], dim=64, layers=[128, 64], batch=65536, loss="in_batch_softmax",
             sparse_lr=0.01, dense_lr=0.001)
 CFG1 = dict(rows=[200_000, 50_000], dim=64, layers=[128, 64], batch=1024, loss="bce", sparse_lr=0.01, dense_lr=0.001)
@@ -460,7 +462,6 @@ def run_ours(args):
     G = cfg["batch"]                     # configs[1]: batch 65536
 
     parity = []
-    extra = {}
     if world == 1:
         main = time_block(cfg, G, dev, rank, world, local, args, None, None, lib, with_kernels=True)
         workload = ("BASELINE configs[1] on 1 GPU: 2 tables 10M x 64 fp32, batch 65536, MLP 64-128-64, in-batch softmax, "
@@ -488,29 +489,65 @@ def run_ours(args):
             leave(world, 0 if all(p["ok"] for p in parity) else 4)
             return
         main = time_block(cfg, G // world, dev, rank, world, local, args, "table_wise", args.exchange, lib, with_kernels=True)
-        srw = time_block(cfg, G // world, dev, rank, world, local, args, "row_wise", args.exchange, lib, with_kernels=False)
-        weak = time_block(cfg, G, dev, rank, world, local, args, None, args.exchange, lib, with_kernels=False)
-        gcfg = dict(cfg, negatives="global")
-        sgl = time_block(gcfg, G // world, dev, rank, world, local, args, "table_wise", args.exchange, lib, with_kernels=False)
-        extra["strong_global_negatives"] = {
-            "value": round(G / (sgl["ms_value"] * 1e-3), 1), "ms_per_step": round(sgl["ms_value"], 4), "e2e": round(G / (sgl["ms_e2e"] * 1e-3), 1),
-            "global_batch": G, "per_rank_batch": G // world, "sharding": sgl["sharding"], "last_loss": sgl["last_loss"],
-            "note": "every rank's candidates are negatives for every rank's queries (all-gather + reduce-scatter): the SAME loss "
-                    "function as the 1-GPU run at global batch 65536; per-rank logits flops = 1/N of the 1-GPU step"}
-        extra["retrieval"] = retrieval_probe_sharded(dev, rank, world)
-        extra["strong_row_wise"] = {"value": round(G / (srw["ms_value"] * 1e-3), 1), "ms_per_step": round(srw["ms_value"], 4),
-                                    "e2e": round(G / (srw["ms_e2e"] * 1e-3), 1), "global_batch": G, "per_rank_batch": G // world,
-                                    "sharding": srw["sharding"]}
-        extra["weak"] = {"value": round(world * G / (weak["ms_value"] * 1e-3), 1), "ms_per_step": round(weak["ms_value"], 4),
-                         "e2e": round(world * G / (weak["ms_e2e"] * 1e-3), 1), "global_batch": G * world, "per_rank_batch": G,
-                         "sharding": weak["sharding"], "note": "per-rank batch fixed at 65536 (round 1's headline)"}
         workload = ("BASELINE configs[1] on %d GPUs as stated: 2 tables 10M x 64 fp32 table-wise sharded, GLOBAL batch 65536 "
                     "(per-rank %d), MLP 64-128-64, in-batch softmax (per-rank negatives), fused row-wise Adagrad, Adam" % (world, G // world))
         scaling = "strong"
+    line = None
+    if rank == 0:
+        line = headline(args, cfg, main, pk, world, G, workload, scaling, parity)
+        _PARTIAL["line"] = line          # from here on a wedged side block costs that block, not the headline (see watchdog)
+    if world > 1:
+        side_blocks(args, cfg, dev, rank, world, local, lib, G, line)
     if rank != 0:
         leave(world)
         return
+    finish(args, cfg, dev, world, line)
 
+
+def side_blocks(args, cfg, dev, rank, world, local, lib, G, line):
+    """N > 1: the blocks timed BESIDE the headline (every rank runs them, rank 0 records them).  A block that raises on
+    every rank is recorded as an error and the run goes on; one that wedges is cut by the watchdog, which still prints
+    the headline line with an `incomplete` entry."""
+    def record(name, fn):
+        _PARTIAL["stage"] = name
+        try:
+            out = fn()
+        except Exception as e:      # noqa: BLE001 -- recorded, not hidden: the line says which block failed and why
+            out = {"error": f"{type(e).__name__}: {e}"[:400]}
+            sys.stderr.write(f"bench.py: block {name} failed on rank {rank}: {out['error']}\n")
+        if line is not None:
+            line[name] = out
+
+    def strong_row_wise():
+        srw = time_block(cfg, G // world, dev, rank, world, local, args, "row_wise", args.exchange, lib, with_kernels=False)
+        return {"value": round(G / (srw["ms_value"] * 1e-3), 1), "ms_per_step": round(srw["ms_value"], 4),
+                "e2e": round(G / (srw["ms_e2e"] * 1e-3), 1), "global_batch": G, "per_rank_batch": G // world,
+                "sharding": srw["sharding"], "last_loss": srw["last_loss"]}
+
+    def weak():
+        wk = time_block(cfg, G, dev, rank, world, local, args, None, args.exchange, lib, with_kernels=False)
+        return {"value": round(world * G / (wk["ms_value"] * 1e-3), 1), "ms_per_step": round(wk["ms_value"], 4),
+                "e2e": round(world * G / (wk["ms_e2e"] * 1e-3), 1), "global_batch": G * world, "per_rank_batch": G,
+                "sharding": wk["sharding"], "last_loss": wk["last_loss"], "note": "per-rank batch fixed at 65536 (round 1's headline)"}
+
+    def strong_global_negatives():
+        sgl = time_block(dict(cfg, negatives="global"), G // world, dev, rank, world, local, args, "table_wise", args.exchange, lib,
+                         with_kernels=False)
+        return {"value": round(G / (sgl["ms_value"] * 1e-3), 1), "ms_per_step": round(sgl["ms_value"], 4),
+                "e2e": round(G / (sgl["ms_e2e"] * 1e-3), 1), "global_batch": G, "per_rank_batch": G // world,
+                "sharding": sgl["sharding"], "last_loss": sgl["last_loss"],
+                "note": "every rank's candidates are negatives for every rank's queries (all-gather + reduce-scatter): the SAME loss "
+                        "function as the 1-GPU run at global batch 65536; per-rank logits flops = 1/N of the 1-GPU step"}
+
+    record("strong_row_wise", strong_row_wise)
+    record("weak", weak)
+    record("strong_global_negatives", strong_global_negatives)
+    record("retrieval", lambda: retrieval_probe_sharded(dev, rank, world))
+    _PARTIAL["stage"] = "done"
+
+
+def headline(args, cfg, main, pk, world, G, workload, scaling, parity):
+    """The JSON line of the headline block (configs[1]); the other blocks are added to it afterwards."""
     B = main["batch"]
     per_call = main["per_call"]
     fwd_bytes, bwd_bytes = algorithmic_bytes(cfg, B, main["uniq"])
@@ -559,14 +596,24 @@ def run_ours(args):
     }
     if parity:
         line["parity"] = parity
-    line.update(extra)
     if main["ebc_only_ms"]:
         ms = main["ebc_only_ms"]
         line["ebc_lookup"] = {"gbs": round(fwd_bytes / (ms * 1e-3) / 1e9, 1), "us": round(ms * 1e3, 2), "peak_gbs": pk["hbm"],
                               "frac": round(fwd_bytes / (ms * 1e-3) / 1e9 / pk["hbm"], 4), "bytes": int(fwd_bytes),
                               "how": "40 back-to-back tt_ebc_forward launches over 4 rotating batches, CUDA events around the loop"}
         line["ebc_lookup_gbs"] = line["ebc_lookup"]["gbs"]
+    return line
+
+
+def finish(args, cfg, dev, world, line):
+    """Rank 0: the single-GPU side blocks (retrieval probes, configs[2] / configs[3], CPU baselines), then the line."""
+    if world == 1 and not args.no_cpu_baseline:
+        # first: `cpu_baseline` is part of the bench contract, the blocks after it are extras
+        _PARTIAL["stage"] = "cpu_baseline"
+        line["cpu_baseline"] = cpu_baseline(cfg, steps=1, warmup=1)
+        line["cpu_baseline_cfg1"] = cpu_baseline_cfg1()
     if world == 1:
+        _PARTIAL["stage"] = "retrieval"
         line["retrieval"] = retrieval_probe(dev)
         line["retrieval_large"] = retrieval_probe(dev, n_items=10_000_000, n_queries=131072)
     if world == 1 and not args.no_other_configs:
@@ -574,11 +621,15 @@ def run_ours(args):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import run_configs
         torch.cuda.empty_cache()
-        line["cfg3"] = run_configs.config3()
-        line["cfg4"] = run_configs.config4()
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(cfg, steps=1, warmup=1)
-        line["cpu_baseline_cfg1"] = cpu_baseline_cfg1()
+        for name, fn in (("cfg3", run_configs.config3), ("cfg4", run_configs.config4)):
+            _PARTIAL["stage"] = name
+            try:
+                line[name] = fn()
+            except Exception as e:      # noqa: BLE001 -- recorded in the line; configs[1] stays the value
+                line[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
+                torch.cuda.empty_cache()
+    _PARTIAL["stage"] = "done"
+    _PARTIAL["line"] = None
     print(json.dumps(line))
     leave(world)
 
@@ -745,6 +796,34 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def watchdog():
+    """The run overran its limit (a wedged collective or capture).  If the headline block had been measured, rank 0
+    still prints its line -- with an `incomplete` entry naming the block that was cut -- and the ranks exit 0; before
+    that point there is nothing to report and the exit code is 3.  The other ranks wait 15 s longer than rank 0 and
+    learn the outcome from a marker file."""
+    rank = int(os.environ.get("RANK", 0))
+    marker = os.path.join("/tmp", "tt_bench_partial_%s" % os.environ.get("MASTER_PORT", "0"))
+    sys.stderr.write("bench.py: watchdog expired on rank %d during block '%s'\n" % (rank, _PARTIAL["stage"]))
+    rc = 3
+    if rank == 0:
+        line = _PARTIAL["line"]
+        if line is not None:
+            line = dict(line)
+            line["incomplete"] = {"cut_block": _PARTIAL["stage"], "reason": "watchdog: the block did not finish within the run's limit; "
+                                  "the headline block (value / e2e / roofline / parity) had completed before it started"}
+            try:
+                print(json.dumps(line))
+                open(marker, "w").close()
+                rc = 0
+            except Exception:       # noqa: BLE001 -- a block was mutating the dict: nothing printable
+                rc = 3
+    elif os.path.exists(marker) and time.time() - os.path.getmtime(marker) < 120:
+        rc = 0
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(rc)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -759,8 +838,8 @@ def main():
     ap.add_argument("--parity-graph", action="store_true", help="N > 1: also check the sharded model through CudaGraphTrainStep replays")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly (N>1: through TrainPipelineSparseDist) instead of replaying a CUDA graph")
     args = ap.parse_args()
-    # a wedged collective / capture must not hold the box: the default run takes a few minutes
-    wd = threading.Timer(float(os.environ.get("TT_BENCH_WATCHDOG_S", "900")), lambda: (sys.stderr.write("bench.py: watchdog expired\n"), os._exit(3)))
+    # a wedged collective / capture must not hold the box: the default run takes about a minute
+    wd = threading.Timer(float(os.environ.get("TT_BENCH_WATCHDOG_S", "600")) + (0 if int(os.environ.get("RANK", 0)) == 0 else 15), watchdog)
     wd.daemon = True
     wd.start()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -1,0 +1,121 @@
+"""bench.py's host logic, on CPU: the JSON line carries every key the bench contract names, the side blocks of an
+N > 1 run are recorded one by one (a failing block becomes an `error` entry, the others stay), and a run cut by the
+watchdog still prints the headline line once that block is measured.  No kernel runs here: `time_block` and the
+retrieval probe are replaced by fakes with the shape of their real results."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def _args(**kw):
+    d = dict(gpus=1, steps=10, warmup=3, impl="ours", no_cpu_baseline=True, no_other_configs=True, exchange="peer",
+             parity_only=False, parity_graph=False, no_graph=False)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def _block(ms=2.8, B=65536, sharding=None):
+    return {"ms_value": ms, "ms_e2e": ms * 1.02, "launches": 470, "clocks": {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 9},
+            "per_call": {"tt_inbatch_softmax_forward_bf16": {"ms": 0.9, "calls": 5}, "tt_inbatch_softmax_backward_bf16": {"ms": 1.3, "calls": 5},
+                         "tt_ebc_forward": {"ms": 0.03, "calls": 5}, "tt_ebc_backward_fused": {"ms": 0.08, "calls": 5}},
+            "ebc_only_ms": 0.0125, "uniq": [65300, 65310], "last_loss": 11.09, "e2e_api": "CudaGraphTrainStep", "h2d": 2 * B * 8 + B * 4,
+            "sharding": sharding, "cuda_graph": True, "batch": B}
+
+
+def test_headline_line_has_every_contract_key():
+    line = bench.headline(_args(), dict(bench.CFG2), _block(), bench.peaks(), 1, 65536, "BASELINE configs[1] on 1 GPU", "strong", [])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert k in line, k
+    assert line["metric"] == "two-tower train samples/s" and line["unit"] == "samples/s" and line["higher_is_better"] is True
+    assert line["vs_baseline"] is None                 # BASELINE.md publishes no number for this metric
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert abs(line["value"] - 65536 / 2.8e-3) < 1.0 and line["ms_per_step"] == 2.8
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in line["e2e"], k
+    assert line["e2e"]["h2d_bytes_per_step"] == 2 * 65536 * 8 + 65536 * 4 and line["e2e"]["value"] < line["value"]
+    r = line["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s"
+    assert abs(r["achieved"] - 6.0 * 65536 ** 2 * 64 / 2.2e-3 / 1e12) < 0.1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert line["gpu_launches"] > 0
+    assert line["ebc_lookup"]["frac"] == pytest.approx(line["ebc_lookup"]["gbs"] / line["ebc_lookup"]["peak_gbs"], abs=1e-3)
+    json.dumps(line)
+
+
+def test_side_blocks_are_recorded_one_by_one_and_a_failing_block_does_not_take_the_others(monkeypatch):
+    calls = []
+
+    def fake_time_block(cfg, B, dev, rank, world, local, args, sharding, exchange, lib, with_kernels):
+        calls.append((B, sharding, cfg.get("negatives", "local")))
+        if sharding == "row_wise":
+            raise RuntimeError("peer buffer rendezvous failed")
+        return _block(ms=0.5, B=B, sharding=[sharding or "table_wise"])
+
+    monkeypatch.setattr(bench, "time_block", fake_time_block)
+    monkeypatch.setattr(bench, "retrieval_probe_sharded", lambda dev, rank, world: {"queries_per_s_total": 1.0})
+    line = {"value": 1.0}
+    bench.side_blocks(_args(gpus=4), dict(bench.CFG2), None, 0, 4, 0, None, 65536, line)
+    assert calls == [(16384, "row_wise", "local"), (65536, None, "local"), (16384, "table_wise", "global")]
+    assert "error" in line["strong_row_wise"] and "rendezvous" in line["strong_row_wise"]["error"]
+    assert line["weak"]["value"] == pytest.approx(4 * 65536 / 0.5e-3, rel=1e-6) and line["weak"]["global_batch"] == 4 * 65536
+    assert line["strong_global_negatives"]["value"] == pytest.approx(65536 / 0.5e-3, rel=1e-6)
+    assert line["retrieval"] == {"queries_per_s_total": 1.0}
+    assert bench._PARTIAL["stage"] == "done"
+    # the other ranks run the same blocks and record nothing
+    calls.clear()
+    bench.side_blocks(_args(gpus=4), dict(bench.CFG2), None, 3, 4, 3, None, 65536, None)
+    assert len(calls) == 3
+
+
+@pytest.mark.parametrize("have_line", [True, False])
+def test_watchdog_prints_the_headline_once_it_exists(have_line, tmp_path):
+    code = (
+        "import sys, json; sys.path.insert(0, %r); import bench\n"
+        "bench._PARTIAL['stage'] = 'weak'\n"
+        "bench._PARTIAL['line'] = {'metric': 'two-tower train samples/s', 'value': 1.5} if %r else None\n"
+        "bench.watchdog()\n" % (ROOT, have_line))
+    env = dict(os.environ, RANK="0", MASTER_PORT="0%d" % os.getpid())
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    marker = "/tmp/tt_bench_partial_0%d" % os.getpid()
+    if have_line:
+        assert p.returncode == 0, p.stderr
+        line = json.loads(p.stdout.strip().splitlines()[-1])
+        assert line["value"] == 1.5 and line["incomplete"]["cut_block"] == "weak"
+        # a non-zero rank learns the outcome from the marker
+        p2 = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(env, RANK="1"), timeout=300)
+        assert p2.returncode == 0 and p2.stdout.strip() == ""
+        os.remove(marker)
+    else:
+        assert p.returncode == 3 and p.stdout.strip() == ""
+        assert not os.path.exists(marker)
+    assert "watchdog expired on rank 0 during block 'weak'" in p.stderr
+
+
+def test_reference_arm_line_shape(monkeypatch, capsys):
+    """`--impl reference`: the oracle port timed on the host cores; same metric / unit / config keys as our arm."""
+    monkeypatch.setattr(bench, "cpu_baseline", lambda cfg, steps, warmup, sample_batch=None: {
+        "value": 8000.0, "unit": "samples/s", "cores": 16, "kind": "port", "ms_per_step": 8192.0, "sample": "x"})
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    bench.run_reference(_args(impl="reference", steps=4, warmup=1))
+    line = json.loads(capsys.readouterr().out.strip())
+    assert line["impl"] == "reference" and line["metric"] == "two-tower train samples/s" and line["unit"] == "samples/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["steps"] == 4 and line["warmup"] == 1 and line["higher_is_better"] is True
+    # ranks other than 0 print nothing
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    bench.run_reference(_args(impl="reference"))
+    assert capsys.readouterr().out == ""
