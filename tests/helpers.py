@@ -25,3 +25,19 @@ def random_kjt(keys: Sequence[str], rows: Sequence[int], batch: int, max_len: in
 
 def make_tables(dims: Sequence[int], rows: Sequence[int], pooling: Sequence[str]) -> List[TableSpec]:
     return [TableSpec(f"t_f{i}", rows[i], dims[i], [f"f{i}"], pooling[i]) for i in range(len(dims))]
+
+
+def load_reference_golden():
+    """tests/golden/reference_train.npz: outputs of the reference's own bodies (tests/golden/make_reference_golden.py)."""
+    import os
+
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_train.npz"))
+    e0, e1, dim, l0, l1, B, steps = (int(x) for x in z["meta"])
+
+    def T_(k):
+        return torch.from_numpy(np.asarray(z[k]))
+
+    return {"z": z, "emb": [e0, e1], "dim": dim, "layers": [l0, l1], "B": B, "steps": steps, "lr": float(z["lr"]), "T": T_,
+            "init": {k[5:]: T_(k) for k in z.files if k.startswith("init.")},
+            "final": {k[6:]: T_(k) for k in z.files if k.startswith("final.")}}

@@ -11,7 +11,7 @@ import torch.nn.functional as F
 import oracle
 from oracle.ebc import TableSpec
 from oracle.kjt import block_bucketize_vectorized
-from helpers import random_kjt
+from helpers import load_reference_golden, random_kjt
 
 with open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")) as f:
     G = json.load(f)
@@ -222,3 +222,53 @@ def test_gathered_range_shard_kat():
     rank 0 bags: [7, 1], [9]; rank 1 bags: [], [5, 4, 6]  ->  global bags [7-5], [9-5], [], [5-5, 6-5]."""
     v, l = oracle.gathered_range_shard([T([7, 1, 9]), T([5, 4, 6])], [T([2, 1], dtype=torch.int32), T([0, 3], dtype=torch.int32)], [5], [10], 2)
     assert v.tolist() == [2, 4, 0, 1] and l.tolist() == [1, 1, 0, 2]
+
+
+# ---- fixtures made by EXECUTING the reference's own code (tests/golden/make_reference_golden.py) -------------------------
+def test_oracle_transform_equals_the_reference_transform_output():
+    """oracle.transform_to_torchrec_batch against what the reference's own loop (utils/model_training.py:43-69) produced for
+    the same raw columns: ids >= rows (modulo), id 0 (empty bag), bit-exact."""
+    G = load_reference_golden()
+    cat = ["user_id", "product_id"]
+    n_zero = 0
+    for i in range(G["steps"] + 2):
+        raw = {c: G["z"][f"raw{i}_{c}"].tolist() for c in cat}
+        raw["label"] = G["z"][f"batch{i}_labels"].tolist()
+        v, l, y = oracle.transform_to_torchrec_batch(raw, cat, G["emb"])
+        assert torch.equal(v, G["T"](f"batch{i}_values")) and torch.equal(l, G["T"](f"batch{i}_lengths")) and torch.equal(y, G["T"](f"batch{i}_labels"))
+        n_zero += int((l == 0).sum())
+    assert n_zero > 0                      # the fixture does exercise empty bags
+
+
+def test_oracle_train_steps_equal_the_reference_bodies_on_stock_torch():
+    """The oracle's whole train step against the reference's TwoTower / TwoTowerTrainTask / train() / evaluate() bodies run
+    on stock torch (nn.EmbeddingBag, relu(nn.Linear), BCEWithLogitsLoss, row-wise Adagrad in the backward, Adam): loss and
+    logits of every step, final weights, Adagrad accumulators, evaluate()'s average loss.  fp32 on both sides, same ops:
+    rtol 1e-5 (summation order inside torch only)."""
+    G = load_reference_golden()
+    cat = ["user_id", "product_id"]
+    specs = [TableSpec(f"t_{c}", G["emb"][i], G["dim"], [c]) for i, c in enumerate(cat)]
+    orc = oracle.OracleTwoTower(specs, G["layers"], loss="bce", sparse_lr=G["lr"], dense_lr=G["lr"], seed=0)
+    orc.load_torchrec_state_dict(G["init"])
+    assert set(orc.torchrec_state_dict()) == set(G["init"])          # TorchRec's key names
+    for i in range(G["steps"]):
+        loss, logits = orc.train_step(cat, G["T"](f"batch{i}_values"), G["T"](f"batch{i}_lengths"), G["T"](f"batch{i}_labels"))
+        torch.testing.assert_close(loss, G["T"](f"step{i}_loss"), rtol=1e-5, atol=1e-7, msg=lambda m: f"step {i} loss: {m}")
+        torch.testing.assert_close(logits, G["T"](f"step{i}_logits"), rtol=1e-5, atol=1e-6, msg=lambda m: f"step {i} logits: {m}")
+    got = orc.torchrec_state_dict()
+    moved = 0.0
+    for k, want in G["final"].items():
+        torch.testing.assert_close(got[k], want, rtol=1e-5, atol=1e-6, msg=lambda m: f"{k}: {m}")
+        moved = max(moved, float((want - G["init"][k]).abs().max()))
+    assert moved > 5e-3                    # the steps did move the weights: the comparison is not vacuous
+    for c in cat:
+        torch.testing.assert_close(orc.sparse_state[f"t_{c}"]["sum"], G["T"](f"sum.t_{c}"), rtol=1e-5, atol=1e-12)
+    total = 0.0
+    for j in range(2):
+        i = G["steps"] + j
+        q, cnd = orc.forward(cat, G["T"](f"batch{i}_values"), G["T"](f"batch{i}_lengths"))
+        loss, logits = orc.loss(q, cnd, G["T"](f"batch{i}_labels"))
+        torch.testing.assert_close(loss.detach(), G["T"](f"eval{j}_loss"), rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(logits.detach(), G["T"](f"eval{j}_logits"), rtol=1e-5, atol=1e-6)
+        total += float(loss)
+    assert abs(total / (2 * G["B"]) - float(G["z"]["eval_average_loss"])) < 1e-8   # U:246 divides by the SAMPLE count
