@@ -24,7 +24,9 @@ unsharded TorchRec executes on CPU -- NOT by this repo's package and NOT by orac
 
 The fixture stores the raw batches, what the reference's transform made of them, the seeded initial weights, and -- all
 produced by the reference's bodies on stock torch -- the loss / logits of every training step, the final weights, the
-row-wise Adagrad accumulators and the evaluate() average loss.  tests/test_oracle_golden.py holds oracle/ to it on CPU,
+row-wise Adagrad accumulators, the evaluate() average loss, and the item / user embeddings the reference's own
+``create_keyed_jagged_tensor`` / ``process_embeddings`` (03_model_training.py:1056-1122) compute from the trained model, with
+their exact top-100 by stock ``torch.sort``.  tests/test_oracle_golden.py holds oracle/ to it on CPU,
 tests/test_gpu_zz_reference_golden.py holds the CUDA path to it on the GPU box (where /root/reference does not exist).
 """
 import itertools
@@ -67,6 +69,11 @@ class KeyedJaggedTensor:
 
     def offsets(self):
         return self._offsets
+
+    def length_per_key(self):
+        n = len(self._keys)
+        stride = self._lengths.numel() // n
+        return [int(self._lengths[k * stride:(k + 1) * stride].sum()) for k in range(n)]
 
     def to(self, device, non_blocking=False):
         return self
@@ -249,6 +256,19 @@ class _Auroc:
         return torch.tensor(0.0)
 
 
+def _functions_of(path, names, env):
+    """Executes ONLY the named top-level function definitions of a notebook source (the rest of the file talks to Spark /
+    MLflow / a Databricks workspace); returns the namespace."""
+    import ast
+    with open(path) as f:
+        tree = ast.parse(f.read(), path)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert sorted(n.name for n in keep) == sorted(names), [n.name for n in keep]
+    ns = dict(env)
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
 def main():
     install_standins()
     sys.modules["torchmetrics"].AUROC = _Auroc
@@ -323,6 +343,23 @@ def main():
         out["init." + k] = v.numpy()
     for k, v in final.items():
         out["final." + k] = v.numpy()
+    # 03_model_training.py:1056-1122: the reference's own corpus / query embedding functions on the trained model
+    nb = _functions_of("/root/reference/03_model_training.py", ["create_keyed_jagged_tensor", "process_embeddings"],
+                       {"torch": torch, "KeyedJaggedTensor": KeyedJaggedTensor})
+    two_tower.eval()
+    for key, n in (("product_id", EMB[1]), ("user_id", EMB[0])):
+        kjt = nb["create_keyed_jagged_tensor"](n, list(CAT), key, device="cpu")
+        emb = nb["process_embeddings"](two_tower, kjt, key)
+        assert emb is not None and emb.shape == (n, LAYERS[-1])
+        out[f"corpus_{key}_values"] = kjt.values().numpy().astype(np.int64)
+        out[f"corpus_{key}_lengths"] = kjt.lengths().numpy().astype(np.int32)
+        out[f"corpus_{key}_embeddings"] = emb.numpy().astype(np.float32)
+    # 04_evaluate_retrieval.py:134-141 asks a remote Vector Search index for the 100 best items per user by score; the
+    # service is not here -- stock torch gives the exact answer (descending score, stable: ties keep the lower id)
+    users, items = torch.from_numpy(out["corpus_user_id_embeddings"]), torch.from_numpy(out["corpus_product_id_embeddings"])
+    order = torch.sort(users @ items.t(), dim=1, descending=True, stable=True)
+    out["top100_scores"] = order.values[:, :100].numpy().astype(np.float32)
+    out["top100_ids"] = order.indices[:, :100].numpy().astype(np.int64)
     out["meta"] = np.asarray([EMB[0], EMB[1], DIM, LAYERS[0], LAYERS[1], B, STEPS], dtype=np.int64)
     out["lr"] = np.float32(LR)
     path = os.path.join(HERE, "reference_train.npz")

@@ -80,3 +80,29 @@ def test_train_steps_equal_the_reference_bodies(cuda):
     assert abs(total / (2 * G["B"]) - float(G["z"]["eval_average_loss"])) < 1e-6
     for k, v in model.module.two_tower.state_dict().items():
         assert torch.equal(v, before[k])
+
+
+def test_corpus_embeddings_and_topk_equal_the_reference_functions(cuda):
+    """create_keyed_jagged_tensor / process_embeddings (same signatures as 03_model_training.py:1056-1122) and the top-100
+    search against what the reference's own functions computed from the trained model (tolerances of
+    tests/test_gpu_train.py's retrieval test: embeddings and scores rtol 1e-5 / atol 1e-5, recall >= 0.999)."""
+    import two_tower_recommender_model_b200 as tt
+    G = load_reference_golden()
+    emb, dim, layers = G["emb"], G["dim"], G["layers"]
+    ebc = tt.EmbeddingBagCollection(tables=[tt.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=dim, num_embeddings=emb[i], feature_names=[c])
+                                            for i, c in enumerate(CAT)], device=cuda)
+    model = tt.TwoTower(ebc, layers, device=cuda)
+    model.load_state_dict(G["final"])
+    model.eval()
+    out = {}
+    for key, n in (("product_id", emb[1]), ("user_id", emb[0])):
+        kjt = tt.create_keyed_jagged_tensor(n, CAT, key, device=cuda)
+        assert torch.equal(kjt.values().cpu(), G["T"](f"corpus_{key}_values")) and torch.equal(kjt.lengths().cpu(), G["T"](f"corpus_{key}_lengths"))
+        out[key] = tt.process_embeddings(model, kjt, key)
+        torch.testing.assert_close(out[key].cpu(), G["T"](f"corpus_{key}_embeddings"), rtol=1e-5, atol=1e-5)
+    index = tt.BruteForceIndex(out["product_id"])
+    scores, ids = index.search(out["user_id"], num_results=100)
+    torch.testing.assert_close(scores.cpu(), G["T"]("top100_scores"), rtol=1e-5, atol=1e-5)
+    want = G["T"]("top100_ids")
+    recall = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(ids.cpu(), want)) / want.numel()
+    assert recall >= 0.999

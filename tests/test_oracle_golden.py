@@ -272,3 +272,31 @@ def test_oracle_train_steps_equal_the_reference_bodies_on_stock_torch():
         torch.testing.assert_close(logits.detach(), G["T"](f"eval{j}_logits"), rtol=1e-5, atol=1e-6)
         total += float(loss)
     assert abs(total / (2 * G["B"]) - float(G["z"]["eval_average_loss"])) < 1e-8   # U:246 divides by the SAMPLE count
+
+
+def test_oracle_corpus_embeddings_and_topk_equal_the_reference_functions():
+    """oracle towers / oracle.exact_topk against the item and user embeddings the reference's own create_keyed_jagged_tensor
+    + process_embeddings (03_model_training.py:1056-1122) computed from the trained model, and their top-100 by torch.sort."""
+    G = load_reference_golden()
+    cat = ["user_id", "product_id"]
+    specs = [TableSpec(f"t_{c}", G["emb"][i], G["dim"], [c]) for i, c in enumerate(cat)]
+    orc = oracle.OracleTwoTower(specs, G["layers"], loss="bce", seed=0)
+    orc.load_torchrec_state_dict(G["final"])
+    embs = {}
+    for key, n in (("product_id", G["emb"][1]), ("user_id", G["emb"][0])):
+        v, l = G["T"](f"corpus_{key}_values"), G["T"](f"corpus_{key}_lengths")
+        assert v.tolist() == list(range(n)) and l.tolist() == ([0] * n + [1] * n if key == "product_id" else [1] * n + [0] * n)
+        with torch.no_grad():
+            q, c = orc.forward(cat, v, l)
+        embs[key] = c if key == "product_id" else q
+        torch.testing.assert_close(embs[key], G["T"](f"corpus_{key}_embeddings"), rtol=1e-5, atol=1e-6)
+    ws, wi = oracle.exact_topk(embs["user_id"], embs["product_id"], 100)
+    torch.testing.assert_close(ws, G["T"]("top100_scores"), rtol=1e-5, atol=1e-6)
+    want = G["T"]("top100_ids")
+    # ids: equal wherever the neighbouring scores are further apart than fp32 summation noise
+    gap = (G["T"]("top100_scores")[:, :-1] - G["T"]("top100_scores")[:, 1:]).abs()
+    clear = torch.ones_like(want, dtype=torch.bool)
+    clear[:, :-1] &= gap > 1e-6
+    clear[:, 1:] &= gap > 1e-6
+    clear[:, -1] = False                   # the 100th may swap with the 101st
+    assert torch.equal(wi[clear], want[clear]) and float(clear.float().mean()) > 0.9
