@@ -25,9 +25,13 @@ class OracleTwoTower(nn.Module):
         dense_lr: float = 1e-2, temperature: float = 1.0,
         query_features: Optional[List[str]] = None,
         candidate_features: Optional[List[str]] = None, seed: int = 0,
-        dense_optimizer: str = "adam",
+        dense_optimizer: str = "adam", dense_index: Optional[int] = None, dense_dim: int = 0,
     ) -> None:
+        """``layer_sizes`` may be ``[user_layers, item_layers]`` and ``dense_index`` / ``dense_dim`` concatenate
+        ``dense[:, :dense_index]`` / ``dense[:, dense_index:dense_dim]`` to the tower inputs, as the Ray-Tune variant of
+        the reference does (/root/reference/ray_tune_optuna_tuning_alex_test.py:227-306)."""
         super().__init__()
+        self.dense_index, self.dense_dim = dense_index, dense_dim
         self.tables = list(tables)
         self.loss_kind = loss
         self.sparse_optimizer = sparse_optimizer
@@ -54,8 +58,12 @@ class OracleTwoTower(nn.Module):
         dim_of = dict(zip(keys, dims))
         q_in = sum(dim_of[f] for f in self.query_features)
         c_in = sum(dim_of[f] for f in self.candidate_features)
-        self.query_proj = self._make_mlp(q_in, layer_sizes, g)
-        self.candidate_proj = self._make_mlp(c_in, layer_sizes, g)
+        per_tower = any(isinstance(x, (list, tuple)) for x in layer_sizes)
+        q_layers, c_layers = (layer_sizes[0], layer_sizes[1]) if per_tower else (layer_sizes, layer_sizes)
+        if dense_index is not None:
+            q_in, c_in = q_in + dense_index, c_in + (dense_dim - dense_index)
+        self.query_proj = self._make_mlp(q_in, q_layers, g)
+        self.candidate_proj = self._make_mlp(c_in, c_layers, g)
         self.sparse_state: Dict[str, Dict[str, torch.Tensor]] = {}
         for t in self.tables:
             st = {"sum": torch.zeros(t.num_embeddings)}
@@ -118,17 +126,20 @@ class OracleTwoTower(nn.Module):
                 out[feat] = self.embedding_bags[t.name](values[s:e], offsets[f * B:(f + 1) * B + 1] - s)
         return out
 
-    def towers(self, pooled: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    def towers(self, pooled: Dict[str, torch.Tensor], dense: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         q = torch.cat([pooled[f] for f in self.query_features], dim=1)
         c = torch.cat([pooled[f] for f in self.candidate_features], dim=1)
+        if self.dense_index is not None:
+            q = torch.cat([q, dense[:, :self.dense_index].float()], dim=1)
+            c = torch.cat([c, dense[:, self.dense_index:self.dense_dim].float()], dim=1)
         for lin in self.query_proj:
             q = torch.relu(lin(q))
         for lin in self.candidate_proj:
             c = torch.relu(lin(c))
         return q, c
 
-    def forward(self, keys, values, lengths):
-        return self.towers(self.pooled(keys, values, lengths))
+    def forward(self, keys, values, lengths, dense: Optional[torch.Tensor] = None):
+        return self.towers(self.pooled(keys, values, lengths), dense)
 
     def loss(self, q: torch.Tensor, c: torch.Tensor, labels: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         if self.loss_kind == "bce":

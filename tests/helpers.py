@@ -41,3 +41,18 @@ def load_reference_golden():
     return {"z": z, "emb": [e0, e1], "dim": dim, "layers": [l0, l1], "B": B, "steps": steps, "lr": float(z["lr"]), "T": T_,
             "init": {k[5:]: T_(k) for k in z.files if k.startswith("init.")},
             "final": {k[6:]: T_(k) for k in z.files if k.startswith("final.")}}
+
+
+def load_raytune_golden():
+    """tests/golden/reference_raytune.npz: the reference's Ray-Tune TwoTower class run on stock torch
+    (tests/golden/make_reference_raytune_golden.py)."""
+    import os
+
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_raytune.npz"))
+    G = {k: torch.from_numpy(np.asarray(z[k])) for k in z.files if "." not in k}
+    G["weights"] = {k[7:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith("weight.")}
+    G["grads"] = {k[5:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith("grad.")}
+    G.update(feats_u=["u_a", "u_b"], feats_i=["i_a"], dims={"u_a": 36, "u_b": 4, "i_a": 36}, rows={"u_a": 100, "u_b": 7, "i_a": 90},
+             layers=[[64, 16], [32, 16]], dense_index=3, dense_dim=5)
+    return G

@@ -106,3 +106,34 @@ def test_corpus_embeddings_and_topk_equal_the_reference_functions(cuda):
     want = G["T"]("top100_ids")
     recall = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(ids.cpu(), want)) / want.numel()
     assert recall >= 0.999
+
+
+def test_ray_tune_towers_equal_the_reference_class(cuda):
+    """Several features per tower, one layer stack per tower, dense features concatenated to the tower inputs
+    (ray_tune_optuna_tuning_alex_test.py:181-306): embeddings, logits, loss and every parameter's gradient against what the
+    reference's own class computed on stock torch (tests/golden/reference_raytune.npz).  Tolerances of
+    tests/test_gpu_train.py::test_ray_tune_variant_towers (fp32 kernels, summation order only)."""
+    import two_tower_recommender_model_b200 as tt
+    from helpers import load_raytune_golden
+    G = load_raytune_golden()
+    keys = list(G["dims"])
+    cfgs = [tt.EmbeddingBagConfig(name=f"t_{k}", embedding_dim=G["dims"][k], num_embeddings=G["rows"][k], feature_names=[k]) for k in keys]
+    ebc = tt.EmbeddingBagCollection(tables=cfgs, device=cuda)
+    model = tt.TwoTower(ebc, G["layers"], device=cuda, query_features=G["feats_u"], candidate_features=G["feats_i"],
+                        dense_index=G["dense_index"], dense_dim=G["dense_dim"])
+    assert set(model.state_dict()) == set(G["weights"])
+    model.load_state_dict(G["weights"])
+    task = tt.TwoTowerTrainTask(model)
+    batch = tt.Batch(G["dense"].to(cuda), tt.KeyedJaggedTensor.from_lengths_sync(keys, G["values"].to(cuda), G["lengths"].to(cuda)),
+                     G["labels"].to(cuda))
+    with torch.no_grad():
+        q, c = model(batch)
+    torch.testing.assert_close(q.cpu(), G["q"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(c.cpu(), G["c"], rtol=1e-4, atol=1e-5)
+    loss, (_, logits, _) = task(batch)
+    torch.testing.assert_close(logits.cpu(), G["logits"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(loss.detach().cpu(), G["loss"], rtol=1e-5, atol=1e-6)
+    loss.backward()
+    for k, p in model.state_dict(keep_vars=True).items():
+        assert p.grad is not None, k
+        torch.testing.assert_close(p.grad.cpu(), G["grads"][k], rtol=1e-4, atol=1e-6, msg=lambda m: f"grad of {k}: {m}")

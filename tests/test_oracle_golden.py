@@ -300,3 +300,32 @@ def test_oracle_corpus_embeddings_and_topk_equal_the_reference_functions():
     clear[:, 1:] &= gap > 1e-6
     clear[:, -1] = False                   # the 100th may swap with the 101st
     assert torch.equal(wi[clear], want[clear]) and float(clear.float().mean()) > 0.9
+
+
+def test_oracle_ray_tune_towers_equal_the_reference_class():
+    """Several features per tower, one layer stack per tower, dense features concatenated to the tower inputs: the oracle
+    against the reference's own Ray-Tune TwoTower class (ray_tune_optuna_tuning_alex_test.py:181-306) run on stock torch --
+    embeddings, logits, BCE loss and the gradient of every parameter."""
+    from helpers import load_raytune_golden
+    G = load_raytune_golden()
+    keys = list(G["dims"])
+    specs = [TableSpec(f"t_{k}", G["rows"][k], G["dims"][k], [k]) for k in keys]
+    orc = oracle.OracleTwoTower(specs, G["layers"], loss="bce", query_features=G["feats_u"], candidate_features=G["feats_i"],
+                                dense_index=G["dense_index"], dense_dim=G["dense_dim"], seed=0)
+    assert set(orc.torchrec_state_dict()) == set(G["weights"])
+    orc.load_torchrec_state_dict(G["weights"])
+    q, c = orc.forward(keys, G["values"], G["lengths"], G["dense"])
+    loss, logits = orc.loss(q, c, G["labels"])
+    torch.testing.assert_close(q.detach(), G["q"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(c.detach(), G["c"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(logits.detach(), G["logits"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(loss.detach(), G["loss"], rtol=1e-6, atol=1e-7)
+    loss.backward()
+    got = {f"ebc.embedding_bags.{s.name}.weight": orc.embedding_bags[s.name].weight.grad for s in specs}
+    for tower, mods in (("query_proj", orc.query_proj), ("candidate_proj", orc.candidate_proj)):
+        for i, lin in enumerate(mods):
+            got[f"{tower}._mlp.{i}._linear.weight"], got[f"{tower}._mlp.{i}._linear.bias"] = lin.weight.grad, lin.bias.grad
+    assert set(got) == set(G["grads"])
+    for k, want in G["grads"].items():
+        torch.testing.assert_close(got[k], want, rtol=1e-5, atol=1e-8, msg=lambda m: f"grad of {k}: {m}")
+        assert float(want.abs().max()) > 0
