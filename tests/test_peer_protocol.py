@@ -24,7 +24,7 @@ class FakeExchange:
     def __init__(self):
         self._pooled2 = torch.zeros(2, self.rows, self.cols)
         self._grad2 = torch.zeros(2, self.rows, self.cols)
-        self.cur, self.dirty = 0, [False, False]
+        self.cur, self.dirty, self.forward_open = 0, [False, False], False
         self.barriers = 0
 
     flip = S.PeerExchange.flip
@@ -73,12 +73,12 @@ def fake_kernels(monkeypatch):
     return state
 
 
-def _forward(ex, train):
+def _forward(ex, train, scatter_add=True):
     values = torch.zeros(1, dtype=torch.int64)
     offsets = torch.zeros(2, dtype=torch.int32)
     anchor = torch.zeros(0, requires_grad=train)
     with torch.set_grad_enabled(train):
-        out = S._PeerTwLookup.apply(ex, FakeLocalEbc(), (ex.cols, {}), ("f",), values, offsets, True, None, anchor)
+        out = S._PeerTwLookup.apply(ex, FakeLocalEbc(), (ex.cols, {}), ("f",), values, offsets, scatter_add, None, anchor)
     return out
 
 
@@ -133,3 +133,22 @@ def test_replays_after_eval_forwards_start_from_a_clear_buffer(fake_kernels):
         assert ex.cur == 1
         _run(ex, "C" + "E" * evals + "C" + "T" + "C")
         assert ex.dirty == [False, False]
+
+
+def test_table_wise_replay_after_an_eval_forward_waits_for_the_readers(fake_kernels):
+    """Store mode (table-wise) has nothing to clear, but a replay writes the ONE buffer it was captured with: if the last
+    operation was an eager forward, a peer may still be reading that buffer -- clean() lines the ranks up, once."""
+    ex = FakeExchange()
+    fake_kernels["ex"] = ex
+    out = _forward(ex, train=True, scatter_add=False)
+    out.sum().backward()
+    assert ex.barriers == 2 and ex.dirty == [False, False] and not ex.forward_open
+    ex.clean()
+    assert ex.barriers == 2                          # steady state of a training loop: nothing to do, no barrier
+    _forward(ex, train=False, scatter_add=False)
+    _forward(ex, train=False, scatter_add=False)
+    assert ex.barriers == 4 and ex.forward_open and ex.dirty == [False, False]
+    ex.clean()
+    assert ex.barriers == 5 and not ex.forward_open
+    ex.clean()
+    assert ex.barriers == 5

@@ -129,6 +129,10 @@ class PeerExchange:
         # with them the number of barriers) agree across ranks.
         self._pooled2.zero_()
         self.dirty = [False, False]
+        # forward_open: the last thing this exchange did was a forward (no backward since).  Eager steps alternate buffers,
+        # so the next eager forward never touches the rows a peer may still be reading; a captured step replays on ONE
+        # fixed buffer and must not start while that can be the case (see clean()).
+        self.forward_open = False
         dist.barrier(group=pg)
 
     def _peers(self, handle, byte_offset: int = 0, flags: int = 0):
@@ -156,14 +160,17 @@ class PeerExchange:
         return self._grad_peers[b]
 
     def clean(self) -> None:
-        """Clears every scatter-add buffer a backward-less forward left dirty (collective: one barrier when anything
-        was dirty).  ``CudaGraphTrainStep`` calls it before a replay: the captured step assumes a clean buffer."""
-        if not any(self.dirty):
+        """What ``CudaGraphTrainStep`` does before a replay (a captured step runs on ONE fixed buffer and cannot look at
+        flags): clears every scatter-add buffer a backward-less forward left dirty, and -- if the last operation was an
+        eager forward, whose rows a peer may still be reading from the very buffer the replay writes -- lines the ranks
+        up.  Collective: one barrier when there was anything to do, none in the steady state of a training loop."""
+        if not any(self.dirty) and not self.forward_open:
             return
         for b in (0, 1):
             if self.dirty[b]:
                 self.pooled(b).zero_()
                 self.dirty[b] = False
+        self.forward_open = False
         self.barrier_pooled()
 
     def barrier_pooled(self) -> None:
@@ -200,6 +207,7 @@ class _PeerTwLookup(torch.autograd.Function):
         ex.barrier_pooled()           # every owner's rows have landed here
         if scatter_add:
             ex.dirty[b] = True
+        ex.forward_open = True
         ctx.ex, ctx.ebc, ctx.layout, ctx.kjt_keys, ctx.n_anchors, ctx.buf = ex, ebc, layout, kjt_keys, len(anchors), b
         ctx.scatter_add = scatter_add
         ctx.pre_backward = pre_backward
@@ -211,6 +219,7 @@ class _PeerTwLookup(torch.autograd.Function):
         from ctypes import byref
         from .. import _native as N
         ex, ebc, b = ctx.ex, ctx.ebc, ctx.buf
+        ex.forward_open = False        # every reader of the pooled rows is upstream of this node; the gradient barrier follows
         gbuf = ex.grad(b)
         if grad.data_ptr() != gbuf.data_ptr():
             gbuf.copy_(grad)          # the producer did not write in place (see FusedTowersTC grad_dst)
