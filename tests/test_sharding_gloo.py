@@ -235,3 +235,61 @@ def test_sharded_equals_unsharded_world2_gloo():
             p.terminate()
             msgs.append("worker hung")
     assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)
+
+
+# ------------------------------------------------------------------ corpus-sharded retrieval (SURVEY 8(e) fallback)
+def _worker_corpus_sharded(rank, world, port, errq):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import two_tower_recommender_model_b200 as tt
+        from two_tower_recommender_model_b200 import retrieval
+        # the device kernel -> oracle (tests only): same contract, global ids through item_index_base
+        def topk(q, items, k, item_index_base=0, precision="fp32", items_bf16=None):
+            s, i = oracle.exact_topk(q, items, k)
+            return s, i + item_index_base
+        retrieval.score_topk = topk
+        g = torch.Generator().manual_seed(3)
+        n_items, d, Q = 157, 8, 11
+        # entries on a 1/4 grid: every dot product is exact in fp32 and TIES ACROSS SHARDS are common
+        items = torch.randint(-4, 5, (n_items, d), generator=g).float() / 4
+        items[100] = items[3]                       # the same vector in shard 0 and shard 1: a guaranteed cross-shard tie
+        queries = [torch.randint(-4, 5, (Q, d), generator=g).float() / 4 for _ in range(world)]
+        per = -(-n_items // world)
+        lo, hi = rank * per, min((rank + 1) * per, n_items)
+        for k in (1, 10, 100, 200):                 # 100 > one shard's share of the top, 200 > the whole corpus
+            index = tt.CorpusShardedIndex(items[lo:hi], first_id=lo)
+            s, i = index.search(queries[rank], k)
+            ws, wi = oracle.exact_topk(queries[rank], items, min(k, n_items))
+            kk = min(k, n_items)
+            assert s.shape == (Q, k) and i.shape == (Q, k)
+            assert torch.equal(s[:, :kk], ws) and torch.equal(i[:, :kk], wi), f"k={k}"
+            if k > n_items:                         # more results asked for than items exist: the tail is padding
+                assert torch.isinf(s[:, kk:]).all()
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put(f"rank {rank}:\n{traceback.format_exc()}")
+        raise
+
+
+def test_corpus_sharded_retrieval_world2_gloo():
+    """Each rank holds half of the corpus, the queries are all-gathered, per-shard top-k lists return to the query's rank in
+    one all-to-all and are merged: ids and scores bit-exact against the oracle's top-k over the whole corpus, ties across
+    shards resolved to the lower id."""
+    ctx = mp.get_context("spawn")
+    errq = ctx.SimpleQueue()
+    port = 29850 + os.getpid() % 100
+    procs = [ctx.Process(target=_worker_corpus_sharded, args=(r, 2, port, errq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    msgs = []
+    while not errq.empty():
+        msgs.append(errq.get())
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+            msgs.append("worker hung")
+    assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)

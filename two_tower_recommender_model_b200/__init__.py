@@ -11,7 +11,7 @@ from .distributed.planner.storage_reservations import HeuristicalStorageReservat
 from .graph import CudaGraphTrainStep  # noqa: F401
 from .modules import MLP, EmbeddingBagCollection, EmbeddingBagConfig, PoolingType  # noqa: F401
 from .optim import FlatAdam, KeyedOptimizerWrapper, RowWiseAdagrad, RowWiseAdam  # noqa: F401
-from .retrieval import (BruteForceIndex, create_keyed_jagged_tensor, embed_corpus, embed_corpus_sharded,  # noqa: F401
+from .retrieval import (BruteForceIndex, CorpusShardedIndex, create_keyed_jagged_tensor, embed_corpus, embed_corpus_sharded,  # noqa: F401
                         process_embeddings, retrieval_metrics)
 from .shim import install_torchrec_shim  # noqa: F401
 from .sparse import JaggedTensor, KeyedJaggedTensor, KeyedTensor  # noqa: F401

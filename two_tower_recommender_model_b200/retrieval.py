@@ -166,6 +166,60 @@ class BruteForceIndex:
                 "result": {"row_count": len(rows), "data_array": rows}}
 
 
+class CorpusShardedIndex:
+    """Exact inner-product retrieval when the corpus does NOT fit one GPU ("fall back to corpus-sharding
+    + [Q, k]-per-rank all-to-all merge"): every rank keeps the embeddings of ITS contiguous id range (what
+    ``embed_corpus_sharded`` returns), the queries of all ranks are all-gathered, each rank scores every query against
+    its shard with the single-GPU top-k kernel (``item_index_base`` = first id of the shard, so the kernel already
+    returns global ids), the per-shard top-k lists travel to the rank that owns the query in ONE all-to-all, and the W
+    lists are merged there (descending score, ties -> lower id: the order of ``BruteForceIndex`` on the whole corpus).
+    The query count must be the same on every rank (pad the last block); ``BruteForceIndex.from_sharded`` -- corpus
+    all-gathered, queries sharded, no merge -- is the faster layout whenever the corpus fits."""
+
+    def __init__(self, local_item_embeddings: torch.Tensor, first_id: int, pg=None, precision: str = "fp32") -> None:
+        self._items = local_item_embeddings.contiguous().float()
+        self._first, self._pg, self._precision = int(first_id), pg, precision
+        self._items_bf16 = None
+        if precision == "bf16" and self._items.shape[0] > 0:
+            from .functional import cast_bf16
+            self._items_bf16 = cast_bf16(self._items)
+
+    def search(self, query_embeddings: torch.Tensor, num_results: int = 100):
+        """``query_embeddings`` [Q, d]: THIS rank's queries.  Returns ``(scores [Q, k] f32, ids [Q, k] int64)`` over the
+        whole (sharded) corpus; a collective -- every rank calls it with the same Q and k."""
+        from torch import distributed as dist
+        pg = self._pg
+        W = dist.get_world_size(pg) if dist.is_available() and dist.is_initialized() else 1
+        q = query_embeddings.to(self._items.device).float().contiguous()
+        Q, k = q.shape[0], int(num_results)
+        if W > 1:
+            allq = q.new_empty(W * Q, q.shape[1])
+            dist.all_gather_into_tensor(allq, q, group=pg)
+        else:
+            allq = q
+        n_local = self._items.shape[0]
+        kl = min(k, n_local)
+        part_s = torch.full((W * Q, k), float("-inf"), dtype=torch.float32, device=q.device)
+        part_i = torch.full((W * Q, k), (1 << 62), dtype=torch.int64, device=q.device)
+        if kl > 0:
+            sc, ix = score_topk(allq, self._items, kl, item_index_base=self._first, precision=self._precision,
+                                items_bf16=self._items_bf16)
+            part_s[:, :kl], part_i[:, :kl] = sc, ix
+        if W > 1:
+            recv_s, recv_i = torch.empty_like(part_s), torch.empty_like(part_i)
+            dist.all_to_all_single(recv_s, part_s, group=pg)      # block r of the send buffer = rank r's queries
+            dist.all_to_all_single(recv_i, part_i, group=pg)
+            cand_s = recv_s.view(W, Q, k).permute(1, 0, 2).reshape(Q, W * k)
+            cand_i = recv_i.view(W, Q, k).permute(1, 0, 2).reshape(Q, W * k)
+        else:
+            cand_s, cand_i = part_s, part_i
+        # merge: by id ascending first, then a STABLE sort by descending score -> equal scores keep the lower id first
+        by_id = torch.argsort(cand_i, dim=1, stable=True)
+        cand_s, cand_i = cand_s.gather(1, by_id), cand_i.gather(1, by_id)
+        order = torch.argsort(cand_s, dim=1, descending=True, stable=True)[:, :k]
+        return cand_s.gather(1, order), cand_i.gather(1, order)
+
+
 def retrieval_metrics(pred_ids: torch.Tensor, targets: Sequence[Sequence[int]], k: int) -> Dict[str, float]:
     """precision_at_k / recall_at_k / ndcg_at_k (mean over rows), computed on the
     device: ``pred_ids`` is ``[Q, >=k]`` int64, ``targets[i]`` the relevant ids of row i."""
