@@ -160,3 +160,121 @@ def test_planner_properties(tables, W):
             assert len(ps.ranks) == 1 and 0 <= ps.ranks[0] < W
         else:
             assert ps.ranks == list(range(W)) and ps.block_size * W >= c.num_embeddings
+
+
+# ---- floating-point oracle functions: invariants the domain offers ---------------------------------------------------------
+from oracle.ebc import TableSpec  # noqa: E402
+
+
+@settings(max_examples=40, deadline=None)
+@given(jagged(max_f=3), st.integers(0, 2 ** 31 - 1), st.sampled_from(["sum", "mean"]))
+def test_ebc_forward_properties(j, seed, pooling):
+    """ebc_forward == per-feature F.embedding_bag (what unsharded TorchRec runs); linear in the tables; empty bags give zero
+    rows; the dense gradient is the adjoint of the lookup: <ebc(W), G> == <W, ebc_dense_grads(G)>."""
+    F, B, rows, vals, lens = j
+    g = torch.Generator().manual_seed(seed)
+    keys = [f"f{i}" for i in range(F)]
+    specs = [TableSpec(f"t{i}", rows[i], 4, [keys[i]], pooling) for i in range(F)]
+    W1 = [torch.randn(r, 4, generator=g, dtype=torch.float64) for r in rows]
+    W2 = [torch.randn(r, 4, generator=g, dtype=torch.float64) for r in rows]
+    o1 = oracle.ebc_forward(specs, W1, keys, vals, lens)
+    torch.testing.assert_close(o1, oracle.ebc_forward_torch(specs, W1, keys, vals, lens), rtol=1e-12, atol=1e-12)
+    o2 = oracle.ebc_forward(specs, W2, keys, vals, lens)
+    o12 = oracle.ebc_forward(specs, [2.0 * a - 3.0 * b for a, b in zip(W1, W2)], keys, vals, lens)
+    torch.testing.assert_close(o12, 2.0 * o1 - 3.0 * o2, rtol=1e-10, atol=1e-10)
+    for f in range(F):
+        empty = lens[f * B:(f + 1) * B] == 0
+        assert (o1[empty][:, 4 * f:4 * f + 4] == 0).all()
+    G = torch.randn(B, 4 * F, generator=g, dtype=torch.float64)
+    grads = oracle.ebc_dense_grads(specs, keys, vals, lens, G)
+    lhs = float((o1 * G).sum())
+    rhs = float(sum((w * gr).sum() for w, gr in zip(W1, grads)))
+    assert abs(lhs - rhs) <= 1e-9 * (1.0 + abs(lhs))
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 30), st.integers(1, 6), st.integers(0, 40), st.integers(0, 2 ** 31 - 1))
+def test_rowwise_optimizer_properties(R, D, n, seed):
+    """Row-wise Adagrad: the sparse-exact form (unique rows + summed gradients) equals the dense form; untouched rows and
+    their accumulators do not move; the accumulator never decreases.  Row-wise Adam: only touched rows advance, and a first
+    step moves every touched element with a non-zero gradient by lr in magnitude (bias-corrected m / sqrt(v) with v = mean g^2
+    per row is +-1 for D = 1)."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, R, (n,), generator=g)
+    contrib = torch.randn(n, D, generator=g, dtype=torch.float64)
+    dense = torch.zeros(R, D, dtype=torch.float64).index_add_(0, ids, contrib)
+    w0 = torch.randn(R, D, generator=g, dtype=torch.float64)
+    s0 = torch.rand(R, generator=g, dtype=torch.float64)
+    wd, sd = w0.clone(), s0.clone()
+    oracle.rowwise_adagrad_dense(wd, sd, dense, lr=0.1)
+    ws, ss = w0.clone(), s0.clone()
+    rows = torch.unique(ids, sorted=True)
+    oracle.rowwise_adagrad_sparse(ws, ss, rows, dense[rows], lr=0.1)
+    torch.testing.assert_close(ws, wd, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(ss, sd, rtol=1e-12, atol=1e-12)
+    untouched = torch.ones(R, dtype=torch.bool)
+    untouched[rows] = False
+    assert torch.equal(wd[untouched], w0[untouched]) and torch.equal(sd[untouched], s0[untouched])
+    assert (sd >= s0).all()
+    wa, m, v = w0.clone(), torch.zeros(R, D, dtype=torch.float64), torch.zeros(R, dtype=torch.float64)
+    oracle.rowwise_adam_sparse(wa, m, v, rows, dense[rows], step=1, lr=0.05, eps=0.0 if D == 1 else 1e-8)
+    assert torch.equal(wa[untouched], w0[untouched]) and (m[untouched] == 0).all() and (v[untouched] == 0).all()
+    if D == 1 and rows.numel():
+        nz = dense[rows].abs().squeeze(1) > 1e-9
+        torch.testing.assert_close((wa[rows] - w0[rows]).abs().squeeze(1)[nz], torch.full((int(nz.sum()),), 0.05, dtype=torch.float64),
+                                   rtol=1e-9, atol=1e-12)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.integers(0, 25), min_size=0, max_size=60))
+def test_dedup_rows_properties(ids):
+    """dedup_rows: keys ascending and unique, counts add up to n, unique[inverse] gives the input back."""
+    t = torch.tensor(ids, dtype=torch.int64)
+    u, inv, cnt = oracle.dedup_rows(t)
+    assert u.tolist() == sorted(set(ids)) and int(cnt.sum()) == len(ids)
+    assert torch.equal(u[inv], t)
+    assert cnt.tolist() == [ids.count(int(x)) for x in u]
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 6), st.integers(1, 12), st.integers(1, 12), st.integers(0, 2 ** 31 - 1))
+def test_retrieval_metrics_properties(Q, n_pred, k, seed):
+    """precision / recall / ndcg at k lie in [0, 1]; retrieving exactly the targets first gives recall = ndcg = 1;
+    retrieving nothing relevant gives 0 everywhere."""
+    g = torch.Generator().manual_seed(seed)
+    pred = [torch.randperm(40, generator=g)[:n_pred].tolist() for _ in range(Q)]
+    tgt = [torch.randperm(40, generator=g)[:int(torch.randint(1, 8, (1,), generator=g))].tolist() for _ in range(Q)]
+    m = oracle.retrieval_metrics(pred, tgt, k)
+    assert all(0.0 <= x <= 1.0 + 1e-12 for x in m.values())
+    perfect = [t + [100 + i for i in range(k)] for t in tgt]
+    mp = oracle.retrieval_metrics(perfect, tgt, k)
+    if all(len(t) <= k for t in tgt):
+        assert abs(mp[f"recall_at_{k}"] - 1.0) < 1e-12
+    assert abs(mp[f"ndcg_at_{k}"] - 1.0) < 1e-12
+    m0 = oracle.retrieval_metrics([[1000 + i for i in range(n_pred)] for _ in range(Q)], tgt, k)
+    assert all(x == 0.0 for x in m0.values())
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.integers(1, 24), st.integers(1, 8), st.floats(0.2, 3.0), st.integers(0, 2 ** 31 - 1))
+def test_in_batch_softmax_properties(B, d, temp, seed):
+    """In-batch softmax: the chunked form equals the full form; d loss / d S = softmax - onehot has zero row sums, so with
+    IDENTICAL candidates the loss is log B, dQ = 0 and the candidates' gradients add up to zero (the closed form the GPU
+    test checks at B = 65 536)."""
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(B, d, generator=g, dtype=torch.float64, requires_grad=True)
+    c = torch.randn(B, d, generator=g, dtype=torch.float64, requires_grad=True)
+    l0, diag0 = oracle.in_batch_softmax_loss(q, c, temp)
+    l1, diag1 = oracle.in_batch_softmax_loss_chunked(q, c, temp, chunk=5)
+    torch.testing.assert_close(l1, l0, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(diag1, diag0, rtol=1e-12, atol=1e-12)
+    l0.backward()
+    # d loss / d S has zero row sums (softmax - onehot): dQ = (dS) C / T  =>  for c_j all equal to u, dQ = 0
+    same = c.detach()[:1].expand(B, d).clone().requires_grad_(True)
+    q2 = q.detach().clone().requires_grad_(True)
+    l2, _ = oracle.in_batch_softmax_loss(q2, same, temp)
+    l2.backward()
+    assert abs(float(l2.detach()) - float(torch.log(torch.tensor(float(B), dtype=torch.float64)))) < 1e-10
+    assert float(q2.grad.abs().max()) < 1e-12
+    # the candidates' gradients add up to (mean_i q_i - mean_i q_i) = 0 when all candidates are equal
+    assert float(same.grad.sum(dim=0).abs().max()) < 1e-10
