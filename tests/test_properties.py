@@ -278,3 +278,30 @@ def test_in_batch_softmax_properties(B, d, temp, seed):
     assert float(q2.grad.abs().max()) < 1e-12
     # the candidates' gradients add up to (mean_i q_i - mean_i q_i) = 0 when all candidates are equal
     assert float(same.grad.sum(dim=0).abs().max()) < 1e-10
+
+
+@settings(max_examples=50, deadline=None)
+@given(jagged(), st.data())
+def test_kjt_container_matches_the_oracle(j, data):
+    """The host-side KeyedJaggedTensor (CPU container path: offsets, per-key slicing, permute with repeats, split) against
+    the oracle's integer ops on the same jagged data."""
+    import two_tower_recommender_model_b200 as tt
+    F, B, rows, vals, lens = j
+    keys = [f"f{i}" for i in range(F)]
+    kjt = tt.KeyedJaggedTensor.from_lengths_sync(keys, vals, lens)
+    offs = oracle.lengths_to_offsets(lens)
+    assert kjt.stride() == B and torch.equal(kjt.offsets().to(torch.int64), offs.to(torch.int64))
+    assert kjt.length_per_key() == [int(lens[f * B:(f + 1) * B].sum()) for f in range(F)]
+    for f, k in enumerate(keys):
+        jt = kjt[k]
+        assert torch.equal(jt.values(), vals[int(offs[f * B]):int(offs[(f + 1) * B])])
+        assert torch.equal(jt.lengths(), lens[f * B:(f + 1) * B])
+    perm = data.draw(st.lists(st.integers(0, F - 1), min_size=1, max_size=F + 2))
+    p = kjt.permute(perm)
+    ol, ov, _ = oracle.permute_2d_sparse_data(perm, lens.view(F, B), vals)
+    assert p.keys() == [keys[i] for i in perm]
+    assert torch.equal(p.lengths(), ol.reshape(-1)) and torch.equal(p.values(), ov)
+    cut = data.draw(st.integers(0, F))
+    a, b = kjt.split([cut, F - cut])
+    assert a.keys() == keys[:cut] and b.keys() == keys[cut:]
+    assert torch.equal(torch.cat([a.values(), b.values()]), vals) and torch.equal(torch.cat([a.lengths(), b.lengths()]), lens)
