@@ -293,3 +293,133 @@ def test_corpus_sharded_retrieval_world2_gloo():
             p.terminate()
             msgs.append("worker hung")
     assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)
+
+
+# ------------------------------------------------------------------ column-wise sharding (the knob that spreads a table-wise owner's work)
+CW_SPECS = [TableSpec("t_a", 40, 8, ["a"], "sum"), TableSpec("t_e", 20, 8, ["e1", "e2"], "mean"), TableSpec("t_c", 33, 4, ["c"], "sum")]
+CW_KEYS = ["e2", "c", "a", "e1"]
+
+
+def _cw_batch(rank):
+    from helpers import random_kjt
+    rows = {"a": 40, "e1": 20, "e2": 20, "c": 33}
+    return random_kjt(CW_KEYS, [rows[k] for k in CW_KEYS], B, 3, seed=300 + rank)
+
+
+def _worker_column_wise(rank, world, port, errq):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import two_tower_recommender_model_b200 as tt
+        from torch.distributed.optim import _apply_optimizer_in_backward as apply_optimizer_in_backward
+        from torch.distributed._shard.sharded_tensor import ShardedTensor
+        from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
+
+        g = torch.Generator().manual_seed(11)
+        full = {s.name: torch.randn(s.num_embeddings, s.embedding_dim, generator=g) for s in CW_SPECS}
+        cfgs = [tt.EmbeddingBagConfig(name=s.name, embedding_dim=s.embedding_dim, num_embeddings=s.num_embeddings, feature_names=list(s.feature_names),
+                                      pooling=tt.PoolingType.MEAN if s.pooling == "mean" else tt.PoolingType.SUM) for s in CW_SPECS]
+        ebc = tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("meta"))
+        apply_optimizer_in_backward(tt.RowWiseAdagrad, ebc.parameters(), {"lr": LR})
+        holder = nn.ModuleDict({"ebc": ebc})
+        planner = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world, compute_device="cpu"),
+                                              constraints={"t_e": ParameterConstraints(sharding_types=["column_wise"]),
+                                                           "t_a": ParameterConstraints(sharding_types=["table_wise"]),
+                                                           "t_c": ParameterConstraints(sharding_types=["row_wise"])})
+        plan = planner.collective_plan(holder, tt.get_default_sharders(), dist.GroupMember.WORLD)
+        p = plan.plan["ebc"]
+        assert p["t_e"].sharding_type == "column_wise" and p["t_e"].ranks == [0, 1]
+        model = tt.DistributedModelParallel(module=holder, device=torch.device("cpu"), plan=plan,
+                                            sharding_kwargs=dict(local_ebc_factory=OracleLocalEbc, bucketize_fn=oracle_bucketize))
+        sharded = model.module["ebc"]
+        assert sharded.shard_info()["t_e"] == ("column_wise", 0, 20) and sharded._col_info["t_e"] == (4 * rank, 4)
+        # load from FULL tensors: every rank keeps its columns
+        sharded.load_state_dict({f"embedding_bags.{k}.weight": v for k, v in full.items()})
+        torch.testing.assert_close(sharded.tw_ebc.embedding_bags["t_e"].weight.detach(), full["t_e"][:, 4 * rank:4 * rank + 4])
+
+        values, lengths = _cw_batch(rank)
+        kjt = tt.KeyedJaggedTensor.from_lengths_sync(CW_KEYS, values, lengths)
+        kt = sharded(kjt)
+        want = oracle.ebc_forward(CW_SPECS, [full[s.name] for s in CW_SPECS], CW_KEYS, values, lengths)
+        assert kt.keys() == ["a", "e1", "e2", "c"] and kt.length_per_key() == [8, 8, 8, 4]
+        torch.testing.assert_close(kt.values(), want, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(kt["e2"], want[:, 16:24], rtol=1e-6, atol=1e-6)
+
+        # backward: the tables see sum_r grad_r / W; a column-wise table applies row-wise Adagrad PER COLUMN SHARD
+        gout = torch.randn(B, want.shape[1], generator=torch.Generator().manual_seed(70 + rank))
+        (kt.values() * gout).sum().backward()
+        ref = {k: v.clone() for k, v in full.items()}
+        dense = [torch.zeros_like(ref[s.name]) for s in CW_SPECS]
+        for r in range(world):
+            v_r, l_r = _cw_batch(r)
+            g_r = torch.randn(B, want.shape[1], generator=torch.Generator().manual_seed(70 + r))
+            for acc, gr in zip(dense, oracle.ebc_dense_grads(CW_SPECS, CW_KEYS, v_r, l_r, g_r)):
+                acc += gr
+        for s, gr in zip(CW_SPECS, dense):
+            if s.name == "t_e":
+                for j in range(world):
+                    blk = ref[s.name][:, 4 * j:4 * j + 4].clone()
+                    oracle.rowwise_adagrad_dense(blk, torch.zeros(s.num_embeddings), gr[:, 4 * j:4 * j + 4] / world, lr=LR)
+                    ref[s.name][:, 4 * j:4 * j + 4] = blk
+            else:
+                oracle.rowwise_adagrad_dense(ref[s.name], torch.zeros(s.num_embeddings), gr / world, lr=LR)
+
+        # state dict: the column-wise table is a ShardedTensor with column shards; gathered as utils/model_training.py:161-182 does
+        sd = model.state_dict()
+        for s in CW_SPECS:
+            t = sd[f"ebc.embedding_bags.{s.name}.weight"]
+            assert isinstance(t, ShardedTensor) and tuple(t.size()) == (s.num_embeddings, s.embedding_dim)
+            full_t = torch.zeros(t.size()) if rank == 0 else None
+            t.gather(0, full_t)
+            if rank == 0:
+                torch.testing.assert_close(full_t, ref[s.name], rtol=1e-5, atol=1e-6, msg=lambda m: f"{s.name}: {m}")
+        md = sd["ebc.embedding_bags.t_e.weight"].metadata().shards_metadata
+        assert sorted((m.shard_offsets, m.shard_sizes) for m in md) == [([0, 0], [20, 4]), ([0, 4], [20, 4])]
+
+        # resume from the module's OWN sharded state dict (no gather): weights survive a round trip through zeros
+        keep = sharded.tw_ebc.embedding_bags["t_e"].weight.detach().clone()
+        own = sharded.state_dict()
+        own = {k: v for k, v in own.items()}
+        saved = {k: [sh.tensor.clone() for sh in v.local_shards()] for k, v in own.items()}
+        with torch.no_grad():
+            sharded.tw_ebc.embedding_bags["t_e"].weight.zero_()
+        for k, v in own.items():                      # the shards alias the live weights: put the saved values back
+            for sh, t0 in zip(v.local_shards(), saved[k]):
+                sh.tensor.copy_(t0)
+        sharded.load_state_dict(own)
+        torch.testing.assert_close(sharded.tw_ebc.embedding_bags["t_e"].weight.detach(), keep)
+
+        # the optimizer-state checkpoint refuses column-wise tables instead of writing something ambiguous
+        sharded.include_optimizer_state(True)
+        try:
+            sharded.state_dict()
+            raise AssertionError("include_optimizer_state with a column-wise table must raise")
+        except NotImplementedError:
+            pass
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put(f"rank {rank}:\n{traceback.format_exc()}")
+        raise
+
+
+def test_column_wise_sharding_world2_gloo():
+    """A column-wise table (two features, mean pooling) next to a table-wise and a row-wise one: forward equals the unsharded
+    lookup, the fused update equals row-wise Adagrad per column shard on the global batch's gradient / W, the state dict holds
+    column shards that ShardedTensor.gather reassembles, and the module reloads both full tensors and its own shards."""
+    ctx = mp.get_context("spawn")
+    errq = ctx.SimpleQueue()
+    port = 29950 + os.getpid() % 40
+    procs = [ctx.Process(target=_worker_column_wise, args=(r, 2, port, errq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    msgs = []
+    while not errq.empty():
+        msgs.append(errq.get())
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+            msgs.append("worker hung")
+    assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)

@@ -5,7 +5,7 @@ The reference passes no constraints and lets TorchRec's enumerator choose; here
 the plan is a deterministic function of (tables, constraints, topology):
 
 * an explicit ``ParameterConstraints(sharding_types=[...])`` for a table wins
-  (``table_wise`` | ``row_wise`` | ``data_parallel``);
+  (``table_wise`` | ``row_wise`` | ``column_wise``; ``data_parallel`` tables are refused);
 * otherwise tables go table-wise, largest first, each to the rank with the
   fewest bytes so far (greedy balance) -- unless a table (weights + row-wise
   optimizer state) does not fit in one GPU's budget, which makes it row-wise.
@@ -157,11 +157,21 @@ class EmbeddingShardingPlanner:
                     for r in range(W):
                         load[r] += nbytes // W
                     ps = ParameterSharding(want, ranks=list(range(W)), block_size=block)
+                elif want == ShardingType.COLUMN_WISE.value:
+                    # split D over as many ranks as divide it (at most W), least-loaded ranks first: shard j =
+                    # columns [j * D/s, (j+1) * D/s) on ranks[j].  Spreads a table-wise owner's lookup / update of the
+                    # global batch over s ranks; every shard keeps its own row-wise optimizer state,
+                    # as TorchRec's column-wise shards (separate fused tables) do.
+                    s_ = max(d for d in range(1, W + 1) if cfg.embedding_dim % d == 0)
+                    ranks = sorted(sorted(range(W), key=lambda i: (load[i], i))[:s_])
+                    for r in ranks:
+                        load[r] += nbytes // s_
+                    ps = ParameterSharding(want, ranks=ranks)
                 elif want == ShardingType.DATA_PARALLEL.value:
                     raise NotImplementedError("data_parallel embedding tables would need a dense [R,D] gradient "
                                               "all-reduce; use table_wise or row_wise")
                 else:
-                    raise NotImplementedError(f"sharding type {want} is not implemented (table_wise, row_wise are)")
+                    raise NotImplementedError(f"sharding type {want} is not implemented (table_wise, row_wise, column_wise are)")
                 ps.num_embeddings, ps.embedding_dim = cfg.num_embeddings, cfg.embedding_dim
                 tables[cfg.name] = ps
             # report in config order

@@ -25,6 +25,18 @@ def make_row_sharded(local_rows: Optional[torch.Tensor], row_offset: int, global
     return ShardedTensor._init_from_local_shards(shards, *global_shape, process_group=pg)
 
 
+def make_col_sharded(local_cols: Optional[torch.Tensor], col_offset: int, global_shape, pg=None):
+    """Wraps this rank's block of COLUMNS (or nothing) of a ``[R, D]`` table as a ShardedTensor (column-wise sharding);
+    ``ShardedTensor.gather`` places shards by their N-d offsets, so utils/model_training.py:161-182 gathers it unchanged."""
+    shards: List = []
+    if local_cols is not None and local_cols.numel() > 0:
+        rank = dist.get_rank(pg)
+        dev = local_cols.device
+        md = ShardMetadata(shard_offsets=[0, col_offset], shard_sizes=list(local_cols.shape), placement=f"rank:{rank}/{dev}")
+        shards.append(Shard(tensor=local_cols, metadata=md))
+    return ShardedTensor._init_from_local_shards(shards, *global_shape, process_group=pg)
+
+
 def gather_if_sharded(t, dst_rank: int = 0) -> Optional[torch.Tensor]:
     if ShardedTensor is not None and isinstance(t, ShardedTensor):
         full = None

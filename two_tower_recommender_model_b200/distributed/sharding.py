@@ -313,6 +313,9 @@ class ShardedEmbeddingBagCollection(nn.Module):
         self._rw_block: Dict[str, int] = {}
         self._rw_feat_block: Dict[str, int] = {}
         self._shard_info: Dict[str, Tuple[str, int, int]] = {}   # table -> (kind, row offset, local rows)
+        self._col_info: Dict[str, Tuple[int, int]] = {}          # column-wise table -> (first column, columns) held here
+        self._real_feat: Dict[str, str] = {}                     # internal name of a column shard's feature -> KJT key
+        self._cw_pieces: Dict[str, List[str]] = {}               # feature of a column-wise table -> its pieces, shard order
         for c in self._configs:
             ps = plan[c.name]
             if ps.sharding_type == "table_wise":
@@ -327,6 +330,35 @@ class ShardedEmbeddingBagCollection(nn.Module):
                     self._shard_info[c.name] = ("table_wise", 0, c.num_embeddings)
                 else:
                     self._shard_info[c.name] = ("table_wise", 0, 0)
+            elif ps.sharding_type == "column_wise":
+                # Shard j = columns [j*dw, (j+1)*dw) of the table on ranks[j].  Each shard is handled as a table of the
+                # table-wise group whose features carry an internal name ("<feature>@cw<j>"): ids travel to every shard
+                # owner, every owner looks up the global batch in its column slice, the slices return with the table-wise
+                # output exchange and are laid side by side.  Each shard keeps its OWN row-wise optimizer state (the
+                # mean of g^2 runs over the shard's columns), as TorchRec's column-wise shards -- separate fused tables -- do.
+                ranks = list(ps.ranks) if ps.ranks else list(range(W))
+                if len(set(ranks)) != len(ranks) or c.embedding_dim % len(ranks):
+                    raise ValueError(f"column_wise {c.name}: needs distinct ranks whose number divides embedding_dim "
+                                     f"(ranks {ranks}, dim {c.embedding_dim})")
+                if self._peer_exchange:
+                    raise NotImplementedError("column_wise tables use the NCCL exchange; build the module with peer_exchange=False")
+                dw = c.embedding_dim // len(ranks)
+                self._shard_info[c.name] = ("column_wise", 0, 0)
+                for j, owner in enumerate(ranks):
+                    vfs = []
+                    for f in c.feature_names:
+                        vf = f"{f}@cw{j}"
+                        vfs.append(vf)
+                        self._real_feat[vf] = f
+                        self._cw_pieces.setdefault(f, []).append(vf)
+                        self._tw.dest_features[owner].append(vf)
+                        self._tw.feat_dim[vf], self._tw.feat_rows[vf] = dw, c.num_embeddings
+                    if owner == r:
+                        tw_local_cfgs.append(EmbeddingBagConfig(name=c.name, embedding_dim=dw, num_embeddings=c.num_embeddings,
+                                                                feature_names=vfs, pooling=c.pooling,
+                                                                weight_init_min=c.get_weight_init_min(), weight_init_max=c.get_weight_init_max()))
+                        self._shard_info[c.name] = ("column_wise", 0, c.num_embeddings)
+                        self._col_info[c.name] = (j * dw, dw)
             elif ps.sharding_type == "row_wise":
                 block = ps.block_size or -(-c.num_embeddings // W)
                 self._rw_block[c.name] = block
@@ -405,7 +437,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
             return self._dist_dense_ids_rw(grp, keys, dense[0], B)
         if self._peer_exchange and getattr(kjt, "_values_padded", False) and kjt.values().is_cuda:
             return self._dist_kjt_gather(grp, kjt, B)
-        sub = kjt.permute([keys.index(f) for f in grp.features])
+        sub = kjt.permute([keys.index(self._real_feat.get(f, f)) for f in grp.features])
         lengths, values = sub.lengths(), sub.values()
         if grp.kind == "row_wise":
             F = len(grp.features)
@@ -455,7 +487,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
         key-major KJT over the global batch is built by ``tt_kjt_from_columns`` where the ids land."""
         W, pg = self._world, self._pg
         n_local = len(grp.dest_features[self._rank])
-        order = [keys.index(f) for f in grp.features]
+        order = [keys.index(self._real_feat.get(f, f)) for f in grp.features]
         if order == list(range(ids.shape[0])):
             send = ids
         else:
@@ -633,7 +665,10 @@ class ShardedEmbeddingBagCollection(nn.Module):
                 cols[f] = col
                 c0 += d
         whole, self._whole = self._whole, None
-        values = whole if whole is not None else torch.cat([cols[f] for f in self._out_features], dim=1)
+        if whole is None:
+            # a column-wise table's feature is the row of its shards' slices, in shard order
+            parts = [cols[p] for f in self._out_features for p in self._cw_pieces.get(f, (f,))]
+        values = whole if whole is not None else torch.cat(parts, dim=1)
         return KeyedTensor(keys=self._out_features, length_per_key=self._out_dims, values=values)
 
     def _group_forward_peer(self, grp: _Group, kjt, ebc, B: int, scatter_add: bool) -> Dict[str, torch.Tensor]:
@@ -672,7 +707,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
         kind, _off, rows = self._shard_info[name]
         if rows == 0:
             return None
-        local = self.tw_ebc if kind == "table_wise" else self.rw_ebc
+        local = self.rw_ebc if kind == "row_wise" else self.tw_ebc
         return local.embedding_bags[name].weight.detach()[:rows]
 
     def include_optimizer_state(self, on: bool = True) -> "ShardedEmbeddingBagCollection":
@@ -683,17 +718,24 @@ class ShardedEmbeddingBagCollection(nn.Module):
         return self
 
     def _local_ebc_of(self, name: str):
-        return self.tw_ebc if self._shard_info[name][0] == "table_wise" else self.rw_ebc
+        return self.rw_ebc if self._shard_info[name][0] == "row_wise" else self.tw_ebc
 
     def state_dict(self, *args, destination=None, prefix: str = "", keep_vars: bool = False):
         from .. import _native as N
-        from .sharded_tensor import make_row_sharded
+        from .sharded_tensor import make_col_sharded, make_row_sharded
         destination = {} if destination is None else destination
         for c in self._configs:
-            _kind, off, _rows = self._shard_info[c.name]
+            kind, off, _rows = self._shard_info[c.name]
+            if kind == "column_wise":
+                destination[f"{prefix}embedding_bags.{c.name}.weight"] = make_col_sharded(
+                    self._local_weight(c.name), self._col_info.get(c.name, (0, 0))[0], (c.num_embeddings, c.embedding_dim), self._pg)
+                continue
             destination[f"{prefix}embedding_bags.{c.name}.weight"] = make_row_sharded(
                 self._local_weight(c.name), off, (c.num_embeddings, c.embedding_dim), self._pg)
         if getattr(self, "_state_dict_with_optimizer", False):
+            if any(k == "column_wise" for k, _o, _r in self._shard_info.values()):
+                raise NotImplementedError("include_optimizer_state: every column shard keeps its own row-wise state, which has no "
+                                          "place under the unsharded key names; checkpoint column-wise tables weights-only")
             step = 0
             for c in self._configs:
                 _kind, off, rows = self._shard_info[c.name]
@@ -712,6 +754,18 @@ class ShardedEmbeddingBagCollection(nn.Module):
                     step = max(step, l.fused_step())
             destination[f"{prefix}fused_optimizer_step"] = torch.tensor(float(step), dtype=torch.float32)
         return destination
+
+    def _cols_from(self, src, c0: int, cols: int, name: str) -> torch.Tensor:
+        """This rank's columns [c0, c0 + cols) of a column-wise table out of a checkpoint entry (full tensor, or the
+        ShardedTensor this module itself writes)."""
+        from .sharded_tensor import ShardedTensor
+        if ShardedTensor is not None and isinstance(src, ShardedTensor):
+            for sh in src.local_shards():
+                if sh.metadata.shard_offsets[1] == c0 and sh.metadata.shard_sizes[1] == cols:
+                    return sh.tensor
+            raise RuntimeError(f"{name}: the ShardedTensor in the checkpoint is split differently from this module's plan "
+                               f"(need columns [{c0}, {c0 + cols}) on this rank); gather it to a full tensor first and load that")
+        return src[:, c0:c0 + cols]
 
     def _rows_from(self, src, off: int, rows: int, name: str) -> torch.Tensor:
         """This rank's rows [off, off + rows) out of a checkpoint entry: a full tensor, or the ShardedTensor this
@@ -736,7 +790,12 @@ class ShardedEmbeddingBagCollection(nn.Module):
                     missing_keys.append(key)
                 continue
             w = self._local_weight(c.name)
-            _kind, off, rows = self._shard_info[c.name]
+            kind, off, rows = self._shard_info[c.name]
+            if kind == "column_wise":
+                if w is not None:
+                    with torch.no_grad():
+                        w.copy_(self._cols_from(state_dict[key], *self._col_info[c.name], key).to(w.device))
+                continue
             if w is not None:
                 with torch.no_grad():
                     w.copy_(self._rows_from(state_dict[key], off, rows, key).to(w.device))
