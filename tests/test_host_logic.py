@@ -117,6 +117,16 @@ def test_planner():
     plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=4, hbm_cap=8 * 2 ** 30)).plan(big)
     assert plan.plan["ebc"]["t_big"].sharding_type == "row_wise"
     assert "t_big" in str(plan)
+    # column-wise: as many shards as divide D (at most W), on distinct ranks, least-loaded first; data-parallel tables are refused
+    cw = torch.nn.ModuleDict({"ebc": tt.EmbeddingBagCollection(tables=[
+        tt.EmbeddingBagConfig(name="t_x", embedding_dim=36, num_embeddings=5000, feature_names=["x"]), mk("t_y", 100)], device=torch.device("meta"))})
+    plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=8), constraints={"t_x": ParameterConstraints(sharding_types=["column_wise"]),
+                                                                                        "t_y": ParameterConstraints(sharding_types=["column_wise"])}).plan(cw)
+    px, py = plan.plan["ebc"]["t_x"], plan.plan["ebc"]["t_y"]
+    assert px.sharding_type == "column_wise" and px.ranks == [0, 1, 2, 3, 4, 5]           # 36 = 6 x 6; 7 and 8 do not divide it
+    assert py.ranks == list(range(8)) and 36 % len(px.ranks) == 0 and 64 % len(py.ranks) == 0
+    with pytest.raises(NotImplementedError):
+        tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=2), constraints={"t_x": ParameterConstraints(sharding_types=["data_parallel"])}).plan(cw)
 
 
 def test_shim_resolves_reference_imports():
