@@ -1,0 +1,85 @@
+"""Optimizer state inside the checkpoint, host logic on CPU: ``include_optimizer_state(True)`` puts the
+fused row-wise state under ``embedding_bags.<table>.sum`` (+ ``fused_optimizer_step``) in ``state_dict()``; a module that
+loads it takes the SAME next step as the one that kept training, one that loads the reference's weights-only format
+(utils/model_training.py:161-189) does not.  The device work (pooled lookup + fused row-wise Adagrad in the backward) is
+replaced by the oracle stand-in of tests/test_reference_boundary.py; the kernels are held to the oracle on the GPU."""
+import os
+import sys
+
+import pytest
+import torch
+from torch.distributed.optim import _apply_optimizer_in_backward as apply_optimizer_in_backward
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import two_tower_recommender_model_b200 as tt  # noqa: E402
+from helpers import random_kjt  # noqa: E402
+from test_reference_boundary import _OracleLookup  # noqa: E402
+
+KEYS, ROWS, DIM, B, LR = ["u", "i"], [23, 31], 8, 16, 0.1
+
+
+@pytest.fixture()
+def oracle_device_work(monkeypatch):
+    from two_tower_recommender_model_b200 import _native as N
+    from two_tower_recommender_model_b200.modules import embedding_modules
+    monkeypatch.setattr(embedding_modules, "EbcLookup", _OracleLookup)
+    monkeypatch.setattr(N, "require_cuda", lambda t, name: None)
+
+
+def _ebc(seed):
+    torch.manual_seed(seed)
+    cfgs = [tt.EmbeddingBagConfig(name=f"t_{k}", embedding_dim=DIM, num_embeddings=ROWS[j], feature_names=[k]) for j, k in enumerate(KEYS)]
+    ebc = tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("cpu"))
+    apply_optimizer_in_backward(tt.RowWiseAdagrad, ebc.parameters(), {"lr": LR})
+    return ebc
+
+
+def _step(ebc, s):
+    v, l = random_kjt(KEYS, ROWS, B, 3, seed=40 + s, dup_pool=6)          # a small id pool: rows are hit in several steps
+    out = ebc(tt.KeyedJaggedTensor.from_lengths_sync(KEYS, v, l)).values()
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(90 + s))
+    (out * g).sum().backward()
+
+
+def test_fused_optimizer_state_travels_in_the_state_dict(oracle_device_work):
+    a = _ebc(0)
+    for s in range(2):
+        _step(a, s)
+    plain = a.state_dict()
+    assert set(plain) == {"embedding_bags.t_u.weight", "embedding_bags.t_i.weight"}          # the reference's format
+    full = {k: v.clone() for k, v in a.include_optimizer_state(True).state_dict().items()}
+    assert set(full) == set(plain) | {"embedding_bags.t_u.sum", "embedding_bags.t_i.sum", "fused_optimizer_step"}
+    assert float(full["embedding_bags.t_u.sum"].max()) > 0 and full["embedding_bags.t_u.sum"].shape == (ROWS[0],)
+
+    b = _ebc(1)                      # resumes WITH the optimizer state
+    b.load_state_dict(full)
+    c = _ebc(2)                      # resumes from a weights-only checkpoint: the accumulators restart at zero
+    c.load_state_dict({k: v.clone() for k, v in plain.items()})
+    for m in (a, b, c):
+        _step(m, 2)
+    for k in plain:
+        assert torch.equal(a.state_dict()[k], b.state_dict()[k]), k
+    for t in ("t_u", "t_i"):
+        assert torch.equal(a.fused_optimizer_state()[t]["sum"], b.fused_optimizer_state()[t]["sum"])
+    # the weights-only resume takes a different (larger: sqrt(sum) restarted) step on rows both runs had already visited
+    assert not torch.equal(a.state_dict()["embedding_bags.t_u.weight"], c.state_dict()["embedding_bags.t_u.weight"])
+
+
+def test_optimizer_state_keys_under_the_two_tower_prefix(oracle_device_work):
+    """Through the TwoTower wrapper the entries sit under ``ebc.`` like the weights; a strict load of either format works."""
+    ebc = _ebc(3)
+    tower = tt.TwoTower(ebc, [8, 4], device=torch.device("cpu"))
+    _step(tower.ebc, 0)
+    tower.ebc.include_optimizer_state(True)
+    sd = tower.state_dict()
+    assert {"ebc.embedding_bags.t_u.sum", "ebc.embedding_bags.t_i.sum", "ebc.fused_optimizer_step"} <= set(sd)
+    other = tt.TwoTower(_ebc(4), [8, 4], device=torch.device("cpu"))
+    res = other.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(other.ebc.fused_optimizer_state()["t_i"]["sum"], tower.ebc.fused_optimizer_state()["t_i"]["sum"])
+    weights_only = {k: v for k, v in sd.items() if k.endswith(".weight") or k.endswith(".bias")}
+    res = tt.TwoTower(_ebc(5), [8, 4], device=torch.device("cpu")).load_state_dict(weights_only, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys

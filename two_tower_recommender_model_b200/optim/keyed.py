@@ -40,3 +40,6 @@ class KeyedOptimizerWrapper(KeyedOptimizer):
 
     def load_state_dict(self, state_dict: Mapping[str, Any]) -> None:
         self._optimizer.load_state_dict(state_dict)
+        # torch rebuilds param_groups / state on load: keep reading the live objects (utils/model_training.py:303 prints
+        # ``pipeline._optimizer.param_groups[i]["lr"]``, schedulers write it)
+        self.state, self.param_groups = self._optimizer.state, self._optimizer.param_groups
