@@ -187,3 +187,41 @@ def test_planner_prefers_row_wise_when_ranks_outnumber_tables():
     assert all(st == "table_wise" for st, _ in small.values())
     forced = plan_for(8, [10_000_000, 10_000_000], {"t0": ParameterConstraints(sharding_types=["table_wise"])})
     assert forced["t0"][0] == "table_wise" and forced["t1"][0] == "row_wise"
+
+
+def test_c_host_links_and_calls_the_library(tmp_path):
+    """A plain-C host (no Python, no torch) includes include/tt_b200.h, links libtt_b200.so and calls the entry points that
+    need no device: ABI version, build architecture, workspace queries, and the argument check of a compute entry point
+    (a NULL plan must come back as an error code with a message, not a crash).  This is the binding INTEGRATION.md section 3
+    shows for a C / C++ host."""
+    import shutil
+    import subprocess
+    from two_tower_recommender_model_b200 import _native as N
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    N.load()
+    lib = N.library_path()
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "tt_b200.h"
+int main(void) {
+  if (tt_abi_version() != TT_ABI_VERSION) { printf("abi %d != %d\n", tt_abi_version(), TT_ABI_VERSION); return 1; }
+  if (strcmp(tt_build_arch(), "sm_100a") != 0) { printf("arch %s\n", tt_build_arch()); return 2; }
+  if (tt_kjt_offsets_workspace_bytes(1 << 20) == 0 || tt_ebc_backward_workspace_bytes(131072) == 0 ||
+      tt_topk_workspace_bytes(1024, 100000, 100) == 0) { printf("workspace query returned 0\n"); return 3; }
+  int rc = tt_ebc_forward(NULL, NULL, NULL, NULL, NULL);
+  if (rc >= 0) { printf("NULL plan accepted (rc %d)\n", rc); return 4; }
+  const char* msg = tt_last_error();
+  if (msg == NULL || msg[0] == 0) { printf("no error text\n"); return 5; }
+  printf("ok abi=%d arch=%s rc=%d msg=%s\n", tt_abi_version(), tt_build_arch(), rc, msg);
+  return 0;
+}
+''')
+    exe = tmp_path / "host"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    lib, "-Wl,-rpath," + os.path.dirname(lib)], check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith(f"ok abi={N.TT_ABI_VERSION} arch=sm_100a")
