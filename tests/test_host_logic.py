@@ -225,3 +225,39 @@ int main(void) {
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.startswith(f"ok abi={N.TT_ABI_VERSION} arch=sm_100a")
+
+
+def test_entry_points_survive_null_and_zero_arguments():
+    """Every entry point of the C ABI called with NULL pointers and zero sizes (in a child process: a crash must not take
+    pytest down): workspace queries return a size, compute entry points come back with an error code and a message or with
+    'nothing to do' -- none may crash.  (Found this way: tt_topk_workspace_bytes(0, ..) and
+    tt_gemm_bf16_splitk_workspace_bytes(0, ..) divided by zero, i.e. an EMPTY query batch killed the process.)"""
+    import json
+    import subprocess
+    import sys
+    child = r'''
+import ctypes, json, sys
+sys.path.insert(0, %r)
+from two_tower_recommender_model_b200 import _native as N
+lib = N.load()
+for name, (res, args) in N.SIGNATURES.items():
+    if not args:
+        continue
+    vals = [0.0 if a is ctypes.c_float else (None if (a in (ctypes.c_void_p, ctypes.c_char_p) or "LP_" in a.__name__) else 0) for a in args]
+    print("CALL", name, flush=True)
+    rc = getattr(lib, name)(*vals)
+    msg = lib.tt_last_error()
+    print("DONE", json.dumps({"name": name, "rc": int(rc), "msg": msg.decode() if msg else ""}), flush=True)
+''' % ROOT
+    p = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=600)
+    lines = p.stdout.strip().splitlines()
+    assert p.returncode == 0, f"crashed in {lines[-1] if lines else '?'}: rc {p.returncode}\n{p.stderr[-400:]}"
+    done = [json.loads(l[5:]) for l in lines if l.startswith("DONE ")]
+    assert len(done) == sum(1 for _r, a in N.SIGNATURES.values() if a)
+    for d in done:
+        if d["name"].endswith("_workspace_bytes"):
+            assert d["rc"] > 0, d
+        elif d["name"].startswith("tt_set_") or d["name"] == "tt_adam_flat":
+            assert d["rc"] == 0, d                     # mode setters; Adam over zero elements is a no-op
+        else:
+            assert d["rc"] < 0 and d["msg"], d         # bad arguments are reported, with text

@@ -426,7 +426,8 @@ static int gemm_dispatch_mn(int bn, const CUtensorMap& ta, const CUtensorMap& tb
 }
 
 static int splitk_splits(int64_t M, int64_t N, int64_t K, int bn) {
-  const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
+  int64_t tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
+  if (tiles < 1) tiles = 1;                                     // an empty output (M or N == 0) must not divide by zero
   const int64_t total_kb = (K + kBK - 1) / kBK;
   int64_t want = (kNumSMs + tiles - 1) / tiles;          // one wave of CTAs (fewer partials to reduce)
   if (want > total_kb / 4) want = total_kb / 4;          // at least 4 K-blocks per slice

@@ -583,6 +583,7 @@ static size_t score_topk_smem() {
 
 static int topk_splits(int64_t Q, int64_t N) {
   int64_t qtiles = (Q + kTkTile - 1) / kTkTile;
+  if (qtiles < 1) qtiles = 1;                                   // Q == 0 (an empty query batch) must not divide by zero
   int64_t want = (2 * kNumSMs + qtiles - 1) / qtiles;
   int64_t max_splits = (N + 4 * kTkTile - 1) / (4 * kTkTile);  // at least 256 items per split
   if (want > max_splits) want = max_splits;
