@@ -261,3 +261,12 @@ for name, (res, args) in N.SIGNATURES.items():
             assert d["rc"] == 0, d                     # mode setters; Adam over zero elements is a no-op
         else:
             assert d["rc"] < 0 and d["msg"], d         # bad arguments are reported, with text
+
+
+def test_retrieval_with_an_empty_query_batch():
+    """No queries -> empty [0, k] results, no kernel launch (so this runs without a GPU)."""
+    items = torch.randn(50, 8)
+    for index in (tt.BruteForceIndex(items), tt.CorpusShardedIndex(items, first_id=0)):
+        s, i = index.search(torch.zeros(0, 8), 10)
+        assert s.shape == (0, 10) and i.shape == (0, 10) and s.dtype == torch.float32 and i.dtype == torch.int64
+

@@ -144,6 +144,8 @@ class BruteForceIndex:
         n_items = self._items.shape[0] if self._items is not None else self._items_bf16.shape[0]
         q = query_embeddings.to(dev).float().contiguous()
         k = min(num_results, n_items)
+        if q.shape[0] == 0:            # an empty query batch: nothing to launch
+            return (torch.empty(0, k, dtype=torch.float32, device=dev), torch.empty(0, k, dtype=torch.int64, device=dev))
         s_out, i_out = [], []
         for s in range(0, q.shape[0], query_chunk):
             sc, ix = score_topk(q[s:s + query_chunk], self._items, k, precision=self._precision, items_bf16=self._items_bf16)
@@ -192,6 +194,8 @@ class CorpusShardedIndex:
         W = dist.get_world_size(pg) if dist.is_available() and dist.is_initialized() else 1
         q = query_embeddings.to(self._items.device).float().contiguous()
         Q, k = q.shape[0], int(num_results)
+        if Q == 0:                     # the same on every rank: nothing to exchange
+            return (torch.empty(0, k, dtype=torch.float32, device=q.device), torch.empty(0, k, dtype=torch.int64, device=q.device))
         if W > 1:
             allq = q.new_empty(W * Q, q.shape[1])
             dist.all_gather_into_tensor(allq, q, group=pg)
