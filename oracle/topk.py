@@ -33,7 +33,7 @@ def retrieval_metrics(pred: Sequence[Sequence[int]], targets: Sequence[Sequence[
     as called at 04_evaluate_retrieval.py:202-210: per-row precision_at_k /
     recall_at_k / ndcg_at_k over the first ``k`` retrieved ids, then the mean.
     (mlflow semantics: precision = hits / len(retrieved[:k]); recall = hits /
-    len(set(targets)); ndcg with binary relevance, ideal = all targets first.)"""
+    len(set(targets)); ndcg with binary relevance, ideal = all targets first, cut at the length of the retrieved list.)"""
     import math
     P: List[float] = []
     R: List[float] = []
@@ -46,7 +46,9 @@ def retrieval_metrics(pred: Sequence[Sequence[int]], targets: Sequence[Sequence[
         P.append(nh / len(p) if p else 0.0)
         R.append(nh / len(tset) if tset else 0.0)
         dcg = sum(h / math.log2(i + 2) for i, h in enumerate(hits))
-        ideal = sum(1.0 / math.log2(i + 2) for i in range(min(len(tset), k)))
+        # a list shorter than k: mlflow hands sklearn's ndcg_score k = len(retrieved[:k]), so the ideal ranking is cut at the
+        # number of ids actually retrieved (the reference always asks for, and gets, k = 100 results: 04_evaluate_retrieval.py:134-141)
+        ideal = sum(1.0 / math.log2(i + 2) for i in range(min(len(tset), len(p))))
         N.append(dcg / ideal if ideal > 0 else 0.0)
     n = max(len(P), 1)
     return {f"precision_at_{k}": sum(P) / n, f"recall_at_{k}": sum(R) / n, f"ndcg_at_{k}": sum(N) / n}

@@ -305,3 +305,23 @@ def test_kjt_container_matches_the_oracle(j, data):
     a, b = kjt.split([cut, F - cut])
     assert a.keys() == keys[:cut] and b.keys() == keys[cut:]
     assert torch.equal(torch.cat([a.values(), b.values()]), vals) and torch.equal(torch.cat([a.lengths(), b.lengths()]), lens)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 7), st.integers(1, 15), st.integers(1, 15), st.integers(0, 2 ** 31 - 1))
+def test_product_retrieval_metrics_match_the_oracle(Q, n_pred, k, seed):
+    """tt.retrieval_metrics (tensor form; torch ops only, so it runs here) against the oracle's per-row restatement of
+    mlflow's retriever metrics (04_evaluate_retrieval.py:202-226): duplicates in the targets, k larger / smaller than the
+    list, rows without a hit."""
+    import two_tower_recommender_model_b200 as tt
+    g = torch.Generator().manual_seed(seed)
+    pred = torch.stack([torch.randperm(30, generator=g)[:n_pred] for _ in range(Q)])
+    tgt = []
+    for _ in range(Q):
+        t = torch.randint(0, 30, (int(torch.randint(1, 9, (1,), generator=g)),), generator=g).tolist()   # may repeat ids
+        tgt.append(t)
+    got = tt.retrieval_metrics(pred, tgt, k)
+    want = oracle.retrieval_metrics(pred.tolist(), tgt, k)
+    assert set(got) == set(want)
+    for key in want:
+        assert abs(got[key] - want[key]) < 1e-5, (key, got[key], want[key])
