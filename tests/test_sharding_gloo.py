@@ -423,3 +423,89 @@ def test_column_wise_sharding_world2_gloo():
             p.terminate()
             msgs.append("worker hung")
     assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)
+
+
+# ------------------------------------------------------------------ corpus embedding against sharded tables + both multi-rank retrieval layouts
+def _worker_sharded_retrieval(rank, world, port, sharding, errq):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import two_tower_recommender_model_b200 as tt
+        from two_tower_recommender_model_b200 import _native as N, retrieval
+        from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
+        from two_tower_recommender_model_b200.modules import mlp
+        # device work -> oracle / plain torch (tests only)
+        mlp.linear_act = lambda x, w, b, relu: torch.relu(torch.nn.functional.linear(x, w, b)) if relu else torch.nn.functional.linear(x, w, b)
+        N.require_cuda = lambda t, name: None
+
+        def topk(q, items, k, item_index_base=0, precision="fp32", items_bf16=None):
+            s, i = oracle.exact_topk(q, items, k)
+            return s, i + item_index_base
+        retrieval.score_topk = topk
+
+        cat, emb, dim, layers = ["user_id", "product_id"], [13, 37], 8, [8, 4]      # 37 items: not a multiple of the world size
+        specs = [TableSpec(f"t_{c}", emb[i], dim, [c]) for i, c in enumerate(cat)]
+        orc = oracle.OracleTwoTower(specs, layers, loss="bce", seed=21)
+        ebc = tt.EmbeddingBagCollection(tables=[tt.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=dim, num_embeddings=emb[i], feature_names=[c])
+                                                for i, c in enumerate(cat)], device=torch.device("meta"))
+        tower = tt.TwoTower(ebc, layers, device=torch.device("cpu"))
+        plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world, compute_device="cpu"),
+                                           constraints={f"t_{c}": ParameterConstraints(sharding_types=[sharding]) for c in cat}
+                                           ).collective_plan(tower, tt.get_default_sharders(), dist.GroupMember.WORLD)
+        model = tt.DistributedModelParallel(module=tower, device=torch.device("cpu"), plan=plan,
+                                            sharding_kwargs=dict(local_ebc_factory=OracleLocalEbc, bucketize_fn=oracle_bucketize))
+        model.load_state_dict(orc.torchrec_state_dict())
+        tw = model.module
+        tw.eval()
+        with torch.no_grad():
+            iv = torch.arange(emb[1])
+            il = torch.cat([torch.zeros(emb[1], dtype=torch.int32), torch.ones(emb[1], dtype=torch.int32)])
+            _, items_ref = orc.forward(cat, iv, il)
+            uv = torch.arange(emb[0])
+            ul = torch.cat([torch.ones(emb[0], dtype=torch.int32), torch.zeros(emb[0], dtype=torch.int32)])
+            users_ref, _ = orc.forward(cat, uv, ul)
+        per = -(-emb[1] // world)
+        for chunk in (5, 7, 19, 1 << 18):                 # chunks that do and do not divide a rank's share
+            local, first = tt.embed_corpus_sharded(tw, cat, "product_id", emb[1], torch.device("cpu"), chunk=chunk)
+            lo, hi = rank * per, min((rank + 1) * per, emb[1])
+            assert first == lo and local.shape == (hi - lo, layers[-1]), (chunk, local.shape)
+            torch.testing.assert_close(local, items_ref[lo:hi], rtol=1e-5, atol=1e-6, msg=lambda m: f"chunk {chunk}: {m}")
+        # every rank asks for ITS block of users (6 + 6 of the 13, the last one left out): same count on both ranks
+        q = users_ref[rank * 6:(rank + 1) * 6]
+        ws, wi = oracle.exact_topk(q, items_ref, 10)
+        gathered = tt.BruteForceIndex.from_sharded(local, precision="fp32")           # corpus all-gathered, queries sharded
+        s1, i1 = gathered.search(q, 10)
+        kept = tt.CorpusShardedIndex(local, first_id=first)                           # corpus stays sharded, lists merged
+        s2, i2 = kept.search(q, 10)
+        for s_, i_ in ((s1, i1), (s2, i2)):
+            torch.testing.assert_close(s_, ws, rtol=1e-5, atol=1e-6)
+            assert float((i_ == wi).float().mean()) >= 0.98                           # near-ties may swap under another summation order
+        assert torch.equal(i1, i2)
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put(f"rank {rank}:\n{traceback.format_exc()}")
+        raise
+
+
+@pytest.mark.parametrize("sharding", ["table_wise", "row_wise"])
+def test_sharded_corpus_embedding_and_retrieval_world2_gloo(sharding):
+    """embed_corpus_sharded against table-wise / row-wise sharded tables (a corpus size the world size does not divide, chunk
+    sizes that do not divide a rank's share), then both multi-rank retrieval layouts -- BruteForceIndex.from_sharded and
+    CorpusShardedIndex -- against the oracle's towers and exact top-k."""
+    ctx = mp.get_context("spawn")
+    errq = ctx.SimpleQueue()
+    port = 30010 + os.getpid() % 50 + (0 if sharding == "table_wise" else 60)
+    procs = [ctx.Process(target=_worker_sharded_retrieval, args=(r, 2, port, sharding, errq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    msgs = []
+    while not errq.empty():
+        msgs.append(errq.get())
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+            msgs.append("worker hung")
+    assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)
