@@ -509,3 +509,121 @@ def test_sharded_corpus_embedding_and_retrieval_world2_gloo(sharding):
             p.terminate()
             msgs.append("worker hung")
     assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)
+
+
+# ------------------------------------------------------------------ sharded checkpoint with the fused optimizer state
+def _worker_sharded_resume(rank, world, port, errq):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import two_tower_recommender_model_b200 as tt
+        from torch.distributed.optim import _apply_optimizer_in_backward as apply_optimizer_in_backward
+        from torch.distributed._shard.sharded_tensor import ShardedTensor
+        from two_tower_recommender_model_b200 import _native as N
+        from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
+        from two_tower_recommender_model_b200.modules import embedding_modules
+        from test_reference_boundary import _OracleLookup as _FusedOracleLookup
+        # the REAL local EmbeddingBagCollection (its state_dict / optimizer-state bookkeeping is what is under test);
+        # only its device entry point is replaced by the oracle
+        embedding_modules.EbcLookup = _FusedOracleLookup
+        N.require_cuda = lambda t, name: None
+        keys, rows, dim = ["a", "c"], [40, 33], 8
+
+        def build(seed):
+            torch.manual_seed(seed)
+            cfgs = [tt.EmbeddingBagConfig(name=f"t_{k}", embedding_dim=dim, num_embeddings=rows[j], feature_names=[k]) for j, k in enumerate(keys)]
+            ebc = tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("meta"))
+            apply_optimizer_in_backward(tt.RowWiseAdagrad, ebc.parameters(), {"lr": LR})
+            holder = nn.ModuleDict({"ebc": ebc})
+            plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world, compute_device="cpu"),
+                                               constraints={"t_a": ParameterConstraints(sharding_types=["table_wise"]),
+                                                            "t_c": ParameterConstraints(sharding_types=["row_wise"])}
+                                               ).collective_plan(holder, tt.get_default_sharders(), dist.GroupMember.WORLD)
+            model = tt.DistributedModelParallel(module=holder, device=torch.device("cpu"), plan=plan,
+                                                sharding_kwargs=dict(bucketize_fn=oracle_bucketize))
+            return model.module["ebc"]
+
+        def step(m, s):
+            from helpers import random_kjt
+            v, l = random_kjt(keys, rows, B, 3, seed=500 + 10 * s + rank, dup_pool=30)
+            out = m(tt.KeyedJaggedTensor.from_lengths_sync(keys, v, l)).values()
+            g = torch.randn(out.shape, generator=torch.Generator().manual_seed(600 + 10 * s + rank))
+            (out * g).sum().backward()
+
+        def local_state(m):
+            out = {}
+            for local in (m.tw_ebc, m.rw_ebc):
+                if local is not None:
+                    for name, bag in local.embedding_bags.items():
+                        out[name + ".weight"] = bag.weight.detach().clone()
+                        out[name + ".sum"] = local.fused_optimizer_state()[name]["sum"].clone()
+            return out
+
+        a = build(0)
+        for s in range(2):
+            step(a, s)
+        plain = a.state_dict()
+        assert set(plain) == {"embedding_bags.t_a.weight", "embedding_bags.t_c.weight"}
+        full = a.include_optimizer_state(True).state_dict()
+        assert set(full) == set(plain) | {"embedding_bags.t_a.sum", "embedding_bags.t_c.sum", "fused_optimizer_step"}
+        assert isinstance(full["embedding_bags.t_c.sum"], ShardedTensor) and tuple(full["embedding_bags.t_c.sum"].size()) == (33,)
+        # the shards alias the live tensors: a checkpoint writer would serialise them here; keep copies instead
+        frozen = {k: ([sh.tensor.clone() for sh in v.local_shards()] if isinstance(v, ShardedTensor) else v.clone()) for k, v in full.items()}
+        b = build(1)                           # resumes from the sharded checkpoint, no gather
+        for k, v in full.items():              # hand b a checkpoint whose shards hold the frozen values
+            if isinstance(v, ShardedTensor):
+                for sh, t0 in zip(v.local_shards(), frozen[k]):
+                    assert torch.equal(sh.tensor, t0)
+        b.load_state_dict(full)
+        # gathered (full-tensor) form of the same checkpoint, as utils/model_training.py:161-182 writes it, weights + state
+        gathered = {}
+        for k, v in full.items():
+            if isinstance(v, ShardedTensor):
+                out = torch.zeros(v.size()) if rank == 0 else None
+                v.gather(0, out)
+                lst = [out]
+                dist.broadcast_object_list(lst, src=0)
+                gathered[k] = lst[0]
+            else:
+                gathered[k] = v
+        c = build(2)
+        c.load_state_dict(gathered)
+        d = build(3)                           # weights only: the accumulators restart
+        d.load_state_dict({k: v for k, v in gathered.items() if k.endswith(".weight")})
+        for m in (a, b, c, d):
+            step(m, 2)
+        sa, sb, sc, sd_ = local_state(a), local_state(b), local_state(c), local_state(d)
+        assert sa, "every rank holds a row-wise shard"
+        for k in sa:
+            assert torch.equal(sa[k], sb[k]), f"own-shard resume differs at {k}"
+            assert torch.equal(sa[k], sc[k]), f"gathered resume differs at {k}"
+        differs = torch.tensor([1.0 if any(not torch.equal(sa[k], sd_[k]) for k in sa if k.endswith(".weight")) else 0.0])
+        dist.all_reduce(differs, op=dist.ReduceOp.MAX)          # a rank whose shard saw no repeated row cannot tell
+        assert float(differs) == 1.0, "the weights-only resume took the same step: the accumulators did not matter?"
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put(f"rank {rank}:\n{traceback.format_exc()}")
+        raise
+
+
+def test_sharded_checkpoint_with_optimizer_state_world2_gloo():
+    """Two ranks, one table-wise and one row-wise table: after include_optimizer_state(True) the sharded state dict carries
+    the fused row-wise accumulators as ShardedTensors; a module resumed from its own shards, and one resumed from the gathered
+    full tensors, take the same third step as the module that kept training; a weights-only resume does not."""
+    ctx = mp.get_context("spawn")
+    errq = ctx.SimpleQueue()
+    port = 30140 + os.getpid() % 50
+    procs = [ctx.Process(target=_worker_sharded_resume, args=(r, 2, port, errq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    msgs = []
+    while not errq.empty():
+        msgs.append(errq.get())
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+            msgs.append("worker hung")
+    assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)
