@@ -26,12 +26,17 @@ class OracleTwoTower(nn.Module):
         query_features: Optional[List[str]] = None,
         candidate_features: Optional[List[str]] = None, seed: int = 0,
         dense_optimizer: str = "adam", dense_index: Optional[int] = None, dense_dim: int = 0,
+        column_blocks: Optional[Dict[str, int]] = None,
     ) -> None:
         """``layer_sizes`` may be ``[user_layers, item_layers]`` and ``dense_index`` / ``dense_dim`` concatenate
         ``dense[:, :dense_index]`` / ``dense[:, dense_index:dense_dim]`` to the tower inputs, as the Ray-Tune variant of
         the reference does (/root/reference/ray_tune_optuna_tuning_alex_test.py:227-306)."""
         super().__init__()
         self.dense_index, self.dense_dim = dense_index, dense_dim
+        # column-wise sharded tables (TorchRec: each column shard is its own fused table): row-wise Adagrad runs per block of
+        # D / n columns, each block with its own per-row accumulator -- {table name: number of column shards}
+        self.column_blocks = dict(column_blocks or {})
+        self.column_state: Dict[str, torch.Tensor] = {}
         self.tables = list(tables)
         self.loss_kind = loss
         self.sparse_optimizer = sparse_optimizer
@@ -152,6 +157,19 @@ class OracleTwoTower(nn.Module):
         s = (q @ c.t()) / self.temperature
         return F.cross_entropy(s, torch.arange(q.shape[0])), s.diagonal()
 
+    def _rowwise_adagrad(self, t: TableSpec, w: torch.Tensor, g: torch.Tensor) -> None:
+        n = self.column_blocks.get(t.name, 1)
+        if n == 1:
+            rowwise_adagrad_dense(w, self.sparse_state[t.name]["sum"], g, lr=self.sparse_lr, eps=self.sparse_eps)
+            return
+        st = self.column_state.setdefault(t.name, torch.zeros(t.num_embeddings, n))
+        dw = t.embedding_dim // n
+        for j in range(n):
+            blk, acc = w[:, j * dw:(j + 1) * dw].clone(), st[:, j].clone()
+            rowwise_adagrad_dense(blk, acc, g[:, j * dw:(j + 1) * dw], lr=self.sparse_lr, eps=self.sparse_eps)
+            w[:, j * dw:(j + 1) * dw] = blk
+            st[:, j] = acc
+
     # ---- one data-parallel step as W ranks would do it: every rank's loss is the mean over ITS
     # batch; tower gradients are AVERAGED (DDP); embedding gradients of all ranks meet in the
     # (model-parallel) tables and are divided by W as well -- TorchRec's pooled all-to-all /
@@ -195,7 +213,7 @@ class OracleTwoTower(nn.Module):
                     continue
                 assert self.sparse_optimizer == "rowwise_adagrad"
                 g = w.grad / W if gradient_division else w.grad
-                rowwise_adagrad_dense(w, self.sparse_state[t.name]["sum"], g, lr=self.sparse_lr, eps=self.sparse_eps)
+                self._rowwise_adagrad(t, w, g)
                 w.grad = None
         self.dense_opt.step()
         return losses
@@ -219,7 +237,7 @@ class OracleTwoTower(nn.Module):
                 if g is None:
                     continue
                 if self.sparse_optimizer == "rowwise_adagrad":
-                    rowwise_adagrad_dense(w, self.sparse_state[t.name]["sum"], g, lr=self.sparse_lr, eps=self.sparse_eps)
+                    self._rowwise_adagrad(t, w, g)
                 else:
                     ids = torch.cat([values[int(offsets[list(keys).index(f) * B]):int(offsets[(list(keys).index(f) + 1) * B])]
                                      for f in t.feature_names])

@@ -39,7 +39,9 @@ def _worker(rank, world, port, sharding, errq):
         from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
 
         specs = [TableSpec(f"t_{c}", EMB[i], DIM, [c]) for i, c in enumerate(CAT)]
-        ref = oracle.OracleTwoTower(specs, LAYERS, loss="bce", sparse_lr=LR, dense_lr=LR, seed=3, dense_optimizer="sgd")
+        # column-wise: every column shard is its own fused table with its own row-wise accumulator (one shard per rank)
+        blocks = {s.name: world for s in specs} if sharding == "column_wise" else None
+        ref = oracle.OracleTwoTower(specs, LAYERS, loss="bce", sparse_lr=LR, dense_lr=LR, seed=3, dense_optimizer="sgd", column_blocks=blocks)
         ebc = tt.EmbeddingBagCollection(tables=[tt.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=DIM, num_embeddings=EMB[i], feature_names=[c])
                                                 for i, c in enumerate(CAT)], device=torch.device("meta"))
         task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, LAYERS, device=dev))
@@ -126,7 +128,7 @@ def _run_ranks(target, args_of_rank, world=2, timeout=300):
     assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)
 
 
-MODES = ["table_wise", "row_wise", "table_wise_peer", "table_wise_dense", "table_wise_dense_peer", "row_wise_dense_peer"]
+MODES = ["table_wise", "row_wise", "table_wise_peer", "table_wise_dense", "table_wise_dense_peer", "row_wise_dense_peer", "column_wise"]
 
 
 @pytest.mark.parametrize("sharding", MODES)

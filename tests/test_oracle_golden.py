@@ -329,3 +329,33 @@ def test_oracle_ray_tune_towers_equal_the_reference_class():
     for k, want in G["grads"].items():
         torch.testing.assert_close(got[k], want, rtol=1e-5, atol=1e-8, msg=lambda m: f"grad of {k}: {m}")
         assert float(want.abs().max()) > 0
+
+
+def test_oracle_column_blocks_known_answer():
+    """Column-wise shards keep one row-wise accumulator PER SHARD.  With one column per shard the mean over the shard's
+    columns is g^2 itself, so the first Adagrad step moves every touched element by exactly lr (w -= lr * g / |g|), whereas
+    the unsharded table moves a row by lr * g / rms(g) -- the known answer that tells the two apart."""
+    cat = ["user_id", "product_id"]
+    specs = [TableSpec("t_user_id", 11, 2, ["user_id"]), TableSpec("t_product_id", 7, 2, ["product_id"])]
+    lr = 0.1
+    a = oracle.OracleTwoTower(specs, [32, 16], loss="bce", sparse_lr=lr, dense_lr=0.0, seed=4, dense_optimizer="sgd",
+                              column_blocks={"t_user_id": 2})
+    b = oracle.OracleTwoTower(specs, [32, 16], loss="bce", sparse_lr=lr, dense_lr=0.0, seed=4, dense_optimizer="sgd")
+    w0 = a.embedding_bags["t_user_id"].weight.detach().clone()
+    v = torch.tensor([1, 3, 3, 5, 2, 4, 6, 0])
+    l = torch.ones(8, dtype=torch.int32)
+    y = torch.tensor([1, 0, 1, 0], dtype=torch.int32)
+    a.train_step(cat, v, l, y)
+    b.train_step(cat, v, l, y)
+    da = a.embedding_bags["t_user_id"].weight.detach() - w0
+    db = b.embedding_bags["t_user_id"].weight.detach() - w0
+    touched = torch.zeros(11, dtype=torch.bool)
+    touched[[1, 3, 5]] = True
+    assert (da[~touched] == 0).all() and (db[~touched] == 0).all()
+    moved = da[touched].abs()
+    torch.testing.assert_close(moved[moved > 0], torch.full_like(moved[moved > 0], lr), rtol=1e-5, atol=1e-7)
+    assert float(moved.max()) > 0
+    # the unsharded table: one accumulator per row, the row moves by lr * g / rms(g): |step|^2 per row sums to D * lr^2
+    torch.testing.assert_close(db[touched].pow(2).sum(dim=1), torch.full((3,), 2 * lr * lr), rtol=1e-4, atol=1e-8)
+    # the table without column blocks is updated identically by both
+    torch.testing.assert_close(a.embedding_bags["t_product_id"].weight, b.embedding_bags["t_product_id"].weight)
