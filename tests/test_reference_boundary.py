@@ -224,3 +224,30 @@ def test_reference_forward_signature(reference):
                                    CAT, EMB)["cat_cols"] == CAT
     chunks = [list(x) for x in ref.batched(iter(range(5)), 2)]
     assert chunks == [[0, 1], [2, 3], [4]]
+
+
+def test_reference_train_with_validation_inside_the_epoch(reference, capsys):
+    """``validation_freq`` (U:307-317): the reference's train() cuts the epoch into chunks with its own ``batched`` helper,
+    runs its evaluate() between them and switches the pipeline's model back to training.  The pipeline here has to follow:
+    fresh ``map`` objects on every progress() call, StopIteration at every chunk end, eval forwards without updates."""
+    ref, _ = reference
+    device = torch.device("cpu")
+    model, optimizer = _build(ref, device)
+    tw = model.module.two_tower
+    specs = [TableSpec(f"t_{c}", EMB[i], DIM, [c]) for i, c in enumerate(CAT)]
+    orc = oracle.OracleTwoTower(specs, LAYERS, loss="bce", sparse_lr=LR, dense_lr=LR, seed=12)
+    tw.load_state_dict(orc.torchrec_state_dict())
+    raws, val = _raw_batches(4, seed=6), _raw_batches(2, seed=7)
+    transform_partial = partial(ref.transform_to_torchrec_batch, num_embeddings_per_feature=EMB)
+    pipeline = ref.TrainPipelineSparseDist(model, optimizer, device)
+    ref.train(pipeline, raws, val, epoch=0, print_lr=False, validation_freq=2, limit_train_batches=None,
+              limit_val_batches=None, transform_partial=transform_partial)
+    out = capsys.readouterr().out
+    assert out.count("Average loss over val set") == 2 and out.count("Total number of iterations:") == 2
+    assert model.training                                   # train() switched it back after the last evaluation
+    for raw in raws:
+        v, l, y = oracle.transform_to_torchrec_batch(raw, CAT, EMB)
+        orc.train_step(CAT, v, l, y)
+    want = orc.torchrec_state_dict()
+    for k, t in tw.state_dict().items():
+        torch.testing.assert_close(t, want[k], rtol=1e-5, atol=1e-6, msg=lambda m: f"{k}: {m}")
