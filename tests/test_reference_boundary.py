@@ -251,3 +251,43 @@ def test_reference_train_with_validation_inside_the_epoch(reference, capsys):
     want = orc.torchrec_state_dict()
     for k, t in tw.state_dict().items():
         torch.testing.assert_close(t, want[k], rtol=1e-5, atol=1e-6, msg=lambda m: f"{k}: {m}")
+
+
+def test_reference_train_val_test_and_checkpoint_logging(reference, monkeypatch, capsys):
+    """The reference's top-level loop ``train_val_test`` (U:320-372) on the shim: base evaluation, 2 epochs of its train() +
+    evaluate(), ``log_state_dict_to_mlflow`` -> ``gather_and_get_state_dict`` (U:161-189) after every epoch, final test
+    evaluation.  The logged checkpoints carry TorchRec's key names under ``two_tower.``; stripped of that prefix (as
+    03_model_training.py:1026-1052 does on reload) the last one loads into a fresh TwoTower and reproduces the trained model."""
+    ref, logged = reference
+    import two_tower_recommender_model_b200 as tt
+    device = torch.device("cpu")
+    model, optimizer = _build(ref, device)
+    tw = model.module.two_tower
+    specs = [TableSpec(f"t_{c}", EMB[i], DIM, [c]) for i, c in enumerate(CAT)]
+    orc = oracle.OracleTwoTower(specs, LAYERS, loss="bce", sparse_lr=LR, dense_lr=LR, seed=13)
+    tw.load_state_dict(orc.torchrec_state_dict())
+    saved = {}
+    ref.mlflow.pytorch = types.SimpleNamespace(
+        log_state_dict=lambda sd, artifact_path: saved.__setitem__(artifact_path, {k: v.detach().clone() for k, v in sd.items()}))
+    monkeypatch.setenv("RANK", "0")
+    train, val, test = _raw_batches(3, seed=8), _raw_batches(2, seed=9), _raw_batches(2, seed=10)
+    args = types.SimpleNamespace(epochs=2, print_lr=False, validation_freq=None, limit_train_batches=None, limit_val_batches=None,
+                                 limit_test_batches=None)
+    transform_partial = partial(ref.transform_to_torchrec_batch, num_embeddings_per_feature=EMB)
+    test_auroc = ref.train_val_test(args, model, optimizer, device, train, val, test, transform_partial)
+    assert 0.0 <= test_auroc <= 1.0 and {"val_loss", "val_auroc", "test_loss", "test_auroc"} <= set(logged)
+    assert sorted(saved) == ["model_state_dict_0", "model_state_dict_1"]
+    for _ in range(2):
+        for raw in train:
+            v, l, y = oracle.transform_to_torchrec_batch(raw, CAT, EMB)
+            orc.train_step(CAT, v, l, y)
+    want = orc.torchrec_state_dict()
+    last = saved["model_state_dict_1"]
+    assert set(last) == {"two_tower." + k for k in want}
+    fresh_ebc = ref.EmbeddingBagCollection(tables=[ref.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=DIM, num_embeddings=EMB[i], feature_names=[c])
+                                                   for i, c in enumerate(CAT)], device=device)
+    fresh = ref.TwoTower(embedding_bag_collection=fresh_ebc, layer_sizes=LAYERS, device=device)     # the reference's class
+    fresh.load_state_dict({k[len("two_tower."):]: v for k, v in last.items()})
+    for k, t in fresh.state_dict().items():
+        torch.testing.assert_close(t, want[k], rtol=1e-5, atol=1e-6, msg=lambda m: f"{k}: {m}")
+    assert isinstance(fresh.ebc, tt.EmbeddingBagCollection)
