@@ -291,3 +291,57 @@ def test_reference_train_val_test_and_checkpoint_logging(reference, monkeypatch,
     for k, t in fresh.state_dict().items():
         torch.testing.assert_close(t, want[k], rtol=1e-5, atol=1e-6, msg=lambda m: f"{k}: {m}")
     assert isinstance(fresh.ebc, tt.EmbeddingBagCollection)
+
+
+def _notebook_functions(path, names, env):
+    """Executes ONLY the named top-level function definitions of a notebook source (the rest of the file drives Spark /
+    MLflow / a Databricks workspace)."""
+    import ast
+    with open(path) as f:
+        tree = ast.parse(f.read(), path)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert sorted(n.name for n in keep) == sorted(names)
+    ns = dict(env)
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+def test_reference_reload_and_corpus_embedding_functions(reference):
+    """03_model_training.py:1015-1122 on the shim: the notebook's own ``get_mlflow_model`` (rebuilds EmbeddingBagConfig /
+    EmbeddingBagCollection / TwoTower from the logged params, strips ``two_tower.``, load_state_dict), then its
+    ``create_keyed_jagged_tensor`` and ``process_embeddings`` on the reloaded model -- item and user embeddings equal the
+    oracle's towers."""
+    ref, _ = reference
+    import two_tower_recommender_model_b200 as tt
+    nb_path = "/root/reference/03_model_training.py"
+    specs = [TableSpec(f"t_{c}", EMB[i], DIM, [c]) for i, c in enumerate(CAT)]
+    orc = oracle.OracleTwoTower(specs, LAYERS, loss="bce", seed=14)
+    logged_sd = {"two_tower." + k: v for k, v in orc.torchrec_state_dict().items()}     # what log_state_dict_to_mlflow wrote
+    mlflow = sys.modules["mlflow"]
+    params = {"cat_cols": repr(CAT), "emb_counts": repr(EMB), "layer_sizes": repr(LAYERS), "embedding_dim": repr(DIM)}
+    mlflow.get_run = lambda run_id: types.SimpleNamespace(data=types.SimpleNamespace(params=params))
+    mlflow.MlflowClient = lambda: types.SimpleNamespace(download_artifacts=lambda *a, **k: None)
+    mlflow.pytorch = types.SimpleNamespace(load_state_dict=lambda path, map_location=None: dict(logged_sd))
+    nb = _notebook_functions(nb_path, ["get_mlflow_model", "create_keyed_jagged_tensor", "process_embeddings"],
+                             {"torch": torch, "mlflow": mlflow, "EmbeddingBagConfig": ref.EmbeddingBagConfig,
+                              "EmbeddingBagCollection": ref.EmbeddingBagCollection, "TwoTower": ref.TwoTower,
+                              "KeyedJaggedTensor": ref.KeyedJaggedTensor})
+    model, ebc, eb_configs, cat_cols, emb_counts = nb["get_mlflow_model"]("run-1", artifact_path="model_state_dict_1", device="cpu")
+    assert isinstance(ebc, tt.EmbeddingBagCollection) and cat_cols == CAT and emb_counts == EMB and len(eb_configs) == 2
+    for k, want in orc.torchrec_state_dict().items():
+        torch.testing.assert_close(model.state_dict()[k], want, rtol=0, atol=0)
+    model.eval()
+    with torch.no_grad():
+        iv = torch.arange(EMB[1])
+        il = torch.cat([torch.zeros(EMB[1], dtype=torch.int32), torch.ones(EMB[1], dtype=torch.int32)])
+        _, items_ref = orc.forward(CAT, iv, il)
+        uv = torch.arange(EMB[0])
+        ul = torch.cat([torch.ones(EMB[0], dtype=torch.int32), torch.zeros(EMB[0], dtype=torch.int32)])
+        users_ref, _ = orc.forward(CAT, uv, ul)
+    kjt = nb["create_keyed_jagged_tensor"](EMB[1], CAT, "product_id", device="cpu")       # the notebook's own functions
+    assert isinstance(kjt, tt.KeyedJaggedTensor) and kjt.length_per_key() == [0, EMB[1]]
+    items = nb["process_embeddings"](model, kjt, "product_id")
+    users = nb["process_embeddings"](model, nb["create_keyed_jagged_tensor"](EMB[0], CAT, "user_id", device="cpu"), "user_id")
+    assert items is not None and users is not None                                        # it returns None on any exception
+    torch.testing.assert_close(items, items_ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(users, users_ref, rtol=1e-5, atol=1e-6)
