@@ -39,7 +39,8 @@ CAT, EMB, DIM, LAYERS, B, LR = ["user_id", "product_id"], [97, 53], 16, [32, 16]
 
 # ------------------------------------------------------------------ oracle stand-ins for the device work
 class _OracleLookup(torch.autograd.Function):
-    """EbcLookup's contract: pooled [B, sum D]; backward applies row-wise Adagrad in place, weights get no .grad."""
+    """EbcLookup's contract: pooled [B, sum D]; backward applies row-wise Adagrad in place and the weights get no .grad --
+    or, without an in-backward optimizer, hands the tables their dense gradient."""
 
     @staticmethod
     def forward(ctx, ebc, kjt_keys, values, offsets, batch, *anchors):
@@ -55,6 +56,8 @@ class _OracleLookup(torch.autograd.Function):
         values, lengths = ctx.saved_tensors
         ebc = ctx.ebc
         grads = oracle.ebc_dense_grads(ctx.specs, ctx.keys, values, lengths, g)
+        if ebc._in_backward_kind() is None:
+            return (None,) * 5 + tuple(grads)      # no fused optimizer: the tables receive their dense gradient
         for s, gr in zip(ctx.specs, grads):
             w = ebc.embedding_bags[s.name].weight
             cfg = next(c for c in ebc.embedding_bag_configs() if c.name == s.name)
@@ -345,3 +348,45 @@ def test_reference_reload_and_corpus_embedding_functions(reference):
     assert items is not None and users is not None                                        # it returns None on any exception
     torch.testing.assert_close(items, items_ref, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(users, users_ref, rtol=1e-5, atol=1e-6)
+
+
+def test_reference_ray_tune_two_tower_class_runs_on_the_shim(reference):
+    """ray_tune_optuna_tuning_alex_test.py:181-306: the reference's multi-feature / dense-concat ``TwoTower`` class, extracted
+    unchanged, built on THIS package's EmbeddingBagCollection / MLP / KeyedJaggedTensor / Batch.  Its embeddings, logits,
+    loss and tower gradients equal what the same class computed on stock torch (tests/golden/reference_raytune.npz)."""
+    import ast
+    from typing import List, Optional, Tuple
+    import two_tower_recommender_model_b200 as tt
+    from helpers import load_raytune_golden
+    ref, _ = reference
+    path = "/root/reference/ray_tune_optuna_tuning_alex_test.py"
+    with open(path) as f:
+        tree = ast.parse(f.read(), path)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "TwoTower"]
+    ns = {"torch": torch, "nn": nn, "List": List, "Optional": Optional, "Tuple": Tuple, "MLP": ref.MLP, "Batch": ref.Batch,
+          "EmbeddingBagCollection": ref.EmbeddingBagCollection}
+    exec(compile(ast.Module(body=cls, type_ignores=[]), path, "exec"), ns)
+    G = load_raytune_golden()
+    keys = list(G["dims"])
+    ebc = ref.EmbeddingBagCollection(tables=[ref.EmbeddingBagConfig(name=f"t_{k}", embedding_dim=G["dims"][k], num_embeddings=G["rows"][k],
+                                                                    feature_names=[k]) for k in keys], device=torch.device("cpu"))
+    user_in = sum(G["dims"][k] for k in G["feats_u"]) + G["dense_index"]
+    item_in = sum(G["dims"][k] for k in G["feats_i"]) + (G["dense_dim"] - G["dense_index"])
+    model = ns["TwoTower"](ebc, G["layers"], [user_in, item_in], G["feats_u"], G["feats_i"], dense_index=G["dense_index"],
+                           device=torch.device("cpu"))
+    assert isinstance(model.ebc, tt.EmbeddingBagCollection) and isinstance(model.user_proj, tt.MLP)
+    rename = {"query_proj": "user_proj", "candidate_proj": "item_proj"}           # the fixture uses this package's tower names
+    model.load_state_dict({".".join([rename.get(k.split(".")[0], k.split(".")[0])] + k.split(".")[1:]): v for k, v in G["weights"].items()})
+    batch = ref.Batch(dense_features=G["dense"], sparse_features=ref.KeyedJaggedTensor.from_lengths_sync(keys, G["values"], G["lengths"]),
+                      labels=G["labels"])
+    q, c = model(batch)                                                           # the reference's forward
+    torch.testing.assert_close(q.detach(), G["q"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(c.detach(), G["c"], rtol=1e-5, atol=1e-6)
+    logits = (q * c).sum(dim=1).squeeze()
+    loss = nn.BCEWithLogitsLoss()(logits, G["labels"].float())
+    torch.testing.assert_close(loss.detach(), G["loss"], rtol=1e-6, atol=1e-7)
+    loss.backward()
+    for name, p in model.named_parameters():
+        head, rest = name.split(".", 1)
+        ours = {"user_proj": "query_proj", "item_proj": "candidate_proj"}.get(head, head) + "." + rest
+        torch.testing.assert_close(p.grad, G["grads"][ours], rtol=1e-5, atol=1e-8, msg=lambda m: f"grad of {name}: {m}")
