@@ -390,3 +390,65 @@ def test_reference_ray_tune_two_tower_class_runs_on_the_shim(reference):
         head, rest = name.split(".", 1)
         ours = {"user_proj": "query_proj", "item_proj": "candidate_proj"}.get(head, head) + "." + rest
         torch.testing.assert_close(p.grad, G["grads"][ours], rtol=1e-5, atol=1e-8, msg=lambda m: f"grad of {name}: {m}")
+
+
+def test_reference_ray_tune_transform_and_train_task_run_on_the_shim(reference):
+    """ray_tune_optuna_tuning_alex_test.py:121-153,320-375: the Ray-Tune variant's ``transform_to_torchrec_batch`` (dense
+    columns concatenated into ``Batch.dense_features``) and its ``TwoTowerTrainTask`` (``return_sparse``: reads
+    ``batch.sparse_features[name].values()``; ``WeightedBCELoss`` on the first dense columns) on this package's types;
+    logits / loss against the oracle's towers with the dense features concatenated."""
+    import ast
+    from dataclasses import dataclass, field
+    from typing import List, Optional, Tuple
+    ref, _ = reference
+    path = "/root/reference/ray_tune_optuna_tuning_alex_test.py"
+    with open(path) as f:
+        tree = ast.parse(f.read(), path)
+    want_names = {"TwoTower", "WeightedBCELoss", "TwoTowerTrainTask", "transform_to_torchrec_batch"}
+    body = [n for n in tree.body if isinstance(n, (ast.ClassDef, ast.FunctionDef)) and n.name in want_names]
+    assert {n.name for n in body} == want_names
+    ns = {"torch": torch, "nn": nn, "List": List, "Optional": Optional, "Tuple": Tuple, "MLP": ref.MLP, "Batch": ref.Batch,
+          "EmbeddingBagCollection": ref.EmbeddingBagCollection, "KeyedJaggedTensor": ref.KeyedJaggedTensor,
+          "dataclass": dataclass, "field": field}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+
+    cat, emb, dim, Bn = ["u_a", "i_a"], [50, 40], 8, 12
+    g = torch.Generator().manual_seed(2)
+    raw = {"u_a": torch.randint(0, 120, (Bn,), generator=g).tolist(), "i_a": torch.randint(0, 90, (Bn,), generator=g).tolist(),
+           "label": torch.randint(0, 2, (Bn,), generator=g).tolist(),
+           "d0": torch.rand(Bn, generator=g), "d1": torch.rand(Bn, 2, generator=g)}      # a 1-d and a 2-d dense column
+    batch = ns["transform_to_torchrec_batch"](raw, emb, cat, dense_cols=["d0", "d1"])     # the reference's function
+    assert isinstance(batch, ref.Batch) and batch.dense_features.shape == (Bn, 3)
+    v, l, y = oracle.transform_to_torchrec_batch(raw, cat, emb)
+    assert torch.equal(batch.sparse_features.values(), v) and torch.equal(batch.sparse_features.lengths(), l)
+
+    specs = [TableSpec(f"t_{c}", emb[i], dim, [c]) for i, c in enumerate(cat)]
+    orc = oracle.OracleTwoTower(specs, [[16, 4], [8, 4]], loss="bce", seed=3, query_features=["u_a"], candidate_features=["i_a"],
+                                dense_index=1, dense_dim=3)
+    ebc = ref.EmbeddingBagCollection(tables=[ref.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=dim, num_embeddings=emb[i], feature_names=[c])
+                                             for i, c in enumerate(cat)], device=torch.device("cpu"))
+    tower = ns["TwoTower"](ebc, [[16, 4], [8, 4]], [dim + 1, dim + 2], ["u_a"], ["i_a"], dense_index=1, device=torch.device("cpu"))
+    rename = {"query_proj": "user_proj", "candidate_proj": "item_proj"}
+    tower.load_state_dict({".".join([rename.get(k.split(".")[0], k.split(".")[0])] + k.split(".")[1:]): t
+                           for k, t in orc.torchrec_state_dict().items()})
+    q_ref, c_ref = orc.forward(cat, v, l, batch.dense_features.detach())
+    logits_ref = (q_ref * c_ref).sum(dim=1)
+
+    task = ns["TwoTowerTrainTask"](tower, return_sparse=True, sparse_feature_names=["u_a"])
+    loss, (l2, logits, labels, sparse_values) = task(batch)
+    torch.testing.assert_close(logits, logits_ref.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(loss.detach(), torch.nn.functional.binary_cross_entropy_with_logits(logits_ref, y.float()).detach(), rtol=1e-6, atol=1e-7)
+    nu = int(l[:Bn].sum())
+    assert torch.equal(sparse_values["u_a"], v[:nu]) and torch.equal(labels, y)
+    # weighted loss: BCELoss(reduction="none") on the probabilities, weighted by the interaction type in dense[:, :3]
+    onehot = torch.zeros(Bn, 3)
+    onehot[torch.arange(Bn), torch.randint(0, 3, (Bn,), generator=g)] = 1.0
+    wbatch = ref.Batch(dense_features=onehot, sparse_features=batch.sparse_features, labels=batch.labels)
+    weights = {(1, 0, 0): 1.0, (0, 1, 0): 2.0, (0, 0, 1): 0.5}
+    wtask = ns["TwoTowerTrainTask"](tower, loss_fn=ns["WeightedBCELoss"](weights), return_sparse=False)
+    wloss, (_, wlogits, _) = wtask(wbatch)
+    q2, c2 = orc.forward(cat, v, l, onehot)
+    p2 = torch.sigmoid((q2 * c2).sum(dim=1))
+    per = torch.nn.functional.binary_cross_entropy(p2, y.float(), reduction="none")
+    wts = torch.tensor([weights[tuple(int(x) for x in row)] for row in onehot.tolist()])
+    torch.testing.assert_close(wloss.detach(), (per * wts).mean().detach(), rtol=1e-5, atol=1e-7)
