@@ -452,3 +452,36 @@ def test_reference_ray_tune_transform_and_train_task_run_on_the_shim(reference):
     per = torch.nn.functional.binary_cross_entropy(p2, y.float(), reduction="none")
     wts = torch.tensor([weights[tuple(int(x) for x in row)] for row in onehot.tolist()])
     torch.testing.assert_close(wloss.detach(), (per * wts).mean().detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_workshop_serving_wrapper_runs_on_the_shim(reference):
+    """workshop/02-mosaic-model-training.py:1120-1210: the pyfunc ``TwoTowerWrapper`` (serving is out of scope for speed,
+    SURVEY section 2, but it is a caller of the path): its ``_transform_to_torchrec_batch`` keeps id 0 as a real row
+    (``is not None`` instead of truthiness) and ``predict`` returns sigmoid(q . c) as a list -- on this package's types,
+    against the oracle's towers."""
+    import ast
+    from typing import Dict, List, Optional
+    import numpy as np
+    ref, _ = reference
+    path = "/root/reference/workshop/02-mosaic-model-training.py"
+    with open(path) as f:
+        tree = ast.parse(f.read(), path)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "TwoTowerWrapper"]
+    assert len(cls) == 1
+    ns = {"torch": torch, "np": np, "Dict": Dict, "List": List, "Optional": Optional, "PythonModel": object, "Batch": ref.Batch,
+          "KeyedJaggedTensor": ref.KeyedJaggedTensor, "cat_cols": list(CAT), "emb_counts": list(EMB)}
+    exec(compile(ast.Module(body=cls, type_ignores=[]), path, "exec"), ns)
+    specs = [TableSpec(f"t_{c}", EMB[i], DIM, [c]) for i, c in enumerate(CAT)]
+    orc = oracle.OracleTwoTower(specs, LAYERS, loss="bce", seed=15)
+    ebc = ref.EmbeddingBagCollection(tables=[ref.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=DIM, num_embeddings=EMB[i], feature_names=[c])
+                                             for i, c in enumerate(CAT)], device=torch.device("cpu"))
+    tower = ref.TwoTower(embedding_bag_collection=ebc, layer_sizes=LAYERS, device=torch.device("cpu"))
+    tower.load_state_dict(orc.torchrec_state_dict())
+    wrapper = ns["TwoTowerWrapper"](tower, torch.device("cpu"))
+    users, items = [0, 5, 200, 96], [7, 0, 53, 52]                    # id 0 stays a row here; 200 % 97 = 6, 53 % 53 = 0
+    probs = wrapper.predict(None, {"user_id": users, "product_id": items})
+    assert isinstance(probs, list) and len(probs) == 4
+    v = torch.tensor([u % EMB[0] for u in users] + [i % EMB[1] for i in items])
+    with torch.no_grad():
+        q, c = orc.forward(CAT, v, torch.ones(8, dtype=torch.int32))
+    torch.testing.assert_close(torch.tensor(probs), torch.sigmoid((q * c).sum(dim=1)), rtol=1e-5, atol=1e-6)
