@@ -597,7 +597,9 @@ def headline(args, cfg, main, pk, world, G, workload, scaling, parity):
                    "exchange": (args.exchange if world > 1 else None), "sharding": main["sharding"],
                    "l2": "tables 5.12 GB >> 126 MB L2, random ids; no flush needed"},
         "e2e": {"value": round(total_batch / (main["ms_e2e"] * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(main["ms_e2e"], 4),
-                "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": 4, "last_loss": main["last_loss"], "api": main["e2e_api"]},
+                # whole job: every rank copies its own share of the batch in and reads its own loss back
+                "h2d_bytes_per_step": main["h2d"] * world, "d2h_bytes_per_step": 4 * world,
+                "h2d_bytes_per_step_per_rank": main["h2d"], "last_loss": main["last_loss"], "api": main["e2e_api"]},
         "gpu_launches": main["launches"], "clocks": main["clocks"], "roofline": roof, "kernels": kernels,
         "calls_ms": {k: round(v["ms"], 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1]["ms"])},
         "ebc_lookup_gbs": kernels.get("tt_ebc_forward", kernels.get("tt_ebc_forward_peer", {})).get("achieved"),
