@@ -42,6 +42,17 @@ import torch  # noqa: E402
 CAT = ["user_id", "product_id"]
 # rank 0's line once the headline block is measured + the block in flight: what the watchdog prints if a later block wedges
 _PARTIAL = {"line": None, "stage": "headline"}
+# watchdog deadlines (time.time()): the whole run, and the side block in flight (shorter: a wedged side block is cut early)
+_DEADLINE = {"run": None, "block": None}
+
+
+def stage(name, limit_s=None):
+    """Names the block in flight and (re)arms its own time limit; ``limit_s=None`` leaves only the run's limit."""
+    _PARTIAL["stage"] = name
+    _DEADLINE["block"] = None if limit_s is None else time.time() + limit_s
+
+
+BLOCK_LIMIT_S = float(os.environ.get("TT_BENCH_BLOCK_S", "180"))
 CFG2 = dict(rows=[10_000_000, 10_000_000], dim=64, layers=[128, 64], batch=65536, loss="in_batch_softmax",
             sparse_lr=0.01, dense_lr=0.001)
 CFG1 = dict(rows=[200_000, 50_000], dim=64, layers=[128, 64], batch=1024, loss="bce", sparse_lr=0.01, dense_lr=0.001)
@@ -517,7 +528,7 @@ def side_blocks(args, cfg, dev, rank, world, local, lib, G, line):
     every rank is recorded as an error and the run goes on; one that wedges is cut by the watchdog, which still prints
     the headline line with an `incomplete` entry."""
     def record(name, fn):
-        _PARTIAL["stage"] = name
+        stage(name, BLOCK_LIMIT_S)
         try:
             out = fn()
         except Exception as e:      # noqa: BLE001 -- recorded, not hidden: the line says which block failed and why
@@ -551,7 +562,7 @@ def side_blocks(args, cfg, dev, rank, world, local, lib, G, line):
     record("weak", weak)
     record("strong_global_negatives", strong_global_negatives)
     record("retrieval", lambda: retrieval_probe_sharded(dev, rank, world))
-    _PARTIAL["stage"] = "done"
+    stage("done")
 
 
 def headline(args, cfg, main, pk, world, G, workload, scaling, parity):
@@ -619,11 +630,11 @@ def finish(args, cfg, dev, world, line):
     """Rank 0: the single-GPU side blocks (retrieval probes, configs[2] / configs[3], CPU baselines), then the line."""
     if world == 1 and not args.no_cpu_baseline:
         # first: `cpu_baseline` is part of the bench contract, the blocks after it are extras
-        _PARTIAL["stage"] = "cpu_baseline"
+        stage("cpu_baseline", BLOCK_LIMIT_S)
         line["cpu_baseline"] = cpu_baseline(cfg, steps=1, warmup=1)
         line["cpu_baseline_cfg1"] = cpu_baseline_cfg1()
     if world == 1:
-        _PARTIAL["stage"] = "retrieval"
+        stage("retrieval", BLOCK_LIMIT_S)
         line["retrieval"] = retrieval_probe(dev)
         line["retrieval_large"] = retrieval_probe(dev, n_items=10_000_000, n_queries=131072)
     if world == 1 and not args.no_other_configs:
@@ -632,13 +643,13 @@ def finish(args, cfg, dev, world, line):
         import run_configs
         torch.cuda.empty_cache()
         for name, fn in (("cfg3", run_configs.config3), ("cfg4", run_configs.config4)):
-            _PARTIAL["stage"] = name
+            stage(name, BLOCK_LIMIT_S)
             try:
                 line[name] = fn()
             except Exception as e:      # noqa: BLE001 -- recorded in the line; configs[1] stays the value
                 line[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
                 torch.cuda.empty_cache()
-    _PARTIAL["stage"] = "done"
+    stage("done")
     _PARTIAL["line"] = None
     print(json.dumps(line))
     leave(world)
@@ -819,7 +830,7 @@ def watchdog():
         line = _PARTIAL["line"]
         if line is not None:
             line = dict(line)
-            line["incomplete"] = {"cut_block": _PARTIAL["stage"], "reason": "watchdog: the block did not finish within the run's limit; "
+            line["incomplete"] = {"cut_block": _PARTIAL["stage"], "reason": "watchdog: the block did not finish within its limit; "
                                   "the headline block (value / e2e / roofline / parity) had completed before it started"}
             try:
                 print(json.dumps(line))
@@ -832,6 +843,23 @@ def watchdog():
     sys.stdout.flush()
     sys.stderr.flush()
     os._exit(rc)
+
+
+def start_watchdog(run_limit_s):
+    """A daemon thread that ends the process (through ``watchdog``) once the run's limit, or the limit of the side block in
+    flight (``stage``), has passed.  Ranks other than 0 wait 15 s longer so that rank 0 can print first."""
+    grace = 0 if int(os.environ.get("RANK", 0)) == 0 else 15
+    _DEADLINE["run"] = time.time() + run_limit_s
+
+    def poll():
+        while True:
+            time.sleep(0.5)
+            now = time.time() - grace
+            blk = _DEADLINE["block"]
+            if now > _DEADLINE["run"] or (blk is not None and now > blk):
+                watchdog()
+
+    threading.Thread(target=poll, daemon=True).start()
 
 
 def main():
@@ -849,9 +877,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly (N>1: through TrainPipelineSparseDist) instead of replaying a CUDA graph")
     args = ap.parse_args()
     # a wedged collective / capture must not hold the box: the default run takes about a minute
-    wd = threading.Timer(float(os.environ.get("TT_BENCH_WATCHDOG_S", "600")) + (0 if int(os.environ.get("RANK", 0)) == 0 else 15), watchdog)
-    wd.daemon = True
-    wd.start()
+    start_watchdog(float(os.environ.get("TT_BENCH_WATCHDOG_S", "600")))
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -119,3 +119,33 @@ def test_reference_arm_line_shape(monkeypatch, capsys):
     monkeypatch.setenv("WORLD_SIZE", "2")
     bench.run_reference(_args(impl="reference"))
     assert capsys.readouterr().out == ""
+
+
+def test_a_wedged_side_block_is_cut_at_its_own_limit():
+    """The polling watchdog: the run's limit is far away, the side block in flight has its own short one -- the process ends
+    there, rank 0 prints the headline with the block named; a finished block (stage("done")) disarms it."""
+    code = (
+        "import sys, time; sys.path.insert(0, %r); import bench\n"
+        "bench._PARTIAL['line'] = {'metric': 'two-tower train samples/s', 'value': 2.5}\n"
+        "bench.start_watchdog(300.0)\n"
+        "bench.stage('strong_row_wise', 60.0); time.sleep(1.2); bench.stage('weak', 1.0)\n"
+        "time.sleep(30)\n"
+        "print('not reached')\n" % ROOT)
+    env = dict(os.environ, RANK="0", MASTER_PORT="1%d" % os.getpid())
+    t0 = __import__("time").time()
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    took = __import__("time").time() - t0
+    marker = "/tmp/tt_bench_partial_1%d" % os.getpid()
+    if os.path.exists(marker):
+        os.remove(marker)
+    assert p.returncode == 0 and "not reached" not in p.stdout and took < 25, (p.returncode, took, p.stderr[-300:])
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["value"] == 2.5 and line["incomplete"]["cut_block"] == "weak"
+    code_ok = (
+        "import sys, time; sys.path.insert(0, %r); import bench\n"
+        "bench.start_watchdog(300.0)\n"
+        "bench.stage('weak', 1.0); bench.stage('done'); time.sleep(3)\n"
+        "print('finished')\n" % ROOT)
+    p = subprocess.run([sys.executable, "-c", code_ok], capture_output=True, text=True, env=env, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip() == "finished"
+
