@@ -485,3 +485,29 @@ def test_workshop_serving_wrapper_runs_on_the_shim(reference):
     with torch.no_grad():
         q, c = orc.forward(CAT, v, torch.ones(8, dtype=torch.int32))
     torch.testing.assert_close(torch.tensor(probs), torch.sigmoid((q * c).sum(dim=1)), rtol=1e-5, atol=1e-6)
+
+
+def test_reference_extract_columns_reads_our_search_response(reference, monkeypatch):
+    """04_evaluate_retrieval.py:117-141: the notebook asks ``index.similarity_search(query_vector=, columns=, num_results=k)``
+    and feeds the response to its own ``extract_columns``.  ``BruteForceIndex`` stands in for the remote index; the notebook's
+    function, extracted unchanged, reads its response (the scoring kernel is replaced by the oracle here)."""
+    import two_tower_recommender_model_b200 as tt
+    from two_tower_recommender_model_b200 import retrieval
+    monkeypatch.setattr(retrieval, "score_topk", lambda q, items, k, item_index_base=0, precision="fp32", items_bf16=None:
+                        oracle.exact_topk(q, items, k))
+    # this notebook holds cell magics, so it does not parse as a module: cut the one function out by its indentation
+    lines = open("/root/reference/04_evaluate_retrieval.py").read().splitlines()
+    start = next(i for i, ln in enumerate(lines) if ln.startswith("def extract_columns("))
+    end = next(i for i in range(start + 1, len(lines)) if lines[i].strip() and not lines[i].startswith((" ", "\t")))
+    nb = {}
+    exec(compile("\n".join(lines[start:end]), "04_evaluate_retrieval.py:extract_columns", "exec"), nb)
+    g = torch.Generator().manual_seed(4)
+    items = torch.randn(300, 16, generator=g)
+    user = torch.randn(16, generator=g)
+    index = tt.BruteForceIndex(items)
+    results = index.similarity_search(query_vector=user.tolist(), columns=["product_id", "embeddings"], num_results=100)
+    got = nb["extract_columns"](results, columns=["product_id", "score"])             # the notebook's own function
+    ws, wi = oracle.exact_topk(user.view(1, -1), items, 100)
+    assert got["product_id_pred"] == wi[0].tolist()
+    torch.testing.assert_close(torch.tensor(got["score_pred"]), ws[0], rtol=1e-6, atol=1e-6)
+    assert list(map(int, got["product_id_pred"])) == got["product_id_pred"]           # N04:163 maps the ids through int()
