@@ -359,3 +359,28 @@ def test_oracle_column_blocks_known_answer():
     torch.testing.assert_close(db[touched].pow(2).sum(dim=1), torch.full((3,), 2 * lr * lr), rtol=1e-4, atol=1e-8)
     # the table without column blocks is updated identically by both
     torch.testing.assert_close(a.embedding_bags["t_product_id"].weight, b.embedding_bags["t_product_id"].weight)
+
+
+def test_oracle_ndcg_against_sklearn():
+    """mlflow's retriever ``ndcg_at_k`` (04_evaluate_retrieval.py:202-226) is sklearn's ``ndcg_score`` over the retrieved ids
+    (descending scores, relevance 1 if a target) plus the targets that were not retrieved (relevance 1, lowest score), cut
+    at the number of ids retrieved.  The oracle's closed form against that stock implementation on random rows."""
+    sklearn_metrics = pytest.importorskip("sklearn.metrics")
+    g = torch.Generator().manual_seed(123)
+    checked = 0
+    for _ in range(200):
+        n_pred = int(torch.randint(1, 12, (1,), generator=g))
+        k = int(torch.randint(1, 12, (1,), generator=g))
+        pred = torch.randperm(25, generator=g)[:n_pred].tolist()
+        tgt = torch.randperm(25, generator=g)[:int(torch.randint(1, 8, (1,), generator=g))].tolist()
+        retrieved = pred[:k]
+        docs = retrieved + [t for t in tgt if t not in retrieved]
+        if len(docs) < 2:
+            continue                                   # sklearn refuses a single document
+        y_true = [1.0 if d in tgt else 0.0 for d in docs]
+        y_score = [float(len(docs) - i) for i in range(len(retrieved))] + [0.0] * (len(docs) - len(retrieved))
+        want = sklearn_metrics.ndcg_score([y_true], [y_score], k=len(retrieved), ignore_ties=True)
+        got = oracle.retrieval_metrics([pred], [tgt], k)[f"ndcg_at_{k}"]
+        assert abs(got - want) < 1e-9, (pred, tgt, k, got, want)
+        checked += 1
+    assert checked > 150
