@@ -732,9 +732,11 @@ def retrieval_probe_sharded(dev, rank, world, n_items=10_000_000, q_per_rank=131
 
 
 # ----------------------------------------------------------------------------- CPU baseline / reference arm
-def cpu_baseline(cfg, steps, warmup, sample_batch=None):
+def cpu_baseline(cfg, steps, warmup, sample_batch=None, budget_s=None):
     """Oracle port of the reference's unsharded CPU path (dense [R,D] embedding gradient + row-wise Adagrad over
-    the whole table each step, as nn.EmbeddingBag + a grad hook do) at the FULL configs[1] batch."""
+    the whole table each step, as nn.EmbeddingBag + a grad hook do) at the FULL configs[1] batch.  ``budget_s``
+    bounds the run: the first step sizes it (it is a warm-up step when the budget leaves room for one) -- as many
+    of the `steps` timed steps as fit, then as many of the `warmup` steps as the rest allows."""
     import oracle
     from oracle.ebc import TableSpec
     cores = os.cpu_count() or 1
@@ -744,19 +746,35 @@ def cpu_baseline(cfg, steps, warmup, sample_batch=None):
                               sparse_lr=cfg["sparse_lr"], dense_lr=cfg["dense_lr"], seed=0)
     g = torch.Generator().manual_seed(0)
     Bs = min(sample_batch or cfg["batch"], cfg["batch"])
-    times = []
-    for i in range(warmup + steps):
+    steps0, warmup0, all_dt, elapsed = steps, warmup, [], 0.0
+    i = 0
+    while i < warmup + steps:
         vals = torch.cat([torch.randint(1, r, (Bs,), generator=g) for r in cfg["rows"]])
         lens = torch.ones(2 * Bs, dtype=torch.int32)
         y = torch.randint(0, 2, (Bs,), generator=g, dtype=torch.int32)
         t0 = time.perf_counter()
         m.train_step(CAT, vals, lens, y)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+        dt = time.perf_counter() - t0
+        all_dt.append(dt)
+        elapsed += dt
+        i += 1
+        if budget_s is not None and i <= 2:      # the (cold) first step sizes the run, the second one corrects it
+            steps, warmup = bounded_steps(steps0, warmup0, budget_s - elapsed, dt, done=i)
+    times = all_dt[warmup:warmup + steps]
     sec = sum(times) / len(times)
     return {"value": round(Bs / sec, 1), "unit": "samples/s", "cores": cores, "kind": "port", "ms_per_step": round(sec * 1e3, 2),
+            "steps": steps, "warmup": warmup,
             "sample": f"{Bs} of the {cfg['batch']}-sample batch per step (in-batch negatives = {Bs}), full 10M-row tables, "
                       f"{steps} timed step(s) after {warmup} warm-up"}
+
+
+def bounded_steps(steps, warmup, remaining_s, step_s, done=0):
+    """How many timed / warm-up steps fit when `done` steps are behind us, `remaining_s` of the budget are left and
+    a step takes `step_s`: timed steps first (at least one), then warm-up steps from what is left."""
+    afford = done + int(max(0.0, remaining_s) / max(step_s, 1e-3))
+    afford = max(1, afford)
+    steps = max(1, min(steps, afford))
+    return steps, max(0, min(warmup, afford - steps))
 
 
 def cpu_baseline_cfg1(steps=30, warmup=5):
@@ -797,20 +815,18 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = dict(CFG2)
-    # the FULL configs[1] batch per step, as many steps as asked for but bounded to a few minutes of CPU time:
-    # one probe step sizes the run
-    probe = cpu_baseline(cfg, steps=1, warmup=0)
-    per_step = probe["ms_per_step"] * 1e-3
-    budget_s = float(os.environ.get("TT_REFERENCE_BUDGET_S", "175"))
-    steps = max(1, min(args.steps, int(budget_s / max(per_step, 1e-3))))
-    warmup = 0 if steps < args.steps else min(args.warmup, 1)
-    cb = cpu_baseline(cfg, steps=steps, warmup=warmup) if steps > 1 else probe
+    # the FULL configs[1] batch per step; as many of the asked-for steps / warm-up steps as a few minutes of CPU time hold
+    # (16 host cores: ~8 s per step, so --steps 20 --warmup 5 runs as asked)
+    budget_s = float(os.environ.get("TT_REFERENCE_BUDGET_S", "240"))
+    cb = cpu_baseline(cfg, steps=max(1, args.steps), warmup=max(0, args.warmup), budget_s=budget_s)
+    steps, warmup = cb["steps"], cb["warmup"]
     line = {"impl": "reference", "metric": "two-tower train samples/s", "value": cb["value"], "unit": "samples/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1] (CPU port of the reference's unsharded TorchRec path; torchrec/fbgemm "
                                    "are not installable here)", "per_rank_batch": cfg["batch"], "global_batch": cfg["batch"],
-                       "steps_requested": args.steps, "steps_note": "bounded so that the CPU run ends within a few minutes"},
+                       "steps_requested": args.steps, "warmup_requested": args.warmup,
+                       "steps_note": "bounded so that the CPU run ends within a few minutes (TT_REFERENCE_BUDGET_S, %d s)" % budget_s},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

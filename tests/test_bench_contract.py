@@ -104,8 +104,9 @@ def test_watchdog_prints_the_headline_once_it_exists(have_line, tmp_path):
 
 def test_reference_arm_line_shape(monkeypatch, capsys):
     """`--impl reference`: the oracle port timed on the host cores; same metric / unit / config keys as our arm."""
-    monkeypatch.setattr(bench, "cpu_baseline", lambda cfg, steps, warmup, sample_batch=None: {
-        "value": 8000.0, "unit": "samples/s", "cores": 16, "kind": "port", "ms_per_step": 8192.0, "sample": "x"})
+    monkeypatch.setattr(bench, "cpu_baseline", lambda cfg, steps, warmup, sample_batch=None, budget_s=None: {
+        "value": 8000.0, "unit": "samples/s", "cores": 16, "kind": "port", "ms_per_step": 8192.0, "sample": "x",
+        "steps": steps, "warmup": warmup})
     monkeypatch.setenv("RANK", "0")
     monkeypatch.setenv("WORLD_SIZE", "1")
     bench.run_reference(_args(impl="reference", steps=4, warmup=1))
@@ -119,6 +120,22 @@ def test_reference_arm_line_shape(monkeypatch, capsys):
     monkeypatch.setenv("WORLD_SIZE", "2")
     bench.run_reference(_args(impl="reference"))
     assert capsys.readouterr().out == ""
+
+
+def test_reference_arm_honours_steps_and_warmup_within_its_budget():
+    """The CPU arm runs the steps / warm-up steps it is asked for when they fit its time budget (so that the driver's
+    `steps_match` / `warmup_match` hold), fewer otherwise: timed steps first, at least one."""
+    assert bench.bounded_steps(20, 5, 240.0 - 8.0, 8.0, done=1) == (20, 5)          # 16 host cores, ~8 s per step
+    assert bench.bounded_steps(20, 5, 240.0 - 21.0, 21.0, done=1) == (11, 0)        # a slower host: fewer steps, no warm-up
+    assert bench.bounded_steps(20, 5, 0.0, 300.0, done=1) == (1, 0)                 # one step already overran: it is the result
+    assert bench.bounded_steps(4, 3, 45.0, 10.0, done=2) == (4, 2)
+    tiny = dict(rows=[50, 40], dim=8, layers=[16, 8], batch=32, loss="in_batch_softmax", sparse_lr=0.01, dense_lr=0.001)
+    full = bench.cpu_baseline(tiny, steps=3, warmup=2, budget_s=1000.0)
+    assert (full["steps"], full["warmup"]) == (3, 2) and full["value"] > 0 and "3 timed step(s) after 2 warm-up" in full["sample"]
+    cut = bench.cpu_baseline(tiny, steps=3, warmup=2, budget_s=0.0)
+    assert (cut["steps"], cut["warmup"]) == (1, 0)
+    plain = bench.cpu_baseline(tiny, steps=1, warmup=1)                              # our arm's `cpu_baseline` block: no budget
+    assert (plain["steps"], plain["warmup"]) == (1, 1)
 
 
 def test_a_wedged_side_block_is_cut_at_its_own_limit():

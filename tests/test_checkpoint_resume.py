@@ -83,3 +83,72 @@ def test_optimizer_state_keys_under_the_two_tower_prefix(oracle_device_work):
     weights_only = {k: v for k, v in sd.items() if k.endswith(".weight") or k.endswith(".bias")}
     res = tt.TwoTower(_ebc(5), [8, 4], device=torch.device("cpu")).load_state_dict(weights_only, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
+
+
+def test_flat_adam_state_dict_round_trip(monkeypatch):
+    """FlatAdam keeps its moments and step in flat buffers outside ``Optimizer.state``; ``state_dict()`` carries them
+    (also through ``KeyedOptimizerWrapper`` and ``torch.save``), so a resumed run takes the same next step.  The one
+    device call (``tt_adam_flat_devstep``) is replaced by the same arithmetic in torch; tests/test_gpu_dense.py holds
+    the kernel to ``torch.optim.Adam``."""
+    import io
+
+    from two_tower_recommender_model_b200 import _native as N
+    live = []
+
+    def fake_call(name, p, g, m, v, n, lr, b1, b2, eps, step_ptr, stream):
+        assert name == "tt_adam_flat_devstep"
+        o = next(x for x in live if x.flat_param.data_ptr() == p)
+        assert (g, m, v, n, step_ptr) == (o.flat_grad.data_ptr(), o.exp_avg.data_ptr(), o.exp_avg_sq.data_ptr(), o.flat_param.numel(),
+                                          o.step_dev.data_ptr())
+        o.step_dev += 1
+        t = float(o.step_dev)
+        o.exp_avg.mul_(b1).add_(o.flat_grad, alpha=1 - b1)
+        o.exp_avg_sq.mul_(b2).addcmul_(o.flat_grad, o.flat_grad, value=1 - b2)
+        o.flat_param.addcdiv_(o.exp_avg / (1 - b1 ** t), (o.exp_avg_sq / (1 - b2 ** t)).sqrt() + eps, value=-lr)
+
+    monkeypatch.setattr(N, "require_cuda", lambda t, name: None)
+    monkeypatch.setattr(N, "call", fake_call)
+    monkeypatch.setattr(N, "stream_ptr", lambda dev: 0)
+
+    def build(seed):
+        torch.manual_seed(seed)
+        net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.ReLU(), torch.nn.Linear(8, 2))
+        opt = tt.KeyedOptimizerWrapper(dict(net.named_parameters()), lambda p: tt.FlatAdam(p, lr=1e-2))
+        live.append(opt._optimizer)
+        return net, opt
+
+    x = torch.randn(16, 4, generator=torch.Generator().manual_seed(3))
+
+    def step(net, opt):
+        opt.zero_grad()
+        net(x).pow(2).mean().backward()
+        opt.step()
+
+    a, oa = build(0)
+    want = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.ReLU(), torch.nn.Linear(8, 2))
+    want.load_state_dict(a.state_dict())
+    ow = torch.optim.Adam(want.parameters(), lr=1e-2)
+    for _ in range(2):
+        step(a, oa)
+        step(want, ow)
+    for k, v in want.state_dict().items():                         # the stand-in is Adam: FlatAdam's views / zero_grad bookkeeping hold
+        torch.testing.assert_close(a.state_dict()[k], v, rtol=1e-6, atol=1e-7)
+    sd = {k: v.clone() for k, v in a.state_dict().items()}
+    osd = oa.state_dict()
+    assert osd["flat_adam"]["step"] == 2.0 and osd["flat_adam"]["exp_avg"].numel() == sum(p.numel() for p in a.parameters())
+    buf = io.BytesIO()
+    torch.save(osd, buf)
+    buf.seek(0)
+    b, ob = build(1)                                               # resumed: weights + optimizer state (through torch.save / load)
+    b.load_state_dict(sd)
+    ob.load_state_dict(torch.load(buf))
+    assert ob.param_groups is ob._optimizer.param_groups and ob._optimizer.step_count == 2
+    c, oc = build(2)                                               # resumed from the weights only
+    c.load_state_dict(sd)
+    for net, opt in ((a, oa), (b, ob), (c, oc)):
+        step(net, opt)
+    for k in sd:
+        assert torch.equal(a.state_dict()[k], b.state_dict()[k]), k
+    assert not torch.equal(a.state_dict()["0.weight"], c.state_dict()["0.weight"])      # Adam's moments restarted: another step
+    with pytest.raises(ValueError):
+        ob._optimizer.load_state_dict(dict(osd, flat_adam=dict(osd["flat_adam"], exp_avg=torch.zeros(3))))
