@@ -117,7 +117,7 @@ def test_planner():
     plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=4, hbm_cap=8 * 2 ** 30)).plan(big)
     assert plan.plan["ebc"]["t_big"].sharding_type == "row_wise"
     assert "t_big" in str(plan)
-    # column-wise: as many shards as divide D (at most W), on distinct ranks, least-loaded first; data-parallel tables are refused
+    # column-wise: as many shards as divide D (at most W), on distinct ranks, least-loaded first
     cw = torch.nn.ModuleDict({"ebc": tt.EmbeddingBagCollection(tables=[
         tt.EmbeddingBagConfig(name="t_x", embedding_dim=36, num_embeddings=5000, feature_names=["x"]), mk("t_y", 100)], device=torch.device("meta"))})
     plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=8), constraints={"t_x": ParameterConstraints(sharding_types=["column_wise"]),
@@ -125,8 +125,15 @@ def test_planner():
     px, py = plan.plan["ebc"]["t_x"], plan.plan["ebc"]["t_y"]
     assert px.sharding_type == "column_wise" and px.ranks == [0, 1, 2, 3, 4, 5]           # 36 = 6 x 6; 7 and 8 do not divide it
     assert py.ranks == list(range(8)) and 36 % len(px.ranks) == 0 and 64 % len(py.ranks) == 0
+    # data-parallel: a replica on every rank (dense gradient all-reduce), counted against every rank's budget
+    dp = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=2), constraints={"t_x": ParameterConstraints(sharding_types=["data_parallel"])}).plan(cw)
+    assert dp.plan["ebc"]["t_x"].sharding_type == "data_parallel" and dp.plan["ebc"]["t_x"].ranks == [0, 1]
+    assert dp.plan["ebc"]["t_x"].compute_kernel == "dense" and dp.plan["ebc"]["t_y"].sharding_type == "table_wise"
+    with pytest.raises(RuntimeError):                # a replica that does not fit one GPU
+        tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=2, hbm_cap=5000 * 36 * 4), constraints={
+            "t_x": ParameterConstraints(sharding_types=["data_parallel"])}).plan(cw)
     with pytest.raises(NotImplementedError):
-        tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=2), constraints={"t_x": ParameterConstraints(sharding_types=["data_parallel"])}).plan(cw)
+        tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=2), constraints={"t_x": ParameterConstraints(sharding_types=["table_row_wise"])}).plan(cw)
 
 
 def test_shim_resolves_reference_imports():

@@ -34,6 +34,8 @@ class _OracleLookup(torch.autograd.Function):
         values, lengths = ctx.saved_tensors
         mod = ctx.mod
         grads = oracle.ebc_dense_grads(mod.specs, ctx.keys, values, lengths, g * getattr(mod, "_grad_scale", 1.0))
+        if not all(hasattr(mod.embedding_bags[s.name].weight, "_optimizer_kwargs") for s in mod.specs):
+            return (None, None, None, None) + tuple(grads)      # no in-backward optimizer: dense [R, D] gradients (OPT_DENSE_GRAD)
         for s, gr in zip(mod.specs, grads):  # "fused": row-wise Adagrad applied in backward
             w = mod.embedding_bags[s.name].weight
             oracle.rowwise_adagrad_dense(w.data, mod.state[s.name], gr, lr=w._optimizer_kwargs[0]["lr"])
@@ -56,6 +58,19 @@ class OracleLocalEbc(nn.Module):
         self.state = {s.name: torch.zeros(s.num_embeddings) for s in self.specs}
         self._features = [f for s in self.specs for f in s.feature_names]
         self._dims = [s.embedding_dim for s in self.specs for _ in s.feature_names]
+        self._cfgs = list(tables)
+
+    # what the sharded module's optimizer-state checkpoint asks of a local collection
+    def embedding_bag_configs(self):
+        return self._cfgs
+
+    def _in_backward_kind(self):
+        from two_tower_recommender_model_b200 import _native as N
+        tagged = all(hasattr(self.embedding_bags[s.name].weight, "_optimizer_kwargs") for s in self.specs)
+        return N.OPT_ROWWISE_ADAGRAD if tagged else None      # the stand-in applies row-wise Adagrad whatever the tag says
+
+    def _state_for(self, cfg, w, kind):
+        return {"sum": self.state[cfg.name]}
 
     def forward(self, kjt):
         import two_tower_recommender_model_b200 as tt
@@ -411,6 +426,171 @@ def test_column_wise_sharding_world2_gloo():
     errq = ctx.SimpleQueue()
     port = 29950 + os.getpid() % 40
     procs = [ctx.Process(target=_worker_column_wise, args=(r, 2, port, errq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    msgs = []
+    while not errq.empty():
+        msgs.append(errq.get())
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+            msgs.append("worker hung")
+    assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)
+
+
+# ------------------------------------------------------------------ data-parallel tables (the fourth sharding type the planner honours)
+DP_SPECS = [TableSpec("t_a", 40, 8, ["a"], "sum"), TableSpec("t_s", 9, 4, ["s1", "s2"], "mean"), TableSpec("t_c", 101, 4, ["c"], "sum")]
+DP_KEYS = ["c", "s2", "a", "s1"]
+
+
+def _dp_batch(rank, step=0):
+    from helpers import random_kjt
+    rows = {"a": 40, "s1": 9, "s2": 9, "c": 101}
+    return random_kjt(DP_KEYS, [rows[k] for k in DP_KEYS], B, 3, seed=300 + 10 * step + rank)
+
+
+def _worker_data_parallel(rank, world, port, optimizer, errq):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import two_tower_recommender_model_b200 as tt
+        from torch.distributed.optim import _apply_optimizer_in_backward as apply_optimizer_in_backward
+        from torch.distributed._shard.sharded_tensor import ShardedTensor
+        from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
+
+        g = torch.Generator().manual_seed(11)
+        full = {s.name: torch.randn(s.num_embeddings, s.embedding_dim, generator=g) for s in DP_SPECS}
+        cfgs = [tt.EmbeddingBagConfig(name=s.name, embedding_dim=s.embedding_dim, num_embeddings=s.num_embeddings,
+                                      feature_names=list(s.feature_names),
+                                      pooling=tt.PoolingType.MEAN if s.pooling == "mean" else tt.PoolingType.SUM) for s in DP_SPECS]
+        ebc = tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("meta"))
+        opt_cls = {"adagrad": tt.RowWiseAdagrad, "adam": tt.RowWiseAdam, "sgd": torch.optim.SGD}[optimizer]
+        apply_optimizer_in_backward(opt_cls, ebc.parameters(), {"lr": LR})
+        holder = nn.ModuleDict({"ebc": ebc})
+        plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world, compute_device="cpu"),
+                                           constraints={"t_s": ParameterConstraints(sharding_types=["data_parallel"]),
+                                                        "t_c": ParameterConstraints(sharding_types=["row_wise"])}
+                                           ).collective_plan(holder, tt.get_default_sharders(), dist.GroupMember.WORLD)
+        assert plan.plan["ebc"]["t_s"].sharding_type == "data_parallel" and plan.plan["ebc"]["t_s"].ranks == [0, 1]
+        model = tt.DistributedModelParallel(module=holder, device=torch.device("cpu"), plan=plan,
+                                            sharding_kwargs=dict(local_ebc_factory=OracleLocalEbc, bucketize_fn=oracle_bucketize))
+        sharded = model.module["ebc"]
+        assert sharded.shard_info()["t_s"] == ("data_parallel", 0, 9) and sharded.dp_ebc is not None
+        rep = sharded.dp_ebc.embedding_bags["t_s"].weight
+        assert not hasattr(rep, "_optimizer_classes")                       # the replica's backward yields the dense gradient
+        # construction broadcast rank 0's replica: identical start on every rank (then the known weights are loaded)
+        lst = [rep.detach().clone()]
+        dist.broadcast_object_list(lst, src=0)
+        assert torch.equal(lst[0], rep.detach())
+        sharded.load_state_dict({f"embedding_bags.{k}.weight": v for k, v in full.items()})
+        torch.testing.assert_close(rep.detach(), full["t_s"])
+
+        # reference: the unsharded update on the GLOBAL batch's gradient / W (dense forms; untouched rows have zero gradient)
+        ref = {k: v.clone() for k, v in full.items()}
+        st_sum = torch.zeros(9)
+        st_m, st_v = torch.zeros(9, 4), torch.zeros(9)
+        n_steps = 3
+        for step in range(n_steps):
+            values, lengths = _dp_batch(rank, step)
+            kjt = tt.KeyedJaggedTensor.from_lengths_sync(DP_KEYS, values, lengths)
+            kt = sharded(kjt)
+            want = oracle.ebc_forward(DP_SPECS, [ref[s.name] for s in DP_SPECS], DP_KEYS, values, lengths)
+            assert kt.keys() == ["a", "s1", "s2", "c"] and kt.length_per_key() == [8, 4, 4, 4]
+            torch.testing.assert_close(kt.values(), want, rtol=1e-5, atol=1e-6, msg=lambda m: f"step {step} forward: {m}")
+            gout = torch.randn(B, want.shape[1], generator=torch.Generator().manual_seed(900 + 10 * step + rank))
+            (kt.values() * gout).sum().backward()
+            model.sync_dense_grads()                 # what TrainPipelineSparseDist / CudaGraphTrainStep call after the backward
+            assert rep.grad is None
+            dense = [torch.zeros_like(ref[s.name]) for s in DP_SPECS]
+            for r in range(world):
+                v_r, l_r = _dp_batch(r, step)
+                g_r = torch.randn(B, want.shape[1], generator=torch.Generator().manual_seed(900 + 10 * step + r))
+                for acc, gr in zip(dense, oracle.ebc_dense_grads(DP_SPECS, DP_KEYS, v_r, l_r, g_r)):
+                    acc += gr
+            gs = dense[1] / world
+            if optimizer == "adagrad":
+                oracle.rowwise_adagrad_dense(ref["t_s"], st_sum, gs, lr=LR)
+            elif optimizer == "sgd":
+                ref["t_s"] -= LR * gs
+            else:                                    # row-wise Adam, touched rows only (oracle's sparse form on the rows with gradient)
+                hit = (gs != 0).any(dim=1).nonzero().flatten()
+                oracle.rowwise_adam_sparse(ref["t_s"], st_m, st_v, hit, gs[hit], step=step + 1, lr=LR)
+            # the sharded tables next to it keep their fused path (the stand-in applies row-wise Adagrad whatever the tag)
+            oracle.rowwise_adagrad_dense(ref["t_a"], sharded_state("t_a", ref), dense[0] / world, lr=LR)
+            oracle.rowwise_adagrad_dense(ref["t_c"], sharded_state("t_c", ref), dense[2] / world, lr=LR)
+            torch.testing.assert_close(rep.detach(), ref["t_s"], rtol=1e-5, atol=1e-6, msg=lambda m: f"step {step} replica: {m}")
+        # replicas stayed identical
+        lst = [rep.detach().clone()]
+        dist.broadcast_object_list(lst, src=0)
+        assert torch.equal(lst[0], rep.detach())
+
+        # state dict: the replicated table is a PLAIN tensor (utils/model_training.py:178-180 keeps rank 0's copy), the others ShardedTensors
+        sd = model.state_dict()
+        t = sd["ebc.embedding_bags.t_s.weight"]
+        assert isinstance(t, torch.Tensor) and not isinstance(t, ShardedTensor)
+        torch.testing.assert_close(t, ref["t_s"], rtol=1e-5, atol=1e-6)
+        for name in ("t_a", "t_c"):
+            t = sd[f"ebc.embedding_bags.{name}.weight"]
+            assert isinstance(t, ShardedTensor)
+            full_t = torch.zeros(t.size()) if rank == 0 else None
+            t.gather(0, full_t)
+            if rank == 0:
+                torch.testing.assert_close(full_t, ref[name], rtol=1e-5, atol=1e-6, msg=lambda m: f"{name}: {m}")
+        # optimizer state of the replica travels behind include_optimizer_state and reloads
+        sharded.include_optimizer_state(True)
+        sd2 = sharded.state_dict()
+        if optimizer == "adagrad":
+            torch.testing.assert_close(sd2["embedding_bags.t_s.sum"], st_sum, rtol=1e-5, atol=1e-7)
+        elif optimizer == "adam":
+            torch.testing.assert_close(sd2["embedding_bags.t_s.exp_avg"], st_m, rtol=1e-5, atol=1e-7)
+            torch.testing.assert_close(sd2["embedding_bags.t_s.exp_avg_sq"], st_v, rtol=1e-5, atol=1e-7)
+            assert float(sd2["fused_optimizer_step"]) == n_steps
+        # (the replica's entries only: the stand-in of the sharded tables keeps no reloadable state; their round trip is
+        # test_sharded_checkpoint_with_optimizer_state_world2_gloo's subject)
+        keep = {k: v.clone() for k, v in sd2.items() if ".t_s." in k or k == "fused_optimizer_step"}
+        sharded._dp_state.clear()
+        sharded._dp_step = 0
+        with torch.no_grad():
+            rep.zero_()
+        sharded.load_state_dict(keep, strict=False)
+        torch.testing.assert_close(rep.detach(), ref["t_s"], rtol=1e-5, atol=1e-6)
+        if optimizer == "adagrad":
+            torch.testing.assert_close(sharded._dp_state["t_s"]["sum"], st_sum, rtol=1e-5, atol=1e-7)
+        if optimizer == "adam":
+            assert sharded._dp_step == n_steps
+        # an evaluation forward (no backward, no sync) leaves everything as it is
+        with torch.no_grad():
+            values, lengths = _dp_batch(rank, 7)
+            kt = sharded(tt.KeyedJaggedTensor.from_lengths_sync(DP_KEYS, values, lengths))
+        torch.testing.assert_close(kt["s2"], oracle.ebc_forward(DP_SPECS, [ref[s.name] for s in DP_SPECS], DP_KEYS, values, lengths)[:, 12:16],
+                                   rtol=1e-5, atol=1e-6)
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put(f"rank {rank}:\n{traceback.format_exc()}")
+        raise
+
+
+_SHARDED_STATE = {}
+
+
+def sharded_state(name, ref):
+    """Row-wise Adagrad accumulator of a sharded (non-replicated) table of the reference run."""
+    return _SHARDED_STATE.setdefault(name, torch.zeros(ref[name].shape[0]))
+
+
+@pytest.mark.parametrize("optimizer", ["adagrad", "adam", "sgd"])
+def test_data_parallel_tables_world2_gloo(optimizer):
+    """A data_parallel table (two features, mean pooling) next to a table-wise and a row-wise one: the replica is looked up on
+    the rank's own batch, `sync_dense_grads` averages its dense gradient over the ranks and applies the tagged optimizer
+    (row-wise Adagrad / row-wise Adam / SGD) identically on every rank -- equal to the unsharded update on the global batch's
+    gradient / W over three steps; the state dict holds it as a plain tensor; its optimizer state reloads."""
+    ctx = mp.get_context("spawn")
+    errq = ctx.SimpleQueue()
+    port = 29700 + os.getpid() % 200 + {"adagrad": 0, "adam": 1, "sgd": 2}[optimizer]
+    procs = [ctx.Process(target=_worker_data_parallel, args=(r, 2, port, optimizer, errq)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

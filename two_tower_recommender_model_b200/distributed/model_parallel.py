@@ -6,7 +6,7 @@ keeps it data-parallel.  ``.module``, ``._plan.plan`` (03_model_training.py:819)
 
 world_size == 1: tables are materialised whole on ``device``.
 world_size  > 1: every EmbeddingBagCollection is replaced by a
-``ShardedEmbeddingBagCollection`` (table-wise / row-wise, see sharding.py) and the
+``ShardedEmbeddingBagCollection`` (table-wise / row-wise / column-wise / data-parallel, see sharding.py) and the
 dense parameters are all-reduced through one flat gradient buffer.
 """
 from typing import Any, Dict, Iterator, List, Optional, Tuple
@@ -63,6 +63,7 @@ class DistributedModelParallel(nn.Module):
                                    "EmbeddingBagCollection tables may be constructed on meta")
         module.to(self.device)
         self._dmp_wrapped_module = module
+        self._dp_modules = [m for m in module.modules() if getattr(m, "dp_ebc", None) is not None]
         if world > 1 and init_data_parallel:
             from .sharding import DenseGradSync
             self._dense_sync = DenseGradSync(module, pg)
@@ -107,5 +108,9 @@ class DistributedModelParallel(nn.Module):
         return fn(batch, ready_event)
 
     def sync_dense_grads(self) -> None:
+        """After the backward of a training step: joins (or runs) the all-reduce of the tower gradients, then averages the
+        dense gradients of data_parallel embedding tables and applies their optimizer (sharding.py)."""
         if self._dense_sync is not None:
             self._dense_sync.all_reduce()
+        for m in self._dp_modules:
+            m.sync_data_parallel()

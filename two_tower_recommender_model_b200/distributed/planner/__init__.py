@@ -5,7 +5,8 @@ The reference passes no constraints and lets TorchRec's enumerator choose; here
 the plan is a deterministic function of (tables, constraints, topology):
 
 * an explicit ``ParameterConstraints(sharding_types=[...])`` for a table wins
-  (``table_wise`` | ``row_wise`` | ``column_wise``; ``data_parallel`` tables are refused);
+  (``table_wise`` | ``row_wise`` | ``column_wise`` | ``data_parallel``: a replica on every rank, dense gradient
+  all-reduce -- meant for SMALL tables such as configs[2]'s aisle / department features);
 * otherwise tables go table-wise, largest first, each to the rank with the
   fewest bytes so far (greedy balance) -- unless a table (weights + row-wise
   optimizer state) does not fit in one GPU's budget, which makes it row-wise.
@@ -168,10 +169,16 @@ class EmbeddingShardingPlanner:
                         load[r] += nbytes // s_
                     ps = ParameterSharding(want, ranks=ranks)
                 elif want == ShardingType.DATA_PARALLEL.value:
-                    raise NotImplementedError("data_parallel embedding tables would need a dense [R,D] gradient "
-                                              "all-reduce; use table_wise or row_wise")
+                    # a full replica on every rank; its dense [R, D] gradient is all-reduced after the backward and the
+                    # table's optimizer applied to the replica (sharding.py: sync_data_parallel) -- for small tables
+                    if any(load[r] + nbytes > budget for r in range(W)):
+                        raise RuntimeError(f"table {cfg.name} ({nbytes / 2**30:.1f} GiB) does not fit every rank's budget as a "
+                                           "data_parallel replica; constrain it to row_wise")
+                    for r in range(W):
+                        load[r] += nbytes
+                    ps = ParameterSharding(want, compute_kernel="dense", ranks=list(range(W)))
                 else:
-                    raise NotImplementedError(f"sharding type {want} is not implemented (table_wise, row_wise, column_wise are)")
+                    raise NotImplementedError(f"sharding type {want} is not implemented (table_wise, row_wise, column_wise, data_parallel are)")
                 ps.num_embeddings, ps.embedding_dim = cfg.num_embeddings, cfg.embedding_dim
                 tables[cfg.name] = ps
             # report in config order

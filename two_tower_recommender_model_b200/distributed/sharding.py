@@ -310,6 +310,11 @@ class ShardedEmbeddingBagCollection(nn.Module):
         self._tw.dest_features = [[] for _ in range(W)]
         tw_local_cfgs: List[EmbeddingBagConfig] = []
         rw_local_cfgs: List[EmbeddingBagConfig] = []
+        dp_local_cfgs: List[EmbeddingBagConfig] = []
+        self._dp_features: List[str] = []                        # features of data_parallel tables, local EBC order
+        self._dp_tags: Dict[str, Dict[str, Any]] = {}            # data_parallel table -> its in-backward optimizer tags
+        self._dp_state: Dict[str, Dict[str, torch.Tensor]] = {}  # ... -> row-wise optimizer state of the replica
+        self._dp_step = 0
         self._rw_block: Dict[str, int] = {}
         self._rw_feat_block: Dict[str, int] = {}
         self._shard_info: Dict[str, Tuple[str, int, int]] = {}   # table -> (kind, row offset, local rows)
@@ -375,6 +380,14 @@ class ShardedEmbeddingBagCollection(nn.Module):
                                                         feature_names=list(c.feature_names), pooling=PoolingType.SUM,
                                                         weight_init_min=c.get_weight_init_min(), weight_init_max=c.get_weight_init_max()))
                 self._shard_info[c.name] = ("row_wise", r * block, local_rows)
+            elif ps.sharding_type == "data_parallel":
+                # a full replica on every rank: looked up locally on the rank's own batch (no exchange); its dense
+                # gradient is all-reduced and the table's optimizer applied to the replica in sync_data_parallel()
+                dp_local_cfgs.append(EmbeddingBagConfig(name=c.name, embedding_dim=c.embedding_dim, num_embeddings=c.num_embeddings,
+                                                        feature_names=list(c.feature_names), pooling=c.pooling,
+                                                        weight_init_min=c.get_weight_init_min(), weight_init_max=c.get_weight_init_max()))
+                self._dp_features.extend(c.feature_names)
+                self._shard_info[c.name] = ("data_parallel", 0, c.num_embeddings)
             else:
                 raise NotImplementedError(f"sharding type {ps.sharding_type}")
         self._tw.features = [f for d in self._tw.dest_features for f in d]
@@ -385,9 +398,19 @@ class ShardedEmbeddingBagCollection(nn.Module):
         # state_dict / load_state_dict speak TorchRec's key names (one ShardedTensor per table).
         tw_ebc = local_ebc_factory(tw_local_cfgs, self._device) if tw_local_cfgs else None
         rw_ebc = local_ebc_factory(rw_local_cfgs, self._device) if rw_local_cfgs else None
+        dp_ebc = local_ebc_factory(dp_local_cfgs, self._device) if dp_local_cfgs else None
         object.__setattr__(self, "tw_ebc", tw_ebc)
         object.__setattr__(self, "rw_ebc", rw_ebc)
+        object.__setattr__(self, "dp_ebc", dp_ebc)
         self._tw.local_ebc, self._rw.local_ebc = tw_ebc, rw_ebc
+        if dp_ebc is not None:
+            # The replicas carry NO in-backward tags: their lookup's backward returns the dense [R, D] gradient
+            # (OPT_DENSE_GRAD), which sync_data_parallel() all-reduces before it applies the table's optimizer itself.
+            # Identical start on every rank, as DDP does for the towers.
+            self._dp_tags = {c.name: tags.get(c.name, {}) for c in dp_local_cfgs}
+            src = dist.get_global_rank(pg, 0) if pg is not None else 0
+            for c in dp_local_cfgs:
+                dist.broadcast(dp_ebc.embedding_bags[c.name].weight.data, src=src, group=pg)
         self._gradient_division = get_gradient_division()
         for local in (tw_ebc, rw_ebc):
             if local is not None:
@@ -419,9 +442,82 @@ class ShardedEmbeddingBagCollection(nn.Module):
         self._pre_backward = fn
 
     def local_parameters(self):
-        for local in (self.tw_ebc, self.rw_ebc):
+        for local in (self.tw_ebc, self.rw_ebc, self.dp_ebc):
             if local is not None:
                 yield from local.parameters()
+
+    # ---- data-parallel tables -------------------------------------------------------------------
+    def _dp_sub_kjt(self, kjt: KeyedJaggedTensor) -> KeyedJaggedTensor:
+        """The rank's own batch restricted to the features of the data_parallel tables (no exchange)."""
+        keys, feats = list(kjt.keys()), self._dp_features
+        if keys == feats:
+            return kjt
+        order = [keys.index(f) for f in feats]
+        dense = getattr(kjt, "_id_columns", None)
+        if dense is not None and dense[0].is_cuda:      # one id per bag: rebuild from the id columns, no host sync
+            dev = dense[0].device
+            sel = self._cached(("dp_order", tuple(order)), lambda: torch.tensor(order, dtype=torch.int64, device=dev))
+            table_rows = {f: c.num_embeddings for c in self._configs for f in c.feature_names}
+            rows = self._cached(("dp_rows",), lambda: torch.tensor([table_rows[f] for f in feats], dtype=torch.int64, device=dev))
+            return KeyedJaggedTensor.from_id_columns(list(feats), dense[0].index_select(0, sel), rows)
+        return kjt.permute(order)
+
+    def sync_data_parallel(self) -> None:
+        """After the backward of a training step (``DistributedModelParallel.sync_dense_grads`` calls it, next to the
+        towers' all-reduce): the dense ``[R, D]`` gradient of every data_parallel table is averaged over the ranks -- the
+        gradient of the same global objective the sharded tables see through the gradient division -- and the optimizer
+        the table was tagged with (``apply_optimizer_in_backward``) is applied to the replica, identically on every
+        rank.  Row-wise Adagrad / SGD in their dense forms (a row without gradient does not move); row-wise Adam advances
+        the rows whose averaged gradient is non-zero.  Untagged tables keep the averaged ``.grad`` for the caller's
+        optimizer.  Collective: every rank calls it once per training step."""
+        if self.dp_ebc is None:
+            return
+        from ..optim.rowwise_adagrad import RowWiseAdagrad
+        from ..optim.rowwise_adam import RowWiseAdam
+        W = self._world
+        advanced = False
+        for name, tags in self._dp_tags.items():
+            w = self.dp_ebc.embedding_bags[name].weight
+            g = w.grad if w.grad is not None else torch.zeros_like(w)       # a rank without a gradient still joins
+            if self._gradient_division and g.is_cuda:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self._pg)
+            else:
+                dist.all_reduce(g, group=self._pg)
+                if self._gradient_division:
+                    g.div_(W)
+            classes = tags.get("_optimizer_classes")
+            if not classes:
+                w.grad = g
+                continue
+            cls, kw = classes[0], tags.get("_optimizer_kwargs", [{}])[0]
+            st = self._dp_state.setdefault(name, {})
+            with torch.no_grad():
+                if issubclass(cls, RowWiseAdagrad):
+                    if "sum" not in st:
+                        st["sum"] = torch.full((w.shape[0],), float(kw.get("initial_accumulator_value", 0.0)), dtype=torch.float32, device=w.device)
+                    st["sum"] += g.pow(2).mean(dim=1)
+                    w -= float(kw.get("lr", RowWiseAdagrad.DEFAULT_LR)) * g / (st["sum"].sqrt() + float(kw.get("eps", RowWiseAdagrad.DEFAULT_EPS))).unsqueeze(1)
+                elif issubclass(cls, RowWiseAdam):
+                    if "exp_avg" not in st:
+                        st["exp_avg"] = torch.zeros_like(w)
+                        st["exp_avg_sq"] = torch.zeros(w.shape[0], dtype=torch.float32, device=w.device)
+                    if not advanced:
+                        self._dp_step += 1
+                        advanced = True
+                    b1, b2 = kw.get("betas", (0.9, 0.999))
+                    t = self._dp_step
+                    hit = (g != 0).any(dim=1)
+                    m = torch.where(hit.unsqueeze(1), b1 * st["exp_avg"] + (1 - b1) * g, st["exp_avg"])
+                    v = torch.where(hit, b2 * st["exp_avg_sq"] + (1 - b2) * g.pow(2).mean(dim=1), st["exp_avg_sq"])
+                    st["exp_avg"], st["exp_avg_sq"] = m, v
+                    upd = (m / (1 - b1 ** t)) / ((v / (1 - b2 ** t)).sqrt() + float(kw.get("eps", RowWiseAdam.DEFAULT_EPS))).unsqueeze(1)
+                    w -= float(kw.get("lr", RowWiseAdam.DEFAULT_LR)) * torch.where(hit.unsqueeze(1), upd, torch.zeros_like(upd))
+                elif issubclass(cls, torch.optim.SGD):
+                    w -= float(kw.get("lr", 1e-3)) * g
+                else:
+                    raise NotImplementedError(f"optimizer {cls.__name__} on a data_parallel table; supported: RowWiseAdagrad, "
+                                              "RowWiseAdam, torch.optim.SGD (plain)")
+            w.grad = None
 
     # ---- input dist ----------------------------------------------------------------------------
     def _dist_group(self, grp: _Group, kjt: KeyedJaggedTensor):
@@ -664,6 +760,12 @@ class ShardedEmbeddingBagCollection(nn.Module):
                     col = col / ln.unsqueeze(1)
                 cols[f] = col
                 c0 += d
+        # data-parallel: the replica is looked up on the rank's own batch, nothing travels
+        if self._dp_features:
+            kt = self.dp_ebc(self._dp_sub_kjt(features))
+            for f in self._dp_features:
+                cols[f] = kt[f]
+            self._whole = None
         whole, self._whole = self._whole, None
         if whole is None:
             # a column-wise table's feature is the row of its shards' slices, in shard order
@@ -707,7 +809,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
         kind, _off, rows = self._shard_info[name]
         if rows == 0:
             return None
-        local = self.rw_ebc if kind == "row_wise" else self.tw_ebc
+        local = self._local_ebc_of(name)
         return local.embedding_bags[name].weight.detach()[:rows]
 
     def include_optimizer_state(self, on: bool = True) -> "ShardedEmbeddingBagCollection":
@@ -718,7 +820,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
         return self
 
     def _local_ebc_of(self, name: str):
-        return self.rw_ebc if self._shard_info[name][0] == "row_wise" else self.tw_ebc
+        return {"row_wise": self.rw_ebc, "data_parallel": self.dp_ebc}.get(self._shard_info[name][0], self.tw_ebc)
 
     def state_dict(self, *args, destination=None, prefix: str = "", keep_vars: bool = False):
         from .. import _native as N
@@ -730,15 +832,24 @@ class ShardedEmbeddingBagCollection(nn.Module):
                 destination[f"{prefix}embedding_bags.{c.name}.weight"] = make_col_sharded(
                     self._local_weight(c.name), self._col_info.get(c.name, (0, 0))[0], (c.num_embeddings, c.embedding_dim), self._pg)
                 continue
+            if kind == "data_parallel":
+                # replicated: a plain tensor, as TorchRec's data-parallel tables appear in a state dict
+                # (utils/model_training.py:178-180 keeps rank 0's copy)
+                destination[f"{prefix}embedding_bags.{c.name}.weight"] = self._local_weight(c.name)
+                continue
             destination[f"{prefix}embedding_bags.{c.name}.weight"] = make_row_sharded(
                 self._local_weight(c.name), off, (c.num_embeddings, c.embedding_dim), self._pg)
         if getattr(self, "_state_dict_with_optimizer", False):
             if any(k == "column_wise" for k, _o, _r in self._shard_info.values()):
                 raise NotImplementedError("include_optimizer_state: every column shard keeps its own row-wise state, which has no "
                                           "place under the unsharded key names; checkpoint column-wise tables weights-only")
-            step = 0
+            step = self._dp_step
             for c in self._configs:
                 _kind, off, rows = self._shard_info[c.name]
+                if _kind == "data_parallel":
+                    for k, v in self._dp_state.get(c.name, {}).items():
+                        destination[f"{prefix}embedding_bags.{c.name}.{k}"] = v.detach()
+                    continue
                 local = self._local_ebc_of(c.name)
                 kind = next((l._in_backward_kind() for l in (self.tw_ebc, self.rw_ebc) if l is not None), None)
                 names = {N.OPT_ROWWISE_ADAGRAD: ("sum",), N.OPT_ROWWISE_ADAM: ("exp_avg", "exp_avg_sq")}.get(kind, ())
@@ -801,6 +912,9 @@ class ShardedEmbeddingBagCollection(nn.Module):
                     w.copy_(self._rows_from(state_dict[key], off, rows, key).to(w.device))
             for k in ("sum", "exp_avg", "exp_avg_sq"):
                 skey = f"{prefix}embedding_bags.{c.name}.{k}"
+                if skey in state_dict and kind == "data_parallel":
+                    self._dp_state.setdefault(c.name, {})[k] = state_dict[skey].detach().to(device=w.device, dtype=torch.float32).clone()
+                    continue
                 if skey in state_dict and rows > 0:
                     local = self._local_ebc_of(c.name)
                     part = self._rows_from(state_dict[skey], off, rows, skey).detach().to(device=w.device, dtype=torch.float32)
@@ -811,6 +925,7 @@ class ShardedEmbeddingBagCollection(nn.Module):
                     local._fused_state.setdefault(c.name, {})[k] = part.clone()
         skey = f"{prefix}fused_optimizer_step"
         if skey in state_dict:
+            self._dp_step = int(round(float(state_dict[skey])))
             for l in (self.tw_ebc, self.rw_ebc):
                 if l is not None and hasattr(l, "_fused_step"):
                     l._fused_step = int(round(float(state_dict[skey])))

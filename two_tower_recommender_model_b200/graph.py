@@ -51,6 +51,12 @@ class CudaGraphTrainStep:
         self._stream = torch.cuda.Stream(device=self._dev)
         # sharded modules whose row-wise peer exchange adds into pre-cleared buffers (see PeerExchange.clean)
         self._sharded = [m for m in model.modules() if isinstance(getattr(m, "_peer", None), dict)]
+        for m in self._sharded:
+            if getattr(m, "dp_ebc", None) is not None:
+                # their update runs in Python after an all-reduce (row-wise Adam's bias correction is a host-side step count)
+                raise NotImplementedError("CudaGraphTrainStep: data_parallel embedding tables are updated outside the kernels "
+                                          "(sharding.py: sync_data_parallel); run the step eagerly (TrainPipelineSparseDist) or "
+                                          "shard these tables table_wise / row_wise")
 
     def _clean_exchanges(self) -> None:
         """A captured step assumes the scatter-add buffer it was captured with is clear; eager forwards without a
