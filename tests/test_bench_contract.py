@@ -78,6 +78,32 @@ def test_side_blocks_are_recorded_one_by_one_and_a_failing_block_does_not_take_t
     assert len(calls) == 3
 
 
+def test_a_sharding_that_failed_its_parity_check_is_not_timed(monkeypatch):
+    """N > 1: a failed row-wise parity check leaves the table-wise headline standing; the blocks that would run row-wise
+    (strong_row_wise always, weak once the ranks outnumber the two tables) are recorded as skipped, on every rank alike."""
+    calls = []
+
+    def fake_time_block(cfg, B, dev, rank, world, local, args, sharding, exchange, lib, with_kernels):
+        calls.append((B, sharding, cfg.get("negatives", "local")))
+        return _block(ms=0.5, B=B, sharding=[sharding or "table_wise"])
+
+    monkeypatch.setattr(bench, "time_block", fake_time_block)
+    monkeypatch.setattr(bench, "retrieval_probe_sharded", lambda dev, rank, world: {"queries_per_s_total": 1.0})
+    for world, weak_timed in ((8, False), (2, True)):
+        calls.clear()
+        line = {"value": 1.0}
+        bench.side_blocks(_args(gpus=world, parity_failed=["row_wise"]), dict(bench.CFG2), None, 0, world, 0, None, 65536, line)
+        assert "skipped" in line["strong_row_wise"] and "row_wise" in line["strong_row_wise"]["skipped"]
+        assert ("skipped" not in line["weak"]) == weak_timed
+        assert "value" in line["strong_global_negatives"] and line["retrieval"] == {"queries_per_s_total": 1.0}
+        assert [c[1] for c in calls] == ([None, "table_wise"] if weak_timed else ["table_wise"])
+    # and the headline line names the failed sharding next to the parity records
+    parity = [{"mode": "table_wise/peer/eager", "ok": True}, {"mode": "row_wise/peer/eager", "ok": False}]
+    line = bench.headline(_args(gpus=8, parity_failed=["row_wise"]), dict(bench.CFG2), _block(B=8192, sharding=["table_wise"]), bench.peaks(), 8, 65536,
+                          "configs[1] on 8 GPUs", "strong", parity)
+    assert line["parity_failed"] == ["row_wise"] and line["parity"] == parity and line["value"] > 0
+
+
 @pytest.mark.parametrize("have_line", [True, False])
 def test_watchdog_prints_the_headline_once_it_exists(have_line, tmp_path):
     code = (
