@@ -384,3 +384,48 @@ def test_oracle_ndcg_against_sklearn():
         assert abs(got - want) < 1e-9, (pred, tgt, k, got, want)
         checked += 1
     assert checked > 150
+
+
+@pytest.mark.parametrize("eps", [1e-10, 1e-8])
+def test_rowwise_adagrad_at_dim_1_is_torch_adagrad(eps):
+    """A pin that stock torch holds: with one column per row the row-wise mean of g^2 IS g^2, so row-wise Adagrad
+    (oracle/ebc.py, restating torchrec.optim.RowWiseAdagrad) must equal ``torch.optim.Adagrad`` step for step --
+    accumulate first, eps OUTSIDE the square root, lr_decay = 0.  Both eps values SURVEY 8(c) item 5 names."""
+    g0 = torch.Generator().manual_seed(3)
+    w = torch.randn(50, 1, generator=g0)
+    p = torch.nn.Parameter(w.clone())
+    opt = torch.optim.Adagrad([p], lr=0.05, eps=eps, initial_accumulator_value=0.0, lr_decay=0.0)
+    s = torch.zeros(50)
+    w_sparse, s_sparse = w.clone(), torch.zeros(50)
+    for step in range(5):
+        grad = torch.randn(50, 1, generator=g0)
+        grad[torch.rand(50, generator=g0) < 0.5] = 0.0          # rows without an occurrence this step
+        p.grad = grad.clone()
+        opt.step()
+        oracle.rowwise_adagrad_dense(w, s, grad, lr=0.05, eps=eps)
+        rows = grad[:, 0].nonzero().flatten()
+        oracle.rowwise_adagrad_sparse(w_sparse, s_sparse, rows, grad[rows], lr=0.05, eps=eps)
+        torch.testing.assert_close(w, p.detach(), rtol=1e-6, atol=1e-7, msg=lambda m: f"step {step}: {m}")
+        torch.testing.assert_close(s, opt.state[p]["sum"].reshape(-1), rtol=1e-6, atol=1e-12)
+        torch.testing.assert_close(w_sparse, w, rtol=1e-6, atol=1e-7)
+
+
+def test_rowwise_adam_at_dim_1_is_torch_adam():
+    """The same pin for the row-wise Adam extension (FBGEMM PARTIAL_ROWWISE_ADAM semantics): at one column per row, with
+    every row touched at every step, it must equal ``torch.optim.Adam`` -- first moment, second moment, both bias
+    corrections, eps added to sqrt(v_hat)."""
+    g0 = torch.Generator().manual_seed(4)
+    w = torch.randn(40, 1, generator=g0)
+    p = torch.nn.Parameter(w.clone())
+    opt = torch.optim.Adam([p], lr=0.02, betas=(0.9, 0.999), eps=1e-8)
+    m, v = torch.zeros(40, 1), torch.zeros(40)
+    rows = torch.arange(40)
+    for step in range(1, 6):
+        grad = torch.randn(40, 1, generator=g0)
+        p.grad = grad.clone()
+        opt.step()
+        oracle.rowwise_adam_sparse(w, m, v, rows, grad, step, lr=0.02, beta1=0.9, beta2=0.999, eps=1e-8)
+        torch.testing.assert_close(w, p.detach(), rtol=1e-5, atol=1e-7, msg=lambda msg: f"step {step}: {msg}")
+        # torch forms the first moment with lerp_ (m + (1 - b1) * (g - m)): same value, another rounding
+        torch.testing.assert_close(m, opt.state[p]["exp_avg"], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(v, opt.state[p]["exp_avg_sq"].reshape(-1), rtol=1e-5, atol=1e-10)
