@@ -7,6 +7,19 @@ import torch
 from oracle.ebc import TableSpec
 
 
+FBGEMM_BUCKETIZE_VECTOR = dict(
+    # fbgemm_gpu's own unit-test vector for block_bucketize_sparse_features (fbgemm_gpu/test/sparse_ops_test.py,
+    # test_block_bucketize_sparse_features; the dependency pinned at requirements.txt:2 is not installable here, so the vector
+    # is quoted from its test suite and RE-DERIVED BY HAND in the comments of test_bucketize_fbgemm_unit_test_vector):
+    # T = 4 features, B = 2, my_size = 2, block_sizes = [5, 15, 10, 20]
+    lengths=[0, 2, 1, 3, 2, 3, 3, 1],
+    indices=[3, 4, 15, 11, 28, 29, 1, 10, 11, 12, 13, 11, 22, 20, 20],
+    block_sizes=[5, 15, 10, 20], my_size=2, B=2,
+    new_lengths=[0, 2, 0, 1, 1, 0, 1, 0, 0, 0, 1, 2, 1, 3, 2, 1],
+    new_indices=[3, 4, 11, 1, 11, 0, 13, 14, 0, 1, 2, 3, 2, 0, 0],
+    unbucketize_permute=[0, 1, 5, 2, 6, 7, 3, 8, 9, 10, 11, 4, 12, 13, 14])
+
+
 def random_kjt(keys: Sequence[str], rows: Sequence[int], batch: int, max_len: int, seed: int,
                empty_frac: float = 0.2, dup_pool: int = 0):
     """Returns (values int64, lengths int32).  ``dup_pool`` > 0 draws ids from a small

@@ -277,3 +277,44 @@ def test_retrieval_with_an_empty_query_batch():
         s, i = index.search(torch.zeros(0, 8), 10)
         assert s.shape == (0, 10) and i.shape == (0, 10) and s.dtype == torch.float32 and i.dtype == torch.int64
 
+
+
+def test_torchrec_docstring_examples(monkeypatch):
+    """The examples TorchRec publishes in its own docstrings (torchrec 0.7 / 1.0, the versions the reference pins at
+    requirements.txt:1; not installable here, quoted from their documentation), on this package's containers:
+    KeyedJaggedTensor -- keys [Feature0, Feature1], bags [V0 V1] [] [V2] / [V3] [V4] [V5 V6 V7]  ->  lengths [2 0 1 1 1 3],
+    offsets [0 2 2 3 4 5 8], offset_per_key [0 3 8];  EmbeddingBagCollection -- tables t1 (dim 3, feature f1) and t2 (dim 4,
+    feature f2) on the same bags  ->  pooled values of shape [3, 7], keys [f1, f2], offset_per_key [0 3 7]."""
+    vals = torch.arange(8)
+    by_lengths = tt.KeyedJaggedTensor(keys=["Feature0", "Feature1"], values=vals, lengths=torch.tensor([2, 0, 1, 1, 1, 3], dtype=torch.int32))
+    by_offsets = tt.KeyedJaggedTensor(keys=["Feature0", "Feature1"], values=vals, offsets=torch.tensor([0, 2, 2, 3, 4, 5, 8], dtype=torch.int32))
+    for kjt in (by_lengths, by_offsets):
+        assert kjt.lengths().tolist() == [2, 0, 1, 1, 1, 3] and kjt.offsets().tolist() == [0, 2, 2, 3, 4, 5, 8]
+        assert kjt.offset_per_key() == [0, 3, 8] and kjt.length_per_key() == [3, 5] and kjt.stride() == 3
+        assert kjt["Feature0"].values().tolist() == [0, 1, 2] and kjt["Feature1"].lengths().tolist() == [1, 1, 3]
+        assert kjt.to_dict()["Feature1"].values().tolist() == [3, 4, 5, 6, 7]
+    # the EmbeddingBagCollection example; the one device call is replaced by the oracle (tests only)
+    import oracle
+    from oracle.ebc import TableSpec
+    from two_tower_recommender_model_b200 import _native as N
+    from two_tower_recommender_model_b200.modules import embedding_modules
+
+    class Lookup(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, ebc, kjt_keys, values, offsets, batch, *anchors):
+            specs = [TableSpec(c.name, c.num_embeddings, c.embedding_dim, list(c.feature_names)) for c in ebc.embedding_bag_configs()]
+            ws = [ebc.embedding_bags[s.name].weight.detach() for s in specs]
+            return oracle.ebc_forward(specs, ws, list(kjt_keys), values, (offsets[1:] - offsets[:-1]).to(torch.int32))
+
+    monkeypatch.setattr(embedding_modules, "EbcLookup", Lookup)
+    monkeypatch.setattr(N, "require_cuda", lambda t, name: None)
+    ebc = tt.EmbeddingBagCollection(tables=[
+        tt.EmbeddingBagConfig(name="t1", embedding_dim=3, num_embeddings=10, feature_names=["f1"]),
+        tt.EmbeddingBagConfig(name="t2", embedding_dim=4, num_embeddings=10, feature_names=["f2"])], device=torch.device("cpu"))
+    features = tt.KeyedJaggedTensor(keys=["f1", "f2"], values=vals, offsets=torch.tensor([0, 2, 2, 3, 4, 5, 8], dtype=torch.int32))
+    with torch.no_grad():
+        pooled = ebc(features)
+    assert tuple(pooled.values().shape) == (3, 7) and pooled.keys() == ["f1", "f2"] and pooled.offset_per_key() == [0, 3, 7]
+    w1, w2 = ebc.embedding_bags["t1"].weight.detach(), ebc.embedding_bags["t2"].weight.detach()
+    torch.testing.assert_close(pooled["f1"], torch.stack([w1[0] + w1[1], torch.zeros(3), w1[2]]))          # sum pooling, empty bag -> zeros
+    torch.testing.assert_close(pooled["f2"], torch.stack([w2[3], w2[4], w2[5] + w2[6] + w2[7]]))

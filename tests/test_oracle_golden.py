@@ -11,7 +11,7 @@ import torch.nn.functional as F
 import oracle
 from oracle.ebc import TableSpec
 from oracle.kjt import block_bucketize_vectorized
-from helpers import load_reference_golden, random_kjt
+from helpers import FBGEMM_BUCKETIZE_VECTOR, load_reference_golden, random_kjt
 
 with open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")) as f:
     G = json.load(f)
@@ -70,6 +70,18 @@ def test_bucketize_out_of_range_ids_kat():
         assert nl.tolist() == [0, 1, 0, 1, 0, 0, 1, 0, 1, 0, 0, 0]
         assert nv.tolist() == [4, 6148914691236517205, 33, 3]
         assert unb.tolist() == [3, 0, 2, 1]
+
+
+def test_bucketize_fbgemm_unit_test_vector():
+    """The oracle's block_bucketize against the vector fbgemm's own test suite holds (tests/helpers.py: FBGEMM_BUCKETIZE_VECTOR).  By hand:
+    bags f0: [] [3 4]; f1: [15] [11 28 29]; f2: [1 10] [11 12 13]; f3: [11 22 20] [20].  bucket = id // block, local = id % block:
+    f0 (5): 3, 4 -> bucket 0; f1 (15): 15 -> (1, 0), 11 -> (0, 11), 28 -> (1, 13), 29 -> (1, 14); f2 (10): 1 -> (0, 1), 10 -> (1, 0),
+    11 12 13 -> (1, 1 2 3); f3 (20): 11 -> (0, 11), 22 -> (1, 2), 20 -> (1, 0), 20 -> (1, 0).  Output order [bucket][feature][sample]."""
+    c = FBGEMM_BUCKETIZE_VECTOR
+    rows = [b * c["my_size"] for b in c["block_sizes"]]           # the oracle derives block = ceil(rows / W)
+    for fn in (oracle.block_bucketize_sparse_features, block_bucketize_vectorized):
+        nl, nv, unb = fn(T(c["lengths"], dtype=torch.int32), T(c["indices"]), rows, c["my_size"], c["B"])
+        assert nl.tolist() == c["new_lengths"] and nv.tolist() == c["new_indices"] and unb.tolist() == c["unbucketize_permute"]
 
 
 @pytest.mark.parametrize("seed", range(5))
