@@ -318,3 +318,48 @@ def test_torchrec_docstring_examples(monkeypatch):
     w1, w2 = ebc.embedding_bags["t1"].weight.detach(), ebc.embedding_bags["t2"].weight.detach()
     torch.testing.assert_close(pooled["f1"], torch.stack([w1[0] + w1[1], torch.zeros(3), w1[2]]))          # sum pooling, empty bag -> zeros
     torch.testing.assert_close(pooled["f2"], torch.stack([w2[3], w2[4], w2[5] + w2[6] + w2[7]]))
+
+
+def test_a_replaced_loss_fn_is_called_like_the_reference_does(monkeypatch):
+    """utils/model_training.py:129-140: the task's loss is ``self.loss_fn(logits, labels.float())``.  The plain mean BCE is
+    computed by the fused kernel; a module put in its place (here ``pos_weight``) must be honoured, not silently ignored."""
+    import oracle
+    from oracle.ebc import TableSpec
+    from two_tower_recommender_model_b200 import _native as N
+    from two_tower_recommender_model_b200 import two_tower as two_tower_mod
+    from two_tower_recommender_model_b200.modules import embedding_modules, mlp
+
+    class Lookup(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, ebc, kjt_keys, values, offsets, batch, *anchors):
+            specs = [TableSpec(c.name, c.num_embeddings, c.embedding_dim, list(c.feature_names)) for c in ebc.embedding_bag_configs()]
+            ws = [ebc.embedding_bags[s.name].weight.detach() for s in specs]
+            return oracle.ebc_forward(specs, ws, list(kjt_keys), values, (offsets[1:] - offsets[:-1]).to(torch.int32))
+
+    fused_calls = []
+
+    def fused_bce(q, c, labels):
+        fused_calls.append(1)
+        logits = (q * c).sum(dim=1)
+        return torch.nn.functional.binary_cross_entropy_with_logits(logits, labels.float()), logits
+
+    monkeypatch.setattr(embedding_modules, "EbcLookup", Lookup)
+    monkeypatch.setattr(mlp, "linear_act", lambda x, w, b, relu: torch.relu(torch.nn.functional.linear(x, w, b)) if relu else torch.nn.functional.linear(x, w, b))
+    monkeypatch.setattr(two_tower_mod, "dot_bce_loss", fused_bce)
+    monkeypatch.setattr(N, "require_cuda", lambda t, name: None)
+    torch.manual_seed(0)
+    ebc = tt.EmbeddingBagCollection(tables=[tt.EmbeddingBagConfig(name=f"t_{k}", embedding_dim=8, num_embeddings=20, feature_names=[k])
+                                            for k in ("u", "i")], device=torch.device("cpu"))
+    task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, [8, 4], device=torch.device("cpu")))
+    kjt = tt.KeyedJaggedTensor.from_lengths_sync(["u", "i"], torch.arange(12) % 20, torch.ones(12, dtype=torch.int32))
+    batch = tt.Batch(torch.zeros(1), kjt, torch.tensor([1, 0, 0, 1, 0, 0], dtype=torch.int32))
+    with torch.no_grad():
+        plain, (_, logits, labels) = task(batch)
+        assert fused_calls == [1] and task._loss_fn_is_plain_bce()
+        task.loss_fn = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor(3.0))
+        weighted, (_, logits_w, _) = task(batch)
+    assert fused_calls == [1]                                   # the fused kernel was not used for the replaced loss
+    torch.testing.assert_close(logits_w, logits)
+    want = torch.nn.functional.binary_cross_entropy_with_logits(logits, labels.float(), pos_weight=torch.tensor(3.0))
+    torch.testing.assert_close(weighted, want)
+    assert abs(float(weighted) - float(plain)) > 1e-4

@@ -134,12 +134,22 @@ class TwoTowerTrainTask(nn.Module):
         self.two_tower = two_tower
         self.loss_kind = loss
         self.temperature = temperature
-        self.loss_fn: nn.Module = nn.BCEWithLogitsLoss()  # kept for API parity; the fused kernel computes it
+        # the reference's attribute (utils/model_training.py:129); while it is the plain mean BCE-with-logits the fused kernel
+        # computes it, a loss module put in its place (pos_weight, a weighted BCE as ray_tune_optuna_tuning_alex_test.py:309-330)
+        # is CALLED on the row-wise dot products, as the reference's forward does (utils/model_training.py:136-140)
+        self.loss_fn: nn.Module = nn.BCEWithLogitsLoss()
+
+    def _loss_fn_is_plain_bce(self) -> bool:
+        f = self.loss_fn
+        return (type(f) is nn.BCEWithLogitsLoss and f.weight is None and f.pos_weight is None and f.reduction == "mean")
 
     def forward(self, batch: Batch) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
         uses_dense = getattr(self.two_tower, "dense_index", None) is not None
         query_embedding, candidate_embedding = self.two_tower(batch if uses_dense else batch.sparse_features)
-        if self.loss_kind == "bce":
+        if self.loss_kind == "bce" and not self._loss_fn_is_plain_bce():
+            logits = (query_embedding * candidate_embedding).sum(dim=1).squeeze()
+            loss = self.loss_fn(logits, batch.labels.float())
+        elif self.loss_kind == "bce":
             loss, logits = dot_bce_loss(query_embedding, candidate_embedding, batch.labels)
         else:
             loss, logits = in_batch_softmax_loss(query_embedding, candidate_embedding, self.temperature, self.precision,
