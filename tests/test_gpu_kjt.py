@@ -75,21 +75,6 @@ def test_block_bucketize(cuda, F, B, L, W, rows):
     assert torch.equal((nv.cpu() + w_of * blocks[f_of])[unb.cpu()], v)
 
 
-def test_block_bucketize_fbgemm_unit_test_vector(cuda):
-    """tt_kjt_block_bucketize on the vector fbgemm's own test suite holds for block_bucketize_sparse_features
-    (tests/helpers.py: FBGEMM_BUCKETIZE_VECTOR, re-derived by hand in tests/test_oracle_golden.py): T = 4, B = 2, my_size = 2."""
-    from two_tower_recommender_model_b200.functional import block_bucketize
-    from helpers import FBGEMM_BUCKETIZE_VECTOR as c
-    rows = [b * c["my_size"] for b in c["block_sizes"]]
-    l = torch.tensor(c["lengths"], dtype=torch.int32)
-    v = torch.tensor(c["indices"], dtype=torch.int64)
-    off = oracle.lengths_to_offsets(l)
-    nl, no, nv, unb = block_bucketize(l.to(cuda), off.to(cuda), v.to(cuda), torch.tensor(rows), 4, c["B"], c["my_size"])
-    assert nl.cpu().tolist() == c["new_lengths"] and nv.cpu().tolist() == c["new_indices"]
-    assert unb.cpu().tolist() == c["unbucketize_permute"]
-    assert torch.equal(no.cpu(), oracle.lengths_to_offsets(torch.tensor(c["new_lengths"], dtype=torch.int32)))
-
-
 def test_block_bucketize_out_of_range_ids(cuda):
     """Ids outside [0, block*W) (a KJT built without the reference's modulo, negative ids) take fbgemm's fallback
     bucket = id % W, local = id / W on unsigned ids: no out-of-bounds write, same answer as the oracle."""

@@ -128,7 +128,9 @@ def _run_ranks(target, args_of_rank, world=2, timeout=300):
     assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)
 
 
-MODES = ["table_wise", "row_wise", "table_wise_peer", "table_wise_dense", "table_wise_dense_peer", "row_wise_dense_peer", "column_wise"]
+MODES = ["table_wise", "row_wise", "table_wise_peer", "table_wise_dense", "table_wise_dense_peer", "row_wise_dense_peer"]
+# "column_wise" (same worker) lives in tests/test_gpu_zz_multi_column_wise.py: it was written after the round's GPU budget was
+# spent, and files sort so that a first run of it cannot hide the modes above, which have run green on 2 GPUs
 
 
 @pytest.mark.parametrize("sharding", MODES)
