@@ -363,3 +363,23 @@ def test_a_replaced_loss_fn_is_called_like_the_reference_does(monkeypatch):
     want = torch.nn.functional.binary_cross_entropy_with_logits(logits, labels.float(), pos_weight=torch.tensor(3.0))
     torch.testing.assert_close(weighted, want)
     assert abs(float(weighted) - float(plain)) > 1e-4
+
+
+def test_build_digest_does_not_depend_on_where_the_tree_lies(tmp_path):
+    """The GPU box runs from a scratch copy of the tree: the library built here must count as current there (no recompile
+    in smoke()), and a changed source must not."""
+    import importlib.util
+    import shutil
+    from two_tower_recommender_model_b200 import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dst = tmp_path / "elsewhere"
+    shutil.copytree(os.path.join(root, "two_tower_recommender_model_b200", "csrc"), dst / "two_tower_recommender_model_b200" / "csrc")
+    shutil.copytree(os.path.join(root, "include"), dst / "include")
+    shutil.copy(os.path.join(root, "two_tower_recommender_model_b200", "build.py"), dst / "two_tower_recommender_model_b200" / "build.py")
+    spec = importlib.util.spec_from_file_location("build_elsewhere", dst / "two_tower_recommender_model_b200" / "build.py")
+    other = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(other)
+    assert other.CSRC != build.CSRC and other._digest() == build._digest()
+    with open(dst / "two_tower_recommender_model_b200" / "csrc" / "common.cuh", "a") as f:
+        f.write("\n// changed\n")
+    assert other._digest() != build._digest()

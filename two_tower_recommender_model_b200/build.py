@@ -40,11 +40,13 @@ def _digest() -> str:
     h = hashlib.sha256()
     paths = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     paths.append(os.path.join(INCLUDE, "tt_b200.h"))
+    # file NAMES and contents, flags without the -I directories: the digest must not depend on where the tree lies
+    # (the GPU box runs from a scratch copy; a path-dependent digest made every smoke() there recompile the library)
     for p in paths:
-        h.update(p.encode())
+        h.update(os.path.basename(p).encode())
         with open(p, "rb") as f:
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(f for f in NVCC_FLAGS if not f.startswith("-I")).encode())
     return h.hexdigest()
 
 
