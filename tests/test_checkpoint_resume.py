@@ -152,3 +152,18 @@ def test_flat_adam_state_dict_round_trip(monkeypatch):
     assert not torch.equal(a.state_dict()["0.weight"], c.state_dict()["0.weight"])      # Adam's moments restarted: another step
     with pytest.raises(ValueError):
         ob._optimizer.load_state_dict(dict(osd, flat_adam=dict(osd["flat_adam"], exp_avg=torch.zeros(3))))
+
+
+def test_optimizer_state_of_the_wrong_size_is_refused(oracle_device_work):
+    """The fused update indexes the accumulators by row: a checkpoint entry of another table size must fail the load (as a
+    weight of the wrong size does), not become a buffer the kernel writes past."""
+    a = _ebc(0)
+    _step(a, 0)
+    sd = {k: v.clone() for k, v in a.include_optimizer_state(True).state_dict().items()}
+    sd["embedding_bags.t_u.sum"] = sd["embedding_bags.t_u.sum"][:-3].clone()
+    b = _ebc(1)
+    with pytest.raises(RuntimeError, match="size mismatch for embedding_bags.t_u.sum"):
+        b.load_state_dict(sd)
+    assert "t_u" not in b.fused_optimizer_state() or "sum" not in b.fused_optimizer_state()["t_u"]
+    with pytest.raises(ValueError, match="t_i.sum"):
+        b.load_fused_optimizer_state({"t_i": {"sum": torch.zeros(ROWS[1] + 1)}})

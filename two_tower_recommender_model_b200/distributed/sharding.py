@@ -918,6 +918,9 @@ class ShardedEmbeddingBagCollection(nn.Module):
                 if skey in state_dict and rows > 0:
                     local = self._local_ebc_of(c.name)
                     part = self._rows_from(state_dict[skey], off, rows, skey).detach().to(device=w.device, dtype=torch.float32)
+                    if part.shape[0] != rows or (k == "exp_avg" and tuple(part.shape[1:]) != (c.embedding_dim,)):
+                        raise RuntimeError(f"size mismatch for {skey}: this rank needs rows [{off}, {off + rows}) of a "
+                                           f"{c.num_embeddings}-row table, the checkpoint entry gives {tuple(part.shape)}")
                     full_rows = local.embedding_bags[c.name].weight.shape[0]
                     if part.shape[0] != full_rows:      # a row-wise shard padded to >= 1 row
                         pad = torch.zeros((full_rows - part.shape[0],) + tuple(part.shape[1:]), dtype=part.dtype, device=part.device)

@@ -305,6 +305,10 @@ class EmbeddingBagCollection(nn.Module):
     def load_fused_optimizer_state(self, state: Dict[str, Dict[str, torch.Tensor]], step: int = 0) -> None:
         for name, st in state.items():
             w = self.embedding_bags[name].weight
+            for k, v in st.items():
+                want = tuple(w.shape) if k == "exp_avg" else (w.shape[0],)
+                if tuple(v.shape) != want:
+                    raise ValueError(f"fused optimizer state {name}.{k}: shape {tuple(v.shape)}, table needs {want}")
             self._fused_state[name] = {k: v.to(w.device).clone() for k, v in st.items()}
         self._fused_step = int(step)
         self._fused_step_dev = None
@@ -345,7 +349,13 @@ class EmbeddingBagCollection(nn.Module):
         for key in [k for k in state_dict if k in names]:
             cfg, k = names[key]
             w = self.embedding_bags[cfg.name].weight
-            self._fused_state.setdefault(cfg.name, {})[k] = state_dict.pop(key).detach().to(device=w.device, dtype=torch.float32).clone()
+            t = state_dict.pop(key)
+            want = (cfg.num_embeddings, cfg.embedding_dim) if k == "exp_avg" else (cfg.num_embeddings,)
+            if tuple(t.shape) != want:
+                # the update kernel indexes the state by row: a shorter tensor would be written out of bounds
+                error_msgs.append(f"size mismatch for {key}: checkpoint {tuple(t.shape)}, table needs {want}")
+                continue
+            self._fused_state.setdefault(cfg.name, {})[k] = t.detach().to(device=w.device, dtype=torch.float32).clone()
         step_key = prefix + "fused_optimizer_step"
         if step_key in state_dict:
             self._fused_step = int(round(float(state_dict.pop(step_key))))
