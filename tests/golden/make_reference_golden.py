@@ -362,7 +362,7 @@ def main():
     out["top100_ids"] = order.indices[:, :100].numpy().astype(np.int64)
     out["meta"] = np.asarray([EMB[0], EMB[1], DIM, LAYERS[0], LAYERS[1], B, STEPS], dtype=np.int64)
     out["lr"] = np.float32(LR)
-    path = os.path.join(HERE, "reference_train.npz")
+    path = os.path.join(os.environ.get("TT_GOLDEN_OUT", HERE), "reference_train.npz")      # TT_GOLDEN_OUT: write elsewhere (tests/test_golden_provenance.py)
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {os.path.getsize(path)} bytes, losses {[float(out[f'step{i}_loss']) for i in range(STEPS)]}, eval {avg_loss:.6f}")
     dist.destroy_process_group()

@@ -70,7 +70,7 @@ def main():
         ours = f"{rename.get(head, head)}.{rest}"
         out["weight." + ours] = p.detach().numpy()
         out["grad." + ours] = p.grad.numpy()
-    path = os.path.join(HERE, "reference_raytune.npz")
+    path = os.path.join(os.environ.get("TT_GOLDEN_OUT", HERE), "reference_raytune.npz")      # TT_GOLDEN_OUT: write elsewhere (tests/test_golden_provenance.py)
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {os.path.getsize(path)} bytes, loss {float(loss):.6f}, |logits| max {float(logits.abs().max()):.3f}")
 
