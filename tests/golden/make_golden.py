@@ -112,7 +112,7 @@ def main():
         g = torch.randn(7); gs.append(L(g)); p.grad = g.clone(); opt.step()
     G["adam_torch"] = {"source": "torch", "p0": L(p0_), "grads": gs, "lr": 0.05, "p3": L(p.detach())}
 
-    with open(os.path.join(HERE, "golden.json"), "w") as f:
+    with open(os.path.join(os.environ.get("TT_GOLDEN_OUT", HERE), "golden.json"), "w") as f:      # TT_GOLDEN_OUT: tests/test_golden_provenance.py
         json.dump(G, f, indent=1)
     print("wrote", len(G), "cases")
 

@@ -33,3 +33,31 @@ def test_generators_reproduce_the_committed_fixtures(tmp_path, script, fixture):
             assert (a == b).mean() >= 0.999, k           # a near-tie may swap under a reordered sum
         else:
             assert np.array_equal(a, b), k
+
+
+def test_stock_torch_generator_reproduces_golden_json(tmp_path):
+    """tests/golden/golden.json (hand KATs + outputs of stock torch ops): regenerated and compared value by value."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(GOLDEN, "make_golden.py")], capture_output=True, text=True,
+                       env=dict(os.environ, TT_GOLDEN_OUT=str(tmp_path)), cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    with open(tmp_path / "golden.json") as f:
+        new = json.load(f)
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        old = json.load(f)
+
+    def same(a, b, path):
+        if isinstance(a, dict):
+            assert isinstance(b, dict) and sorted(a) == sorted(b), path
+            for k in a:
+                same(a[k], b[k], f"{path}.{k}")
+        elif isinstance(a, list):
+            assert isinstance(b, list) and len(a) == len(b), path
+            for i, (x, y) in enumerate(zip(a, b)):
+                same(x, y, f"{path}[{i}]")
+        elif isinstance(a, float) or isinstance(b, float):
+            assert abs(a - b) <= 1e-6 + 2e-5 * abs(a), (path, a, b)
+        else:
+            assert a == b, (path, a, b)
+
+    same(old, new, "golden")
