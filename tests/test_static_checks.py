@@ -148,3 +148,64 @@ def test_every_c_abi_call_site_matches_the_ctypes_signature():
                 problems.append(f"{where}: {name} called with {nargs} arguments, its signature has {len(SIGNATURES[name][1])}")
     assert not problems, "\n".join(problems)
     assert len(called) >= 50          # the scan found the call sites (54 entry points, tt_adam_flat is for C hosts only)
+
+
+def test_package_and_oracle_attributes_used_by_gpu_only_code_exist():
+    """``tt.X.Y`` / ``oracle.X`` chains written in tests, bench.py, tools and the driver entry resolve to real attributes, and every
+    ``from <project module> import name`` names something that exists (static attributes of modules and classes only)."""
+    import importlib
+    import sys
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import oracle
+    import two_tower_recommender_model_b200 as tt
+    import two_tower_recommender_model_b200._native  # noqa: F401
+    import two_tower_recommender_model_b200.functional  # noqa: F401
+    roots = {"tt": tt, "oracle": oracle}
+    module_type = type(os)
+    problems = set()
+    own = ("two_tower_recommender_model_b200", "oracle", "helpers", "run_configs", "bench", "test_reference_boundary", "test_gpu_multi")
+    for fn in _python_files():
+        rel = os.path.relpath(fn, ROOT)
+        with open(fn) as f:
+            tree = ast.parse(f.read(), fn)
+        pkg = rel[:-3].replace(os.sep, ".").rsplit(".", 1)[0] if rel.startswith("two_tower_recommender_model_b200") else None
+        if pkg is not None and rel.endswith("__init__.py"):
+            pkg = rel[:-len("/__init__.py")].replace(os.sep, ".")
+        for n in ast.walk(tree):
+            if isinstance(n, ast.Attribute) and pkg is None:
+                parts, base = [], n
+                while isinstance(base, ast.Attribute):
+                    parts.append(base.attr)
+                    base = base.value
+                if isinstance(base, ast.Name) and base.id in roots:
+                    obj = roots[base.id]
+                    for i, p in enumerate(reversed(parts)):
+                        if not hasattr(obj, p):
+                            if isinstance(obj, (module_type, type)):
+                                problems.add(f"{rel}:{n.lineno}: {base.id}.{'.'.join(list(reversed(parts))[:i + 1])}")
+                            break
+                        obj = getattr(obj, p)
+            elif isinstance(n, ast.ImportFrom):
+                mod = n.module or ""
+                if n.level:
+                    if pkg is None:
+                        continue
+                    base_parts = pkg.split(".")
+                    base_parts = base_parts[:len(base_parts) - (n.level - 1)]
+                    mod = ".".join(base_parts + ([mod] if mod else []))
+                if not mod.startswith(own):
+                    continue
+                try:
+                    m = importlib.import_module(mod)
+                except Exception as e:          # noqa: BLE001
+                    problems.add(f"{rel}:{n.lineno}: cannot import {mod}: {e}")
+                    continue
+                for a in n.names:
+                    if a.name != "*" and not hasattr(m, a.name):
+                        try:
+                            importlib.import_module(mod + "." + a.name)
+                        except Exception:       # noqa: BLE001
+                            problems.add(f"{rel}:{n.lineno}: {mod} has no {a.name}")
+    assert not problems, "\n".join(sorted(problems))
