@@ -209,3 +209,72 @@ def test_package_and_oracle_attributes_used_by_gpu_only_code_exist():
                         except Exception:       # noqa: BLE001
                             problems.add(f"{rel}:{n.lineno}: {mod} has no {a.name}")
     assert not problems, "\n".join(sorted(problems))
+
+
+def test_calls_into_the_package_bind_to_the_signatures():
+    """Every call in tests / bench.py / tools / the driver entry whose callee resolves statically to a function or class of
+    this package or of oracle/ (``tt.X(...)``, names brought in by ``from <project module> import``) binds to that callee's
+    signature: positional count and keyword names.  ~800 call sites, most of them in code that only runs on a GPU."""
+    import importlib
+    import inspect
+    import sys
+
+    import torch
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import oracle
+    import two_tower_recommender_model_b200 as tt
+    import two_tower_recommender_model_b200._native  # noqa: F401
+    import two_tower_recommender_model_b200.functional  # noqa: F401
+    own = ("two_tower_recommender_model_b200", "oracle", "helpers", "bench")
+    module_type = type(os)
+
+    def resolve(node, env):
+        parts = []
+        while isinstance(node, ast.Attribute):
+            parts.append(node.attr)
+            node = node.value
+        if not isinstance(node, ast.Name) or node.id not in env:
+            return None
+        obj = env[node.id]
+        for p in reversed(parts):
+            if not isinstance(obj, (module_type, type)) or not hasattr(obj, p):
+                return None
+            obj = getattr(obj, p)
+        return obj
+
+    problems, checked = [], 0
+    for fn in _python_files():
+        rel = os.path.relpath(fn, ROOT)
+        if rel.startswith(("two_tower_recommender_model_b200", "oracle")):
+            continue                      # the package's own internals are executed by the CPU suite through stand-ins
+        with open(fn) as f:
+            tree = ast.parse(f.read(), fn)
+        env = {"tt": tt, "oracle": oracle}
+        for n in ast.walk(tree):
+            if isinstance(n, ast.ImportFrom) and not n.level and (n.module or "").startswith(own):
+                try:
+                    m = importlib.import_module(n.module)
+                except Exception:          # noqa: BLE001 -- reported by the import check above
+                    continue
+                for a in n.names:
+                    if hasattr(m, a.name):
+                        env[a.asname or a.name] = getattr(m, a.name)
+        for n in ast.walk(tree):
+            if not isinstance(n, ast.Call) or any(isinstance(a, ast.Starred) for a in n.args) or any(k.arg is None for k in n.keywords):
+                continue
+            obj = resolve(n.func, env)
+            if obj is None or not callable(obj) or (isinstance(obj, type) and issubclass(obj, torch.autograd.Function)):
+                continue
+            try:
+                sig = inspect.signature(obj)
+            except (TypeError, ValueError):
+                continue
+            checked += 1
+            try:
+                sig.bind(*[None] * len(n.args), **{k.arg: None for k in n.keywords})
+            except TypeError as e:
+                problems.append(f"{rel}:{n.lineno}: {ast.unparse(n.func)}: {e}")
+    assert not problems, "\n".join(problems)
+    assert checked > 500
