@@ -278,3 +278,15 @@ def test_calls_into_the_package_bind_to_the_signatures():
                 problems.append(f"{rel}:{n.lineno}: {ast.unparse(n.func)}: {e}")
     assert not problems, "\n".join(problems)
     assert checked > 500
+
+
+def test_unverified_gpu_tests_dry_run_on_cpu():
+    """tests/dryrun_zz.py: the GPU tests that have not run on a GPU yet, executed on CPU with the device entry points replaced by
+    the oracle (in a subprocess: the stand-ins are patched process-wide)."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dryrun_zz.py")], capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    for done in ("checkpoint_resume dry run ok", "corpus_sharded dry run ok", "golden batch construction ok", "golden train steps ok",
+                 "golden corpus ok", "golden raytune ok", "fbgemm vector ok"):
+        assert done in r.stdout, done
