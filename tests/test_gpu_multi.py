@@ -50,7 +50,9 @@ def _worker(rank, world, port, sharding, errq):
         # *_dense*: batches arrive as dense id columns (from_id_columns) -> single all-to-all input dist, no host sync
         peer = sharding.endswith("_peer")
         dense_ids = "_dense" in sharding
-        sharding = "table_wise" if sharding.startswith("table_wise") else ("row_wise" if sharding.startswith("row_wise") else sharding)
+        for kind in ("table_wise", "row_wise", "data_parallel"):
+            if sharding.startswith(kind):
+                sharding = kind
         cons = {f"t_{c}": ParameterConstraints(sharding_types=[sharding]) for c in CAT} if sharding != "planner" else None
         plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world), constraints=cons).collective_plan(task, tt.get_default_sharders(), dist.GroupMember.WORLD)
         model = tt.DistributedModelParallel(module=task, device=dev, plan=plan, sharding_kwargs={"peer_exchange": True} if peer else None)
@@ -129,7 +131,7 @@ def _run_ranks(target, args_of_rank, world=2, timeout=300):
 
 
 MODES = ["table_wise", "row_wise", "table_wise_peer", "table_wise_dense", "table_wise_dense_peer", "row_wise_dense_peer"]
-# "column_wise" (same worker) lives in tests/test_gpu_zz_multi_column_wise.py: it was written after the round's GPU budget was
+# "column_wise" (same worker) lives in tests/test_gpu_zz_multi_more_shardings.py: it was written after the round's GPU budget was
 # spent, and files sort so that a first run of it cannot hide the modes above, which have run green on 2 GPUs
 
 
