@@ -643,27 +643,39 @@ def headline(args, cfg, main, pk, world, G, workload, scaling, parity):
 
 def finish(args, cfg, dev, world, line):
     """Rank 0: the single-GPU side blocks (retrieval probes, configs[2] / configs[3], CPU baselines), then the line."""
+    def record(name, fn):
+        """A side block that raises becomes an `error` entry: the headline line is printed whatever happens after it."""
+        try:
+            line[name] = fn()
+        except Exception as e:      # noqa: BLE001 -- recorded in the line, configs[1] stays the value
+            line[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
+            sys.stderr.write(f"bench.py: block {name} failed: {line[name]['error']}\n")
+            try:
+                if torch.cuda.is_available():
+                    torch.cuda.empty_cache()
+            except Exception:       # noqa: BLE001 -- a sticky CUDA error: the later blocks will record it too, the line still prints
+                pass
+
     if world == 1 and not args.no_cpu_baseline:
         # first: `cpu_baseline` is part of the bench contract, the blocks after it are extras
         stage("cpu_baseline", BLOCK_LIMIT_S)
-        line["cpu_baseline"] = cpu_baseline(cfg, steps=1, warmup=1)
-        line["cpu_baseline_cfg1"] = cpu_baseline_cfg1()
+        record("cpu_baseline", lambda: cpu_baseline(cfg, steps=1, warmup=1))
+        record("cpu_baseline_cfg1", cpu_baseline_cfg1)
     if world == 1:
         stage("retrieval", BLOCK_LIMIT_S)
-        line["retrieval"] = retrieval_probe(dev)
-        line["retrieval_large"] = retrieval_probe(dev, n_items=10_000_000, n_queries=131072)
+        record("retrieval", lambda: retrieval_probe(dev))
+        record("retrieval_large", lambda: retrieval_probe(dev, n_items=10_000_000, n_queries=131072))
     if world == 1 and not args.no_other_configs:
         # BASELINE configs[2] and configs[3] at full size on this GPU (eager steps, CUDA events); configs[1] stays the `value`
         sys.path.insert(0, os.path.join(ROOT, "tools"))
-        import run_configs
         torch.cuda.empty_cache()
-        for name, fn in (("cfg3", run_configs.config3), ("cfg4", run_configs.config4)):
+        for name in ("cfg3", "cfg4"):
             stage(name, BLOCK_LIMIT_S)
-            try:
-                line[name] = fn()
-            except Exception as e:      # noqa: BLE001 -- recorded in the line; configs[1] stays the value
-                line[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
-                torch.cuda.empty_cache()
+
+            def run(name=name):
+                import run_configs
+                return {"cfg3": run_configs.config3, "cfg4": run_configs.config4}[name]()
+            record(name, run)
     stage("done")
     _PARTIAL["line"] = None
     print(json.dumps(line))

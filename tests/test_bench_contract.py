@@ -192,3 +192,36 @@ def test_a_wedged_side_block_is_cut_at_its_own_limit():
     p = subprocess.run([sys.executable, "-c", code_ok], capture_output=True, text=True, env=env, timeout=300)
     assert p.returncode == 0 and p.stdout.strip() == "finished"
 
+
+
+def test_single_gpu_side_blocks_that_raise_become_error_entries(monkeypatch, capsys):
+    """N = 1: the CPU baselines, the retrieval probes and the cfg3 / cfg4 blocks run AFTER the headline is measured; one that
+    raises (host out of memory, a device fault) is recorded as an `error` entry and the line -- headline included -- still prints."""
+    import types
+    calls = []
+
+    def cpu_fail(cfg, steps, warmup, sample_batch=None, budget_s=None):
+        raise MemoryError("host out of memory")
+
+    def probe(dev, n_items=2_000_000, n_queries=16384, d=64, k=100):
+        calls.append(n_items)
+        if n_items > 2_000_000:
+            raise RuntimeError("CUDA error: an illegal memory access was encountered")
+        return {"queries_per_s": 1.0}
+
+    fake_cfgs = types.ModuleType("run_configs")
+    fake_cfgs.config3 = lambda: {"ms_per_step": 4.4}
+    fake_cfgs.config4 = lambda: (_ for _ in ()).throw(RuntimeError("out of memory"))
+    monkeypatch.setitem(sys.modules, "run_configs", fake_cfgs)
+    monkeypatch.setattr(bench, "cpu_baseline", cpu_fail)
+    monkeypatch.setattr(bench, "cpu_baseline_cfg1", lambda: {"value": 96000.0})
+    monkeypatch.setattr(bench, "retrieval_probe", probe)
+    monkeypatch.setattr(bench.torch.cuda, "empty_cache", lambda: None)
+    line = bench.headline(_args(), dict(bench.CFG2), _block(), bench.peaks(), 1, 65536, "BASELINE configs[1] on 1 GPU", "strong", [])
+    bench.finish(_args(no_cpu_baseline=False, no_other_configs=False), dict(bench.CFG2), None, 1, line)
+    out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert out["value"] == line["value"] and out["roofline"]["frac"] > 0
+    assert "MemoryError" in out["cpu_baseline"]["error"] and out["cpu_baseline_cfg1"] == {"value": 96000.0}
+    assert out["retrieval"] == {"queries_per_s": 1.0} and "illegal memory access" in out["retrieval_large"]["error"]
+    assert out["cfg3"] == {"ms_per_step": 4.4} and "out of memory" in out["cfg4"]["error"]
+    assert calls == [2_000_000, 10_000_000] and bench._PARTIAL["stage"] == "done"
