@@ -320,6 +320,30 @@ def parity_check(world, rank, dev, sharding, exchange, steps=3, precision="bf16"
         tt.functional.set_deterministic_softmax_backward(False)
 
 
+def ebc_lookup_alone(model, kjts, B, dev):
+    """EBC lookup alone (BASELINE's second metric): 40 back-to-back lookups over rotating batches, one event pair around
+    the loop (the lookup is a ~15 us kernel; tables are 5 GB of random rows, nothing is L2-resident).  Returns ms per call."""
+    from ctypes import byref
+    from two_tower_recommender_model_b200 import _native as N
+    nb = len(kjts)
+    ebc_mod = model.module.two_tower.ebc
+    plan, total_dim = ebc_mod._build_plan(tuple(kjts[0].keys()), B, with_state=False)
+    vals = [k.values().contiguous() for k in kjts]
+    offs = [k.offsets().to(torch.int32).contiguous() for k in kjts]
+    pooled = torch.empty(B, total_dim, dtype=torch.float32, device=dev)
+    sp = N.stream_ptr(dev)
+    for i in range(4):
+        N.call("tt_ebc_forward", byref(plan), N.ptr(vals[i % nb]), N.ptr(offs[i % nb]), N.ptr(pooled), sp)
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for i in range(40):
+        N.call("tt_ebc_forward", byref(plan), N.ptr(vals[i % nb]), N.ptr(offs[i % nb]), N.ptr(pooled), sp)
+    a1.record()
+    torch.cuda.synchronize()
+    return a0.elapsed_time(a1) / 40
+
+
 def time_block(cfg, B, dev, rank, world, local, args, sharding, exchange, lib, with_kernels):
     """Builds the model for one (per-rank batch, sharding) point, captures the step as a CUDA graph and times the
     device-resident and the end-to-end loops.  Returns a dict (max over ranks applied by the caller)."""
@@ -425,42 +449,32 @@ def time_block(cfg, B, dev, rank, world, local, args, sharding, exchange, lib, w
         clocks["window"] = ("device-resident + end-to-end timed steps + %d further replays of the same step "
                             "(the sampler is started before the warm-up)" % extra)
 
-    per_call = {}
+    # value / e2e are measured at this point; what follows explains them (per-call times, the lookup alone).  Every rank
+    # runs the same eager steps, so a failure here is either common to all ranks or a fault that ends the run anyway.
+    per_call, explain_error = {}, None
     if with_kernels:
-        N.enable_timing(True)
-        for i in range(min(args.steps, 5)):
-            step(resident[i % nb])
-        torch.cuda.synchronize()
-        per_call = N.timing_summary()
-        N.enable_timing(False)
+        try:
+            N.enable_timing(True)
+            for i in range(min(args.steps, 5)):
+                step(resident[i % nb])
+            torch.cuda.synchronize()
+            per_call = N.timing_summary()
+        except Exception as e:      # noqa: BLE001 -- recorded in the line (`explain_error`), the measured value stands
+            explain_error = f"per-call pass: {type(e).__name__}: {e}"[:300]
+        finally:
+            N.enable_timing(False)
 
     ebc_only_ms = None
-    if with_kernels and world == 1:
-        # EBC lookup alone (BASELINE's second metric): 40 back-to-back lookups over rotating batches, one event pair
-        # around the loop (the lookup is a ~15 us kernel; tables are 5 GB of random rows, nothing is L2-resident)
-        from ctypes import byref
-        ebc_mod = model.module.two_tower.ebc
-        kj = [resident[i].sparse_features for i in range(nb)]
-        plan, total_dim = ebc_mod._build_plan(tuple(kj[0].keys()), B, with_state=False)
-        vals = [k.values().contiguous() for k in kj]
-        offs = [k.offsets().to(torch.int32).contiguous() for k in kj]
-        pooled = torch.empty(B, total_dim, dtype=torch.float32, device=dev)
-        sp = N.stream_ptr(dev)
-        for i in range(4):
-            N.call("tt_ebc_forward", byref(plan), N.ptr(vals[i % nb]), N.ptr(offs[i % nb]), N.ptr(pooled), sp)
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for i in range(40):
-            N.call("tt_ebc_forward", byref(plan), N.ptr(vals[i % nb]), N.ptr(offs[i % nb]), N.ptr(pooled), sp)
-        a1.record()
-        torch.cuda.synchronize()
-        ebc_only_ms = a0.elapsed_time(a1) / 40
-
+    if with_kernels and world == 1 and explain_error is None:
+        try:
+            ebc_only_ms = ebc_lookup_alone(model, [resident[i].sparse_features for i in range(nb)], B, dev)
+        except Exception as e:      # noqa: BLE001
+            explain_error = f"lookup-alone loop: {type(e).__name__}: {e}"[:300]
     uniq = [int(torch.unique(resident[0].sparse_features[c].values()[:B]).numel()) for c in CAT]
     out = {"ms_value": ms_value, "ms_e2e": ms_e2e, "launches": int(launches), "clocks": clocks, "per_call": per_call,
            "ebc_only_ms": ebc_only_ms, "uniq": uniq, "last_loss": last, "e2e_api": e2e_api, "h2d": raw[0].nbytes(),
-           "sharding": plan_kinds(model) if world > 1 else None, "cuda_graph": bool(use_graph), "batch": B}
+           "sharding": plan_kinds(model) if world > 1 else None, "cuda_graph": bool(use_graph), "batch": B,
+           "explain_error": explain_error}
     del model, opt, graph_step, resident, raw
     torch.cuda.empty_cache()
     return out
@@ -628,6 +642,8 @@ def headline(args, cfg, main, pk, world, G, workload, scaling, parity):
         "calls_ms": {k: round(v["ms"], 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1]["ms"])},
         "ebc_lookup_gbs": kernels.get("tt_ebc_forward", kernels.get("tt_ebc_forward_peer", {})).get("achieved"),
     }
+    if main.get("explain_error"):
+        line["explain_error"] = main["explain_error"]
     if parity:
         line["parity"] = parity
         if getattr(args, "parity_failed", None):
