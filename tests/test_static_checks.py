@@ -290,3 +290,23 @@ def test_unverified_gpu_tests_dry_run_on_cpu():
     for done in ("checkpoint_resume dry run ok", "corpus_sharded dry run ok", "golden batch construction ok", "golden train steps ok",
                  "golden corpus ok", "golden raytune ok", "fbgemm vector ok"):
         assert done in r.stdout, done
+
+
+def test_bench_single_gpu_flow_dry_run_on_cpu():
+    """tests/dryrun_bench.py: bench.py's time_block (eager variant) -> headline -> finish on a tiny configuration, device entry
+    points replaced by the oracle, CUDA timing by wall-clock fakes.  Checked here: it runs through and the line it prints has
+    the contract's keys and every side block of the N = 1 run."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dryrun_bench.py")], capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0 and "bench dry run ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+    line = json.loads(next(ln for ln in r.stdout.splitlines() if ln.startswith('{"metric"')))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "cpu_baseline_cfg1", "retrieval", "retrieval_large",
+              "kernels", "calls_ms", "ebc_lookup"):
+        assert k in line, k
+    assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 2 * 64 * 8 + 64 * 4
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0 and "error" not in line["cpu_baseline_cfg1"]
+    assert line["retrieval"]["queries_per_s"] > 0 and "error" not in line["retrieval_large"]
+    assert line["roofline"]["bound"] == "tensor" and "explain_error" not in line
