@@ -1,6 +1,7 @@
-"""Dry run, on CPU, of bench.py's single-GPU flow -- ``time_block`` (eager variant) -> ``headline`` -> ``finish`` -- on a tiny
-configuration, with the DEVICE ENTRY POINTS replaced by the oracle / plain torch and the CUDA timing primitives by wall-clock
-fakes (tests only; the product has no CPU path).  It executes the glue the CPU suite otherwise only sees through fakes of
+"""Dry run, on CPU, of bench.py's single-GPU flow -- ``time_block`` (eager variant, then the default one behind
+``CudaGraphTrainStep``, whose "replay" here runs the step again) -> ``headline`` -> ``finish`` -- on a tiny configuration, with
+the DEVICE ENTRY POINTS replaced by the oracle / plain torch and the CUDA runtime primitives (events, streams, graphs) by
+wall-clock / no-op fakes (tests only; the product has no CPU path).  It executes the glue the CPU suite otherwise only sees through fakes of
 ``time_block``: model construction, the raw-batch path, the pipeline loop, the explanatory passes, the line assembly, every
 side block.  The numbers it prints mean nothing; the line's SHAPE is what tests/test_static_checks.py checks.
 
@@ -106,6 +107,50 @@ class _Event:
         return (other.t - self.t) * 1e3
 
 
+class _Stream:
+    def __init__(self, device=None):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+    def wait_event(self, ev):
+        pass
+
+
+class _Graph:
+    """A "captured" step is replayed by running it again: same effect on the static buffers as a real replay."""
+    owner = None
+
+    def replay(self):
+        _Graph.owner._out = _Graph.owner._step()
+
+
+class _Ctx:
+    def __init__(self, *a, **k):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_graph_init = tt.CudaGraphTrainStep.__init__
+
+
+def _gs_init(self, *a, **k):
+    _graph_init(self, *a, **k)
+    _Graph.owner = self
+
+
+tt.CudaGraphTrainStep.__init__ = _gs_init
+torch.cuda.Stream = _Stream
+torch.cuda.current_stream = lambda device=None: _Stream()
+torch.cuda.stream = _Ctx
+torch.cuda.graph = _Ctx
+torch.cuda.CUDAGraph = _Graph
 torch.cuda.Event = _Event
 torch.cuda.synchronize = lambda *a, **k: None
 torch.cuda.empty_cache = lambda: None
@@ -122,6 +167,12 @@ lib = N.load()
 main = bench.time_block(tiny, tiny["batch"], cpu, 0, 1, 0, args, None, None, lib, with_kernels=True)
 assert main["explain_error"] is None, main["explain_error"]
 assert _calls.get("tt_ebc_forward") == 44 and _calls.get("tt_adam_flat_devstep", 0) >= 2 * (args.steps + args.warmup)
+# the default variant: the step behind CudaGraphTrainStep (eager warm-up calls, "capture", replays), as the driver runs it
+args.no_graph = False
+_calls.clear()
+main = bench.time_block(tiny, tiny["batch"], cpu, 0, 1, 0, args, None, None, lib, with_kernels=True)
+assert main["explain_error"] is None and main["cuda_graph"] is True and _Graph.owner.captured, main
+assert "CudaGraphTrainStep" in main["e2e_api"] and main["last_loss"] > 0
 line = bench.headline(args, tiny, main, bench.peaks(), 1, tiny["batch"], "dry run", "strong", [])
 bench.finish(args, tiny, cpu, 1, line)
 print("bench dry run ok")

@@ -293,8 +293,8 @@ def test_unverified_gpu_tests_dry_run_on_cpu():
 
 
 def test_bench_single_gpu_flow_dry_run_on_cpu():
-    """tests/dryrun_bench.py: bench.py's time_block (eager variant) -> headline -> finish on a tiny configuration, device entry
-    points replaced by the oracle, CUDA timing by wall-clock fakes.  Checked here: it runs through and the line it prints has
+    """tests/dryrun_bench.py: bench.py's time_block (eager variant and the default one behind CudaGraphTrainStep) -> headline ->
+    finish on a tiny configuration, device entry points replaced by the oracle, CUDA events / streams / graphs by fakes.  Checked here: it runs through and the line it prints has
     the contract's keys and every side block of the N = 1 run."""
     import json
     import subprocess
@@ -309,4 +309,4 @@ def test_bench_single_gpu_flow_dry_run_on_cpu():
     assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 2 * 64 * 8 + 64 * 4
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0 and "error" not in line["cpu_baseline_cfg1"]
     assert line["retrieval"]["queries_per_s"] > 0 and "error" not in line["retrieval_large"]
-    assert line["roofline"]["bound"] == "tensor" and "explain_error" not in line
+    assert line["roofline"]["bound"] == "tensor" and "explain_error" not in line and line["config"]["cuda_graph"] is True
