@@ -310,3 +310,21 @@ def test_bench_single_gpu_flow_dry_run_on_cpu():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0 and "error" not in line["cpu_baseline_cfg1"]
     assert line["retrieval"]["queries_per_s"] > 0 and "error" not in line["retrieval_large"]
     assert line["roofline"]["bound"] == "tensor" and "explain_error" not in line and line["config"]["cuda_graph"] is True
+
+
+def test_bench_multi_rank_flow_dry_run_on_cpu_world2_gloo():
+    """tests/dryrun_bench_world2.py: bench.py's N > 1 flow on two gloo ranks -- parity checks (table-wise / row-wise, eager and
+    through CudaGraphTrainStep), the headline block, every side block, the exit path -- with the device entry points replaced by
+    the oracle and the NCCL exchange standing in for the peer-memory one."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dryrun_bench_world2.py")], capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0 and "bench world-2 dry run ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+    line = json.loads(next(ln for ln in r.stdout.splitlines() if ln.startswith('{"metric"')))
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["config"]["sharding"] == ["table_wise"]
+    assert [p["mode"] for p in line["parity"]] == ["table_wise/nccl/eager", "row_wise/nccl/eager", "table_wise/nccl/cuda_graph", "row_wise/nccl/cuda_graph"]
+    assert all(p["ok"] for p in line["parity"]) and "parity_failed" not in line
+    assert line["e2e"]["d2h_bytes_per_step"] == 8 and line["e2e"]["h2d_bytes_per_step"] == 2 * line["e2e"]["h2d_bytes_per_step_per_rank"]
+    for k in ("strong_row_wise", "weak", "strong_global_negatives", "retrieval"):
+        assert k in line, k
