@@ -528,8 +528,8 @@ def run_ours(args):
             return
         args.parity_failed = sorted(failed)      # a sharding that failed is not timed (side_blocks records why)
         main = time_block(cfg, G // world, dev, rank, world, local, args, "table_wise", args.exchange, lib, with_kernels=True)
-        workload = ("BASELINE configs[1] on %d GPUs as stated: 2 tables 10M x 64 fp32 table-wise sharded, GLOBAL batch 65536 "
-                    "(per-rank %d), MLP 64-128-64, in-batch softmax (per-rank negatives), fused row-wise Adagrad, Adam" % (world, G // world))
+        workload = ("BASELINE configs[1] on %d GPUs as stated: 2 tables 10M x 64 fp32 table-wise sharded, GLOBAL batch %d "
+                    "(per-rank %d), MLP 64-128-64, in-batch softmax (per-rank negatives), fused row-wise Adagrad, Adam" % (world, G, G // world))
         scaling = "strong"
     line = None
     if rank == 0:

@@ -59,6 +59,45 @@ def _linear_act(x, w, b, relu):
     return torch.relu(y) if relu else y
 
 
+class FusedTowers:
+    """FusedTowersTC's contract in plain torch: tower t = relu(relu(x_t W1^T + b1) W2^T + b2) on the column window
+    [cols[t], cols[t] + in_dim) of the pooled matrix; returns one output per tower plus the stacked bf16 copies."""
+
+    @staticmethod
+    def apply(pooled, cols, in_dim, grad_dst, *params):
+        ys = []
+        for t, c0 in enumerate(cols):
+            w1, b1, w2, b2 = params[4 * t: 4 * t + 4]
+            h = torch.relu(torch.nn.functional.linear(pooled[:, c0:c0 + in_dim], w1, b1))
+            ys.append(torch.relu(torch.nn.functional.linear(h, w2, b2)))
+        return (*ys, torch.stack([y.detach().bfloat16() for y in ys]))
+
+
+class _TorchProxy:
+    """``torch`` as bench.py sees it in a dry run: everything is the real module, except that a CUDA device is the CPU."""
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    @staticmethod
+    def device(*args, **kwargs):
+        return torch.device("cpu")
+
+
+def run_bench_on_cpu(bench, tiny):
+    """Points bench.py's own ``torch`` at the proxy, its workload at `tiny`, its process group at gloo and its probes at small
+    sizes, so that ``bench.run_ours(args)`` -- the function the driver's launch reaches -- can run unchanged."""
+    import torch.distributed as dist
+    bench.torch = _TorchProxy()
+    bench.CFG2 = dict(tiny)
+    bench.CFG1 = dict(rows=[300, 200], dim=16, layers=[32, 16], batch=32, loss="bce", sparse_lr=0.01, dense_lr=0.001)
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend=None, **kw: real_init("gloo")
+    probe, probe_sharded = bench.retrieval_probe, bench.retrieval_probe_sharded
+    bench.retrieval_probe = lambda dev, n_items=3000, n_queries=64, d=64, k=100: probe(dev, min(n_items, 3000), min(n_queries, 64), d, k)
+    bench.retrieval_probe_sharded = lambda dev, r, w: probe_sharded(dev, r, w, n_items=3001, q_per_rank=32, d=16, k=10)
+
+
 def _dot_bce(q, c, labels):
     logits = (q * c).sum(dim=1)
     return torch.nn.functional.binary_cross_entropy_with_logits(logits, labels.float()), logits.detach()
@@ -169,6 +208,7 @@ def install():
     embedding_modules.EbcLookup = OracleLookup
     mlp.linear_act = _linear_act
     tw_mod.dot_bce_loss = _dot_bce
+    tw_mod.FusedTowersTC = FusedTowers
     tw_mod.in_batch_softmax_loss = _softmax_loss
     jt.KeyedJaggedTensor.from_id_columns = staticmethod(_from_id_columns)
     Fn.block_bucketize = _bucketize

@@ -293,8 +293,8 @@ def test_unverified_gpu_tests_dry_run_on_cpu():
 
 
 def test_bench_single_gpu_flow_dry_run_on_cpu():
-    """tests/dryrun_bench.py: bench.py's time_block (eager variant and the default one behind CudaGraphTrainStep) -> headline ->
-    finish on a tiny configuration, device entry points replaced by the oracle, CUDA events / streams / graphs by fakes.  Checked here: it runs through and the line it prints has
+    """tests/dryrun_bench.py: bench.py's run_ours(args) itself (default variant: the step behind CudaGraphTrainStep) and time_block
+    in its eager variant, on a tiny configuration, device entry points replaced by the oracle, CUDA events / streams / graphs by fakes.  Checked here: it runs through and the line it prints has
     the contract's keys and every side block of the N = 1 run."""
     import json
     import subprocess
@@ -313,9 +313,9 @@ def test_bench_single_gpu_flow_dry_run_on_cpu():
 
 
 def test_bench_multi_rank_flow_dry_run_on_cpu_world2_gloo():
-    """tests/dryrun_bench_world2.py: bench.py's N > 1 flow on two gloo ranks -- parity checks (table-wise / row-wise, eager and
-    through CudaGraphTrainStep), the headline block, every side block, the exit path -- with the device entry points replaced by
-    the oracle and the NCCL exchange standing in for the peer-memory one."""
+    """tests/dryrun_bench_world2.py: bench.py's run_ours(args) itself on two gloo ranks -- parity checks (table-wise / row-wise,
+    bf16-configured and fp32, eager and through CudaGraphTrainStep), the headline block, every side block, the exit path -- with
+    the device entry points replaced by the oracle and the NCCL exchange standing in for the peer-memory one."""
     import json
     import subprocess
     import sys
@@ -323,7 +323,9 @@ def test_bench_multi_rank_flow_dry_run_on_cpu_world2_gloo():
     assert r.returncode == 0 and "bench world-2 dry run ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
     line = json.loads(next(ln for ln in r.stdout.splitlines() if ln.startswith('{"metric"')))
     assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["config"]["sharding"] == ["table_wise"]
-    assert [p["mode"] for p in line["parity"]] == ["table_wise/nccl/eager", "row_wise/nccl/eager", "table_wise/nccl/cuda_graph", "row_wise/nccl/cuda_graph"]
+    assert [(p["mode"], p["precision"]) for p in line["parity"]] == [
+        ("table_wise/nccl/eager", "bf16"), ("row_wise/nccl/eager", "bf16"), ("table_wise/nccl/eager", "fp32"), ("row_wise/nccl/eager", "fp32"),
+        ("table_wise/nccl/cuda_graph", "fp32"), ("row_wise/nccl/cuda_graph", "fp32")]
     assert all(p["ok"] for p in line["parity"]) and "parity_failed" not in line
     assert line["e2e"]["d2h_bytes_per_step"] == 8 and line["e2e"]["h2d_bytes_per_step"] == 2 * line["e2e"]["h2d_bytes_per_step_per_rank"]
     for k in ("strong_row_wise", "weak", "strong_global_negatives", "retrieval"):
