@@ -28,6 +28,16 @@ def worker(rank, world, port):
     S.run_bench_on_cpu(bench, tiny)
     args = argparse.Namespace(gpus=world, steps=3, warmup=3, impl="ours", no_cpu_baseline=True, no_other_configs=True, exchange="nccl",
                               parity_only=False, parity_graph=True, no_graph=False)
+    if os.environ.get("DRYRUN_FAIL_ROW_WISE"):
+        # what a failed row-wise parity check does to the run: the table-wise headline stands, row-wise blocks are skipped
+        real = bench.parity_check
+
+        def parity_check(world, rank, dev, sharding, exchange, **kw):
+            p = real(world, rank, dev, sharding, exchange, **kw)
+            if sharding == "row_wise":
+                p["ok"] = False
+            return p
+        bench.parity_check = parity_check
     bench.run_ours(args)        # every rank leaves through bench.leave(): flush + os._exit(0)
     raise AssertionError("run_ours returned on a multi-rank run")
 

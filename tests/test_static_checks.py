@@ -330,3 +330,17 @@ def test_bench_multi_rank_flow_dry_run_on_cpu_world2_gloo():
     assert line["e2e"]["d2h_bytes_per_step"] == 8 and line["e2e"]["h2d_bytes_per_step"] == 2 * line["e2e"]["h2d_bytes_per_step_per_rank"]
     for k in ("strong_row_wise", "weak", "strong_global_negatives", "retrieval"):
         assert k in line, k
+
+
+def test_bench_multi_rank_run_with_a_failed_row_wise_parity_check_dry_run():
+    """The same two-rank dry run with the row-wise parity results forced to `ok: false`: the run still ends with rc 0 and the
+    table-wise headline; `parity_failed` names the sharding, the row-wise block is recorded as skipped, the others are timed."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dryrun_bench_world2.py")], capture_output=True, text=True, cwd=ROOT,
+                       timeout=900, env=dict(os.environ, DRYRUN_FAIL_ROW_WISE="1"))
+    assert r.returncode == 0 and "bench world-2 dry run ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+    line = json.loads(next(ln for ln in r.stdout.splitlines() if ln.startswith('{"metric"')))
+    assert line["parity_failed"] == ["row_wise"] and line["value"] > 0 and line["config"]["sharding"] == ["table_wise"]
+    assert "skipped" in line["strong_row_wise"] and "value" in line["weak"] and "retrieval" in line
