@@ -344,3 +344,14 @@ def test_bench_multi_rank_run_with_a_failed_row_wise_parity_check_dry_run():
     line = json.loads(next(ln for ln in r.stdout.splitlines() if ln.startswith('{"metric"')))
     assert line["parity_failed"] == ["row_wise"] and line["value"] > 0 and line["config"]["sharding"] == ["table_wise"]
     assert "skipped" in line["strong_row_wise"] and "value" in line["weak"] and "retrieval" in line
+
+
+def test_driver_smoke_entry_dry_run_on_cpu():
+    """tests/dryrun_smoke.py: ``__graft_entry__.smoke()`` -- what the driver runs on the GPU box before the bench -- with the device
+    entry points replaced by the oracle: its own flow and its comparisons against the oracle's numbers."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dryrun_smoke.py")], capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0 and "smoke dry run ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+    for leg in ("smoke[bce]", "smoke[in_batch_softmax]", "smoke[bf16 tcgen05]", "top-100 indices bit-exact"):
+        assert leg in r.stdout, leg
