@@ -57,6 +57,7 @@ def stage(name, limit_s=None):
 BLOCK_LIMIT_S = float(os.environ.get("TT_BENCH_BLOCK_S", "180"))
 CFG2 = dict(rows=[10_000_000, 10_000_000], dim=64, layers=[128, 64], batch=65536, loss="in_batch_softmax",
             sparse_lr=0.01, dense_lr=0.001)
+CFG3_SHARDED = dict(batch=65536, big_rows=100_000_000, D=128, L=20)      # configs[2]; the dry runs shrink it
 CFG1 = dict(rows=[200_000, 50_000], dim=64, layers=[128, 64], batch=1024, loss="bce", sparse_lr=0.01, dense_lr=0.001)
 
 
@@ -589,6 +590,18 @@ def side_blocks(args, cfg, dev, rank, world, local, lib, G, line):
     record("weak", not_timed(weak_kind) if weak_kind in bad else weak)
     record("strong_global_negatives", strong_global_negatives)
     record("retrieval", lambda: retrieval_probe_sharded(dev, rank, world))
+
+    def cfg3_row_wise():
+        # configs[2] as stated (row-wise sharded 100M-row tables, L = 20) at this N.  LAST: it is the one block of this run
+        # that has not been timed on GPUs before -- if it wedges, the watchdog cuts it and every block above is already in the line
+        if args.exchange != "peer":
+            return {"skipped": "needs the peer-memory exchange (the sync-free multi-hot input dist is what makes the step capturable)"}
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import run_configs
+        return run_configs.config3_sharded(dev, rank, world, steps=max(args.steps, 5), warmup=args.warmup, **CFG3_SHARDED)
+
+    if not args.no_other_configs:
+        record("cfg3_row_wise", cfg3_row_wise)
     stage("done")
 
 
@@ -695,6 +708,13 @@ def finish(args, cfg, dev, world, line):
     stage("done")
     _PARTIAL["line"] = None
     print(json.dumps(line))
+    if world > 1:
+        # ranks still stuck in a side block that rank 0 left through an error entry learn from this file, when their own
+        # watchdog fires, that the line is out (see watchdog())
+        try:
+            open(_marker_path(), "w").close()
+        except OSError:
+            pass
     leave(world)
 
 
@@ -704,7 +724,11 @@ def leave(world, rc=0):
     sys.stdout.flush()
     sys.stderr.flush()
     if world > 1:
-        torch.cuda.synchronize()
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:      # noqa: BLE001 -- a device fault inside a recorded side block must not change the exit code
+            sys.stderr.write(f"bench.py: synchronize at exit failed: {type(e).__name__}: {e}\n")
+            sys.stderr.flush()
         os._exit(rc)
     if rc:
         sys.exit(rc)
@@ -876,13 +900,17 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _marker_path():
+    return os.path.join("/tmp", "tt_bench_partial_%s" % os.environ.get("MASTER_PORT", "0"))
+
+
 def watchdog():
     """The run overran its limit (a wedged collective or capture).  If the headline block had been measured, rank 0
     still prints its line -- with an `incomplete` entry naming the block that was cut -- and the ranks exit 0; before
     that point there is nothing to report and the exit code is 3.  The other ranks wait 15 s longer than rank 0 and
     learn the outcome from a marker file."""
     rank = int(os.environ.get("RANK", 0))
-    marker = os.path.join("/tmp", "tt_bench_partial_%s" % os.environ.get("MASTER_PORT", "0"))
+    marker = _marker_path()
     sys.stderr.write("bench.py: watchdog expired on rank %d during block '%s'\n" % (rank, _PARTIAL["stage"]))
     rc = 3
     if rank == 0:
@@ -897,7 +925,7 @@ def watchdog():
                 rc = 0
             except Exception:       # noqa: BLE001 -- a block was mutating the dict: nothing printable
                 rc = 3
-    elif os.path.exists(marker) and time.time() - os.path.getmtime(marker) < 120:
+    elif os.path.exists(marker) and time.time() - os.path.getmtime(marker) < 600:
         rc = 0
     sys.stdout.flush()
     sys.stderr.flush()
@@ -909,6 +937,11 @@ def start_watchdog(run_limit_s):
     flight (``stage``), has passed.  Ranks other than 0 wait 15 s longer so that rank 0 can print first."""
     grace = 0 if int(os.environ.get("RANK", 0)) == 0 else 15
     _DEADLINE["run"] = time.time() + run_limit_s
+    if grace == 0:
+        try:
+            os.remove(_marker_path())       # a marker left by an earlier run on the same port says nothing about this one
+        except OSError:
+            pass
 
     def poll():
         while True:

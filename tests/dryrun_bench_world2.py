@@ -26,8 +26,24 @@ def worker(rank, world, port):
     import bench
     tiny = dict(rows=[700, 500], dim=16, layers=[32, 16], batch=64, loss="in_batch_softmax", sparse_lr=0.01, dense_lr=0.001)
     S.run_bench_on_cpu(bench, tiny)
-    args = argparse.Namespace(gpus=world, steps=3, warmup=3, impl="ours", no_cpu_baseline=True, no_other_configs=True, exchange="nccl",
+    args = argparse.Namespace(gpus=world, steps=3, warmup=3, impl="ours", no_cpu_baseline=True, no_other_configs=False, exchange="nccl",
                               parity_only=False, parity_graph=True, no_graph=False)
+    if os.environ.get("DRYRUN_CFG3_SHARDED"):
+        # configs[2] row-wise sharded (the last side block of an N > 1 run), called directly: tiny tables, fp32 towers, the NCCL
+        # exchange (the peer-memory one needs NVLink symmetric memory)
+        import torch
+        import torch.distributed as dist
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import run_configs
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        out = run_configs.config3_sharded(torch.device("cpu"), rank, world, steps=3, warmup=2, batch=64, big_rows=5000, D=16, L=4,
+                                          layers=(32, 16), precision="fp32", peer_exchange=False)
+        assert out["sharding"] == ["row_wise"] and out["cuda_graph"] and out["per_rank_batch"] == 32 and out["value"] > 0, out
+        assert out["ids_per_rank_per_step"] == 32 * 4 + 3 * 32 and 0 < out["last_loss"] < 20, out
+        if rank == 0:
+            import json
+            print(json.dumps(out))
+        bench.leave(world)
     if os.environ.get("DRYRUN_FAIL_ROW_WISE"):
         # what a failed row-wise parity check does to the run: the table-wise headline stands, row-wise blocks are skipped
         real = bench.parity_check

@@ -328,8 +328,9 @@ def test_bench_multi_rank_flow_dry_run_on_cpu_world2_gloo():
         ("table_wise/nccl/cuda_graph", "fp32"), ("row_wise/nccl/cuda_graph", "fp32")]
     assert all(p["ok"] for p in line["parity"]) and "parity_failed" not in line
     assert line["e2e"]["d2h_bytes_per_step"] == 8 and line["e2e"]["h2d_bytes_per_step"] == 2 * line["e2e"]["h2d_bytes_per_step_per_rank"]
-    for k in ("strong_row_wise", "weak", "strong_global_negatives", "retrieval"):
+    for k in ("strong_row_wise", "weak", "strong_global_negatives", "retrieval", "cfg3_row_wise"):
         assert k in line, k
+    assert "skipped" in line["cfg3_row_wise"]          # configs[2] sharded needs the peer-memory exchange; its own dry run is below
 
 
 def test_bench_multi_rank_run_with_a_failed_row_wise_parity_check_dry_run():
@@ -355,3 +356,17 @@ def test_driver_smoke_entry_dry_run_on_cpu():
     assert r.returncode == 0 and "smoke dry run ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
     for leg in ("smoke[bce]", "smoke[in_batch_softmax]", "smoke[bf16 tcgen05]", "top-100 indices bit-exact"):
         assert leg in r.stdout, leg
+
+
+def test_config3_sharded_block_dry_run_on_cpu_world2_gloo():
+    """tools/run_configs.py::config3_sharded -- configs[2] row-wise sharded, the last side block of an N > 1 bench run -- on two
+    gloo ranks with tiny tables, fp32 towers and the NCCL exchange: its model construction, the multi-hot batches in their
+    fixed-capacity buffers, the CudaGraphTrainStep.step_kjt loop, the max over ranks and the block's result dict."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dryrun_bench_world2.py")], capture_output=True, text=True, cwd=ROOT,
+                       timeout=900, env=dict(os.environ, DRYRUN_CFG3_SHARDED="1"))
+    assert r.returncode == 0 and "bench world-2 dry run ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+    out = json.loads(next(ln for ln in r.stdout.splitlines() if ln.startswith('{"config": 3')))
+    assert out["sharding"] == ["row_wise"] and out["cuda_graph"] is True and out["global_batch"] == 64 and out["value"] > 0

@@ -6,6 +6,8 @@ few steps each, and prints one JSON line per configuration (timing with CUDA eve
   3: multi-hot user history (L=20, mean) + product/aisle/department tables, 100M rows x 128 (51 GB each)
   4: batch 262144, bf16 towers 128->1024->512->256, fused row-wise Adam, in-batch softmax d=256
   5: retrieval: item-tower corpus of 10M items, top-100 for 131072 queries (1/8 of the 1M: one GPU's share)
+
+`config3_sharded` (configs[2] row-wise sharded over the ranks of a multi-GPU run) is called by `bench.py --gpus N`.
 """
 import json
 import os
@@ -108,6 +110,72 @@ def config3(steps=5, warmup=2):
                        "frac": round(6.0 * B * B * 64 / sm_ms / 1e9 / tf, 4)},
            "peak_source": src, "hbm_gb_allocated": round(torch.cuda.memory_allocated() / 1e9, 1)}
     del task, tower, ebc, opt, batches, gstep, parts
+    torch.cuda.empty_cache()
+    return out
+
+
+def config3_sharded(device, rank, world, steps=5, warmup=3, batch=65536, big_rows=100_000_000, D=128, L=20, layers=(128, 64),
+                    precision="bf16", peer_exchange=True):
+    """configs[2] AS STATED on `world` GPUs (called by every rank of a `bench.py --gpus N` run): the four tables ROW-WISE sharded
+    (100M x 128 fp32 hist / product: 51 GB each, 51 / world per rank; aisle / department alongside), GLOBAL batch 65536, mean-
+    pooled history of L = 20, in-batch softmax with per-rank negatives, fused row-wise Adagrad, Adam on the towers.  The
+    per-rank KJT sits in a fixed-capacity buffer, so the input dist is the sync-free all-gather + tt_kjt_gathered_range route,
+    the partial sums of the shards are ADDED into the sample's rank over NVLink peer memory, and the whole step replays as ONE
+    CUDA graph (the combination tests/test_gpu_multi.py::test_two_rank_multi_hot_sync_free_input_dist_and_graph checks
+    against the oracle at small size).  Timed with CUDA events, max over ranks; value = global batch / step time.
+    (`peer_exchange=False`, `precision="fp32"`, small sizes: the CPU dry run of tests/dryrun_bench_world2.py.)"""
+    import torch.distributed as dist
+    from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
+    Br = batch // world
+    rows = {"hist": big_rows, "product": big_rows, "aisle": 134, "department": 21}
+    cfgs = [tt.EmbeddingBagConfig(name=f"t_{k}", embedding_dim=D, num_embeddings=r, feature_names=[k],
+                                  pooling=tt.PoolingType.MEAN if k == "hist" else tt.PoolingType.SUM) for k, r in rows.items()]
+    ebc = tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("meta"))
+    tower = tt.TwoTower(ebc, list(layers), device=device, query_features=["hist"], candidate_features=["product", "aisle", "department"],
+                        precision=precision)
+    task = tt.TwoTowerTrainTask(tower, loss="in_batch_softmax", precision=precision)
+    apply_optimizer_in_backward(tt.RowWiseAdagrad, task.two_tower.ebc.parameters(), {"lr": 0.01})
+    cons = {f"t_{k}": ParameterConstraints(sharding_types=["row_wise"]) for k in rows}
+    plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world), constraints=cons
+                                       ).collective_plan(task, tt.get_default_sharders(), dist.GroupMember.WORLD)
+    model = tt.DistributedModelParallel(module=task, device=device, plan=plan, sharding_kwargs={"peer_exchange": True} if peer_exchange else None)
+    opt = tt.KeyedOptimizerWrapper(dict(model.named_parameters()), lambda p: tt.FlatAdam(p, lr=1e-3))
+    model.train()
+    keys = list(rows)
+    g = torch.Generator(device=device).manual_seed(300 + rank)
+    parts = []
+    for _ in range(3):
+        lens = torch.cat([torch.full((Br,), L, dtype=torch.int32, device=device), torch.ones(3 * Br, dtype=torch.int32, device=device)])
+        cols = [torch.randint(0, rows["hist"], (Br * L,), device=device, generator=g), torch.randint(0, rows["product"], (Br,), device=device, generator=g),
+                torch.randint(0, 134, (Br,), device=device, generator=g), torch.randint(0, 21, (Br,), device=device, generator=g)]
+        parts.append((torch.cat(cols), lens, torch.zeros(Br, dtype=torch.int32, device=device)))
+    gstep = tt.CudaGraphTrainStep(model, opt, keys, list(rows.values()), Br, device, warmup_steps=2, kjt_capacity=Br * L + 3 * Br)
+    loss = None
+    for i in range(2 + 1 + max(warmup, 1)):            # eager warm-up steps, the capture, replays
+        loss = gstep.step_kjt(*parts[i % 3])[0]
+    dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        loss = gstep.step_kjt(*parts[i % 3])[0]
+    b.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / steps], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    hbm, _tf, src = _peaks()
+    nnz = Br * L + 3 * Br                                 # ids a rank contributes; it looks up ~ world * nnz / world of the global batch
+    fwd_bytes = nnz * (8 + 4 * D) + 4 * (4 * Br) + 4 * Br * D * 4
+    out = {"config": 3, "what": "configs[2] on %d GPUs: 4 tables row-wise sharded (2 x 100M x 128 fp32 = 102 GB over the ranks), GLOBAL batch %d "
+                                "(per-rank %d), L=20 mean history, in-batch softmax (per-rank negatives), fused row-wise Adagrad, Adam; sync-free "
+                                "multi-hot input dist, peer-memory exchange, whole step as one CUDA graph" % (world, batch, Br),
+           "value": round(batch / ms * 1e3, 1), "unit": "samples/s", "ms_per_step": round(ms, 4), "global_batch": batch, "per_rank_batch": Br,
+           "sharding": sorted({ps.sharding_type for tables in plan.plan.values() for ps in tables.values()}), "cuda_graph": gstep.captured,
+           "last_loss": float(loss), "ids_per_rank_per_step": nnz, "lookup_bytes_per_rank": fwd_bytes, "hbm_peak_gbs": hbm, "peak_source": src,
+           "hbm_gb_allocated_per_rank": round(torch.cuda.memory_allocated() / 1e9, 1) if torch.cuda.is_available() else None}
+    del model, task, tower, ebc, opt, gstep, parts
     torch.cuda.empty_cache()
     return out
 
