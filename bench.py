@@ -904,21 +904,22 @@ def _marker_path():
     return os.path.join("/tmp", "tt_bench_partial_%s" % os.environ.get("MASTER_PORT", "0"))
 
 
-def watchdog():
-    """The run overran its limit (a wedged collective or capture).  If the headline block had been measured, rank 0
+def watchdog(why=None):
+    """The run overran its limit (a wedged collective or capture) -- or, with `why`, was told to end.  If the headline block had been measured, rank 0
     still prints its line -- with an `incomplete` entry naming the block that was cut -- and the ranks exit 0; before
     that point there is nothing to report and the exit code is 3.  The other ranks wait 15 s longer than rank 0 and
     learn the outcome from a marker file."""
     rank = int(os.environ.get("RANK", 0))
     marker = _marker_path()
-    sys.stderr.write("bench.py: watchdog expired on rank %d during block '%s'\n" % (rank, _PARTIAL["stage"]))
+    sys.stderr.write("bench.py: %s on rank %d during block '%s'\n" % ("watchdog expired" if why is None else why, rank, _PARTIAL["stage"]))
     rc = 3
     if rank == 0:
         line = _PARTIAL["line"]
         if line is not None:
             line = dict(line)
-            line["incomplete"] = {"cut_block": _PARTIAL["stage"], "reason": "watchdog: the block did not finish within its limit; "
-                                  "the headline block (value / e2e / roofline / parity) had completed before it started"}
+            line["incomplete"] = {"cut_block": _PARTIAL["stage"],
+                                  "reason": ("watchdog: the block did not finish within its limit" if why is None else why) +
+                                  "; the headline block (value / e2e / roofline / parity) had completed before it started"}
             try:
                 print(json.dumps(line))
                 open(marker, "w").close()
@@ -943,6 +944,21 @@ def start_watchdog(run_limit_s):
         except OSError:
             pass
 
+    # SIGTERM is what torchrun sends the surviving ranks when one rank dies.  A Python-level handler only runs once the main
+    # thread is back in the interpreter -- not while it waits inside a collective -- so the signal is routed to a pipe
+    # (signal.set_wakeup_fd: written by the C-level handler at once) that the watchdog thread polls: rank 0 still prints the
+    # headline line, if it has one, before the process goes.
+    term_r = None
+    try:
+        import signal
+        term_r, term_w = os.pipe()
+        os.set_blocking(term_r, False)
+        os.set_blocking(term_w, False)
+        signal.signal(signal.SIGTERM, lambda signum, frame: None)
+        signal.set_wakeup_fd(term_w, warn_on_full_buffer=False)
+    except (ValueError, OSError, AttributeError):      # not the main thread (tests import this module), or no pipes
+        term_r = None
+
     def poll():
         while True:
             time.sleep(0.5)
@@ -950,6 +966,13 @@ def start_watchdog(run_limit_s):
             blk = _DEADLINE["block"]
             if now > _DEADLINE["run"] or (blk is not None and now > blk):
                 watchdog()
+            if term_r is not None:
+                try:
+                    got = os.read(term_r, 64)
+                except (BlockingIOError, OSError):
+                    got = b""
+                if got and signal.SIGTERM in got:
+                    watchdog("SIGTERM (torchrun ends the surviving ranks when one rank dies)")
 
     threading.Thread(target=poll, daemon=True).start()
 

@@ -225,3 +225,36 @@ def test_single_gpu_side_blocks_that_raise_become_error_entries(monkeypatch, cap
     assert out["retrieval"] == {"queries_per_s": 1.0} and "illegal memory access" in out["retrieval_large"]["error"]
     assert out["cfg3"] == {"ms_per_step": 4.4} and "out of memory" in out["cfg4"]["error"]
     assert calls == [2_000_000, 10_000_000] and bench._PARTIAL["stage"] == "done"
+
+
+def test_sigterm_from_torchrun_still_gets_the_headline_out():
+    """When one rank dies torchrun sends the others SIGTERM.  Rank 0 -- possibly waiting inside a collective, where no Python
+    signal handler would run -- still prints the headline line it holds (the signal reaches the watchdog thread through a
+    wake-up pipe) and exits 0; a rank that holds no line exits 3.  Either way the process ends at once."""
+    import signal
+    import time
+    code = (
+        "import sys, time; sys.path.insert(0, %r); import bench\n"
+        "bench._PARTIAL['line'] = %s\n"
+        "bench.start_watchdog(300.0); bench.stage('cfg3_row_wise', 200.0)\n"
+        "print('ready', flush=True)\n"
+        "time.sleep(60)\n"
+        "print('not reached')\n")
+    for have_line in (True, False):
+        env = dict(os.environ, RANK="0", MASTER_PORT="2%d" % os.getpid())
+        p = subprocess.Popen([sys.executable, "-c", code % (ROOT, "{'metric': 'two-tower train samples/s', 'value': 7.5}" if have_line else "None")],
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+        assert p.stdout.readline().strip() == "ready"
+        t0 = time.time()
+        p.send_signal(signal.SIGTERM)
+        out, err = p.communicate(timeout=60)
+        assert time.time() - t0 < 20 and "not reached" not in out, err[-300:]
+        marker = "/tmp/tt_bench_partial_2%d" % os.getpid()
+        if os.path.exists(marker):
+            os.remove(marker)
+        if have_line:
+            line = json.loads(out.strip().splitlines()[-1])
+            assert p.returncode == 0 and line["value"] == 7.5 and line["incomplete"]["cut_block"] == "cfg3_row_wise"
+            assert "SIGTERM" in line["incomplete"]["reason"]
+        else:
+            assert p.returncode == 3 and out.strip() == ""
