@@ -58,6 +58,7 @@ BLOCK_LIMIT_S = float(os.environ.get("TT_BENCH_BLOCK_S", "180"))
 CFG2 = dict(rows=[10_000_000, 10_000_000], dim=64, layers=[128, 64], batch=65536, loss="in_batch_softmax",
             sparse_lr=0.01, dense_lr=0.001)
 CFG3_SHARDED = dict(batch=65536, big_rows=100_000_000, D=128, L=20)      # configs[2]; the dry runs shrink it
+CFG4_SHARDED = dict(batch=262144, rows=(10_000_000, 10_000_000), D=128, layers=(1024, 512, 256))      # configs[3]
 CFG1 = dict(rows=[200_000, 50_000], dim=64, layers=[128, 64], batch=1024, loss="bce", sparse_lr=0.01, dense_lr=0.001)
 
 
@@ -592,15 +593,24 @@ def side_blocks(args, cfg, dev, rank, world, local, lib, G, line):
     record("retrieval", lambda: retrieval_probe_sharded(dev, rank, world))
 
     def cfg3_row_wise():
-        # configs[2] as stated (row-wise sharded 100M-row tables, L = 20) at this N.  LAST: it is the one block of this run
-        # that has not been timed on GPUs before -- if it wedges, the watchdog cuts it and every block above is already in the line
+        # configs[2] as stated (row-wise sharded 100M-row tables, L = 20) at this N.  LAST: this block and the one before it
+        # have not been timed on GPUs before -- if one wedges, the watchdog cuts it and every block above is already in the line
         if args.exchange != "peer":
             return {"skipped": "needs the peer-memory exchange (the sync-free multi-hot input dist is what makes the step capturable)"}
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import run_configs
         return run_configs.config3_sharded(dev, rank, world, steps=max(args.steps, 5), warmup=args.warmup, **CFG3_SHARDED)
 
+    def cfg4_sharded():
+        # configs[3] as stated (B = 262144 global, bf16 towers 1024-512-256, d = 256 logits, row-wise Adam) at this N: id-column
+        # batches, so every piece of it is a path the blocks above already ran -- the combination is what is new
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import run_configs
+        return run_configs.config4_sharded(dev, rank, world, steps=max(args.steps, 5), warmup=args.warmup,
+                                           peer_exchange=(args.exchange == "peer"), **CFG4_SHARDED)
+
     if not args.no_other_configs:
+        record("cfg4_sharded", cfg4_sharded)
         record("cfg3_row_wise", cfg3_row_wise)
     stage("done")
 

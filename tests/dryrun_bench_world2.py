@@ -40,9 +40,15 @@ def worker(rank, world, port):
                                           layers=(32, 16), precision="fp32", peer_exchange=False)
         assert out["sharding"] == ["row_wise"] and out["cuda_graph"] and out["per_rank_batch"] == 32 and out["value"] > 0, out
         assert out["ids_per_rank_per_step"] == 32 * 4 + 3 * 32 and 0 < out["last_loss"] < 20, out
+        # configs[3] under the planner's sharding (the block before it): tiny tables, fp32 towers of three layers, row-wise Adam
+        out4 = run_configs.config4_sharded(torch.device("cpu"), rank, world, steps=3, warmup=2, batch=64, rows=(900, 700), D=16,
+                                           layers=(32, 24, 16), precision="fp32", peer_exchange=False)
+        assert out4["sharding"] == ["table_wise"] and out4["cuda_graph"] and out4["per_rank_batch"] == 32 and out4["value"] > 0, out4
+        assert 0 < out4["last_loss"] < 20 and out4["per_rank_tflops_credited"] >= 0, out4
         if rank == 0:
             import json
             print(json.dumps(out))
+            print(json.dumps(out4))
         bench.leave(world)
     if os.environ.get("DRYRUN_FAIL_ROW_WISE"):
         # what a failed row-wise parity check does to the run: the table-wise headline stands, row-wise blocks are skipped

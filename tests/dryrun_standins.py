@@ -21,7 +21,7 @@ live_adams = []     # FlatAdam instances, so that the faked tt_adam_flat_devstep
 
 
 class OracleLookup(torch.autograd.Function):
-    """EbcLookup's contract on CPU: pooled [B, sum D] (sum / mean pooling); backward applies the tagged row-wise Adagrad in
+    """EbcLookup's contract on CPU: pooled [B, sum D] (sum / mean pooling); backward applies the tagged row-wise Adagrad / Adam in
     place on ``grad * ebc._grad_scale`` and the weights get no .grad -- or, without an in-backward optimizer, hands the tables
     their dense gradient."""
 
@@ -45,12 +45,21 @@ class OracleLookup(torch.autograd.Function):
         kind = ebc._in_backward_kind()
         if kind is None:
             return (None,) * 5 + tuple(grads)
+        from two_tower_recommender_model_b200 import _native as N
+        if kind == N.OPT_ROWWISE_ADAM:
+            ebc._fused_step += 1          # the kernel advances its device-side counter; here the host-side one stands for it
         for s, gr in zip(ctx.specs, grads):
             w = ebc.embedding_bags[s.name].weight
             cfg = next(c for c in ebc.embedding_bag_configs() if c.name == s.name)
-            st = ebc._state_for(cfg, w, kind)["sum"]
+            st = ebc._state_for(cfg, w, kind)
             kw = w._optimizer_kwargs[0]
-            oracle.rowwise_adagrad_dense(w.data, st, gr, lr=kw["lr"], eps=kw.get("eps", 1e-10))
+            if kind == N.OPT_ROWWISE_ADAM:
+                hit = (gr != 0).any(dim=1).nonzero().flatten()
+                b1, b2 = kw.get("betas", (0.9, 0.999))
+                oracle.rowwise_adam_sparse(w.data, st["exp_avg"], st["exp_avg_sq"], hit, gr[hit], step=ebc._fused_step, lr=kw["lr"],
+                                           beta1=b1, beta2=b2, eps=kw.get("eps", 1e-8))
+            else:
+                oracle.rowwise_adagrad_dense(w.data, st["sum"], gr, lr=kw["lr"], eps=kw.get("eps", 1e-10))
         return (None,) * 5 + (None,) * ctx.n
 
 

@@ -328,7 +328,7 @@ def test_bench_multi_rank_flow_dry_run_on_cpu_world2_gloo():
         ("table_wise/nccl/cuda_graph", "fp32"), ("row_wise/nccl/cuda_graph", "fp32")]
     assert all(p["ok"] for p in line["parity"]) and "parity_failed" not in line
     assert line["e2e"]["d2h_bytes_per_step"] == 8 and line["e2e"]["h2d_bytes_per_step"] == 2 * line["e2e"]["h2d_bytes_per_step_per_rank"]
-    for k in ("strong_row_wise", "weak", "strong_global_negatives", "retrieval", "cfg3_row_wise"):
+    for k in ("strong_row_wise", "weak", "strong_global_negatives", "retrieval", "cfg4_sharded", "cfg3_row_wise"):
         assert k in line, k
     assert "skipped" in line["cfg3_row_wise"]          # configs[2] sharded needs the peer-memory exchange; its own dry run is below
 
@@ -358,9 +358,10 @@ def test_driver_smoke_entry_dry_run_on_cpu():
         assert leg in r.stdout, leg
 
 
-def test_config3_sharded_block_dry_run_on_cpu_world2_gloo():
-    """tools/run_configs.py::config3_sharded -- configs[2] row-wise sharded, the last side block of an N > 1 bench run -- on two
-    gloo ranks with tiny tables, fp32 towers and the NCCL exchange: its model construction, the multi-hot batches in their
+def test_config3_and_config4_sharded_blocks_dry_run_on_cpu_world2_gloo():
+    """tools/run_configs.py::config3_sharded / config4_sharded -- configs[2] row-wise sharded and configs[3] under the planner's
+    sharding (row-wise Adam, three-layer towers), the last two side blocks of an N > 1 bench run -- on two gloo ranks with tiny
+    tables, fp32 towers and the NCCL exchange: its model construction, the multi-hot batches in their
     fixed-capacity buffers, the CudaGraphTrainStep.step_kjt loop, the max over ranks and the block's result dict."""
     import json
     import subprocess
@@ -370,3 +371,5 @@ def test_config3_sharded_block_dry_run_on_cpu_world2_gloo():
     assert r.returncode == 0 and "bench world-2 dry run ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
     out = json.loads(next(ln for ln in r.stdout.splitlines() if ln.startswith('{"config": 3')))
     assert out["sharding"] == ["row_wise"] and out["cuda_graph"] is True and out["global_batch"] == 64 and out["value"] > 0
+    out4 = json.loads(next(ln for ln in r.stdout.splitlines() if ln.startswith('{"config": 4')))
+    assert out4["sharding"] == ["table_wise"] and out4["cuda_graph"] is True and out4["global_batch"] == 64 and out4["value"] > 0

@@ -7,7 +7,8 @@ few steps each, and prints one JSON line per configuration (timing with CUDA eve
   4: batch 262144, bf16 towers 128->1024->512->256, fused row-wise Adam, in-batch softmax d=256
   5: retrieval: item-tower corpus of 10M items, top-100 for 131072 queries (1/8 of the 1M: one GPU's share)
 
-`config3_sharded` (configs[2] row-wise sharded over the ranks of a multi-GPU run) is called by `bench.py --gpus N`.
+`config3_sharded` / `config4_sharded` (configs[2] row-wise sharded, configs[3] under the planner's sharding, over the ranks of a
+multi-GPU run) are called by `bench.py --gpus N`.
 """
 import json
 import os
@@ -234,6 +235,60 @@ def config4(steps=3, warmup=1):
                            "frac": round(tower_flops / max(gemm_ms, 1e-9) / 1e9 / tf, 4), "flops": "3 GEMMs (y, dX, dW) x 3 layers x 2 towers"},
            "whole_step_tflops_credited": round((logit_flops + tower_flops) / (ms * 1e-3) / 1e12, 1), "peak_source": src}
     del task, ebc, opt, batches, gstep, raw
+    torch.cuda.empty_cache()
+    return out
+
+
+def config4_sharded(device, rank, world, steps=5, warmup=3, batch=262144, rows=(10_000_000, 10_000_000), D=128, layers=(1024, 512, 256),
+                    precision="bf16", peer_exchange=True):
+    """configs[3] AS STATED on `world` GPUs (called by every rank of a `bench.py --gpus N` run): GLOBAL batch 262144 (per-rank
+    262144 / world), bf16 towers 128 -> 1024 -> 512 -> 256, in-batch softmax over d = 256 (per-rank negatives), two 10M x 128
+    tables with fused row-wise ADAM, sharded as the planner decides (table-wise while the tables can occupy the ranks, row-wise
+    beyond: the same rule the weak-scaling block of bench.py runs under), id-column batches (one fixed-size exchange, no host
+    sync), peer-memory output exchange, the whole step as ONE CUDA graph.  Timed with CUDA events, max over ranks."""
+    import torch.distributed as dist
+    Br = batch // world
+    cat = ["user_id", "product_id"]
+    cfgs = [tt.EmbeddingBagConfig(name=f"t_{c}", embedding_dim=D, num_embeddings=rows[i], feature_names=[c]) for i, c in enumerate(cat)]
+    ebc = tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("meta"))
+    task = tt.TwoTowerTrainTask(tt.TwoTower(ebc, list(layers), device=device, precision=precision), loss="in_batch_softmax", precision=precision)
+    apply_optimizer_in_backward(tt.RowWiseAdam, task.two_tower.ebc.parameters(), {"lr": 0.01})
+    plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world)).collective_plan(task, tt.get_default_sharders(), dist.GroupMember.WORLD)
+    model = tt.DistributedModelParallel(module=task, device=device, plan=plan, sharding_kwargs={"peer_exchange": True} if peer_exchange else None)
+    opt = tt.KeyedOptimizerWrapper(dict(model.named_parameters()), lambda p: tt.FlatAdam(p, lr=1e-3))
+    model.train()
+    g = torch.Generator(device=device).manual_seed(400 + rank)
+    raw = [(torch.stack([torch.randint(1, r, (Br,), device=device, generator=g) for r in rows]), torch.zeros(Br, dtype=torch.int32, device=device))
+           for _ in range(2)]
+    gstep = tt.CudaGraphTrainStep(model, opt, cat, list(rows), Br, device, warmup_steps=2)
+    loss = None
+    for i in range(2 + 1 + max(warmup, 1)):            # eager warm-up steps, the capture, replays
+        loss = gstep(*raw[i % 2])[0]
+    dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        loss = gstep(*raw[i % 2])[0]
+    b.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / steps], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    _hbm, tf, src = _peaks()
+    d_out = layers[-1]
+    logit_flops = 6.0 * Br * Br * d_out                                                   # per rank, per-rank negatives
+    tower_flops = 3 * 2.0 * Br * sum(a_ * b_ for a_, b_ in zip((D,) + tuple(layers[:-1]), layers)) * 2
+    out = {"config": 4, "what": "configs[3] on %d GPUs: GLOBAL batch %d (per-rank %d), bf16 towers %d-%s, in-batch softmax d=%d (per-rank "
+                                "negatives), 2 x 10M x %d tables, fused row-wise Adam, planner-chosen sharding, peer-memory exchange, whole step "
+                                "as one CUDA graph" % (world, batch, Br, D, "-".join(str(x) for x in layers), d_out, D),
+           "value": round(batch / ms * 1e3, 1), "unit": "samples/s", "ms_per_step": round(ms, 4), "global_batch": batch, "per_rank_batch": Br,
+           "sharding": sorted({ps.sharding_type for tables in plan.plan.values() for ps in tables.values()}), "cuda_graph": gstep.captured,
+           "last_loss": float(loss), "per_rank_tflops_credited": round((logit_flops + tower_flops) / (ms * 1e-3) / 1e12, 1),
+           "frac_of_sustained_bf16_peak": round((logit_flops + tower_flops) / (ms * 1e-3) / 1e12 / tf, 4), "peak_source": src,
+           "flops_credited": "per rank: 6*Br*Br*d logits + 3 GEMMs x layers x 2 towers; communication and the embedding update are inside the time"}
+    del model, task, ebc, opt, gstep, raw
     torch.cuda.empty_cache()
     return out
 
