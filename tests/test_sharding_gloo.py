@@ -807,3 +807,119 @@ def test_sharded_checkpoint_with_optimizer_state_world2_gloo():
             p.terminate()
             msgs.append("worker hung")
     assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)
+
+
+# ------------------------------------------------------------------ random MIXED plans: all four sharding types in one collection
+def _worker_mixed_plans(rank, world, port, errq):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import random
+        import two_tower_recommender_model_b200 as tt
+        from helpers import random_kjt
+        from torch.distributed.optim import _apply_optimizer_in_backward as apply_optimizer_in_backward
+        from torch.distributed._shard.sharded_tensor import ShardedTensor
+        from two_tower_recommender_model_b200.distributed.planner import ParameterConstraints
+
+        for seed in range(int(os.environ.get("TT_MIXED_PLAN_SEEDS", "8"))):
+            rnd = random.Random(1000 + seed)                      # the same draw on every rank
+            n_tables = rnd.randint(2, 5)
+            kinds = [rnd.choice(["table_wise", "row_wise", "column_wise", "data_parallel"]) for _ in range(n_tables)]
+            specs, feat_rows = [], {}
+            for t, kind in enumerate(kinds):
+                dim = rnd.choice([4, 8, 12])
+                rows = rnd.randint(5, 60)
+                feats = [f"f{t}_{j}" for j in range(rnd.randint(1, 2))]
+                specs.append(TableSpec(f"t{t}", rows, dim, feats, rnd.choice(["sum", "mean"])))
+                for f in feats:
+                    feat_rows[f] = rows
+            keys = [f for s in specs for f in s.feature_names]
+            rnd.shuffle(keys)                                     # KJT key order unrelated to table order
+            Bm = rnd.randint(3, 7)
+            g = torch.Generator().manual_seed(seed)
+            full = {s.name: torch.randn(s.num_embeddings, s.embedding_dim, generator=g) for s in specs}
+            cfgs = [tt.EmbeddingBagConfig(name=s.name, embedding_dim=s.embedding_dim, num_embeddings=s.num_embeddings,
+                                          feature_names=list(s.feature_names),
+                                          pooling=tt.PoolingType.MEAN if s.pooling == "mean" else tt.PoolingType.SUM) for s in specs]
+            ebc = tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("meta"))
+            apply_optimizer_in_backward(tt.RowWiseAdagrad, ebc.parameters(), {"lr": LR})
+            holder = nn.ModuleDict({"ebc": ebc})
+            plan = tt.EmbeddingShardingPlanner(topology=tt.Topology(world_size=world, compute_device="cpu"),
+                                               constraints={s.name: ParameterConstraints(sharding_types=[k]) for s, k in zip(specs, kinds)}
+                                               ).collective_plan(holder, tt.get_default_sharders(), dist.GroupMember.WORLD)
+            assert [plan.plan["ebc"][s.name].sharding_type for s in specs] == kinds
+            model = tt.DistributedModelParallel(module=holder, device=torch.device("cpu"), plan=plan,
+                                                sharding_kwargs=dict(local_ebc_factory=OracleLocalEbc, bucketize_fn=oracle_bucketize))
+            sharded = model.module["ebc"]
+            sharded.load_state_dict({f"embedding_bags.{k}.weight": v for k, v in full.items()})
+            tag = f"seed {seed} kinds {kinds} keys {keys}"
+
+            def batch(r):
+                return random_kjt(keys, [feat_rows[k] for k in keys], Bm, 3, seed=7000 + 10 * seed + r)
+
+            values, lengths = batch(rank)
+            kt = sharded(tt.KeyedJaggedTensor.from_lengths_sync(keys, values, lengths))
+            want = oracle.ebc_forward(specs, [full[s.name] for s in specs], keys, values, lengths)
+            assert kt.keys() == [f for s in specs for f in s.feature_names], tag
+            torch.testing.assert_close(kt.values(), want, rtol=1e-5, atol=1e-6, msg=lambda m: f"{tag} forward: {m}")
+            gout = torch.randn(Bm, want.shape[1], generator=torch.Generator().manual_seed(8000 + 10 * seed + rank))
+            (kt.values() * gout).sum().backward()
+            model.sync_dense_grads()
+            # reference: row-wise Adagrad on the global batch's gradient / W; column-wise tables per column shard
+            dense = [torch.zeros_like(full[s.name]) for s in specs]
+            for r in range(world):
+                v_r, l_r = batch(r)
+                g_r = torch.randn(Bm, want.shape[1], generator=torch.Generator().manual_seed(8000 + 10 * seed + r))
+                for acc, gr in zip(dense, oracle.ebc_dense_grads(specs, keys, v_r, l_r, g_r)):
+                    acc += gr
+            ref = {k: v.clone() for k, v in full.items()}
+            for s, kind, gr in zip(specs, kinds, dense):
+                if kind == "column_wise":
+                    shards = len(plan.plan["ebc"][s.name].ranks)
+                    dw = s.embedding_dim // shards
+                    for j in range(shards):
+                        blk = ref[s.name][:, j * dw:(j + 1) * dw].clone()
+                        oracle.rowwise_adagrad_dense(blk, torch.zeros(s.num_embeddings), gr[:, j * dw:(j + 1) * dw] / world, lr=LR)
+                        ref[s.name][:, j * dw:(j + 1) * dw] = blk
+                else:
+                    oracle.rowwise_adagrad_dense(ref[s.name], torch.zeros(s.num_embeddings), gr / world, lr=LR)
+            sd = model.state_dict()
+            for s, kind in zip(specs, kinds):
+                t = sd[f"ebc.embedding_bags.{s.name}.weight"]
+                if kind == "data_parallel":
+                    assert not isinstance(t, ShardedTensor), tag
+                    got = t
+                else:
+                    assert isinstance(t, ShardedTensor) and tuple(t.size()) == (s.num_embeddings, s.embedding_dim), tag
+                    got = torch.zeros(t.size()) if rank == 0 else None
+                    t.gather(0, got)
+                if rank == 0 or kind == "data_parallel":
+                    torch.testing.assert_close(got, ref[s.name], rtol=1e-5, atol=1e-6, msg=lambda m: f"{tag} table {s.name} ({kind}): {m}")
+            dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put(f"rank {rank}:\n{traceback.format_exc()}")
+        raise
+
+
+def test_random_mixed_sharding_plans_world2_gloo():
+    """Eight random collections (2-5 tables, 1-2 features each, sum / mean pooling, shuffled KJT key order) whose tables draw their
+    sharding type from all four -- table-wise, row-wise, column-wise, data-parallel -- IN ONE collection: forward equals the
+    unsharded lookup of the rank's batch, and after one fused step every table equals row-wise Adagrad on the global batch's
+    gradient / W (per column shard for column-wise tables), gathered as utils/model_training.py:161-182 does."""
+    ctx = mp.get_context("spawn")
+    errq = ctx.SimpleQueue()
+    port = 29400 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker_mixed_plans, args=(r, 2, port, errq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+    msgs = []
+    while not errq.empty():
+        msgs.append(errq.get())
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+            msgs.append("worker hung")
+    assert not msgs and all(p.exitcode == 0 for p in procs), "\n".join(msgs)
