@@ -895,6 +895,16 @@ def _worker_mixed_plans(rank, world, port, errq):
                     t.gather(0, got)
                 if rank == 0 or kind == "data_parallel":
                     torch.testing.assert_close(got, ref[s.name], rtol=1e-5, atol=1e-6, msg=lambda m: f"{tag} table {s.name} ({kind}): {m}")
+            # the pipeline's prefetch hook (input dist issued one batch ahead) on the updated tables, under no_grad (an evaluation pass)
+            v2, l2 = random_kjt(keys, [feat_rows[k] for k in keys], Bm, 3, seed=9000 + 10 * seed + rank)
+            kjt2 = tt.KeyedJaggedTensor.from_lengths_sync(keys, v2, l2)
+            model.start_sparse_data_dist(tt.Batch(torch.zeros(1), kjt2, torch.zeros(Bm, dtype=torch.int32)), None)
+            with torch.no_grad():
+                kt2 = sharded(kjt2)
+            lst = [ref]
+            dist.broadcast_object_list(lst, src=0)            # rank 0's reference (identical on every rank by construction)
+            want2 = oracle.ebc_forward(specs, [lst[0][s.name] for s in specs], keys, v2, l2)
+            torch.testing.assert_close(kt2.values(), want2, rtol=1e-5, atol=1e-6, msg=lambda m: f"{tag} prefetched forward: {m}")
             dist.barrier()
         dist.destroy_process_group()
     except Exception:
