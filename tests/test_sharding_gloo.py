@@ -905,6 +905,18 @@ def _worker_mixed_plans(rank, world, port, errq):
             dist.broadcast_object_list(lst, src=0)            # rank 0's reference (identical on every rank by construction)
             want2 = oracle.ebc_forward(specs, [lst[0][s.name] for s in specs], keys, v2, l2)
             torch.testing.assert_close(kt2.values(), want2, rtol=1e-5, atol=1e-6, msg=lambda m: f"{tag} prefetched forward: {m}")
+            # resume: a second module built from the same plan loads the first one's OWN state dict (row shards, column shards,
+            # replicated tensors -- no gather) and gives the same lookup
+            ebc_b = tt.EmbeddingBagCollection(tables=cfgs, device=torch.device("meta"))
+            apply_optimizer_in_backward(tt.RowWiseAdagrad, ebc_b.parameters(), {"lr": LR})
+            model_b = tt.DistributedModelParallel(module=nn.ModuleDict({"ebc": ebc_b}), device=torch.device("cpu"), plan=plan,
+                                                  sharding_kwargs=dict(local_ebc_factory=OracleLocalEbc, bucketize_fn=oracle_bucketize))
+            own = {k: (v.clone() if not isinstance(v, ShardedTensor) else v) for k, v in sharded.state_dict().items()}
+            res = model_b.module["ebc"].load_state_dict(own)
+            assert not res.missing_keys, tag
+            with torch.no_grad():
+                kt3 = model_b.module["ebc"](tt.KeyedJaggedTensor.from_lengths_sync(keys, v2, l2))
+            torch.testing.assert_close(kt3.values(), kt2.values(), rtol=0, atol=0, msg=lambda m: f"{tag} reloaded module: {m}")
             dist.barrier()
         dist.destroy_process_group()
     except Exception:
