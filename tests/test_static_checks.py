@@ -373,3 +373,15 @@ def test_config3_and_config4_sharded_blocks_dry_run_on_cpu_world2_gloo():
     assert out["sharding"] == ["row_wise"] and out["cuda_graph"] is True and out["global_batch"] == 64 and out["value"] > 0
     out4 = json.loads(next(ln for ln in r.stdout.splitlines() if ln.startswith('{"config": 4')))
     assert out4["sharding"] == ["table_wise"] and out4["cuda_graph"] is True and out4["global_batch"] == 64 and out4["value"] > 0
+
+
+def test_two_gpu_training_worker_dry_run_on_cpu_world2_gloo():
+    """tests/dryrun_multi.py: the training worker of tests/test_gpu_multi.py on two gloo ranks with the oracle-backed lookup in
+    place of the kernels -- in the modes that have not run on GPUs yet (column_wise, data_parallel, data_parallel_dense) and two
+    that have; the worker's own assertions (losses of every step, gathered tables against the oracle) are the check."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dryrun_multi.py")], capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0 and "multi dry run ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+    for mode in ("table_wise", "row_wise", "column_wise", "data_parallel", "data_parallel_dense"):
+        assert f"mode {mode} ok" in r.stdout, mode
