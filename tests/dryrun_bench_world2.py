@@ -52,6 +52,8 @@ def worker(rank, world, port):
         bench.leave(world)
     if os.environ.get("DRYRUN_FAIL_ROW_WISE"):
         # what a failed row-wise parity check does to the run: the table-wise headline stands, row-wise blocks are skipped
+        # (the four eager parity modes and the configs[1] blocks are enough for that)
+        args.parity_graph, args.no_other_configs = False, True
         real = bench.parity_check
 
         def parity_check(world, rank, dev, sharding, exchange, **kw):

@@ -581,16 +581,22 @@ def sharded_state(name, ref):
     return _SHARDED_STATE.setdefault(name, torch.zeros(ref[name].shape[0]))
 
 
-@pytest.mark.parametrize("optimizer", ["adagrad", "adam", "sgd"])
-def test_data_parallel_tables_world2_gloo(optimizer):
+def _worker_data_parallel_all(rank, world, port, errq):
+    """One pair of processes takes the three optimizers in turn (a process start costs more than the test itself)."""
+    for i, optimizer in enumerate(("adagrad", "adam", "sgd")):
+        _SHARDED_STATE.clear()
+        _worker_data_parallel(rank, world, port + i, optimizer, errq)
+
+
+def test_data_parallel_tables_world2_gloo():
     """A data_parallel table (two features, mean pooling) next to a table-wise and a row-wise one: the replica is looked up on
     the rank's own batch, `sync_dense_grads` averages its dense gradient over the ranks and applies the tagged optimizer
     (row-wise Adagrad / row-wise Adam / SGD) identically on every rank -- equal to the unsharded update on the global batch's
     gradient / W over three steps; the state dict holds it as a plain tensor; its optimizer state reloads."""
     ctx = mp.get_context("spawn")
     errq = ctx.SimpleQueue()
-    port = 29700 + os.getpid() % 200 + {"adagrad": 0, "adam": 1, "sgd": 2}[optimizer]
-    procs = [ctx.Process(target=_worker_data_parallel, args=(r, 2, port, optimizer, errq)) for r in range(2)]
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker_data_parallel_all, args=(r, 2, port, errq)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
@@ -668,15 +674,19 @@ def _worker_sharded_retrieval(rank, world, port, sharding, errq):
         raise
 
 
-@pytest.mark.parametrize("sharding", ["table_wise", "row_wise"])
-def test_sharded_corpus_embedding_and_retrieval_world2_gloo(sharding):
+def _worker_sharded_retrieval_all(rank, world, port, errq):
+    for i, sharding in enumerate(("table_wise", "row_wise")):          # one pair of processes, both shardings in turn
+        _worker_sharded_retrieval(rank, world, port + i, sharding, errq)
+
+
+def test_sharded_corpus_embedding_and_retrieval_world2_gloo():
     """embed_corpus_sharded against table-wise / row-wise sharded tables (a corpus size the world size does not divide, chunk
     sizes that do not divide a rank's share), then both multi-rank retrieval layouts -- BruteForceIndex.from_sharded and
     CorpusShardedIndex -- against the oracle's towers and exact top-k."""
     ctx = mp.get_context("spawn")
     errq = ctx.SimpleQueue()
-    port = 30010 + os.getpid() % 50 + (0 if sharding == "table_wise" else 60)
-    procs = [ctx.Process(target=_worker_sharded_retrieval, args=(r, 2, port, sharding, errq)) for r in range(2)]
+    port = 30010 + os.getpid() % 50
+    procs = [ctx.Process(target=_worker_sharded_retrieval_all, args=(r, 2, port, errq)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
