@@ -838,7 +838,7 @@ def _worker_mixed_plans(rank, world, port, errq):
             specs, feat_rows = [], {}
             for t, kind in enumerate(kinds):
                 dim = rnd.choice([4, 8, 12])
-                rows = rnd.randint(5, 60)
+                rows = rnd.choice([1, 2, 3]) if rnd.random() < 0.25 else rnd.randint(5, 60)      # 1 row over 2 ranks: a zero-row shard
                 feats = [f"f{t}_{j}" for j in range(rnd.randint(1, 2))]
                 specs.append(TableSpec(f"t{t}", rows, dim, feats, rnd.choice(["sum", "mean"])))
                 for f in feats:
