@@ -293,6 +293,13 @@ def test_torchrec_docstring_examples(monkeypatch):
         assert kjt.offset_per_key() == [0, 3, 8] and kjt.length_per_key() == [3, 5] and kjt.stride() == 3
         assert kjt["Feature0"].values().tolist() == [0, 1, 2] and kjt["Feature1"].lengths().tolist() == [1, 1, 3]
         assert kjt.to_dict()["Feature1"].values().tolist() == [3, 4, 5, 6, 7]
+        # the same container permuted / split by key (KeyedJaggedTensor.permute / .split: whole keys move, bags keep their order)
+        p = kjt.permute([1, 0])
+        assert p.keys() == ["Feature1", "Feature0"] and p.values().tolist() == [3, 4, 5, 6, 7, 0, 1, 2]
+        assert p.lengths().tolist() == [1, 1, 3, 2, 0, 1] and p.offset_per_key() == [0, 5, 8]
+        a, b = kjt.split([1, 1])
+        assert a.keys() == ["Feature0"] and a.values().tolist() == [0, 1, 2] and a.lengths().tolist() == [2, 0, 1]
+        assert b.keys() == ["Feature1"] and b.values().tolist() == [3, 4, 5, 6, 7] and b.lengths().tolist() == [1, 1, 3]
     # the EmbeddingBagCollection example; the one device call is replaced by the oracle (tests only)
     import oracle
     from oracle.ebc import TableSpec
