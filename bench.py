@@ -18,6 +18,8 @@ backward, Adam on the towers.  Synthetic ids, random-init weights (no network fo
           on small tables against an unsharded replica on rank 0 (`parity`).  A failed table-wise check ends the
           run with rc 4 and no number; a failed row-wise check leaves the (table-wise) headline standing, and the
           blocks that use row-wise sharding are recorded as skipped instead of timed (`parity_failed`).
+          Last come configs[3] and configs[2] AS STATED, sharded over the N GPUs (`cfg4_sharded`, `cfg3_row_wise`;
+          tools/run_configs.py), each under its own time limit: an error or a cut there costs that block only.
 
 One "step" = forward + backward + both optimizers on one batch.
   value : samples/s with the batch already resident in HBM (max over ranks, CUDA events).
